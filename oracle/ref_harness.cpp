@@ -1,0 +1,300 @@
+// TEST INFRASTRUCTURE -- not part of the product path.
+//
+// C-ABI harness around the UNMODIFIED reference classes (AnacletoLAB/parSMURF, compiled from
+// /root/reference/src by oracle/Makefile into oracle/_ref/libparsmurf_ref.so).  It exists to
+//   (1) pin oracle/psm_oracle.cpp (our CPU restatement) against the real reference,
+//   (2) generate the golden fixtures under tests/golden/ (scripts/make_golden.py),
+//   (3) serve as bench.py's `--impl reference` / cpu_baseline arm ("kind": "reference").
+// Nothing here is reference source: it only *calls* the reference's public classes
+//   Folds / TestTrainDivider / Partition / SamplerKNN / rfRanger / Curves / hyperSMURF
+// in the order of src/hyperSMURF.cpp:257-346.
+//
+// rand() is interposed at link time (-Wl,--wrap=rand) so the SMOTE draws of
+// src/samplerKNN.cpp:95,99 can be exported for injection into the CUDA path.
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <memory>
+#include <sstream>
+#include <iostream>
+#include <omp.h>
+
+#include "HyperSMURFUtils.h"
+#include "folds.h"
+#include "testtraindivider.h"
+#include "partition.h"
+#include "samplerKNN.h"
+#include "curves.h"
+#include "rfRanger.h"
+#include "ForestProbability.h"
+#include "DataDouble.h"
+#include "hyperSMURF.h"
+#include "ANN.h"
+
+// ---------------------------------------------------------------- rand() recorder
+extern "C" int __real_rand(void);
+static thread_local std::vector<int32_t>* g_rand_sink = nullptr;
+extern "C" int __wrap_rand(void) {
+	int r = __real_rand();
+	if (g_rand_sink) g_rand_sink->push_back(r);
+	return r;
+}
+
+namespace {
+
+struct CoutSilencer {
+	std::streambuf* old;
+	std::ostringstream sink;
+	CoutSilencer() { old = std::cout.rdbuf(sink.rdbuf()); }
+	~CoutSilencer() { std::cout.rdbuf(old); }
+};
+
+struct RefCtx {
+	uint32_t n, m, nFolds;
+	std::vector<double> x;            // row-major [n][m+1], last col 1.0 pos / 2.0 neg
+	std::vector<uint32_t> y;          // 0/1
+	std::vector<uint32_t> ff;         // fold assignment
+	std::unique_ptr<Folds> folds;
+	std::unique_ptr<TestTrainDivider> ttd;
+};
+
+struct RefForest {
+	std::unique_ptr<rfRanger> rf;
+	uint32_t m, T, mtry, seed, rfThr;
+};
+
+std::vector<std::string> make_names(uint32_t m, const char* last) {
+	std::vector<std::string> nomi = generateOrderedNames(m + 1);
+	nomi[m] = last;
+	return nomi;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Build Folds (from a fold-assignment vector, src/folds.cpp:79-110) and TestTrainDivider
+// (src/testtraindivider.cpp:5-106).  glibc's rand() state is reset with srand(1) first so the
+// training-negative shuffle is the one a fresh `parSMURF1 --seed != 0` process performs.
+void* ref_ctx_create(const double* x, uint32_t n, uint32_t m, const uint32_t* labels,
+                     const uint32_t* foldAssign, uint32_t nFolds, int reset_rand) {
+	RefCtx* c = new RefCtx;
+	c->n = n; c->m = m; c->nFolds = nFolds;
+	c->x.assign(x, x + (size_t)n * (m + 1));
+	c->y.assign(labels, labels + n);
+	c->ff.assign(foldAssign, foldAssign + n);
+	if (reset_rand) srand(1);
+	c->folds.reset(new Folds(nFolds, n, c->y.data(), c->ff, false));
+	c->folds->computeFolds();
+	c->ttd.reset(new TestTrainDivider(c->folds.get(), MODE_CV));
+	return c;
+}
+
+void ref_ctx_destroy(void* h) { delete (RefCtx*)h; }
+
+// sizes[4] = trngPosNum, trngNegNum, testPosNum, testNegNum
+void ref_ctx_fold_sizes(void* h, uint32_t fold, uint32_t* sizes) {
+	RefCtx* c = (RefCtx*)h;
+	sizes[0] = c->ttd->trngPosNum[fold]; sizes[1] = c->ttd->trngNegNum[fold];
+	sizes[2] = c->ttd->testPosNum[fold]; sizes[3] = c->ttd->testNegNum[fold];
+}
+
+void ref_ctx_fold_indices(void* h, uint32_t fold, uint32_t* trngPos, uint32_t* trngNeg,
+                          uint32_t* testPos, uint32_t* testNeg) {
+	RefCtx* c = (RefCtx*)h;
+	std::memcpy(trngPos, c->ttd->trngPosIdx[fold], sizeof(uint32_t) * c->ttd->trngPosNum[fold]);
+	std::memcpy(trngNeg, c->ttd->trngNegIdx[fold], sizeof(uint32_t) * c->ttd->trngNegNum[fold]);
+	std::memcpy(testPos, c->ttd->testPosIdx[fold], sizeof(uint32_t) * c->ttd->testPosNum[fold]);
+	std::memcpy(testNeg, c->ttd->testNegIdx[fold], sizeof(uint32_t) * c->ttd->testNegNum[fold]);
+}
+
+uint32_t ref_partition_maxsize(void* h, uint32_t nParts, uint32_t fp, uint32_t ratio) {
+	RefCtx* c = (RefCtx*)h;
+	Partition part(c->folds.get(), c->ttd.get(), nParts, fp, ratio, c->m, c->n);
+	return part.maxSize;
+}
+
+// SamplerKNN::sample() for one (fold, partition).  Outputs the row-major training matrix, the
+// sizes {trngPos, trngNeg, lineLen} and the rand() outputs it consumed (for injection).
+// Returns the number of draws consumed, or -1 if a buffer is too small.
+int64_t ref_sample_partition(void* h, uint32_t fold, uint32_t part_id, uint32_t nParts, uint32_t fp,
+                             uint32_t ratio, uint32_t k, double* trngData, uint64_t trngCap,
+                             uint32_t* sizes, int32_t* draws, uint64_t drawsCap) {
+	RefCtx* c = (RefCtx*)h;
+	Partition part(c->folds.get(), c->ttd.get(), nParts, fp, ratio, c->m, c->n);
+	part.setFold(fold);
+	SamplerKNN samp(&part, MODE_CV, c->x.data(), c->m, c->n, k);
+	samp.setPartition(part_id);
+	std::vector<int32_t> rec;
+	g_rand_sink = &rec;
+	samp.sample();
+	g_rand_sink = nullptr;
+	sizes[0] = samp.trngPos; sizes[1] = samp.trngNeg; sizes[2] = samp.lineLen;
+	uint64_t need = (uint64_t)samp.lineLen * (c->m + 1);
+	if (need > trngCap || rec.size() > drawsCap) return -1;
+	std::memcpy(trngData, samp.trngData, need * sizeof(double));
+	if (draws) std::memcpy(draws, rec.data(), rec.size() * sizeof(int32_t));
+	return (int64_t)rec.size();
+}
+
+// Exact kNN as SamplerKNN::minOversample issues it (src/samplerKNN.cpp:60-93): ANNkd_tree over
+// `P` points of dimension `dim`, annkSearch(q, k, idx, dist, eps=0); or ANNbruteForce.
+int ref_knn(const double* pts, int P, int dim, int k, int32_t* nnIdx, double* nnDist, int brute) {
+	ANNpointArray dataPts = annAllocPts(P, dim);
+	for (int i = 0; i < P; i++) std::memcpy(dataPts[i], pts + (size_t)i * dim, sizeof(double) * dim);
+	std::vector<ANNidx> idx(k);
+	std::vector<ANNdist> dd(k);
+	if (brute) {
+		ANNbruteForce bf(dataPts, P, dim);
+		for (int i = 0; i < P; i++) {
+			bf.annkSearch(dataPts[i], k, idx.data(), dd.data(), 0);
+			for (int j = 0; j < k; j++) { nnIdx[(size_t)i * k + j] = idx[j]; nnDist[(size_t)i * k + j] = dd[j]; }
+		}
+	} else {
+		ANNkd_tree kd(dataPts, P, dim);
+		for (int i = 0; i < P; i++) {
+			kd.annkSearch(dataPts[i], k, idx.data(), dd.data(), 0);
+			for (int j = 0; j < k; j++) { nnIdx[(size_t)i * k + j] = idx[j]; nnDist[(size_t)i * k + j] = dd[j]; }
+		}
+	}
+	annDeallocPts(dataPts);
+	annClose();
+	return 0;
+}
+
+// rfRanger train ctor + train() on a column-major matrix [m+1][Ntr] (src/hyperSMURF.cpp:289-303).
+void* ref_forest_train(const double* colmajor, uint32_t Ntr, uint32_t m, uint32_t T, uint32_t mtry,
+                       uint32_t seed, uint32_t rfThr) {
+	CoutSilencer quiet;
+	std::vector<double> copy(colmajor, colmajor + (size_t)Ntr * (m + 1));
+	std::unique_ptr<Data> input(new DataDouble(copy, make_names(m, "Labels"), Ntr, m + 1));
+	RefForest* f = new RefForest;
+	f->m = m; f->T = T; f->mtry = mtry; f->seed = seed; f->rfThr = rfThr;
+	f->rf.reset(new rfRanger(m, false, std::move(input), T, mtry, rfThr, seed));
+	f->rf->train(false);
+	return f;
+}
+
+void ref_forest_destroy(void* h) { delete (RefForest*)h; }
+
+uint64_t ref_forest_tree_nodes(void* h, uint32_t t) {
+	RefForest* f = (RefForest*)h;
+	return f->rf->forest->getSplitVarIDs()[t].size();
+}
+
+// ranger's layouts (SURVEY §7 "Tree export layout"): left/right child ids (0 = none), split var,
+// split value, and per node {frac0, frac1} (NaN for internal nodes).
+void ref_forest_export_tree(void* h, uint32_t t, uint64_t* left, uint64_t* right, uint64_t* var,
+                            double* value, double* frac) {
+	RefForest* f = (RefForest*)h;
+	auto child = f->rf->forest->getChildNodeIDs()[t];
+	auto vars = f->rf->forest->getSplitVarIDs()[t];
+	auto vals = f->rf->forest->getSplitValues()[t];
+	auto tcc = ((ForestProbability*)f->rf->forest)->getTerminalClassCounts()[t];
+	size_t N = vars.size();
+	for (size_t i = 0; i < N; i++) {
+		left[i] = child[0][i]; right[i] = child[1][i]; var[i] = vars[i]; value[i] = vals[i];
+		if (tcc[i].empty()) { frac[2 * i] = frac[2 * i + 1] = std::nan(""); }
+		else { frac[2 * i] = tcc[i][0]; frac[2 * i + 1] = tcc[i].size() > 1 ? tcc[i][1] : 0.0; }
+	}
+}
+
+// rfRanger predict ctor (deep copy of the trained forest) + predict() on a column-major test
+// matrix [m+1][Nte] whose label column is 0 (src/hyperSMURF.cpp:316-333). preds = [Nte][2].
+int ref_forest_predict(void* h, const double* colmajor, uint32_t Nte, double* preds) {
+	RefForest* f = (RefForest*)h;
+	CoutSilencer quiet;
+	std::vector<double> copy(colmajor, colmajor + (size_t)Nte * (f->m + 1));
+	std::unique_ptr<Data> test(new DataDouble(copy, make_names(f->m, "dependent"), Nte, f->m + 1));
+	rfRanger rfTest(f->rf->forest, f->m, true, std::move(test), f->T, f->mtry, f->rfThr, 2 * f->seed);
+	rfTest.predict(false);
+	const auto& p = rfTest.forestPred->getPredictions();
+	for (uint32_t i = 0; i < Nte; i++) { preds[2 * i] = p[0][i][0]; preds[2 * i + 1] = p[0][i].size() > 1 ? p[0][i][1] : 0.0; }
+	return 0;
+}
+
+// Curves: AUROC first, then AUPRC (order matters, src/hyperSMURF.cpp:382-384). out = {auroc, auprc}.
+void ref_curves(const uint32_t* labels, const double* preds, uint64_t N, double* out) {
+	std::vector<uint32_t> l(labels, labels + N);
+	Curves c(l, preds);
+	out[0] = c.evalAUROC_ok();
+	out[1] = c.evalAUPRC();
+}
+
+// The reference's own CV driver: Folds (from file vector) -> hyperSMURF::initStandard -> smurfIt
+// (src/parSMURF.cpp:97-106).  class1/class2 must be zero-filled by the caller, length n.
+// Returns wall seconds of smurfIt() (the reference's Timer region).
+double ref_cv(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign,
+              uint32_t nFolds, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees,
+              uint32_t mtry, uint32_t seed, uint32_t nThr, uint32_t rfThr, int32_t minFold, int32_t maxFold,
+              int reset_rand, double* class1, double* class2) {
+	CoutSilencer quiet;
+	std::vector<double> xx(x, x + (size_t)n * (m + 1));
+	std::vector<uint32_t> yy(labels, labels + n);
+	std::vector<uint32_t> ff(foldAssign, foldAssign + n);
+	CommonParams cp;
+	cp.nn = n; cp.mm = m; cp.nFolds = nFolds; cp.seed = seed; cp.verboseLevel = VERBSILENT;
+	cp.nThr = nThr; cp.rfThr = rfThr; cp.wmode = MODE_CV; cp.woptimiz = OPT_NO; cp.rfVerbose = false;
+	cp.verboseMPI = false; cp.noMtSender = false; cp.customCV = false;
+	cp.minFold = (uint32_t)minFold; cp.maxFold = (uint32_t)maxFold;
+	std::vector<GridParams> gp(1);
+	gp[0].nParts = nParts; gp[0].fp = fp; gp[0].ratio = ratio; gp[0].k = k; gp[0].nTrees = nTrees; gp[0].mtry = mtry;
+	gp[0].auroc = gp[0].auprc = 0;
+	omp_set_num_threads(nThr);
+	if (reset_rand) srand(1);
+	Folds foldManager(nFolds, n, yy.data(), ff, false);
+	foldManager.computeFolds();
+	hyperSMURF smurfer(&cp, gp, &foldManager, xx, yy, class1, class2);
+	smurfer.initStandard();
+	Timer t; t.startTime();
+	smurfer.smurfIt();
+	t.endTime();
+	return t.duration();
+}
+
+// Bounded CPU-baseline sample: partitions [p0, p1) of one fold through the reference classes in the
+// order of src/hyperSMURF.cpp:261-346, `nThr` OpenMP threads over partitions (as the reference does).
+// Accumulates into class1/class2 (length n).  Returns wall seconds.
+double ref_run_partitions(void* h, uint32_t fold, uint32_t p0, uint32_t p1, uint32_t nParts, uint32_t fp,
+                          uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
+                          uint32_t nThr, uint32_t rfThr, double* class1, double* class2) {
+	RefCtx* c = (RefCtx*)h;
+	CoutSilencer quiet;
+	Partition part(c->folds.get(), c->ttd.get(), nParts, fp, ratio, c->m, c->n);
+	part.setFold(fold);
+	omp_lock_t lock; omp_init_lock(&lock);
+	omp_set_num_threads(nThr);
+	const uint32_t mm = c->m;
+	Timer t; t.startTime();
+	#pragma omp parallel for schedule(dynamic, 1)
+	for (int32_t cp = (int32_t)p0; cp < (int32_t)p1; cp++) {
+		uint32_t seedCustom = seed + cp + fold * nParts;
+		SamplerKNN samp(&part, MODE_CV, c->x.data(), mm, c->n, k);
+		samp.setPartition(cp);
+		samp.sample();
+		std::vector<double> trng((size_t)samp.lineLen * (mm + 1));
+		transposeMatrix(trng.data(), samp.trngData, samp.lineLen, mm + 1);
+		std::unique_ptr<Data> input(new DataDouble(trng, make_names(mm, "Labels"), samp.trngSize, mm + 1));
+		rfRanger rf(mm, false, std::move(input), nTrees, mtry, rfThr, seedCustom);
+		rf.train(false);
+		samp.copyTestSet(c->x.data());
+		std::vector<double> test((size_t)samp.testSize * (mm + 1));
+		transposeMatrix(test.data(), samp.testData, samp.testSize, mm + 1);
+		std::unique_ptr<Data> tdata(new DataDouble(test, make_names(mm, "dependent"), samp.testSize, mm + 1));
+		rfRanger rfTest(rf.forest, mm, true, std::move(tdata), nTrees, mtry, rfThr, 2 * seedCustom);
+		rfTest.predict(false);
+		const auto& predictions = rfTest.forestPred->getPredictions();
+		omp_set_lock(&lock);
+		samp.accumulateAndDivideResInProbVect(predictions, class1, class2, nParts);
+		omp_unset_lock(&lock);
+	}
+	t.endTime();
+	omp_destroy_lock(&lock);
+	return t.duration();
+}
+
+int ref_num_procs(void) { return omp_get_num_procs(); }
+
+}  // extern "C"
