@@ -1,0 +1,129 @@
+/* parsmurf_b200 -- C ABI of the B200-native hyperSMURF partition pipeline.
+ *
+ * The reference (AnacletoLAB/parSMURF) has no FFI layer: the boundary this library replaces is the set of
+ * C++ class interfaces that hyperSMURF::smurfIt calls per fold and per partition
+ * (src/hyperSMURF.cpp:255-396).  Each entry group below cites the reference interface it stands in for.
+ * The C++ host mirror of those classes (parsmurf_b200/host/) and the Python binding (parsmurf_b200/_capi.py)
+ * are both thin callers of exactly these symbols.
+ *
+ * Conventions: every call returns PSM_OK (0) or a negative PSM_E* code and never throws or aborts across
+ * the ABI; psm_last_error() gives the text.  Host buffers are borrowed for the duration of the call.
+ * All calls on one context are issued from one host thread; partition concurrency is expressed as batched
+ * launches, not host threads.  There is NO CPU fallback: without a CUDA device every compute entry fails
+ * with PSM_E_CUDA.
+ */
+#ifndef PARSMURF_B200_H
+#define PARSMURF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSM_OK 0
+#define PSM_E_CUDA (-1)        /* CUDA runtime error (no device, launch failure, out of memory) */
+#define PSM_E_ARG (-2)         /* invalid argument / call order */
+#define PSM_E_TOOFEW_POS (-3)  /* P < 2: the reference abort()s (src/samplerKNN.cpp:44-48) */
+#define PSM_E_LOCALK (-4)      /* min(k,P) < 2 with fp > 0: the reference divides by zero (src/samplerKNN.cpp:95) */
+#define PSM_E_NEIGHBOUR (-5)   /* a neighbour slot SMOTE needs is -1 (duplicates): the reference reads pos[-1] */
+#define PSM_E_CHUNK (-6)       /* last negative chunk underflows uint32 in the reference (src/sampler.cpp:68) */
+#define PSM_E_LIMIT (-7)       /* size outside this build's limits (Ntr >= 2^24, bootstrap count >= 2^15, k > 64) */
+#define PSM_E_OVERFLOW (-8)    /* internal capacity exceeded (node / item pools) */
+
+typedef struct psm_ctx psm_ctx;
+
+/* ---- (1) context --------------------------------------------------------------------------------------- */
+int psm_ctx_create(int device, psm_ctx** out);
+int psm_ctx_destroy(psm_ctx* ctx);
+const char* psm_last_error(psm_ctx* ctx);
+/* Launch everything on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream). */
+int psm_set_stream(psm_ctx* ctx, void* cuda_stream);
+/* Device-memory budget (bytes) for one partition batch of the training kernels; 0 = default (24 GiB). */
+int psm_set_batch_budget(psm_ctx* ctx, uint64_t bytes);
+int psm_sync(psm_ctx* ctx);
+
+/* ---- (2) dataset: `x` of hyperSMURF's ctor (src/hyperSMURF.h:26-28): row-major f64 [n][m+1], column m is
+ *      1.0 for positives / 2.0 for negatives (src/fileImport.cpp:88-91).  Uploaded once. ------------------- */
+int psm_dataset_upload(psm_ctx* ctx, const double* x_host, uint32_t n, uint32_t m);
+int psm_dataset_attach_device(psm_ctx* ctx, const double* x_dev, uint32_t n, uint32_t m);
+
+/* ---- (3) fold: the four index arrays Partition::setFold exposes (src/partition.cpp:25-37) ---------------- */
+int psm_fold_begin(psm_ctx* ctx, const uint32_t* trngPosIdx, uint32_t trngPosNum, const uint32_t* trngNegIdx,
+                   uint32_t trngNegNum, const uint32_t* testPosIdx, uint32_t testPosNum,
+                   const uint32_t* testNegIdx, uint32_t testNegNum);
+
+/* ---- (4) kNN: replaces ANNkd_tree + annkSearch in SamplerKNN::minOversample (src/samplerKNN.cpp:60-93).
+ *      Exact brute force over the fold's positives; zero distances excluded; ascending (distance, index);
+ *      missing slots = -1 / +inf.  localk = min(k, P).  Computed once per fold (fact: pos is the same for
+ *      every partition, src/sampler.cpp:69). ---------------------------------------------------------------- */
+int psm_fold_knn(psm_ctx* ctx, uint32_t k);
+int psm_fold_knn_get(psm_ctx* ctx, int32_t* nnIdx /*[P][localk]*/, double* nnDist /*[P][localk] or NULL*/);
+int psm_fold_knn_set(psm_ctx* ctx, const int32_t* nnIdx, uint32_t localk);   /* inject a neighbour table */
+
+/* ---- (5) partition batch: Sampler::setPartition + SamplerKNN::sample (src/sampler.cpp:62-71,
+ *      src/samplerKNN.cpp:8-141) + transposeMatrix (src/hyperSMURF.cpp:289-291) for partitions [p0,p1).
+ *      `draws` = the rand() outputs SMOTE consumes, in consumption order, partitions concatenated
+ *      (P*fp*(m+1) per partition; src/samplerKNN.cpp:95,99). ------------------------------------------------ */
+int psm_batch_begin(psm_ctx* ctx, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t p0, uint32_t p1);
+int psm_batch_assemble(psm_ctx* ctx, const int32_t* draws_host, uint64_t ndraws);
+/* sizes[3] = {trngPos, trngNeg, Ntr}; out = row-major [Ntr][m+1] like Sampler::trngData (may be NULL) */
+int psm_batch_get_training(psm_ctx* ctx, uint32_t p, uint32_t* sizes, double* out_rowmajor);
+
+/* ---- (6) forest training: rfRanger train ctor + train() (src/rfRanger.cpp:6-54,177-183) -> ranger
+ *      ForestProbability (min_node_size 10, sample_fraction 1 with replacement, no importance).
+ *      forest_seeds[p-p0] = seed + p + fold*nParts (src/hyperSMURF.cpp:273).  Optional injection of the
+ *      reference's draws: bootstrap[(p-p0)*T+t][Ntr] sample ids (stride = that partition's Ntr, partitions
+ *      concatenated) and cand[(p-p0)*T+t][cand_nodes][mtry] split-variable candidates per node id. ----------- */
+int psm_batch_train(psm_ctx* ctx, uint32_t nTrees, uint32_t mtry, const uint32_t* forest_seeds,
+                    const uint64_t* inj_bootstrap, const uint32_t* inj_cand, uint32_t inj_cand_nodes);
+int psm_batch_tree_nodes(psm_ctx* ctx, uint32_t p, uint32_t t, uint64_t* nNodes);
+/* ranger getter layouts (src/ranger/Forest/Forest.h:82-101, ForestProbability.h:40-44): child ids (0 = none),
+ * split var, split value, frac[2*node+c] (NaN for internal nodes; class 0 = positive). */
+int psm_batch_export_tree(psm_ctx* ctx, uint32_t p, uint32_t t, uint64_t* left, uint64_t* right, uint64_t* var,
+                          double* value, double* frac);
+/* bootstrap multiplicities of tree (p,t): counts[Ntr] (parity check of the device mt19937_64 replay) */
+int psm_batch_get_inbag(psm_ctx* ctx, uint32_t p, uint32_t t, uint32_t* counts);
+
+/* ---- (7) predict + accumulate: Sampler::copyTestSet + rfRanger predict ctor/predict() +
+ *      accumulateAndDivideResInProbVect (src/sampler.cpp:81-98,116-133; src/rfRanger.cpp:56-118,185-191).
+ *      Adds pred[i][c] * (1/nPartsTotal) of every partition of the batch, in ascending partition order,
+ *      into the fold score buffer (rows = test positives then test negatives). ----------------------------- */
+int psm_batch_predict_accumulate(psm_ctx* ctx, uint32_t nPartsTotal);
+
+/* ---- (8) fold scores / reduce / scatter ------------------------------------------------------------------- */
+int psm_fold_scores_get(psm_ctx* ctx, double* class1 /*[Nte]*/, double* class2 /*[Nte] or NULL*/);
+/* device pointers of the fold score buffer [2][Nte] so the caller can ncclReduce / all_reduce it in place
+ * (the MPI_Gather + master sum of src/hyperSMURF_MPI.cpp:594-618) */
+int psm_fold_scores_devptr(psm_ctx* ctx, double** class12_dev, uint32_t* Nte);
+/* class1Prob/class2Prob[testIdx[i]] += fold scores (scatter by original example id); host arrays length n */
+int psm_fold_scatter_host(psm_ctx* ctx, double* class1Prob, double* class2Prob);
+
+/* ---- (9) curves: Curves ctor + evalAUROC_ok + evalAUPRC (src/curves.cpp:7-36,77-122). out = {auroc, auprc}.
+ *      tie_mode 0: descending order from the identical host std::sort call (bit-parity with the reference's
+ *      tie order); tie_mode 1: stable device radix sort (ties in index order; may differ from the reference by
+ *      more than 1e-6 on heavily tied scores). --------------------------------------------- */
+int psm_curves(psm_ctx* ctx, const uint32_t* labels, const double* scores, uint64_t N, int tie_mode, double* out);
+
+/* ---- convenience: steps (5)-(7) for partitions [p0,p1) of the current fold, batched under the memory budget.
+ *      draws_host as in psm_batch_assemble for [p0,p1) (or NULL when fp == 0). ------------------------------ */
+int psm_fold_run_partitions(psm_ctx* ctx, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t nTrees, uint32_t mtry,
+                            uint32_t seed, uint32_t fold, uint32_t p0, uint32_t p1, const int32_t* draws_host);
+
+/* ---- instrumentation: accumulated device time (ms, CUDA events on the context stream) and launch counts per
+ *      kernel class since the last reset.  ids: 0 knn, 1 assemble, 2 feature_sort, 3 bootstrap, 4 build_lists,
+ *      5 split_search, 6 split_select, 7 level_finalize, 8 partition_lists, 9 predict, 10 curves, 11 gather. --- */
+#define PSM_NUM_KERNEL_CLASSES 12
+int psm_profile_enable(psm_ctx* ctx, int on);
+int psm_profile_reset(psm_ctx* ctx);
+int psm_profile_get(psm_ctx* ctx, double* ms /*[12]*/, uint64_t* launches /*[12]*/);
+/* algorithmic split-search bytes (sum over searched nodes of n_node*(mtry*8+8)) since last reset */
+int psm_stats_get(psm_ctx* ctx, uint64_t* split_bytes, uint64_t* nodes_total, uint64_t* levels_total);
+
+const char* psm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,691 @@
+// parsmurf_b200 -- C-ABI implementation (include/parsmurf_b200.h): context, device buffers, batch orchestration.
+// No CPU fallback: every compute entry needs a CUDA device and fails with PSM_E_CUDA otherwise.
+#include "../../include/parsmurf_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace psm;
+
+namespace {
+
+struct DevBuf {
+	void* p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) { cudaFree(p); p = nullptr; cap = 0; }
+		size_t want = bytes + bytes / 16 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template <typename T> T* as() const { return (T*)p; }
+};
+
+struct ProfPair { cudaEvent_t a, b; int cls; };
+
+}  // namespace
+
+struct psm_ctx {
+	int device = 0;
+	cudaStream_t stream = 0;
+	uint64_t budget = 24ull << 30;
+	std::string err;
+
+	// dataset
+	DevBuf xOwned;
+	const double* x = nullptr;
+	uint32_t n = 0, m = 0;
+
+	// fold
+	bool foldOpen = false;
+	uint32_t P = 0, Nneg = 0, nTP = 0, nTN = 0, Nte = 0, localk = 0;
+	bool haveKnn = false;
+	std::vector<uint32_t> hTestIdx;
+	DevBuf dPos, dNeg, dTest, dXp, dNN, dNNd, dKnnScratch, dClass12;
+
+	// batch
+	bool batchOpen = false, assembled = false, trained = false;
+	uint32_t nParts = 0, fp = 0, ratio = 0, p0 = 0, p1 = 0, nB = 0, maxNtr = 0;
+	std::vector<PartDesc> hParts;
+	uint64_t totalD = 0, totalS = 0, totalDraws = 0;
+	DevBuf dParts, dD, dS, dKeysA, dKeysB, dValsA, dValsB, dDraws, dErr;
+
+	// train
+	uint32_t T = 0, mtry = 0;
+	TrainArgs A;
+	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dFlags, dItems0, dItems1, dCand, dRes, dDec, dCounters, dStats, dSeeds,
+	    dInjBoot, dInjBootOff, dInjCand;
+	uint32_t* hCounters = nullptr;   // pinned
+	uint64_t statSplitBytes = 0, statNodes = 0, statLevels = 0;
+
+	// predict
+	DevBuf dPredScratch;
+
+	// curves
+	DevBuf cLabels, cPerm, cSorted, cTp, cPartials, cOut, cScores, cKeysA, cKeysB, cValsA, cValsB, cHist;
+
+	// profiling
+	bool profOn = false;
+	std::vector<ProfPair> profPending;
+	std::vector<cudaEvent_t> evPool;
+	double profMs[PSM_NUM_KERNEL_CLASSES] = {0};
+	uint64_t profLaunches[PSM_NUM_KERNEL_CLASSES] = {0};
+};
+
+namespace {
+
+int fail(psm_ctx* c, int code, const std::string& msg) {
+	if (c) c->err = msg;
+	return code;
+}
+int cuda_fail(psm_ctx* c, cudaError_t e, const char* where) {
+	return fail(c, PSM_E_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                        \
+	do {                                                                \
+		cudaError_t _e = (call);                                        \
+		if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call);        \
+	} while (0)
+#define ENSURE(buf, bytes) CU((buf).ensure(bytes))
+
+cudaEvent_t get_event(psm_ctx* c) {
+	if (!c->evPool.empty()) { cudaEvent_t e = c->evPool.back(); c->evPool.pop_back(); return e; }
+	cudaEvent_t e;
+	cudaEventCreate(&e);
+	return e;
+}
+
+struct ProfScope {
+	psm_ctx* c; int cls; cudaEvent_t a = nullptr;
+	ProfScope(psm_ctx* c_, int cls_, int launches) : c(c_), cls(cls_) {
+		c->profLaunches[cls] += launches;
+		if (c->profOn) { a = get_event(c); cudaEventRecord(a, c->stream); }
+	}
+	~ProfScope() {
+		if (a) { cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream); c->profPending.push_back({a, b, cls}); }
+	}
+};
+
+void prof_resolve(psm_ctx* c) {
+	if (c->profPending.empty()) return;
+	cudaStreamSynchronize(c->stream);
+	for (auto& p : c->profPending) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) c->profMs[p.cls] += ms;
+		c->evPool.push_back(p.a); c->evPool.push_back(p.b);
+	}
+	c->profPending.clear();
+}
+
+enum { K_KNN = 0, K_ASSEMBLE, K_SORT, K_BOOT, K_LISTS, K_SEARCH, K_SELECT, K_FINALIZE, K_PARTITION, K_PREDICT, K_CURVES, K_GATHER };
+
+int partition_sizes(uint32_t P, uint32_t Nneg, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t p, PartDesc* d) {
+	// Sampler::setPartition (src/sampler.cpp:62-71) + SamplerKNN::setup (src/samplerKNN.cpp:15-30)
+	uint32_t chunk = (uint32_t)std::ceil(Nneg / (double)nParts);
+	uint64_t before = (uint64_t)chunk * (nParts - 1);
+	if (p == nParts - 1 && before > Nneg) return PSM_E_CHUNK;
+	uint32_t negAvail = (p != nParts - 1) ? chunk : (uint32_t)(Nneg - before);
+	uint32_t nPosOut = (fp + 1) * P;
+	uint32_t nNegOut = nPosOut * ratio;
+	if (nNegOut == 0) nNegOut = negAvail;
+	if (nNegOut > negAvail) nNegOut = negAvail;
+	d->negOffset = p * chunk;
+	d->nPosOut = nPosOut;
+	d->nNegOut = nNegOut;
+	d->Ntr = nPosOut + nNegOut;
+	return PSM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* psm_version(void) { return "parsmurf_b200 0.1 (sm_100a)"; }
+
+int psm_ctx_create(int device, psm_ctx** out) {
+	if (!out) return PSM_E_ARG;
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || device < 0 || device >= count) return PSM_E_CUDA;
+	if (cudaSetDevice(device) != cudaSuccess) return PSM_E_CUDA;
+	psm_ctx* c = new psm_ctx;
+	c->device = device;
+	if (cudaMallocHost((void**)&c->hCounters, CNT_COUNT * sizeof(uint32_t)) != cudaSuccess) { delete c; return PSM_E_CUDA; }
+	memset(&c->A, 0, sizeof(c->A));
+	*out = c;
+	return PSM_OK;
+}
+
+int psm_ctx_destroy(psm_ctx* ctx) {
+	if (!ctx) return PSM_E_ARG;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	DevBuf* bufs[] = {&ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dClass12,
+	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr,
+	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dFlags, &ctx->dItems0, &ctx->dItems1,
+	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
+	                  &ctx->dInjCand, &ctx->dPredScratch, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
+	                  &ctx->cScores, &ctx->cKeysA, &ctx->cKeysB, &ctx->cValsA, &ctx->cValsB, &ctx->cHist};
+	for (DevBuf* b : bufs) b->release();
+	for (auto& p : ctx->profPending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+	for (auto e : ctx->evPool) cudaEventDestroy(e);
+	if (ctx->hCounters) cudaFreeHost(ctx->hCounters);
+	delete ctx;
+	return PSM_OK;
+}
+
+const char* psm_last_error(psm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int psm_set_stream(psm_ctx* ctx, void* s) {
+	if (!ctx) return PSM_E_ARG;
+	ctx->stream = (cudaStream_t)s;
+	return PSM_OK;
+}
+int psm_set_batch_budget(psm_ctx* ctx, uint64_t bytes) {
+	if (!ctx) return PSM_E_ARG;
+	ctx->budget = bytes ? bytes : (24ull << 30);
+	return PSM_OK;
+}
+int psm_sync(psm_ctx* ctx) {
+	if (!ctx) return PSM_E_ARG;
+	CU(cudaStreamSynchronize(ctx->stream));
+	return PSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ dataset
+int psm_dataset_upload(psm_ctx* ctx, const double* x_host, uint32_t n, uint32_t m) {
+	if (!ctx || !x_host || n == 0 || m == 0) return fail(ctx, PSM_E_ARG, "dataset_upload: bad arguments");
+	CU(cudaSetDevice(ctx->device));
+	size_t bytes = (size_t)n * (m + 1) * sizeof(double);
+	ENSURE(ctx->xOwned, bytes);
+	CU(cudaMemcpyAsync(ctx->xOwned.p, x_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));   // x_host is only borrowed for the call
+	ctx->x = ctx->xOwned.as<double>();
+	ctx->n = n; ctx->m = m;
+	ctx->foldOpen = ctx->batchOpen = false;
+	return PSM_OK;
+}
+
+int psm_dataset_attach_device(psm_ctx* ctx, const double* x_dev, uint32_t n, uint32_t m) {
+	if (!ctx || !x_dev || n == 0 || m == 0) return fail(ctx, PSM_E_ARG, "dataset_attach_device: bad arguments");
+	ctx->x = x_dev; ctx->n = n; ctx->m = m;
+	ctx->foldOpen = ctx->batchOpen = false;
+	return PSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ fold
+int psm_fold_begin(psm_ctx* ctx, const uint32_t* trngPosIdx, uint32_t P, const uint32_t* trngNegIdx, uint32_t Nneg,
+                   const uint32_t* testPosIdx, uint32_t nTP, const uint32_t* testNegIdx, uint32_t nTN) {
+	if (!ctx || !ctx->x) return fail(ctx, PSM_E_ARG, "fold_begin: no dataset");
+	if ((P && !trngPosIdx) || (Nneg && !trngNegIdx) || (nTP && !testPosIdx) || (nTN && !testNegIdx)) return fail(ctx, PSM_E_ARG, "fold_begin: null index array");
+	CU(cudaSetDevice(ctx->device));
+	for (uint32_t i = 0; i < P; i++) if (trngPosIdx[i] >= ctx->n) return fail(ctx, PSM_E_ARG, "fold_begin: index out of range");
+	ctx->P = P; ctx->Nneg = Nneg; ctx->nTP = nTP; ctx->nTN = nTN; ctx->Nte = nTP + nTN;
+	ctx->haveKnn = false; ctx->batchOpen = false; ctx->localk = 0;
+	ENSURE(ctx->dPos, std::max<size_t>(4, (size_t)P * 4));
+	ENSURE(ctx->dNeg, std::max<size_t>(4, (size_t)Nneg * 4));
+	ENSURE(ctx->dTest, std::max<size_t>(4, (size_t)ctx->Nte * 4));
+	ENSURE(ctx->dClass12, std::max<size_t>(16, (size_t)ctx->Nte * 16));
+	ctx->hTestIdx.resize(ctx->Nte);
+	if (nTP) memcpy(ctx->hTestIdx.data(), testPosIdx, (size_t)nTP * 4);       // positives first, then negatives (sampler.cpp:90-95)
+	if (nTN) memcpy(ctx->hTestIdx.data() + nTP, testNegIdx, (size_t)nTN * 4);
+	// synchronous copies: the host arrays are only borrowed for the duration of the call
+	if (P) CU(cudaMemcpyAsync(ctx->dPos.p, trngPosIdx, (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (Nneg) CU(cudaMemcpyAsync(ctx->dNeg.p, trngNegIdx, (size_t)Nneg * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (ctx->Nte) CU(cudaMemcpyAsync(ctx->dTest.p, ctx->hTestIdx.data(), (size_t)ctx->Nte * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemsetAsync(ctx->dClass12.p, 0, std::max<size_t>(16, (size_t)ctx->Nte * 16), ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->foldOpen = true;
+	return PSM_OK;
+}
+
+int psm_fold_knn(psm_ctx* ctx, uint32_t k) {
+	if (!ctx || !ctx->foldOpen) return fail(ctx, PSM_E_ARG, "fold_knn: no open fold");
+	if (ctx->P < 2) return fail(ctx, PSM_E_TOOFEW_POS, "fold_knn: fewer than two training positives");
+	CU(cudaSetDevice(ctx->device));
+	const uint32_t localk = std::min(k, ctx->P);                                // samplerKNN.cpp:52
+	if (localk == 0 || localk > 64) return fail(ctx, PSM_E_LIMIT, "fold_knn: k must be in 1..64");
+	const uint32_t P = ctx->P, m = ctx->m;
+	ENSURE(ctx->dXp, (size_t)P * m * 8);
+	ENSURE(ctx->dNN, (size_t)P * localk * 4);
+	ENSURE(ctx->dNNd, (size_t)P * localk * 8);
+	size_t scratchElems = std::min<size_t>((size_t)P * P, std::max<size_t>((size_t)P * 64, (size_t)1 << 27));
+	ENSURE(ctx->dKnnScratch, scratchElems * 8);
+	{
+		ProfScope ps(ctx, K_GATHER, 1);
+		launch_gather_rows(ctx->x, m + 1, m, ctx->dPos.as<uint32_t>(), P, ctx->dXp.as<double>(), ctx->stream);
+	}
+	{
+		size_t qb = std::min<size_t>(scratchElems / P, P);
+		ProfScope ps(ctx, K_KNN, (int)(2 * ((P + qb - 1) / qb)));
+		int rc = launch_knn(ctx->dXp.as<double>(), (int)P, (int)m, (int)localk, ctx->dKnnScratch.as<double>(), scratchElems,
+		                    ctx->dNN.as<int32_t>(), ctx->dNNd.as<double>(), ctx->stream);
+		if (rc) return fail(ctx, PSM_E_LIMIT, "fold_knn: launch failed");
+	}
+	CU(cudaGetLastError());
+	ctx->localk = localk; ctx->haveKnn = true;
+	return PSM_OK;
+}
+
+int psm_fold_knn_get(psm_ctx* ctx, int32_t* nnIdx, double* nnDist) {
+	if (!ctx || !ctx->haveKnn || !nnIdx) return fail(ctx, PSM_E_ARG, "fold_knn_get: no neighbour table");
+	size_t cnt = (size_t)ctx->P * ctx->localk;
+	CU(cudaMemcpyAsync(nnIdx, ctx->dNN.p, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (nnDist) {
+		if (!ctx->dNNd.p) return fail(ctx, PSM_E_ARG, "fold_knn_get: distances not available for an injected table");
+		CU(cudaMemcpyAsync(nnDist, ctx->dNNd.p, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CU(cudaStreamSynchronize(ctx->stream));
+	return PSM_OK;
+}
+
+int psm_fold_knn_set(psm_ctx* ctx, const int32_t* nnIdx, uint32_t localk) {
+	if (!ctx || !ctx->foldOpen || !nnIdx || localk == 0) return fail(ctx, PSM_E_ARG, "fold_knn_set: bad arguments");
+	size_t cnt = (size_t)ctx->P * localk;
+	ENSURE(ctx->dNN, cnt * 4);
+	CU(cudaMemcpyAsync(ctx->dNN.p, nnIdx, cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->localk = localk; ctx->haveKnn = true;
+	return PSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ batch
+int psm_batch_begin(psm_ctx* ctx, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t p0, uint32_t p1) {
+	if (!ctx || !ctx->foldOpen) return fail(ctx, PSM_E_ARG, "batch_begin: no open fold");
+	if (nParts == 0 || p0 >= p1 || p1 > nParts) return fail(ctx, PSM_E_ARG, "batch_begin: bad partition range");
+	if (ctx->P < 2) return fail(ctx, PSM_E_TOOFEW_POS, "batch_begin: fewer than two training positives");
+	CU(cudaSetDevice(ctx->device));
+	ctx->nParts = nParts; ctx->fp = fp; ctx->ratio = ratio; ctx->p0 = p0; ctx->p1 = p1; ctx->nB = p1 - p0;
+	ctx->hParts.resize(ctx->nB);
+	uint64_t dOff = 0, sOff = 0, drOff = 0;
+	ctx->maxNtr = 0;
+	for (uint32_t i = 0; i < ctx->nB; i++) {
+		PartDesc& d = ctx->hParts[i];
+		int rc = partition_sizes(ctx->P, ctx->Nneg, nParts, fp, ratio, p0 + i, &d);
+		if (rc) return fail(ctx, rc, "batch_begin: last negative chunk would underflow (trngNeg < ceil(trngNeg/nParts)*(nParts-1))");
+		if (d.Ntr >= kMaxRows) return fail(ctx, PSM_E_LIMIT, "batch_begin: training matrix has >= 2^24 rows");
+		if ((uint64_t)d.negOffset + d.nNegOut > ctx->Nneg) return fail(ctx, PSM_E_CHUNK, "batch_begin: negative chunk out of range");
+		d.dOffset = dOff; d.sOffset = sOff; d.drawOffset = drOff;
+		dOff += (uint64_t)d.Ntr * (ctx->m + 1);
+		sOff += (uint64_t)d.Ntr * ctx->m;
+		drOff += (uint64_t)ctx->P * fp * (ctx->m + 1);
+		ctx->maxNtr = std::max(ctx->maxNtr, d.Ntr);
+	}
+	ctx->totalD = dOff; ctx->totalS = sOff; ctx->totalDraws = drOff;
+	ENSURE(ctx->dParts, ctx->nB * sizeof(PartDesc));
+	CU(cudaMemcpyAsync(ctx->dParts.p, ctx->hParts.data(), ctx->nB * sizeof(PartDesc), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->batchOpen = true; ctx->assembled = false; ctx->trained = false;
+	return PSM_OK;
+}
+
+int psm_batch_assemble(psm_ctx* ctx, const int32_t* draws_host, uint64_t ndraws) {
+	if (!ctx || !ctx->batchOpen) return fail(ctx, PSM_E_ARG, "batch_assemble: no open batch");
+	if (ctx->fp > 0) {
+		if (!ctx->haveKnn) return fail(ctx, PSM_E_ARG, "batch_assemble: run psm_fold_knn first");
+		if (ctx->localk < 2) return fail(ctx, PSM_E_LOCALK, "batch_assemble: min(k,P) < 2");
+		if (!draws_host || ndraws < ctx->totalDraws) return fail(ctx, PSM_E_ARG, "batch_assemble: too few SMOTE draws");
+	}
+	CU(cudaSetDevice(ctx->device));
+	ENSURE(ctx->dD, std::max<uint64_t>(8, ctx->totalD * 8));
+	ENSURE(ctx->dErr, 16);
+	ENSURE(ctx->dDraws, std::max<uint64_t>(4, ctx->totalDraws * 4));
+	if (ctx->totalDraws) CU(cudaMemcpyAsync(ctx->dDraws.p, draws_host, ctx->totalDraws * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemsetAsync(ctx->dErr.p, 0, 16, ctx->stream));
+	{
+		ProfScope ps(ctx, K_ASSEMBLE, 1);
+		launch_assemble(ctx->x, ctx->m, ctx->dPos.as<uint32_t>(), ctx->P, ctx->dNeg.as<uint32_t>(), ctx->dNN.as<int32_t>(),
+		                std::max(ctx->localk, 2u), ctx->fp, ctx->dDraws.as<int32_t>(), ctx->dParts.as<PartDesc>(), ctx->nB, ctx->maxNtr,
+		                ctx->dD.as<double>(), ctx->dErr.as<int>(), ctx->stream);
+	}
+	CU(cudaGetLastError());
+	int herr = 0;
+	CU(cudaMemcpyAsync(&herr, ctx->dErr.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));   // also keeps `draws_host` borrowed only for the call
+	if (herr) return fail(ctx, PSM_E_NEIGHBOUR, "batch_assemble: SMOTE needs a neighbour that does not exist (duplicate positives)");
+	ctx->assembled = true; ctx->trained = false;
+	return PSM_OK;
+}
+
+int psm_batch_get_training(psm_ctx* ctx, uint32_t p, uint32_t* sizes, double* out) {
+	if (!ctx || !ctx->assembled || p < ctx->p0 || p >= ctx->p1) return fail(ctx, PSM_E_ARG, "batch_get_training: partition not assembled");
+	const PartDesc& d = ctx->hParts[p - ctx->p0];
+	if (sizes) { sizes[0] = d.nPosOut; sizes[1] = d.nNegOut; sizes[2] = d.Ntr; }
+	if (out) {
+		const uint32_t ld = ctx->m + 1;
+		std::vector<double> col((size_t)d.Ntr * ld);
+		CU(cudaMemcpyAsync(col.data(), ctx->dD.as<double>() + d.dOffset, col.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		for (uint32_t c = 0; c < ld; c++)
+			for (uint32_t r = 0; r < d.Ntr; r++) out[(size_t)r * ld + c] = col[(size_t)c * d.Ntr + r];
+	}
+	return PSM_OK;
+}
+
+int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* forest_seeds, const uint64_t* inj_bootstrap,
+                    const uint32_t* inj_cand, uint32_t inj_cand_nodes) {
+	if (!ctx || !ctx->assembled) return fail(ctx, PSM_E_ARG, "batch_train: batch not assembled");
+	if (T == 0 || mtry == 0 || mtry > ctx->m) return fail(ctx, PSM_E_ARG, "batch_train: need 1 <= mtry <= m and nTrees >= 1");
+	if (!forest_seeds && !(inj_bootstrap && inj_cand)) return fail(ctx, PSM_E_ARG, "batch_train: forest_seeds required unless all draws are injected");
+	if (tree_smem_bytes(ctx->m, mtry) > 200 * 1024) return fail(ctx, PSM_E_LIMIT, "batch_train: m too large for the candidate generator");
+	CU(cudaSetDevice(ctx->device));
+	const uint32_t m = ctx->m, nB = ctx->nB, stride = ctx->maxNtr;
+	const uint32_t nTrees = nB * T;
+	const uint32_t NC = 2 * stride + 2;
+	const uint64_t itemCap64 = (uint64_t)nTrees * (stride / 11 + 2);
+	if (itemCap64 >= (1ull << 31)) return fail(ctx, PSM_E_LIMIT, "batch_train: batch too large (reduce the batch budget)");
+	const uint32_t itemCap = (uint32_t)itemCap64;
+	ctx->T = T; ctx->mtry = mtry;
+
+	ENSURE(ctx->dS, ctx->totalS * 8);
+	ENSURE(ctx->dKeysA, ctx->totalS * 8); ENSURE(ctx->dKeysB, ctx->totalS * 8);
+	ENSURE(ctx->dValsA, ctx->totalS * 4); ENSURE(ctx->dValsB, ctx->totalS * 4);
+	const size_t listBytes = (size_t)nTrees * m * stride * 8;
+	ENSURE(ctx->dLists0, listBytes); ENSURE(ctx->dLists1, listBytes);
+	ENSURE(ctx->dInbag, (size_t)nTrees * stride * 4);
+	ENSURE(ctx->dMt, (size_t)nTrees * 312 * 8);
+	ENSURE(ctx->dTs, (size_t)nTrees * sizeof(TreeState));
+	ENSURE(ctx->dNodes, (size_t)nTrees * NC * sizeof(Node16));
+	ENSURE(ctx->dFlags, (size_t)nTrees * stride);
+	ENSURE(ctx->dItems0, (size_t)itemCap * sizeof(Item)); ENSURE(ctx->dItems1, (size_t)itemCap * sizeof(Item));
+	ENSURE(ctx->dCand, (size_t)itemCap * mtry * 4);
+	ENSURE(ctx->dRes, (size_t)itemCap * mtry * sizeof(SearchRes));
+	ENSURE(ctx->dDec, (size_t)itemCap * sizeof(SplitDec));
+	ENSURE(ctx->dCounters, CNT_COUNT * 4);
+	ENSURE(ctx->dStats, STAT_COUNT * 8);
+	ENSURE(ctx->dSeeds, (size_t)nB * 4);
+
+	TrainArgs& A = ctx->A;
+	A.nTrees = nTrees; A.T = T; A.m = m; A.mtry = mtry; A.stride = stride; A.NC = NC; A.itemCap = itemCap;
+	A.injCandNodes = inj_cand ? inj_cand_nodes : 0; A.listBuf = 0;
+	A.parts = ctx->dParts.as<PartDesc>(); A.Dall = ctx->dD.as<double>(); A.Sall = ctx->dS.as<entry_t>();
+	A.lists[0] = ctx->dLists0.as<entry_t>(); A.lists[1] = ctx->dLists1.as<entry_t>();
+	A.inbag = ctx->dInbag.as<uint32_t>(); A.mt = ctx->dMt.as<unsigned long long>(); A.ts = ctx->dTs.as<TreeState>();
+	A.nodes = ctx->dNodes.as<Node16>(); A.flags = ctx->dFlags.as<unsigned char>();
+	A.items[0] = ctx->dItems0.as<Item>(); A.items[1] = ctx->dItems1.as<Item>();
+	A.cand = ctx->dCand.as<uint32_t>(); A.res = ctx->dRes.as<SearchRes>(); A.dec = ctx->dDec.as<SplitDec>();
+	A.counters = ctx->dCounters.as<uint32_t>(); A.stats = ctx->dStats.as<unsigned long long>();
+	A.injCand = nullptr;
+
+	cudaStream_t s = ctx->stream;
+	CU(cudaMemsetAsync(A.inbag, 0, (size_t)nTrees * stride * 4, s));
+	CU(cudaMemsetAsync(A.ts, 0, (size_t)nTrees * sizeof(TreeState), s));
+	CU(cudaMemsetAsync(A.counters, 0, CNT_COUNT * 4, s));
+	CU(cudaMemsetAsync(A.stats, 0, STAT_COUNT * 8, s));
+	if (forest_seeds) CU(cudaMemcpyAsync(ctx->dSeeds.p, forest_seeds, (size_t)nB * 4, cudaMemcpyHostToDevice, s));
+	if (inj_cand) {
+		size_t bytes = (size_t)nTrees * inj_cand_nodes * mtry * 4;
+		ENSURE(ctx->dInjCand, bytes);
+		CU(cudaMemcpyAsync(ctx->dInjCand.p, inj_cand, bytes, cudaMemcpyHostToDevice, s));
+		A.injCand = ctx->dInjCand.as<uint32_t>();
+	}
+	{
+		ProfScope ps(ctx, K_SORT, 1);
+		launch_feature_sort(A.Dall, A.parts, nB, m, ctx->dKeysA.as<unsigned long long>(), ctx->dKeysB.as<unsigned long long>(),
+		                    ctx->dValsA.as<uint32_t>(), ctx->dValsB.as<uint32_t>(), ctx->dS.as<entry_t>(), s);
+	}
+	if (!(inj_bootstrap && inj_cand)) {
+		if (!forest_seeds) return fail(ctx, PSM_E_ARG, "batch_train: forest_seeds required");
+		ProfScope ps(ctx, K_BOOT, 1);
+		launch_bootstrap(A, ctx->dSeeds.as<uint32_t>(), s);   // also leaves each tree's mt19937_64 state after the bootstrap draws
+	}
+	if (inj_bootstrap) {
+		std::vector<uint64_t> off(nB);
+		uint64_t o = 0;
+		for (uint32_t i = 0; i < nB; i++) { off[i] = o; o += (uint64_t)T * ctx->hParts[i].Ntr; }
+		ENSURE(ctx->dInjBoot, o * 8); ENSURE(ctx->dInjBootOff, (size_t)nB * 8);
+		CU(cudaMemcpyAsync(ctx->dInjBoot.p, inj_bootstrap, o * 8, cudaMemcpyHostToDevice, s));
+		CU(cudaMemcpyAsync(ctx->dInjBootOff.p, off.data(), (size_t)nB * 8, cudaMemcpyHostToDevice, s));
+		CU(cudaMemsetAsync(A.inbag, 0, (size_t)nTrees * stride * 4, s));
+		ProfScope ps(ctx, K_BOOT, 1);
+		launch_inbag_from_ids(A, ctx->dInjBoot.as<unsigned long long>(), ctx->dInjBootOff.as<uint64_t>(), s);
+		CU(cudaStreamSynchronize(s));   // `off` is a local
+	}
+	{
+		ProfScope ps(ctx, K_LISTS, 1);
+		launch_build_lists(A, s);
+	}
+	{
+		ProfScope ps(ctx, K_FINALIZE, 1);
+		if (launch_init_trees(A, s)) return fail(ctx, PSM_E_CUDA, "batch_train: cannot configure shared memory");
+	}
+	CU(cudaGetLastError());
+
+	int buf = 0;
+	uint64_t levels = 0;
+	while (true) {
+		CU(cudaMemcpyAsync(ctx->hCounters, A.counters, CNT_COUNT * 4, cudaMemcpyDeviceToHost, s));
+		CU(cudaStreamSynchronize(s));
+		const uint32_t nItems = ctx->hCounters[CNT_NEXT_ITEMS];
+		const uint32_t e = ctx->hCounters[CNT_ERROR];
+		if (e & ERR_COUNT_LIMIT) return fail(ctx, PSM_E_LIMIT, "batch_train: a bootstrap multiplicity exceeds 32767");
+		if (e & ERR_POOL_OVERFLOW) return fail(ctx, PSM_E_OVERFLOW, "batch_train: node or work-item pool overflow");
+		if (e & ERR_INJ_CAND) return fail(ctx, PSM_E_ARG, "batch_train: injected candidate table has fewer nodes than a tree grew");
+		if (nItems == 0) break;
+		if (nItems > itemCap) return fail(ctx, PSM_E_OVERFLOW, "batch_train: work-item pool overflow");
+		CU(cudaMemsetAsync(A.counters + CNT_NEXT_ITEMS, 0, 4, s));
+		{ ProfScope ps(ctx, K_SEARCH, 1); launch_split_search(A, nItems, buf, s); }
+		{ ProfScope ps(ctx, K_SELECT, 1); launch_split_select(A, nItems, buf, s); }
+		{ ProfScope ps(ctx, K_FINALIZE, 1); launch_level_finalize(A, buf, s); }
+		{ ProfScope ps(ctx, K_PARTITION, 1); launch_partition_lists(A, nItems, buf, s); }
+		CU(cudaGetLastError());
+		buf ^= 1; A.listBuf ^= 1; levels++;
+	}
+	unsigned long long hs[STAT_COUNT];
+	CU(cudaMemcpyAsync(hs, A.stats, STAT_COUNT * 8, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	ctx->statSplitBytes += hs[STAT_SPLIT_BYTES];
+	ctx->statNodes += hs[STAT_NODES] + nTrees;
+	ctx->statLevels += levels;
+	ctx->trained = true;
+	return PSM_OK;
+}
+
+static int fetch_tree(psm_ctx* ctx, uint32_t p, uint32_t t, TreeState* ts, std::vector<Node16>* nodes) {
+	if (!ctx || !ctx->trained || p < ctx->p0 || p >= ctx->p1 || t >= ctx->T) return fail(ctx, PSM_E_ARG, "tree export: no such trained tree");
+	const size_t tree = (size_t)(p - ctx->p0) * ctx->T + t;
+	CU(cudaMemcpyAsync(ts, ctx->A.ts + tree, sizeof(TreeState), cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	if (nodes) {
+		nodes->resize(ts->nNodes);
+		CU(cudaMemcpyAsync(nodes->data(), ctx->A.nodes + tree * ctx->A.NC, (size_t)ts->nNodes * sizeof(Node16), cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+	}
+	return PSM_OK;
+}
+
+int psm_batch_tree_nodes(psm_ctx* ctx, uint32_t p, uint32_t t, uint64_t* nNodes) {
+	TreeState ts;
+	int rc = fetch_tree(ctx, p, t, &ts, nullptr);
+	if (rc) return rc;
+	*nNodes = ts.nNodes;
+	return PSM_OK;
+}
+
+int psm_batch_export_tree(psm_ctx* ctx, uint32_t p, uint32_t t, uint64_t* left, uint64_t* right, uint64_t* var, double* value, double* frac) {
+	TreeState ts;
+	std::vector<Node16> nodes;
+	int rc = fetch_tree(ctx, p, t, &ts, &nodes);
+	if (rc) return rc;
+	for (uint32_t i = 0; i < ts.nNodes; i++) {
+		const Node16& nd = nodes[i];
+		if (node_is_leaf(nd)) {
+			left[i] = right[i] = 0; var[i] = 0; value[i] = 0.0;
+			unsigned long long bits = nd.b & 0x7FFFFFFFFFFFFFFFull;
+			double f1; memcpy(&f1, &bits, 8);
+			frac[2 * i] = nd.a; frac[2 * i + 1] = f1;
+		} else {
+			left[i] = nd.b >> 32; right[i] = left[i] + 1; var[i] = nd.b & 0xFFFFFFFFull; value[i] = nd.a;
+			frac[2 * i] = frac[2 * i + 1] = std::nan("");
+		}
+	}
+	return PSM_OK;
+}
+
+int psm_batch_get_inbag(psm_ctx* ctx, uint32_t p, uint32_t t, uint32_t* counts) {
+	if (!ctx || !ctx->trained || p < ctx->p0 || p >= ctx->p1 || t >= ctx->T || !counts) return fail(ctx, PSM_E_ARG, "get_inbag: no such trained tree");
+	const size_t tree = (size_t)(p - ctx->p0) * ctx->T + t;
+	CU(cudaMemcpyAsync(counts, ctx->A.inbag + tree * ctx->A.stride, (size_t)ctx->hParts[p - ctx->p0].Ntr * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return PSM_OK;
+}
+
+int psm_batch_predict_accumulate(psm_ctx* ctx, uint32_t nPartsTotal) {
+	if (!ctx || !ctx->trained || nPartsTotal == 0) return fail(ctx, PSM_E_ARG, "predict_accumulate: batch not trained");
+	if (ctx->Nte == 0) return PSM_OK;
+	CU(cudaSetDevice(ctx->device));
+	ENSURE(ctx->dPredScratch, (size_t)ctx->nB * 2 * ctx->Nte * 8);
+	{
+		ProfScope ps(ctx, K_PREDICT, 2);
+		if (launch_predict(ctx->x, ctx->m, ctx->dTest.as<uint32_t>(), ctx->Nte, ctx->A.nodes, ctx->A.NC, ctx->nB, ctx->T,
+		                   ctx->dPredScratch.as<double>(), ctx->stream))
+			return fail(ctx, PSM_E_CUDA, "predict_accumulate: cannot configure shared memory");
+		launch_accumulate(ctx->dPredScratch.as<double>(), ctx->Nte, ctx->nB, 1.0 / (double)nPartsTotal, ctx->dClass12.as<double>(), ctx->stream);
+	}
+	CU(cudaGetLastError());
+	return PSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ scores
+int psm_fold_scores_get(psm_ctx* ctx, double* class1, double* class2) {
+	if (!ctx || !ctx->foldOpen || !class1) return fail(ctx, PSM_E_ARG, "fold_scores_get: no open fold");
+	if (ctx->Nte == 0) return PSM_OK;
+	CU(cudaMemcpyAsync(class1, ctx->dClass12.p, (size_t)ctx->Nte * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	if (class2) CU(cudaMemcpyAsync(class2, ctx->dClass12.as<double>() + ctx->Nte, (size_t)ctx->Nte * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return PSM_OK;
+}
+
+int psm_fold_scores_devptr(psm_ctx* ctx, double** class12_dev, uint32_t* Nte) {
+	if (!ctx || !ctx->foldOpen || !class12_dev || !Nte) return fail(ctx, PSM_E_ARG, "fold_scores_devptr: no open fold");
+	*class12_dev = ctx->dClass12.as<double>();
+	*Nte = ctx->Nte;
+	return PSM_OK;
+}
+
+int psm_fold_scatter_host(psm_ctx* ctx, double* class1Prob, double* class2Prob) {
+	if (!ctx || !ctx->foldOpen || !class1Prob) return fail(ctx, PSM_E_ARG, "fold_scatter_host: no open fold");
+	std::vector<double> c((size_t)ctx->Nte * 2);
+	if (ctx->Nte == 0) return PSM_OK;
+	CU(cudaMemcpyAsync(c.data(), ctx->dClass12.p, c.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	for (uint32_t i = 0; i < ctx->Nte; i++) {
+		class1Prob[ctx->hTestIdx[i]] += c[i];
+		if (class2Prob) class2Prob[ctx->hTestIdx[i]] += c[(size_t)ctx->Nte + i];
+	}
+	return PSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ curves
+int psm_curves(psm_ctx* ctx, const uint32_t* labels, const double* scores, uint64_t N, int tie_mode, double* out) {
+	if (!ctx || !labels || !scores || !out || N == 0 || N >= (1ull << 32)) return fail(ctx, PSM_E_ARG, "curves: bad arguments");
+	CU(cudaSetDevice(ctx->device));
+	cudaStream_t s = ctx->stream;
+	uint32_t totP = 0, totN = 0;
+	for (uint64_t i = 0; i < N; i++) { totP += labels[i] == 1; totN += labels[i] == 0; }   // curves.cpp:16-17
+	ENSURE(ctx->cLabels, N * 4); ENSURE(ctx->cSorted, N + 64);
+	const uint64_t nBlocks = (N + 4095) / 4096;
+	ENSURE(ctx->cTp, (nBlocks + 1) * 4); ENSURE(ctx->cPartials, nBlocks * 16); ENSURE(ctx->cOut, 16);
+	CU(cudaMemcpyAsync(ctx->cLabels.p, labels, N * 4, cudaMemcpyHostToDevice, s));
+	const uint32_t* dPerm = nullptr;
+	std::vector<uint32_t> perm;
+	if (tie_mode == 0) {
+		// the identical call the reference makes (curves.cpp:31-33): same libstdc++ introsort => same tie order
+		std::vector<size_t> idx(N);
+		std::iota(idx.begin(), idx.end(), 0);
+		std::sort(idx.begin(), idx.end(), [&](size_t i, size_t j) { return scores[i] > scores[j]; });
+		perm.resize(N);
+		for (uint64_t i = 0; i < N; i++) perm[i] = (uint32_t)idx[i];
+		ENSURE(ctx->cPerm, N * 4);
+		CU(cudaMemcpyAsync(ctx->cPerm.p, perm.data(), N * 4, cudaMemcpyHostToDevice, s));
+		dPerm = ctx->cPerm.as<uint32_t>();
+	} else {
+		ENSURE(ctx->cScores, N * 8);
+		ENSURE(ctx->cKeysA, N * 8); ENSURE(ctx->cKeysB, N * 8); ENSURE(ctx->cValsA, N * 4); ENSURE(ctx->cValsB, N * 4);
+		const uint64_t rBlocks = (N + 4095) / 4096;
+		ENSURE(ctx->cHist, rBlocks * 256 * 4);
+		CU(cudaMemcpyAsync(ctx->cScores.p, scores, N * 8, cudaMemcpyHostToDevice, s));
+		ProfScope ps(ctx, K_CURVES, 1 + 3 * 8);
+		if (launch_sort_scores_desc(ctx->cScores.as<double>(), N, ctx->cKeysA.as<unsigned long long>(), ctx->cKeysB.as<unsigned long long>(),
+		                            ctx->cValsA.as<uint32_t>(), ctx->cValsB.as<uint32_t>(), ctx->cHist.as<uint32_t>(), s))
+			return fail(ctx, PSM_E_ARG, "curves: sort launch failed");
+		dPerm = ctx->cValsA.as<uint32_t>();
+	}
+	{
+		ProfScope ps(ctx, K_CURVES, 5);
+		launch_gather_labels(ctx->cLabels.as<uint32_t>(), dPerm, N, ctx->cSorted.as<unsigned char>(), s);
+		if (launch_curves(ctx->cSorted.as<unsigned char>(), N, totP, totN, ctx->cTp.as<uint32_t>(), ctx->cPartials.as<double>(), nBlocks * 2,
+		                  ctx->cOut.as<double>(), s))
+			return fail(ctx, PSM_E_ARG, "curves: launch failed");
+	}
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(out, ctx->cOut.p, 16, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	return PSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ convenience
+int psm_fold_run_partitions(psm_ctx* ctx, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t nTrees, uint32_t mtry, uint32_t seed,
+                            uint32_t fold, uint32_t p0, uint32_t p1, const int32_t* draws_host) {
+	if (!ctx || !ctx->foldOpen) return fail(ctx, PSM_E_ARG, "fold_run_partitions: no open fold");
+	if (nParts == 0 || p0 >= p1 || p1 > nParts || nTrees == 0) return fail(ctx, PSM_E_ARG, "fold_run_partitions: bad arguments");
+	// per-partition device bytes of one batch (upper bound with Ntr of partition p0)
+	PartDesc d0;
+	int rc = partition_sizes(ctx->P, ctx->Nneg, nParts, fp, ratio, p0, &d0);
+	if (rc) return fail(ctx, rc, "fold_run_partitions: invalid partition geometry");
+	const uint64_t Ntr = d0.Ntr, m = ctx->m, T = nTrees;
+	const uint64_t perPart = Ntr * (8 * (m + 1) + 8 * m + 24 * m + 16 * T * m + 4 * T + T + 32 * T + 8) + (uint64_t)ctx->Nte * 16 +
+	                         T * (Ntr / 11 + 2) * (2 * sizeof(Item) + mtry * 4 + mtry * sizeof(SearchRes) + sizeof(SplitDec)) + T * 312 * 8;
+	uint64_t nb = std::max<uint64_t>(1, ctx->budget / std::max<uint64_t>(perPart, 1));
+	const uint64_t perDraw = (uint64_t)ctx->P * fp * (ctx->m + 1);
+	for (uint32_t b0 = p0; b0 < p1;) {
+		uint32_t b1 = (uint32_t)std::min<uint64_t>(p1, (uint64_t)b0 + nb);
+		if ((rc = psm_batch_begin(ctx, nParts, fp, ratio, b0, b1))) return rc;
+		if ((rc = psm_batch_assemble(ctx, draws_host ? draws_host + (uint64_t)(b0 - p0) * perDraw : nullptr, (uint64_t)(b1 - b0) * perDraw))) return rc;
+		std::vector<uint32_t> seeds(b1 - b0);
+		for (uint32_t p = b0; p < b1; p++) seeds[p - b0] = seed + p + fold * nParts;     // hyperSMURF.cpp:273
+		if ((rc = psm_batch_train(ctx, nTrees, mtry, seeds.data(), nullptr, nullptr, 0))) return rc;
+		if ((rc = psm_batch_predict_accumulate(ctx, nParts))) return rc;
+		b0 = b1;
+	}
+	return PSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ instrumentation
+int psm_profile_enable(psm_ctx* ctx, int on) {
+	if (!ctx) return PSM_E_ARG;
+	prof_resolve(ctx);
+	ctx->profOn = on != 0;
+	return PSM_OK;
+}
+int psm_profile_reset(psm_ctx* ctx) {
+	if (!ctx) return PSM_E_ARG;
+	prof_resolve(ctx);
+	for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) { ctx->profMs[i] = 0; ctx->profLaunches[i] = 0; }
+	ctx->statSplitBytes = ctx->statNodes = ctx->statLevels = 0;
+	return PSM_OK;
+}
+int psm_profile_get(psm_ctx* ctx, double* ms, uint64_t* launches) {
+	if (!ctx) return PSM_E_ARG;
+	prof_resolve(ctx);
+	for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) { if (ms) ms[i] = ctx->profMs[i]; if (launches) launches[i] = ctx->profLaunches[i]; }
+	return PSM_OK;
+}
+int psm_stats_get(psm_ctx* ctx, uint64_t* split_bytes, uint64_t* nodes_total, uint64_t* levels_total) {
+	if (!ctx) return PSM_E_ARG;
+	if (split_bytes) *split_bytes = ctx->statSplitBytes;
+	if (nodes_total) *nodes_total = ctx->statNodes;
+	if (levels_total) *levels_total = ctx->statLevels;
+	return PSM_OK;
+}
+
+}  // extern "C"

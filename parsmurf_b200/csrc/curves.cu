@@ -1,0 +1,246 @@
+// K7 curves -- AUROC / AUPRC of (labels, scores) as the reference's Curves class computes them
+// (reference src/curves.cpp:7-36 ctor: descending sort; :103-122 evalAUROC_ok; :77-100 evalAUPRC;
+//  src/curves.h:73-128 cumulSum / traps_integrate).
+//
+// Faithfully kept quirks: no tie grouping; FP[last] is overwritten with totN (curves.cpp:87,112); the PR curve
+// gets a prepended (recall 0, precision 1) point (:92-93); ROC terms are formed in *float* and summed in double
+// (curves.h:119-128 with T=float), PR terms in double; NaN precisions skip their trapezoids.
+//
+// Pipeline: [device radix sort by descending score | host permutation] -> gather labels -> device-wide inclusive
+// scan (TP) -> per-element trapezoid terms -> deterministic two-level fp64 reduction.  HBM-bound byte work.
+#include "kernels.cuh"
+
+namespace psm {
+
+constexpr int CB = 256;          // threads
+constexpr int CI = 16;           // items per thread
+constexpr int CTILE = CB * CI;   // elements per block
+
+__global__ void gather_labels_kernel(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ perm, uint64_t N,
+                                     unsigned char* __restrict__ out) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < N) out[i] = (unsigned char)labels[perm[i]];
+}
+void launch_gather_labels(const uint32_t* labels, const uint32_t* perm, uint64_t N, unsigned char* out, cudaStream_t s) {
+	if (!N) return;
+	gather_labels_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(labels, perm, N, out);
+}
+
+__device__ __forceinline__ uint32_t block_reduce_u32(uint32_t v, uint32_t* sh) {
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+	__syncthreads();
+	uint32_t t = 0;
+	for (int w = 0; w < CB / 32; w++) t += sh[w];
+	__syncthreads();
+	return t;
+}
+
+__global__ void __launch_bounds__(CB) tp_blocksum_kernel(const unsigned char* __restrict__ l, uint64_t N, uint32_t* __restrict__ blockSums) {
+	__shared__ uint32_t sh[CB / 32];
+	uint64_t b0 = (uint64_t)blockIdx.x * CTILE;
+	uint32_t v = 0;
+	for (int k = 0; k < CI; k++) { uint64_t i = b0 + (uint64_t)k * CB + threadIdx.x; if (i < N) v += l[i]; }
+	uint32_t t = block_reduce_u32(v, sh);
+	if (threadIdx.x == 0) blockSums[blockIdx.x] = t;
+}
+
+// single block: exclusive scan of blockSums in place
+__global__ void __launch_bounds__(1024) scan_blocksums_kernel(uint32_t* __restrict__ a, uint32_t n) {
+	__shared__ uint32_t wsum[32];
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (uint32_t b = 0; b < n; b += 1024) {
+		uint32_t i = b + threadIdx.x;
+		uint32_t v = i < n ? a[i] : 0, inc = v;
+		for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+		if (lane == 31) wsum[w] = inc;
+		__syncthreads();
+		uint32_t off = carry;
+		for (int ww = 0; ww < w; ww++) off += wsum[ww];
+		if (i < n) a[i] = off + inc - v;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry = off + inc;
+		__syncthreads();
+	}
+}
+
+// TP[i] (inclusive) for a block's tile, element order i = b0 + t*CI + k (thread-contiguous so the scan is a
+// per-thread serial prefix + one block scan of thread totals)
+__global__ void __launch_bounds__(CB) curve_terms_kernel(const unsigned char* __restrict__ l, uint64_t N, uint32_t totP, uint32_t totN,
+                                                          const uint32_t* __restrict__ blockOffsets, double* __restrict__ partials) {
+	__shared__ uint32_t wsum[CB / 32];
+	__shared__ double dsum[2][CB / 32];
+	const uint64_t b0 = (uint64_t)blockIdx.x * CTILE;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	// this kernel counted block sums with a strided mapping; here use the contiguous mapping for the scan
+	uint32_t loc[CI + 1];
+	uint32_t run = 0;
+	const uint64_t t0 = b0 + (uint64_t)tid * CI;
+#pragma unroll
+	for (int k = 0; k < CI + 1; k++) {       // one element of look-ahead for the i+1 terms
+		uint64_t i = t0 + k;
+		uint32_t v = (i < N) ? l[i] : 0;
+		run += v;
+		loc[k] = run;
+	}
+	uint32_t mine = loc[CI - 1], inc = mine;
+	for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+	if (lane == 31) wsum[w] = inc;
+	__syncthreads();
+	uint32_t off = blockOffsets[blockIdx.x] + inc - mine;
+	for (int ww = 0; ww < w; ww++) off += wsum[ww];
+	const float fP = __uint2float_rn(totP), fN = __uint2float_rn(totN);
+	const double dP = (double)totP;
+	double roc = 0.0, pr = 0.0;
+#pragma unroll
+	for (int k = 0; k < CI; k++) {
+		const uint64_t i = t0 + k;
+		if (i >= N) break;
+		const uint32_t tp0 = off + loc[k];
+		uint32_t fp0 = (uint32_t)(i + 1) - tp0;
+		if (i == N - 1) fp0 = totN;
+		// PR segment ending at point i+1 (points: 0 = (0,1); j+1 = (rec_j, prec_j))
+		double precPrev, recPrev;
+		if (i == 0) { precPrev = 1.0; recPrev = 0.0; }
+		else {
+			const uint32_t tpm = tp0 - l[i];
+			const uint32_t fpm = (uint32_t)i - tpm;
+			precPrev = __ddiv_rn((double)tpm, (double)(tpm + fpm));
+			recPrev = __ddiv_rn((double)tpm, dP);
+		}
+		const double prec = __ddiv_rn((double)tp0, (double)(tp0 + fp0));
+		const double rec = __ddiv_rn((double)tp0, dP);
+		if (!(isnan(precPrev) || isnan(prec)))
+			pr += __dmul_rn(__dmul_rn(__dadd_rn(precPrev, prec), __dsub_rn(rec, recPrev)), 0.5);
+		// ROC segment from i to i+1
+		if (i + 1 < N) {
+			const uint32_t tp1 = off + loc[k + 1];
+			uint32_t fp1 = (uint32_t)(i + 2) - tp1;
+			if (i + 1 == N - 1) fp1 = totN;
+			const float x0 = __fdiv_rn(__uint2float_rn(fp0), fN), x1 = __fdiv_rn(__uint2float_rn(fp1), fN);
+			const float y0 = __fdiv_rn(__uint2float_rn(tp0), fP), y1 = __fdiv_rn(__uint2float_rn(tp1), fP);
+			if (!(isnan(y0) || isnan(y1)))
+				roc += __dmul_rn((double)__fmul_rn(__fadd_rn(y0, y1), __fsub_rn(x1, x0)), 0.5);
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) { roc += __shfl_xor_sync(0xffffffffu, roc, o); pr += __shfl_xor_sync(0xffffffffu, pr, o); }
+	if (lane == 0) { dsum[0][w] = roc; dsum[1][w] = pr; }
+	__syncthreads();
+	if (tid == 0) {
+		double a = 0, b = 0;
+		for (int ww = 0; ww < CB / 32; ww++) { a += dsum[0][ww]; b += dsum[1][ww]; }
+		partials[2 * (size_t)blockIdx.x] = a;
+		partials[2 * (size_t)blockIdx.x + 1] = b;
+	}
+}
+
+__global__ void __launch_bounds__(256) curve_final_kernel(const double* __restrict__ partials, uint32_t nBlocks, double* __restrict__ out2) {
+	__shared__ double sh[2][256];
+	double a = 0, b = 0;
+	// fixed assignment: thread t sums blocks t, t+256, ... in order -> deterministic
+	for (uint32_t i = threadIdx.x; i < nBlocks; i += 256) { a += partials[2 * (size_t)i]; b += partials[2 * (size_t)i + 1]; }
+	sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b;
+	__syncthreads();
+	for (int s = 128; s > 0; s >>= 1) {
+		if (threadIdx.x < s) { sh[0][threadIdx.x] += sh[0][threadIdx.x + s]; sh[1][threadIdx.x] += sh[1][threadIdx.x + s]; }
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) { out2[0] = sh[0][0]; out2[1] = sh[1][0]; }
+}
+
+// block sums must use the same element->block mapping as curve_terms_kernel (contiguous CTILE per block): they do.
+int launch_curves(const unsigned char* labelsSorted, uint64_t N, uint32_t totP, uint32_t totN, uint32_t* tpScratch, double* partials,
+                  size_t partialsCap, double* out2, cudaStream_t s) {
+	if (N == 0) return -1;
+	const uint32_t nBlocks = (uint32_t)((N + CTILE - 1) / CTILE);
+	if ((size_t)nBlocks * 2 > partialsCap) return -2;
+	tp_blocksum_kernel<<<nBlocks, CB, 0, s>>>(labelsSorted, N, tpScratch);
+	scan_blocksums_kernel<<<1, 1024, 0, s>>>(tpScratch, nBlocks);
+	curve_terms_kernel<<<nBlocks, CB, 0, s>>>(labelsSorted, N, totP, totN, tpScratch, partials);
+	curve_final_kernel<<<1, 256, 0, s>>>(partials, nBlocks, out2);
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-wide stable LSD radix sort of scores in DESCENDING order (tie_mode 1): key = ~f64_key(score),
+// payload = original index; 8 passes x 8 bits; per pass: per-block digit histogram -> scan -> stable scatter.
+// ------------------------------------------------------------------------------------------------
+constexpr int RB = 256;
+constexpr int RTILES = 16;                 // tiles of RB elements per block
+constexpr int RCHUNK = RB * RTILES;
+
+__global__ void sort_init_kernel(const double* __restrict__ scores, uint64_t N, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < N) { keys[i] = ~f64_key(scores[i]); vals[i] = (uint32_t)i; }
+}
+
+__global__ void __launch_bounds__(RB) radix_hist_kernel(const unsigned long long* __restrict__ keys, uint64_t N, int shift, uint32_t nBlocks,
+                                                         uint32_t* __restrict__ hist /*[256][nBlocks]*/) {
+	__shared__ uint32_t h[256];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	const uint64_t b0 = (uint64_t)blockIdx.x * RCHUNK;
+	for (int t = 0; t < RTILES; t++) {
+		uint64_t i = b0 + (uint64_t)t * RB + threadIdx.x;
+		if (i < N) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+	}
+	__syncthreads();
+	hist[(size_t)threadIdx.x * nBlocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RB) radix_scatter_kernel(const unsigned long long* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t N,
+                                                            int shift, uint32_t nBlocks, const uint32_t* __restrict__ hist,
+                                                            unsigned long long* __restrict__ kout, uint32_t* __restrict__ vout) {
+	__shared__ uint32_t base[257];
+	__shared__ uint32_t wc[8][257];
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const unsigned lt = lanemask_lt();
+	base[tid] = hist[(size_t)tid * nBlocks + blockIdx.x];
+	if (tid == 0) base[256] = 0;
+	for (int i = tid; i < 8 * 257; i += RB) (&wc[0][0])[i] = 0;
+	__syncthreads();
+	const uint64_t b0 = (uint64_t)blockIdx.x * RCHUNK;
+	for (int t = 0; t < RTILES; t++) {
+		const uint64_t i = b0 + (uint64_t)t * RB + tid;
+		const bool valid = i < N;
+		unsigned long long key = valid ? kin[i] : 0ull;
+		uint32_t val = valid ? vin[i] : 0u;
+		const uint32_t d = valid ? ((uint32_t)(key >> shift) & 255u) : 256u;
+		const unsigned peers = __match_any_sync(0xffffffffu, d);
+		const uint32_t rk = __popc(peers & lt), cw = __popc(peers);
+		const uint32_t stamp = (uint32_t)t + 1;
+		if (rk == 0) wc[w][d] = (stamp << 6) | cw;
+		__syncthreads();
+		if (valid) {
+			uint32_t off = base[d];
+			for (int ww = 0; ww < w; ww++) { uint32_t s = wc[ww][d]; if ((s >> 6) == stamp) off += s & 63u; }
+			kout[off + rk] = key;
+			vout[off + rk] = val;
+		}
+		__syncthreads();
+		if (rk == 0 && valid) atomicAdd(&base[d], cw);
+	}
+}
+
+// returns 0 with the sorted permutation in valsA (8 passes -> back in A)
+int launch_sort_scores_desc(const double* scores, uint64_t N, unsigned long long* keysA, unsigned long long* keysB, uint32_t* valsA,
+                            uint32_t* valsB, uint32_t* hist, cudaStream_t s) {
+	if (N == 0 || N >= (1ull << 32)) return -1;
+	const uint32_t nBlocks = (uint32_t)((N + RCHUNK - 1) / RCHUNK);
+	sort_init_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(scores, N, keysA, valsA);
+	unsigned long long *kin = keysA, *kout = keysB;
+	uint32_t *vin = valsA, *vout = valsB;
+	for (int pass = 0; pass < 8; pass++) {
+		radix_hist_kernel<<<nBlocks, RB, 0, s>>>(kin, N, pass * 8, nBlocks, hist);
+		scan_blocksums_kernel<<<1, 1024, 0, s>>>(hist, 256u * nBlocks);
+		radix_scatter_kernel<<<nBlocks, RB, 0, s>>>(kin, vin, N, pass * 8, nBlocks, hist, kout, vout);
+		unsigned long long* tk = kin; kin = kout; kout = tk;
+		uint32_t* tv = vin; vin = vout; vout = tv;
+	}
+	return 0;
+}
+
+}  // namespace psm

@@ -1,0 +1,71 @@
+// parsmurf_b200 -- kernel launcher declarations shared by the .cu translation units and api.cu
+#pragma once
+#include "common.cuh"
+
+namespace psm {
+
+enum { CNT_NEXT_ITEMS = 0, CNT_ERROR = 1, CNT_COUNT = 4 };
+enum { ERR_COUNT_LIMIT = 1, ERR_POOL_OVERFLOW = 2, ERR_INJ_CAND = 4 };
+enum { STAT_SPLIT_BYTES = 0, STAT_NODES = 1, STAT_COUNT = 4 };
+
+// everything the level kernels need, passed by value
+struct TrainArgs {
+	uint32_t nTrees;      // trees in this batch = partitions * T
+	uint32_t T;           // trees per partition
+	uint32_t m;
+	uint32_t mtry;
+	uint32_t stride;      // list / flag / inbag stride per tree = max Ntr of the batch
+	uint32_t NC;          // node capacity per tree
+	uint32_t itemCap;
+	uint32_t injCandNodes;
+	int listBuf;          // which of lists[0/1] holds the current level's segments
+	const PartDesc* parts;
+	const double* Dall;
+	const entry_t* Sall;
+	entry_t* lists[2];    // [tree][feature][stride]
+	uint32_t* inbag;      // [tree][stride]
+	unsigned long long* mt;   // [tree][312]
+	TreeState* ts;
+	Node16* nodes;        // [tree][NC]
+	unsigned char* flags; // [tree][stride]
+	Item* items[2];
+	uint32_t* cand;       // [itemCap][mtry]
+	SearchRes* res;       // [itemCap][mtry]
+	SplitDec* dec;        // [itemCap]
+	uint32_t* counters;   // [CNT_COUNT]
+	unsigned long long* stats;   // [STAT_COUNT]
+	const uint32_t* injCand;     // [tree][injCandNodes][mtry] or nullptr
+};
+
+// knn.cu
+void launch_gather_rows(const double* x, uint32_t ld, uint32_t m, const uint32_t* idx, uint32_t count, double* out, cudaStream_t s);
+int launch_knn(const double* Xp, int P, int m, int localk, double* Dscratch, size_t scratchElems, int32_t* nnIdx, double* nnDist, cudaStream_t s);
+// assemble.cu
+void launch_assemble(const double* x, uint32_t m, const uint32_t* posIdx, uint32_t P, const uint32_t* negIdx, const int32_t* nn,
+                     uint32_t localk, uint32_t fp, const int32_t* draws, const PartDesc* parts, uint32_t nPartsBatch,
+                     uint32_t maxNtr, double* Dall, int* err, cudaStream_t s);
+// sort.cu
+void launch_feature_sort(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, unsigned long long* keysA,
+                         unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, entry_t* Sall, cudaStream_t s);
+// train.cu
+size_t tree_smem_bytes(uint32_t m, uint32_t mtry);
+void launch_bootstrap(const TrainArgs& A, const uint32_t* forestSeeds, cudaStream_t s);
+void launch_inbag_from_ids(const TrainArgs& A, const unsigned long long* ids, const uint64_t* idOffsets, cudaStream_t s);
+void launch_build_lists(const TrainArgs& A, cudaStream_t s);
+int launch_init_trees(const TrainArgs& A, cudaStream_t s);
+void launch_split_search(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
+void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
+void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s);
+void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
+// predict.cu
+int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_t Nte, const Node16* nodes, uint32_t NC,
+                   uint32_t nPartsBatch, uint32_t T, double* scratch, cudaStream_t s);
+void launch_accumulate(const double* scratch, uint32_t Nte, uint32_t nPartsBatch, double divider, double* class12, cudaStream_t s);
+// curves.cu
+int launch_curves(const unsigned char* labelsSorted, uint64_t N, uint32_t totP, uint32_t totN, uint32_t* tpScratch,
+                  double* partials, size_t partialsCap, double* out2, cudaStream_t s);
+void launch_gather_labels(const uint32_t* labels, const uint32_t* perm, uint64_t N, unsigned char* out, cudaStream_t s);
+int launch_sort_scores_desc(const double* scores, uint64_t N, unsigned long long* keysA, unsigned long long* keysB, uint32_t* valsA,
+                            uint32_t* valsB, uint32_t* hist, cudaStream_t s);
+
+}  // namespace psm

@@ -1,0 +1,116 @@
+// K3 feature_rank -- per (partition, feature) ascending order of the training rows + dense ranks.
+//
+// Stands in for Data::sort (reference src/ranger/Utility/Data.cpp:187-215, reached from
+// ForestProbability::initInternal, src/ranger/Forest/ForestProbability.cpp:97-99): ranger stores, per
+// column, the sorted unique values and each row's index into them.  Here each column becomes a list of
+// (dense rank, row) in ascending value order -- the "sorted-index" form the level-wise split search streams.
+// Equal doubles get equal ranks (-0.0 == +0.0 as in std::unique's operator==).
+//
+// One CTA per (partition, feature) segment: LSD radix sort, 8 passes x 8 bits over the order-preserving
+// u64 image of the f64 values, payload = row id, ping-pong buffers in global memory (L2 resident: a segment
+// is Ntr*12 B), stable in-tile ranking with __match_any_sync.  Then a block scan turns "value changed" flags
+// into dense ranks.  Byte work only -- no tensor cores.
+#include "kernels.cuh"
+
+namespace psm {
+
+constexpr int ST = 256;   // threads per CTA = elements per tile
+
+__global__ void __launch_bounds__(ST) feature_sort_kernel(const double* __restrict__ Dall, const PartDesc* __restrict__ parts,
+                                                           uint32_t m, unsigned long long* __restrict__ keysA,
+                                                           unsigned long long* __restrict__ keysB, uint32_t* __restrict__ valsA,
+                                                           uint32_t* __restrict__ valsB, entry_t* __restrict__ Sall) {
+	__shared__ uint32_t base[257];
+	__shared__ uint32_t wc[8][257];
+	__shared__ uint32_t wsum[8];
+	__shared__ uint32_t carry_s;
+	const uint32_t seg = blockIdx.x;
+	const uint32_t pl = seg / m, f = seg % m;
+	const PartDesc pd = parts[pl];
+	const uint32_t N = pd.Ntr;
+	const size_t so = pd.sOffset + (size_t)f * N;
+	const double* src = Dall + pd.dOffset + (size_t)f * N;
+	unsigned long long* kin = keysA + so;
+	unsigned long long* kout = keysB + so;
+	uint32_t* vin = valsA + so;
+	uint32_t* vout = valsB + so;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const unsigned lt = lanemask_lt();
+
+	for (uint32_t i = tid; i < N; i += ST) { kin[i] = f64_key(src[i]); vin[i] = i; }
+	for (int i = tid; i < 8 * 257; i += ST) (&wc[0][0])[i] = 0;
+	__syncthreads();
+
+	const uint32_t ntiles = (N + ST - 1) / ST;
+	for (int pass = 0; pass < 8; pass++) {
+		const int shift = pass * 8;
+		for (int i = tid; i < 257; i += ST) base[i] = 0;
+		__syncthreads();
+		for (uint32_t i = tid; i < N; i += ST) atomicAdd(&base[(uint32_t)(kin[i] >> shift) & 255u], 1u);
+		__syncthreads();
+		// exclusive scan of the 256 digit counts (warp 0..7 each scan 32 bins, then add warp offsets)
+		{
+			uint32_t v = base[tid];
+			uint32_t inc = v;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+			if (lane == 31) wsum[w] = inc;
+			__syncthreads();
+			uint32_t off = 0;
+			for (int ww = 0; ww < w; ww++) off += wsum[ww];
+			base[tid] = off + inc - v;
+			__syncthreads();
+		}
+		for (uint32_t t = 0; t < ntiles; t++) {
+			const uint32_t i = t * ST + tid;
+			const bool valid = i < N;
+			unsigned long long key = valid ? kin[i] : 0ull;
+			uint32_t val = valid ? vin[i] : 0u;
+			const uint32_t d = valid ? ((uint32_t)(key >> shift) & 255u) : 256u;
+			const unsigned peers = __match_any_sync(0xffffffffu, d);
+			const uint32_t rk = __popc(peers & lt);
+			const uint32_t cw = __popc(peers);
+			const uint32_t stamp = (uint32_t)pass * ntiles + t + 1;   // unique per (pass, tile); fits: 8*ntiles < 2^20 for N < 2^25
+			if (rk == 0) wc[w][d] = (stamp << 6) | cw;                 // cw <= 32
+			__syncthreads();
+			if (valid) {
+				uint32_t off = base[d];
+				for (int ww = 0; ww < w; ww++) { uint32_t s = wc[ww][d]; if ((s >> 6) == stamp) off += s & 63u; }
+				kout[off + rk] = key;
+				vout[off + rk] = val;
+			}
+			__syncthreads();
+			if (rk == 0 && valid) atomicAdd(&base[d], cw);
+		}
+		__syncthreads();
+		unsigned long long* tk = kin; kin = kout; kout = tk;
+		uint32_t* tv = vin; vin = vout; vout = tv;
+	}
+	// 8 passes: result is back in keysA/valsA (== kin/vin).  Dense ranks by block scan of "value changed".
+	entry_t* S = Sall + so;
+	if (tid == 0) carry_s = 0;
+	__syncthreads();
+	for (uint32_t t = 0; t < ntiles; t++) {
+		const uint32_t i = t * ST + tid;
+		uint32_t flag = (i > 0 && i < N) ? (kin[i] != kin[i - 1]) : 0u;
+		uint32_t inc = flag;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+		if (lane == 31) wsum[w] = inc;
+		__syncthreads();
+		uint32_t off = carry_s;
+		for (int ww = 0; ww < w; ww++) off += wsum[ww];
+		const uint32_t rank = off + inc;
+		if (i < N) S[i] = e_make(vin[i], rank, 0, 0);
+		__syncthreads();
+		if (tid == ST - 1) carry_s = rank;
+		__syncthreads();
+	}
+}
+
+void launch_feature_sort(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, unsigned long long* keysA,
+                         unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, entry_t* Sall, cudaStream_t s) {
+	feature_sort_kernel<<<nPartsBatch * m, ST, 0, s>>>(Dall, parts, m, keysA, keysB, valsA, valsB, Sall);
+}
+
+}  // namespace psm

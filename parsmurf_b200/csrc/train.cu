@@ -1,0 +1,524 @@
+// K4/K5 forest training -- level-wise, node-parallel growth of every tree of a partition batch at once.
+//
+// Replaces ranger's per-tree recursive growth as rfRanger drives it (reference src/rfRanger.cpp:6-54,177-183):
+//   Tree::bootstrap                         src/ranger/Tree/Tree.cpp:413-446      -> bootstrap_kernel
+//   Tree::createPossibleSplitVarSubset      src/ranger/Tree/Tree.cpp:245-272      -> gen_candidates (rng.cuh)
+//   TreeProbability::splitNodeInternal      src/ranger/Tree/TreeProbability.cpp:81-121
+//   TreeProbability::findBestSplit{,ValueSmallQ,ValueLargeQ}   :141-358           -> split_search_kernel / split_select_kernel
+//   Tree::splitNode (child ids, partition)  src/ranger/Tree/Tree.cpp:274-346      -> level_finalize_kernel / partition_lists_kernel
+//   TreeProbability::addToTerminalNodes     src/ranger/Tree/TreeProbability.cpp:47-63
+//
+// Data layout (HBM, all per batch): for every tree and every feature a list of 8-byte entries
+// (label | multiplicity | dense rank | row), ascending by feature value, containing the tree's in-bag rows.
+// Every open node owns the same contiguous segment [start, start+cnt) in all m lists of its tree, so
+//   * split search for (node, candidate feature) is ONE coalesced stream over cnt entries -- no gathers;
+//     class counts are prefix-summed with warp shuffles, the Gini proxy sum_c L_c^2/n_L + sum_c R_c^2/n_R is
+//     evaluated in fp64 exactly as ranger rounds it, arg-max reduced with shuffles (first candidate in draw
+//     order, then lowest value, strict '>': TreeProbability.cpp:274,340);
+//   * after the split decision every list segment is stably partitioned into the two child segments
+//     (ping-pong buffers), which keeps all lists sorted without ever sorting again.
+// Node ids are assigned breadth-first in parent-id order exactly like Tree.cpp:294-302, which is what makes
+// the i-th mtry draw of the device stream belong to node i.
+#include "kernels.cuh"
+#include "rng.cuh"
+
+namespace psm {
+
+// ------------------------------------------------------------------------------------------ bootstrap
+// one warp per tree: replay mt19937_64((uint32)((t+1)*forestSeed)) and histogram Ntr accepted draws.
+__global__ void __launch_bounds__(32) bootstrap_kernel(TrainArgs A, const uint32_t* __restrict__ forestSeeds) {
+	__shared__ unsigned long long mt[MT_N];
+	const uint32_t tree = blockIdx.x;
+	const uint32_t pl = tree / A.T, t = tree % A.T;
+	const uint32_t N = A.parts[pl].Ntr;
+	const int lane = lane_id();
+	const uint32_t treeSeed = (uint32_t)((unsigned long long)(t + 1) * forestSeeds[pl]);   // Forest.cpp:438
+	mt_seed(mt, (unsigned long long)treeSeed);
+	uint32_t* cnt = A.inbag + (size_t)tree * A.stride;
+	uint32_t taken = 0, pos = MT_N;
+	while (taken < N) {
+		mt_twist(mt);
+		pos = 0;
+		for (int b = 0; b < MT_N && taken < N; b += 32) {
+			int i = b + lane;
+			unsigned long long v = 0;
+			bool ok = false;
+			if (i < MT_N) ok = lemire_accept(mt_temper(mt[i]), (unsigned long long)N, &v);
+			unsigned acc = __ballot_sync(0xffffffffu, ok);
+			uint32_t seq = taken + __popc(acc & lanemask_lt());
+			if (ok && seq < N) atomicAdd(&cnt[(uint32_t)v], 1u);
+			uint32_t nacc = __popc(acc);
+			if (taken + nacc >= N) {
+				// position just after the N-th accepted output
+				uint32_t need = N - taken;   // 1..nacc
+				unsigned m2 = acc;
+				for (uint32_t k = 1; k < need; k++) m2 &= m2 - 1;
+				pos = b + __ffs(m2);         // index of need-th set bit + 1
+				taken = N;
+			} else {
+				taken += nacc;
+				pos = (b + 32 < MT_N) ? b + 32 : MT_N;
+			}
+		}
+	}
+	unsigned long long* g = A.mt + (size_t)tree * MT_N;
+	for (int i = lane; i < MT_N; i += 32) g[i] = mt[i];
+	if (lane == 0) A.ts[tree].mtPos = pos;
+}
+
+// injected bootstrap: histogram of the reference's sampleIDs
+__global__ void inbag_from_ids_kernel(TrainArgs A, const unsigned long long* __restrict__ ids, const uint64_t* __restrict__ idOffsets) {
+	const uint32_t tree = blockIdx.y;
+	const uint32_t pl = tree / A.T, t = tree % A.T;
+	const uint32_t N = A.parts[pl].Ntr;
+	const unsigned long long* src = ids + idOffsets[pl] + (size_t)t * N;
+	uint32_t* cnt = A.inbag + (size_t)tree * A.stride;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) atomicAdd(&cnt[(uint32_t)src[i]], 1u);
+}
+
+// ------------------------------------------------------------------------------------------ per-tree lists
+// one warp per (tree, feature): filter the partition's sorted (rank,row) list by in-bag count.
+__global__ void __launch_bounds__(128) build_lists_kernel(TrainArgs A) {
+	const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (wid >= A.nTrees * A.m) return;
+	const uint32_t tree = wid / A.m, f = wid % A.m;
+	const uint32_t pl = tree / A.T;
+	const PartDesc pd = A.parts[pl];
+	const int lane = lane_id();
+	const entry_t* S = A.Sall + pd.sOffset + (size_t)f * pd.Ntr;
+	const uint32_t* cnt = A.inbag + (size_t)tree * A.stride;
+	entry_t* out = A.lists[0] + ((size_t)tree * A.m + f) * A.stride;
+	uint32_t off = 0;
+	bool bad = false;
+	for (uint32_t b = 0; b < pd.Ntr; b += 32) {
+		uint32_t i = b + lane;
+		entry_t e = (i < pd.Ntr) ? S[i] : 0;
+		uint32_t row = e_row(e);
+		uint32_t c = (i < pd.Ntr) ? cnt[row] : 0;
+		bool keep = c > 0;
+		if (c > kMaxCount) bad = true;
+		unsigned mk = __ballot_sync(0xffffffffu, keep);
+		if (keep) out[off + __popc(mk & lanemask_lt())] = e_make(row, e_rank(e), c, row >= pd.nPosOut ? 1u : 0u);
+		off += __popc(mk);
+	}
+	if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&A.counters[CNT_ERROR], ERR_COUNT_LIMIT);
+	if (f == 0 && lane == 0) A.ts[tree].nEntries = off;
+}
+
+// ------------------------------------------------------------------------------------------ candidates
+// Draw the mtry split-variable candidates of ONE node from the tree's stream (warp-cooperative).
+// out == nullptr: consume the draws without storing (trivially terminal node).  perm[] is iota(m) on entry and
+// exit in Fisher-Yates mode, all-zero in rejection mode.
+__device__ void gen_candidates(unsigned long long* mt, uint32_t& pos, uint32_t m, uint32_t mtry, uint32_t* perm, uint32_t* jbuf,
+                               uint32_t* out) {
+	const int lane = lane_id();
+	const bool fisher = !(mtry < (m + 1) / 10);   // utility.cpp:86
+	if (fisher) {
+		if (out == nullptr) {
+			uint32_t rem = mtry;
+			while (rem) {
+				if (pos == MT_N) { mt_twist(mt); pos = 0; }
+				uint32_t take = min(rem, (uint32_t)MT_N - pos);
+				pos += take; rem -= take;
+			}
+			return;
+		}
+		uint32_t q0 = 0;
+		while (q0 < mtry) {
+			if (pos == MT_N) { mt_twist(mt); pos = 0; }
+			uint32_t take = min(min(32u, mtry - q0), (uint32_t)MT_N - pos);
+			if ((uint32_t)lane < take) {
+				uint32_t q = q0 + lane;
+				double u = canonical01(mt_temper(mt[pos + lane]));
+				double jd = __dadd_rn((double)q, __dmul_rn(u, (double)(m - q)));     // utility.cpp:133
+				uint32_t j = (uint32_t)__double2ull_rz(jd);
+				jbuf[q] = j < m ? j : m - 1;
+			}
+			pos += take; q0 += take;
+		}
+		__syncwarp();
+		if (lane == 0)
+			for (uint32_t q = 0; q < mtry; q++) { uint32_t j = jbuf[q]; uint32_t a = perm[q]; perm[q] = perm[j]; perm[j] = a; }
+		__syncwarp();
+		for (uint32_t q = lane; q < mtry; q += 32) out[q] = perm[q];
+		__syncwarp();
+		if (lane == 0)
+			for (int q = (int)mtry - 1; q >= 0; q--) { uint32_t j = jbuf[q]; uint32_t a = perm[q]; perm[q] = perm[j]; perm[j] = a; }
+		__syncwarp();
+	} else {
+		uint32_t count = 0;
+		while (true) {
+			if (pos == MT_N) { mt_twist(mt); pos = 0; }
+			if (lane == 0) {
+				while (count < mtry && pos < (uint32_t)MT_N) {
+					unsigned long long v;
+					if (!lemire_accept(mt_temper(mt[pos++]), (unsigned long long)m, &v)) continue;
+					uint32_t draw = (uint32_t)v;      // range [0, m-1]; the skipped column m is never reached (utility.cpp:107-111)
+					if (perm[draw]) continue;         // already selected: draw again (utility.cpp:112)
+					perm[draw] = 1;
+					jbuf[count++] = draw;
+				}
+			}
+			count = __shfl_sync(0xffffffffu, count, 0);
+			pos = __shfl_sync(0xffffffffu, pos, 0);
+			if (count == mtry) break;
+		}
+		__syncwarp();
+		if (out) for (uint32_t q = lane; q < mtry; q += 32) out[q] = jbuf[q];
+		if (lane == 0) for (uint32_t q = 0; q < mtry; q++) perm[jbuf[q]] = 0;
+		__syncwarp();
+	}
+}
+
+__device__ __forceinline__ void write_leaf(Node16* nd, uint32_t npos, uint32_t nneg) {
+	double n = (double)(npos + nneg);                                     // TreeProbability.cpp:49-62
+	Node16 v;
+	v.a = __ddiv_rn((double)npos, n);
+	v.b = (unsigned long long)__double_as_longlong(__ddiv_rn((double)nneg, n)) | 0x8000000000000000ull;
+	*nd = v;
+}
+
+__device__ __forceinline__ bool node_live(uint32_t npos, uint32_t nneg) {
+	return (npos + nneg > 10u) && npos > 0 && nneg > 0;                    // TreeProbability.cpp:84-105
+}
+
+// shared-memory carve-up of the one-warp-per-tree kernels
+struct TreeSmem {
+	unsigned long long* mt;
+	uint32_t* perm;
+	uint32_t* jbuf;
+	uint32_t* child;   // 64 entries
+};
+__device__ __forceinline__ TreeSmem carve(unsigned char* raw, uint32_t m, uint32_t mtry) {
+	TreeSmem s;
+	s.mt = (unsigned long long*)raw;
+	s.perm = (uint32_t*)(raw + MT_N * 8);
+	s.jbuf = s.perm + m;
+	s.child = s.jbuf + mtry;
+	return s;
+}
+size_t tree_smem_bytes(uint32_t m, uint32_t mtry) { return MT_N * 8 + (size_t)(m + mtry + 64) * 4; }
+
+__device__ __forceinline__ void init_perm(uint32_t* perm, uint32_t m, uint32_t mtry) {
+	const bool fisher = !(mtry < (m + 1) / 10);
+	for (uint32_t i = lane_id(); i < m; i += 32) perm[i] = fisher ? i : 0u;
+	__syncwarp();
+}
+
+// root node of every tree: class totals, terminal test, first candidate draw, first work item
+__global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
+	extern __shared__ __align__(16) unsigned char raw[];
+	TreeSmem sm = carve(raw, A.m, A.mtry);
+	const uint32_t tree = blockIdx.x;
+	const uint32_t pl = tree / A.T;
+	const PartDesc pd = A.parts[pl];
+	const int lane = lane_id();
+	const uint32_t* cnt = A.inbag + (size_t)tree * A.stride;
+	uint32_t npos = 0, nneg = 0;
+	for (uint32_t r = lane; r < pd.Ntr; r += 32) { uint32_t c = cnt[r]; if (r < pd.nPosOut) npos += c; else nneg += c; }
+	for (int o = 16; o > 0; o >>= 1) { npos += __shfl_xor_sync(0xffffffffu, npos, o); nneg += __shfl_xor_sync(0xffffffffu, nneg, o); }
+	TreeState ts = A.ts[tree];
+	Node16* nodes = A.nodes + (size_t)tree * A.NC;
+	const bool live = node_live(npos, nneg);
+	uint32_t item = 0xFFFFFFFFu;
+	if (live) {
+		if (lane == 0) item = atomicAdd(&A.counters[CNT_NEXT_ITEMS], 1u);
+		item = __shfl_sync(0xffffffffu, item, 0);
+		if (lane == 0) {
+			Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = ts.nEntries; it.npos = npos; it.nneg = nneg;
+			A.items[0][item] = it;
+		}
+	} else if (lane == 0) {
+		write_leaf(&nodes[0], npos, nneg);
+	}
+	if (A.injCand) {
+		if (live) for (uint32_t q = lane; q < A.mtry; q += 32) A.cand[(size_t)item * A.mtry + q] = A.injCand[((size_t)tree * A.injCandNodes + 0) * A.mtry + q];
+	} else {
+		unsigned long long* g = A.mt + (size_t)tree * MT_N;
+		for (int i = lane; i < MT_N; i += 32) sm.mt[i] = g[i];
+		init_perm(sm.perm, A.m, A.mtry);
+		uint32_t pos = ts.mtPos;
+		gen_candidates(sm.mt, pos, A.m, A.mtry, sm.perm, sm.jbuf, live ? A.cand + (size_t)item * A.mtry : nullptr);
+		for (int i = lane; i < MT_N; i += 32) g[i] = sm.mt[i];
+		ts.mtPos = pos;
+	}
+	if (lane == 0) {
+		ts.nNodes = 1; ts.itemBase = live ? item : 0; ts.itemCount = live ? 1 : 0; ts.overflow = 0;
+		A.ts[tree] = ts;
+	}
+}
+
+// ------------------------------------------------------------------------------------------ split search
+// one warp per (open node, candidate feature): stream the node's segment of that feature's list.
+__global__ void __launch_bounds__(128) split_search_kernel(TrainArgs A, uint32_t nItems, int buf) {
+	const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (wid >= nItems * A.mtry) return;
+	const uint32_t item = wid / A.mtry, c = wid % A.mtry;
+	const Item it = A.items[buf][item];
+	const uint32_t f = A.cand[(size_t)item * A.mtry + c];
+	const int lane = lane_id();
+	const entry_t* list = A.lists[A.listBuf] + ((size_t)it.tree * A.m + f) * A.stride + it.start;
+	const uint32_t cnt = it.cnt;
+	const uint32_t n = it.npos + it.nneg;
+	uint32_t lp = 0, ln = 0;
+	double best = -1.0;
+	uint32_t bpos = 0xFFFFFFFFu, blp = 0, bln = 0;
+	entry_t e = (lane < cnt) ? ld_nc_u64(list + lane) : 0;
+	for (uint32_t b = 0; b < cnt; b += 32) {
+		const uint32_t i = b + lane;
+		entry_t nxt = (i + 32 < cnt) ? ld_nc_u64(list + i + 32) : 0;
+		const uint32_t w = (i < cnt) ? e_count(e) : 0u;
+		const uint32_t neg = e_neg(e);
+		// inclusive warp scan of (positives, negatives) packed as two 32-bit lanes of one u64
+		unsigned long long pk = neg ? (unsigned long long)w : ((unsigned long long)w << 32);
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			unsigned long long t = __shfl_up_sync(0xffffffffu, pk, o);
+			if (lane >= o) pk += t;
+		}
+		const uint32_t lpi = lp + (uint32_t)(pk >> 32), lni = ln + (uint32_t)pk;
+		const uint32_t rk = e_rank(e);
+		uint32_t rnext = __shfl_down_sync(0xffffffffu, rk, 1);
+		const uint32_t rfirst = e_rank(__shfl_sync(0xffffffffu, nxt, 0));
+		if (lane == 31) rnext = rfirst;
+		if (i + 1 < cnt && rk != rnext) {
+			const uint32_t nl = lpi + lni, nr = n - nl;
+			const unsigned long long rp = it.npos - lpi, rn = it.nneg - lni;
+			const double sl = (double)((unsigned long long)lpi * lpi + (unsigned long long)lni * lni);
+			const double sr = (double)(rp * rp + rn * rn);
+			const double score = __dadd_rn(__ddiv_rn(sr, (double)nr), __ddiv_rn(sl, (double)nl));   // TreeProbability.cpp:337
+			if (score > best) { best = score; bpos = i; blp = lpi; bln = lni; }
+		}
+		const unsigned long long tot = __shfl_sync(0xffffffffu, pk, 31);
+		lp += (uint32_t)(tot >> 32); ln += (uint32_t)tot;
+		e = nxt;
+	}
+	// arg-max over lanes: highest score, then lowest position (ascending value order, strict '>')
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		double os = __shfl_xor_sync(0xffffffffu, best, o);
+		uint32_t op = __shfl_xor_sync(0xffffffffu, bpos, o);
+		uint32_t olp = __shfl_xor_sync(0xffffffffu, blp, o);
+		uint32_t oln = __shfl_xor_sync(0xffffffffu, bln, o);
+		if (os > best || (os == best && op < bpos)) { best = os; bpos = op; blp = olp; bln = oln; }
+	}
+	if (lane == 0) {
+		SearchRes r; r.score = best; r.pos = bpos; r.lpos = blp; r.lneg = bln; r.pad = 0;
+		A.res[(size_t)item * A.mtry + c] = r;
+	}
+}
+
+// one warp per open node: pick the winning candidate, compute the threshold, mark rows going left
+__global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t nItems, int buf) {
+	const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (item >= nItems) return;
+	const Item it = A.items[buf][item];
+	const int lane = lane_id();
+	double best = -1.0;
+	uint32_t bc = 0xFFFFFFFFu;
+	for (uint32_t c = lane; c < A.mtry; c += 32) {
+		double s = A.res[(size_t)item * A.mtry + c].score;
+		if (s > best) { best = s; bc = c; }          // ascending c per lane: first maximum stays
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		double os = __shfl_xor_sync(0xffffffffu, best, o);
+		uint32_t oc = __shfl_xor_sync(0xffffffffu, bc, o);
+		if (os > best || (os == best && oc < bc)) { best = os; bc = oc; }
+	}
+	Node16* node = A.nodes + (size_t)it.tree * A.NC + it.node;
+	SplitDec d; d.split = 0; d.nleft = 0; d.lpos = 0; d.lneg = 0;
+	if (lane == 0) atomicAdd(&A.stats[STAT_SPLIT_BYTES], (unsigned long long)(it.npos + it.nneg) * ((unsigned long long)A.mtry * 8ull + 8ull));
+	if (!(best >= 0.0)) {                             // TreeProbability.cpp:184-186: no candidate had two distinct values
+		if (lane == 0) { write_leaf(node, it.npos, it.nneg); A.dec[item] = d; }
+		return;
+	}
+	const SearchRes r = A.res[(size_t)item * A.mtry + bc];
+	const uint32_t f = A.cand[(size_t)item * A.mtry + bc];
+	const entry_t* list = A.lists[A.listBuf] + ((size_t)it.tree * A.m + f) * A.stride + it.start;
+	const PartDesc pd = A.parts[it.tree / A.T];
+	if (lane == 0) {
+		const double* col = A.Dall + pd.dOffset + (size_t)f * pd.Ntr;
+		const double lo = col[e_row(list[r.pos])], hi = col[e_row(list[r.pos + 1])];
+		double thr = __dmul_rn(__dadd_rn(lo, hi), 0.5);     // TreeProbability.cpp:348
+		if (thr == hi) thr = lo;                            // :353-355
+		Node16 v; v.a = thr; v.b = (unsigned long long)f;   // left child id is filled in by level_finalize
+		*node = v;
+		d.split = 1; d.nleft = r.pos + 1; d.lpos = r.lpos; d.lneg = r.lneg;
+		A.dec[item] = d;
+	}
+	unsigned char* flags = A.flags + (size_t)it.tree * A.stride;
+	for (uint32_t i = lane; i < it.cnt; i += 32) flags[e_row(list[i])] = (i <= r.pos) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------ level finalize
+// one warp per tree: breadth-first child ids in parent-id order, child work items, leaf payloads of trivially
+// terminal children, and the mtry draw of every new node in node-id order.
+__global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf) {
+	extern __shared__ __align__(16) unsigned char raw[];
+	TreeSmem sm = carve(raw, A.m, A.mtry);
+	const uint32_t tree = blockIdx.x;
+	TreeState ts = A.ts[tree];
+	if (ts.itemCount == 0) return;
+	const int lane = lane_id();
+	const unsigned lt = lanemask_lt();
+	const Item* cur = A.items[buf] + ts.itemBase;
+	const SplitDec* dec = A.dec + ts.itemBase;
+	Item* nextItems = A.items[buf ^ 1];
+	Node16* nodes = A.nodes + (size_t)tree * A.NC;
+
+	// pass 1: count splits and live children
+	uint32_t nsplit = 0, nlive = 0;
+	for (uint32_t b = 0; b < ts.itemCount; b += 32) {
+		uint32_t i = b + lane;
+		uint32_t l = 0, s = 0;
+		if (i < ts.itemCount) {
+			SplitDec d = dec[i];
+			if (d.split) {
+				Item it = cur[i];
+				s = 1;
+				l = (node_live(d.lpos, d.lneg) ? 1u : 0u) + (node_live(it.npos - d.lpos, it.nneg - d.lneg) ? 1u : 0u);
+			}
+		}
+		for (int o = 16; o > 0; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); s += __shfl_xor_sync(0xffffffffu, s, o); }
+		nlive += l; nsplit += s;
+	}
+	if (nsplit == 0) {
+		if (lane == 0) { ts.itemCount = 0; A.ts[tree] = ts; }
+		return;
+	}
+	uint32_t nextBase = 0;
+	if (lane == 0) nextBase = atomicAdd(&A.counters[CNT_NEXT_ITEMS], nlive);
+	nextBase = __shfl_sync(0xffffffffu, nextBase, 0);
+	if (nextBase + nlive > A.itemCap || ts.nNodes + 2 * nsplit > A.NC) {
+		if (lane == 0) { atomicOr(&A.counters[CNT_ERROR], ERR_POOL_OVERFLOW); ts.itemCount = 0; ts.overflow = 1; A.ts[tree] = ts; }
+		return;
+	}
+	uint32_t pos = ts.mtPos;
+	unsigned long long* g = A.mt + (size_t)tree * MT_N;
+	if (!A.injCand) {
+		for (int i = lane; i < MT_N; i += 32) sm.mt[i] = g[i];
+		init_perm(sm.perm, A.m, A.mtry);
+	}
+	// pass 2
+	uint32_t childBase = ts.nNodes, liveOff = 0;
+	for (uint32_t b = 0; b < ts.itemCount; b += 32) {
+		uint32_t i = b + lane;
+		SplitDec d; d.split = 0; d.nleft = 0; d.lpos = 0; d.lneg = 0;
+		Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = 0; it.npos = 0; it.nneg = 0;
+		if (i < ts.itemCount) { d = dec[i]; it = cur[i]; }
+		const unsigned smask = __ballot_sync(0xffffffffu, d.split != 0);
+		const uint32_t sp = __popc(smask & lt);
+		const uint32_t leftId = childBase + 2 * sp;
+		const uint32_t rpos = it.npos - d.lpos, rneg = it.nneg - d.lneg;
+		const bool liveL = d.split && node_live(d.lpos, d.lneg);
+		const bool liveR = d.split && node_live(rpos, rneg);
+		uint32_t l = (liveL ? 1u : 0u) + (liveR ? 1u : 0u);
+		uint32_t inc = l;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+		const uint32_t myOff = nextBase + liveOff + inc - l;
+		if (d.split) {
+			nodes[it.node].b = (nodes[it.node].b & 0xFFFFFFFFull) | ((unsigned long long)leftId << 32);   // Tree.cpp:294-302
+			uint32_t o = myOff;
+			if (liveL) {
+				Item c; c.tree = tree; c.node = leftId; c.start = it.start; c.cnt = d.nleft; c.npos = d.lpos; c.nneg = d.lneg;
+				nextItems[o] = c; sm.child[2 * sp] = o; o++;
+			} else { write_leaf(&nodes[leftId], d.lpos, d.lneg); sm.child[2 * sp] = 0xFFFFFFFFu; }
+			if (liveR) {
+				Item c; c.tree = tree; c.node = leftId + 1; c.start = it.start + d.nleft; c.cnt = it.cnt - d.nleft; c.npos = rpos; c.nneg = rneg;
+				nextItems[o] = c; sm.child[2 * sp + 1] = o;
+			} else { write_leaf(&nodes[leftId + 1], rpos, rneg); sm.child[2 * sp + 1] = 0xFFFFFFFFu; }
+		}
+		__syncwarp();
+		const uint32_t nchild = 2 * __popc(smask);
+		for (uint32_t c = 0; c < nchild; c++) {
+			const uint32_t ci = sm.child[c];
+			if (A.injCand) {
+				if (ci != 0xFFFFFFFFu)
+					for (uint32_t q = lane; q < A.mtry; q += 32)
+						A.cand[(size_t)ci * A.mtry + q] = A.injCand[((size_t)tree * A.injCandNodes + (childBase + c)) * A.mtry + q];
+			} else {
+				gen_candidates(sm.mt, pos, A.m, A.mtry, sm.perm, sm.jbuf, ci != 0xFFFFFFFFu ? A.cand + (size_t)ci * A.mtry : nullptr);
+			}
+		}
+		__syncwarp();
+		childBase += nchild;
+		liveOff += __shfl_sync(0xffffffffu, inc, 31);
+	}
+	if (!A.injCand) for (int i = lane; i < MT_N; i += 32) g[i] = sm.mt[i];
+	if (lane == 0) {
+		if (A.injCand && childBase > A.injCandNodes) atomicOr(&A.counters[CNT_ERROR], ERR_INJ_CAND);
+		ts.nNodes = childBase; ts.itemBase = nextBase; ts.itemCount = nlive; ts.mtPos = pos;
+		A.ts[tree] = ts;
+		atomicAdd(&A.stats[STAT_NODES], (unsigned long long)(2 * nsplit));
+	}
+}
+
+// ------------------------------------------------------------------------------------------ partition
+// one warp per (split node, feature): stable two-way partition of the node's segment into the other buffer.
+__global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint32_t nItems, int buf) {
+	const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (wid >= nItems * A.m) return;
+	const uint32_t item = wid / A.m, f = wid % A.m;
+	const SplitDec d = A.dec[item];
+	if (!d.split) return;
+	const Item it = A.items[buf][item];
+	const int lane = lane_id();
+	const unsigned lt = lanemask_lt();
+	const size_t lo = ((size_t)it.tree * A.m + f) * A.stride + it.start;
+	const entry_t* src = A.lists[A.listBuf] + lo;
+	entry_t* dstL = A.lists[A.listBuf ^ 1] + lo;
+	entry_t* dstR = dstL + d.nleft;
+	const unsigned char* flags = A.flags + (size_t)it.tree * A.stride;
+	uint32_t offL = 0, offR = 0;
+	for (uint32_t b = 0; b < it.cnt; b += 32) {
+		const uint32_t i = b + lane;
+		const bool valid = i < it.cnt;
+		entry_t e = valid ? ld_nc_u64(src + i) : 0;
+		const bool gl = valid && flags[e_row(e)] != 0;
+		const unsigned mL = __ballot_sync(0xffffffffu, gl);
+		const unsigned mR = __ballot_sync(0xffffffffu, valid && !gl);
+		if (gl) dstL[offL + __popc(mL & lt)] = e;
+		else if (valid) dstR[offR + __popc(mR & lt)] = e;
+		offL += __popc(mL); offR += __popc(mR);
+	}
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+void launch_bootstrap(const TrainArgs& A, const uint32_t* forestSeeds, cudaStream_t s) {
+	bootstrap_kernel<<<A.nTrees, 32, 0, s>>>(A, forestSeeds);
+}
+void launch_inbag_from_ids(const TrainArgs& A, const unsigned long long* ids, const uint64_t* idOffsets, cudaStream_t s) {
+	dim3 grid((A.stride + 255) / 256, A.nTrees);
+	inbag_from_ids_kernel<<<grid, 256, 0, s>>>(A, ids, idOffsets);
+}
+void launch_build_lists(const TrainArgs& A, cudaStream_t s) {
+	size_t warps = (size_t)A.nTrees * A.m;
+	build_lists_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A);
+}
+int launch_init_trees(const TrainArgs& A, cudaStream_t s) {
+	size_t smem = tree_smem_bytes(A.m, A.mtry);
+	if (smem > 48 * 1024) {
+		if (cudaFuncSetAttribute(init_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+		if (cudaFuncSetAttribute(level_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+	}
+	init_trees_kernel<<<A.nTrees, 32, smem, s>>>(A);
+	return 0;
+}
+void launch_split_search(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
+	size_t warps = (size_t)nItems * A.mtry;
+	split_search_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
+}
+void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
+	split_select_kernel<<<(nItems + 3) / 4, 128, 0, s>>>(A, nItems, buf);
+}
+void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s) {
+	level_finalize_kernel<<<A.nTrees, 32, tree_smem_bytes(A.m, A.mtry), s>>>(A, buf);
+}
+void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
+	size_t warps = (size_t)nItems * A.m;
+	partition_lists_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
+}
+
+}  // namespace psm

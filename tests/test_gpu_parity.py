@@ -1,0 +1,206 @@
+"""GPU parity tests: every CUDA stage, called through the C ABI, against the CPU oracle on the same seeded inputs.
+Bars: neighbour tables equal; training matrices, bootstrap counts, trees and scores BIT-exact; AUROC/AUPRC within
+1e-12 (tie_mode 0; the trapezoid terms are the reference's, only the fp64 summation is parallel)."""
+import numpy as np
+import pytest
+
+from helpers import CASES, make_case, trees_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _fold_setup(ctx, oracle, case, fold=0):
+    x = oracle.make_x(case["X"], case["y"])
+    rnd = oracle.GlibcRand(1)
+    ttd = oracle.o_ttd(case["y"], case["f"], case["nF"], rnd)
+    fd = ttd[fold]
+    ctx.dataset_upload(x)
+    ctx.fold_begin(fd["trngPos"], fd["trngNeg"], fd["testPos"], fd["testNeg"])
+    return x, fd, rnd
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_knn_matches_oracle(ctx, oracle, name):
+    case = make_case(name)
+    x, fd, _ = _fold_setup(ctx, oracle, case)
+    ctx.fold_knn(case["k"])
+    idx, dist = ctx.fold_knn_get()
+    pts = x[fd["trngPos"]]                      # all m+1 columns, as the reference feeds ANN (label column adds 0)
+    oi, od = oracle.o_knn(pts, min(case["k"], len(pts)))
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist.view(np.uint64), od.view(np.uint64))
+
+
+def test_knn_duplicates_and_missing(ctx, oracle):
+    # duplicates are excluded like self matches; missing neighbours come back as -1 / inf
+    pts = np.array([[0, 0], [1, 0], [0, 2], [3, 0], [1, 0], [0, 0]], float)
+    x = np.concatenate([pts, np.ones((6, 1))], axis=1)
+    x = np.concatenate([x, np.array([[9.0, 9.0, 2.0]])])
+    ctx.dataset_upload(np.ascontiguousarray(x))
+    ctx.fold_begin(np.arange(6), np.array([6]), np.array([0]), np.array([6]))
+    ctx.fold_knn(6)
+    idx, dist = ctx.fold_knn_get()
+    oi, od = oracle.o_knn(x[:6], 6)
+    assert np.array_equal(idx, oi)
+    assert list(idx[0]) == [1, 4, 2, 3, -1, -1]
+    assert np.isinf(dist[0, 4]) and np.isinf(dist[0, 5])
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_assemble_bit_exact(ctx, oracle, name):
+    case = make_case(name)
+    x, fd, rnd = _fold_setup(ctx, oracle, case)
+    ctx.fold_knn(case["k"])
+    nn, _ = ctx.fold_knn_get()
+    P = len(fd["trngPos"])
+    per = P * case["fp"] * (case["m"] + 1)
+    draws = rnd.fill(per * case["nParts"])
+    ctx.batch_begin(case["nParts"], case["fp"], case["ratio"], 0, case["nParts"])
+    ctx.batch_assemble(draws)
+    for p in range(case["nParts"]):
+        rc, sz = oracle.o_partition_sizes(P, len(fd["trngNeg"]), case["nParts"], case["fp"], case["ratio"], p)
+        assert rc == 0
+        rc, want = oracle.o_assemble(x, fd["trngPos"], fd["trngNeg"][sz["negOffset"]:], sz["nNegOut"], nn, case["fp"], draws[p * per:(p + 1) * per])
+        assert rc == 0
+        got, gsz = ctx.batch_get_training(p)
+        assert gsz["Ntr"] == sz["Ntr"] and gsz["trngPos"] == sz["nPosOut"] and gsz["trngNeg"] == sz["nNegOut"]
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), "partition %d differs" % p
+
+
+def _train_case(ctx, oracle, case, fold=0, seed=7):
+    x, fd, rnd = _fold_setup(ctx, oracle, case, fold)
+    ctx.fold_knn(case["k"])
+    P = len(fd["trngPos"])
+    per = P * case["fp"] * (case["m"] + 1)
+    draws = rnd.fill(per * case["nParts"])
+    ctx.batch_begin(case["nParts"], case["fp"], case["ratio"], 0, case["nParts"])
+    ctx.batch_assemble(draws)
+    seeds = np.array([seed + p + fold * case["nParts"] for p in range(case["nParts"])], np.uint32)
+    ctx.batch_train(case["T"], case["mtry"], seeds)
+    return x, fd, seeds
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_bootstrap_replay_matches_std_mt19937_64(ctx, oracle, name):
+    case = make_case(name)
+    x, fd, seeds = _train_case(ctx, oracle, case)
+    for p in (0, case["nParts"] - 1):
+        tr, sz = ctx.batch_get_training(p)
+        for t in (0, case["T"] - 1):
+            tree_seed = (int(seeds[p]) * (t + 1)) & 0xFFFFFFFF
+            boot, _ = oracle.o_tree_draws(tree_seed, sz["Ntr"], case["m"], case["mtry"], 1)
+            want = np.bincount(boot.astype(np.int64), minlength=sz["Ntr"]).astype(np.uint32)
+            got = ctx.batch_get_inbag(p, t, sz["Ntr"])
+            assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_trees_bit_exact(ctx, oracle, name):
+    case = make_case(name)
+    x, fd, seeds = _train_case(ctx, oracle, case)
+    total_nodes = 0
+    for p in range(case["nParts"]):
+        tr, sz = ctx.batch_get_training(p)
+        of = oracle.o_forest_train(np.ascontiguousarray(tr.T), case["T"], case["mtry"], int(seeds[p]))
+        for t in range(case["T"]):
+            ok, why = trees_equal(ctx.batch_export_tree(p, t), of.tree(t))
+            assert ok, "partition %d tree %d: %s" % (p, t, why)
+            total_nodes += len(of.tree(t)["var"])
+    assert total_nodes > case["nParts"] * case["T"]
+
+
+def test_trees_with_injected_draws(ctx, oracle):
+    """reference-exported draws injected instead of the device replay: same trees"""
+    case = make_case("fy_26")
+    x, fd, seeds = _train_case(ctx, oracle, case)
+    cap = 4096
+    boots, cands = [], []
+    for p in range(case["nParts"]):
+        _, sz = ctx.batch_get_training(p)
+        for t in range(case["T"]):
+            tree_seed = (int(seeds[p]) * (t + 1)) & 0xFFFFFFFF
+            b, c = oracle.o_tree_draws(tree_seed, sz["Ntr"], case["m"], case["mtry"], cap)
+            boots.append(b); cands.append(c)
+    ref = [[ctx.batch_export_tree(p, t) for t in range(case["T"])] for p in range(case["nParts"])]
+    ctx.batch_train(case["T"], case["mtry"], None, inj_bootstrap=np.concatenate(boots), inj_cand=np.stack(cands))
+    for p in range(case["nParts"]):
+        for t in range(case["T"]):
+            ok, why = trees_equal(ctx.batch_export_tree(p, t), ref[p][t])
+            assert ok, why
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fold_scores_bit_exact_and_curves(ctx, oracle, name):
+    case = make_case(name)
+    x = oracle.make_x(case["X"], case["y"])
+    rc, o1, o2 = oracle.o_cv(x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
+    assert rc == 0
+    rnd = oracle.GlibcRand(1)
+    ttd = oracle.o_ttd(case["y"], case["f"], case["nF"], rnd)
+    ctx.dataset_upload(x)
+    c1 = np.zeros(case["n"]); c2 = np.zeros(case["n"])
+    for fold in range(case["nF"]):
+        fd = ttd[fold]
+        ctx.fold_begin(fd["trngPos"], fd["trngNeg"], fd["testPos"], fd["testNeg"])
+        ctx.fold_knn(case["k"])
+        per = len(fd["trngPos"]) * case["fp"] * (case["m"] + 1)
+        draws = rnd.fill(per * case["nParts"])
+        ctx.fold_run_partitions(case["nParts"], case["fp"], case["ratio"], case["T"], case["mtry"], 7, fold, 0, case["nParts"], draws)
+        ctx.fold_scatter_host(c1, c2)
+    assert np.array_equal(c1.view(np.uint64), o1.view(np.uint64))
+    assert np.array_equal(c2.view(np.uint64), o2.view(np.uint64))
+    want = oracle.o_curves(case["y"], o1)
+    got = ctx.curves(case["y"], c1, tie_mode=0)
+    assert abs(got[0] - want[0]) < 1e-12 and abs(got[1] - want[1]) < 1e-12
+    got1 = ctx.curves(case["y"], c1, tie_mode=1)
+    assert abs(got1[0] - want[0]) < 5e-3 and abs(got1[1] - want[1]) < 5e-3   # stable tie order may differ
+
+
+def test_small_batches_equal_one_batch(ctx, oracle):
+    """the memory-budget batching must not change results"""
+    case = make_case("fy_26")
+    x, fd, rnd = _fold_setup(ctx, oracle, case)
+    ctx.fold_knn(case["k"])
+    per = len(fd["trngPos"]) * case["fp"] * (case["m"] + 1)
+    draws = rnd.fill(per * case["nParts"])
+    ctx.fold_run_partitions(case["nParts"], case["fp"], case["ratio"], case["T"], case["mtry"], 7, 0, 0, case["nParts"], draws)
+    a1, a2 = ctx.fold_scores_get()
+    ctx.set_batch_budget(1)   # forces one partition per batch
+    ctx.fold_begin(fd["trngPos"], fd["trngNeg"], fd["testPos"], fd["testNeg"])
+    ctx.fold_knn(case["k"])
+    ctx.fold_run_partitions(case["nParts"], case["fp"], case["ratio"], case["T"], case["mtry"], 7, 0, 0, case["nParts"], draws)
+    b1, b2 = ctx.fold_scores_get()
+    ctx.set_batch_budget(0)
+    assert np.array_equal(a1, b1) and np.array_equal(a2, b2)
+
+
+def test_curves_heavy_ties_and_sizes(ctx, oracle):
+    rng = np.random.default_rng(5)
+    for N, levels in ((1000, None), (200000, 21), (1 << 20, None)):
+        s = rng.random(N)
+        if levels:
+            s = np.round(s * (levels - 1)) / (levels - 1)
+        y = (rng.random(N) < 0.02 + 0.3 * s).astype(np.uint32)
+        want = oracle.o_curves(y, s)
+        got = ctx.curves(y, s, tie_mode=0)
+        assert abs(got[0] - want[0]) < 1e-12 and abs(got[1] - want[1]) < 1e-12
+        if not levels:   # no ties: the device sort must give the same order
+            got1 = ctx.curves(y, s, tie_mode=1)
+            assert abs(got1[0] - want[0]) < 1e-12 and abs(got1[1] - want[1]) < 1e-12
+
+
+def test_error_codes(ctx, oracle):
+    import parsmurf_b200 as psm
+    case = make_case("fy_26")
+    x, fd, rnd = _fold_setup(ctx, oracle, case)
+    with pytest.raises(psm.PsmError) as e:
+        ctx.batch_begin(4, 2, 3, 3, 2)
+    assert e.value.code == -2
+    ctx.fold_begin(fd["trngPos"][:1], fd["trngNeg"], fd["testPos"], fd["testNeg"])
+    with pytest.raises(psm.PsmError) as e:
+        ctx.fold_knn(5)
+    assert e.value.code == -3     # the reference abort()s with < 2 positives
+    ctx.fold_begin(fd["trngPos"], fd["trngNeg"][:41], fd["testPos"], fd["testNeg"])
+    with pytest.raises(psm.PsmError) as e:
+        ctx.batch_begin(10, 1, 1, 0, 10)   # 41 negatives / 10 parts: last chunk underflows in the reference
+    assert e.value.code == -6
