@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- hyperSMURF partition pipeline (kNN + SMOTE + RF train + predict + ensemble + AUROC/AUPRC) on B200.
+
+A "step" is one complete cross-validation of BASELINE.json configs[1]:
+    synthetic 1M x 26, imbalanced 1:1000, nParts=100, fp=2, ratio=3, k=5, nTrees=10, mtry=5, 5-fold CV  (500 partitions)
+metric = partitions/sec (whole job, all GPUs); ms_per_step = CV wall time.
+
+  python bench.py --gpus N --steps K --warmup W                   our arm (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K --warmup W  the reference's own CPU code on the host cores
+  torchrun ... bench.py --gpus N ...                              N ranks, partitions sharded, one NCCL all-reduce per fold
+
+`value`  : dataset already resident in HBM when the timed region starts (device pointer attached).
+`e2e`    : the same CV through the public host API with the dataset in pinned HOST memory: the H2D copy of x, the
+           index/draw uploads and the D2H of the scores are inside the timed region.
+`roofline`: split_search kernel -- algorithmic bytes (sum over searched nodes of n_node*(mtry*8+8)) divided by
+           its accumulated CUDA-event time inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "cfg2": dict(n=1_000_000, m=26, npos=1000, nFolds=5, nParts=100, fp=2, ratio=3, k=5, nTrees=10, mtry=5, seed=1, shift=5),
+    # small smoke-sized variant for quick checks (not a bench line)
+    "small": dict(n=50_000, m=26, npos=200, nFolds=5, nParts=10, fp=2, ratio=3, k=5, nTrees=10, mtry=5, seed=1, shift=5),
+}
+
+
+def make_data(w):
+    """Seeded synthetic imbalanced data of the named shape: iid N(0,1) features, positives shifted by +1 on
+    the first `shift` features so AUROC < 1; exactly `npos` positives; stratified folds."""
+    rng = np.random.default_rng(1)
+    n, m = w["n"], w["m"]
+    x = np.empty((n, m + 1), dtype=np.float64)
+    x[:, :m] = rng.standard_normal((n, m))
+    y = np.zeros(n, np.uint32)
+    y[rng.choice(n, w["npos"], replace=False)] = 1
+    x[y == 1, : w["shift"]] += 1.0
+    x[:, m] = np.where(y > 0, 1.0, 2.0)
+    f = np.zeros(n, np.uint32)
+    for c in (0, 1):
+        idx = np.flatnonzero(y == c)
+        rng.shuffle(idx)
+        f[idx] = np.arange(len(idx)) % w["nFolds"]
+    return x, y, f
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for i, nm in enumerate(names):
+                    if r[5 + i].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_sample(w, x, y, f, parts_sample, threads):
+    """Time the reference's own CPU code (oracle/_ref, unmodified classes) on a bounded sample: `parts_sample` partitions of
+    fold 0 with `threads` OpenMP threads over partitions (ensThrd), rfThrd 1 -- falls back to the oracle port if the
+    compiled reference did not travel."""
+    from oracle import pyoracle as O
+    if O.have_ref():
+        ctx = O.RefCtx(x, y, f, w["nFolds"])
+        secs, _, _ = ctx.run_partitions(0, 0, parts_sample, w["nParts"], w["fp"], w["ratio"], w["k"], w["nTrees"], w["mtry"], w["seed"], threads)
+        return secs, "reference"
+    t0 = time.time()
+    # the port has no partition sub-range: scale a full fold by the sample fraction
+    O.o_cv(x, y, f, w["nFolds"], w["nParts"], w["fp"], w["ratio"], w["k"], w["nTrees"], w["mtry"], w["seed"], 0, 1, threads)
+    return (time.time() - t0) * parts_sample / w["nParts"], "port"
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    x, y, f = make_data(w)
+    cores = os.cpu_count() or 1
+    sample = max(1, min(w["nParts"], cores))
+    times = []
+    kind = "reference"
+    for i in range(args.warmup + args.steps):
+        secs, kind = cpu_sample(w, x, y, f, sample, cores)
+        if i >= args.warmup:
+            times.append(secs)
+    total = sum(times)
+    value = sample * len(times) / total
+    desc = "%d of %d partitions of fold 0 per step (Nte=%d test rows each), %d OpenMP threads over partitions, rfThrd 1" % (sample, w["nParts"], w["n"] // w["nFolds"], cores)
+    line = {"impl": "reference", "metric": "partitions/sec", "value": value, "unit": "partitions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, w),
+            "cpu_baseline": {"value": value, "unit": "partitions/s", "cores": cores, "kind": kind, "sample": desc},
+            "e2e": {"value": value, "unit": "partitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, w):
+    return {"workload": "BASELINE.json configs[1]: synthetic %dx%d imbalanced 1:%d, nParts=%d, fp=%d, ratio=%d, k=%d, nTrees=%d, mtry=%d, %d-fold CV"
+            % (w["n"], w["m"], w["n"] // w["npos"], w["nParts"], w["fp"], w["ratio"], w["k"], w["nTrees"], w["mtry"], w["nFolds"]),
+            "partitions_per_step": w["nParts"] * w["nFolds"], "parallelism": "partitions sharded over %d GPU(s), dataset replicated, one NCCL all-reduce of fold scores per fold" % args.gpus,
+            "l2_policy": "inputs larger than L2 (dataset 216 MB + per-fold training batch ~2.7 GB >> 126 MB L2); no explicit flush",
+            "curves_tie_mode": "device radix sort (stable)"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    from parsmurf_b200 import host_api as H
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- parsmurf_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    x, y, f = make_data(w)
+    n, m = w["n"], w["m"]
+    x_pinned = torch.from_numpy(x).pin_memory()
+    x_host = x_pinned.numpy()
+    x_dev = x_pinned.to("cuda", non_blocking=False)
+    torch.cuda.synchronize()
+
+    class _Arr:   # zero-copy view of a raw device pointer as a torch tensor
+        def __init__(self, ptr, count):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+    def reduce(ptr, count):
+        t = torch.as_tensor(_Arr(ptr, count), device="cuda")
+        dist.all_reduce(t)
+        torch.cuda.current_stream().synchronize()
+
+    common = dict(labels=y, folds=f, nFolds=w["nFolds"], nParts=w["nParts"], fp=w["fp"], ratio=w["ratio"], k=w["k"], nTrees=w["nTrees"], mtry=w["mtry"],
+                  seed=w["seed"], device=local, stream=stream.cuda_stream, tie_mode=1, eval_fold_curves=True, rank=rank, world=world,
+                  reduce=reduce if world > 1 else None, profile=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        outs = [fn() for _ in range(steps)]
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), outs
+
+    run_dev = lambda: H.cv_run(None, x_device_ptr=x_dev.data_ptr(), n=n, m=m, **common)
+    run_e2e = lambda: H.cv_run(x_host, **common)
+
+    for _ in range(args.warmup):
+        run_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, outs = timed(run_dev, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(min(args.warmup, 1)):
+        run_e2e()
+    ms_e2e, outs_e2e = timed(run_e2e, args.steps)
+
+    parts = w["nParts"] * w["nFolds"]
+    value = parts * args.steps / (ms_dev / 1000.0)
+    e2e_value = parts * args.steps / (ms_e2e / 1000.0)
+    # per-step traffic of the e2e path, counted from what is copied
+    P_tr = w["npos"] - w["npos"] // w["nFolds"]
+    per_fold_idx = 4 * (n + (n - n // w["nFolds"]))                       # train pos/neg + test pos/neg + test index list
+    draws = 4 * P_tr * w["fp"] * (m + 1) * w["nParts"]
+    h2d = x.nbytes + w["nFolds"] * (per_fold_idx + draws) + (w["nFolds"] + 1) * 12 * (n // w["nFolds"])   # + curves inputs
+    d2h = w["nFolds"] * 16 * (n // w["nFolds"]) + (w["nFolds"] + 1) * 16
+
+    # roofline of the dominant training kernel over the timed region (this rank's kernels)
+    km = {k_: sum(o["kernel_ms"][k_] for o in outs) for k_ in outs[0]["kernel_ms"]}
+    kl = {k_: sum(o["kernel_launches"][k_] for o in outs) for k_ in outs[0]["kernel_launches"]}
+    split_bytes = sum(o["stats"]["split_bytes"] for o in outs)
+    peak, peak_src = peaks()
+    ss_ms, ss_launches = km["split_search"], max(kl["split_search"], 1)
+    achieved = split_bytes / (ss_ms / 1000.0) / 1e9 if ss_ms > 0 else 0.0
+    roofline = {"kernel": "split_search_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": split_bytes / ss_launches,
+                "avg_launch_ms": ss_ms / ss_launches, "launches": kl["split_search"],
+                "kernel_ms_per_step": {k_: v / args.steps for k_, v in km.items()}}
+    if rank == 0:
+        line = {"metric": "partitions/sec", "value": value, "unit": "partitions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, w), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "partitions/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(sum(kl.values())), "roofline": roofline,
+                "examples_per_sec": n * args.steps / (ms_dev / 1000.0),
+                "quality": {"auroc": outs[-1]["auroc"], "auprc": outs[-1]["auprc"]}}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = max(1, min(w["nParts"], cores))
+            secs, kind = cpu_sample(w, x, y, f, sample, cores)
+            line["cpu_baseline"] = {"value": sample / secs, "unit": "partitions/s", "cores": cores, "kind": kind,
+                                    "sample": "%d of %d partitions of fold 0 (Nte=%d), %d OpenMP threads over partitions, rfThrd 1, %.1f s" % (sample, w["nParts"], n // w["nFolds"], cores, secs)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,10 @@ int psm_curves(psm_ctx* ctx, const uint32_t* labels, const double* scores, uint6
 int psm_fold_run_partitions(psm_ctx* ctx, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t nTrees, uint32_t mtry,
                             uint32_t seed, uint32_t fold, uint32_t p0, uint32_t p1, const int32_t* draws_host);
 
+/* largest number of partitions starting at p0 that one batch may hold under the memory budget (>= 1) */
+int psm_batch_capacity(psm_ctx* ctx, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t nTrees, uint32_t mtry, uint32_t p0,
+                       uint32_t* capacity);
+
 /* ---- instrumentation: accumulated device time (ms, CUDA events on the context stream) and launch counts per
  *      kernel class since the last reset.  ids: 0 knn, 1 assemble, 2 feature_sort, 3 bootstrap, 4 build_lists,
  *      5 split_search, 6 split_select, 7 level_finalize, 8 partition_lists, 9 predict, 10 curves, 11 gather. --- */

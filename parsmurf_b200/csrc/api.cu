@@ -634,18 +634,31 @@ int psm_curves(psm_ctx* ctx, const uint32_t* labels, const double* scores, uint6
 }
 
 // ------------------------------------------------------------------------------------------ convenience
+int psm_batch_capacity(psm_ctx* ctx, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t nTrees, uint32_t mtry, uint32_t p0, uint32_t* capacity) {
+	if (!ctx || !ctx->foldOpen || !capacity || nParts == 0 || p0 >= nParts || nTrees == 0) return fail(ctx, PSM_E_ARG, "batch_capacity: bad arguments");
+	// per-partition device bytes of one batch (upper bound with Ntr of partition p0; later partitions are never larger)
+	PartDesc d0;
+	int rc = partition_sizes(ctx->P, ctx->Nneg, nParts, fp, ratio, p0, &d0);
+	if (rc) return fail(ctx, rc, "batch_capacity: invalid partition geometry");
+	const uint64_t Ntr = d0.Ntr, m = ctx->m, T = nTrees;
+	const uint64_t perPart = Ntr * (8 * (m + 1) + 8 * m + 24 * m + 16 * T * m + 4 * T + T + 32 * T + 8) + (uint64_t)ctx->Nte * 16 +
+	                         T * (Ntr / 11 + 2) * (2 * sizeof(Item) + mtry * 4 + mtry * sizeof(SearchRes) + sizeof(SplitDec)) + T * 312 * 8 +
+	                         (uint64_t)ctx->P * fp * (m + 1) * 4;
+	uint64_t nb = std::max<uint64_t>(1, ctx->budget / std::max<uint64_t>(perPart, 1));
+	// keep the work-item pool index below 2^31
+	const uint64_t itemsPerPart = T * (Ntr / 11 + 2);
+	nb = std::min<uint64_t>(nb, std::max<uint64_t>(1, ((1ull << 31) - 1) / std::max<uint64_t>(itemsPerPart, 1)));
+	*capacity = (uint32_t)std::min<uint64_t>(nb, nParts - p0);
+	return PSM_OK;
+}
+
 int psm_fold_run_partitions(psm_ctx* ctx, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t nTrees, uint32_t mtry, uint32_t seed,
                             uint32_t fold, uint32_t p0, uint32_t p1, const int32_t* draws_host) {
 	if (!ctx || !ctx->foldOpen) return fail(ctx, PSM_E_ARG, "fold_run_partitions: no open fold");
 	if (nParts == 0 || p0 >= p1 || p1 > nParts || nTrees == 0) return fail(ctx, PSM_E_ARG, "fold_run_partitions: bad arguments");
-	// per-partition device bytes of one batch (upper bound with Ntr of partition p0)
-	PartDesc d0;
-	int rc = partition_sizes(ctx->P, ctx->Nneg, nParts, fp, ratio, p0, &d0);
-	if (rc) return fail(ctx, rc, "fold_run_partitions: invalid partition geometry");
-	const uint64_t Ntr = d0.Ntr, m = ctx->m, T = nTrees;
-	const uint64_t perPart = Ntr * (8 * (m + 1) + 8 * m + 24 * m + 16 * T * m + 4 * T + T + 32 * T + 8) + (uint64_t)ctx->Nte * 16 +
-	                         T * (Ntr / 11 + 2) * (2 * sizeof(Item) + mtry * 4 + mtry * sizeof(SearchRes) + sizeof(SplitDec)) + T * 312 * 8;
-	uint64_t nb = std::max<uint64_t>(1, ctx->budget / std::max<uint64_t>(perPart, 1));
+	int rc;
+	uint32_t nb = 1;
+	if ((rc = psm_batch_capacity(ctx, nParts, fp, ratio, nTrees, mtry, p0, &nb))) return rc;
 	const uint64_t perDraw = (uint64_t)ctx->P * fp * (ctx->m + 1);
 	for (uint32_t b0 = p0; b0 < p1;) {
 		uint32_t b1 = (uint32_t)std::min<uint64_t>(p1, (uint64_t)b0 + nb);

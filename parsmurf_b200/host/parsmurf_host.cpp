@@ -1,0 +1,596 @@
+// parsmurf_b200 host layer -- see parsmurf_host.h.  Every method cites the reference code it mirrors
+// (paths relative to the reference repository).  No example data is touched on the CPU here: all of it goes
+// through the C ABI (include/parsmurf_b200.h).
+#include "parsmurf_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+namespace parsmurf {
+
+// ------------------------------------------------------------------------------------------ GlibcRand
+// glibc stdlib/random_r.c: TYPE_3 (x^31 + x^3 + 1), seeded through the 16807 Park-Miller LCG, first 310 discarded
+void GlibcRand::srand(uint32_t seed) {
+	if (seed == 0) seed = 1;
+	int32_t word = (int32_t)seed;
+	tbl[0] = word;
+	for (int i = 1; i < 31; i++) {
+		long hi = word / 127773, lo = word % 127773;
+		word = (int32_t)(16807 * lo - 2836 * hi);
+		if (word < 0) word += 2147483647;
+		tbl[i] = word;
+	}
+	f = 3; r = 0;
+	for (int i = 0; i < 310; i++) rand();
+}
+int32_t GlibcRand::rand() {
+	uint32_t v = (uint32_t)tbl[f] + (uint32_t)tbl[r];
+	tbl[f] = (int32_t)v;
+	if (++f >= 31) { f = 0; ++r; }
+	else if (++r >= 31) r = 0;
+	return (int32_t)(v >> 1);
+}
+void GlibcRand::fill(int32_t* out, size_t count) {
+	for (size_t i = 0; i < count; i++) out[i] = rand();
+}
+void GlibcRand::shuffle(uint32_t* a, size_t n) {
+	for (size_t i = 1; i < n; i++) {
+		size_t j = (size_t)(rand() % (int64_t)(i + 1));
+		if (i != j) std::swap(a[i], a[j]);
+	}
+}
+
+// ------------------------------------------------------------------------------------------ Folds (src/folds.cpp:26-117)
+Folds::Folds(uint32_t numberOfFolds, uint32_t classSize_, const uint32_t* labels_, std::vector<uint32_t>& ff, bool randomFold_, GlibcRand* rng_)
+    : classSize(classSize_), nFolds(numberOfFolds), labels(labels_), fromFile(ff), nPos(numberOfFolds), nNeg(numberOfFolds),
+      foldsIdx(numberOfFolds + 1), folds(classSize_), randomFold(randomFold_), rng(rng_) {}
+
+void Folds::computeFolds() {
+	totPos = 0;
+	for (uint32_t i = 0; i < classSize; i++) totPos += labels[i] >= 1;
+	totNeg = classSize - totPos;
+	std::fill(nPos.begin(), nPos.end(), 0);
+	std::fill(nNeg.begin(), nNeg.end(), 0);
+	if (randomFold) {
+		std::vector<uint32_t> pos, neg;
+		for (uint32_t i = 0; i < classSize; i++) (labels[i] > 0 ? pos : neg).push_back(i);
+		rng->shuffle(pos.data(), pos.size());
+		rng->shuffle(neg.data(), neg.size());
+		uint32_t ffSize = classSize / nFolds, ffRemn = classSize % nFolds;
+		foldsIdx[0] = 0;
+		for (uint32_t i = 0; i < nFolds; i++) {
+			foldsIdx[i + 1] = foldsIdx[i] + ffSize;
+			if (ffRemn != 0) { foldsIdx[i + 1]++; ffRemn--; }
+		}
+		for (uint32_t i = 0; i < totPos; i++) { folds[foldsIdx[i % nFolds] + i / nFolds] = pos[i]; nPos[i % nFolds]++; }
+		for (uint32_t i = totPos; i < totPos + totNeg; i++) { folds[foldsIdx[i % nFolds] + i / nFolds] = neg[i - totPos]; nNeg[i % nFolds]++; }
+	} else {
+		std::vector<uint32_t> hist(nFolds, 0);
+		for (uint32_t v : fromFile) {
+			if (v >= nFolds) throw Error(PSM_E_ARG, "Folds: fold id out of range");
+			hist[v]++;
+		}
+		foldsIdx[0] = 0;
+		for (uint32_t i = 1; i <= nFolds; i++) foldsIdx[i] = foldsIdx[i - 1] + hist[i - 1];
+		std::fill(hist.begin(), hist.end(), 0);
+		for (uint32_t i = 0; i < classSize; i++) {
+			uint32_t bin = fromFile[i];
+			folds[foldsIdx[bin] + hist[bin]++] = i;
+			if (labels[i] > 0) nPos[bin]++; else nNeg[bin]++;
+		}
+	}
+	maxPos = *std::max_element(nPos.begin(), nPos.end());
+	maxNeg = *std::max_element(nNeg.begin(), nNeg.end());
+}
+
+// ------------------------------------------------------------------------------------------ TestTrainDivider
+void TestTrainDivider::build(uint32_t i, uint32_t cur, int64_t jump) {
+	const Folds* F = folds;
+	for (uint32_t j = F->foldsIdx[cur]; j < F->foldsIdx[cur + 1]; j++)
+		(F->labels[F->folds[j]] < 1 ? testNegIdx[i] : testPosIdx[i]).push_back(F->folds[j]);
+	for (uint32_t kf = 0; kf < F->nFolds; kf++) {
+		if (kf == cur || (int64_t)kf == jump) continue;
+		for (uint32_t j = F->foldsIdx[kf]; j < F->foldsIdx[kf + 1]; j++)
+			(F->labels[F->folds[j]] < 1 ? trngNegIdx[i] : trngPosIdx[i]).push_back(F->folds[j]);
+	}
+}
+
+// src/testtraindivider.cpp:5-106
+TestTrainDivider::TestTrainDivider(const Folds* folds_, uint8_t wmode_, GlibcRand* rng) : folds(folds_), wmode(wmode_), nFolds(folds_->nFolds) {
+	testPosIdx.resize(nFolds); testNegIdx.resize(nFolds); trngPosIdx.resize(nFolds); trngNegIdx.resize(nFolds);
+	for (uint32_t i = 0; i < nFolds; i++) {
+		build(i, i, -1);
+		rng->shuffle(trngNegIdx[i].data(), trngNegIdx[i].size());            // :90
+	}
+	if (wmode == MODE_TRAIN) { trngPosIdx[0] = testPosIdx[0]; trngNegIdx[0] = testNegIdx[0]; }   // :101-104
+	for (uint32_t i = 0; i < nFolds; i++) {
+		testPosNum.push_back(testPosIdx[i].size()); testNegNum.push_back(testNegIdx[i].size());
+		trngPosNum.push_back(trngPosIdx[i].size()); trngNegNum.push_back(trngNegIdx[i].size());
+	}
+}
+
+// src/testtraindivider.cpp:126-236 -- inner CV: fold `foldToJump` is left out entirely, no shuffle
+TestTrainDivider::TestTrainDivider(const Folds* folds_, uint8_t wmode_, uint32_t foldToJump) : folds(folds_), wmode(wmode_), nFolds(folds_->nFolds - 1) {
+	testPosIdx.resize(nFolds); testNegIdx.resize(nFolds); trngPosIdx.resize(nFolds); trngNegIdx.resize(nFolds);
+	uint32_t cur = 0;
+	for (uint32_t i = 0; i < nFolds; i++) {
+		if (cur == foldToJump) cur++;
+		build(i, cur, foldToJump);
+		cur++;
+	}
+	for (uint32_t i = 0; i < nFolds; i++) {
+		testPosNum.push_back(testPosIdx[i].size()); testNegNum.push_back(testNegIdx[i].size());
+		trngPosNum.push_back(trngPosIdx[i].size()); trngNegNum.push_back(trngNegIdx[i].size());
+	}
+}
+
+// ------------------------------------------------------------------------------------------ Partition (src/partition.cpp:7-37)
+Partition::Partition(const Folds* folds_, const TestTrainDivider* ttd_, uint32_t nPart_, uint32_t fp_, uint32_t ratio_, uint32_t m_, uint32_t n_)
+    : folds(folds_), ttd(ttd_), nPart(nPart_), fp(fp_), ratio(ratio_), m(m_), n(n_) {
+	maxSize = ratio == 0 ? ((fp + 1) * folds->maxPos + folds->maxNeg) * (folds->nFolds - 1) : (fp + 1) * (ratio + 1) * folds->maxPos * (folds->nFolds - 1);
+	if (folds->nFolds == 1) maxSize = ratio == 0 ? ((fp + 1) * folds->maxPos + folds->maxNeg) : (fp + 1) * (ratio + 1) * folds->maxPos;
+}
+void Partition::setFold(uint32_t f) {
+	currentFold = f;
+	trngPosNum = ttd->trngPosNum[f]; trngNegNum = ttd->trngNegNum[f]; testPosNum = ttd->testPosNum[f]; testNegNum = ttd->testNegNum[f];
+	trngPosIdx = ttd->trngPosIdx[f].data(); trngNegIdx = ttd->trngNegIdx[f].data();
+	testPosIdx = ttd->testPosIdx[f].data(); testNegIdx = ttd->testNegIdx[f].data();
+}
+
+// ------------------------------------------------------------------------------------------ Device
+Device::Device(int device, void* cudaStream) {
+	int rc = psm_ctx_create(device, &ctx);
+	if (rc) throw Error(rc, "parsmurf_b200: no usable CUDA device (there is no CPU fallback)");
+	if (cudaStream) check(psm_set_stream(ctx, cudaStream));
+}
+Device::~Device() { if (ctx) psm_ctx_destroy(ctx); }
+void Device::check(int rc) const { if (rc) throw Error(rc, psm_last_error(ctx)); }
+void Device::upload(const double* x, uint32_t n_, uint32_t m_) { check(psm_dataset_upload(ctx, x, n_, m_)); n = n_; m = m_; foldTag = nullptr; }
+void Device::attachDevice(const double* x, uint32_t n_, uint32_t m_) { check(psm_dataset_attach_device(ctx, x, n_, m_)); n = n_; m = m_; foldTag = nullptr; }
+void Device::ensureFold(const Partition* part) {
+	if (foldTag == (const void*)part->ttd && foldId == part->currentFold) return;
+	check(psm_fold_begin(ctx, part->trngPosIdx, part->trngPosNum, part->trngNegIdx, part->trngNegNum, part->testPosIdx, part->testPosNum,
+	                     part->testNegIdx, part->testNegNum));
+	foldTag = part->ttd; foldId = part->currentFold; knnK = 0;
+}
+void Device::ensureKnn(uint32_t k) {
+	if (knnK == k) return;
+	check(psm_fold_knn(ctx, k));
+	knnK = k;
+}
+
+// ------------------------------------------------------------------------------------------ SamplerKNN
+SamplerKNN::SamplerKNN(const Partition* part_, uint8_t wmode_, Device* dev_, uint32_t m_, uint32_t n_, uint32_t k_, GlibcRand* rng_)
+    : part(part_), dev(dev_), m(m_), n(n_), wmode(wmode_), k(k_), rng(rng_) {
+	testSize = part->testPosNum + part->testNegNum;                         // src/sampler.cpp:11
+}
+void SamplerKNN::setPartitionRange(uint32_t a, uint32_t b) {
+	if (a >= b || b > part->nPart) throw Error(PSM_E_ARG, "SamplerKNN::setPartitionRange: bad range");
+	p0 = a; p1 = b; currentPartition = a; currentFold = part->currentFold;
+	posForOverSmpl = part->trngPosNum;                                       // src/sampler.cpp:67
+	uint32_t negInEach = (uint32_t)std::ceil(part->trngNegNum / (double)part->nPart);
+	negForUndrSmpl = (a != part->nPart - 1) ? negInEach : part->trngNegNum - negInEach * (part->nPart - 1);
+}
+void SamplerKNN::sample() {
+	dev->ensureFold(part);
+	std::vector<int32_t> draws;
+	if (part->fp > 0) {
+		dev->ensureKnn(k);                                                   // src/samplerKNN.cpp:60-93, once per fold
+		draws.resize((size_t)(p1 - p0) * posForOverSmpl * part->fp * (m + 1));
+		rng->fill(draws.data(), draws.size());                               // src/samplerKNN.cpp:95,99 in partition order
+	}
+	dev->check(psm_batch_begin(dev->ctx, part->nPart, part->fp, part->ratio, p0, p1));
+	dev->check(psm_batch_assemble(dev->ctx, draws.empty() ? nullptr : draws.data(), draws.size()));
+	uint32_t sz[3];
+	dev->check(psm_batch_get_training(dev->ctx, p0, sz, nullptr));
+	trngPos = sz[0]; trngNeg = sz[1]; lineLen = sz[2]; trngSize = trngPos + trngNeg;   // src/samplerKNN.cpp:8-13
+}
+std::vector<double> SamplerKNN::trngData(uint32_t p) {
+	uint32_t sz[3];
+	dev->check(psm_batch_get_training(dev->ctx, p, sz, nullptr));
+	std::vector<double> out((size_t)sz[2] * (m + 1));
+	dev->check(psm_batch_get_training(dev->ctx, p, sz, out.data()));
+	return out;
+}
+
+// ------------------------------------------------------------------------------------------ rfRanger
+rfRanger::rfRanger(Device* dev_, uint32_t /*m*/, bool prediction_mode_, const SamplerKNN* samp_, uint32_t numTrees_, uint32_t mtry_, uint32_t rfThrd, uint32_t seedBase)
+    : dev(dev_), samp(samp_), mtry(mtry_), rfSeed(seedBase), num_threads(rfThrd), numTrees(numTrees_), prediction_mode(prediction_mode_) {}
+void rfRanger::train(bool) {
+	std::vector<uint32_t> seeds(samp->p1 - samp->p0);
+	for (uint32_t p = samp->p0; p < samp->p1; p++) seeds[p - samp->p0] = rfSeed + p;
+	dev->check(psm_batch_train(dev->ctx, numTrees, mtry, seeds.data(), nullptr, nullptr, 0));
+}
+void rfRanger::predict(bool) { dev->check(psm_batch_predict_accumulate(dev->ctx, samp->part->nPart)); }
+rfRanger::TreeExport rfRanger::getTree(uint32_t p, uint32_t t) const {
+	uint64_t nn = 0;
+	dev->check(psm_batch_tree_nodes(dev->ctx, p, t, &nn));
+	TreeExport e;
+	e.left.resize(nn); e.right.resize(nn); e.splitVarIDs.resize(nn); e.splitValues.resize(nn); e.terminalClassCounts.resize(2 * nn);
+	dev->check(psm_batch_export_tree(dev->ctx, p, t, e.left.data(), e.right.data(), e.splitVarIDs.data(), e.splitValues.data(), e.terminalClassCounts.data()));
+	return e;
+}
+
+// ------------------------------------------------------------------------------------------ Curves
+Curves::Curves(Device* dev_, const std::vector<uint32_t>& labels, const double* predictions, int tieMode_)
+    : dev(dev_), labls(labels), preds(predictions), tieMode(tieMode_) {}
+void Curves::eval() {
+	if (done) return;
+	dev->check(psm_curves(dev->ctx, labls.data(), preds, labls.size(), tieMode, res));
+	done = true;
+}
+double Curves::evalAUROC_ok() { eval(); return res[0]; }
+double Curves::evalAUPRC() { eval(); return res[1]; }
+
+// ------------------------------------------------------------------------------------------ hyperSMURF
+hyperSMURF::hyperSMURF(const CommonParams* cp, std::vector<GridParams>& gp, Folds* fm, Device* dev_, const std::vector<uint32_t>& y_,
+                       double* c1, double* c2, GlibcRand* rng_)
+    : commonParams(cp), gridParams(gp), foldManager(fm), dev(dev_), y(y_), class1Prob(c1), class2Prob(c2), rng(rng_) {}
+hyperSMURF::~hyperSMURF() {}
+
+void hyperSMURF::setSharding(uint32_t rank_, uint32_t world_, std::function<void(double*, uint64_t)> reduce_) {
+	rank = rank_; world = world_ ? world_ : 1; reduce = std::move(reduce_);
+}
+
+void hyperSMURF::initStandard() {                                           // src/hyperSMURF.cpp:22-51
+	nn = commonParams->nn; mm = commonParams->mm; nFolds = commonParams->nFolds;
+	setGridParams(0);
+	seed = commonParams->seed; verboseLevel = commonParams->verboseLevel;
+	wmode = commonParams->wmode; woptimiz = commonParams->woptimiz; inInternalCV = false;
+	ttd.reset(new TestTrainDivider(foldManager, wmode, rng));
+	part.reset(new Partition(foldManager, ttd.get(), nPart, fp, ratio, mm, nn));
+}
+void hyperSMURF::initInternalCV(uint32_t jump) {                            // src/hyperSMURF.cpp:53-78
+	nn = commonParams->nn; mm = commonParams->mm; nFolds = commonParams->nFolds - 1;
+	seed = commonParams->seed; verboseLevel = commonParams->verboseLevel;
+	wmode = MODE_CV; woptimiz = OPT_NO; inInternalCV = true; foldToJump = jump;
+	ttd.reset(new TestTrainDivider(foldManager, wmode, jump));
+}
+void hyperSMURF::setGridParams(uint32_t idx) {                              // src/hyperSMURF.cpp:80-88
+	idxInGridParams = idx;
+	nPart = gridParams[idx].nParts; numTrees = gridParams[idx].nTrees; fp = gridParams[idx].fp; ratio = gridParams[idx].ratio;
+	k = gridParams[idx].k; mtry = gridParams[idx].mtry;
+}
+void hyperSMURF::createPart() { part.reset(new Partition(foldManager, ttd.get(), nPart, fp, ratio, mm, nn)); }
+
+void hyperSMURF::smurfIt() {                                                // src/hyperSMURF.cpp:151-496 (CV paths)
+	if (wmode != MODE_CV) throw Error(PSM_E_ARG, "hyperSMURF::smurfIt: only mode \"cv\" is implemented on the GPU path");
+	uint32_t startingFold = 0, endingFold = nFolds;
+	if (!inInternalCV && commonParams->minFold != (uint32_t)-1) startingFold = commonParams->minFold;
+	if (!inInternalCV && commonParams->maxFold != (uint32_t)-1) endingFold = commonParams->maxFold;
+	if (woptimiz != OPT_NO) { tempcl1.assign(nn, 0.0); tempcl2.assign(nn, 0.0); }
+	if (!inInternalCV) { foldAuroc.assign(nFolds, 0.0); foldAuprc.assign(nFolds, 0.0); }
+
+	for (uint32_t currentFold = startingFold; currentFold < endingFold; currentFold++) {
+		if (woptimiz == OPT_GRID) {                                         // :176-228 grid exploration on the inner folds
+			hyperSMURF inner(commonParams, gridParams, foldManager, dev, y, tempcl1.data(), tempcl2.data(), rng);
+			inner.setSharding(rank, world, reduce);
+			inner.curvesTieMode = curvesTieMode;
+			inner.initInternalCV(currentFold);
+			std::string statFileName = "fold" + std::to_string(currentFold) + ".dat";
+			for (uint32_t i = 0; i < gridParams.size(); i++) {
+				std::fill(tempcl1.begin(), tempcl1.end(), 0.0);
+				std::fill(tempcl2.begin(), tempcl2.end(), 0.0);
+				inner.setGridParams(i);
+				inner.createPart();
+				inner.smurfIt();
+				if (rank == 0) {
+					std::ofstream tf(statFileName.c_str(), std::ios::app);   // :191-199
+					tf << std::to_string(i) << " " << std::to_string(gridParams[i].nParts) << " " << std::to_string(gridParams[i].fp) << " "
+					   << std::to_string(gridParams[i].ratio) << " " << std::to_string(gridParams[i].k) << " " << std::to_string(gridParams[i].nTrees) << " "
+					   << std::to_string(gridParams[i].mtry) << " " << std::to_string(gridParams[i].auroc) << " " << std::to_string(gridParams[i].auprc) << " "
+					   << std::endl;
+				}
+			}
+			auto best = std::max_element(gridParams.begin(), gridParams.end(), [](const GridParams& a, const GridParams& b) { return a.auprc < b.auprc; });
+			nPart = best->nParts; fp = best->fp; ratio = best->ratio; k = best->k; numTrees = best->nTrees; mtry = best->mtry;   // :207-224
+			part->nPart = nPart; part->fp = fp; part->ratio = ratio;
+		} else if (woptimiz == OPT_AUTOGP) {
+			throw Error(PSM_E_ARG, "optimizer \"autogp\" (spearmint via std::system) is out of scope of the GPU path");
+		}
+		if (!inInternalCV && commonParams->customCV) {                      // :230-248 params.dat override
+			const GridParams& g = gridParams[currentFold];
+			nPart = g.nParts; fp = g.fp; ratio = g.ratio; k = g.k; numTrees = g.nTrees; mtry = g.mtry;
+			part->nPart = nPart; part->fp = fp; part->ratio = ratio;
+		}
+		part->setFold(currentFold);                                         // :255
+		dev->invalidateFold();
+		dev->ensureFold(part.get());
+
+		// this rank's contiguous chunk of partitions (src/MPIHelper.cpp:29-37)
+		uint32_t cnt = nPart / world + ((nPart % world) > rank ? 1 : 0);
+		uint32_t first = 0;
+		for (uint32_t r2 = 0; r2 < rank; r2++) first += nPart / world + ((nPart % world) > r2 ? 1 : 0);
+		const uint32_t last = first + cnt;
+		const uint64_t perPartDraws = (uint64_t)part->trngPosNum * fp * (mm + 1);
+		std::vector<int32_t> skip;
+		auto skipDraws = [&](uint64_t count) {                              // keep the one SMOTE stream in partition order on every rank
+			skip.resize(1 << 16);
+			while (count) { size_t c = (size_t)std::min<uint64_t>(count, skip.size()); rng->fill(skip.data(), c); count -= c; }
+		};
+		skipDraws(perPartDraws * first);
+		uint32_t cap = 1;
+		if (cnt) dev->check(psm_batch_capacity(dev->ctx, nPart, fp, ratio, numTrees, mtry, first, &cap));
+		for (uint32_t b0 = first; b0 < last; b0 += cap) {                   // the `#pragma omp for` over partitions (:257-261), as batches
+			const uint32_t b1 = std::min(last, b0 + cap);
+			SamplerKNN samp(part.get(), wmode, dev, mm, nn, k, rng);        // :275
+			samp.setPartitionRange(b0, b1);                                 // :276
+			samp.sample();                                                  // :277
+			rfRanger rf(dev, mm, false, &samp, numTrees, mtry, commonParams->rfThr, seed + currentFold * nPart);   // :273,302
+			rf.train(commonParams->rfVerbose);                              // :303
+			samp.copyTestSet();                                             // :316
+			rfRanger rfTest(dev, mm, true, &samp, numTrees, mtry, commonParams->rfThr, 2 * (seed + currentFold * nPart));   // :330
+			rfTest.predict(commonParams->rfVerbose);                        // :331
+			samp.accumulateAndDivideResInProbVect(nPart);                   // :344-346 (done on the device by predict)
+		}
+		skipDraws(perPartDraws * (nPart - last));
+		if (world > 1 && reduce) {                                          // src/hyperSMURF_MPI.cpp:594-618
+			double* ptr = nullptr; uint32_t nte = 0;
+			dev->check(psm_fold_scores_devptr(dev->ctx, &ptr, &nte));
+			dev->check(psm_sync(dev->ctx));
+			reduce(ptr, 2ull * nte);
+		}
+		dev->check(psm_fold_scatter_host(dev->ctx, class1Prob, class2Prob));
+
+		if (evalFoldCurves && !inInternalCV) {                              // :365-396 per-fold AUROC / AUPRC
+			std::vector<uint32_t> tl; std::vector<double> tp;
+			for (uint32_t i = 0; i < ttd->testPosNum[currentFold]; i++) { uint32_t v = ttd->testPosIdx[currentFold][i]; tl.push_back(y[v]); tp.push_back(class1Prob[v]); }
+			for (uint32_t i = 0; i < ttd->testNegNum[currentFold]; i++) { uint32_t v = ttd->testNegIdx[currentFold][i]; tl.push_back(y[v]); tp.push_back(class1Prob[v]); }
+			Curves c(dev, tl, tp.data(), curvesTieMode);
+			foldAuroc[currentFold] = c.evalAUROC_ok();                      // AUROC first, then AUPRC (:382-384)
+			foldAuprc[currentFold] = c.evalAUPRC();
+			if (verboseLevel > VERBSILENT && rank == 0)
+				std::cout << "External CV on fold " << currentFold << " -> AUROC: " << foldAuroc[currentFold] << " - AUPRC: " << foldAuprc[currentFold] << std::endl;
+		}
+	}
+
+	if (inInternalCV) {                                                     // :456-482
+		std::vector<uint32_t> tl; std::vector<double> tp;
+		for (uint32_t f = 0; f < nFolds; f++) {
+			for (uint32_t v : ttd->testPosIdx[f]) { tl.push_back(y[v]); tp.push_back(class1Prob[v]); }
+			for (uint32_t v : ttd->testNegIdx[f]) { tl.push_back(y[v]); tp.push_back(class1Prob[v]); }
+		}
+		Curves c(dev, tl, tp.data(), curvesTieMode);
+		gridParams[idxInGridParams].auroc = c.evalAUROC_ok();
+		gridParams[idxInGridParams].auprc = c.evalAUPRC();
+	} else {                                                                // :484-488
+		Curves c(dev, y, class1Prob, curvesTieMode);
+		auroc = c.evalAUROC_ok();
+		auprc = c.evalAUPRC();
+		if (verboseLevel > VERBSILENT && rank == 0) std::cout << "AUROC: " << auroc << " - AUPRC: " << auprc << std::endl;
+	}
+}
+
+// ------------------------------------------------------------------------------------------ JSON config
+namespace {
+struct JVal {
+	enum T { NUL, BOOL, NUM, STR, ARR, OBJ } t = NUL;
+	bool b = false; double num = 0; std::string s;
+	std::vector<JVal> arr;
+	std::vector<std::pair<std::string, JVal>> obj;
+	const JVal* get(const std::string& k) const { for (auto& kv : obj) if (kv.first == k) return &kv.second; return nullptr; }
+};
+struct JParser {
+	const std::string& s; size_t i = 0;
+	explicit JParser(const std::string& s_) : s(s_) {}
+	void ws() { while (i < s.size() && (s[i] == ' ' || s[i] == '\t' || s[i] == '\n' || s[i] == '\r')) i++; }
+	[[noreturn]] void bad(const char* w) { throw Error(PSM_E_ARG, std::string("config JSON: ") + w + " at offset " + std::to_string(i)); }
+	JVal parse() {
+		ws();
+		if (i >= s.size()) bad("unexpected end");
+		JVal v;
+		char c = s[i];
+		if (c == '{') {
+			v.t = JVal::OBJ; i++;
+			while (true) {
+				ws();
+				if (i < s.size() && s[i] == '}') { i++; break; }            // also accepts a trailing comma like jsoncons does (cfgEx/gridTune.json)
+				JVal key = parse();
+				if (key.t != JVal::STR) bad("object key must be a string");
+				ws();
+				if (i >= s.size() || s[i] != ':') bad("':' expected");
+				i++;
+				v.obj.emplace_back(key.s, parse());
+				ws();
+				if (i < s.size() && s[i] == ',') { i++; continue; }
+				if (i < s.size() && s[i] == '}') { i++; break; }
+				bad("',' or '}' expected");
+			}
+		} else if (c == '[') {
+			v.t = JVal::ARR; i++;
+			while (true) {
+				ws();
+				if (i < s.size() && s[i] == ']') { i++; break; }
+				v.arr.push_back(parse());
+				ws();
+				if (i < s.size() && s[i] == ',') { i++; continue; }
+				if (i < s.size() && s[i] == ']') { i++; break; }
+				bad("',' or ']' expected");
+			}
+		} else if (c == '"') {
+			v.t = JVal::STR; i++;
+			while (i < s.size() && s[i] != '"') {
+				if (s[i] == '\\' && i + 1 < s.size()) {
+					char e = s[i + 1];
+					v.s += e == 'n' ? '\n' : e == 't' ? '\t' : e;
+					i += 2;
+				} else v.s += s[i++];
+			}
+			if (i >= s.size()) bad("unterminated string");
+			i++;
+		} else if (!s.compare(i, 4, "true")) { v.t = JVal::BOOL; v.b = true; i += 4; }
+		else if (!s.compare(i, 5, "false")) { v.t = JVal::BOOL; v.b = false; i += 5; }
+		else if (!s.compare(i, 4, "null")) { i += 4; }
+		else {
+			size_t j = i;
+			while (j < s.size() && (isdigit((unsigned char)s[j]) || s[j] == '-' || s[j] == '+' || s[j] == '.' || s[j] == 'e' || s[j] == 'E')) j++;
+			if (j == i) bad("unexpected character");
+			v.t = JVal::NUM; v.num = std::stod(s.substr(i, j - i)); i = j;
+		}
+		return v;
+	}
+};
+template <typename T> T jnum(const JVal* o, const char* k, T def) { const JVal* v = o ? o->get(k) : nullptr; return (v && v->t == JVal::NUM) ? (T)v->num : def; }
+bool jbool(const JVal* o, const char* k, bool def) { const JVal* v = o ? o->get(k) : nullptr; return (v && v->t == JVal::BOOL) ? v->b : def; }
+std::string jstr(const JVal* o, const char* k, const std::string& def) { const JVal* v = o ? o->get(k) : nullptr; return (v && v->t == JVal::STR) ? v->s : def; }
+std::vector<int64_t> jarr(const JVal* o, const char* k) {
+	std::vector<int64_t> out;
+	const JVal* v = o ? o->get(k) : nullptr;
+	if (v && v->t == JVal::ARR) for (auto& e : v->arr) out.push_back((int64_t)e.num);
+	else if (v && v->t == JVal::NUM) out.push_back((int64_t)v->num);
+	if (out.empty()) out.push_back(-1);                                     // sentinel, ArgHandler_new.cpp:333-334
+	return out;
+}
+}  // namespace
+
+Config Config::fromString(const std::string& text) {
+	JParser p(text);
+	JVal root = p.parse();
+	if (root.t != JVal::OBJ) throw Error(PSM_E_ARG, "config JSON: top level must be an object");
+	const JVal *exec = root.get("exec"), *data = root.get("data"), *sim = root.get("simulate"), *flds = root.get("folds"), *params = root.get("params");
+	Config c;
+	c.dataFilename = jstr(data, "dataFile", ""); c.foldFilename = jstr(data, "foldFile", ""); c.labelFilename = jstr(data, "labelFile", "");
+	c.common.outfilename = jstr(data, "outFile", "output.txt");             // default: ArgHandler_new.cpp:144-148
+	c.common.forestDirname = jstr(data, "forestDir", "");
+	if (jbool(exec, "saveTime", false)) c.common.timeFilename = jstr(exec, "timeFile", "");
+	c.simulate = jbool(sim, "simulation", false);
+	c.common.nn = c.simulate ? jnum<uint32_t>(sim, "n", 1000) : 0;
+	c.common.mm = c.simulate ? jnum<uint32_t>(sim, "m", 10) : 0;
+	c.prob = c.simulate ? jnum<double>(sim, "prob", 0.01) : 0.0;
+	c.common.nFolds = jnum<uint32_t>(flds, "nFolds", 3);
+	c.common.minFold = jnum<uint32_t>(flds, "startingFold", (uint32_t)-1);
+	c.common.maxFold = jnum<uint32_t>(flds, "endingFold", (uint32_t)-1);
+	c.common.seed = jnum<uint32_t>(exec, "seed", 1);
+	c.common.verboseLevel = jnum<uint32_t>(exec, "verboseLevel", 0);
+	c.common.nThr = jnum<uint32_t>(exec, "ensThrd", 1);
+	c.common.rfThr = jnum<uint32_t>(exec, "rfThrd", 1);
+	c.printCfg = jbool(exec, "printCfg", false);
+	std::string mode = jstr(exec, "mode", "cv"), optim = jstr(exec, "optimizer", "no");
+	if (mode == "cv") c.common.wmode = MODE_CV;
+	else if (mode == "train") { c.common.wmode = MODE_TRAIN; c.common.nFolds = 1; }
+	else if (mode == "predict") { c.common.wmode = MODE_PREDICT; c.common.nFolds = 1; }
+	else throw Error(PSM_E_ARG, "Invalid prediction mode. Please specify either 'cv', 'train' or 'predict'");
+	if (optim == "no") c.common.woptimiz = OPT_NO;
+	else if (optim == "grid") c.common.woptimiz = OPT_GRID;
+	else if (optim == "autogp") c.common.woptimiz = OPT_AUTOGP;
+	else throw Error(PSM_E_ARG, "Invalid optimizer");
+	// cartesian product in the reference's loop order (ArgHandler_new.cpp:343-361); defaults of checkConfig (:294-330)
+	for (int64_t v1 : jarr(params, "nParts")) for (int64_t v2 : jarr(params, "fp")) for (int64_t v3 : jarr(params, "ratio"))
+	for (int64_t v4 : jarr(params, "k")) for (int64_t v5 : jarr(params, "nTrees")) for (int64_t v6 : jarr(params, "mtry")) {
+		GridParams g;
+		g.nParts = v1 < 0 ? 3 : (uint32_t)v1; g.fp = v2 < 0 ? 1 : (uint32_t)v2; g.ratio = v3 < 0 ? 1 : (uint32_t)v3;
+		g.k = v4 < 0 ? 5 : (uint32_t)v4; g.nTrees = v5 < 0 ? 50 : (uint32_t)v5; g.mtry = v6 < 0 ? 0 : (uint32_t)v6;
+		g.auroc = g.auprc = 0;
+		c.grid.push_back(g);
+	}
+	return c;
+}
+Config Config::fromFile(const std::string& path) {
+	std::ifstream f(path.c_str());
+	if (!f) throw Error(PSM_E_ARG, "cannot open config file " + path);
+	std::stringstream ss; ss << f.rdbuf();
+	Config c = fromString(ss.str());
+	c.common.cfgFilename = path;
+	return c;
+}
+void Config::processMtry(uint32_t mm) {                                      // ArgHandler_new.cpp:366-375
+	for (auto& g : grid) { if (g.mtry > mm) g.mtry = 0; if (g.mtry == 0) g.mtry = (uint32_t)std::sqrt((double)mm); }
+}
+
+}  // namespace parsmurf
+
+// ------------------------------------------------------------------------------------------ C entry points for bindings
+extern "C" {
+
+typedef int (*psmh_reduce_fn)(void* user, double* dev_ptr, uint64_t count);
+
+// Whole CV through the host classes, like parSMURF1's main (src/parSMURF.cpp:97-106) with data already in memory.
+// foldAssign == NULL -> random stratified folds (src/folds.cpp:27-77).  metrics = {auroc, auprc}; foldMetrics [nFolds][2] or NULL.
+// x_is_device != 0: `x` is a device pointer (dataset already resident in HBM).
+int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+                uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed, int device, void* stream,
+                int tieMode, int evalFoldCurves, uint32_t rank, uint32_t world, psmh_reduce_fn reduce, void* reduceUser, uint64_t batchBudget,
+                int profile, double* class1, double* class2, double* metrics, double* foldMetrics, double* kernelMs, uint64_t* kernelLaunches,
+                uint64_t* stats3, char* errbuf, size_t errlen) {
+	using namespace parsmurf;
+	try {
+		Device dev(device, stream);
+		if (batchBudget) dev.check(psm_set_batch_budget(dev.ctx, batchBudget));
+		if (profile) dev.check(psm_profile_enable(dev.ctx, 1));
+		if (x_is_device) dev.attachDevice(x, n, m); else dev.upload(x, n, m);
+		GlibcRand rng(1);
+		std::vector<uint32_t> y(labels, labels + n), ff;
+		if (foldAssign) ff.assign(foldAssign, foldAssign + n);
+		Folds folds(nFolds, n, y.data(), ff, foldAssign == nullptr, &rng);
+		folds.computeFolds();
+		CommonParams cp;
+		cp.nn = n; cp.mm = m; cp.nFolds = nFolds; cp.seed = seed; cp.wmode = MODE_CV; cp.woptimiz = OPT_NO;
+		std::vector<GridParams> gp(1);
+		gp[0] = GridParams{nParts, fp, ratio, k, nTrees, mtry, 0, 0};
+		hyperSMURF smurfer(&cp, gp, &folds, &dev, y, class1, class2, &rng);
+		smurfer.curvesTieMode = tieMode; smurfer.evalFoldCurves = evalFoldCurves != 0;
+		if (world > 1) smurfer.setSharding(rank, world, [&](double* p, uint64_t c) { if (reduce && reduce(reduceUser, p, c)) throw Error(PSM_E_CUDA, "reduce callback failed"); });
+		smurfer.initStandard();
+		smurfer.smurfIt();
+		if (metrics) { metrics[0] = smurfer.auroc; metrics[1] = smurfer.auprc; }
+		if (foldMetrics) for (uint32_t f = 0; f < nFolds; f++) { foldMetrics[2 * f] = smurfer.foldAuroc[f]; foldMetrics[2 * f + 1] = smurfer.foldAuprc[f]; }
+		if (kernelMs || kernelLaunches) dev.check(psm_profile_get(dev.ctx, kernelMs, kernelLaunches));
+		if (stats3) dev.check(psm_stats_get(dev.ctx, &stats3[0], &stats3[1], &stats3[2]));
+		return 0;
+	} catch (const parsmurf::Error& e) {
+		if (errbuf && errlen) { strncpy(errbuf, e.what(), errlen - 1); errbuf[errlen - 1] = 0; }
+		return e.code ? e.code : -1;
+	} catch (const std::exception& e) {
+		if (errbuf && errlen) { strncpy(errbuf, e.what(), errlen - 1); errbuf[errlen - 1] = 0; }
+		return -1;
+	}
+}
+
+// host-only helpers exposed for the CPU tests (no GPU needed)
+void psmh_rand_fill(uint32_t seed, int32_t* out, uint64_t count) { parsmurf::GlibcRand g(seed); g.fill(out, count); }
+
+// folds + ttd index arrays of one fold; sizes[4] always filled; index pointers may be NULL
+int psmh_ttd_fold(const uint32_t* labels, const uint32_t* foldAssign, uint32_t n, uint32_t nFolds, uint32_t fold, int64_t foldToJump, uint32_t* sizes,
+                  uint32_t* trngPos, uint32_t* trngNeg, uint32_t* testPos, uint32_t* testNeg) {
+	using namespace parsmurf;
+	try {
+		GlibcRand rng(1);
+		std::vector<uint32_t> ff;
+		if (foldAssign) ff.assign(foldAssign, foldAssign + n);
+		Folds folds(nFolds, n, labels, ff, foldAssign == nullptr, &rng);
+		folds.computeFolds();
+		std::unique_ptr<TestTrainDivider> t(foldToJump < 0 ? new TestTrainDivider(&folds, MODE_CV, &rng) : new TestTrainDivider(&folds, MODE_CV, (uint32_t)foldToJump));
+		if (fold >= t->nFolds) return PSM_E_ARG;
+		sizes[0] = t->trngPosNum[fold]; sizes[1] = t->trngNegNum[fold]; sizes[2] = t->testPosNum[fold]; sizes[3] = t->testNegNum[fold];
+		if (trngPos) std::copy(t->trngPosIdx[fold].begin(), t->trngPosIdx[fold].end(), trngPos);
+		if (trngNeg) std::copy(t->trngNegIdx[fold].begin(), t->trngNegIdx[fold].end(), trngNeg);
+		if (testPos) std::copy(t->testPosIdx[fold].begin(), t->testPosIdx[fold].end(), testPos);
+		if (testNeg) std::copy(t->testNegIdx[fold].begin(), t->testNegIdx[fold].end(), testNeg);
+		return 0;
+	} catch (...) { return PSM_E_ARG; }
+}
+
+// parse a cfgEx-style JSON; out[0..] = {nFolds, seed, wmode, woptimiz, gridSize, ensThrd, rfThrd, simulate, n, m}; grid [gridSize][6] if non-NULL
+int psmh_config_parse(const char* json, uint32_t* out10, uint32_t* grid, uint32_t gridCap, char* errbuf, size_t errlen) {
+	using namespace parsmurf;
+	try {
+		Config c = Config::fromString(json);
+		out10[0] = c.common.nFolds; out10[1] = c.common.seed; out10[2] = c.common.wmode; out10[3] = c.common.woptimiz; out10[4] = (uint32_t)c.grid.size();
+		out10[5] = c.common.nThr; out10[6] = c.common.rfThr; out10[7] = c.simulate; out10[8] = c.common.nn; out10[9] = c.common.mm;
+		if (grid) for (size_t i = 0; i < c.grid.size() && i < gridCap; i++) {
+			const GridParams& g = c.grid[i];
+			uint32_t* r = grid + 6 * i;
+			r[0] = g.nParts; r[1] = g.fp; r[2] = g.ratio; r[3] = g.k; r[4] = g.nTrees; r[5] = g.mtry;
+		}
+		return 0;
+	} catch (const std::exception& e) {
+		if (errbuf && errlen) { strncpy(errbuf, e.what(), errlen - 1); errbuf[errlen - 1] = 0; }
+		return PSM_E_ARG;
+	}
+}
+
+}  // extern "C"

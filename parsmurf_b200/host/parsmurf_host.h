@@ -1,0 +1,236 @@
+// parsmurf_b200 host layer -- C++ mirror of the reference's class boundaries for the partition pipeline.
+//
+// The reference (AnacletoLAB/parSMURF) has no FFI: hyperSMURF::smurfIt calls Partition, SamplerKNN, rfRanger
+// and Curves directly (reference src/hyperSMURF.cpp:255-396).  These classes keep those names, constructor
+// arguments, public fields and call order, but their bodies forward to the C ABI in include/parsmurf_b200.h
+// (CUDA, sm_100a).  Differences a maintainer must know:
+//   * `x` is uploaded once into a `Device` (the GPU context); samplers borrow the Device instead of `const double* x`.
+//   * partition concurrency is a RANGE [p0,p1) handled by batched launches (setPartitionRange) instead of one
+//     OpenMP thread per partition; setPartition(p) still works (range of one).
+//   * rand(): the reference draws from the process-global glibc rand(), never seeded for seed != 0
+//     (src/ArgHandler_new.cpp:257-262).  The host owns a private replica of that generator (GlibcRand, seed 1),
+//     so a run equals a fresh single-threaded (ensThrd 1) reference process bit for bit and stays deterministic.
+//   * errors throw parsmurf::Error (the reference abort()s or swallows exceptions, src/samplerKNN.cpp:38-48,
+//     src/rfRanger.cpp:51-53); Error::code is the PSM_E_* value.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/parsmurf_b200.h"
+
+namespace parsmurf {
+
+// reference src/HyperSMURFUtils.h:17-68
+enum verbLvl { VERBSILENT = 0, VERBPROGR = 1, VERBRF = 2, VERBALL = 3 };
+enum wmode_t { MODE_CV = 1, MODE_TRAIN = 2, MODE_PREDICT = 4 };
+enum woptimizer { OPT_NO = 16, OPT_GRID = 32, OPT_AUTOGP = 64 };
+
+struct GridParams {
+	uint32_t nParts, fp, ratio, k, nTrees, mtry;
+	double auroc, auprc;
+};
+
+struct CommonParams {
+	uint32_t nn = 0, mm = 0, nFolds = 0, seed = 1, verboseLevel = 0;
+	std::string outfilename, timeFilename, forestDirname, cfgFilename;
+	uint32_t nThr = 1, rfThr = 1;
+	uint8_t wmode = MODE_CV, woptimiz = OPT_NO;
+	bool rfVerbose = false, verboseMPI = false, noMtSender = false, customCV = false;
+	uint32_t minFold = (uint32_t)-1, maxFold = (uint32_t)-1;
+};
+
+struct Error : std::runtime_error {
+	int code;
+	Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+// glibc rand()/srand() replica (stdlib/random_r.c TYPE_3): the stream behind std::random_shuffle
+// (src/folds.cpp:41-42, src/testtraindivider.cpp:90) and SMOTE (src/samplerKNN.cpp:95,99)
+class GlibcRand {
+public:
+	explicit GlibcRand(uint32_t seed = 1) { srand(seed); }
+	void srand(uint32_t seed);
+	int32_t rand();
+	void fill(int32_t* out, size_t count);
+	void shuffle(uint32_t* a, size_t n);   // libstdc++ std::random_shuffle(first, last)
+private:
+	int32_t tbl[31];
+	int f, r;
+};
+
+// reference src/folds.h:10-40
+class Folds {
+public:
+	Folds(uint32_t numberOfFolds, uint32_t classSize, const uint32_t* labels, std::vector<uint32_t>& ff, bool randomFold, GlibcRand* rng);
+	void computeFolds();
+	const uint32_t classSize, nFolds;
+	const uint32_t* labels;
+	std::vector<uint32_t>& fromFile;
+	uint32_t totPos = 0, totNeg = 0;
+	std::vector<uint32_t> nPos, nNeg, foldsIdx, folds;
+	uint32_t maxPos = 0, maxNeg = 0;
+	bool randomFold;
+	GlibcRand* rng;
+};
+
+// reference src/testtraindivider.h:13-36 (both constructors)
+class TestTrainDivider {
+public:
+	TestTrainDivider(const Folds* folds, uint8_t wmode, GlibcRand* rng);
+	TestTrainDivider(const Folds* folds, uint8_t wmode, uint32_t foldToJump);
+	const Folds* const folds;
+	const uint8_t wmode;
+	uint32_t nFolds;
+	std::vector<std::vector<uint32_t>> testPosIdx, testNegIdx, trngPosIdx, trngNegIdx;
+	std::vector<uint32_t> testPosNum, testNegNum, trngPosNum, trngNegNum;
+private:
+	void build(uint32_t i, uint32_t currFoldIdx, int64_t foldToJump);
+};
+
+// reference src/partition.h:7-36
+class Partition {
+public:
+	Partition(const Folds* folds, const TestTrainDivider* ttd, uint32_t nPart, uint32_t fp, uint32_t ratio, uint32_t m, uint32_t n);
+	void setFold(uint32_t currentFold);
+	const Folds* const folds;
+	const TestTrainDivider* const ttd;
+	uint32_t nPart, fp, ratio;
+	const uint32_t m, n;
+	uint32_t maxSize;
+	uint32_t currentFold = 0;
+	uint32_t trngPosNum = 0, trngNegNum = 0, testPosNum = 0, testNegNum = 0;
+	const uint32_t *testPosIdx = nullptr, *testNegIdx = nullptr, *trngPosIdx = nullptr, *trngNegIdx = nullptr;
+};
+
+// The GPU context: owns psm_ctx and the device-resident copy of x (new; the reference shares `x` between threads)
+class Device {
+public:
+	Device(int device, void* cudaStream = nullptr);
+	~Device();
+	Device(const Device&) = delete;
+	void upload(const double* x, uint32_t n, uint32_t m);
+	void attachDevice(const double* x_dev, uint32_t n, uint32_t m);
+	// begins the fold on the device if it is not the current one (upload index arrays, zero fold scores, drop kNN)
+	void ensureFold(const Partition* part);
+	void ensureKnn(uint32_t k);
+	void invalidateFold() { foldTag = nullptr; }
+	void check(int rc) const;
+	psm_ctx* ctx = nullptr;
+	uint32_t n = 0, m = 0;
+	const void* foldTag = nullptr;
+	uint32_t foldId = (uint32_t)-1, knnK = 0;
+};
+
+// reference src/sampler.h:11-73 + src/samplerKNN.h:13-35
+class SamplerKNN {
+public:
+	SamplerKNN(const Partition* part, uint8_t wmode, Device* dev, uint32_t m, uint32_t n, uint32_t k, GlibcRand* rng);
+	void setPartition(uint32_t currentPart) { setPartitionRange(currentPart, currentPart + 1); }
+	void setPartitionRange(uint32_t p0, uint32_t p1);
+	void sample();                                  // setup + minOversample + majUndersample for the whole range, on the device
+	void copyTestSet() {}                           // test rows are gathered by index inside the predict kernel
+	// scores are accumulated on the device by rfRanger::predict(); kept for call-order compatibility
+	void accumulateAndDivideResInProbVect(uint32_t /*nPart*/) {}
+	std::vector<double> trngData(uint32_t p);       // row-major [trngSize][m+1] host copy (debug / parity)
+	const Partition* const part;
+	Device* const dev;
+	const uint32_t m, n;
+	const uint8_t wmode;
+	uint32_t currentPartition = 0, currentFold = 0, p0 = 0, p1 = 0;
+	uint32_t posForOverSmpl = 0, negForUndrSmpl = 0;
+	uint32_t trngPos = 0, trngNeg = 0, trngSize = 0, lineLen = 0, testSize = 0;   // of partition p0
+private:
+	uint32_t k;
+	GlibcRand* rng;
+};
+
+// reference src/rfRanger.h:18-67 -- ranger ForestProbability with parSMURF's fixed hyper-parameters
+class rfRanger {
+public:
+	rfRanger(Device* dev, uint32_t m, bool prediction_mode, const SamplerKNN* samp, uint32_t numTrees, uint32_t mtry, uint32_t rfThrd, uint32_t seedBase);
+	void train(bool verbose);     // forest seed of partition p = seedBase + p  (seedBase = seed + fold*nPart, src/hyperSMURF.cpp:273)
+	void predict(bool verbose);   // predict the fold's test rows and accumulate pred * (1/nPart) into the fold score buffer
+	// ranger getter layouts (src/ranger/Forest/Forest.h:82-101, ForestProbability.h:40-44)
+	struct TreeExport { std::vector<uint64_t> left, right, splitVarIDs; std::vector<double> splitValues, terminalClassCounts; };
+	TreeExport getTree(uint32_t p, uint32_t t) const;
+	Device* const dev;
+	const SamplerKNN* const samp;
+	uint32_t mtry, rfSeed, min_node_size = 10, num_threads, numTrees;
+	bool prediction_mode;
+};
+
+// reference src/curves.h:12-21
+class Curves {
+public:
+	Curves(Device* dev, const std::vector<uint32_t>& labels, const double* predictions, int tieMode = 0);
+	double evalAUROC_ok();
+	double evalAUPRC();
+private:
+	void eval();
+	Device* dev;
+	std::vector<uint32_t> labls;
+	const double* preds;
+	int tieMode;
+	bool done = false;
+	double res[2] = {0, 0};
+};
+
+// reference src/hyperSMURF.h:24-79
+class hyperSMURF {
+public:
+	hyperSMURF(const CommonParams* commonParams, std::vector<GridParams>& gridParams, Folds* foldManager, Device* dev,
+	           const std::vector<uint32_t>& y, double* class1Prob, double* class2Prob, GlibcRand* rng);
+	~hyperSMURF();
+	void initStandard();
+	void initInternalCV(uint32_t foldToJump);
+	void setGridParams(uint32_t idx);
+	void createPart();
+	void smurfIt();
+
+	// multi-GPU: this rank handles partitions [rank*.., ..) of every fold (src/MPIHelper.cpp:29-37) and `reduce`
+	// sums the fold score buffer [2*Nte] f64 across ranks in place (the MPI_Gather + master sum of
+	// src/hyperSMURF_MPI.cpp:594-618).  Default: single rank, no reduce.
+	void setSharding(uint32_t rank, uint32_t world, std::function<void(double* dev_ptr, uint64_t count)> reduce);
+	int curvesTieMode = 0;
+	bool evalFoldCurves = true;
+	std::vector<double> foldAuroc, foldAuprc;
+	double auroc = 0, auprc = 0;
+
+private:
+	const CommonParams* const commonParams;
+	std::vector<GridParams>& gridParams;
+	Folds* const foldManager;
+	Device* const dev;
+	const std::vector<uint32_t>& y;
+	double* const class1Prob;
+	double* const class2Prob;
+	GlibcRand* rng;
+	std::unique_ptr<TestTrainDivider> ttd;
+	std::unique_ptr<Partition> part;
+	uint32_t nn = 0, mm = 0, nFolds = 0, nPart = 0, numTrees = 0, fp = 0, ratio = 0, k = 0, mtry = 0, seed = 0, verboseLevel = 0;
+	uint8_t wmode = MODE_CV, woptimiz = OPT_NO;
+	bool inInternalCV = false;
+	uint32_t idxInGridParams = 0, foldToJump = 0;
+	uint32_t rank = 0, world = 1;
+	std::function<void(double*, uint64_t)> reduce;
+	std::vector<double> tempcl1, tempcl2;
+};
+
+// JSON configuration surface of cfgEx/*.json (reference src/ArgHandler_new.cpp:84-141, 294-375)
+struct Config {
+	CommonParams common;
+	std::vector<GridParams> grid;
+	std::string dataFilename, foldFilename, labelFilename;
+	bool simulate = false;
+	double prob = 0.0;
+	bool printCfg = false;
+	static Config fromFile(const std::string& path);
+	static Config fromString(const std::string& json);
+	void processMtry(uint32_t mm);   // mtry 0 or > m -> (uint32_t)sqrt(m)
+};
+
+}  // namespace parsmurf

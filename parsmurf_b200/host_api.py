@@ -1,0 +1,98 @@
+"""ctypes binding of the C++ host layer (libparsmurf_host.so: parsmurf::hyperSMURF and friends, parsmurf_b200/host/).
+`cv_run` is the call a user makes: the whole cross-validation through the reference-shaped host classes."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi
+from ._capi import KERNEL_CLASSES, PsmError, dp, u32, u32p, u64, u64p, vp, i32p, _p
+
+REDUCE_FN = C.CFUNCTYPE(C.c_int, vp, vp, u64)
+_hlib = None
+
+
+def hlib():
+    global _hlib
+    if _hlib is None:
+        _capi.lib()   # RTLD_GLOBAL: resolves libparsmurf_b200.so for the host library
+        if not os.path.exists(_capi.HOST_LIB_PATH):
+            raise ImportError("parsmurf_b200: %s is missing -- run __graft_entry__.build()" % _capi.HOST_LIB_PATH)
+        L = C.CDLL(_capi.HOST_LIB_PATH)
+        L.psmh_cv_run.argtypes = [vp, C.c_int, u32, u32, u32p, u32p] + [u32] * 8 + [C.c_int, vp, C.c_int, C.c_int, u32, u32, REDUCE_FN, vp, u64,
+                                  C.c_int, dp, dp, dp, dp, dp, u64p, u64p, C.c_char_p, C.c_size_t]
+        L.psmh_rand_fill.argtypes = [u32, i32p, u64]
+        L.psmh_ttd_fold.argtypes = [u32p, u32p, u32, u32, u32, C.c_int64, u32p, u32p, u32p, u32p, u32p]
+        L.psmh_config_parse.argtypes = [C.c_char_p, u32p, u32p, u32, C.c_char_p, C.c_size_t]
+        _hlib = L
+    return _hlib
+
+
+def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, device=0, stream=None, tie_mode=0, eval_fold_curves=True,
+           rank=0, world=1, reduce=None, batch_budget=0, profile=False, x_device_ptr=None, n=None, m=None):
+    """Run the whole CV on one GPU (or this rank's share of the partitions when world > 1).
+
+    x: host row-major float64 [n][m+1] (label column 1.0/2.0), or None with x_device_ptr/n/m for a dataset already in HBM.
+    folds: per-example fold ids, or None for the reference's random stratified folds.
+    reduce(dev_ptr, count): sums `count` float64 at device pointer `dev_ptr` across ranks in place (world > 1).
+    Returns dict(class1, class2, auroc, auprc, fold_metrics, kernel_ms, kernel_launches, stats)."""
+    L = hlib()
+    if x is not None:
+        assert x.dtype == np.float64 and x.flags.c_contiguous
+        n, m = x.shape[0], x.shape[1] - 1
+        xptr, isdev = x.ctypes.data, 0
+    else:
+        xptr, isdev = x_device_ptr, 1
+    labels = np.ascontiguousarray(labels, np.uint32)
+    folds = None if folds is None else np.ascontiguousarray(folds, np.uint32)
+    c1 = np.zeros(n); c2 = np.zeros(n); met = np.zeros(2); fm = np.zeros((nFolds, 2))
+    kms = np.zeros(len(KERNEL_CLASSES)); kl = np.zeros(len(KERNEL_CLASSES), np.uint64); st = np.zeros(3, np.uint64)
+    err = C.create_string_buffer(512)
+
+    def _cb(user, ptr, count):
+        try:
+            reduce(ptr, count)
+            return 0
+        except Exception as e:   # never unwind through C
+            print("reduce callback failed:", e)
+            return 1
+    cb = REDUCE_FN(_cb) if reduce is not None else REDUCE_FN()
+    rc = L.psmh_cv_run(vp(xptr), isdev, n, m, _p(labels, u32p), _p(folds, u32p), nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, device,
+                       vp(stream) if stream else None, tie_mode, int(eval_fold_curves), rank, world, cb, None, batch_budget, int(profile),
+                       _p(c1, dp), _p(c2, dp), _p(met, dp), _p(fm, dp), _p(kms, dp), _p(kl, u64p), _p(st, u64p), err, 512)
+    if rc != 0:
+        raise PsmError(rc, err.value.decode())
+    return dict(class1=c1, class2=c2, auroc=float(met[0]), auprc=float(met[1]), fold_metrics=fm,
+                kernel_ms={k_: float(kms[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
+                kernel_launches={k_: int(kl[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
+                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2])))
+
+
+def ttd_fold(labels, folds, nFolds, fold, fold_to_jump=-1):
+    L = hlib()
+    labels = np.ascontiguousarray(labels, np.uint32)
+    folds = None if folds is None else np.ascontiguousarray(folds, np.uint32)
+    s = np.zeros(4, np.uint32)
+    rc = L.psmh_ttd_fold(_p(labels, u32p), _p(folds, u32p), len(labels), nFolds, fold, fold_to_jump, _p(s, u32p), None, None, None, None)
+    if rc:
+        raise PsmError(rc, "ttd_fold")
+    a = [np.zeros(int(v), np.uint32) for v in s]
+    L.psmh_ttd_fold(_p(labels, u32p), _p(folds, u32p), len(labels), nFolds, fold, fold_to_jump, _p(s, u32p), *[_p(v, u32p) for v in a])
+    return dict(trngPos=a[0], trngNeg=a[1], testPos=a[2], testNeg=a[3])
+
+
+def rand_fill(seed, count):
+    out = np.zeros(count, np.int32)
+    hlib().psmh_rand_fill(seed, _p(out, i32p), count)
+    return out
+
+
+def config_parse(text):
+    out = np.zeros(10, np.uint32); grid = np.zeros((4096, 6), np.uint32); err = C.create_string_buffer(512)
+    rc = hlib().psmh_config_parse(text.encode(), _p(out, u32p), _p(grid, u32p), 4096, err, 512)
+    if rc:
+        raise PsmError(rc, err.value.decode())
+    keys = ["nFolds", "seed", "wmode", "woptimiz", "gridSize", "ensThrd", "rfThrd", "simulate", "n", "m"]
+    d = {k_: int(out[i]) for i, k_ in enumerate(keys)}
+    d["grid"] = [dict(zip(["nParts", "fp", "ratio", "k", "nTrees", "mtry"], [int(v) for v in row])) for row in grid[: d["gridSize"]]]
+    return d
