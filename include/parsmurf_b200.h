@@ -68,6 +68,11 @@ int psm_fold_knn_set(psm_ctx* ctx, const int32_t* nnIdx, uint32_t localk);   /* 
  *      (P*fp*(m+1) per partition; src/samplerKNN.cpp:95,99). ------------------------------------------------ */
 int psm_batch_begin(psm_ctx* ctx, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t p0, uint32_t p1);
 int psm_batch_assemble(psm_ctx* ctx, const int32_t* draws_host, uint64_t ndraws);
+/* Same, but the draws are generated ON THE DEVICE by replaying glibc's rand() (TYPE_3 additive-feedback generator)
+ * from `window31`: the generator's last 31 state words in chronological order (oldest first), positioned at the first
+ * draw of partition p0.  psm_glibc_jump advances such a window by n draws on the host in O(log n). */
+int psm_batch_assemble_glibc(psm_ctx* ctx, const uint32_t* window31);
+int psm_glibc_jump(uint32_t* window31, uint64_t n);
 /* sizes[3] = {trngPos, trngNeg, Ntr}; out = row-major [Ntr][m+1] like Sampler::trngData (may be NULL) */
 int psm_batch_get_training(psm_ctx* ctx, uint32_t p, uint32_t* sizes, double* out_rowmajor);
 

@@ -66,6 +66,9 @@ def lib():
         L.psm_fold_knn_set.argtypes = [vp, i32p, u32]
         L.psm_batch_begin.argtypes = [vp, u32, u32, u32, u32, u32]
         L.psm_batch_assemble.argtypes = [vp, i32p, u64]
+        L.psm_batch_assemble_glibc.argtypes = [vp, u32p]
+        L.psm_glibc_jump.argtypes = [u32p, u64]
+        L.psm_batch_capacity.argtypes = [vp, u32, u32, u32, u32, u32, u32, u32p]
         L.psm_batch_get_training.argtypes = [vp, u32, u32p, dp]
         L.psm_batch_train.argtypes = [vp, u32, u32, u32p, u64p, u32p, u32]
         L.psm_batch_tree_nodes.argtypes = [vp, u32, u32, u64p]
@@ -83,6 +86,24 @@ def lib():
         L.psm_stats_get.argtypes = [vp, u64p, u64p, u64p]
         _lib = L
     return _lib
+
+
+def glibc_jump(window31, n):
+    """advance a chronological 31-word glibc rand() window by n draws (host, O(log n))"""
+    w = np.ascontiguousarray(window31, np.uint32).copy()
+    lib().psm_glibc_jump(w.ctypes.data_as(u32p), n)
+    return w
+
+
+def glibc_initial_window(seed=1):
+    """window of a freshly seeded glibc generator (srand(seed)): r[313..343] in the linear indexing of random_r.c"""
+    r = [seed if seed else 1]
+    for i in range(1, 31):
+        r.append((16807 * r[i - 1]) % 2147483647)
+    r += r[0:3]
+    for i in range(34, 344):
+        r.append((r[i - 31] + r[i - 3]) & 0xFFFFFFFF)
+    return np.array(r[344 - 31:344], np.uint32)
 
 
 def _p(a, t):
@@ -162,6 +183,16 @@ class Context:
     def batch_assemble(self, draws):
         draws = None if draws is None else np.ascontiguousarray(draws, np.int32)
         self._ck(self.L.psm_batch_assemble(self.h, _p(draws, i32p), 0 if draws is None else draws.size))
+
+    def batch_assemble_glibc(self, window31):
+        w = np.ascontiguousarray(window31, np.uint32)
+        assert w.size == 31
+        self._ck(self.L.psm_batch_assemble_glibc(self.h, _p(w, u32p)))
+
+    def batch_capacity(self, nParts, fp, ratio, nTrees, mtry, p0):
+        c = u32()
+        self._ck(self.L.psm_batch_capacity(self.h, nParts, fp, ratio, nTrees, mtry, p0, C.byref(c)))
+        return c.value
 
     def batch_get_training(self, p):
         sizes = np.zeros(3, np.uint32)

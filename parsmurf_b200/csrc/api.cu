@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -56,15 +57,16 @@ struct psm_ctx {
 	uint32_t nParts = 0, fp = 0, ratio = 0, p0 = 0, p1 = 0, nB = 0, maxNtr = 0;
 	std::vector<PartDesc> hParts;
 	uint64_t totalD = 0, totalS = 0, totalDraws = 0;
-	DevBuf dParts, dD, dS, dKeysA, dKeysB, dValsA, dValsB, dDraws, dErr;
+	DevBuf dParts, dD, dS, dKeysA, dKeysB, dValsA, dValsB, dDraws, dErr, dRandScratch;
 
 	// train
 	uint32_t T = 0, mtry = 0;
 	TrainArgs A;
-	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dFlags, dItems0, dItems1, dCand, dRes, dDec, dCounters, dStats, dSeeds,
+	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dFlags, dFlagBits, dItems0, dItems1, dCand, dRes, dDec, dCounters, dStats, dSeeds,
 	    dInjBoot, dInjBootOff, dInjCand;
 	uint32_t* hCounters = nullptr;   // pinned
 	uint64_t statSplitBytes = 0, statNodes = 0, statLevels = 0;
+	uint32_t maxNodes = 0;
 
 	// predict
 	DevBuf dPredScratch;
@@ -170,8 +172,8 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf* bufs[] = {&ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dClass12,
-	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr,
-	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dFlags, &ctx->dItems0, &ctx->dItems1,
+	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
+	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dFlags, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
 	                  &ctx->dInjCand, &ctx->dPredScratch, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
 	                  &ctx->cScores, &ctx->cKeysA, &ctx->cKeysB, &ctx->cValsA, &ctx->cValsB, &ctx->cHist};
@@ -328,18 +330,27 @@ int psm_batch_begin(psm_ctx* ctx, uint32_t nParts, uint32_t fp, uint32_t ratio, 
 	return PSM_OK;
 }
 
-int psm_batch_assemble(psm_ctx* ctx, const int32_t* draws_host, uint64_t ndraws) {
+static int assemble_common(psm_ctx* ctx, const int32_t* draws_host, uint64_t ndraws, const uint32_t* window31) {
 	if (!ctx || !ctx->batchOpen) return fail(ctx, PSM_E_ARG, "batch_assemble: no open batch");
 	if (ctx->fp > 0) {
 		if (!ctx->haveKnn) return fail(ctx, PSM_E_ARG, "batch_assemble: run psm_fold_knn first");
 		if (ctx->localk < 2) return fail(ctx, PSM_E_LOCALK, "batch_assemble: min(k,P) < 2");
-		if (!draws_host || ndraws < ctx->totalDraws) return fail(ctx, PSM_E_ARG, "batch_assemble: too few SMOTE draws");
+		if (!window31 && (!draws_host || ndraws < ctx->totalDraws)) return fail(ctx, PSM_E_ARG, "batch_assemble: too few SMOTE draws");
 	}
 	CU(cudaSetDevice(ctx->device));
 	ENSURE(ctx->dD, std::max<uint64_t>(8, ctx->totalD * 8));
 	ENSURE(ctx->dErr, 16);
 	ENSURE(ctx->dDraws, std::max<uint64_t>(4, ctx->totalDraws * 4));
-	if (ctx->totalDraws) CU(cudaMemcpyAsync(ctx->dDraws.p, draws_host, ctx->totalDraws * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (ctx->totalDraws) {
+		if (window31) {
+			ENSURE(ctx->dRandScratch, (61 + 64 * 31) * 4);
+			ProfScope ps(ctx, K_GATHER, 1);
+			if (launch_glibc_rand_fill(window31, ctx->totalDraws, ctx->dRandScratch.as<uint32_t>(), ctx->dDraws.as<int32_t>(), ctx->stream))
+				return fail(ctx, PSM_E_CUDA, "batch_assemble: rand replay launch failed");
+		} else {
+			CU(cudaMemcpyAsync(ctx->dDraws.p, draws_host, ctx->totalDraws * 4, cudaMemcpyHostToDevice, ctx->stream));
+		}
+	}
 	CU(cudaMemsetAsync(ctx->dErr.p, 0, 16, ctx->stream));
 	{
 		ProfScope ps(ctx, K_ASSEMBLE, 1);
@@ -353,6 +364,19 @@ int psm_batch_assemble(psm_ctx* ctx, const int32_t* draws_host, uint64_t ndraws)
 	CU(cudaStreamSynchronize(ctx->stream));   // also keeps `draws_host` borrowed only for the call
 	if (herr) return fail(ctx, PSM_E_NEIGHBOUR, "batch_assemble: SMOTE needs a neighbour that does not exist (duplicate positives)");
 	ctx->assembled = true; ctx->trained = false;
+	return PSM_OK;
+}
+
+int psm_batch_assemble(psm_ctx* ctx, const int32_t* draws_host, uint64_t ndraws) { return assemble_common(ctx, draws_host, ndraws, nullptr); }
+
+int psm_batch_assemble_glibc(psm_ctx* ctx, const uint32_t* window31) {
+	if (!window31) return fail(ctx, PSM_E_ARG, "batch_assemble_glibc: null window");
+	return assemble_common(ctx, nullptr, 0, window31);
+}
+
+int psm_glibc_jump(uint32_t* window31, uint64_t n) {
+	if (!window31) return PSM_E_ARG;
+	glibc_window_jump(window31, n);
 	return PSM_OK;
 }
 
@@ -378,7 +402,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	if (!forest_seeds && !(inj_bootstrap && inj_cand)) return fail(ctx, PSM_E_ARG, "batch_train: forest_seeds required unless all draws are injected");
 	if (tree_smem_bytes(ctx->m, mtry) > 200 * 1024) return fail(ctx, PSM_E_LIMIT, "batch_train: m too large for the candidate generator");
 	CU(cudaSetDevice(ctx->device));
-	const uint32_t m = ctx->m, nB = ctx->nB, stride = ctx->maxNtr;
+	const uint32_t m = ctx->m, nB = ctx->nB, stride = (ctx->maxNtr + 3) & ~3u;   // multiple of 4: keeps every list 16-byte aligned
 	const uint32_t nTrees = nB * T;
 	const uint32_t NC = 2 * stride + 2;
 	const uint64_t itemCap64 = (uint64_t)nTrees * (stride / 11 + 2);
@@ -389,13 +413,16 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	ENSURE(ctx->dS, ctx->totalS * 8);
 	ENSURE(ctx->dKeysA, ctx->totalS * 8); ENSURE(ctx->dKeysB, ctx->totalS * 8);
 	ENSURE(ctx->dValsA, ctx->totalS * 4); ENSURE(ctx->dValsB, ctx->totalS * 4);
-	const size_t listBytes = (size_t)nTrees * m * stride * 8;
+	int entry32 = (ctx->maxNtr <= Ent<uint32_t>::kMaxRowsE && !getenv("PSM_FORCE_ENTRY64")) ? 1 : 0;
+	size_t listBytes = (size_t)nTrees * m * stride * (entry32 ? 4 : 8);
 	ENSURE(ctx->dLists0, listBytes); ENSURE(ctx->dLists1, listBytes);
 	ENSURE(ctx->dInbag, (size_t)nTrees * stride * 4);
 	ENSURE(ctx->dMt, (size_t)nTrees * 312 * 8);
 	ENSURE(ctx->dTs, (size_t)nTrees * sizeof(TreeState));
 	ENSURE(ctx->dNodes, (size_t)nTrees * NC * sizeof(Node16));
 	ENSURE(ctx->dFlags, (size_t)nTrees * stride);
+	const uint32_t flagWords = (stride + 31) / 32;
+	ENSURE(ctx->dFlagBits, (size_t)nTrees * flagWords * 4);
 	ENSURE(ctx->dItems0, (size_t)itemCap * sizeof(Item)); ENSURE(ctx->dItems1, (size_t)itemCap * sizeof(Item));
 	ENSURE(ctx->dCand, (size_t)itemCap * mtry * 4);
 	ENSURE(ctx->dRes, (size_t)itemCap * mtry * sizeof(SearchRes));
@@ -408,9 +435,10 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	A.nTrees = nTrees; A.T = T; A.m = m; A.mtry = mtry; A.stride = stride; A.NC = NC; A.itemCap = itemCap;
 	A.injCandNodes = inj_cand ? inj_cand_nodes : 0; A.listBuf = 0;
 	A.parts = ctx->dParts.as<PartDesc>(); A.Dall = ctx->dD.as<double>(); A.Sall = ctx->dS.as<entry_t>();
-	A.lists[0] = ctx->dLists0.as<entry_t>(); A.lists[1] = ctx->dLists1.as<entry_t>();
+	A.lists[0] = ctx->dLists0.p; A.lists[1] = ctx->dLists1.p; A.entry32 = entry32;
 	A.inbag = ctx->dInbag.as<uint32_t>(); A.mt = ctx->dMt.as<unsigned long long>(); A.ts = ctx->dTs.as<TreeState>();
 	A.nodes = ctx->dNodes.as<Node16>(); A.flags = ctx->dFlags.as<unsigned char>();
+	A.flagBits = ctx->dFlagBits.as<uint32_t>(); A.flagWords = flagWords;
 	A.items[0] = ctx->dItems0.as<Item>(); A.items[1] = ctx->dItems1.as<Item>();
 	A.cand = ctx->dCand.as<uint32_t>(); A.res = ctx->dRes.as<SearchRes>(); A.dec = ctx->dDec.as<SplitDec>();
 	A.counters = ctx->dCounters.as<uint32_t>(); A.stats = ctx->dStats.as<unsigned long long>();
@@ -454,6 +482,20 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		ProfScope ps(ctx, K_LISTS, 1);
 		launch_build_lists(A, s);
 	}
+	if (entry32) {
+		// the compact 4-byte entries hold multiplicities up to 15; fall back to the 8-byte layout if a tree exceeds that
+		CU(cudaMemcpyAsync(ctx->hCounters, A.counters, CNT_COUNT * 4, cudaMemcpyDeviceToHost, s));
+		CU(cudaStreamSynchronize(s));
+		if (ctx->hCounters[CNT_ERROR] & ERR_COUNT_LIMIT) {
+			entry32 = 0;
+			listBytes = (size_t)nTrees * m * stride * 8;
+			ENSURE(ctx->dLists0, listBytes); ENSURE(ctx->dLists1, listBytes);
+			A.lists[0] = ctx->dLists0.p; A.lists[1] = ctx->dLists1.p; A.entry32 = 0;
+			CU(cudaMemsetAsync(A.counters, 0, CNT_COUNT * 4, s));
+			ProfScope ps(ctx, K_LISTS, 1);
+			launch_build_lists(A, s);
+		}
+	}
 	{
 		ProfScope ps(ctx, K_FINALIZE, 1);
 		if (launch_init_trees(A, s)) return fail(ctx, PSM_E_CUDA, "batch_train: cannot configure shared memory");
@@ -473,10 +515,26 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		if (nItems == 0) break;
 		if (nItems > itemCap) return fail(ctx, PSM_E_OVERFLOW, "batch_train: work-item pool overflow");
 		CU(cudaMemsetAsync(A.counters + CNT_NEXT_ITEMS, 0, 4, s));
+		const bool trace = getenv("PSM_TRACE_LEVELS") != nullptr;
+		cudaEvent_t tev[5];
+		if (trace) for (auto& e : tev) cudaEventCreate(&e);
+		if (trace) cudaEventRecord(tev[0], s);
 		{ ProfScope ps(ctx, K_SEARCH, 1); launch_split_search(A, nItems, buf, s); }
-		{ ProfScope ps(ctx, K_SELECT, 1); launch_split_select(A, nItems, buf, s); }
+		if (trace) cudaEventRecord(tev[1], s);
+		{ ProfScope ps(ctx, K_SELECT, 2); launch_split_select(A, nItems, buf, s); launch_pack_flags(A, s); }
+		if (trace) cudaEventRecord(tev[2], s);
 		{ ProfScope ps(ctx, K_FINALIZE, 1); launch_level_finalize(A, buf, s); }
+		if (trace) cudaEventRecord(tev[3], s);
 		{ ProfScope ps(ctx, K_PARTITION, 1); launch_partition_lists(A, nItems, buf, s); }
+		if (trace) {
+			cudaEventRecord(tev[4], s);
+			cudaStreamSynchronize(s);
+			float t[4];
+			for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
+			fprintf(stderr, "[psm level %3llu] items %7u  search %8.1f us  select %7.1f us  finalize %7.1f us  partition %8.1f us\n",
+			        (unsigned long long)levels, nItems, t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3);
+			for (auto& e : tev) cudaEventDestroy(e);
+		}
 		CU(cudaGetLastError());
 		buf ^= 1; A.listBuf ^= 1; levels++;
 	}
@@ -486,6 +544,13 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	ctx->statSplitBytes += hs[STAT_SPLIT_BYTES];
 	ctx->statNodes += hs[STAT_NODES] + nTrees;
 	ctx->statLevels += levels;
+	{   // largest tree of the batch: sizes the shared-memory tree buffers of the predict kernel
+		std::vector<TreeState> hts(nTrees);
+		CU(cudaMemcpyAsync(hts.data(), A.ts, (size_t)nTrees * sizeof(TreeState), cudaMemcpyDeviceToHost, s));
+		CU(cudaStreamSynchronize(s));
+		ctx->maxNodes = 0;
+		for (const TreeState& t : hts) ctx->maxNodes = std::max(ctx->maxNodes, t.nNodes);
+	}
 	ctx->trained = true;
 	return PSM_OK;
 }
@@ -546,7 +611,7 @@ int psm_batch_predict_accumulate(psm_ctx* ctx, uint32_t nPartsTotal) {
 	ENSURE(ctx->dPredScratch, (size_t)ctx->nB * 2 * ctx->Nte * 8);
 	{
 		ProfScope ps(ctx, K_PREDICT, 2);
-		if (launch_predict(ctx->x, ctx->m, ctx->dTest.as<uint32_t>(), ctx->Nte, ctx->A.nodes, ctx->A.NC, ctx->nB, ctx->T,
+		if (launch_predict(ctx->x, ctx->m, ctx->dTest.as<uint32_t>(), ctx->Nte, ctx->A.nodes, ctx->A.NC, ctx->A.ts, ctx->maxNodes, ctx->nB, ctx->T,
 		                   ctx->dPredScratch.as<double>(), ctx->stream))
 			return fail(ctx, PSM_E_CUDA, "predict_accumulate: cannot configure shared memory");
 		launch_accumulate(ctx->dPredScratch.as<double>(), ctx->Nte, ctx->nB, 1.0 / (double)nPartsTotal, ctx->dClass12.as<double>(), ctx->stream);

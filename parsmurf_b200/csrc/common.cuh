@@ -25,6 +25,28 @@ __host__ __device__ __forceinline__ entry_t e_make(uint32_t row, uint32_t rank, 
 	return (entry_t)row | ((entry_t)rank << 24) | ((entry_t)count << 48) | ((entry_t)neg << 63);
 }
 
+// Entry codecs.  E = unsigned long long is the general layout above.  E = uint32_t is the compact layout used when a
+// partition's training matrix has <= 16384 rows and no bootstrap multiplicity exceeds 15 (all BASELINE configs with
+// m = 26): [31:28] multiplicity | [27:14] dense rank | [13:0] row; the label is implied by the row (rows below nPosOut
+// are positives).  Halving the entry halves the HBM traffic of split search and of the per-level list partition.
+template <typename E> struct Ent;
+template <> struct Ent<unsigned long long> {
+	static constexpr uint32_t kMaxRowsE = kMaxRows, kMaxCountE = kMaxCount;
+	__host__ __device__ static __forceinline__ uint32_t row(unsigned long long e) { return e_row(e); }
+	__host__ __device__ static __forceinline__ uint32_t rank(unsigned long long e) { return e_rank(e); }
+	__host__ __device__ static __forceinline__ uint32_t count(unsigned long long e) { return e_count(e); }
+	__host__ __device__ static __forceinline__ uint32_t neg(unsigned long long e, uint32_t) { return e_neg(e); }
+	__host__ __device__ static __forceinline__ unsigned long long make(uint32_t r, uint32_t k, uint32_t c, uint32_t n) { return e_make(r, k, c, n); }
+};
+template <> struct Ent<uint32_t> {
+	static constexpr uint32_t kMaxRowsE = 1u << 14, kMaxCountE = 15;
+	__host__ __device__ static __forceinline__ uint32_t row(uint32_t e) { return e & 0x3FFFu; }
+	__host__ __device__ static __forceinline__ uint32_t rank(uint32_t e) { return (e >> 14) & 0x3FFFu; }
+	__host__ __device__ static __forceinline__ uint32_t count(uint32_t e) { return e >> 28; }
+	__host__ __device__ static __forceinline__ uint32_t neg(uint32_t e, uint32_t nPosOut) { return (e & 0x3FFFu) >= nPosOut ? 1u : 0u; }
+	__host__ __device__ static __forceinline__ uint32_t make(uint32_t r, uint32_t k, uint32_t c, uint32_t) { return r | (k << 14) | (c << 28); }
+};
+
 // Packed 16-byte forest node, the only thing prediction reads:
 //   internal: a = split threshold (f64), b = feature id (low 32) | left child id (high 32, >= 1); right = left + 1
 //   leaf:     a = fraction of class 0 (positive), b = bits(fraction of class 1) with the sign bit set

@@ -1,0 +1,123 @@
+// Device replay of glibc rand() -- the stream SMOTE draws from (reference src/samplerKNN.cpp:95,99; the generator is
+// glibc stdlib/random_r.c TYPE_3: r[i] = r[i-3] + r[i-31] (mod 2^32), output r[i] >> 1).
+//
+// The recurrence is linear over Z/2^32, so the stream can be entered anywhere: x^n mod (x^31 - x^28 - 1) gives the
+// coefficients c_j with r[t+n] = sum_j c_j r[t+j].  Each thread jumps to the start of its own 1024-draw chunk by
+// multiplying precomputed powers x^(1024*2^j), rebuilds the 31-word window there and then steps the plain recurrence.
+// This removes the host-side generation of P*fp*(m+1) draws per partition (32M draws per CV at BASELINE configs[1]).
+#include "kernels.cuh"
+
+#include <cstring>
+#include <vector>
+
+namespace psm {
+
+constexpr int GR_DEG = 31;
+constexpr uint32_t GR_CHUNK = 1024;
+
+// ---- polynomial arithmetic mod x^31 - x^28 - 1 over Z/2^32 (host and device) ----
+__host__ __device__ inline void gr_polymul(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+	uint32_t d[2 * GR_DEG - 1];
+	for (int k = 0; k < 2 * GR_DEG - 1; k++) d[k] = 0;
+	for (int i = 0; i < GR_DEG; i++) {
+		const uint32_t ai = a[i];
+		if (ai == 0) continue;
+		for (int j = 0; j < GR_DEG; j++) d[i + j] += ai * b[j];
+	}
+	for (int k = 2 * GR_DEG - 2; k >= GR_DEG; k--) {   // x^k = x^(k-3) + x^(k-31)
+		d[k - 3] += d[k];
+		d[k - GR_DEG] += d[k];
+	}
+	for (int k = 0; k < GR_DEG; k++) out[k] = d[k];
+}
+
+// x^n mod charpoly
+static void gr_xpow(uint64_t n, uint32_t* out) {
+	uint32_t result[GR_DEG] = {0}, base[GR_DEG] = {0}, tmp[GR_DEG];
+	result[0] = 1;
+	base[1] = 1;
+	while (n) {
+		if (n & 1) { gr_polymul(result, base, tmp); memcpy(result, tmp, sizeof(tmp)); }
+		n >>= 1;
+		if (n) { gr_polymul(base, base, tmp); memcpy(base, tmp, sizeof(tmp)); }
+	}
+	memcpy(out, result, sizeof(result));
+}
+
+// extend a chronological window w[0..30] (w[30] newest) to 61 values by stepping the recurrence
+static void gr_extend(const uint32_t* w31, uint32_t* w61) {
+	memcpy(w61, w31, GR_DEG * 4);
+	for (int i = GR_DEG; i < 2 * GR_DEG - 1; i++) w61[i] = w61[i - 3] + w61[i - GR_DEG];
+}
+
+// advance a chronological window by n draws (host helper, exported through the C ABI as psm_glibc_jump)
+void glibc_window_jump(uint32_t* w31, uint64_t n) {
+	if (n == 0) return;
+	uint32_t c[GR_DEG], w61[2 * GR_DEG - 1], nw[GR_DEG];
+	gr_xpow(n, c);
+	gr_extend(w31, w61);
+	for (int d = 0; d < GR_DEG; d++) {
+		uint32_t s = 0;
+		for (int j = 0; j < GR_DEG; j++) s += c[j] * w61[d + j];
+		nw[d] = s;
+	}
+	memcpy(w31, nw, sizeof(nw));
+}
+
+__global__ void __launch_bounds__(128) glibc_rand_fill_kernel(const uint32_t* __restrict__ w61, const uint32_t* __restrict__ jump /*[nj][31]*/,
+                                                               int nj, unsigned long long count, int32_t* __restrict__ out) {
+	const unsigned long long chunk = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long first = chunk * GR_CHUNK;
+	if (first >= count) return;
+	uint32_t q[GR_DEG], t[GR_DEG], pj[GR_DEG];
+	for (int k = 0; k < GR_DEG; k++) q[k] = 0;
+	q[0] = 1;                                              // x^0
+	for (int j = 0; j < nj; j++) {
+		if ((chunk >> j) & 1ull) {
+			for (int k = 0; k < GR_DEG; k++) pj[k] = jump[j * GR_DEG + k];
+			gr_polymul(q, pj, t);
+			for (int k = 0; k < GR_DEG; k++) q[k] = t[k];
+		}
+	}
+	uint32_t w[GR_DEG];                                    // window at the chunk start: r[first-31 .. first-1] relative to the stream
+	for (int d = 0; d < GR_DEG; d++) {
+		uint32_t s = 0;
+		for (int j = 0; j < GR_DEG; j++) s += q[j] * w61[d + j];
+		w[d] = s;
+	}
+	const unsigned long long n = (count - first < GR_CHUNK) ? (count - first) : GR_CHUNK;
+	int f = 0, r = GR_DEG - 3;                             // oldest at f, r = f - 3 (mod 31)
+	int32_t* o = out + first;
+	for (unsigned long long i = 0; i < n; i++) {
+		const uint32_t v = w[f] + w[r];
+		w[f] = v;
+		o[i] = (int32_t)(v >> 1);
+		f = (f + 1 == GR_DEG) ? 0 : f + 1;
+		r = (r + 1 == GR_DEG) ? 0 : r + 1;
+	}
+}
+
+// host side of the launch: fills `out` (device) with the next `count` rand() outputs of the stream whose chronological
+// window is w31; scratch = device buffer of at least (61 + 64*31) uint32
+int launch_glibc_rand_fill(const uint32_t* w31, unsigned long long count, uint32_t* scratchDev, int32_t* out, cudaStream_t s) {
+	if (count == 0) return 0;
+	const unsigned long long chunks = (count + GR_CHUNK - 1) / GR_CHUNK;
+	int nj = 0;
+	while ((1ull << nj) < chunks) nj++;
+	if (nj == 0) nj = 1;
+	std::vector<uint32_t> h(61 + (size_t)nj * GR_DEG);
+	gr_extend(w31, h.data());
+	uint32_t p[GR_DEG], tmp[GR_DEG];
+	gr_xpow(GR_CHUNK, p);
+	for (int j = 0; j < nj; j++) {
+		memcpy(&h[61 + (size_t)j * GR_DEG], p, sizeof(p));
+		gr_polymul(p, p, tmp);
+		memcpy(p, tmp, sizeof(p));
+	}
+	if (cudaMemcpyAsync(scratchDev, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+	if (cudaStreamSynchronize(s) != cudaSuccess) return -1;    // `h` is a local
+	glibc_rand_fill_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(scratchDev, scratchDev + 61, nj, count, out);
+	return 0;
+}
+
+}  // namespace psm

@@ -22,12 +22,15 @@ struct TrainArgs {
 	const PartDesc* parts;
 	const double* Dall;
 	const entry_t* Sall;
-	entry_t* lists[2];    // [tree][feature][stride]
+	void* lists[2];       // [tree][feature][stride] of entry_t (entry32 == 0) or uint32_t (entry32 == 1)
+	int entry32;
 	uint32_t* inbag;      // [tree][stride]
 	unsigned long long* mt;   // [tree][312]
 	TreeState* ts;
 	Node16* nodes;        // [tree][NC]
-	unsigned char* flags; // [tree][stride]
+	unsigned char* flags; // [tree][stride]   go-left flag per row, written by split_select
+	uint32_t* flagBits;   // [tree][flagWords] the same flags bit-packed for the partition kernel
+	uint32_t flagWords;
 	Item* items[2];
 	uint32_t* cand;       // [itemCap][mtry]
 	SearchRes* res;       // [itemCap][mtry]
@@ -56,10 +59,14 @@ int launch_init_trees(const TrainArgs& A, cudaStream_t s);
 void launch_split_search(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
 void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s);
+void launch_pack_flags(const TrainArgs& A, cudaStream_t s);
 void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
+// glibc_rand.cu
+void glibc_window_jump(uint32_t* w31, uint64_t n);
+int launch_glibc_rand_fill(const uint32_t* w31, unsigned long long count, uint32_t* scratchDev, int32_t* out, cudaStream_t s);
 // predict.cu
 int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_t Nte, const Node16* nodes, uint32_t NC,
-                   uint32_t nPartsBatch, uint32_t T, double* scratch, cudaStream_t s);
+                   const TreeState* ts, uint32_t maxNodes, uint32_t nPartsBatch, uint32_t T, double* scratch, cudaStream_t s);
 void launch_accumulate(const double* scratch, uint32_t Nte, uint32_t nPartsBatch, double divider, double* class12, cudaStream_t s);
 // curves.cu
 int launch_curves(const unsigned char* labelsSorted, uint64_t N, uint32_t totP, uint32_t totN, uint32_t* tpScratch,

@@ -78,6 +78,7 @@ __global__ void inbag_from_ids_kernel(TrainArgs A, const unsigned long long* __r
 
 // ------------------------------------------------------------------------------------------ per-tree lists
 // one warp per (tree, feature): filter the partition's sorted (rank,row) list by in-bag count.
+template <typename E>
 __global__ void __launch_bounds__(128) build_lists_kernel(TrainArgs A) {
 	const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (wid >= A.nTrees * A.m) return;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(128) build_lists_kernel(TrainArgs A) {
 	const int lane = lane_id();
 	const entry_t* S = A.Sall + pd.sOffset + (size_t)f * pd.Ntr;
 	const uint32_t* cnt = A.inbag + (size_t)tree * A.stride;
-	entry_t* out = A.lists[0] + ((size_t)tree * A.m + f) * A.stride;
+	E* out = reinterpret_cast<E*>(A.lists[0]) + ((size_t)tree * A.m + f) * A.stride;
 	uint32_t off = 0;
 	bool bad = false;
 	for (uint32_t b = 0; b < pd.Ntr; b += 32) {
@@ -96,9 +97,9 @@ __global__ void __launch_bounds__(128) build_lists_kernel(TrainArgs A) {
 		uint32_t row = e_row(e);
 		uint32_t c = (i < pd.Ntr) ? cnt[row] : 0;
 		bool keep = c > 0;
-		if (c > kMaxCount) bad = true;
+		if (c > Ent<E>::kMaxCountE) bad = true;
 		unsigned mk = __ballot_sync(0xffffffffu, keep);
-		if (keep) out[off + __popc(mk & lanemask_lt())] = e_make(row, e_rank(e), c, row >= pd.nPosOut ? 1u : 0u);
+		if (keep) out[off + __popc(mk & lanemask_lt())] = Ent<E>::make(row, e_rank(e), c, row >= pd.nPosOut ? 1u : 0u);
 		off += __popc(mk);
 	}
 	if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&A.counters[CNT_ERROR], ERR_COUNT_LIMIT);
@@ -250,48 +251,124 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 
 // ------------------------------------------------------------------------------------------ split search
 // one warp per (open node, candidate feature): stream the node's segment of that feature's list.
-__global__ void __launch_bounds__(128) split_search_kernel(TrainArgs A, uint32_t nItems, int buf) {
+// Each lane owns SS_IPL consecutive entries of a 32*SS_IPL-entry chunk (two 16-byte loads from a 16-byte aligned
+// base: odd segment starts are handled by shifting the chunk grid one entry to the left and masking), so the class
+// counts need ONE warp scan per chunk; the next chunk's loads are issued before the current chunk is evaluated.
+// The exact fp64 score (two IEEE divisions) is only evaluated for positions whose fp32 estimate could still beat the
+// lane's running best: estimate error < 1e-6 relative, filter margin 5e-6, so no winner is ever skipped.
+constexpr int SS_IPL = 4;
+
+__device__ __forceinline__ void ss_vec(const unsigned long long* p, unsigned long long (&e)[SS_IPL]) {
+	const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(p));
+	const ulonglong2 c = __ldg(reinterpret_cast<const ulonglong2*>(p + 2));
+	e[0] = a.x; e[1] = a.y; e[2] = c.x; e[3] = c.y;
+}
+__device__ __forceinline__ void ss_vec(const uint32_t* p, uint32_t (&e)[SS_IPL]) {
+	const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+	e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w;
+}
+template <typename E>
+__device__ __forceinline__ void ss_load(const E* __restrict__ base, uint32_t v, uint32_t lo, uint32_t hi, E (&e)[SS_IPL]) {
+	// entries v..v+3 of the aligned grid; valid iff lo <= index < hi
+	if (v >= lo && v + SS_IPL <= hi) {
+		ss_vec(base + v, e);
+	} else {
+#pragma unroll
+		for (int j = 0; j < SS_IPL; j++) e[j] = (v + j >= lo && v + j < hi) ? __ldg(base + v + j) : (E)0;
+	}
+}
+
+template <typename E>
+__global__ void __launch_bounds__(128, 8) split_search_kernel(TrainArgs A, uint32_t nItems, int buf) {
 	const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (wid >= nItems * A.mtry) return;
 	const uint32_t item = wid / A.mtry, c = wid % A.mtry;
 	const Item it = A.items[buf][item];
 	const uint32_t f = A.cand[(size_t)item * A.mtry + c];
 	const int lane = lane_id();
-	const entry_t* list = A.lists[A.listBuf] + ((size_t)it.tree * A.m + f) * A.stride + it.start;
-	const uint32_t cnt = it.cnt;
+	constexpr uint32_t APE = 16 / sizeof(E);                  // entries per 16 bytes
+	const uint32_t off = it.start % APE;                      // A.stride % 4 == 0, so list + start - off is 16-byte aligned
+	const uint32_t nPosOut = A.parts[it.tree / A.T].nPosOut;
+	const E* base = reinterpret_cast<const E*>(A.lists[A.listBuf]) + ((size_t)it.tree * A.m + f) * A.stride + (it.start - off);
+	const uint32_t lo = off, hi = it.cnt + off;                // valid index range in the aligned grid
 	const uint32_t n = it.npos + it.nneg;
 	uint32_t lp = 0, ln = 0;
 	double best = -1.0;
+	float wbound = 0.0f;                                      // warp-uniform: (best exact score of earlier chunks) * (1 - 4e-6)
 	uint32_t bpos = 0xFFFFFFFFu, blp = 0, bln = 0;
-	entry_t e = (lane < cnt) ? ld_nc_u64(list + lane) : 0;
-	for (uint32_t b = 0; b < cnt; b += 32) {
-		const uint32_t i = b + lane;
-		entry_t nxt = (i + 32 < cnt) ? ld_nc_u64(list + i + 32) : 0;
-		const uint32_t w = (i < cnt) ? e_count(e) : 0u;
-		const uint32_t neg = e_neg(e);
-		// inclusive warp scan of (positives, negatives) packed as two 32-bit lanes of one u64
-		unsigned long long pk = neg ? (unsigned long long)w : ((unsigned long long)w << 32);
+	E e[SS_IPL], nx[SS_IPL];
+	ss_load<E>(base, lane * SS_IPL, lo, hi, e);
+	for (uint32_t b = 0; b < hi; b += 32 * SS_IPL) {
+		const uint32_t v0 = b + lane * SS_IPL;
+		ss_load<E>(base, v0 + 32 * SS_IPL, lo, hi, nx);       // prefetch the next chunk
+		// lane-local inclusive prefix of (positives, negatives), packed hi/lo in one u64
+		unsigned long long pk[SS_IPL];
+		unsigned long long run = 0;
+#pragma unroll
+		for (int j = 0; j < SS_IPL; j++) {
+			const unsigned long long w = Ent<E>::count(e[j]);   // 0 for masked entries
+			run += Ent<E>::neg(e[j], nPosOut) ? w : (w << 32);
+			pk[j] = run;
+		}
+		unsigned long long inc = run;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
-			unsigned long long t = __shfl_up_sync(0xffffffffu, pk, o);
-			if (lane >= o) pk += t;
+			unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= o) inc += t;
 		}
-		const uint32_t lpi = lp + (uint32_t)(pk >> 32), lni = ln + (uint32_t)pk;
-		const uint32_t rk = e_rank(e);
-		uint32_t rnext = __shfl_down_sync(0xffffffffu, rk, 1);
-		const uint32_t rfirst = e_rank(__shfl_sync(0xffffffffu, nxt, 0));
-		if (lane == 31) rnext = rfirst;
-		if (i + 1 < cnt && rk != rnext) {
-			const uint32_t nl = lpi + lni, nr = n - nl;
-			const unsigned long long rp = it.npos - lpi, rn = it.nneg - lni;
-			const double sl = (double)((unsigned long long)lpi * lpi + (unsigned long long)lni * lni);
-			const double sr = (double)(rp * rp + rn * rn);
-			const double score = __dadd_rn(__ddiv_rn(sr, (double)nr), __ddiv_rn(sl, (double)nl));   // TreeProbability.cpp:337
-			if (score > best) { best = score; bpos = i; blp = lpi; bln = lni; }
+		const unsigned long long excl = inc - run;
+		const uint32_t rfirst_next_lane = Ent<E>::rank(__shfl_down_sync(0xffffffffu, e[0], 1));
+		const uint32_t rfirst_next_chunk = Ent<E>::rank(__shfl_sync(0xffffffffu, nx[0], 0));
+		// phase 1: fp32 estimate of the Gini proxy at every candidate position of the chunk (no divisions)
+		float est[SS_IPL];
+		float emax = 0.0f;
+#pragma unroll
+		for (int j = 0; j < SS_IPL; j++) {
+			const uint32_t v = v0 + j;
+			const uint32_t rk = Ent<E>::rank(e[j]);
+			const uint32_t rnext = (j + 1 < SS_IPL) ? Ent<E>::rank(e[(j + 1) % SS_IPL]) : (lane == 31 ? rfirst_next_chunk : rfirst_next_lane);
+			est[j] = -1.0f;
+			if (v >= lo && v + 1 < hi && rk != rnext) {
+				const unsigned long long tot = excl + pk[j];
+				const uint32_t lpi = lp + (uint32_t)(tot >> 32), lni = ln + (uint32_t)tot;
+				const uint32_t nl = lpi + lni, nr = n - nl;
+				const uint32_t rp = it.npos - lpi, rn = it.nneg - lni;
+				const float fl = (float)lpi, fn = (float)lni, frp = (float)rp, frn = (float)rn;
+				est[j] = __fdividef(fl * fl + fn * fn, (float)nl) + __fdividef(frp * frp + frn * frn, (float)nr);
+				emax = fmaxf(emax, est[j]);
+			}
 		}
-		const unsigned long long tot = __shfl_sync(0xffffffffu, pk, 31);
+		// Only positions whose estimate is within the estimate's error (< 1e-6 relative; margin 4e-6) of the best
+		// estimate of this chunk, or of the best exact score of earlier chunks, can be the arg-max: evaluate those
+		// exactly (two IEEE fp64 divisions, TreeProbability.cpp:337).  Estimates are >= 0, so their bit patterns order
+		// like unsigned integers and one redux gives the warp maximum.
+		const float cmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(emax)));
+		const float thr = fmaxf(cmax * 0.999996f, wbound);
+#pragma unroll
+		for (int j = 0; j < SS_IPL; j++) {
+			if (__any_sync(0xffffffffu, est[j] >= thr)) {
+				if (est[j] >= thr) {
+					const unsigned long long tot = excl + pk[j];
+					const uint32_t lpi = lp + (uint32_t)(tot >> 32), lni = ln + (uint32_t)tot;
+					const uint32_t nl = lpi + lni, nr = n - nl;
+					const uint32_t rp = it.npos - lpi, rn = it.nneg - lni;
+					const unsigned long long sli = (unsigned long long)lpi * lpi + (unsigned long long)lni * lni;
+					const unsigned long long sri = (unsigned long long)rp * rp + (unsigned long long)rn * rn;
+					const double score = __dadd_rn(__ddiv_rn((double)sri, (double)nr), __ddiv_rn((double)sli, (double)nl));
+					if (score > best) { best = score; bpos = v0 + j - off; blp = lpi; bln = lni; }
+				}
+			}
+		}
+		// warp-uniform bound for the following chunks: a later position must strictly beat the best exact score so far
+		{
+			const float bf = best > 0.0 ? __double2float_rd(best) : 0.0f;
+			const float wb = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(bf)));
+			wbound = wb * 0.999996f;
+		}
+		const unsigned long long tot = __shfl_sync(0xffffffffu, inc, 31);
 		lp += (uint32_t)(tot >> 32); ln += (uint32_t)tot;
-		e = nxt;
+#pragma unroll
+		for (int j = 0; j < SS_IPL; j++) e[j] = nx[j];
 	}
 	// arg-max over lanes: highest score, then lowest position (ascending value order, strict '>')
 #pragma unroll
@@ -309,6 +386,7 @@ __global__ void __launch_bounds__(128) split_search_kernel(TrainArgs A, uint32_t
 }
 
 // one warp per open node: pick the winning candidate, compute the threshold, mark rows going left
+template <typename E>
 __global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t nItems, int buf) {
 	const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (item >= nItems) return;
@@ -335,11 +413,11 @@ __global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t
 	}
 	const SearchRes r = A.res[(size_t)item * A.mtry + bc];
 	const uint32_t f = A.cand[(size_t)item * A.mtry + bc];
-	const entry_t* list = A.lists[A.listBuf] + ((size_t)it.tree * A.m + f) * A.stride + it.start;
+	const E* list = reinterpret_cast<const E*>(A.lists[A.listBuf]) + ((size_t)it.tree * A.m + f) * A.stride + it.start;
 	const PartDesc pd = A.parts[it.tree / A.T];
 	if (lane == 0) {
 		const double* col = A.Dall + pd.dOffset + (size_t)f * pd.Ntr;
-		const double lo = col[e_row(list[r.pos])], hi = col[e_row(list[r.pos + 1])];
+		const double lo = col[Ent<E>::row(list[r.pos])], hi = col[Ent<E>::row(list[r.pos + 1])];
 		double thr = __dmul_rn(__dadd_rn(lo, hi), 0.5);     // TreeProbability.cpp:348
 		if (thr == hi) thr = lo;                            // :353-355
 		Node16 v; v.a = thr; v.b = (unsigned long long)f;   // left child id is filled in by level_finalize
@@ -348,7 +426,7 @@ __global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t
 		A.dec[item] = d;
 	}
 	unsigned char* flags = A.flags + (size_t)it.tree * A.stride;
-	for (uint32_t i = lane; i < it.cnt; i += 32) flags[e_row(list[i])] = (i <= r.pos) ? 1 : 0;
+	for (uint32_t i = lane; i < it.cnt; i += 32) flags[Ent<E>::row(list[i])] = (i <= r.pos) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------ level finalize
@@ -457,6 +535,10 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 
 // ------------------------------------------------------------------------------------------ partition
 // one warp per (split node, feature): stable two-way partition of the node's segment into the other buffer.
+// Latency-bound (entry load -> flag lookup -> store), so four independent 32-entry chunks are in flight per warp.
+constexpr int PL_UNROLL = 4;
+
+template <typename E>
 __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint32_t nItems, int buf) {
 	const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (wid >= nItems * A.m) return;
@@ -467,22 +549,51 @@ __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint3
 	const int lane = lane_id();
 	const unsigned lt = lanemask_lt();
 	const size_t lo = ((size_t)it.tree * A.m + f) * A.stride + it.start;
-	const entry_t* src = A.lists[A.listBuf] + lo;
-	entry_t* dstL = A.lists[A.listBuf ^ 1] + lo;
-	entry_t* dstR = dstL + d.nleft;
-	const unsigned char* flags = A.flags + (size_t)it.tree * A.stride;
+	const E* src = reinterpret_cast<const E*>(A.lists[A.listBuf]) + lo;
+	E* dstL = reinterpret_cast<E*>(A.lists[A.listBuf ^ 1]) + lo;
+	E* dstR = dstL + d.nleft;
+	// go-left flags bit-packed per tree (pack_flags_kernel): a warp's 32 lookups touch ~10 cache lines instead of ~27
+	const uint32_t* fbits = A.flagBits + (size_t)it.tree * A.flagWords;
 	uint32_t offL = 0, offR = 0;
-	for (uint32_t b = 0; b < it.cnt; b += 32) {
-		const uint32_t i = b + lane;
-		const bool valid = i < it.cnt;
-		entry_t e = valid ? ld_nc_u64(src + i) : 0;
-		const bool gl = valid && flags[e_row(e)] != 0;
-		const unsigned mL = __ballot_sync(0xffffffffu, gl);
-		const unsigned mR = __ballot_sync(0xffffffffu, valid && !gl);
-		if (gl) dstL[offL + __popc(mL & lt)] = e;
-		else if (valid) dstR[offR + __popc(mR & lt)] = e;
-		offL += __popc(mL); offR += __popc(mR);
+	for (uint32_t b = 0; b < it.cnt; b += 32 * PL_UNROLL) {
+		E e[PL_UNROLL];
+		bool valid[PL_UNROLL], gl[PL_UNROLL];
+#pragma unroll
+		for (int k = 0; k < PL_UNROLL; k++) {
+			const uint32_t i = b + k * 32 + lane;
+			valid[k] = i < it.cnt;
+			e[k] = valid[k] ? __ldg(src + i) : (E)0;
+		}
+#pragma unroll
+		for (int k = 0; k < PL_UNROLL; k++) {
+			const uint32_t r = Ent<E>::row(e[k]);
+			gl[k] = valid[k] && ((__ldg(fbits + (r >> 5)) >> (r & 31u)) & 1u);
+		}
+#pragma unroll
+		for (int k = 0; k < PL_UNROLL; k++) {
+			const unsigned mL = __ballot_sync(0xffffffffu, gl[k]);
+			const unsigned mR = __ballot_sync(0xffffffffu, valid[k] && !gl[k]);
+			if (gl[k]) dstL[offL + __popc(mL & lt)] = e[k];
+			else if (valid[k]) dstR[offR + __popc(mR & lt)] = e[k];
+			offL += __popc(mL); offR += __popc(mR);
+		}
 	}
+}
+
+// 32 flag bytes -> one word, all trees of the batch
+__global__ void __launch_bounds__(256) pack_flags_kernel(TrainArgs A) {
+	const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= (size_t)A.nTrees * A.flagWords) return;
+	const uint32_t tree = (uint32_t)(w / A.flagWords), wi = (uint32_t)(w % A.flagWords);
+	const uint32_t* src = reinterpret_cast<const uint32_t*>(A.flags + (size_t)tree * A.stride) + (size_t)wi * 8;   // stride % 4 == 0
+	const uint32_t nw = A.stride / 4;
+	uint32_t bits = 0;
+#pragma unroll
+	for (int q = 0; q < 8; q++) {
+		const uint32_t v = (wi * 8 + q < nw) ? __ldg(src + q) : 0u;
+		bits |= ((v & 1u) | ((v >> 7) & 2u) | ((v >> 14) & 4u) | ((v >> 21) & 8u)) << (4 * q);
+	}
+	A.flagBits[w] = bits;
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -495,7 +606,8 @@ void launch_inbag_from_ids(const TrainArgs& A, const unsigned long long* ids, co
 }
 void launch_build_lists(const TrainArgs& A, cudaStream_t s) {
 	size_t warps = (size_t)A.nTrees * A.m;
-	build_lists_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A);
+	if (A.entry32) build_lists_kernel<uint32_t><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A);
+	else build_lists_kernel<unsigned long long><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A);
 }
 int launch_init_trees(const TrainArgs& A, cudaStream_t s) {
 	size_t smem = tree_smem_bytes(A.m, A.mtry);
@@ -508,17 +620,24 @@ int launch_init_trees(const TrainArgs& A, cudaStream_t s) {
 }
 void launch_split_search(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
 	size_t warps = (size_t)nItems * A.mtry;
-	split_search_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
+	if (A.entry32) split_search_kernel<uint32_t><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
+	else split_search_kernel<unsigned long long><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
 }
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
-	split_select_kernel<<<(nItems + 3) / 4, 128, 0, s>>>(A, nItems, buf);
+	if (A.entry32) split_select_kernel<uint32_t><<<(nItems + 3) / 4, 128, 0, s>>>(A, nItems, buf);
+	else split_select_kernel<unsigned long long><<<(nItems + 3) / 4, 128, 0, s>>>(A, nItems, buf);
+}
+void launch_pack_flags(const TrainArgs& A, cudaStream_t s) {
+	size_t words = (size_t)A.nTrees * A.flagWords;
+	pack_flags_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(A);
 }
 void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s) {
 	level_finalize_kernel<<<A.nTrees, 32, tree_smem_bytes(A.m, A.mtry), s>>>(A, buf);
 }
 void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
 	size_t warps = (size_t)nItems * A.m;
-	partition_lists_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
+	if (A.entry32) partition_lists_kernel<uint32_t><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
+	else partition_lists_kernel<unsigned long long><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
 }
 
 }  // namespace psm

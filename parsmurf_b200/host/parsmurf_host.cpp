@@ -9,8 +9,16 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <thread>
+
+#include <chrono>
 
 namespace parsmurf {
+
+double g_phase[PH_COUNT] = {0};
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+PhaseScope::PhaseScope(int p) : ph(p), t0(now_s()) {}
+PhaseScope::~PhaseScope() { g_phase[ph] += now_s() - t0; }
 
 // ------------------------------------------------------------------------------------------ GlibcRand
 // glibc stdlib/random_r.c: TYPE_3 (x^31 + x^3 + 1), seeded through the 16807 Park-Miller LCG, first 310 discarded
@@ -36,6 +44,17 @@ int32_t GlibcRand::rand() {
 }
 void GlibcRand::fill(int32_t* out, size_t count) {
 	for (size_t i = 0; i < count; i++) out[i] = rand();
+}
+void GlibcRand::window(uint32_t* out) const {
+	for (int i = 0; i < 31; i++) out[i] = (uint32_t)tbl[(f + i) % 31];
+}
+void GlibcRand::discard(uint64_t n) {
+	if (n < 64) { for (uint64_t i = 0; i < n; i++) rand(); return; }
+	uint32_t w[31];
+	window(w);
+	psm_glibc_jump(w, n);
+	for (int i = 0; i < 31; i++) tbl[i] = (int32_t)w[i];
+	f = 0; r = 28;
 }
 void GlibcRand::shuffle(uint32_t* a, size_t n) {
 	for (size_t i = 1; i < n; i++) {
@@ -90,6 +109,9 @@ void Folds::computeFolds() {
 // ------------------------------------------------------------------------------------------ TestTrainDivider
 void TestTrainDivider::build(uint32_t i, uint32_t cur, int64_t jump) {
 	const Folds* F = folds;
+	const uint32_t jumpPos = jump >= 0 ? F->nPos[jump] : 0, jumpNeg = jump >= 0 ? F->nNeg[jump] : 0;
+	testPosIdx[i].reserve(F->nPos[cur]); testNegIdx[i].reserve(F->nNeg[cur]);
+	trngPosIdx[i].reserve(F->totPos - F->nPos[cur] - jumpPos); trngNegIdx[i].reserve(F->totNeg - F->nNeg[cur] - jumpNeg);
 	for (uint32_t j = F->foldsIdx[cur]; j < F->foldsIdx[cur + 1]; j++)
 		(F->labels[F->folds[j]] < 1 ? testNegIdx[i] : testPosIdx[i]).push_back(F->folds[j]);
 	for (uint32_t kf = 0; kf < F->nFolds; kf++) {
@@ -102,10 +124,24 @@ void TestTrainDivider::build(uint32_t i, uint32_t cur, int64_t jump) {
 // src/testtraindivider.cpp:5-106
 TestTrainDivider::TestTrainDivider(const Folds* folds_, uint8_t wmode_, GlibcRand* rng) : folds(folds_), wmode(wmode_), nFolds(folds_->nFolds) {
 	testPosIdx.resize(nFolds); testNegIdx.resize(nFolds); trngPosIdx.resize(nFolds); trngNegIdx.resize(nFolds);
+	// Fold i's std::random_shuffle (:90) consumes trngNeg_i - 1 rand() calls, so its place in the one rand() stream is known
+	// up front; with the generator's jump-ahead the folds are built concurrently and still shuffle exactly like the
+	// sequential reference.
+	std::vector<uint64_t> off(nFolds + 1, 0);
 	for (uint32_t i = 0; i < nFolds; i++) {
-		build(i, i, -1);
-		rng->shuffle(trngNegIdx[i].data(), trngNegIdx[i].size());            // :90
+		uint64_t nneg = folds->totNeg - folds->nNeg[i];
+		off[i + 1] = off[i] + (nneg > 0 ? nneg - 1 : 0);
 	}
+	std::vector<std::thread> th;
+	for (uint32_t i = 0; i < nFolds; i++)
+		th.emplace_back([this, i, rng, &off]() {
+			GlibcRand local = *rng;
+			local.discard(off[i]);
+			build(i, i, -1);
+			local.shuffle(trngNegIdx[i].data(), trngNegIdx[i].size());
+		});
+	for (auto& t : th) t.join();
+	rng->discard(off[nFolds]);
 	if (wmode == MODE_TRAIN) { trngPosIdx[0] = testPosIdx[0]; trngNegIdx[0] = testNegIdx[0]; }   // :101-104
 	for (uint32_t i = 0; i < nFolds; i++) {
 		testPosNum.push_back(testPosIdx[i].size()); testNegNum.push_back(testNegIdx[i].size());
@@ -178,13 +214,25 @@ void SamplerKNN::setPartitionRange(uint32_t a, uint32_t b) {
 void SamplerKNN::sample() {
 	dev->ensureFold(part);
 	std::vector<int32_t> draws;
+	const uint64_t ndraws = (uint64_t)(p1 - p0) * posForOverSmpl * part->fp * (m + 1);   // src/samplerKNN.cpp:95,99 in partition order
 	if (part->fp > 0) {
 		dev->ensureKnn(k);                                                   // src/samplerKNN.cpp:60-93, once per fold
-		draws.resize((size_t)(p1 - p0) * posForOverSmpl * part->fp * (m + 1));
-		rng->fill(draws.data(), draws.size());                               // src/samplerKNN.cpp:95,99 in partition order
+		if (!deviceDraws) {
+			PhaseScope ps(PH_DRAWS);
+			draws.resize(ndraws);
+			rng->fill(draws.data(), draws.size());
+		}
 	}
+	PhaseScope ps(PH_ASSEMBLE);
 	dev->check(psm_batch_begin(dev->ctx, part->nPart, part->fp, part->ratio, p0, p1));
-	dev->check(psm_batch_assemble(dev->ctx, draws.empty() ? nullptr : draws.data(), draws.size()));
+	if (deviceDraws && ndraws) {
+		uint32_t w[31];
+		rng->window(w);
+		dev->check(psm_batch_assemble_glibc(dev->ctx, w));                   // the same stream, replayed on the GPU
+		rng->discard(ndraws);
+	} else {
+		dev->check(psm_batch_assemble(dev->ctx, draws.empty() ? nullptr : draws.data(), draws.size()));
+	}
 	uint32_t sz[3];
 	dev->check(psm_batch_get_training(dev->ctx, p0, sz, nullptr));
 	trngPos = sz[0]; trngNeg = sz[1]; lineLen = sz[2]; trngSize = trngPos + trngNeg;   // src/samplerKNN.cpp:8-13
@@ -241,7 +289,7 @@ void hyperSMURF::initStandard() {                                           // s
 	setGridParams(0);
 	seed = commonParams->seed; verboseLevel = commonParams->verboseLevel;
 	wmode = commonParams->wmode; woptimiz = commonParams->woptimiz; inInternalCV = false;
-	ttd.reset(new TestTrainDivider(foldManager, wmode, rng));
+	{ PhaseScope ps(PH_FOLDS_TTD); ttd.reset(new TestTrainDivider(foldManager, wmode, rng)); }
 	part.reset(new Partition(foldManager, ttd.get(), nPart, fp, ratio, mm, nn));
 }
 void hyperSMURF::initInternalCV(uint32_t jump) {                            // src/hyperSMURF.cpp:53-78
@@ -299,7 +347,7 @@ void hyperSMURF::smurfIt() {                                                // s
 		}
 		part->setFold(currentFold);                                         // :255
 		dev->invalidateFold();
-		dev->ensureFold(part.get());
+		{ PhaseScope ps(PH_FOLD_BEGIN); dev->ensureFold(part.get()); }
 
 		// this rank's contiguous chunk of partitions (src/MPIHelper.cpp:29-37)
 		uint32_t cnt = nPart / world + ((nPart % world) > rank ? 1 : 0);
@@ -307,12 +355,8 @@ void hyperSMURF::smurfIt() {                                                // s
 		for (uint32_t r2 = 0; r2 < rank; r2++) first += nPart / world + ((nPart % world) > r2 ? 1 : 0);
 		const uint32_t last = first + cnt;
 		const uint64_t perPartDraws = (uint64_t)part->trngPosNum * fp * (mm + 1);
-		std::vector<int32_t> skip;
-		auto skipDraws = [&](uint64_t count) {                              // keep the one SMOTE stream in partition order on every rank
-			skip.resize(1 << 16);
-			while (count) { size_t c = (size_t)std::min<uint64_t>(count, skip.size()); rng->fill(skip.data(), c); count -= c; }
-		};
-		skipDraws(perPartDraws * first);
+		auto skipDraws = [&](uint64_t count) { rng->discard(count); };      // keep the one SMOTE stream in partition order on every rank
+		{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * first); }
 		uint32_t cap = 1;
 		if (cnt) dev->check(psm_batch_capacity(dev->ctx, nPart, fp, ratio, numTrees, mtry, first, &cap));
 		for (uint32_t b0 = first; b0 < last; b0 += cap) {                   // the `#pragma omp for` over partitions (:257-261), as batches
@@ -321,22 +365,24 @@ void hyperSMURF::smurfIt() {                                                // s
 			samp.setPartitionRange(b0, b1);                                 // :276
 			samp.sample();                                                  // :277
 			rfRanger rf(dev, mm, false, &samp, numTrees, mtry, commonParams->rfThr, seed + currentFold * nPart);   // :273,302
-			rf.train(commonParams->rfVerbose);                              // :303
+			{ PhaseScope ps(PH_TRAIN); rf.train(commonParams->rfVerbose); }   // :303
 			samp.copyTestSet();                                             // :316
 			rfRanger rfTest(dev, mm, true, &samp, numTrees, mtry, commonParams->rfThr, 2 * (seed + currentFold * nPart));   // :330
-			rfTest.predict(commonParams->rfVerbose);                        // :331
+			{ PhaseScope ps(PH_PREDICT); rfTest.predict(commonParams->rfVerbose); dev->check(psm_sync(dev->ctx)); }   // :331
 			samp.accumulateAndDivideResInProbVect(nPart);                   // :344-346 (done on the device by predict)
 		}
-		skipDraws(perPartDraws * (nPart - last));
-		if (world > 1 && reduce) {                                          // src/hyperSMURF_MPI.cpp:594-618
+		{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * (nPart - last)); }
+		if (world > 1 && reduce) {
+			PhaseScope ps(PH_REDUCE);                                          // src/hyperSMURF_MPI.cpp:594-618
 			double* ptr = nullptr; uint32_t nte = 0;
 			dev->check(psm_fold_scores_devptr(dev->ctx, &ptr, &nte));
 			dev->check(psm_sync(dev->ctx));
 			reduce(ptr, 2ull * nte);
 		}
-		dev->check(psm_fold_scatter_host(dev->ctx, class1Prob, class2Prob));
+		{ PhaseScope ps(PH_SCATTER); dev->check(psm_fold_scatter_host(dev->ctx, class1Prob, class2Prob)); }
 
 		if (evalFoldCurves && !inInternalCV) {                              // :365-396 per-fold AUROC / AUPRC
+			PhaseScope ps(PH_CURVES);
 			std::vector<uint32_t> tl; std::vector<double> tp;
 			for (uint32_t i = 0; i < ttd->testPosNum[currentFold]; i++) { uint32_t v = ttd->testPosIdx[currentFold][i]; tl.push_back(y[v]); tp.push_back(class1Prob[v]); }
 			for (uint32_t i = 0; i < ttd->testNegNum[currentFold]; i++) { uint32_t v = ttd->testNegIdx[currentFold][i]; tl.push_back(y[v]); tp.push_back(class1Prob[v]); }
@@ -358,6 +404,7 @@ void hyperSMURF::smurfIt() {                                                // s
 		gridParams[idxInGridParams].auroc = c.evalAUROC_ok();
 		gridParams[idxInGridParams].auprc = c.evalAUPRC();
 	} else {                                                                // :484-488
+		PhaseScope ps(PH_CURVES);
 		Curves c(dev, y, class1Prob, curvesTieMode);
 		auroc = c.evalAUROC_ok();
 		auprc = c.evalAUPRC();
@@ -515,18 +562,25 @@ int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const 
                 uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed, int device, void* stream,
                 int tieMode, int evalFoldCurves, uint32_t rank, uint32_t world, psmh_reduce_fn reduce, void* reduceUser, uint64_t batchBudget,
                 int profile, double* class1, double* class2, double* metrics, double* foldMetrics, double* kernelMs, uint64_t* kernelLaunches,
-                uint64_t* stats3, char* errbuf, size_t errlen) {
+                uint64_t* stats3, double* phases, void* devHandle, char* errbuf, size_t errlen) {
 	using namespace parsmurf;
 	try {
-		Device dev(device, stream);
+		for (int i = 0; i < PH_COUNT; i++) g_phase[i] = 0;
+		double tSetup = now_s();
+		std::unique_ptr<Device> owned;
+		if (!devHandle) owned.reset(new Device(device, stream));
+		Device& dev = devHandle ? *(Device*)devHandle : *owned;
+		if (devHandle && stream) dev.check(psm_set_stream(dev.ctx, stream));
+		dev.check(psm_profile_reset(dev.ctx));
 		if (batchBudget) dev.check(psm_set_batch_budget(dev.ctx, batchBudget));
 		if (profile) dev.check(psm_profile_enable(dev.ctx, 1));
 		if (x_is_device) dev.attachDevice(x, n, m); else dev.upload(x, n, m);
+		g_phase[PH_SETUP] += now_s() - tSetup;
 		GlibcRand rng(1);
 		std::vector<uint32_t> y(labels, labels + n), ff;
 		if (foldAssign) ff.assign(foldAssign, foldAssign + n);
 		Folds folds(nFolds, n, y.data(), ff, foldAssign == nullptr, &rng);
-		folds.computeFolds();
+		{ PhaseScope ps(PH_FOLDS_TTD); folds.computeFolds(); }
 		CommonParams cp;
 		cp.nn = n; cp.mm = m; cp.nFolds = nFolds; cp.seed = seed; cp.wmode = MODE_CV; cp.woptimiz = OPT_NO;
 		std::vector<GridParams> gp(1);
@@ -540,6 +594,7 @@ int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const 
 		if (foldMetrics) for (uint32_t f = 0; f < nFolds; f++) { foldMetrics[2 * f] = smurfer.foldAuroc[f]; foldMetrics[2 * f + 1] = smurfer.foldAuprc[f]; }
 		if (kernelMs || kernelLaunches) dev.check(psm_profile_get(dev.ctx, kernelMs, kernelLaunches));
 		if (stats3) dev.check(psm_stats_get(dev.ctx, &stats3[0], &stats3[1], &stats3[2]));
+		if (phases) for (int i = 0; i < PH_COUNT; i++) phases[i] = g_phase[i];
 		return 0;
 	} catch (const parsmurf::Error& e) {
 		if (errbuf && errlen) { strncpy(errbuf, e.what(), errlen - 1); errbuf[errlen - 1] = 0; }
@@ -549,6 +604,12 @@ int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const 
 		return -1;
 	}
 }
+
+// a persistent GPU context (device buffers are reused across psmh_cv_run calls)
+void* psmh_device_create(int device, void* stream) {
+	try { return new parsmurf::Device(device, stream); } catch (...) { return nullptr; }
+}
+void psmh_device_destroy(void* h) { delete (parsmurf::Device*)h; }
 
 // host-only helpers exposed for the CPU tests (no GPU needed)
 void psmh_rand_fill(uint32_t seed, int32_t* out, uint64_t count) { parsmurf::GlibcRand g(seed); g.fill(out, count); }

@@ -43,6 +43,15 @@ struct CommonParams {
 	uint32_t minFold = (uint32_t)-1, maxFold = (uint32_t)-1;
 };
 
+// wall-clock phase accounting of the host layer (seconds since the last reset), for bench.py / profiling
+enum Phase { PH_SETUP = 0, PH_FOLDS_TTD, PH_FOLD_BEGIN, PH_DRAWS, PH_ASSEMBLE, PH_TRAIN, PH_PREDICT, PH_REDUCE, PH_SCATTER, PH_CURVES, PH_TEARDOWN, PH_COUNT };
+extern double g_phase[PH_COUNT];
+struct PhaseScope {
+	int ph; double t0;
+	explicit PhaseScope(int p);
+	~PhaseScope();
+};
+
 struct Error : std::runtime_error {
 	int code;
 	Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
@@ -57,6 +66,8 @@ public:
 	int32_t rand();
 	void fill(int32_t* out, size_t count);
 	void shuffle(uint32_t* a, size_t n);   // libstdc++ std::random_shuffle(first, last)
+	void window(uint32_t* out31) const;    // last 31 state words, oldest first (what psm_batch_assemble_glibc takes)
+	void discard(uint64_t n);              // skip n draws in O(log n) (linear recurrence jump-ahead)
 private:
 	int32_t tbl[31];
 	int f, r;
@@ -136,6 +147,7 @@ public:
 	// scores are accumulated on the device by rfRanger::predict(); kept for call-order compatibility
 	void accumulateAndDivideResInProbVect(uint32_t /*nPart*/) {}
 	std::vector<double> trngData(uint32_t p);       // row-major [trngSize][m+1] host copy (debug / parity)
+	bool deviceDraws = true;                        // replay rand() on the GPU instead of generating the draws on the host
 	const Partition* const part;
 	Device* const dev;
 	const uint32_t m, n;

@@ -8,6 +8,7 @@ import numpy as np
 from . import _capi
 from ._capi import KERNEL_CLASSES, PsmError, dp, u32, u32p, u64, u64p, vp, i32p, _p
 
+PHASES = ["setup_upload", "folds_ttd", "fold_begin", "smote_draws", "assemble", "train", "predict", "reduce", "scatter", "curves", "teardown"]
 REDUCE_FN = C.CFUNCTYPE(C.c_int, vp, vp, u64)
 _hlib = None
 
@@ -20,7 +21,10 @@ def hlib():
             raise ImportError("parsmurf_b200: %s is missing -- run __graft_entry__.build()" % _capi.HOST_LIB_PATH)
         L = C.CDLL(_capi.HOST_LIB_PATH)
         L.psmh_cv_run.argtypes = [vp, C.c_int, u32, u32, u32p, u32p] + [u32] * 8 + [C.c_int, vp, C.c_int, C.c_int, u32, u32, REDUCE_FN, vp, u64,
-                                  C.c_int, dp, dp, dp, dp, dp, u64p, u64p, C.c_char_p, C.c_size_t]
+                                  C.c_int, dp, dp, dp, dp, dp, u64p, u64p, dp, vp, C.c_char_p, C.c_size_t]
+        L.psmh_device_create.restype = vp
+        L.psmh_device_create.argtypes = [C.c_int, vp]
+        L.psmh_device_destroy.argtypes = [vp]
         L.psmh_rand_fill.argtypes = [u32, i32p, u64]
         L.psmh_ttd_fold.argtypes = [u32p, u32p, u32, u32, u32, C.c_int64, u32p, u32p, u32p, u32p, u32p]
         L.psmh_config_parse.argtypes = [C.c_char_p, u32p, u32p, u32, C.c_char_p, C.c_size_t]
@@ -29,7 +33,7 @@ def hlib():
 
 
 def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, device=0, stream=None, tie_mode=0, eval_fold_curves=True,
-           rank=0, world=1, reduce=None, batch_budget=0, profile=False, x_device_ptr=None, n=None, m=None):
+           rank=0, world=1, reduce=None, batch_budget=0, profile=False, x_device_ptr=None, n=None, m=None, dev_handle=None):
     """Run the whole CV on one GPU (or this rank's share of the partitions when world > 1).
 
     x: host row-major float64 [n][m+1] (label column 1.0/2.0), or None with x_device_ptr/n/m for a dataset already in HBM.
@@ -48,6 +52,7 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     c1 = np.zeros(n); c2 = np.zeros(n); met = np.zeros(2); fm = np.zeros((nFolds, 2))
     kms = np.zeros(len(KERNEL_CLASSES)); kl = np.zeros(len(KERNEL_CLASSES), np.uint64); st = np.zeros(3, np.uint64)
     err = C.create_string_buffer(512)
+    ph = np.zeros(len(PHASES))
 
     def _cb(user, ptr, count):
         try:
@@ -59,13 +64,37 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     cb = REDUCE_FN(_cb) if reduce is not None else REDUCE_FN()
     rc = L.psmh_cv_run(vp(xptr), isdev, n, m, _p(labels, u32p), _p(folds, u32p), nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, device,
                        vp(stream) if stream else None, tie_mode, int(eval_fold_curves), rank, world, cb, None, batch_budget, int(profile),
-                       _p(c1, dp), _p(c2, dp), _p(met, dp), _p(fm, dp), _p(kms, dp), _p(kl, u64p), _p(st, u64p), err, 512)
+                       _p(c1, dp), _p(c2, dp), _p(met, dp), _p(fm, dp), _p(kms, dp), _p(kl, u64p), _p(st, u64p), _p(ph, dp), vp(dev_handle) if dev_handle else None, err, 512)
     if rc != 0:
         raise PsmError(rc, err.value.decode())
     return dict(class1=c1, class2=c2, auroc=float(met[0]), auprc=float(met[1]), fold_metrics=fm,
                 kernel_ms={k_: float(kms[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
                 kernel_launches={k_: int(kl[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
-                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2])))
+                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2])),
+                host_phases_s={k_: float(ph[i]) for i, k_ in enumerate(PHASES)})
+
+
+class HostDevice:
+    """Persistent GPU context for repeated cv_run calls (device buffers are reused, like a long-lived process)."""
+
+    def __init__(self, device=0, stream=None):
+        self.h = hlib().psmh_device_create(device, vp(stream) if stream else None)
+        if not self.h:
+            raise PsmError(-1, "no usable CUDA device %d (parsmurf_b200 has no CPU fallback)" % device)
+
+    def cv_run(self, *a, **kw):
+        return cv_run(*a, dev_handle=self.h, **kw)
+
+    def close(self):
+        if self.h:
+            hlib().psmh_device_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def ttd_fold(labels, folds, nFolds, fold, fold_to_jump=-1):

@@ -67,6 +67,45 @@ def test_assemble_bit_exact(ctx, oracle, name):
         assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), "partition %d differs" % p
 
 
+def test_device_rand_replay_equals_host_draws(ctx, oracle):
+    """SMOTE draws replayed on the GPU from glibc's generator state == the same draws generated on the host"""
+    import parsmurf_b200._capi as capi
+    case = make_case("fy_26")
+    x, fd, rnd = _fold_setup(ctx, oracle, case)
+    ctx.fold_knn(case["k"])
+    P = len(fd["trngPos"])
+    per = P * case["fp"] * (case["m"] + 1)
+    # stream position after the folds' training-negative shuffles (one rand() per element but the first)
+    consumed = sum(len(t["trngNeg"]) - 1 for t in oracle.o_ttd(case["y"], case["f"], case["nF"], None))
+    w = capi.glibc_jump(capi.glibc_initial_window(1), consumed)
+    draws = rnd.fill(per * case["nParts"])
+    ctx.batch_begin(case["nParts"], case["fp"], case["ratio"], 0, case["nParts"])
+    ctx.batch_assemble(draws)
+    want = [ctx.batch_get_training(p)[0] for p in range(case["nParts"])]
+    ctx.batch_begin(case["nParts"], case["fp"], case["ratio"], 0, case["nParts"])
+    ctx.batch_assemble_glibc(w)
+    for p in range(case["nParts"]):
+        got = ctx.batch_get_training(p)[0]
+        assert np.array_equal(got.view(np.uint64), want[p].view(np.uint64))
+
+
+def test_cv_through_host_classes_bit_exact(oracle):
+    """the whole CV through the C++ host mirror (hyperSMURF::smurfIt) == the oracle == the reference at ensThrd 1"""
+    from parsmurf_b200 import host_api as H
+    for name in ("fy_26", "reject_300", "ties_ratio0"):
+        case = make_case(name)
+        x = oracle.make_x(case["X"], case["y"])
+        rc, o1, o2 = oracle.o_cv(x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
+        out = H.cv_run(x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7, tie_mode=0)
+        assert np.array_equal(out["class1"].view(np.uint64), o1.view(np.uint64)), name
+        assert np.array_equal(out["class2"].view(np.uint64), o2.view(np.uint64)), name
+        want = oracle.o_curves(case["y"], o1)
+        assert abs(out["auroc"] - want[0]) < 1e-12 and abs(out["auprc"] - want[1]) < 1e-12
+        # tiny batches (one partition per launch group) give the same bits
+        out2 = H.cv_run(x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7, tie_mode=0, batch_budget=1)
+        assert np.array_equal(out2["class1"].view(np.uint64), o1.view(np.uint64)), name
+
+
 def _train_case(ctx, oracle, case, fold=0, seed=7):
     x, fd, rnd = _fold_setup(ctx, oracle, case, fold)
     ctx.fold_knn(case["k"])
@@ -107,6 +146,19 @@ def test_trees_bit_exact(ctx, oracle, name):
             assert ok, "partition %d tree %d: %s" % (p, t, why)
             total_nodes += len(of.tree(t)["var"])
     assert total_nodes > case["nParts"] * case["T"]
+
+
+def test_trees_bit_exact_wide_entries(ctx, oracle, monkeypatch):
+    """the general 8-byte list-entry layout (used when Ntr > 16384) grows the same trees as the compact one"""
+    monkeypatch.setenv("PSM_FORCE_ENTRY64", "1")
+    case = make_case("ties_ratio0")
+    x, fd, seeds = _train_case(ctx, oracle, case)
+    for p in range(case["nParts"]):
+        tr, sz = ctx.batch_get_training(p)
+        of = oracle.o_forest_train(np.ascontiguousarray(tr.T), case["T"], case["mtry"], int(seeds[p]))
+        for t in range(case["T"]):
+            ok, why = trees_equal(ctx.batch_export_tree(p, t), of.tree(t))
+            assert ok, "partition %d tree %d: %s" % (p, t, why)
 
 
 def test_trees_with_injected_draws(ctx, oracle):
