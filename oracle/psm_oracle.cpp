@@ -401,9 +401,9 @@ void psmo_forest_predict(void* f, const double* rows, uint32_t Nte, uint32_t ld,
 
 void psmo_curves(const uint32_t* labels, const double* preds, uint64_t N, double* out, uint64_t* perm_out) { curves(labels, preds, N, out, perm_out); }
 
-int psmo_cv(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+static int cv_impl(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
             uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
-            uint32_t fold0, uint32_t fold1, uint32_t nthreads, double* class1, double* class2) {
+            uint32_t fold0, uint32_t fold1, uint32_t nthreads, uint32_t part0, uint32_t part1, double* class1, double* class2) {
 	GlibcRand g(1);                                                  // rand() is never seeded for seed != 0 (fact #5)
 	OTTD* ttd = build_ttd(labels, foldAssign, n, nFolds, &g);
 	const size_t ld = (size_t)m + 1;
@@ -432,7 +432,7 @@ int psmo_cv(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, con
 		}
 		std::vector<std::vector<double>> preds(nParts);
 		#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-		for (int32_t p = 0; p < (int32_t)nParts; p++) {
+		for (int32_t p = (int32_t)part0; p < (int32_t)part1; p++) {
 			uint32_t sz[6];
 			int r = partition_sizes(P, tn.size(), nParts, fp, ratio, p, sz);
 			if (r != 0) { rc = r; continue; }
@@ -449,7 +449,7 @@ int psmo_cv(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, con
 		}
 		if (rc) break;
 		const double divider = 1.0 / (double)nParts;                    // sampler.cpp:121
-		for (uint32_t p = 0; p < nParts; p++)
+		for (uint32_t p = part0; p < part1; p++)
 			for (uint32_t i = 0; i < Nte; i++) {
 				class1[testIdx[i]] += preds[p][2 * i] * divider;
 				class2[testIdx[i]] += preds[p][2 * i + 1] * divider;
@@ -457,6 +457,20 @@ int psmo_cv(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, con
 	}
 	delete ttd;
 	return rc;
+}
+
+int psmo_cv(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+            uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
+            uint32_t fold0, uint32_t fold1, uint32_t nthreads, double* class1, double* class2) {
+	return cv_impl(x, n, m, labels, foldAssign, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, fold0, fold1, nthreads, 0, nParts, class1, class2);
+}
+
+// only partitions [part0, part1) of every fold contribute (the share of one rank of a partition-sharded run);
+// the SMOTE stream is still consumed for all partitions, so the sum over disjoint shares equals psmo_cv up to fp64 addition order
+int psmo_cv_parts(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+                  uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
+                  uint32_t part0, uint32_t part1, double* class1, double* class2) {
+	return cv_impl(x, n, m, labels, foldAssign, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, 0, nFolds, 1, part0, part1, class1, class2);
 }
 
 }  // extern "C"

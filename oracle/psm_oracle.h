@@ -76,6 +76,11 @@ int psmo_cv(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, con
             uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
             uint32_t fold0, uint32_t fold1, uint32_t nthreads, double* class1, double* class2);
 
+/* One rank's share of a partition-sharded CV: only partitions [part0, part1) of every fold are trained/accumulated. */
+int psmo_cv_parts(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+                  uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
+                  uint32_t part0, uint32_t part1, double* class1, double* class2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,7 @@ def oracle_lib():
         L.psmo_forest_predict.argtypes = [vp, dp, u32, u32, dp]
         L.psmo_curves.argtypes = [u32p, dp, u64, dp, u64p]
         L.psmo_cv.argtypes = [dp, u32, u32, u32p, u32p] + [u32] * 11 + [dp, dp]
+        L.psmo_cv_parts.argtypes = [dp, u32, u32, u32p, u32p] + [u32] * 10 + [dp, dp]
         _oracle = L
     return _oracle
 
@@ -220,6 +221,15 @@ def o_cv(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, fol
     c1 = np.zeros(n); c2 = np.zeros(n)
     rc = oracle_lib().psmo_cv(_p(x, dp), n, ld - 1, _p(labels, u32p), _p(folds, u32p), nFolds, nParts, fp, ratio, k, nTrees, mtry, seed,
                               fold0, nFolds if fold1 is None else fold1, nthreads, _p(c1, dp), _p(c2, dp))
+    return rc, c1, c2
+
+
+def o_cv_parts(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, part0, part1):
+    n, ld = x.shape
+    labels = np.ascontiguousarray(labels, np.uint32); folds = np.ascontiguousarray(folds, np.uint32)
+    c1 = np.zeros(n); c2 = np.zeros(n)
+    rc = oracle_lib().psmo_cv_parts(_p(x, dp), n, ld - 1, _p(labels, u32p), _p(folds, u32p), nFolds, nParts, fp, ratio, k, nTrees, mtry, seed,
+                                    part0, part1, _p(c1, dp), _p(c2, dp))
     return rc, c1, c2
 
 

@@ -106,6 +106,46 @@ def test_cv_through_host_classes_bit_exact(oracle):
         assert np.array_equal(out2["class1"].view(np.uint64), o1.view(np.uint64)), name
 
 
+def test_two_rank_shares_on_one_gpu(oracle):
+    """partition sharding (rank r of 2 handles its contiguous chunk and skips the other rank's SMOTE draws): the two
+    partial results add up to the single-rank CV; emulated as two sequential runs on one GPU, no collective needed"""
+    from parsmurf_b200 import host_api as H
+    case = make_case("fy_26")
+    x = oracle.make_x(case["X"], case["y"])
+    args = (x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
+    full = H.cv_run(*args, tie_mode=0)
+    noop = lambda ptr, count: None
+    a = H.cv_run(*args, tie_mode=0, rank=0, world=2, reduce=noop, eval_fold_curves=False)
+    b = H.cv_run(*args, tie_mode=0, rank=1, world=2, reduce=noop, eval_fold_curves=False)
+    assert np.allclose(a["class1"] + b["class1"], full["class1"], rtol=0, atol=1e-15)
+    assert np.allclose(a["class2"] + b["class2"], full["class2"], rtol=0, atol=1e-15)
+    assert np.abs(a["class1"]).sum() > 0 and np.abs(b["class1"]).sum() > 0
+    rc, o1, o2 = oracle.o_cv_parts(*args, 0, 2)
+    assert np.array_equal(a["class1"].view(np.uint64), o1.view(np.uint64))
+
+
+def test_cuda_path_against_committed_golden_fixtures(oracle):
+    """CUDA path vs the reference's own outputs stored in tests/golden (no oracle in between)"""
+    import os
+    from parsmurf_b200 import host_api as H
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "cfg1_example_transposed.npz"))
+    x = oracle.make_x(g["X"], g["y"])
+    out = H.cv_run(x, g["y"], g["folds"], int(g["nFolds"]), int(g["nParts"]), int(g["fp"]), int(g["ratio"]), int(g["k"]), int(g["nTrees"]), int(g["mtry"]), int(g["seed"]), tie_mode=0)
+    assert np.array_equal(out["class1"].view(np.uint64), g["class1"].view(np.uint64))
+    assert np.array_equal(out["class2"].view(np.uint64), g["class2"].view(np.uint64))
+    assert abs(out["auroc"] - float(g["auroc"])) < 1e-12 and abs(out["auprc"] - float(g["auprc"])) < 1e-12
+    assert np.allclose(out["fold_metrics"], g["fold_metrics"], rtol=0, atol=1e-12)
+    for name in CASES:
+        c = make_case(name)
+        g = np.load(os.path.join(gold, "case_%s.npz" % name))
+        x = oracle.make_x(c["X"], c["y"])
+        out = H.cv_run(x, c["y"], c["f"], c["nF"], c["nParts"], c["fp"], c["ratio"], c["k"], c["T"], c["mtry"], 7, tie_mode=0)
+        assert np.array_equal(out["class1"].view(np.uint64), g["class1"].view(np.uint64)), name
+        assert abs(out["auroc"] - float(g["auroc"])) < 1e-12 and abs(out["auprc"] - float(g["auprc"])) < 1e-12
+        assert np.allclose(out["fold_metrics"], g["fold_metrics"], rtol=0, atol=1e-12)
+
+
 def _train_case(ctx, oracle, case, fold=0, seed=7):
     x, fd, rnd = _fold_setup(ctx, oracle, case, fold)
     ctx.fold_knn(case["k"])

@@ -1,0 +1,125 @@
+"""Host-side logic of the product (no GPU): the C ABI library loads and exports every symbol the header declares, fails
+loudly without a device, and the C++ host mirror's folds / train-test division / rand replica / JSON surface behave like
+the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import parsmurf_b200 as psm
+from parsmurf_b200 import _capi, host_api as H
+from helpers import make_case
+from oracle import pyoracle as O
+
+
+def test_capi_exports_every_declared_symbol():
+    hdr = open(_capi.HEADER_PATH).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(psm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 30
+    L = psm.lib()
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert b"sm_100a" in L.psm_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(psm.PsmError) as e:
+        psm.Context(0)
+    assert e.value.code == -1
+    x = np.zeros((10, 3)); y = np.zeros(10, np.uint32); y[:4] = 1
+    with pytest.raises(psm.PsmError):
+        H.cv_run(x, y, np.arange(10) % 2, 2, 2, 1, 1, 2, 2, 1, 1)
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dp, dn, fn in os.walk(os.path.join(root, "parsmurf_b200")):
+        if "_build" in dp:
+            continue
+        for f in fn:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "pyoracle" not in txt and "psm_oracle" not in txt and "libparsmurf_ref" not in txt, f
+
+
+def test_glibc_rand_replica_and_jump_ahead():
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    want = np.array([libc.rand() for _ in range(5000)], np.int32)
+    assert np.array_equal(H.rand_fill(1, 5000), want)
+    libc.srand(12345)
+    want2 = np.array([libc.rand() for _ in range(100)], np.int32)
+    assert np.array_equal(H.rand_fill(12345, 100), want2)
+    w0 = _capi.glibc_initial_window(1)
+    for n in (0, 1, 2, 30, 31, 32, 63, 64, 1000, 4999 - 40):
+        w = _capi.glibc_jump(w0, n)
+        seq = [int(v) for v in w]
+        outs = []
+        for _ in range(40):
+            v = (seq[-31] + seq[-3]) & 0xFFFFFFFF
+            seq.append(v); outs.append(v >> 1)
+        assert np.array_equal(np.array(outs, np.int32), want[n:n + 40]), n
+
+
+@pytest.mark.parametrize("name", ["fy_26", "ties_ratio0"])
+def test_ttd_matches_oracle(name):
+    c = make_case(name)
+    o = O.o_ttd(c["y"], c["f"], c["nF"], O.GlibcRand(1))
+    for f in range(c["nF"]):
+        t = H.ttd_fold(c["y"], c["f"], c["nF"], f)
+        for k_ in t:
+            assert np.array_equal(t[k_], o[f][k_]), (f, k_)
+
+
+def test_inner_cv_ttd_skips_fold_and_does_not_shuffle():
+    c = make_case("fy_26")
+    jump = 1
+    full = [H.ttd_fold(c["y"], c["f"], c["nF"], f) for f in range(c["nF"])]
+    for i in range(c["nF"] - 1):
+        t = H.ttd_fold(c["y"], c["f"], c["nF"], i, fold_to_jump=jump)
+        cur = i if i < jump else i + 1
+        assert np.array_equal(t["testPos"], full[cur]["testPos"]) and np.array_equal(t["testNeg"], full[cur]["testNeg"])
+        other = np.flatnonzero((c["f"] != cur) & (c["f"] != jump) & (c["y"] == 0))
+        # fold order of the fold file, not shuffled (src/testtraindivider.cpp:214)
+        want = np.concatenate([np.flatnonzero((c["f"] == k_) & (c["y"] == 0)) for k_ in range(c["nF"]) if k_ not in (cur, jump)])
+        assert np.array_equal(t["trngNeg"], want) and len(other) == len(want)
+
+
+def test_random_folds_are_stratified_round_robin():
+    c = make_case("fy_26")
+    t = [H.ttd_fold(c["y"], None, 5, f) for f in range(5)]
+    npos = [len(v["testPos"]) for v in t]
+    assert sum(npos) == int(c["y"].sum()) and max(npos) - min(npos) <= 1
+    allidx = np.sort(np.concatenate([np.concatenate([v["testPos"], v["testNeg"]]) for v in t]))
+    assert np.array_equal(allidx, np.arange(c["n"]))
+
+
+CFG_GRID = """{
+  "name": "cfgEx_gridTune",
+  "exec": {"name": "parSMURF", "nProcs": 1, "ensThrd": 6, "rfThrd": 4, "seed": 18, "verboseLevel": 1, "saveTime": true,
+           "timeFile": "timeout.txt", "printCfg": true, "mode": "cv", "optimizer": "grid"},
+  "data": {"dataFile": "d.txt", "labelFile": "l.txt", "outFile": "predictions.txt",},
+  "folds": {"nFolds": 5},
+  "params": {"nParts": [10, 20, 30], "fp": [1, 2], "ratio": [1], "k": [5], "nTrees": [10], "mtry": [5, 7, 10]}
+}"""
+
+
+def test_config_surface():
+    d = H.config_parse(CFG_GRID)   # note the trailing comma in "data": jsoncons accepts it, so must we
+    assert d["nFolds"] == 5 and d["seed"] == 18 and d["woptimiz"] == 32 and d["wmode"] == 1 and d["ensThrd"] == 6 and d["rfThrd"] == 4
+    assert d["gridSize"] == 18
+    assert d["grid"][0] == dict(nParts=10, fp=1, ratio=1, k=5, nTrees=10, mtry=5)
+    assert d["grid"][1]["mtry"] == 7 and d["grid"][3] == dict(nParts=10, fp=2, ratio=1, k=5, nTrees=10, mtry=5) and d["grid"][-1]["nParts"] == 30
+    d = H.config_parse('{"exec": {"mode": "cv"}, "simulate": {"simulation": true, "prob": 0.02, "n": 1200, "m": 25}, "folds": {"nFolds": 10}, "params": {}}')
+    assert d["simulate"] == 1 and d["n"] == 1200 and d["m"] == 25
+    assert d["grid"] == [dict(nParts=3, fp=1, ratio=1, k=5, nTrees=50, mtry=0)]      # defaults of ArgHandle::checkConfig
+    with pytest.raises(psm.PsmError):
+        H.config_parse('{"exec": {"mode": "bogus"}}')
+    with pytest.raises(psm.PsmError):
+        H.config_parse('{"exec": ')
