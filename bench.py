@@ -140,7 +140,7 @@ def run_reference(args, w):
             "config": workload_config(args, w),
             "cpu_baseline": {"value": value, "unit": "partitions/s", "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": value, "unit": "partitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, w):
@@ -255,12 +255,24 @@ def run_ours(args, w):
             secs, kind = cpu_sample(w, x, y, f, sample, cores)
             line["cpu_baseline"] = {"value": sample / secs, "unit": "partitions/s", "cores": cores, "kind": kind,
                                     "sample": "%d of %d partitions of fold 0 (Nte=%d), %d OpenMP threads over partitions, rfThrd 1, %.1f s" % (sample, w["nParts"], n // w["nFolds"], cores, secs)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner, ...) goes to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

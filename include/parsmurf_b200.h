@@ -105,6 +105,16 @@ int psm_fold_scores_devptr(psm_ctx* ctx, double** class12_dev, uint32_t* Nte);
 /* class1Prob/class2Prob[testIdx[i]] += fold scores (scatter by original example id); host arrays length n */
 int psm_fold_scatter_host(psm_ctx* ctx, double* class1Prob, double* class2Prob);
 
+/* Device-resident variants (no host round trip of the scores): the 0/1 labels `y` of hyperSMURF's ctor are uploaded once;
+ * fold scores are scattered into device class1Prob/class2Prob[n] (the arrays main() owns in src/parSMURF.cpp:90-93);
+ * per-fold and global AUROC/AUPRC are computed from device memory; psm_scores_get ADDS the device arrays into the host ones. */
+int psm_labels_upload(psm_ctx* ctx, const uint32_t* labels, uint32_t n);
+int psm_scores_reset(psm_ctx* ctx);
+int psm_fold_scatter_device(psm_ctx* ctx);
+int psm_fold_curves(psm_ctx* ctx, int tie_mode, double* out);
+int psm_scores_get(psm_ctx* ctx, double* class1Prob, double* class2Prob);
+int psm_scores_curves(psm_ctx* ctx, int tie_mode, double* out);
+
 /* ---- (9) curves: Curves ctor + evalAUROC_ok + evalAUPRC (src/curves.cpp:7-36,77-122). out = {auroc, auprc}.
  *      tie_mode 0: descending order from the identical host std::sort call (bit-parity with the reference's
  *      tie order); tie_mode 1: stable device radix sort (ties in index order; may differ from the reference by

@@ -71,6 +71,11 @@ struct psm_ctx {
 	// predict
 	DevBuf dPredScratch;
 
+	// device-resident labels / global scores
+	DevBuf dLabels, dFoldLabels, dGlob;
+	std::vector<uint32_t> hLabels;
+	bool haveLabels = false, foldLabelsReady = false;
+
 	// curves
 	DevBuf cLabels, cPerm, cSorted, cTp, cPartials, cOut, cScores, cKeysA, cKeysB, cValsA, cValsB, cHist;
 
@@ -175,7 +180,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
 	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dFlags, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
-	                  &ctx->dInjCand, &ctx->dPredScratch, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
+	                  &ctx->dInjCand, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
 	                  &ctx->cScores, &ctx->cKeysA, &ctx->cKeysB, &ctx->cValsA, &ctx->cValsB, &ctx->cHist};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& p : ctx->profPending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -232,7 +237,7 @@ int psm_fold_begin(psm_ctx* ctx, const uint32_t* trngPosIdx, uint32_t P, const u
 	CU(cudaSetDevice(ctx->device));
 	for (uint32_t i = 0; i < P; i++) if (trngPosIdx[i] >= ctx->n) return fail(ctx, PSM_E_ARG, "fold_begin: index out of range");
 	ctx->P = P; ctx->Nneg = Nneg; ctx->nTP = nTP; ctx->nTN = nTN; ctx->Nte = nTP + nTN;
-	ctx->haveKnn = false; ctx->batchOpen = false; ctx->localk = 0;
+	ctx->haveKnn = false; ctx->batchOpen = false; ctx->localk = 0; ctx->foldLabelsReady = false;
 	ENSURE(ctx->dPos, std::max<size_t>(4, (size_t)P * 4));
 	ENSURE(ctx->dNeg, std::max<size_t>(4, (size_t)Nneg * 4));
 	ENSURE(ctx->dTest, std::max<size_t>(4, (size_t)ctx->Nte * 4));
@@ -651,51 +656,122 @@ int psm_fold_scatter_host(psm_ctx* ctx, double* class1Prob, double* class2Prob) 
 }
 
 // ------------------------------------------------------------------------------------------ curves
-int psm_curves(psm_ctx* ctx, const uint32_t* labels, const double* scores, uint64_t N, int tie_mode, double* out) {
-	if (!ctx || !labels || !scores || !out || N == 0 || N >= (1ull << 32)) return fail(ctx, PSM_E_ARG, "curves: bad arguments");
-	CU(cudaSetDevice(ctx->device));
+// core: labels (u32) and scores (f64) already on the device; hScores (host copy) is only needed for tie_mode 0
+static int curves_core(psm_ctx* ctx, const uint32_t* dLabels, const double* dScores, const double* hScores, uint64_t N, uint32_t totP, uint32_t totN,
+                       int tie_mode, double* out) {
 	cudaStream_t s = ctx->stream;
-	uint32_t totP = 0, totN = 0;
-	for (uint64_t i = 0; i < N; i++) { totP += labels[i] == 1; totN += labels[i] == 0; }   // curves.cpp:16-17
-	ENSURE(ctx->cLabels, N * 4); ENSURE(ctx->cSorted, N + 64);
+	ENSURE(ctx->cSorted, N + 64);
 	const uint64_t nBlocks = (N + 4095) / 4096;
 	ENSURE(ctx->cTp, (nBlocks + 1) * 4); ENSURE(ctx->cPartials, nBlocks * 16); ENSURE(ctx->cOut, 16);
-	CU(cudaMemcpyAsync(ctx->cLabels.p, labels, N * 4, cudaMemcpyHostToDevice, s));
 	const uint32_t* dPerm = nullptr;
 	std::vector<uint32_t> perm;
+	std::vector<double> tmp;
 	if (tie_mode == 0) {
+		if (!hScores) {
+			tmp.resize(N);
+			CU(cudaMemcpyAsync(tmp.data(), dScores, N * 8, cudaMemcpyDeviceToHost, s));
+			CU(cudaStreamSynchronize(s));
+			hScores = tmp.data();
+		}
 		// the identical call the reference makes (curves.cpp:31-33): same libstdc++ introsort => same tie order
 		std::vector<size_t> idx(N);
 		std::iota(idx.begin(), idx.end(), 0);
-		std::sort(idx.begin(), idx.end(), [&](size_t i, size_t j) { return scores[i] > scores[j]; });
+		std::sort(idx.begin(), idx.end(), [&](size_t i, size_t j) { return hScores[i] > hScores[j]; });
 		perm.resize(N);
 		for (uint64_t i = 0; i < N; i++) perm[i] = (uint32_t)idx[i];
 		ENSURE(ctx->cPerm, N * 4);
 		CU(cudaMemcpyAsync(ctx->cPerm.p, perm.data(), N * 4, cudaMemcpyHostToDevice, s));
 		dPerm = ctx->cPerm.as<uint32_t>();
 	} else {
-		ENSURE(ctx->cScores, N * 8);
 		ENSURE(ctx->cKeysA, N * 8); ENSURE(ctx->cKeysB, N * 8); ENSURE(ctx->cValsA, N * 4); ENSURE(ctx->cValsB, N * 4);
 		const uint64_t rBlocks = (N + 4095) / 4096;
 		ENSURE(ctx->cHist, rBlocks * 256 * 4);
-		CU(cudaMemcpyAsync(ctx->cScores.p, scores, N * 8, cudaMemcpyHostToDevice, s));
 		ProfScope ps(ctx, K_CURVES, 1 + 3 * 8);
-		if (launch_sort_scores_desc(ctx->cScores.as<double>(), N, ctx->cKeysA.as<unsigned long long>(), ctx->cKeysB.as<unsigned long long>(),
+		if (launch_sort_scores_desc(dScores, N, ctx->cKeysA.as<unsigned long long>(), ctx->cKeysB.as<unsigned long long>(),
 		                            ctx->cValsA.as<uint32_t>(), ctx->cValsB.as<uint32_t>(), ctx->cHist.as<uint32_t>(), s))
 			return fail(ctx, PSM_E_ARG, "curves: sort launch failed");
 		dPerm = ctx->cValsA.as<uint32_t>();
 	}
 	{
 		ProfScope ps(ctx, K_CURVES, 5);
-		launch_gather_labels(ctx->cLabels.as<uint32_t>(), dPerm, N, ctx->cSorted.as<unsigned char>(), s);
+		launch_gather_labels(dLabels, dPerm, N, ctx->cSorted.as<unsigned char>(), s);
 		if (launch_curves(ctx->cSorted.as<unsigned char>(), N, totP, totN, ctx->cTp.as<uint32_t>(), ctx->cPartials.as<double>(), nBlocks * 2,
 		                  ctx->cOut.as<double>(), s))
 			return fail(ctx, PSM_E_ARG, "curves: launch failed");
 	}
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(out, ctx->cOut.p, 16, cudaMemcpyDeviceToHost, s));
-	CU(cudaStreamSynchronize(s));
+	CU(cudaStreamSynchronize(s));   // also keeps `perm` alive until the upload is done
 	return PSM_OK;
+}
+
+int psm_curves(psm_ctx* ctx, const uint32_t* labels, const double* scores, uint64_t N, int tie_mode, double* out) {
+	if (!ctx || !labels || !scores || !out || N == 0 || N >= (1ull << 32)) return fail(ctx, PSM_E_ARG, "curves: bad arguments");
+	CU(cudaSetDevice(ctx->device));
+	uint32_t totP = 0, totN = 0;
+	for (uint64_t i = 0; i < N; i++) { totP += labels[i] == 1; totN += labels[i] == 0; }   // curves.cpp:16-17
+	ENSURE(ctx->cLabels, N * 4);
+	ENSURE(ctx->cScores, N * 8);
+	CU(cudaMemcpyAsync(ctx->cLabels.p, labels, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (tie_mode != 0) CU(cudaMemcpyAsync(ctx->cScores.p, scores, N * 8, cudaMemcpyHostToDevice, ctx->stream));
+	return curves_core(ctx, ctx->cLabels.as<uint32_t>(), ctx->cScores.as<double>(), scores, N, totP, totN, tie_mode, out);
+}
+
+int psm_labels_upload(psm_ctx* ctx, const uint32_t* labels, uint32_t n) {
+	if (!ctx || !labels || n == 0 || n != ctx->n) return fail(ctx, PSM_E_ARG, "labels_upload: need the dataset first and n labels");
+	CU(cudaSetDevice(ctx->device));
+	ctx->hLabels.assign(labels, labels + n);
+	ENSURE(ctx->dLabels, (size_t)n * 4);
+	ENSURE(ctx->dGlob, (size_t)n * 16);
+	CU(cudaMemcpyAsync(ctx->dLabels.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemsetAsync(ctx->dGlob.p, 0, (size_t)n * 16, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->haveLabels = true;
+	return PSM_OK;
+}
+
+int psm_scores_reset(psm_ctx* ctx) {
+	if (!ctx || !ctx->haveLabels) return fail(ctx, PSM_E_ARG, "scores_reset: upload the labels first");
+	CU(cudaMemsetAsync(ctx->dGlob.p, 0, (size_t)ctx->n * 16, ctx->stream));
+	return PSM_OK;
+}
+
+int psm_fold_scatter_device(psm_ctx* ctx) {
+	if (!ctx || !ctx->foldOpen || !ctx->haveLabels) return fail(ctx, PSM_E_ARG, "fold_scatter_device: need an open fold and uploaded labels");
+	ProfScope ps(ctx, K_GATHER, 1);
+	launch_scatter_scores(ctx->dClass12.as<double>(), ctx->dTest.as<uint32_t>(), ctx->Nte, ctx->n, ctx->dGlob.as<double>(), ctx->stream);
+	CU(cudaGetLastError());
+	return PSM_OK;
+}
+
+int psm_fold_curves(psm_ctx* ctx, int tie_mode, double* out) {
+	if (!ctx || !ctx->foldOpen || !ctx->haveLabels || !out || ctx->Nte == 0) return fail(ctx, PSM_E_ARG, "fold_curves: need an open fold and uploaded labels");
+	CU(cudaSetDevice(ctx->device));
+	ENSURE(ctx->dFoldLabels, (size_t)ctx->Nte * 4);
+	uint32_t totP = 0, totN = 0;
+	for (uint32_t i = 0; i < ctx->Nte; i++) { uint32_t l = ctx->hLabels[ctx->hTestIdx[i]]; totP += l == 1; totN += l == 0; }
+	{
+		ProfScope ps(ctx, K_GATHER, 1);
+		launch_gather_u32(ctx->dLabels.as<uint32_t>(), ctx->dTest.as<uint32_t>(), ctx->Nte, ctx->dFoldLabels.as<uint32_t>(), ctx->stream);
+	}
+	return curves_core(ctx, ctx->dFoldLabels.as<uint32_t>(), ctx->dClass12.as<double>(), nullptr, ctx->Nte, totP, totN, tie_mode, out);
+}
+
+int psm_scores_get(psm_ctx* ctx, double* class1Prob, double* class2Prob) {
+	if (!ctx || !ctx->haveLabels || !class1Prob) return fail(ctx, PSM_E_ARG, "scores_get: no device scores");
+	std::vector<double> h((size_t)ctx->n * 2);
+	CU(cudaMemcpyAsync(h.data(), ctx->dGlob.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	for (uint32_t i = 0; i < ctx->n; i++) { class1Prob[i] += h[i]; if (class2Prob) class2Prob[i] += h[(size_t)ctx->n + i]; }
+	return PSM_OK;
+}
+
+int psm_scores_curves(psm_ctx* ctx, int tie_mode, double* out) {
+	if (!ctx || !ctx->haveLabels || !out) return fail(ctx, PSM_E_ARG, "scores_curves: no device scores");
+	CU(cudaSetDevice(ctx->device));
+	uint32_t totP = 0, totN = 0;
+	for (uint32_t i = 0; i < ctx->n; i++) { totP += ctx->hLabels[i] == 1; totN += ctx->hLabels[i] == 0; }
+	return curves_core(ctx, ctx->dLabels.as<uint32_t>(), ctx->dGlob.as<double>(), nullptr, ctx->n, totP, totN, tie_mode, out);
 }
 
 // ------------------------------------------------------------------------------------------ convenience

@@ -26,6 +26,29 @@ void launch_gather_labels(const uint32_t* labels, const uint32_t* perm, uint64_t
 	gather_labels_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(labels, perm, N, out);
 }
 
+// fold-local labels: out[i] = labels[idx[i]]
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t N, uint32_t* __restrict__ out) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < N) out[i] = src[idx[i]];
+}
+void launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint64_t N, uint32_t* out, cudaStream_t s) {
+	if (!N) return;
+	gather_u32_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(src, idx, N, out);
+}
+// classXProb[testIdx[i]] += fold scores (sampler.cpp:121-132 scatter by original example id)
+__global__ void scatter_scores_kernel(const double* __restrict__ class12, const uint32_t* __restrict__ testIdx, uint32_t Nte, uint32_t n,
+                                      double* __restrict__ glob) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= Nte) return;
+	const uint32_t t = testIdx[i];
+	glob[t] = __dadd_rn(glob[t], class12[i]);
+	glob[(size_t)n + t] = __dadd_rn(glob[(size_t)n + t], class12[(size_t)Nte + i]);
+}
+void launch_scatter_scores(const double* class12, const uint32_t* testIdx, uint32_t Nte, uint32_t n, double* glob, cudaStream_t s) {
+	if (!Nte) return;
+	scatter_scores_kernel<<<(Nte + 255) / 256, 256, 0, s>>>(class12, testIdx, Nte, n, glob);
+}
+
 __device__ __forceinline__ uint32_t block_reduce_u32(uint32_t v, uint32_t* sh) {
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;

@@ -312,6 +312,10 @@ void hyperSMURF::smurfIt() {                                                // s
 	if (!inInternalCV && commonParams->maxFold != (uint32_t)-1) endingFold = commonParams->maxFold;
 	if (woptimiz != OPT_NO) { tempcl1.assign(nn, 0.0); tempcl2.assign(nn, 0.0); }
 	if (!inInternalCV) { foldAuroc.assign(nFolds, 0.0); foldAuprc.assign(nFolds, 0.0); }
+	// scores live on the device for the whole CV (class1Prob/class2Prob of src/parSMURF.cpp:90-93); they are added into the
+	// caller's host arrays once, at the end
+	dev->check(psm_labels_upload(dev->ctx, y.data(), nn));
+	dev->check(psm_scores_reset(dev->ctx));
 
 	for (uint32_t currentFold = startingFold; currentFold < endingFold; currentFold++) {
 		if (woptimiz == OPT_GRID) {                                         // :176-228 grid exploration on the inner folds
@@ -379,21 +383,20 @@ void hyperSMURF::smurfIt() {                                                // s
 			dev->check(psm_sync(dev->ctx));
 			reduce(ptr, 2ull * nte);
 		}
-		{ PhaseScope ps(PH_SCATTER); dev->check(psm_fold_scatter_host(dev->ctx, class1Prob, class2Prob)); }
+		{ PhaseScope ps(PH_SCATTER); dev->check(psm_fold_scatter_device(dev->ctx)); }   // :344-346 scatter by example id, on the device
 
-		if (evalFoldCurves && !inInternalCV) {                              // :365-396 per-fold AUROC / AUPRC
+		if (evalFoldCurves && !inInternalCV) {                              // :365-396 per-fold AUROC / AUPRC (labels y[idx], scores class1Prob[idx])
 			PhaseScope ps(PH_CURVES);
-			std::vector<uint32_t> tl; std::vector<double> tp;
-			for (uint32_t i = 0; i < ttd->testPosNum[currentFold]; i++) { uint32_t v = ttd->testPosIdx[currentFold][i]; tl.push_back(y[v]); tp.push_back(class1Prob[v]); }
-			for (uint32_t i = 0; i < ttd->testNegNum[currentFold]; i++) { uint32_t v = ttd->testNegIdx[currentFold][i]; tl.push_back(y[v]); tp.push_back(class1Prob[v]); }
-			Curves c(dev, tl, tp.data(), curvesTieMode);
-			foldAuroc[currentFold] = c.evalAUROC_ok();                      // AUROC first, then AUPRC (:382-384)
-			foldAuprc[currentFold] = c.evalAUPRC();
+			double r2[2];
+			dev->check(psm_fold_curves(dev->ctx, curvesTieMode, r2));       // Curves(tempLabels, tempPreds): AUROC first, then AUPRC (:382-384)
+			foldAuroc[currentFold] = r2[0];
+			foldAuprc[currentFold] = r2[1];
 			if (verboseLevel > VERBSILENT && rank == 0)
 				std::cout << "External CV on fold " << currentFold << " -> AUROC: " << foldAuroc[currentFold] << " - AUPRC: " << foldAuprc[currentFold] << std::endl;
 		}
 	}
 
+	{ PhaseScope ps(PH_SCATTER); dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob)); }
 	if (inInternalCV) {                                                     // :456-482
 		std::vector<uint32_t> tl; std::vector<double> tp;
 		for (uint32_t f = 0; f < nFolds; f++) {
@@ -405,9 +408,10 @@ void hyperSMURF::smurfIt() {                                                // s
 		gridParams[idxInGridParams].auprc = c.evalAUPRC();
 	} else {                                                                // :484-488
 		PhaseScope ps(PH_CURVES);
-		Curves c(dev, y, class1Prob, curvesTieMode);
-		auroc = c.evalAUROC_ok();
-		auprc = c.evalAUPRC();
+		double r2[2];
+		dev->check(psm_scores_curves(dev->ctx, curvesTieMode, r2));        // Curves(y, class1Prob)
+		auroc = r2[0];
+		auprc = r2[1];
 		if (verboseLevel > VERBSILENT && rank == 0) std::cout << "AUROC: " << auroc << " - AUPRC: " << auprc << std::endl;
 	}
 }
