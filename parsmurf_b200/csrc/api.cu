@@ -65,6 +65,8 @@ struct psm_ctx {
 	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dFlags, dFlagBits, dItems0, dItems1, dCand, dRes, dDec, dCounters, dStats, dSeeds,
 	    dInjBoot, dInjBootOff, dInjCand;
 	uint32_t* hCounters = nullptr;   // pinned
+	void* hStage = nullptr;          // pinned D2H staging
+	size_t hStageCap = 0;
 	uint64_t statSplitBytes = 0, statNodes = 0, statLevels = 0;
 	uint32_t maxNodes = 0;
 
@@ -186,6 +188,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	for (auto& p : ctx->profPending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
 	for (auto e : ctx->evPool) cudaEventDestroy(e);
 	if (ctx->hCounters) cudaFreeHost(ctx->hCounters);
+	if (ctx->hStage) cudaFreeHost(ctx->hStage);
 	delete ctx;
 	return PSM_OK;
 }
@@ -416,8 +419,11 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	ctx->T = T; ctx->mtry = mtry;
 
 	ENSURE(ctx->dS, ctx->totalS * 8);
-	ENSURE(ctx->dKeysA, ctx->totalS * 8); ENSURE(ctx->dKeysB, ctx->totalS * 8);
-	ENSURE(ctx->dValsA, ctx->totalS * 4); ENSURE(ctx->dValsB, ctx->totalS * 4);
+	const bool sortInSmem = ctx->maxNtr <= 16384 && !getenv("PSM_FORCE_RADIX_SORT");
+	if (!sortInSmem) {
+		ENSURE(ctx->dKeysA, ctx->totalS * 8); ENSURE(ctx->dKeysB, ctx->totalS * 8);
+		ENSURE(ctx->dValsA, ctx->totalS * 4); ENSURE(ctx->dValsB, ctx->totalS * 4);
+	}
 	int entry32 = (ctx->maxNtr <= Ent<uint32_t>::kMaxRowsE && !getenv("PSM_FORCE_ENTRY64")) ? 1 : 0;
 	size_t listBytes = (size_t)nTrees * m * stride * (entry32 ? 4 : 8);
 	ENSURE(ctx->dLists0, listBytes); ENSURE(ctx->dLists1, listBytes);
@@ -463,8 +469,13 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	}
 	{
 		ProfScope ps(ctx, K_SORT, 1);
-		launch_feature_sort(A.Dall, A.parts, nB, m, ctx->dKeysA.as<unsigned long long>(), ctx->dKeysB.as<unsigned long long>(),
-		                    ctx->dValsA.as<uint32_t>(), ctx->dValsB.as<uint32_t>(), ctx->dS.as<entry_t>(), s);
+		if (sortInSmem) {
+			if (launch_feature_sort_smem(A.Dall, A.parts, nB, m, ctx->maxNtr, ctx->dS.as<entry_t>(), s))
+				return fail(ctx, PSM_E_CUDA, "batch_train: cannot configure the shared-memory sort");
+		} else {
+			launch_feature_sort(A.Dall, A.parts, nB, m, ctx->dKeysA.as<unsigned long long>(), ctx->dKeysB.as<unsigned long long>(),
+			                    ctx->dValsA.as<uint32_t>(), ctx->dValsB.as<uint32_t>(), ctx->dS.as<entry_t>(), s);
+		}
 	}
 	if (!(inj_bootstrap && inj_cand)) {
 		if (!forest_seeds) return fail(ctx, PSM_E_ARG, "batch_train: forest_seeds required");
@@ -524,7 +535,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		cudaEvent_t tev[5];
 		if (trace) for (auto& e : tev) cudaEventCreate(&e);
 		if (trace) cudaEventRecord(tev[0], s);
-		{ ProfScope ps(ctx, K_SEARCH, 1); launch_split_search(A, nItems, buf, s); }
+		{ ProfScope ps(ctx, K_SEARCH, 3); launch_split_search(A, nItems, buf, s); }
 		if (trace) cudaEventRecord(tev[1], s);
 		{ ProfScope ps(ctx, K_SELECT, 2); launch_split_select(A, nItems, buf, s); launch_pack_flags(A, s); }
 		if (trace) cudaEventRecord(tev[2], s);
@@ -759,10 +770,18 @@ int psm_fold_curves(psm_ctx* ctx, int tie_mode, double* out) {
 
 int psm_scores_get(psm_ctx* ctx, double* class1Prob, double* class2Prob) {
 	if (!ctx || !ctx->haveLabels || !class1Prob) return fail(ctx, PSM_E_ARG, "scores_get: no device scores");
-	std::vector<double> h((size_t)ctx->n * 2);
-	CU(cudaMemcpyAsync(h.data(), ctx->dGlob.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	const size_t need = (size_t)ctx->n * 16;
+	if (ctx->hStageCap < need) {                       // pinned staging buffer, reused across calls
+		if (ctx->hStage) cudaFreeHost(ctx->hStage);
+		ctx->hStage = nullptr; ctx->hStageCap = 0;
+		CU(cudaMallocHost(&ctx->hStage, need));
+		ctx->hStageCap = need;
+	}
+	const double* h = (const double*)ctx->hStage;
+	CU(cudaMemcpyAsync(ctx->hStage, ctx->dGlob.p, need, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	for (uint32_t i = 0; i < ctx->n; i++) { class1Prob[i] += h[i]; if (class2Prob) class2Prob[i] += h[(size_t)ctx->n + i]; }
+	for (uint32_t i = 0; i < ctx->n; i++) class1Prob[i] += h[i];
+	if (class2Prob) for (uint32_t i = 0; i < ctx->n; i++) class2Prob[i] += h[(size_t)ctx->n + i];
 	return PSM_OK;
 }
 

@@ -108,6 +108,98 @@ __global__ void __launch_bounds__(ST) feature_sort_kernel(const double* __restri
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Shared-memory path (Ntr <= 16384, i.e. every BASELINE config with m = 26): the whole segment lives in shared memory
+// (u64 keys + u16 row ids, up to 160 KB) and is sorted by a bitonic network, so HBM sees the column once (read) and
+// the list once (write) instead of 8 radix passes.  Stability is irrelevant: equal values get equal dense ranks and
+// split candidates only exist between different ranks.  Padding keys are all-ones.
+// ------------------------------------------------------------------------------------------------
+constexpr int BT = 1024;
+
+// NPAD = padded segment length (power of two <= 16384); every thread performs NPAD/2/BT compare-exchanges per stage,
+// fully unrolled so their shared-memory loads are issued back to back.
+template <uint32_t NPAD>
+__global__ void __launch_bounds__(BT, 1) feature_sort_smem_kernel(const double* __restrict__ Dall, const PartDesc* __restrict__ parts,
+                                                                   uint32_t m, entry_t* __restrict__ Sall) {
+	extern __shared__ __align__(16) unsigned char smraw[];
+	unsigned long long* keys = reinterpret_cast<unsigned long long*>(smraw);            // [NPAD]
+	unsigned short* ids = reinterpret_cast<unsigned short*>(smraw + (size_t)NPAD * 8);   // [NPAD]
+	__shared__ uint32_t wsum[BT / 32];
+	__shared__ uint32_t carry_s;
+	const uint32_t seg = blockIdx.x;
+	const uint32_t pl = seg / m, f = seg % m;
+	const PartDesc pd = parts[pl];
+	const uint32_t N = pd.Ntr;
+	const double* src = Dall + pd.dOffset + (size_t)f * N;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	for (uint32_t i = tid; i < NPAD; i += BT) {
+		keys[i] = (i < N) ? f64_key(src[i]) : 0xFFFFFFFFFFFFFFFFull;
+		ids[i] = (unsigned short)i;
+	}
+	__syncthreads();
+	constexpr uint32_t CE = (NPAD / 2 + BT - 1) / BT;   // compare-exchanges per thread per stage
+	for (uint32_t k = 2; k <= NPAD; k <<= 1) {
+		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+			unsigned long long a[CE], b[CE];
+			uint32_t lo[CE];
+#pragma unroll
+			for (uint32_t q = 0; q < CE; q++) {
+				const uint32_t t = tid + q * BT;
+				lo[q] = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+				a[q] = keys[lo[q] & (NPAD - 1)];
+				b[q] = keys[(lo[q] | j) & (NPAD - 1)];
+			}
+#pragma unroll
+			for (uint32_t q = 0; q < CE; q++) {
+				const uint32_t t = tid + q * BT;
+				const bool up = (lo[q] & k) == 0;
+				if (t < NPAD / 2 && (a[q] > b[q]) == up && a[q] != b[q]) {
+					const uint32_t hi = lo[q] | j;
+					keys[lo[q]] = b[q]; keys[hi] = a[q];
+					const unsigned short ia = ids[lo[q]]; ids[lo[q]] = ids[hi]; ids[hi] = ia;
+				}
+			}
+			__syncthreads();
+		}
+	}
+	entry_t* S = Sall + pd.sOffset + (size_t)f * N;
+	if (tid == 0) carry_s = 0;
+	__syncthreads();
+	for (uint32_t t0 = 0; t0 < N; t0 += BT) {
+		const uint32_t i = t0 + tid;
+		uint32_t flag = (i > 0 && i < N) ? (keys[i] != keys[i - 1]) : 0u;
+		uint32_t inc = flag;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+		if (lane == 31) wsum[w] = inc;
+		__syncthreads();
+		uint32_t off = carry_s;
+		for (int ww = 0; ww < w; ww++) off += wsum[ww];
+		const uint32_t rank = off + inc;
+		if (i < N) S[i] = e_make(ids[i], rank, 0, 0);
+		__syncthreads();
+		if (tid == BT - 1) carry_s = rank;
+		__syncthreads();
+	}
+}
+
+template <uint32_t NPAD>
+static int launch_sort_smem_N(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, entry_t* Sall, cudaStream_t s) {
+	const size_t smem = (size_t)NPAD * 10;
+	if (cudaFuncSetAttribute(feature_sort_smem_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+	feature_sort_smem_kernel<NPAD><<<nPartsBatch * m, BT, smem, s>>>(Dall, parts, m, Sall);
+	return 0;
+}
+
+int launch_feature_sort_smem(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, uint32_t maxNtr, entry_t* Sall,
+                             cudaStream_t s) {
+	if (maxNtr > 16384) return 1;   // caller falls back to the global-memory radix sort
+	if (maxNtr <= 2048) return launch_sort_smem_N<2048>(Dall, parts, nPartsBatch, m, Sall, s);
+	if (maxNtr <= 4096) return launch_sort_smem_N<4096>(Dall, parts, nPartsBatch, m, Sall, s);
+	if (maxNtr <= 8192) return launch_sort_smem_N<8192>(Dall, parts, nPartsBatch, m, Sall, s);
+	return launch_sort_smem_N<16384>(Dall, parts, nPartsBatch, m, Sall, s);
+}
+
 void launch_feature_sort(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, unsigned long long* keysA,
                          unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, entry_t* Sall, cudaStream_t s) {
 	feature_sort_kernel<<<nPartsBatch * m, ST, 0, s>>>(Dall, parts, m, keysA, keysB, valsA, valsB, Sall);

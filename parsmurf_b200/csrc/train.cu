@@ -171,6 +171,37 @@ __device__ void gen_candidates(unsigned long long* mt, uint32_t& pos, uint32_t m
 	}
 }
 
+// Fisher-Yates draw of up to 32 consecutive nodes at once, one node per lane (mtry <= FY_MAX).  Node c of the group uses the
+// mtry stream outputs [c*mtry, (c+1)*mtry) staged in ubuf; the permutation is the identity with at most 2*mtry overrides,
+// kept as a tiny per-lane (position -> value) map.  out[c] == nullptr: the node's draws are consumed but not stored.
+constexpr uint32_t FY_MAX = 8;
+__device__ __forceinline__ void fy_lane(const unsigned long long* ubuf, uint32_t m, uint32_t mtry, uint32_t* out) {
+	uint32_t kpos[2 * FY_MAX], kval[2 * FY_MAX];
+	uint32_t nk = 0;
+	uint32_t res[FY_MAX];
+#pragma unroll
+	for (uint32_t q = 0; q < FY_MAX; q++) {
+		if (q < mtry) {
+			const double u = canonical01(ubuf[q]);
+			const double jd = __dadd_rn((double)q, __dmul_rn(u, (double)(m - q)));     // utility.cpp:133
+			uint32_t j = (uint32_t)__double2ull_rz(jd);
+			if (j >= m) j = m - 1;
+			// value currently at positions q and j
+			uint32_t vq = q, vj = j, iq = 0xFFFFFFFFu, ij = 0xFFFFFFFFu;
+			for (uint32_t t = 0; t < nk; t++) { if (kpos[t] == q) { vq = kval[t]; iq = t; } if (kpos[t] == j) { vj = kval[t]; ij = t; } }
+			res[q] = vj;                                   // perm[q] after the swap
+			if (j != q) {                                  // perm[j] = old perm[q]
+				if (ij != 0xFFFFFFFFu) kval[ij] = vq; else { kpos[nk] = j; kval[nk] = vq; nk++; }
+			}
+			(void)iq;                                      // position q is never read again (later swaps touch positions > q)
+		}
+	}
+	if (out) {
+#pragma unroll
+		for (uint32_t q = 0; q < FY_MAX; q++) if (q < mtry) out[q] = res[q];
+	}
+}
+
 __device__ __forceinline__ void write_leaf(Node16* nd, uint32_t npos, uint32_t nneg) {
 	double n = (double)(npos + nneg);                                     // TreeProbability.cpp:49-62
 	Node16 v;
@@ -186,6 +217,7 @@ __device__ __forceinline__ bool node_live(uint32_t npos, uint32_t nneg) {
 // shared-memory carve-up of the one-warp-per-tree kernels
 struct TreeSmem {
 	unsigned long long* mt;
+	unsigned long long* ubuf;   // 32 * FY_MAX staged stream outputs
 	uint32_t* perm;
 	uint32_t* jbuf;
 	uint32_t* child;   // 64 entries
@@ -193,12 +225,13 @@ struct TreeSmem {
 __device__ __forceinline__ TreeSmem carve(unsigned char* raw, uint32_t m, uint32_t mtry) {
 	TreeSmem s;
 	s.mt = (unsigned long long*)raw;
-	s.perm = (uint32_t*)(raw + MT_N * 8);
+	s.ubuf = s.mt + MT_N;
+	s.perm = (uint32_t*)(raw + (MT_N + 32 * FY_MAX) * 8);
 	s.jbuf = s.perm + m;
 	s.child = s.jbuf + mtry;
 	return s;
 }
-size_t tree_smem_bytes(uint32_t m, uint32_t mtry) { return MT_N * 8 + (size_t)(m + mtry + 64) * 4; }
+size_t tree_smem_bytes(uint32_t m, uint32_t mtry) { return (MT_N + 32 * FY_MAX) * 8 + (size_t)(m + mtry + 64) * 4; }
 
 __device__ __forceinline__ void init_perm(uint32_t* perm, uint32_t m, uint32_t mtry) {
 	const bool fisher = !(mtry < (m + 1) / 10);
@@ -278,29 +311,42 @@ __device__ __forceinline__ void ss_load(const E* __restrict__ base, uint32_t v, 
 	}
 }
 
-template <typename E>
+// G = lanes per (node, candidate) work item.  G = 32 streams long segments chunk by chunk (128 entries per iteration);
+// G = 16 / 8 pack two / four short segments (<= 64 / <= 32 entries of the aligned grid) into one warp: at deep levels
+// most nodes hold a few dozen rows and the kernel is instruction-issue bound (ncu r01), so the per-warp fixed cost is
+// shared by up to four work items.  Every item is processed by exactly one of the three instantiations.
+template <typename E, int G>
 __global__ void __launch_bounds__(128, 8) split_search_kernel(TrainArgs A, uint32_t nItems, int buf) {
-	const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (wid >= nItems * A.mtry) return;
-	const uint32_t item = wid / A.mtry, c = wid % A.mtry;
+	const uint32_t gid = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
+	if (gid >= nItems * A.mtry) return;
+	const uint32_t item = gid / A.mtry, c = gid % A.mtry;
 	const Item it = A.items[buf][item];
-	const uint32_t f = A.cand[(size_t)item * A.mtry + c];
-	const int lane = lane_id();
 	constexpr uint32_t APE = 16 / sizeof(E);                  // entries per 16 bytes
 	const uint32_t off = it.start % APE;                      // A.stride % 4 == 0, so list + start - off is 16-byte aligned
+	const uint32_t lo = off, hi = it.cnt + off;                // valid index range in the aligned grid
+	if (G == 8 && hi > 32) return;
+	if (G == 16 && (hi <= 32 || hi > 64)) return;
+	if (G == 32 && hi <= 64) return;
+	const int lane = lane_id();
+	const int gl = lane % G;
+	const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));
+	const uint32_t f = A.cand[(size_t)item * A.mtry + c];
 	const uint32_t nPosOut = A.parts[it.tree / A.T].nPosOut;
 	const E* base = reinterpret_cast<const E*>(A.lists[A.listBuf]) + ((size_t)it.tree * A.m + f) * A.stride + (it.start - off);
-	const uint32_t lo = off, hi = it.cnt + off;                // valid index range in the aligned grid
 	const uint32_t n = it.npos + it.nneg;
 	uint32_t lp = 0, ln = 0;
 	double best = -1.0;
-	float wbound = 0.0f;                                      // warp-uniform: (best exact score of earlier chunks) * (1 - 4e-6)
+	float wbound = 0.0f;                                      // group-uniform: (best exact score of earlier chunks) * (1 - 4e-6)
 	uint32_t bpos = 0xFFFFFFFFu, blp = 0, bln = 0;
 	E e[SS_IPL], nx[SS_IPL];
-	ss_load<E>(base, lane * SS_IPL, lo, hi, e);
-	for (uint32_t b = 0; b < hi; b += 32 * SS_IPL) {
-		const uint32_t v0 = b + lane * SS_IPL;
-		ss_load<E>(base, v0 + 32 * SS_IPL, lo, hi, nx);       // prefetch the next chunk
+	ss_load<E>(base, gl * SS_IPL, lo, hi, e);
+	for (uint32_t b = 0; b < hi; b += G * SS_IPL) {
+		const uint32_t v0 = b + gl * SS_IPL;
+		if (G == 32) ss_load<E>(base, v0 + G * SS_IPL, lo, hi, nx);   // prefetch the next chunk (short segments have none)
+		else {
+#pragma unroll
+			for (int j = 0; j < SS_IPL; j++) nx[j] = (E)0;
+		}
 		// lane-local inclusive prefix of (positives, negatives), packed hi/lo in one u64
 		unsigned long long pk[SS_IPL];
 		unsigned long long run = 0;
@@ -312,13 +358,13 @@ __global__ void __launch_bounds__(128, 8) split_search_kernel(TrainArgs A, uint3
 		}
 		unsigned long long inc = run;
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-			if (lane >= o) inc += t;
+		for (int o = 1; o < G; o <<= 1) {
+			unsigned long long t = __shfl_up_sync(gm, inc, o, G);
+			if (gl >= o) inc += t;
 		}
 		const unsigned long long excl = inc - run;
-		const uint32_t rfirst_next_lane = Ent<E>::rank(__shfl_down_sync(0xffffffffu, e[0], 1));
-		const uint32_t rfirst_next_chunk = Ent<E>::rank(__shfl_sync(0xffffffffu, nx[0], 0));
+		const uint32_t rfirst_next_lane = Ent<E>::rank(__shfl_down_sync(gm, e[0], 1, G));
+		const uint32_t rfirst_next_chunk = Ent<E>::rank(__shfl_sync(gm, nx[0], 0, G));
 		// phase 1: fp32 estimate of the Gini proxy at every candidate position of the chunk (no divisions)
 		float est[SS_IPL];
 		float emax = 0.0f;
@@ -326,7 +372,7 @@ __global__ void __launch_bounds__(128, 8) split_search_kernel(TrainArgs A, uint3
 		for (int j = 0; j < SS_IPL; j++) {
 			const uint32_t v = v0 + j;
 			const uint32_t rk = Ent<E>::rank(e[j]);
-			const uint32_t rnext = (j + 1 < SS_IPL) ? Ent<E>::rank(e[(j + 1) % SS_IPL]) : (lane == 31 ? rfirst_next_chunk : rfirst_next_lane);
+			const uint32_t rnext = (j + 1 < SS_IPL) ? Ent<E>::rank(e[(j + 1) % SS_IPL]) : (gl == G - 1 ? rfirst_next_chunk : rfirst_next_lane);
 			est[j] = -1.0f;
 			if (v >= lo && v + 1 < hi && rk != rnext) {
 				const unsigned long long tot = excl + pk[j];
@@ -341,12 +387,12 @@ __global__ void __launch_bounds__(128, 8) split_search_kernel(TrainArgs A, uint3
 		// Only positions whose estimate is within the estimate's error (< 1e-6 relative; margin 4e-6) of the best
 		// estimate of this chunk, or of the best exact score of earlier chunks, can be the arg-max: evaluate those
 		// exactly (two IEEE fp64 divisions, TreeProbability.cpp:337).  Estimates are >= 0, so their bit patterns order
-		// like unsigned integers and one redux gives the warp maximum.
-		const float cmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(emax)));
+		// like unsigned integers and one redux gives the group maximum.
+		const float cmax = __uint_as_float(__reduce_max_sync(gm, __float_as_uint(emax)));
 		const float thr = fmaxf(cmax * 0.999996f, wbound);
 #pragma unroll
 		for (int j = 0; j < SS_IPL; j++) {
-			if (__any_sync(0xffffffffu, est[j] >= thr)) {
+			if (__any_sync(gm, est[j] >= thr)) {
 				if (est[j] >= thr) {
 					const unsigned long long tot = excl + pk[j];
 					const uint32_t lpi = lp + (uint32_t)(tot >> 32), lni = ln + (uint32_t)tot;
@@ -359,27 +405,27 @@ __global__ void __launch_bounds__(128, 8) split_search_kernel(TrainArgs A, uint3
 				}
 			}
 		}
-		// warp-uniform bound for the following chunks: a later position must strictly beat the best exact score so far
-		{
+		if (G == 32) {
+			// group-uniform bound for the following chunks: a later position must strictly beat the best exact score so far
 			const float bf = best > 0.0 ? __double2float_rd(best) : 0.0f;
-			const float wb = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(bf)));
+			const float wb = __uint_as_float(__reduce_max_sync(gm, __float_as_uint(bf)));
 			wbound = wb * 0.999996f;
+			const unsigned long long tot = __shfl_sync(gm, inc, G - 1, G);
+			lp += (uint32_t)(tot >> 32); ln += (uint32_t)tot;
+#pragma unroll
+			for (int j = 0; j < SS_IPL; j++) e[j] = nx[j];
 		}
-		const unsigned long long tot = __shfl_sync(0xffffffffu, inc, 31);
-		lp += (uint32_t)(tot >> 32); ln += (uint32_t)tot;
-#pragma unroll
-		for (int j = 0; j < SS_IPL; j++) e[j] = nx[j];
 	}
-	// arg-max over lanes: highest score, then lowest position (ascending value order, strict '>')
+	// arg-max over the group's lanes: highest score, then lowest position (ascending value order, strict '>')
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		double os = __shfl_xor_sync(0xffffffffu, best, o);
-		uint32_t op = __shfl_xor_sync(0xffffffffu, bpos, o);
-		uint32_t olp = __shfl_xor_sync(0xffffffffu, blp, o);
-		uint32_t oln = __shfl_xor_sync(0xffffffffu, bln, o);
+	for (int o = G / 2; o > 0; o >>= 1) {
+		double os = __shfl_xor_sync(gm, best, o, G);
+		uint32_t op = __shfl_xor_sync(gm, bpos, o, G);
+		uint32_t olp = __shfl_xor_sync(gm, blp, o, G);
+		uint32_t oln = __shfl_xor_sync(gm, bln, o, G);
 		if (os > best || (os == best && op < bpos)) { best = os; bpos = op; blp = olp; bln = oln; }
 	}
-	if (lane == 0) {
+	if (gl == 0) {
 		SearchRes r; r.score = best; r.pos = bpos; r.lpos = blp; r.lneg = bln; r.pad = 0;
 		A.res[(size_t)item * A.mtry + c] = r;
 	}
@@ -426,7 +472,14 @@ __global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t
 		A.dec[item] = d;
 	}
 	unsigned char* flags = A.flags + (size_t)it.tree * A.stride;
-	for (uint32_t i = lane; i < it.cnt; i += 32) flags[Ent<E>::row(list[i])] = (i <= r.pos) ? 1 : 0;
+	// latency-bound (load entry -> scattered byte store): keep four independent loads in flight per lane
+	for (uint32_t b = 0; b < it.cnt; b += 128) {
+		E e4[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) { const uint32_t i = b + k * 32 + lane; e4[k] = (i < it.cnt) ? __ldg(list + i) : (E)0; }
+#pragma unroll
+		for (int k = 0; k < 4; k++) { const uint32_t i = b + k * 32 + lane; if (i < it.cnt) flags[Ent<E>::row(e4[k])] = (i <= r.pos) ? 1 : 0; }
+	}
 }
 
 // ------------------------------------------------------------------------------------------ level finalize
@@ -510,14 +563,35 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 		}
 		__syncwarp();
 		const uint32_t nchild = 2 * __popc(smask);
-		for (uint32_t c = 0; c < nchild; c++) {
-			const uint32_t ci = sm.child[c];
-			if (A.injCand) {
-				if (ci != 0xFFFFFFFFu)
-					for (uint32_t q = lane; q < A.mtry; q += 32)
-						A.cand[(size_t)ci * A.mtry + q] = A.injCand[((size_t)tree * A.injCandNodes + (childBase + c)) * A.mtry + q];
-			} else {
-				gen_candidates(sm.mt, pos, A.m, A.mtry, sm.perm, sm.jbuf, ci != 0xFFFFFFFFu ? A.cand + (size_t)ci * A.mtry : nullptr);
+		const bool laneFY = !A.injCand && A.mtry <= FY_MAX && !(A.mtry < (A.m + 1) / 10);
+		if (laneFY) {
+			// one node per lane: stage the next 32*mtry stream outputs (tempered) and draw up to 32 nodes at once
+			for (uint32_t c0 = 0; c0 < nchild; c0 += 32) {
+				const uint32_t nc = min(32u, nchild - c0);
+				uint32_t need = nc * A.mtry, got = 0;
+				while (got < need) {
+					if (pos == MT_N) { mt_twist(sm.mt); pos = 0; }
+					const uint32_t take = min(need - got, (uint32_t)MT_N - pos);
+					for (uint32_t q = lane; q < take; q += 32) sm.ubuf[got + q] = mt_temper(sm.mt[pos + q]);
+					got += take; pos += take;
+				}
+				__syncwarp();
+				if ((uint32_t)lane < nc) {
+					const uint32_t ci = sm.child[c0 + lane];
+					fy_lane(sm.ubuf + (size_t)lane * A.mtry, A.m, A.mtry, ci != 0xFFFFFFFFu ? A.cand + (size_t)ci * A.mtry : nullptr);
+				}
+				__syncwarp();
+			}
+		} else {
+			for (uint32_t c = 0; c < nchild; c++) {
+				const uint32_t ci = sm.child[c];
+				if (A.injCand) {
+					if (ci != 0xFFFFFFFFu)
+						for (uint32_t q = lane; q < A.mtry; q += 32)
+							A.cand[(size_t)ci * A.mtry + q] = A.injCand[((size_t)tree * A.injCandNodes + (childBase + c)) * A.mtry + q];
+				} else {
+					gen_candidates(sm.mt, pos, A.m, A.mtry, sm.perm, sm.jbuf, ci != 0xFFFFFFFFu ? A.cand + (size_t)ci * A.mtry : nullptr);
+				}
 			}
 		}
 		__syncwarp();
@@ -620,8 +694,17 @@ int launch_init_trees(const TrainArgs& A, cudaStream_t s) {
 }
 void launch_split_search(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
 	size_t warps = (size_t)nItems * A.mtry;
-	if (A.entry32) split_search_kernel<uint32_t><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
-	else split_search_kernel<unsigned long long><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
+	const size_t groups = warps;   // one work item per (node, candidate)
+	const unsigned b32 = (unsigned)((groups * 32 + 127) / 128), b16 = (unsigned)((groups * 16 + 127) / 128), b8 = (unsigned)((groups * 8 + 127) / 128);
+	if (A.entry32) {
+		split_search_kernel<uint32_t, 32><<<b32, 128, 0, s>>>(A, nItems, buf);
+		split_search_kernel<uint32_t, 16><<<b16, 128, 0, s>>>(A, nItems, buf);
+		split_search_kernel<uint32_t, 8><<<b8, 128, 0, s>>>(A, nItems, buf);
+	} else {
+		split_search_kernel<unsigned long long, 32><<<b32, 128, 0, s>>>(A, nItems, buf);
+		split_search_kernel<unsigned long long, 16><<<b16, 128, 0, s>>>(A, nItems, buf);
+		split_search_kernel<unsigned long long, 8><<<b8, 128, 0, s>>>(A, nItems, buf);
+	}
 }
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
 	if (A.entry32) split_select_kernel<uint32_t><<<(nItems + 3) / 4, 128, 0, s>>>(A, nItems, buf);

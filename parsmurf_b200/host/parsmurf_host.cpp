@@ -132,21 +132,29 @@ TestTrainDivider::TestTrainDivider(const Folds* folds_, uint8_t wmode_, GlibcRan
 		uint64_t nneg = folds->totNeg - folds->nNeg[i];
 		off[i + 1] = off[i] + (nneg > 0 ? nneg - 1 : 0);
 	}
-	std::vector<std::thread> th;
+	for (uint32_t i = 0; i < nFolds; i++) {                                  // counts are known without building anything
+		testPosNum.push_back(folds->nPos[i]); testNegNum.push_back(folds->nNeg[i]);
+		trngPosNum.push_back(folds->totPos - folds->nPos[i]); trngNegNum.push_back(folds->totNeg - folds->nNeg[i]);
+	}
+	if (wmode == MODE_TRAIN) { trngPosNum[0] = testPosNum[0]; trngNegNum[0] = testNegNum[0]; }   // :33-36
+	joined.assign(nFolds, 0);
+	const GlibcRand start = *rng;
 	for (uint32_t i = 0; i < nFolds; i++)
-		th.emplace_back([this, i, rng, &off]() {
-			GlibcRand local = *rng;
+		workers.emplace_back([this, i, start, off]() {
+			GlibcRand local = start;
 			local.discard(off[i]);
 			build(i, i, -1);
-			local.shuffle(trngNegIdx[i].data(), trngNegIdx[i].size());
+			local.shuffle(trngNegIdx[i].data(), trngNegIdx[i].size());      // :90
+			if (this->wmode == MODE_TRAIN && i == 0) { trngPosIdx[0] = testPosIdx[0]; trngNegIdx[0] = testNegIdx[0]; }   // :101-104
 		});
-	for (auto& t : th) t.join();
 	rng->discard(off[nFolds]);
-	if (wmode == MODE_TRAIN) { trngPosIdx[0] = testPosIdx[0]; trngNegIdx[0] = testNegIdx[0]; }   // :101-104
-	for (uint32_t i = 0; i < nFolds; i++) {
-		testPosNum.push_back(testPosIdx[i].size()); testNegNum.push_back(testNegIdx[i].size());
-		trngPosNum.push_back(trngPosIdx[i].size()); trngNegNum.push_back(trngNegIdx[i].size());
-	}
+}
+
+TestTrainDivider::~TestTrainDivider() {
+	for (size_t i = 0; i < workers.size(); i++) if (!joined[i]) workers[i].join();
+}
+void TestTrainDivider::ensure(uint32_t fold) const {
+	if (fold < workers.size() && !joined[fold]) { workers[fold].join(); joined[fold] = 1; }
 }
 
 // src/testtraindivider.cpp:126-236 -- inner CV: fold `foldToJump` is left out entirely, no shuffle
@@ -172,6 +180,7 @@ Partition::Partition(const Folds* folds_, const TestTrainDivider* ttd_, uint32_t
 }
 void Partition::setFold(uint32_t f) {
 	currentFold = f;
+	ttd->ensure(f);
 	trngPosNum = ttd->trngPosNum[f]; trngNegNum = ttd->trngNegNum[f]; testPosNum = ttd->testPosNum[f]; testNegNum = ttd->testNegNum[f];
 	trngPosIdx = ttd->trngPosIdx[f].data(); trngNegIdx = ttd->trngNegIdx[f].data();
 	testPosIdx = ttd->testPosIdx[f].data(); testNegIdx = ttd->testNegIdx[f].data();
@@ -400,6 +409,7 @@ void hyperSMURF::smurfIt() {                                                // s
 	if (inInternalCV) {                                                     // :456-482
 		std::vector<uint32_t> tl; std::vector<double> tp;
 		for (uint32_t f = 0; f < nFolds; f++) {
+			ttd->ensure(f);
 			for (uint32_t v : ttd->testPosIdx[f]) { tl.push_back(y[v]); tp.push_back(class1Prob[v]); }
 			for (uint32_t v : ttd->testNegIdx[f]) { tl.push_back(y[v]); tp.push_back(class1Prob[v]); }
 		}
@@ -630,6 +640,7 @@ int psmh_ttd_fold(const uint32_t* labels, const uint32_t* foldAssign, uint32_t n
 		folds.computeFolds();
 		std::unique_ptr<TestTrainDivider> t(foldToJump < 0 ? new TestTrainDivider(&folds, MODE_CV, &rng) : new TestTrainDivider(&folds, MODE_CV, (uint32_t)foldToJump));
 		if (fold >= t->nFolds) return PSM_E_ARG;
+		t->ensure(fold);
 		sizes[0] = t->trngPosNum[fold]; sizes[1] = t->trngNegNum[fold]; sizes[2] = t->testPosNum[fold]; sizes[3] = t->testNegNum[fold];
 		if (trngPos) std::copy(t->trngPosIdx[fold].begin(), t->trngPosIdx[fold].end(), trngPos);
 		if (trngNeg) std::copy(t->trngNegIdx[fold].begin(), t->trngNegIdx[fold].end(), trngNeg);

@@ -18,6 +18,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/parsmurf_b200.h"
@@ -93,6 +94,10 @@ class TestTrainDivider {
 public:
 	TestTrainDivider(const Folds* folds, uint8_t wmode, GlibcRand* rng);
 	TestTrainDivider(const Folds* folds, uint8_t wmode, uint32_t foldToJump);
+	~TestTrainDivider();
+	// the per-fold index arrays are built (and shuffled) by background threads; the counts are valid immediately,
+	// the arrays of fold f after ensure(f)
+	void ensure(uint32_t fold) const;
 	const Folds* const folds;
 	const uint8_t wmode;
 	uint32_t nFolds;
@@ -100,6 +105,8 @@ public:
 	std::vector<uint32_t> testPosNum, testNegNum, trngPosNum, trngNegNum;
 private:
 	void build(uint32_t i, uint32_t currFoldIdx, int64_t foldToJump);
+	mutable std::vector<std::thread> workers;
+	mutable std::vector<char> joined;
 };
 
 // reference src/partition.h:7-36

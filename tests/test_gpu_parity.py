@@ -189,8 +189,9 @@ def test_trees_bit_exact(ctx, oracle, name):
 
 
 def test_trees_bit_exact_wide_entries(ctx, oracle, monkeypatch):
-    """the general 8-byte list-entry layout (used when Ntr > 16384) grows the same trees as the compact one"""
+    """the general paths used when Ntr > 16384 (8-byte list entries, global-memory radix sort) grow the same trees"""
     monkeypatch.setenv("PSM_FORCE_ENTRY64", "1")
+    monkeypatch.setenv("PSM_FORCE_RADIX_SORT", "1")
     case = make_case("ties_ratio0")
     x, fd, seeds = _train_case(ctx, oracle, case)
     for p in range(case["nParts"]):
