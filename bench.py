@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # BASELINE.json configs[1]
     "cfg2": dict(n=1_000_000, m=26, npos=1000, nFolds=5, nParts=100, fp=2, ratio=3, k=5, nTrees=10, mtry=5, seed=1, shift=5),
+    # BASELINE.json configs[2] (Mendelian scale; fp/ratio/k assumed as configs[1]) and configs[3] (high-dimensional)
+    "cfg3": dict(n=14_000_000, m=26, npos=400, nFolds=10, nParts=1000, fp=2, ratio=3, k=5, nTrees=10, mtry=5, seed=1, shift=5),
+    "cfg4": dict(n=200_000, m=1000, npos=10_000, nFolds=5, nParts=10, fp=2, ratio=3, k=10, nTrees=10, mtry=31, seed=1, shift=50),
     # small smoke-sized variant for quick checks (not a bench line)
     "small": dict(n=50_000, m=26, npos=200, nFolds=5, nParts=10, fp=2, ratio=3, k=5, nTrees=10, mtry=5, seed=1, shift=5),
 }
@@ -144,8 +147,8 @@ def run_reference(args, w):
 
 
 def workload_config(args, w):
-    return {"workload": "BASELINE.json configs[1]: synthetic %dx%d imbalanced 1:%d, nParts=%d, fp=%d, ratio=%d, k=%d, nTrees=%d, mtry=%d, %d-fold CV"
-            % (w["n"], w["m"], w["n"] // w["npos"], w["nParts"], w["fp"], w["ratio"], w["k"], w["nTrees"], w["mtry"], w["nFolds"]),
+    return {"workload": "BASELINE.json %s: synthetic %dx%d imbalanced 1:%d, nParts=%d, fp=%d, ratio=%d, k=%d, nTrees=%d, mtry=%d, %d-fold CV"
+            % ({"cfg2": "configs[1]", "cfg3": "configs[2]", "cfg4": "configs[3]"}.get(args.workload, args.workload), w["n"], w["m"], w["n"] // w["npos"], w["nParts"], w["fp"], w["ratio"], w["k"], w["nTrees"], w["mtry"], w["nFolds"]),
             "partitions_per_step": w["nParts"] * w["nFolds"], "parallelism": "partitions sharded over %d GPU(s), dataset replicated, one NCCL all-reduce of fold scores per fold" % args.gpus,
             "l2_policy": "inputs larger than L2 (dataset 216 MB + per-fold training batch ~2.7 GB >> 126 MB L2); no explicit flush",
             "curves_tie_mode": "device radix sort (stable)"}

@@ -62,7 +62,7 @@ struct psm_ctx {
 	// train
 	uint32_t T = 0, mtry = 0;
 	TrainArgs A;
-	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dFlags, dFlagBits, dItems0, dItems1, dCand, dRes, dDec, dCounters, dStats, dSeeds,
+	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dNodes8, dFlags, dFlagBits, dItems0, dItems1, dCand, dRes, dDec, dCounters, dStats, dSeeds,
 	    dInjBoot, dInjBootOff, dInjCand;
 	uint32_t* hCounters = nullptr;   // pinned
 	void* hStage = nullptr;          // pinned D2H staging
@@ -180,7 +180,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf* bufs[] = {&ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dClass12,
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
-	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dFlags, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1,
+	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dFlags, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
 	                  &ctx->dInjCand, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
 	                  &ctx->cScores, &ctx->cKeysA, &ctx->cKeysB, &ctx->cValsA, &ctx->cValsB, &ctx->cHist};
@@ -412,7 +412,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	CU(cudaSetDevice(ctx->device));
 	const uint32_t m = ctx->m, nB = ctx->nB, stride = (ctx->maxNtr + 3) & ~3u;   // multiple of 4: keeps every list 16-byte aligned
 	const uint32_t nTrees = nB * T;
-	const uint32_t NC = 2 * stride + 2;
+	const uint32_t NC = 2 * stride + 2;   // even
 	const uint64_t itemCap64 = (uint64_t)nTrees * (stride / 11 + 2);
 	if (itemCap64 >= (1ull << 31)) return fail(ctx, PSM_E_LIMIT, "batch_train: batch too large (reduce the batch budget)");
 	const uint32_t itemCap = (uint32_t)itemCap64;
@@ -431,6 +431,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	ENSURE(ctx->dMt, (size_t)nTrees * 312 * 8);
 	ENSURE(ctx->dTs, (size_t)nTrees * sizeof(TreeState));
 	ENSURE(ctx->dNodes, (size_t)nTrees * NC * sizeof(Node16));
+	ENSURE(ctx->dNodes8, (size_t)nTrees * NC * 8);
 	ENSURE(ctx->dFlags, (size_t)nTrees * stride);
 	const uint32_t flagWords = (stride + 31) / 32;
 	ENSURE(ctx->dFlagBits, (size_t)nTrees * flagWords * 4);
@@ -535,7 +536,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		cudaEvent_t tev[5];
 		if (trace) for (auto& e : tev) cudaEventCreate(&e);
 		if (trace) cudaEventRecord(tev[0], s);
-		{ ProfScope ps(ctx, K_SEARCH, 3); launch_split_search(A, nItems, buf, s); }
+		{ ProfScope ps(ctx, K_SEARCH, 1); launch_split_search(A, nItems, buf, s); }
 		if (trace) cudaEventRecord(tev[1], s);
 		{ ProfScope ps(ctx, K_SELECT, 2); launch_split_select(A, nItems, buf, s); launch_pack_flags(A, s); }
 		if (trace) cudaEventRecord(tev[2], s);
@@ -626,8 +627,9 @@ int psm_batch_predict_accumulate(psm_ctx* ctx, uint32_t nPartsTotal) {
 	CU(cudaSetDevice(ctx->device));
 	ENSURE(ctx->dPredScratch, (size_t)ctx->nB * 2 * ctx->Nte * 8);
 	{
-		ProfScope ps(ctx, K_PREDICT, 2);
-		if (launch_predict(ctx->x, ctx->m, ctx->dTest.as<uint32_t>(), ctx->Nte, ctx->A.nodes, ctx->A.NC, ctx->A.ts, ctx->maxNodes, ctx->nB, ctx->T,
+		ProfScope ps(ctx, K_PREDICT, 3);
+		launch_pack_forest(ctx->A.nodes, ctx->A.ts, ctx->A.NC, ctx->A.nTrees, ctx->dNodes8.p, ctx->stream);
+		if (launch_predict(ctx->x, ctx->m, ctx->dTest.as<uint32_t>(), ctx->Nte, ctx->A.nodes, ctx->dNodes8.p, ctx->A.NC, ctx->A.ts, ctx->maxNodes, ctx->nB, ctx->T,
 		                   ctx->dPredScratch.as<double>(), ctx->stream))
 			return fail(ctx, PSM_E_CUDA, "predict_accumulate: cannot configure shared memory");
 		launch_accumulate(ctx->dPredScratch.as<double>(), ctx->Nte, ctx->nB, 1.0 / (double)nPartsTotal, ctx->dClass12.as<double>(), ctx->stream);

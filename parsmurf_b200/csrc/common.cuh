@@ -75,6 +75,8 @@ struct Item {
 	uint32_t cnt;     // entries in the segment
 	uint32_t npos;    // samples (with multiplicity) of class 0
 	uint32_t nneg;    // samples of class 1
+	uint32_t nPosOut; // rows below this id are positives (label of compact list entries)
+	uint32_t pad;
 };
 
 struct SearchRes {

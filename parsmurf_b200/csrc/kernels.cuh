@@ -67,7 +67,8 @@ void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaSt
 void glibc_window_jump(uint32_t* w31, uint64_t n);
 int launch_glibc_rand_fill(const uint32_t* w31, unsigned long long count, uint32_t* scratchDev, int32_t* out, cudaStream_t s);
 // predict.cu
-int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_t Nte, const Node16* nodes, uint32_t NC,
+void launch_pack_forest(const Node16* nodes, const TreeState* ts, uint32_t NC, uint32_t nTrees, void* nodes8, cudaStream_t s);
+int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_t Nte, const Node16* nodes, const void* nodes8, uint32_t NC,
                    const TreeState* ts, uint32_t maxNodes, uint32_t nPartsBatch, uint32_t T, double* scratch, cudaStream_t s);
 void launch_accumulate(const double* scratch, uint32_t Nte, uint32_t nPartsBatch, double divider, double* class12, cudaStream_t s);
 // curves.cu

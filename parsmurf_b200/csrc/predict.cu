@@ -15,6 +15,8 @@
 // partition order -- the reference's fp64 summation order at ensThrd = 1, so scores are bit-identical.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace psm {
 
 constexpr int PT = 256;   // rows per CTA
@@ -165,6 +167,164 @@ __global__ void __launch_bounds__(PT) predict_tma_kernel(const double* __restric
 	}
 }
 
+// ---- compact path: 8-byte nodes {float(threshold), feature:12 | left child:20} and an fp32 row tile ----------------------
+// double -> float rounding is monotone, so  float(v) < float(thr)  implies  v < thr  and  float(v) > float(thr)  implies
+// v > thr; only float(v) == float(thr) is undecided and is resolved with the exact fp64 values from global memory (about one
+// visit in 10^7).  Decisions are therefore identical to ranger's fp64 `value <= split_value` (Tree.cpp:163), while shared
+// memory per CTA drops from 88 KB to 44 KB (5 CTAs/SM instead of 2) and a node visit costs LDS.64 + LDS.32 instead of
+// LDS.128 + LDS.64 (ncu r01: the 16-byte-node kernel is bound by shared-memory wavefronts and LDS latency).
+// Leaf payloads are the exact fp64 fractions count_c / n (TreeProbability.cpp:47-63).  Almost every leaf is pure or has
+// n <= 10 samples (min_node_size), so its pair of fractions is one of the 66 values p/n, n <= 10: the leaf stores the code
+// n*11+p and the kernel looks the two doubles up in a shared-memory table built with the same IEEE division; the rare other
+// leaf (a larger node without a valid split) stores code 0xFFFFFFFF and reads its fractions from the 16-byte node array.
+struct __align__(8) Node8 {
+	float thr;       // internal: float(threshold); leaf: fraction code (as bits)
+	uint32_t meta;   // internal: feature | left << 12 ; leaf: 0xFFFFFFFF
+};
+constexpr int LEAF_TAB = 121;
+
+__global__ void __launch_bounds__(256) pack_forest_kernel(const Node16* __restrict__ nodes, const TreeState* __restrict__ ts, uint32_t NC,
+                                                           uint32_t nTrees, Node8* __restrict__ out) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (size_t)nTrees * NC) return;
+	const uint32_t tree = (uint32_t)(i / NC), node = (uint32_t)(i % NC);
+	Node8 o; o.thr = 0.0f; o.meta = 0xFFFFFFFFu;
+	if (node < ts[tree].nNodes) {
+		const Node16 nd = nodes[i];
+		if (!node_is_leaf(nd)) { o.thr = __double2float_rn(nd.a); o.meta = (uint32_t)(nd.b & 0xFFFu) | ((uint32_t)(nd.b >> 32) << 12); }
+		else {
+			const double f0 = nd.a, f1 = __longlong_as_double((long long)(nd.b & 0x7FFFFFFFFFFFFFFFull));
+			uint32_t code = 0xFFFFFFFFu;
+			for (int n = 1; n <= 10 && code == 0xFFFFFFFFu; n++)
+				for (int p2 = 0; p2 <= n; p2++)
+					if (__ddiv_rn((double)p2, (double)n) == f0 && __ddiv_rn((double)(n - p2), (double)n) == f1) { code = (uint32_t)(n * 11 + p2); break; }
+			o.thr = __uint_as_float(code);
+		}
+	}
+	out[i] = o;
+}
+
+constexpr uint32_t TPS = 1;    // trees per pipeline stage
+constexpr uint32_t NBUF = 2;   // pipeline depth: the TMA runs NBUF-1 stages ahead of the traversal (deeper pipelines cost occupancy and measured slower)
+
+__global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __restrict__ x, uint32_t m, const uint32_t* __restrict__ testIdx,
+                                                              uint32_t Nte, const Node16* __restrict__ nodes, const Node8* __restrict__ nodes8,
+                                                              uint32_t NC, const TreeState* __restrict__ ts, uint32_t nPartsBatch, uint32_t T,
+                                                              uint32_t pch, uint32_t maxNodes, double* __restrict__ scratch) {
+	extern __shared__ __align__(128) unsigned char smraw[];
+	float* tile = reinterpret_cast<float*>(smraw);                                     // [m][PT]
+	Node8* tbuf = reinterpret_cast<Node8*>(smraw + (size_t)m * PT * sizeof(float));    // [NBUF][TPS][maxNodes]
+	uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf + (size_t)NBUF * TPS * maxNodes);   // [NBUF]
+	__shared__ double ltab[2][LEAF_TAB];
+	const uint32_t ld = m + 1;
+	const uint32_t r0 = blockIdx.x * PT;
+	const int tid = threadIdx.x;
+	const uint32_t p0 = blockIdx.y * pch;
+	const uint32_t p1 = min(p0 + pch, nPartsBatch);
+	const uint32_t g0 = p0 * T, nT = (p1 - p0) * T;
+	const uint32_t nStages = (nT + TPS - 1) / TPS;
+	if (tid < LEAF_TAB) {
+		const int n = tid / 11, p2 = tid % 11;
+		const bool ok = n >= 1 && p2 <= n;
+		ltab[0][tid] = ok ? __ddiv_rn((double)p2, (double)n) : 0.0;
+		ltab[1][tid] = ok ? __ddiv_rn((double)(n - p2), (double)n) : 0.0;
+	}
+	if (tid == 0) {
+		for (uint32_t q = 0; q < NBUF; q++) mbar_init(&bars[q], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	// thread 0 is the TMA producer; the tree sizes of the stage after next are fetched one stage early so that the global
+	// load latency never sits on the critical path of the block
+	uint32_t szNext[TPS];
+	auto load_sizes = [&](uint32_t stage, uint32_t (&sz)[TPS]) {
+#pragma unroll
+		for (uint32_t q = 0; q < TPS; q++) {
+			const uint32_t t = stage * TPS + q;
+			sz[q] = (t < nT) ? ((ts[g0 + t].nNodes + 1u) & ~1u) * (uint32_t)sizeof(Node8) : 0u;
+		}
+	};
+	auto issue_stage = [&](uint32_t stage, const uint32_t (&sz)[TPS]) {
+		const uint32_t bb = stage % NBUF;
+		uint32_t total = 0;
+#pragma unroll
+		for (uint32_t q = 0; q < TPS; q++) total += sz[q];
+		mbar_expect_tx(&bars[bb], total);
+#pragma unroll
+		for (uint32_t q = 0; q < TPS; q++)
+			if (sz[q]) tma_bulk_g2s(tbuf + ((size_t)bb * TPS + q) * maxNodes, nodes8 + (size_t)(g0 + stage * TPS + q) * NC, sz[q], &bars[bb]);
+	};
+	if (tid == 0) {
+		for (uint32_t q = 0; q + 1 < NBUF && q < nStages; q++) {
+			uint32_t sz0[TPS];
+			load_sizes(q, sz0);
+			issue_stage(q, sz0);
+		}
+		load_sizes(NBUF - 1, szNext);
+	}
+	{
+		const int lane = tid & 31, w = tid >> 5;
+		for (int rr = w; rr < PT; rr += PT / 32) {
+			uint32_t r = r0 + rr;
+			if (r < Nte) {
+				const double* src = x + (size_t)testIdx[r] * ld;
+				for (uint32_t c = lane; c < m; c += 32) tile[(size_t)c * PT + rr] = __double2float_rn(src[c]);
+			}
+		}
+	}
+	__syncthreads();
+	const uint32_t row = r0 + tid;
+	const bool valid = row < Nte;
+	const double* xr = x + (size_t)testIdx[valid ? row : 0] * ld;
+	const double Td = (double)T;
+	double s0 = 0.0, s1 = 0.0;
+	for (uint32_t st = 0; st < nStages; st++) {
+		const uint32_t b = st % NBUF;
+		if (tid == 0 && st + NBUF - 1 < nStages) {        // its buffer was released by the barrier that ended stage st-1
+			issue_stage(st + NBUF - 1, szNext);
+			load_sizes(st + NBUF, szNext);
+		}
+		mbar_wait(&bars[b], (st / NBUF) & 1);
+		if (valid) {
+#pragma unroll 1
+			for (uint32_t q = 0; q < TPS; q++) {
+				const uint32_t i = st * TPS + q;
+				if (i >= nT) break;
+				const uint2* base = reinterpret_cast<const uint2*>(tbuf + ((size_t)b * TPS + q) * maxNodes);
+				const Node16* gtree = nodes + (size_t)(g0 + i) * NC;
+				uint32_t idx = 0;
+				uint2 nd;
+				while (true) {
+					nd = base[idx];
+					if (nd.y == 0xFFFFFFFFu) break;
+					const uint32_t feat = nd.y & 0xFFFu, left = nd.y >> 12;
+					const float thr = __uint_as_float(nd.x);
+					const float v = tile[(size_t)feat * PT + tid];
+					bool goLeft = v < thr;
+					if (v == thr) goLeft = xr[feat] <= gtree[idx].a;         // undecided in fp32: exact fp64 comparison
+					idx = left + (goLeft ? 0u : 1u);
+				}
+				double f0, f1;
+				if (nd.x < (uint32_t)LEAF_TAB) { f0 = ltab[0][nd.x]; f1 = ltab[1][nd.x]; }
+				else {
+					const uint4 raw = __ldg(reinterpret_cast<const uint4*>(gtree + idx));
+					f0 = __hiloint2double((int)raw.y, (int)raw.x);
+					f1 = __hiloint2double((int)(raw.w & 0x7FFFFFFFu), (int)raw.z);
+				}
+				s0 = __dadd_rn(s0, f0);                                      // ForestProbability.cpp:136-141
+				s1 = __dadd_rn(s1, f1);
+				if ((i + 1) % T == 0) {
+					const uint32_t pl = p0 + i / T;
+					scratch[((size_t)pl * 2 + 0) * Nte + row] = __ddiv_rn(s0, Td);   // :145-149
+					scratch[((size_t)pl * 2 + 1) * Nte + row] = __ddiv_rn(s1, Td);
+					s0 = 0.0; s1 = 0.0;
+				}
+			}
+		}
+		__syncthreads();
+	}
+}
+
 __global__ void __launch_bounds__(256) accumulate_kernel(const double* __restrict__ scratch, uint32_t Nte, uint32_t nPartsBatch,
                                                           double divider, double* __restrict__ class12) {
 	const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -178,9 +338,35 @@ __global__ void __launch_bounds__(256) accumulate_kernel(const double* __restric
 	class12[(size_t)Nte + row] = c2;
 }
 
-int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_t Nte, const Node16* nodes, uint32_t NC,
+void launch_pack_forest(const Node16* nodes, const TreeState* ts, uint32_t NC, uint32_t nTrees, void* nodes8, cudaStream_t s) {
+	const size_t total = (size_t)nTrees * NC;
+	pack_forest_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(nodes, ts, NC, nTrees, reinterpret_cast<Node8*>(nodes8));
+}
+
+int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_t Nte, const Node16* nodes, const void* nodes8, uint32_t NC,
                    const TreeState* ts, uint32_t maxNodes, uint32_t nPartsBatch, uint32_t T, double* scratch, cudaStream_t s) {
 	if (Nte == 0 || nPartsBatch == 0) return 0;
+	{
+		// compact path: fp32 tile + 8-byte nodes (feature < 4096, child id < 2^20)
+		const uint32_t mn = (maxNodes + 1u) & ~1u;
+		const size_t smemC = (size_t)m * PT * sizeof(float) + (size_t)NBUF * TPS * mn * sizeof(Node8) + 128;
+		if (nodes8 && maxNodes > 0 && m <= 4096 && NC < (1u << 20) && smemC <= 100 * 1024 && !getenv("PSM_PREDICT_WIDE")) {
+			const uint32_t rowTiles = (Nte + PT - 1) / PT;
+			uint32_t ctasPerSm = (uint32_t)((227 * 1024) / (smemC + 1024));
+			if (ctasPerSm < 1) ctasPerSm = 1;
+			if (ctasPerSm > 8) ctasPerSm = 8;
+			const uint32_t slots = 148 * ctasPerSm;
+			uint32_t chunks = (6 * slots + rowTiles - 1) / rowTiles;
+			if (chunks < 1) chunks = 1;
+			if (chunks > nPartsBatch) chunks = nPartsBatch;
+			const uint32_t pch = (nPartsBatch + chunks - 1) / chunks;
+			chunks = (nPartsBatch + pch - 1) / pch;
+			if (cudaFuncSetAttribute(predict_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC) != cudaSuccess) return -1;
+			predict_compact_kernel<<<dim3(rowTiles, chunks), PT, smemC, s>>>(x, m, testIdx, Nte, nodes, reinterpret_cast<const Node8*>(nodes8), NC, ts,
+			                                                                  nPartsBatch, T, pch, mn, scratch);
+			return 0;
+		}
+	}
 	{
 		// TMA-staged path when the row tile plus two tree buffers fit in shared memory
 		const size_t tileB = (size_t)m * PT * sizeof(double);

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 		if (lane == 0) item = atomicAdd(&A.counters[CNT_NEXT_ITEMS], 1u);
 		item = __shfl_sync(0xffffffffu, item, 0);
 		if (lane == 0) {
-			Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = ts.nEntries; it.npos = npos; it.nneg = nneg;
+			Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = ts.nEntries; it.npos = npos; it.nneg = nneg; it.nPosOut = pd.nPosOut; it.pad = 0;
 			A.items[0][item] = it;
 		}
 	} else if (lane == 0) {
@@ -317,21 +317,23 @@ __device__ __forceinline__ void ss_load(const E* __restrict__ base, uint32_t v, 
 // shared by up to four work items.  Every item is processed by exactly one of the three instantiations.
 template <typename E, int G>
 __global__ void __launch_bounds__(128, 8) split_search_kernel(TrainArgs A, uint32_t nItems, int buf) {
-	const uint32_t gid = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
-	if (gid >= nItems * A.mtry) return;
-	const uint32_t item = gid / A.mtry, c = gid % A.mtry;
+	// grid.y = candidate index, so no integer division is needed to find the work item
+	const uint32_t item = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
+	if (item >= nItems) return;
+	const uint32_t c = blockIdx.y;
 	const Item it = A.items[buf][item];
 	constexpr uint32_t APE = 16 / sizeof(E);                  // entries per 16 bytes
 	const uint32_t off = it.start % APE;                      // A.stride % 4 == 0, so list + start - off is 16-byte aligned
 	const uint32_t lo = off, hi = it.cnt + off;                // valid index range in the aligned grid
+	// size classes (only used when the sub-warp instantiations are launched; measured slower than G = 32 alone at
+	// BASELINE configs[1], where mid-level segments hold ~100 entries, so launch_split_search launches G = 32 for everything)
 	if (G == 8 && hi > 32) return;
 	if (G == 16 && (hi <= 32 || hi > 64)) return;
-	if (G == 32 && hi <= 64) return;
 	const int lane = lane_id();
 	const int gl = lane % G;
 	const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));
 	const uint32_t f = A.cand[(size_t)item * A.mtry + c];
-	const uint32_t nPosOut = A.parts[it.tree / A.T].nPosOut;
+	const uint32_t nPosOut = it.nPosOut;
 	const E* base = reinterpret_cast<const E*>(A.lists[A.listBuf]) + ((size_t)it.tree * A.m + f) * A.stride + (it.start - off);
 	const uint32_t n = it.npos + it.nneg;
 	uint32_t lp = 0, ln = 0;
@@ -416,14 +418,25 @@ __global__ void __launch_bounds__(128, 8) split_search_kernel(TrainArgs A, uint3
 			for (int j = 0; j < SS_IPL; j++) e[j] = nx[j];
 		}
 	}
-	// arg-max over the group's lanes: highest score, then lowest position (ascending value order, strict '>')
-#pragma unroll
-	for (int o = G / 2; o > 0; o >>= 1) {
-		double os = __shfl_xor_sync(gm, best, o, G);
-		uint32_t op = __shfl_xor_sync(gm, bpos, o, G);
-		uint32_t olp = __shfl_xor_sync(gm, blp, o, G);
-		uint32_t oln = __shfl_xor_sync(gm, bln, o, G);
-		if (os > best || (os == best && op < bpos)) { best = os; bpos = op; blp = olp; bln = oln; }
+	// arg-max over the group's lanes: highest score, then lowest position (ascending value order, strict '>').
+	// Scores are positive doubles, so their two 32-bit halves order like unsigned integers: three redux steps.
+	{
+		const unsigned long long sb = best > 0.0 ? (unsigned long long)__double_as_longlong(best) : 0ull;
+		const uint32_t mhi = __reduce_max_sync(gm, (uint32_t)(sb >> 32));
+		const bool c1 = (uint32_t)(sb >> 32) == mhi && sb != 0ull;
+		const uint32_t mlo = __reduce_max_sync(gm, c1 ? (uint32_t)sb : 0u);
+		const bool c2 = c1 && (uint32_t)sb == mlo;
+		const uint32_t mpos = __reduce_min_sync(gm, c2 ? bpos : 0xFFFFFFFFu);
+		const unsigned win = __ballot_sync(gm, c2 && bpos == mpos) & gm;
+		if (win) {
+			const int src = __ffs(win) - 1;
+			best = __shfl_sync(gm, best, src);
+			blp = __shfl_sync(gm, blp, src);
+			bln = __shfl_sync(gm, bln, src);
+			bpos = mpos;
+		} else {
+			best = -1.0; bpos = 0xFFFFFFFFu;
+		}
 	}
 	if (gl == 0) {
 		SearchRes r; r.score = best; r.pos = bpos; r.lpos = blp; r.lneg = bln; r.pad = 0;
@@ -536,7 +549,7 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 	for (uint32_t b = 0; b < ts.itemCount; b += 32) {
 		uint32_t i = b + lane;
 		SplitDec d; d.split = 0; d.nleft = 0; d.lpos = 0; d.lneg = 0;
-		Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = 0; it.npos = 0; it.nneg = 0;
+		Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = 0; it.npos = 0; it.nneg = 0; it.nPosOut = 0; it.pad = 0;
 		if (i < ts.itemCount) { d = dec[i]; it = cur[i]; }
 		const unsigned smask = __ballot_sync(0xffffffffu, d.split != 0);
 		const uint32_t sp = __popc(smask & lt);
@@ -553,11 +566,11 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 			nodes[it.node].b = (nodes[it.node].b & 0xFFFFFFFFull) | ((unsigned long long)leftId << 32);   // Tree.cpp:294-302
 			uint32_t o = myOff;
 			if (liveL) {
-				Item c; c.tree = tree; c.node = leftId; c.start = it.start; c.cnt = d.nleft; c.npos = d.lpos; c.nneg = d.lneg;
+				Item c; c.tree = tree; c.node = leftId; c.start = it.start; c.cnt = d.nleft; c.npos = d.lpos; c.nneg = d.lneg; c.nPosOut = it.nPosOut; c.pad = 0;
 				nextItems[o] = c; sm.child[2 * sp] = o; o++;
 			} else { write_leaf(&nodes[leftId], d.lpos, d.lneg); sm.child[2 * sp] = 0xFFFFFFFFu; }
 			if (liveR) {
-				Item c; c.tree = tree; c.node = leftId + 1; c.start = it.start + d.nleft; c.cnt = it.cnt - d.nleft; c.npos = rpos; c.nneg = rneg;
+				Item c; c.tree = tree; c.node = leftId + 1; c.start = it.start + d.nleft; c.cnt = it.cnt - d.nleft; c.npos = rpos; c.nneg = rneg; c.nPosOut = it.nPosOut; c.pad = 0;
 				nextItems[o] = c; sm.child[2 * sp + 1] = o;
 			} else { write_leaf(&nodes[leftId + 1], rpos, rneg); sm.child[2 * sp + 1] = 0xFFFFFFFFu; }
 		}
@@ -694,17 +707,10 @@ int launch_init_trees(const TrainArgs& A, cudaStream_t s) {
 }
 void launch_split_search(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
 	size_t warps = (size_t)nItems * A.mtry;
-	const size_t groups = warps;   // one work item per (node, candidate)
-	const unsigned b32 = (unsigned)((groups * 32 + 127) / 128), b16 = (unsigned)((groups * 16 + 127) / 128), b8 = (unsigned)((groups * 8 + 127) / 128);
-	if (A.entry32) {
-		split_search_kernel<uint32_t, 32><<<b32, 128, 0, s>>>(A, nItems, buf);
-		split_search_kernel<uint32_t, 16><<<b16, 128, 0, s>>>(A, nItems, buf);
-		split_search_kernel<uint32_t, 8><<<b8, 128, 0, s>>>(A, nItems, buf);
-	} else {
-		split_search_kernel<unsigned long long, 32><<<b32, 128, 0, s>>>(A, nItems, buf);
-		split_search_kernel<unsigned long long, 16><<<b16, 128, 0, s>>>(A, nItems, buf);
-		split_search_kernel<unsigned long long, 8><<<b8, 128, 0, s>>>(A, nItems, buf);
-	}
+	(void)warps;
+	const dim3 grid((nItems * 32 + 127) / 128, A.mtry);   // x: nodes (one warp each), y: candidate
+	if (A.entry32) split_search_kernel<uint32_t, 32><<<grid, 128, 0, s>>>(A, nItems, buf);
+	else split_search_kernel<unsigned long long, 32><<<grid, 128, 0, s>>>(A, nItems, buf);
 }
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
 	if (A.entry32) split_select_kernel<uint32_t><<<(nItems + 3) / 4, 128, 0, s>>>(A, nItems, buf);

@@ -249,6 +249,23 @@ def test_fold_scores_bit_exact_and_curves(ctx, oracle, name):
     assert abs(got1[0] - want[0]) < 5e-3 and abs(got1[1] - want[1]) < 5e-3   # stable tie order may differ
 
 
+def test_predict_paths_agree_bitwise(oracle, monkeypatch):
+    """compact predict (fp32 tile + 8-byte nodes + exact fp64 tie-break) == 16-byte-node TMA path == oracle, incl. data with
+    values that collide in fp32 (features rounded to a coarse grid so float(v) == float(threshold) happens constantly)"""
+    from parsmurf_b200 import host_api as H
+    case = make_case("ties_ratio0")
+    X = case["X"].copy()
+    X[:, 1::5] = np.round(X[:, 1::5] * 4) / 4 + 1e-12 * np.arange(len(X))[:, None]   # equal in fp32, distinct in fp64
+    x = oracle.make_x(X, case["y"])
+    args = (x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
+    rc, o1, o2 = oracle.o_cv(*args)
+    a = H.cv_run(*args, tie_mode=0)
+    monkeypatch.setenv("PSM_PREDICT_WIDE", "1")
+    b = H.cv_run(*args, tie_mode=0)
+    assert np.array_equal(a["class1"].view(np.uint64), o1.view(np.uint64)) and np.array_equal(a["class2"].view(np.uint64), o2.view(np.uint64))
+    assert np.array_equal(b["class1"].view(np.uint64), o1.view(np.uint64)) and np.array_equal(b["class2"].view(np.uint64), o2.view(np.uint64))
+
+
 def test_small_batches_equal_one_batch(ctx, oracle):
     """the memory-budget batching must not change results"""
     case = make_case("fy_26")
