@@ -100,6 +100,8 @@ def ref_lib():
         L.ref_cv.argtypes = [dp, u32, u32, u32p, u32p] + [u32] * 10 + [i32, i32, C.c_int, dp, dp]
         L.ref_run_partitions.restype = C.c_double
         L.ref_run_partitions.argtypes = [vp] + [u32] * 12 + [dp, dp]
+        L.ref_cv_grid.restype = C.c_double
+        L.ref_cv_grid.argtypes = [dp, u32, u32, u32p, u32p, u32, u32p, u32, u32, u32, u32, C.c_int, dp, dp, dp]
         L.ref_num_procs.restype = C.c_int
         _ref = L
     return _ref
@@ -302,3 +304,23 @@ def r_cv(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, nTh
     secs = ref_lib().ref_cv(_p(x, dp), n, ld - 1, _p(labels, u32p), _p(folds, u32p), nFolds, nParts, fp, ratio, k, nTrees, mtry, seed,
                             nThr, rfThr, minFold, maxFold, int(reset_rand), _p(c1, dp), _p(c2, dp))
     return secs, c1, c2
+
+
+def r_cv_grid(x, labels, folds, nFolds, grid, seed, nThr=1, rfThr=1):
+    """reference grid search (optimizer "grid"); grid = list of (nParts, fp, ratio, k, nTrees, mtry).  Runs in a scratch cwd
+    because the reference appends fold<k>.dat files.  Returns (class1, class2, gridMetrics[G][2] of the last outer fold)."""
+    import tempfile
+    n, ld = x.shape
+    x = np.ascontiguousarray(x, np.float64)
+    labels = np.ascontiguousarray(labels, np.uint32); folds = np.ascontiguousarray(folds, np.uint32)
+    g = np.ascontiguousarray(np.array(grid, np.uint32).reshape(-1, 6))
+    c1 = np.zeros(n); c2 = np.zeros(n); gm = np.zeros((len(g), 2))
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            ref_lib().ref_cv_grid(_p(x, dp), n, ld - 1, _p(labels, u32p), _p(folds, u32p), nFolds, _p(g, u32p), len(g), seed, nThr, rfThr, 1,
+                                  _p(c1, dp), _p(c2, dp), _p(gm, dp))
+        finally:
+            os.chdir(cwd)
+    return c1, c2, gm

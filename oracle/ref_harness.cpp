@@ -254,6 +254,40 @@ double ref_cv(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, c
 	return t.duration();
 }
 
+// Grid search (exec.optimizer = "grid", src/hyperSMURF.cpp:176-228): every outer fold runs an inner (nFolds-1)-fold CV per grid
+// point, then the outer fold with the arg-max-AUPRC parameters.  The reference appends fold<k>.dat files to the CWD, so the
+// caller should chdir to a scratch directory.  grid = [G][6] {nParts, fp, ratio, k, nTrees, mtry}; gridMetrics [G][2] receives
+// {auroc, auprc} of the inner CVs of the LAST outer fold.
+double ref_cv_grid(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+                   const uint32_t* grid, uint32_t G, uint32_t seed, uint32_t nThr, uint32_t rfThr, int reset_rand, double* class1,
+                   double* class2, double* gridMetrics) {
+	CoutSilencer quiet;
+	std::vector<double> xx(x, x + (size_t)n * (m + 1));
+	std::vector<uint32_t> yy(labels, labels + n);
+	std::vector<uint32_t> ff(foldAssign, foldAssign + n);
+	CommonParams cp;
+	cp.nn = n; cp.mm = m; cp.nFolds = nFolds; cp.seed = seed; cp.verboseLevel = VERBSILENT;
+	cp.nThr = nThr; cp.rfThr = rfThr; cp.wmode = MODE_CV; cp.woptimiz = OPT_GRID; cp.rfVerbose = false;
+	cp.verboseMPI = false; cp.noMtSender = false; cp.customCV = false;
+	cp.minFold = (uint32_t)-1; cp.maxFold = (uint32_t)-1;
+	std::vector<GridParams> gp(G);
+	for (uint32_t i = 0; i < G; i++) {
+		gp[i].nParts = grid[6 * i]; gp[i].fp = grid[6 * i + 1]; gp[i].ratio = grid[6 * i + 2]; gp[i].k = grid[6 * i + 3];
+		gp[i].nTrees = grid[6 * i + 4]; gp[i].mtry = grid[6 * i + 5]; gp[i].auroc = gp[i].auprc = 0;
+	}
+	omp_set_num_threads(nThr);
+	if (reset_rand) srand(1);
+	Folds foldManager(nFolds, n, yy.data(), ff, false);
+	foldManager.computeFolds();
+	hyperSMURF smurfer(&cp, gp, &foldManager, xx, yy, class1, class2);
+	smurfer.initStandard();
+	Timer t; t.startTime();
+	smurfer.smurfIt();
+	t.endTime();
+	for (uint32_t i = 0; i < G; i++) { gridMetrics[2 * i] = gp[i].auroc; gridMetrics[2 * i + 1] = gp[i].auprc; }
+	return t.duration();
+}
+
 // Bounded CPU-baseline sample: partitions [p0, p1) of one fold through the reference classes in the
 // order of src/hyperSMURF.cpp:261-346, `nThr` OpenMP threads over partitions (as the reference does).
 // Accumulates into class1/class2 (length n).  Returns wall seconds.

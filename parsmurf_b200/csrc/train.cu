@@ -290,6 +290,9 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 // The exact fp64 score (two IEEE divisions) is only evaluated for positions whose fp32 estimate could still beat the
 // lane's running best: estimate error < 1e-6 relative, filter margin 5e-6, so no winner is ever skipped.
 constexpr int SS_IPL = 4;
+#ifndef SS_MINB
+#define SS_MINB 8
+#endif
 
 __device__ __forceinline__ void ss_vec(const unsigned long long* p, unsigned long long (&e)[SS_IPL]) {
 	const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(p));
@@ -316,7 +319,7 @@ __device__ __forceinline__ void ss_load(const E* __restrict__ base, uint32_t v, 
 // most nodes hold a few dozen rows and the kernel is instruction-issue bound (ncu r01), so the per-warp fixed cost is
 // shared by up to four work items.  Every item is processed by exactly one of the three instantiations.
 template <typename E, int G>
-__global__ void __launch_bounds__(128, 8) split_search_kernel(TrainArgs A, uint32_t nItems, int buf) {
+__global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A, uint32_t nItems, int buf) {
 	// grid.y = candidate index, so no integer division is needed to find the work item
 	const uint32_t item = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
 	if (item >= nItems) return;

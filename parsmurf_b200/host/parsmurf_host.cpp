@@ -57,7 +57,13 @@ void GlibcRand::discard(uint64_t n) {
 	f = 0; r = 28;
 }
 void GlibcRand::shuffle(uint32_t* a, size_t n) {
-	for (size_t i = 1; i < n; i++) {
+	// rand() is in [0, 2^31): the modulus is done in 32 bits while i + 1 fits (identical value, much cheaper division)
+	size_t i = 1;
+	for (; i < n && i < 0x7FFFFFFFull; i++) {
+		const uint32_t j = (uint32_t)rand() % (uint32_t)(i + 1);
+		if (i != j) std::swap(a[i], a[j]);
+	}
+	for (; i < n; i++) {
 		size_t j = (size_t)(rand() % (int64_t)(i + 1));
 		if (i != j) std::swap(a[i], a[j]);
 	}
@@ -347,6 +353,10 @@ void hyperSMURF::smurfIt() {                                                // s
 					   << std::endl;
 				}
 			}
+			// the inner CVs used the device score arrays: start the outer fold from a clean device state (the outer scores of
+			// earlier folds were already added into the host arrays below)
+			dev->check(psm_labels_upload(dev->ctx, y.data(), nn));
+			dev->check(psm_scores_reset(dev->ctx));
 			auto best = std::max_element(gridParams.begin(), gridParams.end(), [](const GridParams& a, const GridParams& b) { return a.auprc < b.auprc; });
 			nPart = best->nParts; fp = best->fp; ratio = best->ratio; k = best->k; numTrees = best->nTrees; mtry = best->mtry;   // :207-224
 			part->nPart = nPart; part->fp = fp; part->ratio = ratio;
@@ -394,6 +404,11 @@ void hyperSMURF::smurfIt() {                                                // s
 		}
 		{ PhaseScope ps(PH_SCATTER); dev->check(psm_fold_scatter_device(dev->ctx)); }   // :344-346 scatter by example id, on the device
 
+		if (woptimiz != OPT_NO) {                                          // grid mode: flush this fold's scores to the host now (see above)
+			PhaseScope ps(PH_SCATTER);
+			dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob));
+			dev->check(psm_scores_reset(dev->ctx));
+		}
 		if (evalFoldCurves && !inInternalCV) {                              // :365-396 per-fold AUROC / AUPRC (labels y[idx], scores class1Prob[idx])
 			PhaseScope ps(PH_CURVES);
 			double r2[2];
@@ -419,7 +434,8 @@ void hyperSMURF::smurfIt() {                                                // s
 	} else {                                                                // :484-488
 		PhaseScope ps(PH_CURVES);
 		double r2[2];
-		dev->check(psm_scores_curves(dev->ctx, curvesTieMode, r2));        // Curves(y, class1Prob)
+		if (woptimiz == OPT_NO) dev->check(psm_scores_curves(dev->ctx, curvesTieMode, r2));        // Curves(y, class1Prob), scores still on the device
+		else dev->check(psm_curves(dev->ctx, y.data(), class1Prob, nn, curvesTieMode, r2));
 		auroc = r2[0];
 		auprc = r2[1];
 		if (verboseLevel > VERBSILENT && rank == 0) std::cout << "AUROC: " << auroc << " - AUPRC: " << auprc << std::endl;
@@ -588,8 +604,6 @@ int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const 
 		dev.check(psm_profile_reset(dev.ctx));
 		if (batchBudget) dev.check(psm_set_batch_budget(dev.ctx, batchBudget));
 		if (profile) dev.check(psm_profile_enable(dev.ctx, 1));
-		if (x_is_device) dev.attachDevice(x, n, m); else dev.upload(x, n, m);
-		g_phase[PH_SETUP] += now_s() - tSetup;
 		GlibcRand rng(1);
 		std::vector<uint32_t> y(labels, labels + n), ff;
 		if (foldAssign) ff.assign(foldAssign, foldAssign + n);
@@ -602,13 +616,50 @@ int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const 
 		hyperSMURF smurfer(&cp, gp, &folds, &dev, y, class1, class2, &rng);
 		smurfer.curvesTieMode = tieMode; smurfer.evalFoldCurves = evalFoldCurves != 0;
 		if (world > 1) smurfer.setSharding(rank, world, [&](double* p, uint64_t c) { if (reduce && reduce(reduceUser, p, c)) throw Error(PSM_E_CUDA, "reduce callback failed"); });
-		smurfer.initStandard();
+		smurfer.initStandard();                             // starts the per-fold index builders in the background ...
+		tSetup = now_s();
+		if (x_is_device) dev.attachDevice(x, n, m); else dev.upload(x, n, m);   // ... which overlap the H2D copy of x
+		g_phase[PH_SETUP] += now_s() - tSetup;
 		smurfer.smurfIt();
 		if (metrics) { metrics[0] = smurfer.auroc; metrics[1] = smurfer.auprc; }
 		if (foldMetrics) for (uint32_t f = 0; f < nFolds; f++) { foldMetrics[2 * f] = smurfer.foldAuroc[f]; foldMetrics[2 * f + 1] = smurfer.foldAuprc[f]; }
 		if (kernelMs || kernelLaunches) dev.check(psm_profile_get(dev.ctx, kernelMs, kernelLaunches));
 		if (stats3) dev.check(psm_stats_get(dev.ctx, &stats3[0], &stats3[1], &stats3[2]));
 		if (phases) for (int i = 0; i < PH_COUNT; i++) phases[i] = g_phase[i];
+		return 0;
+	} catch (const parsmurf::Error& e) {
+		if (errbuf && errlen) { strncpy(errbuf, e.what(), errlen - 1); errbuf[errlen - 1] = 0; }
+		return e.code ? e.code : -1;
+	} catch (const std::exception& e) {
+		if (errbuf && errlen) { strncpy(errbuf, e.what(), errlen - 1); errbuf[errlen - 1] = 0; }
+		return -1;
+	}
+}
+
+// Grid search through the host classes (cfgEx/gridTune.json: exec.optimizer = "grid").  grid = [G][6] {nParts, fp, ratio, k, nTrees,
+// mtry}; gridMetrics [G][2] = {auroc, auprc} of the inner CVs of the last outer fold.  fold<k>.dat files are appended in the CWD.
+int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+                     const uint32_t* grid, uint32_t G, uint32_t seed, int device, int tieMode, double* class1, double* class2, double* metrics,
+                     double* gridMetrics, char* errbuf, size_t errlen) {
+	using namespace parsmurf;
+	try {
+		Device dev(device, nullptr);
+		GlibcRand rng(1);
+		std::vector<uint32_t> y(labels, labels + n), ff;
+		if (foldAssign) ff.assign(foldAssign, foldAssign + n);
+		Folds folds(nFolds, n, y.data(), ff, foldAssign == nullptr, &rng);
+		folds.computeFolds();
+		CommonParams cp;
+		cp.nn = n; cp.mm = m; cp.nFolds = nFolds; cp.seed = seed; cp.wmode = MODE_CV; cp.woptimiz = OPT_GRID;
+		std::vector<GridParams> gp(G);
+		for (uint32_t i = 0; i < G; i++) gp[i] = GridParams{grid[6 * i], grid[6 * i + 1], grid[6 * i + 2], grid[6 * i + 3], grid[6 * i + 4], grid[6 * i + 5], 0, 0};
+		hyperSMURF smurfer(&cp, gp, &folds, &dev, y, class1, class2, &rng);
+		smurfer.curvesTieMode = tieMode;
+		smurfer.initStandard();
+		dev.upload(x, n, m);
+		smurfer.smurfIt();
+		if (metrics) { metrics[0] = smurfer.auroc; metrics[1] = smurfer.auprc; }
+		if (gridMetrics) for (uint32_t i = 0; i < G; i++) { gridMetrics[2 * i] = gp[i].auroc; gridMetrics[2 * i + 1] = gp[i].auprc; }
 		return 0;
 	} catch (const parsmurf::Error& e) {
 		if (errbuf && errlen) { strncpy(errbuf, e.what(), errlen - 1); errbuf[errlen - 1] = 0; }

@@ -25,6 +25,7 @@ def hlib():
         L.psmh_device_create.restype = vp
         L.psmh_device_create.argtypes = [C.c_int, vp]
         L.psmh_device_destroy.argtypes = [vp]
+        L.psmh_cv_grid_run.argtypes = [dp, u32, u32, u32p, u32p, u32, u32p, u32, u32, C.c_int, C.c_int, dp, dp, dp, dp, C.c_char_p, C.c_size_t]
         L.psmh_rand_fill.argtypes = [u32, i32p, u64]
         L.psmh_ttd_fold.argtypes = [u32p, u32p, u32, u32, u32, C.c_int64, u32p, u32p, u32p, u32p, u32p]
         L.psmh_config_parse.argtypes = [C.c_char_p, u32p, u32p, u32, C.c_char_p, C.c_size_t]
@@ -72,6 +73,31 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
                 kernel_launches={k_: int(kl[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
                 stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2])),
                 host_phases_s={k_: float(ph[i]) for i, k_ in enumerate(PHASES)})
+
+
+def cv_grid_run(x, labels, folds, nFolds, grid, seed, device=0, tie_mode=0):
+    """Grid search like cfgEx/gridTune.json (exec.optimizer "grid"): grid = list of (nParts, fp, ratio, k, nTrees, mtry).
+    Appends fold<k>.dat files to a scratch directory.  Returns dict(class1, class2, auroc, auprc, grid_metrics)."""
+    import tempfile
+    L = hlib()
+    assert x.dtype == np.float64 and x.flags.c_contiguous
+    n, m = x.shape[0], x.shape[1] - 1
+    labels = np.ascontiguousarray(labels, np.uint32)
+    folds = None if folds is None else np.ascontiguousarray(folds, np.uint32)
+    g = np.ascontiguousarray(np.array(grid, np.uint32).reshape(-1, 6))
+    c1 = np.zeros(n); c2 = np.zeros(n); met = np.zeros(2); gm = np.zeros((len(g), 2))
+    err = C.create_string_buffer(512)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            rc = L.psmh_cv_grid_run(_p(x, dp), n, m, _p(labels, u32p), _p(folds, u32p), nFolds, _p(g, u32p), len(g), seed, device, tie_mode,
+                                    _p(c1, dp), _p(c2, dp), _p(met, dp), _p(gm, dp), err, 512)
+        finally:
+            os.chdir(cwd)
+    if rc != 0:
+        raise PsmError(rc, err.value.decode())
+    return dict(class1=c1, class2=c2, auroc=float(met[0]), auprc=float(met[1]), grid_metrics=gm)
 
 
 class HostDevice:

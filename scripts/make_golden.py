@@ -71,4 +71,12 @@ for name in CASES:
                         nn_kd=nn_kd, dd_kd=dd_kd, nn_bf=nn_bf,
                         **{"t0_" + k: v for k, v in t0.items()}, **{"tL_" + k: v for k, v in tL.items()}, preds0=preds)
     print(name, "AUROC %.6f AUPRC %.6f" % (auroc, auprc), "nodes", len(t0["var"]), len(tL["var"]), "kd==brute", np.array_equal(nn_kd, nn_bf))
+# ---- grid search (cfgEx/gridTune.json shape: optimizer "grid") on the fy_26 case, three grid points
+c = make_case("fy_26")
+x = O.make_x(c["X"], c["y"])
+grid = [(4, 1, 1, 5, 5, 5), (4, 2, 1, 5, 5, 5), (6, 1, 2, 5, 5, 7)]
+c1, c2, gm = O.r_cv_grid(x, c["y"], c["f"], c["nF"], grid, 7)
+au = O.r_curves(c["y"], c1)
+np.savez_compressed(os.path.join(OUT, "grid_fy_26.npz"), class1=c1, class2=c2, grid=np.array(grid, np.uint32), grid_metrics=gm, auroc=au[0], auprc=au[1])
+print("grid", gm.tolist(), au)
 print(os.listdir(OUT))

@@ -146,6 +146,21 @@ def test_cuda_path_against_committed_golden_fixtures(oracle):
         assert np.allclose(out["fold_metrics"], g["fold_metrics"], rtol=0, atol=1e-12)
 
 
+def test_grid_search_matches_reference_golden():
+    """optimizer "grid" (inner CV per grid point, arg-max AUPRC, outer fold with the winner) == the reference's own run"""
+    import os
+    from parsmurf_b200 import host_api as H
+    from oracle import pyoracle as O
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grid_fy_26.npz"))
+    c = make_case("fy_26")
+    x = O.make_x(c["X"], c["y"])
+    out = H.cv_grid_run(x, c["y"], c["f"], c["nF"], [tuple(int(v) for v in r) for r in g["grid"]], 7, tie_mode=0)
+    assert np.allclose(out["grid_metrics"], g["grid_metrics"], rtol=0, atol=1e-12)
+    assert np.array_equal(out["class1"].view(np.uint64), g["class1"].view(np.uint64))
+    assert np.array_equal(out["class2"].view(np.uint64), g["class2"].view(np.uint64))
+    assert abs(out["auroc"] - float(g["auroc"])) < 1e-12 and abs(out["auprc"] - float(g["auprc"])) < 1e-12
+
+
 def _train_case(ctx, oracle, case, fold=0, seed=7):
     x, fd, rnd = _fold_setup(ctx, oracle, case, fold)
     ctx.fold_knn(case["k"])
