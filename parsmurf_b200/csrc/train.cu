@@ -147,26 +147,40 @@ __device__ void gen_candidates(unsigned long long* mt, uint32_t& pos, uint32_t m
 			for (int q = (int)mtry - 1; q >= 0; q--) { uint32_t j = jbuf[q]; uint32_t a = perm[q]; perm[q] = perm[j]; perm[j] = a; }
 		__syncwarp();
 	} else {
+		// drawWithoutReplacementSimple (utility.cpp:94-117), 32 stream outputs per step: every lane maps one output with the
+		// Lemire step and tests it against the selection flags; among equal draws inside the step only the first lane can be
+		// accepted; the step is cut right after the output that completes the mtry-th acceptance, exactly where the
+		// sequential loop of the reference stops consuming the stream.
 		uint32_t count = 0;
-		while (true) {
+		while (count < mtry) {
 			if (pos == MT_N) { mt_twist(mt); pos = 0; }
-			if (lane == 0) {
-				while (count < mtry && pos < (uint32_t)MT_N) {
-					unsigned long long v;
-					if (!lemire_accept(mt_temper(mt[pos++]), (unsigned long long)m, &v)) continue;
-					uint32_t draw = (uint32_t)v;      // range [0, m-1]; the skipped column m is never reached (utility.cpp:107-111)
-					if (perm[draw]) continue;         // already selected: draw again (utility.cpp:112)
-					perm[draw] = 1;
-					jbuf[count++] = draw;
-				}
+			const uint32_t take = min(32u, (uint32_t)MT_N - pos);
+			unsigned long long v = 0;
+			bool ok = false;
+			if ((uint32_t)lane < take) ok = lemire_accept(mt_temper(mt[pos + lane]), (unsigned long long)m, &v);
+			const uint32_t draw = (uint32_t)v;            // range [0, m-1]; the skipped column m is never reached (utility.cpp:107-111)
+			const bool fresh = ok && perm[draw] == 0;     // not selected by an earlier step (utility.cpp:112)
+			const unsigned peers = __match_any_sync(0xffffffffu, fresh ? draw : (0x80000000u | (uint32_t)lane));
+			const bool cand = fresh && ((__ffs(peers) - 1) == lane);
+			const unsigned acc = __ballot_sync(0xffffffffu, cand);
+			const uint32_t need = mtry - count, nacc = __popc(acc);
+			uint32_t last = take - 1;                     // last consumed lane of this step
+			if (nacc >= need) {
+				unsigned m2 = acc;
+				for (uint32_t k = 1; k < need; k++) m2 &= m2 - 1;
+				last = __ffs(m2) - 1;
 			}
-			count = __shfl_sync(0xffffffffu, count, 0);
-			pos = __shfl_sync(0xffffffffu, pos, 0);
-			if (count == mtry) break;
+			if (cand && (uint32_t)lane <= last) {
+				jbuf[count + __popc(acc & lanemask_lt())] = draw;
+				perm[draw] = 1;
+			}
+			__syncwarp();
+			count += min(nacc, need);
+			pos += last + 1;
 		}
 		__syncwarp();
 		if (out) for (uint32_t q = lane; q < mtry; q += 32) out[q] = jbuf[q];
-		if (lane == 0) for (uint32_t q = 0; q < mtry; q++) perm[jbuf[q]] = 0;
+		for (uint32_t q = lane; q < mtry; q += 32) perm[jbuf[q]] = 0;
 		__syncwarp();
 	}
 }
