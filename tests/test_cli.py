@@ -1,0 +1,60 @@
+"""The C++ command-line driver (parsmurf_b200_cv --cfg file.json): parSMURF1's configuration surface end to end."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import make_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "parsmurf_b200", "_build", "parsmurf_b200_cv")
+
+
+def _write_case(tmp_path, case, name):
+    np.savetxt(tmp_path / "data.txt", case["X"], fmt="%.17g")
+    np.savetxt(tmp_path / "labels.txt", case["y"], fmt="%d")
+    np.savetxt(tmp_path / "folds.txt", case["f"], fmt="%d")
+    cfg = {"name": name,
+           "exec": {"name": "parSMURF1", "ensThrd": 4, "rfThrd": 1, "seed": 7, "verboseLevel": 0, "saveTime": True, "timeFile": str(tmp_path / "time.txt"),
+                    "printCfg": False, "mode": "cv", "optimizer": "no"},
+           "data": {"dataFile": str(tmp_path / "data.txt"), "foldFile": str(tmp_path / "folds.txt"), "labelFile": str(tmp_path / "labels.txt"),
+                    "outFile": str(tmp_path / "predictions.txt")},
+           "folds": {"nFolds": case["nF"]},
+           "params": {"nParts": [case["nParts"]], "fp": [case["fp"]], "ratio": [case["ratio"]], "k": [case["k"]], "nTrees": [case["T"]], "mtry": [case["mtry"]]}}
+    (tmp_path / "cfg.json").write_text(json.dumps(cfg, indent=1))
+    return str(tmp_path / "cfg.json")
+
+
+def test_cli_usage_and_no_device_failure(tmp_path):
+    assert os.path.exists(BIN), "run __graft_entry__.build() first"
+    r = subprocess.run([BIN, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--cfg" in r.stdout
+    r = subprocess.run([BIN], capture_output=True, text=True)
+    assert r.returncode == 2
+    import torch
+    if not torch.cuda.is_available():
+        cfg = _write_case(tmp_path, make_case("fy_26"), "nogpu")
+        r = subprocess.run([BIN, "--cfg", cfg], capture_output=True, text=True)
+        assert r.returncode == 1 and "no usable CUDA device" in r.stderr     # fails loudly: there is no CPU fallback
+
+
+@pytest.mark.gpu
+def test_cli_cv_matches_host_api(tmp_path):
+    from oracle import pyoracle as O
+    case = make_case("fy_26")
+    cfg = _write_case(tmp_path, case, "cli_fy26")
+    r = subprocess.run([BIN, "--cfg", cfg], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    mt = re.search(r"AUROC: ([0-9.eE+-]+) - AUPRC: ([0-9.eE+-]+)", r.stdout)
+    assert mt, r.stdout
+    x = O.make_x(case["X"], case["y"])
+    rc, c1, c2 = O.o_cv(x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
+    want = O.o_curves(case["y"], c1)
+    assert abs(float(mt.group(1)) - want[0]) < 1e-8 and abs(float(mt.group(2)) - want[1]) < 1e-8
+    pred = np.loadtxt(tmp_path / "predictions.txt")          # P(pos) \t P(neg) \t label  (src/HyperSMURFUtils.cpp:79-84)
+    assert pred.shape == (case["n"], 3)
+    assert np.allclose(pred[:, 0], c1, rtol=1e-5, atol=1e-12) and np.array_equal(pred[:, 2].astype(int), case["y"].astype(int))
+    assert os.path.exists(tmp_path / "time.txt")
