@@ -179,9 +179,21 @@ __global__ void __launch_bounds__(PT) predict_tma_kernel(const double* __restric
 // leaf (a larger node without a valid split) stores code 0xFFFFFFFF and reads its fractions from the 16-byte node array.
 struct __align__(8) Node8 {
 	float thr;       // internal: float(threshold); leaf: fraction code (as bits)
-	uint32_t meta;   // internal: feature | left << 12 ; leaf: 0xFFFFFFFF
+	uint32_t meta;   // internal: left child (bits 0..19) | feature << 20 (top bit clear) ; leaf: 0xFFFFFFFF
 };
 constexpr int LEAF_TAB = 121;
+
+// the one-in-10^7 visit where float(value) == float(threshold): decide with the exact fp64 values.  Kept out of line on
+// purpose -- inlined, the compiler if-converts it and its ~12 predicated instructions are issued on EVERY node visit
+// (ncu r01: 35 instructions per visit, issue-bound).
+__device__ __noinline__ uint32_t predict_exact_leaf(const double* __restrict__ xr, const Node16* __restrict__ gtree) {
+	uint32_t idx = 0;
+	while (true) {
+		const Node16 nd = gtree[idx];
+		if (node_is_leaf(nd)) return idx;
+		idx = (uint32_t)(nd.b >> 32) + (xr[(uint32_t)nd.b] <= nd.a ? 0u : 1u);       // Tree.cpp:163-169
+	}
+}
 
 __global__ void __launch_bounds__(256) pack_forest_kernel(const Node16* __restrict__ nodes, const TreeState* __restrict__ ts, uint32_t NC,
                                                            uint32_t nTrees, Node8* __restrict__ out) {
@@ -191,7 +203,7 @@ __global__ void __launch_bounds__(256) pack_forest_kernel(const Node16* __restri
 	Node8 o; o.thr = 0.0f; o.meta = 0xFFFFFFFFu;
 	if (node < ts[tree].nNodes) {
 		const Node16 nd = nodes[i];
-		if (!node_is_leaf(nd)) { o.thr = __double2float_rn(nd.a); o.meta = (uint32_t)(nd.b & 0xFFFu) | ((uint32_t)(nd.b >> 32) << 12); }
+		if (!node_is_leaf(nd)) { o.thr = __double2float_rn(nd.a); o.meta = (uint32_t)(nd.b >> 32) | ((uint32_t)(nd.b & 0x7FFu) << 20); }
 		else {
 			const double f0 = nd.a, f1 = __longlong_as_double((long long)(nd.b & 0x7FFFFFFFFFFFFFFFull));
 			uint32_t code = 0xFFFFFFFFu;
@@ -204,8 +216,14 @@ __global__ void __launch_bounds__(256) pack_forest_kernel(const Node16* __restri
 	out[i] = o;
 }
 
-constexpr uint32_t TPS = 1;    // trees per pipeline stage
-constexpr uint32_t NBUF = 2;   // pipeline depth: the TMA runs NBUF-1 stages ahead of the traversal (deeper pipelines cost occupancy and measured slower)
+#ifndef PSM_TPS
+#define PSM_TPS 1
+#endif
+#ifndef PSM_NBUF
+#define PSM_NBUF 2
+#endif
+constexpr uint32_t TPS = PSM_TPS;    // trees per pipeline stage
+constexpr uint32_t NBUF = PSM_NBUF;   // pipeline depth: the TMA runs NBUF-1 stages ahead of the traversal (deeper pipelines cost occupancy and measured slower)
 
 __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __restrict__ x, uint32_t m, const uint32_t* __restrict__ testIdx,
                                                               uint32_t Nte, const Node16* __restrict__ nodes, const Node8* __restrict__ nodes8,
@@ -277,6 +295,7 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 	const bool valid = row < Nte;
 	const double* xr = x + (size_t)testIdx[valid ? row : 0] * ld;
 	const double Td = (double)T;
+	const uint32_t tileLane = smem_u32(tile) + (uint32_t)tid * 4u;   // shared address of tile[0][tid]; PT*4 = 1024 bytes per feature
 	double s0 = 0.0, s1 = 0.0;
 	for (uint32_t st = 0; st < nStages; st++) {
 		const uint32_t b = st % NBUF;
@@ -290,19 +309,25 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 			for (uint32_t q = 0; q < TPS; q++) {
 				const uint32_t i = st * TPS + q;
 				if (i >= nT) break;
-				const uint2* base = reinterpret_cast<const uint2*>(tbuf + ((size_t)b * TPS + q) * maxNodes);
+				// hand-scheduled traversal: 32-bit shared addresses, 12 instructions per node visit
+				const uint32_t nbase = smem_u32(tbuf + ((size_t)b * TPS + q) * maxNodes);
 				const Node16* gtree = nodes + (size_t)(g0 + i) * NC;
-				uint32_t idx = 0;
+				uint32_t idx8 = 0;                               // node index * sizeof(Node8)
 				uint2 nd;
+				bool undecided = false;                          // some visit had float(value) == float(threshold)
 				while (true) {
-					nd = base[idx];
-					if (nd.y == 0xFFFFFFFFu) break;
-					const uint32_t feat = nd.y & 0xFFFu, left = nd.y >> 12;
+					asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nd.x), "=r"(nd.y) : "r"(nbase + idx8));
+					if ((int)nd.y < 0) break;                    // leaf
+					float v;
+					asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(tileLane + ((nd.y >> 10) & 0x1FFC00u)));   // tile[feature][tid]
 					const float thr = __uint_as_float(nd.x);
-					const float v = tile[(size_t)feat * PT + tid];
-					bool goLeft = v < thr;
-					if (v == thr) goLeft = xr[feat] <= gtree[idx].a;         // undecided in fp32: exact fp64 comparison
-					idx = left + (goLeft ? 0u : 1u);
+					undecided |= (v == thr);
+					idx8 = ((nd.y & 0xFFFFFu) + ((v < thr) ? 0u : 1u)) << 3;   // Tree.cpp:163: left iff value <= split_value
+				}
+				uint32_t idx = idx8 >> 3;
+				if (undecided) {                                 // about one row-tree in 10^6: redo this tree with the exact fp64 values
+					idx = predict_exact_leaf(xr, gtree);
+					nd.x = __float_as_uint(tbuf[((size_t)b * TPS + q) * maxNodes + idx].thr);
 				}
 				double f0, f1;
 				if (nd.x < (uint32_t)LEAF_TAB) { f0 = ltab[0][nd.x]; f1 = ltab[1][nd.x]; }
@@ -347,10 +372,10 @@ int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_
                    const TreeState* ts, uint32_t maxNodes, uint32_t nPartsBatch, uint32_t T, double* scratch, cudaStream_t s) {
 	if (Nte == 0 || nPartsBatch == 0) return 0;
 	{
-		// compact path: fp32 tile + 8-byte nodes (feature < 4096, child id < 2^20)
+		// compact path: fp32 tile + 8-byte nodes (feature < 2047, child id < 2^20)
 		const uint32_t mn = (maxNodes + 1u) & ~1u;
 		const size_t smemC = (size_t)m * PT * sizeof(float) + (size_t)NBUF * TPS * mn * sizeof(Node8) + 128;
-		if (nodes8 && maxNodes > 0 && m <= 4096 && NC < (1u << 20) && smemC <= 100 * 1024 && !getenv("PSM_PREDICT_WIDE")) {
+		if (nodes8 && maxNodes > 0 && m <= 2047 && NC < (1u << 20) && smemC <= 100 * 1024 && !getenv("PSM_PREDICT_WIDE")) {
 			const uint32_t rowTiles = (Nte + PT - 1) / PT;
 			uint32_t ctasPerSm = (uint32_t)((227 * 1024) / (smemC + 1024));
 			if (ctasPerSm < 1) ctasPerSm = 1;
