@@ -62,7 +62,7 @@ struct psm_ctx {
 	// train
 	uint32_t T = 0, mtry = 0;
 	TrainArgs A;
-	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dNodes8, dFlags, dFlagBits, dItems0, dItems1, dCand, dRes, dDec, dCounters, dStats, dSeeds,
+	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dNodes8, dFlags, dFlagBits, dItems0, dItems1, dCand, dRes, dDec, dPtask, dCounters, dStats, dSeeds,
 	    dInjBoot, dInjBootOff, dInjCand;
 	uint32_t* hCounters = nullptr;   // pinned
 	void* hStage = nullptr;          // pinned D2H staging
@@ -181,7 +181,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	DevBuf* bufs[] = {&ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dClass12,
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
 	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dFlags, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1,
-	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
+	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dPtask, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
 	                  &ctx->dInjCand, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
 	                  &ctx->cScores, &ctx->cKeysA, &ctx->cKeysB, &ctx->cValsA, &ctx->cValsB, &ctx->cHist};
 	for (DevBuf* b : bufs) b->release();
@@ -439,6 +439,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	ENSURE(ctx->dCand, (size_t)itemCap * mtry * 4);
 	ENSURE(ctx->dRes, (size_t)itemCap * mtry * sizeof(SearchRes));
 	ENSURE(ctx->dDec, (size_t)itemCap * sizeof(SplitDec));
+	ENSURE(ctx->dPtask, (size_t)itemCap * sizeof(PartTask));
 	ENSURE(ctx->dCounters, CNT_COUNT * 4);
 	ENSURE(ctx->dStats, STAT_COUNT * 8);
 	ENSURE(ctx->dSeeds, (size_t)nB * 4);
@@ -452,7 +453,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	A.nodes = ctx->dNodes.as<Node16>(); A.flags = ctx->dFlags.as<unsigned char>();
 	A.flagBits = ctx->dFlagBits.as<uint32_t>(); A.flagWords = flagWords;
 	A.items[0] = ctx->dItems0.as<Item>(); A.items[1] = ctx->dItems1.as<Item>();
-	A.cand = ctx->dCand.as<uint32_t>(); A.res = ctx->dRes.as<SearchRes>(); A.dec = ctx->dDec.as<SplitDec>();
+	A.cand = ctx->dCand.as<uint32_t>(); A.res = ctx->dRes.as<SearchRes>(); A.dec = ctx->dDec.as<SplitDec>(); A.ptask = ctx->dPtask.as<PartTask>();
 	A.counters = ctx->dCounters.as<uint32_t>(); A.stats = ctx->dStats.as<unsigned long long>();
 	A.injCand = nullptr;
 

@@ -93,6 +93,14 @@ struct SplitDec {
 	uint32_t lpos, lneg;  // left samples per class
 };
 
+// what the list partition needs to know about one split node, in one 16-byte load
+struct __align__(16) PartTask {
+	uint32_t tree;
+	uint32_t start;
+	uint32_t cnt;     // 0 = node does not split
+	uint32_t nleft;
+};
+
 // per-tree growth state
 struct TreeState {
 	uint32_t nNodes;      // nodes created so far

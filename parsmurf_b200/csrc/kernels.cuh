@@ -35,6 +35,7 @@ struct TrainArgs {
 	uint32_t* cand;       // [itemCap][mtry]
 	SearchRes* res;       // [itemCap][mtry]
 	SplitDec* dec;        // [itemCap]
+	PartTask* ptask;      // [itemCap]
 	uint32_t* counters;   // [CNT_COUNT]
 	unsigned long long* stats;   // [STAT_COUNT]
 	const uint32_t* injCand;     // [tree][injCandNodes][mtry] or nullptr

@@ -303,19 +303,32 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 // counts need ONE warp scan per chunk; the next chunk's loads are issued before the current chunk is evaluated.
 // The exact fp64 score (two IEEE divisions) is only evaluated for positions whose fp32 estimate could still beat the
 // lane's running best: estimate error < 1e-6 relative, filter margin 5e-6, so no winner is ever skipped.
-constexpr int SS_IPL = 4;
+#ifndef PSM_SS_IPL
+#define PSM_SS_IPL 4
+#endif
+constexpr int SS_IPL = PSM_SS_IPL;   // entries per lane per chunk (multiple of 4)
 #ifndef SS_MINB
 #define SS_MINB 8
 #endif
 
 __device__ __forceinline__ void ss_vec(const unsigned long long* p, unsigned long long (&e)[SS_IPL]) {
-	const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(p));
-	const ulonglong2 c = __ldg(reinterpret_cast<const ulonglong2*>(p + 2));
-	e[0] = a.x; e[1] = a.y; e[2] = c.x; e[3] = c.y;
+#pragma unroll
+	for (int q = 0; q < SS_IPL / 2; q++) {
+		const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(p + 2 * q));
+		e[2 * q] = a.x; e[2 * q + 1] = a.y;
+	}
 }
 __device__ __forceinline__ void ss_vec(const uint32_t* p, uint32_t (&e)[SS_IPL]) {
-	const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
-	e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w;
+	if (SS_IPL == 2) {
+		const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+		e[0] = a.x; e[1 % SS_IPL] = a.y;
+	} else {
+#pragma unroll
+		for (int q = 0; q < SS_IPL / 4; q++) {
+			const uint4 a = __ldg(reinterpret_cast<const uint4*>(p + 4 * q));
+			e[(4 * q) % SS_IPL] = a.x; e[(4 * q + 1) % SS_IPL] = a.y; e[(4 * q + 2) % SS_IPL] = a.z; e[(4 * q + 3) % SS_IPL] = a.w;
+		}
+	}
 }
 template <typename E>
 __device__ __forceinline__ void ss_load(const E* __restrict__ base, uint32_t v, uint32_t lo, uint32_t hi, E (&e)[SS_IPL]) {
@@ -339,7 +352,7 @@ __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A,
 	if (item >= nItems) return;
 	const uint32_t c = blockIdx.y;
 	const Item it = A.items[buf][item];
-	constexpr uint32_t APE = 16 / sizeof(E);                  // entries per 16 bytes
+	constexpr uint32_t APE = (SS_IPL * sizeof(E) < 16 ? SS_IPL * sizeof(E) : 16) / sizeof(E);   // entries per aligned vector load
 	const uint32_t off = it.start % APE;                      // A.stride % 4 == 0, so list + start - off is 16-byte aligned
 	const uint32_t lo = off, hi = it.cnt + off;                // valid index range in the aligned grid
 	// size classes (only used when the sub-warp instantiations are launched; measured slower than G = 32 alone at
@@ -484,7 +497,11 @@ __global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t
 	SplitDec d; d.split = 0; d.nleft = 0; d.lpos = 0; d.lneg = 0;
 	if (lane == 0) atomicAdd(&A.stats[STAT_SPLIT_BYTES], (unsigned long long)(it.npos + it.nneg) * ((unsigned long long)A.mtry * 8ull + 8ull));
 	if (!(best >= 0.0)) {                             // TreeProbability.cpp:184-186: no candidate had two distinct values
-		if (lane == 0) { write_leaf(node, it.npos, it.nneg); A.dec[item] = d; }
+		if (lane == 0) {
+			write_leaf(node, it.npos, it.nneg); A.dec[item] = d;
+			PartTask pt; pt.tree = it.tree; pt.start = it.start; pt.cnt = 0; pt.nleft = 0;
+			A.ptask[item] = pt;
+		}
 		return;
 	}
 	const SearchRes r = A.res[(size_t)item * A.mtry + bc];
@@ -500,6 +517,8 @@ __global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t
 		*node = v;
 		d.split = 1; d.nleft = r.pos + 1; d.lpos = r.lpos; d.lneg = r.lneg;
 		A.dec[item] = d;
+		PartTask pt; pt.tree = it.tree; pt.start = it.start; pt.cnt = it.cnt; pt.nleft = d.nleft;
+		A.ptask[item] = pt;
 	}
 	unsigned char* flags = A.flags + (size_t)it.tree * A.stride;
 	// latency-bound (load entry -> scattered byte store): keep four independent loads in flight per lane
@@ -640,46 +659,71 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 // ------------------------------------------------------------------------------------------ partition
 // one warp per (split node, feature): stable two-way partition of the node's segment into the other buffer.
 // Latency-bound (entry load -> flag lookup -> store), so four independent 32-entry chunks are in flight per warp.
-constexpr int PL_UNROLL = 4;
+// The kernel is bound by its chain of dependent loads (task -> entry -> flag word -> store; ncu r01: long-scoreboard stalls,
+// 64 resident warps per SM all waiting), so each warp serves PL_FPW features of its node with PL_CH chunks each in flight:
+// PL_FPW * PL_CH independent entry loads, then as many independent flag loads, per trip of the chain.  grid.y = feature group.
+#ifndef PSM_PL_FPW
+#define PSM_PL_FPW 1
+#endif
+#ifndef PSM_PL_CH
+#define PSM_PL_CH 3
+#endif
+constexpr int PL_FPW = PSM_PL_FPW;   // features per warp (measured: 1 is best -- more, smaller warps win at every level)
+constexpr int PL_CH = PSM_PL_CH;     // 32-entry chunks in flight per feature (measured at BASELINE configs[1]: 1: 39.7, 2: 30.8, 3: 29.6, 4: 31.4, 8: 44.8 ms per CV)
 
 template <typename E>
 __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint32_t nItems, int buf) {
-	const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (wid >= nItems * A.m) return;
-	const uint32_t item = wid / A.m, f = wid % A.m;
-	const SplitDec d = A.dec[item];
-	if (!d.split) return;
-	const Item it = A.items[buf][item];
+	const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (item >= nItems) return;
+	const uint4 raw = __ldg(reinterpret_cast<const uint4*>(A.ptask + item));
+	const uint32_t tree = raw.x, start = raw.y, cnt = raw.z, nleft = raw.w;
+	if (cnt == 0) return;                                      // node became a leaf
+	const uint32_t f0 = blockIdx.y * PL_FPW;
 	const int lane = lane_id();
 	const unsigned lt = lanemask_lt();
-	const size_t lo = ((size_t)it.tree * A.m + f) * A.stride + it.start;
+	const size_t lo = ((size_t)tree * A.m + f0) * A.stride + start;
 	const E* src = reinterpret_cast<const E*>(A.lists[A.listBuf]) + lo;
-	E* dstL = reinterpret_cast<E*>(A.lists[A.listBuf ^ 1]) + lo;
-	E* dstR = dstL + d.nleft;
-	// go-left flags bit-packed per tree (pack_flags_kernel): a warp's 32 lookups touch ~10 cache lines instead of ~27
-	const uint32_t* fbits = A.flagBits + (size_t)it.tree * A.flagWords;
-	uint32_t offL = 0, offR = 0;
-	for (uint32_t b = 0; b < it.cnt; b += 32 * PL_UNROLL) {
-		E e[PL_UNROLL];
-		bool valid[PL_UNROLL], gl[PL_UNROLL];
+	E* dst = reinterpret_cast<E*>(A.lists[A.listBuf ^ 1]) + lo;
+	const uint32_t* fbits = A.flagBits + (size_t)tree * A.flagWords;   // go-left flags, bit-packed per tree (pack_flags_kernel)
+	const uint32_t nf = min((uint32_t)PL_FPW, A.m - f0);
+	uint32_t offL[PL_FPW], offR[PL_FPW];
 #pragma unroll
-		for (int k = 0; k < PL_UNROLL; k++) {
-			const uint32_t i = b + k * 32 + lane;
-			valid[k] = i < it.cnt;
-			e[k] = valid[k] ? __ldg(src + i) : (E)0;
-		}
+	for (int k = 0; k < PL_FPW; k++) { offL[k] = 0; offR[k] = 0; }
+	for (uint32_t b = 0; b < cnt; b += 32 * PL_CH) {
+		E e[PL_FPW][PL_CH];
+		bool gl[PL_FPW][PL_CH];
+		// fully predicated (no branches): measured faster than skipping the empty chunks of short segments with uniform branches
 #pragma unroll
-		for (int k = 0; k < PL_UNROLL; k++) {
-			const uint32_t r = Ent<E>::row(e[k]);
-			gl[k] = valid[k] && ((__ldg(fbits + (r >> 5)) >> (r & 31u)) & 1u);
-		}
+		for (int k = 0; k < PL_FPW; k++)
 #pragma unroll
-		for (int k = 0; k < PL_UNROLL; k++) {
-			const unsigned mL = __ballot_sync(0xffffffffu, gl[k]);
-			const unsigned mR = __ballot_sync(0xffffffffu, valid[k] && !gl[k]);
-			if (gl[k]) dstL[offL + __popc(mL & lt)] = e[k];
-			else if (valid[k]) dstR[offR + __popc(mR & lt)] = e[k];
-			offL += __popc(mL); offR += __popc(mR);
+			for (int c = 0; c < PL_CH; c++) {
+				const uint32_t i = b + c * 32 + lane;
+				e[k][c] = (i < cnt && (uint32_t)k < nf) ? __ldg(src + (size_t)k * A.stride + i) : (E)0;
+			}
+#pragma unroll
+		for (int k = 0; k < PL_FPW; k++)
+#pragma unroll
+			for (int c = 0; c < PL_CH; c++) {
+				const uint32_t i = b + c * 32 + lane;
+				const uint32_t r = Ent<E>::row(e[k][c]);
+				gl[k][c] = (i < cnt && (uint32_t)k < nf) && ((__ldg(fbits + (r >> 5)) >> (r & 31u)) & 1u);
+			}
+#pragma unroll
+		for (int k = 0; k < PL_FPW; k++) {
+			if ((uint32_t)k < nf) {
+				E* dL = dst + (size_t)k * A.stride;
+				E* dR = dL + nleft;
+#pragma unroll
+				for (int c = 0; c < PL_CH; c++) {
+					const uint32_t i = b + c * 32 + lane;
+					const bool valid = i < cnt;
+					const unsigned mL = __ballot_sync(0xffffffffu, gl[k][c]);
+					const unsigned mR = __ballot_sync(0xffffffffu, valid && !gl[k][c]);
+					if (gl[k][c]) dL[offL[k] + __popc(mL & lt)] = e[k][c];
+					else if (valid) dR[offR[k] + __popc(mR & lt)] = e[k][c];
+					offL[k] += __popc(mL); offR[k] += __popc(mR);
+				}
+			}
 		}
 	}
 }
@@ -742,8 +786,10 @@ void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s) {
 }
 void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
 	size_t warps = (size_t)nItems * A.m;
-	if (A.entry32) partition_lists_kernel<uint32_t><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
-	else partition_lists_kernel<unsigned long long><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(A, nItems, buf);
+	(void)warps;
+	const dim3 grid((nItems * 32 + 127) / 128, (A.m + PL_FPW - 1) / PL_FPW);   // x: nodes (one warp each), y: feature group
+	if (A.entry32) partition_lists_kernel<uint32_t><<<grid, 128, 0, s>>>(A, nItems, buf);
+	else partition_lists_kernel<unsigned long long><<<grid, 128, 0, s>>>(A, nItems, buf);
 }
 
 }  // namespace psm
