@@ -341,6 +341,10 @@ __device__ __forceinline__ void ss_load(const E* __restrict__ base, uint32_t v, 
 	}
 }
 
+template <typename E> struct PkOf;
+template <> struct PkOf<uint32_t> { typedef uint32_t type; static constexpr int shift = 16; };
+template <> struct PkOf<unsigned long long> { typedef unsigned long long type; static constexpr int shift = 32; };
+
 // G = lanes per (node, candidate) work item.  G = 32 streams long segments chunk by chunk (128 entries per iteration);
 // G = 16 / 8 pack two / four short segments (<= 64 / <= 32 entries of the aligned grid) into one warp: at deep levels
 // most nodes hold a few dozen rows and the kernel is instruction-issue bound (ncu r01), so the per-warp fixed cost is
@@ -379,42 +383,44 @@ __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A,
 #pragma unroll
 			for (int j = 0; j < SS_IPL; j++) nx[j] = (E)0;
 		}
-		// lane-local inclusive prefix of (positives, negatives), packed hi/lo in one u64
-		unsigned long long pk[SS_IPL];
-		unsigned long long run = 0;
+		// lane-local inclusive prefix of (positives, negatives) packed in one word: 16+16 bits for the compact entries
+		// (a 128-entry chunk holds at most 128*15 samples), 32+32 bits for the wide ones
+		typedef typename PkOf<E>::type pk_t;
+		constexpr int PKS = PkOf<E>::shift;
+		pk_t pk[SS_IPL];
+		pk_t run = 0;
 #pragma unroll
 		for (int j = 0; j < SS_IPL; j++) {
-			const unsigned long long w = Ent<E>::count(e[j]);   // 0 for masked entries
-			run += Ent<E>::neg(e[j], nPosOut) ? w : (w << 32);
+			const pk_t w = (pk_t)Ent<E>::count(e[j]);             // 0 for masked entries
+			run += Ent<E>::neg(e[j], nPosOut) ? w : (w << PKS);
 			pk[j] = run;
 		}
-		unsigned long long inc = run;
+		pk_t inc = run;
 #pragma unroll
 		for (int o = 1; o < G; o <<= 1) {
-			unsigned long long t = __shfl_up_sync(gm, inc, o, G);
+			pk_t t = __shfl_up_sync(gm, inc, o, G);
 			if (gl >= o) inc += t;
 		}
-		const unsigned long long excl = inc - run;
+		const pk_t excl = inc - run;
 		const uint32_t rfirst_next_lane = Ent<E>::rank(__shfl_down_sync(gm, e[0], 1, G));
 		const uint32_t rfirst_next_chunk = Ent<E>::rank(__shfl_sync(gm, nx[0], 0, G));
-		// phase 1: fp32 estimate of the Gini proxy at every candidate position of the chunk (no divisions)
+		// phase 1: fp32 estimate of the Gini proxy at every candidate position of the chunk (no divisions, no branches).
+		// sum_c L_c^2/n_L + sum_c R_c^2/n_R  ==  n - 2 (L0 L1 / n_L + R0 R1 / n_R)   (two classes), which needs half the conversions.
 		float est[SS_IPL];
 		float emax = 0.0f;
+		const float fP = (float)it.npos, fN = (float)it.nneg, fn = (float)n;
 #pragma unroll
 		for (int j = 0; j < SS_IPL; j++) {
 			const uint32_t v = v0 + j;
 			const uint32_t rk = Ent<E>::rank(e[j]);
 			const uint32_t rnext = (j + 1 < SS_IPL) ? Ent<E>::rank(e[(j + 1) % SS_IPL]) : (gl == G - 1 ? rfirst_next_chunk : rfirst_next_lane);
-			est[j] = -1.0f;
-			if (v >= lo && v + 1 < hi && rk != rnext) {
-				const unsigned long long tot = excl + pk[j];
-				const uint32_t lpi = lp + (uint32_t)(tot >> 32), lni = ln + (uint32_t)tot;
-				const uint32_t nl = lpi + lni, nr = n - nl;
-				const uint32_t rp = it.npos - lpi, rn = it.nneg - lni;
-				const float fl = (float)lpi, fn = (float)lni, frp = (float)rp, frn = (float)rn;
-				est[j] = __fdividef(fl * fl + fn * fn, (float)nl) + __fdividef(frp * frp + frn * frn, (float)nr);
-				emax = fmaxf(emax, est[j]);
-			}
+			const pk_t tot = excl + pk[j];
+			const float fl = (float)(lp + (uint32_t)(tot >> PKS)), fq = (float)(ln + (uint32_t)(tot & (((pk_t)1 << PKS) - 1)));
+			const float nl = fl + fq, nr = fn - nl;
+			const float g2 = __fdividef(fl * fq, nl) + __fdividef((fP - fl) * (fN - fq), nr);
+			const bool ok = v >= lo && v + 1 < hi && rk != rnext;
+			est[j] = ok ? fmaf(-2.0f, g2, fn) : -1.0f;
+			emax = fmaxf(emax, est[j]);
 		}
 		// Only positions whose estimate is within the estimate's error (< 1e-6 relative; margin 4e-6) of the best
 		// estimate of this chunk, or of the best exact score of earlier chunks, can be the arg-max: evaluate those
@@ -426,8 +432,8 @@ __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A,
 		for (int j = 0; j < SS_IPL; j++) {
 			if (__any_sync(gm, est[j] >= thr)) {
 				if (est[j] >= thr) {
-					const unsigned long long tot = excl + pk[j];
-					const uint32_t lpi = lp + (uint32_t)(tot >> 32), lni = ln + (uint32_t)tot;
+					const pk_t tot = excl + pk[j];
+					const uint32_t lpi = lp + (uint32_t)(tot >> PKS), lni = ln + (uint32_t)(tot & (((pk_t)1 << PKS) - 1));
 					const uint32_t nl = lpi + lni, nr = n - nl;
 					const uint32_t rp = it.npos - lpi, rn = it.nneg - lni;
 					const unsigned long long sli = (unsigned long long)lpi * lpi + (unsigned long long)lni * lni;
@@ -442,8 +448,8 @@ __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A,
 			const float bf = best > 0.0 ? __double2float_rd(best) : 0.0f;
 			const float wb = __uint_as_float(__reduce_max_sync(gm, __float_as_uint(bf)));
 			wbound = wb * 0.999996f;
-			const unsigned long long tot = __shfl_sync(gm, inc, G - 1, G);
-			lp += (uint32_t)(tot >> 32); ln += (uint32_t)tot;
+			const pk_t tot = __shfl_sync(gm, inc, G - 1, G);
+			lp += (uint32_t)(tot >> PKS); ln += (uint32_t)(tot & (((pk_t)1 << PKS) - 1));
 #pragma unroll
 			for (int j = 0; j < SS_IPL; j++) e[j] = nx[j];
 		}
