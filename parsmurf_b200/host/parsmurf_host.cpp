@@ -69,20 +69,60 @@ void GlibcRand::shuffle(uint32_t* a, size_t n) {
 	}
 }
 
+// ------------------------------------------------------------------------------------------ index-buffer pool
+// The fold / train-test index arrays are a few MB each and rebuilt for every CV.  Fresh allocations of that size come
+// straight from mmap, and their first-touch page faults cost more than filling them (measured on the B200 host: 3.2 MB
+// filled in 1.6-2 ms fresh vs 0.2 ms recycled), so the library keeps released index vectors and hands them out again.
+namespace {
+struct IndexPool {
+	std::mutex m;
+	std::vector<std::vector<uint32_t>> spare;
+	static constexpr size_t kMaxSpare = 64;
+	std::vector<uint32_t> take(size_t minCap) {
+		std::vector<uint32_t> v;
+		{
+			std::lock_guard<std::mutex> lk(m);
+			size_t best = spare.size();
+			for (size_t i = 0; i < spare.size(); i++)
+				if (spare[i].capacity() >= minCap && (best == spare.size() || spare[i].capacity() < spare[best].capacity())) best = i;
+			if (best != spare.size()) { v.swap(spare[best]); spare.erase(spare.begin() + best); }
+		}
+		v.clear();
+		v.reserve(minCap);
+		return v;
+	}
+	void give(std::vector<uint32_t>& v) {
+		if (v.capacity() < 16384) return;
+		std::lock_guard<std::mutex> lk(m);
+		if (spare.size() < kMaxSpare) { spare.emplace_back(); spare.back().swap(v); }
+	}
+};
+IndexPool g_pool;
+}  // namespace
+
 // ------------------------------------------------------------------------------------------ Folds (src/folds.cpp:26-117)
 Folds::Folds(uint32_t numberOfFolds, uint32_t classSize_, const uint32_t* labels_, std::vector<uint32_t>& ff, bool randomFold_, GlibcRand* rng_)
     : classSize(classSize_), nFolds(numberOfFolds), labels(labels_), fromFile(ff), nPos(numberOfFolds), nNeg(numberOfFolds),
-      foldsIdx(numberOfFolds + 1), folds(classSize_), randomFold(randomFold_), rng(rng_) {}
+      foldsIdx(numberOfFolds + 1), randomFold(randomFold_), rng(rng_) {
+	folds = g_pool.take(classSize); folds.resize(classSize);
+}
+Folds::~Folds() { g_pool.give(folds); g_pool.give(posList); g_pool.give(negList); }
 
 void Folds::computeFolds() {
-	totPos = 0;
-	for (uint32_t i = 0; i < classSize; i++) totPos += labels[i] >= 1;
-	totNeg = classSize - totPos;
 	std::fill(nPos.begin(), nPos.end(), 0);
 	std::fill(nNeg.begin(), nNeg.end(), 0);
+	auto offsets = [&]() {
+		posOff.assign(nFolds + 1, 0); negOff.assign(nFolds + 1, 0);
+		for (uint32_t f = 0; f < nFolds; f++) { posOff[f + 1] = posOff[f] + nPos[f]; negOff[f + 1] = negOff[f] + nNeg[f]; }
+		totPos = posOff[nFolds]; totNeg = negOff[nFolds];
+		posList = g_pool.take(totPos); posList.resize(totPos);
+		negList = g_pool.take(totNeg); negList.resize(totNeg);
+	};
 	if (randomFold) {
-		std::vector<uint32_t> pos, neg;
+		std::vector<uint32_t> pos = g_pool.take(classSize), neg = g_pool.take(classSize);
+		struct Back { std::vector<uint32_t>& v; ~Back() { g_pool.give(v); } } backPos{pos}, backNeg{neg};
 		for (uint32_t i = 0; i < classSize; i++) (labels[i] > 0 ? pos : neg).push_back(i);
+		totPos = (uint32_t)pos.size(); totNeg = (uint32_t)neg.size();
 		rng->shuffle(pos.data(), pos.size());
 		rng->shuffle(neg.data(), neg.size());
 		uint32_t ffSize = classSize / nFolds, ffRemn = classSize % nFolds;
@@ -91,21 +131,31 @@ void Folds::computeFolds() {
 			foldsIdx[i + 1] = foldsIdx[i] + ffSize;
 			if (ffRemn != 0) { foldsIdx[i + 1]++; ffRemn--; }
 		}
+		// round-robin deal: all positives first, then the negatives (src/folds.cpp:52-63)
 		for (uint32_t i = 0; i < totPos; i++) { folds[foldsIdx[i % nFolds] + i / nFolds] = pos[i]; nPos[i % nFolds]++; }
 		for (uint32_t i = totPos; i < totPos + totNeg; i++) { folds[foldsIdx[i % nFolds] + i / nFolds] = neg[i - totPos]; nNeg[i % nFolds]++; }
+		offsets();
+		for (uint32_t f = 0; f < nFolds; f++) {                              // fold f = its positives, then its negatives, in deal order
+			std::copy(folds.begin() + foldsIdx[f], folds.begin() + foldsIdx[f] + nPos[f], posList.begin() + posOff[f]);
+			std::copy(folds.begin() + foldsIdx[f] + nPos[f], folds.begin() + foldsIdx[f + 1], negList.begin() + negOff[f]);
+		}
 	} else {
+		if (fromFile.size() < classSize) throw Error(PSM_E_ARG, "Folds: fold assignment shorter than the label vector");
 		std::vector<uint32_t> hist(nFolds, 0);
-		for (uint32_t v : fromFile) {
+		for (uint32_t i = 0; i < classSize; i++) {
+			const uint32_t v = fromFile[i];
 			if (v >= nFolds) throw Error(PSM_E_ARG, "Folds: fold id out of range");
 			hist[v]++;
+			nPos[v] += labels[i] > 0;
 		}
 		foldsIdx[0] = 0;
-		for (uint32_t i = 1; i <= nFolds; i++) foldsIdx[i] = foldsIdx[i - 1] + hist[i - 1];
-		std::fill(hist.begin(), hist.end(), 0);
-		for (uint32_t i = 0; i < classSize; i++) {
-			uint32_t bin = fromFile[i];
-			folds[foldsIdx[bin] + hist[bin]++] = i;
-			if (labels[i] > 0) nPos[bin]++; else nNeg[bin]++;
+		for (uint32_t f = 0; f < nFolds; f++) { nNeg[f] = hist[f] - nPos[f]; foldsIdx[f + 1] = foldsIdx[f] + hist[f]; }
+		offsets();
+		std::vector<uint32_t> cf(foldsIdx.begin(), foldsIdx.end() - 1), cp(posOff.begin(), posOff.end() - 1), cn(negOff.begin(), negOff.end() - 1);
+		for (uint32_t i = 0; i < classSize; i++) {                            // one pass: every fold keeps ascending example order (src/folds.cpp:93-110)
+			const uint32_t bin = fromFile[i];
+			folds[cf[bin]++] = i;
+			if (labels[i] > 0) posList[cp[bin]++] = i; else negList[cn[bin]++] = i;
 		}
 	}
 	maxPos = *std::max_element(nPos.begin(), nPos.end());
@@ -115,15 +165,16 @@ void Folds::computeFolds() {
 // ------------------------------------------------------------------------------------------ TestTrainDivider
 void TestTrainDivider::build(uint32_t i, uint32_t cur, int64_t jump) {
 	const Folds* F = folds;
+	auto blk = [](std::vector<uint32_t>& dst, const std::vector<uint32_t>& src, const std::vector<uint32_t>& off, uint32_t f) {
+		dst.insert(dst.end(), src.begin() + off[f], src.begin() + off[f + 1]);
+	};
 	const uint32_t jumpPos = jump >= 0 ? F->nPos[jump] : 0, jumpNeg = jump >= 0 ? F->nNeg[jump] : 0;
-	testPosIdx[i].reserve(F->nPos[cur]); testNegIdx[i].reserve(F->nNeg[cur]);
-	trngPosIdx[i].reserve(F->totPos - F->nPos[cur] - jumpPos); trngNegIdx[i].reserve(F->totNeg - F->nNeg[cur] - jumpNeg);
-	for (uint32_t j = F->foldsIdx[cur]; j < F->foldsIdx[cur + 1]; j++)
-		(F->labels[F->folds[j]] < 1 ? testNegIdx[i] : testPosIdx[i]).push_back(F->folds[j]);
-	for (uint32_t kf = 0; kf < F->nFolds; kf++) {
+	testPosIdx[i] = g_pool.take(F->nPos[cur]); testNegIdx[i] = g_pool.take(F->nNeg[cur]);
+	trngPosIdx[i] = g_pool.take(F->totPos - F->nPos[cur] - jumpPos); trngNegIdx[i] = g_pool.take(F->totNeg - F->nNeg[cur] - jumpNeg);
+	blk(testPosIdx[i], F->posList, F->posOff, cur); blk(testNegIdx[i], F->negList, F->negOff, cur);
+	for (uint32_t kf = 0; kf < F->nFolds; kf++) {                            // ascending fold order, as src/testtraindivider.cpp:57-80
 		if (kf == cur || (int64_t)kf == jump) continue;
-		for (uint32_t j = F->foldsIdx[kf]; j < F->foldsIdx[kf + 1]; j++)
-			(F->labels[F->folds[j]] < 1 ? trngNegIdx[i] : trngPosIdx[i]).push_back(F->folds[j]);
+		blk(trngPosIdx[i], F->posList, F->posOff, kf); blk(trngNegIdx[i], F->negList, F->negOff, kf);
 	}
 }
 
@@ -143,24 +194,32 @@ TestTrainDivider::TestTrainDivider(const Folds* folds_, uint8_t wmode_, GlibcRan
 		trngPosNum.push_back(folds->totPos - folds->nPos[i]); trngNegNum.push_back(folds->totNeg - folds->nNeg[i]);
 	}
 	if (wmode == MODE_TRAIN) { trngPosNum[0] = testPosNum[0]; trngNegNum[0] = testNegNum[0]; }   // :33-36
-	joined.assign(nFolds, 0);
+	// Fold f is needed ~one fold of GPU work after fold f-1, so one thread building them in order keeps fold 0's latency
+	// at a single build + shuffle and never competes with itself for cores.
 	const GlibcRand start = *rng;
-	for (uint32_t i = 0; i < nFolds; i++)
-		workers.emplace_back([this, i, start, off]() {
+	worker = std::thread([this, start, off]() {
+		for (uint32_t i = 0; i < nFolds; i++) {
 			GlibcRand local = start;
 			local.discard(off[i]);
 			build(i, i, -1);
 			local.shuffle(trngNegIdx[i].data(), trngNegIdx[i].size());      // :90
 			if (this->wmode == MODE_TRAIN && i == 0) { trngPosIdx[0] = testPosIdx[0]; trngNegIdx[0] = testNegIdx[0]; }   // :101-104
-		});
+			{ std::lock_guard<std::mutex> lk(mtx); nReady = i + 1; }
+			cv.notify_all();
+		}
+	});
 	rng->discard(off[nFolds]);
 }
 
 TestTrainDivider::~TestTrainDivider() {
-	for (size_t i = 0; i < workers.size(); i++) if (!joined[i]) workers[i].join();
+	if (worker.joinable()) worker.join();
+	for (auto* vv : {&testPosIdx, &testNegIdx, &trngPosIdx, &trngNegIdx})
+		for (auto& v : *vv) g_pool.give(v);
 }
 void TestTrainDivider::ensure(uint32_t fold) const {
-	if (fold < workers.size() && !joined[fold]) { workers[fold].join(); joined[fold] = 1; }
+	if (!worker.joinable()) return;                                         // inner-CV constructor builds synchronously
+	std::unique_lock<std::mutex> lk(mtx);
+	cv.wait(lk, [&] { return nReady > fold || nReady >= nFolds; });
 }
 
 // src/testtraindivider.cpp:126-236 -- inner CV: fold `foldToJump` is left out entirely, no shuffle
@@ -368,7 +427,7 @@ void hyperSMURF::smurfIt() {                                                // s
 			nPart = g.nParts; fp = g.fp; ratio = g.ratio; k = g.k; numTrees = g.nTrees; mtry = g.mtry;
 			part->nPart = nPart; part->fp = fp; part->ratio = ratio;
 		}
-		part->setFold(currentFold);                                         // :255
+		{ PhaseScope ps(PH_FOLDS_TTD); part->setFold(currentFold); }      // :255 (waits for the fold's background build + shuffle)
 		dev->invalidateFold();
 		{ PhaseScope ps(PH_FOLD_BEGIN); dev->ensureFold(part.get()); }
 
@@ -605,8 +664,12 @@ int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const 
 		if (batchBudget) dev.check(psm_set_batch_budget(dev.ctx, batchBudget));
 		if (profile) dev.check(psm_profile_enable(dev.ctx, 1));
 		GlibcRand rng(1);
-		std::vector<uint32_t> y(labels, labels + n), ff;
-		if (foldAssign) ff.assign(foldAssign, foldAssign + n);
+		struct Pooled {                                     // label / fold-id copies live in recycled buffers too
+			std::vector<uint32_t> v;
+			Pooled(const uint32_t* src, size_t cnt) { if (src) { v = g_pool.take(cnt); v.assign(src, src + cnt); } }
+			~Pooled() { g_pool.give(v); }
+		} yBuf(labels, n), ffBuf(foldAssign, n);
+		std::vector<uint32_t>& y = yBuf.v; std::vector<uint32_t>& ff = ffBuf.v;
 		Folds folds(nFolds, n, y.data(), ff, foldAssign == nullptr, &rng);
 		{ PhaseScope ps(PH_FOLDS_TTD); folds.computeFolds(); }
 		CommonParams cp;
@@ -645,8 +708,12 @@ int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* la
 	try {
 		Device dev(device, nullptr);
 		GlibcRand rng(1);
-		std::vector<uint32_t> y(labels, labels + n), ff;
-		if (foldAssign) ff.assign(foldAssign, foldAssign + n);
+		struct Pooled {                                     // label / fold-id copies live in recycled buffers too
+			std::vector<uint32_t> v;
+			Pooled(const uint32_t* src, size_t cnt) { if (src) { v = g_pool.take(cnt); v.assign(src, src + cnt); } }
+			~Pooled() { g_pool.give(v); }
+		} yBuf(labels, n), ffBuf(foldAssign, n);
+		std::vector<uint32_t>& y = yBuf.v; std::vector<uint32_t>& ff = ffBuf.v;
 		Folds folds(nFolds, n, y.data(), ff, foldAssign == nullptr, &rng);
 		folds.computeFolds();
 		CommonParams cp;

@@ -18,6 +18,8 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -78,6 +80,8 @@ private:
 class Folds {
 public:
 	Folds(uint32_t numberOfFolds, uint32_t classSize, const uint32_t* labels, std::vector<uint32_t>& ff, bool randomFold, GlibcRand* rng);
+	~Folds();
+	Folds(const Folds&) = delete;
 	void computeFolds();
 	const uint32_t classSize, nFolds;
 	const uint32_t* labels;
@@ -85,6 +89,9 @@ public:
 	uint32_t totPos = 0, totNeg = 0;
 	std::vector<uint32_t> nPos, nNeg, foldsIdx, folds;
 	uint32_t maxPos = 0, maxNeg = 0;
+	// new: folds[] split by class, fold by fold in the same order (positives of fold f at posList[posOff[f] .. posOff[f+1])),
+	// so TestTrainDivider assembles its index arrays by block copies instead of re-reading the labels per fold
+	std::vector<uint32_t> posOff, negOff, posList, negList;
 	bool randomFold;
 	GlibcRand* rng;
 };
@@ -95,8 +102,8 @@ public:
 	TestTrainDivider(const Folds* folds, uint8_t wmode, GlibcRand* rng);
 	TestTrainDivider(const Folds* folds, uint8_t wmode, uint32_t foldToJump);
 	~TestTrainDivider();
-	// the per-fold index arrays are built (and shuffled) by background threads; the counts are valid immediately,
-	// the arrays of fold f after ensure(f)
+	// the per-fold index arrays are built (and shuffled) in fold order by one background thread; the counts are valid
+	// immediately, the arrays of fold f after ensure(f)
 	void ensure(uint32_t fold) const;
 	const Folds* const folds;
 	const uint8_t wmode;
@@ -105,8 +112,10 @@ public:
 	std::vector<uint32_t> testPosNum, testNegNum, trngPosNum, trngNegNum;
 private:
 	void build(uint32_t i, uint32_t currFoldIdx, int64_t foldToJump);
-	mutable std::vector<std::thread> workers;
-	mutable std::vector<char> joined;
+	mutable std::thread worker;
+	mutable std::mutex mtx;
+	mutable std::condition_variable cv;
+	uint32_t nReady = 0;   // folds [0, nReady) are complete (guarded by mtx)
 };
 
 // reference src/partition.h:7-36

@@ -34,12 +34,14 @@ def hlib():
 
 
 def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, device=0, stream=None, tie_mode=0, eval_fold_curves=True,
-           rank=0, world=1, reduce=None, batch_budget=0, profile=False, x_device_ptr=None, n=None, m=None, dev_handle=None):
+           rank=0, world=1, reduce=None, batch_budget=0, profile=False, x_device_ptr=None, n=None, m=None, dev_handle=None, out=None):
     """Run the whole CV on one GPU (or this rank's share of the partitions when world > 1).
 
     x: host row-major float64 [n][m+1] (label column 1.0/2.0), or None with x_device_ptr/n/m for a dataset already in HBM.
     folds: per-example fold ids, or None for the reference's random stratified folds.
     reduce(dev_ptr, count): sums `count` float64 at device pointer `dev_ptr` across ranks in place (world > 1).
+    out: optional (class1, class2) float64 arrays of length n to reuse; they are zeroed and filled (a fresh 8 MB array costs
+    more in first-touch page faults than the copy into it).
     Returns dict(class1, class2, auroc, auprc, fold_metrics, kernel_ms, kernel_launches, stats)."""
     L = hlib()
     if x is not None:
@@ -50,7 +52,13 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
         xptr, isdev = x_device_ptr, 1
     labels = np.ascontiguousarray(labels, np.uint32)
     folds = None if folds is None else np.ascontiguousarray(folds, np.uint32)
-    c1 = np.zeros(n); c2 = np.zeros(n); met = np.zeros(2); fm = np.zeros((nFolds, 2))
+    if out is not None:
+        c1, c2 = out
+        assert c1.dtype == np.float64 and c2.dtype == np.float64 and c1.shape == (n,) and c2.shape == (n,) and c1.flags.c_contiguous and c2.flags.c_contiguous
+        c1.fill(0.0); c2.fill(0.0)
+    else:
+        c1 = np.zeros(n); c2 = np.zeros(n)
+    met = np.zeros(2); fm = np.zeros((nFolds, 2))
     kms = np.zeros(len(KERNEL_CLASSES)); kl = np.zeros(len(KERNEL_CLASSES), np.uint64); st = np.zeros(3, np.uint64)
     err = C.create_string_buffer(512)
     ph = np.zeros(len(PHASES))
