@@ -62,7 +62,7 @@ struct psm_ctx {
 	// train
 	uint32_t T = 0, mtry = 0;
 	TrainArgs A;
-	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dNodes8, dFlags, dFlagBits, dItems0, dItems1, dCand, dRes, dDec, dPtask, dCounters, dStats, dSeeds,
+	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dNodes8, dSplitFeat, dFlagBits, dItems0, dItems1, dCand, dRes, dDec, dPtask, dCounters, dStats, dSeeds,
 	    dInjBoot, dInjBootOff, dInjCand;
 	uint32_t* hCounters = nullptr;   // pinned
 	void* hStage = nullptr;          // pinned D2H staging
@@ -180,7 +180,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf* bufs[] = {&ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dClass12,
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
-	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dFlags, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1,
+	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dSplitFeat, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dPtask, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
 	                  &ctx->dInjCand, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
 	                  &ctx->cScores, &ctx->cKeysA, &ctx->cKeysB, &ctx->cValsA, &ctx->cValsB, &ctx->cHist};
@@ -432,7 +432,6 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	ENSURE(ctx->dTs, (size_t)nTrees * sizeof(TreeState));
 	ENSURE(ctx->dNodes, (size_t)nTrees * NC * sizeof(Node16));
 	ENSURE(ctx->dNodes8, (size_t)nTrees * NC * 8);
-	ENSURE(ctx->dFlags, (size_t)nTrees * stride);
 	const uint32_t flagWords = (stride + 31) / 32;
 	ENSURE(ctx->dFlagBits, (size_t)nTrees * flagWords * 4);
 	ENSURE(ctx->dItems0, (size_t)itemCap * sizeof(Item)); ENSURE(ctx->dItems1, (size_t)itemCap * sizeof(Item));
@@ -440,6 +439,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	ENSURE(ctx->dRes, (size_t)itemCap * mtry * sizeof(SearchRes));
 	ENSURE(ctx->dDec, (size_t)itemCap * sizeof(SplitDec));
 	ENSURE(ctx->dPtask, (size_t)itemCap * sizeof(PartTask));
+	ENSURE(ctx->dSplitFeat, (size_t)itemCap * 4);
 	ENSURE(ctx->dCounters, CNT_COUNT * 4);
 	ENSURE(ctx->dStats, STAT_COUNT * 8);
 	ENSURE(ctx->dSeeds, (size_t)nB * 4);
@@ -450,10 +450,10 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	A.parts = ctx->dParts.as<PartDesc>(); A.Dall = ctx->dD.as<double>(); A.Sall = ctx->dS.as<entry_t>();
 	A.lists[0] = ctx->dLists0.p; A.lists[1] = ctx->dLists1.p; A.entry32 = entry32;
 	A.inbag = ctx->dInbag.as<uint32_t>(); A.mt = ctx->dMt.as<unsigned long long>(); A.ts = ctx->dTs.as<TreeState>();
-	A.nodes = ctx->dNodes.as<Node16>(); A.flags = ctx->dFlags.as<unsigned char>();
+	A.nodes = ctx->dNodes.as<Node16>();
 	A.flagBits = ctx->dFlagBits.as<uint32_t>(); A.flagWords = flagWords;
 	A.items[0] = ctx->dItems0.as<Item>(); A.items[1] = ctx->dItems1.as<Item>();
-	A.cand = ctx->dCand.as<uint32_t>(); A.res = ctx->dRes.as<SearchRes>(); A.dec = ctx->dDec.as<SplitDec>(); A.ptask = ctx->dPtask.as<PartTask>();
+	A.cand = ctx->dCand.as<uint32_t>(); A.res = ctx->dRes.as<SearchRes>(); A.dec = ctx->dDec.as<SplitDec>(); A.ptask = ctx->dPtask.as<PartTask>(); A.splitFeat = ctx->dSplitFeat.as<uint32_t>();
 	A.counters = ctx->dCounters.as<uint32_t>(); A.stats = ctx->dStats.as<unsigned long long>();
 	A.injCand = nullptr;
 
@@ -539,7 +539,11 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		if (trace) cudaEventRecord(tev[0], s);
 		{ ProfScope ps(ctx, K_SEARCH, 1); launch_split_search(A, nItems, buf, s); }
 		if (trace) cudaEventRecord(tev[1], s);
-		{ ProfScope ps(ctx, K_SELECT, 2); launch_split_select(A, nItems, buf, s); launch_pack_flags(A, s); }
+		{
+			ProfScope ps(ctx, K_SELECT, 2);
+			launch_split_select(A, nItems, buf, s);
+			if (launch_tree_flags(A, s)) return fail(ctx, PSM_E_CUDA, "batch_train: cannot configure the flag bitmap");
+		}
 		if (trace) cudaEventRecord(tev[2], s);
 		{ ProfScope ps(ctx, K_FINALIZE, 1); launch_level_finalize(A, buf, s); }
 		if (trace) cudaEventRecord(tev[3], s);
@@ -549,8 +553,14 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 			cudaStreamSynchronize(s);
 			float t[4];
 			for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
-			fprintf(stderr, "[psm level %3llu] items %7u  search %8.1f us  select %7.1f us  finalize %7.1f us  partition %8.1f us\n",
-			        (unsigned long long)levels, nItems, t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3);
+			unsigned long long hs2[STAT_COUNT];
+			cudaMemcpy(hs2, A.stats, STAT_COUNT * 8, cudaMemcpyDeviceToHost);
+			static unsigned long long prevBytes = 0;
+			if (levels == 0) prevBytes = 0;
+			const unsigned long long samples = (hs2[STAT_SPLIT_BYTES] - prevBytes) / ((unsigned long long)mtry * 8ull + 8ull);
+			prevBytes = hs2[STAT_SPLIT_BYTES];
+			fprintf(stderr, "[psm level %3llu] items %7u samples %9llu  search %8.1f us  select %7.1f us  finalize %7.1f us  partition %8.1f us\n",
+			        (unsigned long long)levels, nItems, samples, t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3);
 			for (auto& e : tev) cudaEventDestroy(e);
 		}
 		CU(cudaGetLastError());

@@ -28,14 +28,14 @@ struct TrainArgs {
 	unsigned long long* mt;   // [tree][312]
 	TreeState* ts;
 	Node16* nodes;        // [tree][NC]
-	unsigned char* flags; // [tree][stride]   go-left flag per row, written by split_select
-	uint32_t* flagBits;   // [tree][flagWords] the same flags bit-packed for the partition kernel
+	uint32_t* flagBits;   // [tree][flagWords] go-left flag per in-bag row, bit-packed (tree_flags_kernel -> partition_lists_kernel)
 	uint32_t flagWords;
 	Item* items[2];
 	uint32_t* cand;       // [itemCap][mtry]
 	SearchRes* res;       // [itemCap][mtry]
 	SplitDec* dec;        // [itemCap]
 	PartTask* ptask;      // [itemCap]
+	uint32_t* splitFeat;  // [itemCap] winning feature of each split node
 	uint32_t* counters;   // [CNT_COUNT]
 	unsigned long long* stats;   // [STAT_COUNT]
 	const uint32_t* injCand;     // [tree][injCandNodes][mtry] or nullptr
@@ -62,7 +62,7 @@ int launch_init_trees(const TrainArgs& A, cudaStream_t s);
 void launch_split_search(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
 void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s);
-void launch_pack_flags(const TrainArgs& A, cudaStream_t s);
+int launch_tree_flags(const TrainArgs& A, cudaStream_t s);
 void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
 // glibc_rand.cu
 void glibc_window_jump(uint32_t* w31, uint64_t n);

@@ -501,7 +501,6 @@ __global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t
 	}
 	Node16* node = A.nodes + (size_t)it.tree * A.NC + it.node;
 	SplitDec d; d.split = 0; d.nleft = 0; d.lpos = 0; d.lneg = 0;
-	if (lane == 0) atomicAdd(&A.stats[STAT_SPLIT_BYTES], (unsigned long long)(it.npos + it.nneg) * ((unsigned long long)A.mtry * 8ull + 8ull));
 	if (!(best >= 0.0)) {                             // TreeProbability.cpp:184-186: no candidate had two distinct values
 		if (lane == 0) {
 			write_leaf(node, it.npos, it.nneg); A.dec[item] = d;
@@ -525,15 +524,61 @@ __global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t
 		A.dec[item] = d;
 		PartTask pt; pt.tree = it.tree; pt.start = it.start; pt.cnt = it.cnt; pt.nleft = d.nleft;
 		A.ptask[item] = pt;
+		A.splitFeat[item] = f;
 	}
-	unsigned char* flags = A.flags + (size_t)it.tree * A.stride;
-	// latency-bound (load entry -> scattered byte store): keep four independent loads in flight per lane
-	for (uint32_t b = 0; b < it.cnt; b += 128) {
-		E e4[4];
+}
+
+// ------------------------------------------------------------------------------------------ go-left flags
+// One CTA per tree: bit r of the tree's bitmap = "in-bag row r goes to the left child of its node".  Only the left part
+// [0, nleft) of every split node's segment in the winning feature's list is read; the bits are set with shared-memory
+// atomics and the bitmap leaves the SM as one coalesced store.  (Per-row byte stores straight to global memory were bound
+// by scattered-store throughput: ~60 us per level for the 6M rows of a BASELINE configs[1] fold.)
+constexpr int TF_THREADS = 256;
+constexpr uint32_t TF_LONG = 1024;   // segments with at least this many left entries are shared by the whole CTA
+template <typename E>
+__global__ void __launch_bounds__(TF_THREADS) tree_flags_kernel(TrainArgs A, int bitmapInSmem) {
+	extern __shared__ uint32_t bm_s[];
+	const uint32_t tree = blockIdx.x;
+	const TreeState ts = A.ts[tree];           // still this level's item range: level_finalize runs after this kernel
+	if (ts.itemCount == 0) return;
+	uint32_t* out = A.flagBits + (size_t)tree * A.flagWords;
+	uint32_t* bm = bitmapInSmem ? bm_s : out;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	for (uint32_t w = tid; w < A.flagWords; w += TF_THREADS) bm[w] = 0;
+	__syncthreads();
+	const PartTask* tasks = A.ptask + ts.itemBase;
+	const uint32_t* feats = A.splitFeat + ts.itemBase;
+	const E* lists = reinterpret_cast<const E*>(A.lists[A.listBuf]) + (size_t)tree * A.m * A.stride;
+	auto mark = [&](const E* seg, uint32_t nleft, uint32_t first, uint32_t step) {
+		for (uint32_t b = first; b < nleft; b += 4 * step) {
+			E e4[4];
 #pragma unroll
-		for (int k = 0; k < 4; k++) { const uint32_t i = b + k * 32 + lane; e4[k] = (i < it.cnt) ? __ldg(list + i) : (E)0; }
+			for (int k = 0; k < 4; k++) { const uint32_t i = b + k * step; e4[k] = (i < nleft) ? __ldg(seg + i) : (E)0; }
 #pragma unroll
-		for (int k = 0; k < 4; k++) { const uint32_t i = b + k * 32 + lane; if (i < it.cnt) flags[Ent<E>::row(e4[k])] = (i <= r.pos) ? 1 : 0; }
+			for (int k = 0; k < 4; k++) {
+				const uint32_t i = b + k * step;
+				if (i < nleft) { const uint32_t r = Ent<E>::row(e4[k]); atomicOr(&bm[r >> 5], 1u << (r & 31)); }
+			}
+		}
+	};
+	// long segments (top levels): all threads; short ones: one warp each
+	uint32_t nshort = 0;
+	for (uint32_t i = 0; i < ts.itemCount; i++) {
+		const uint4 raw = __ldg(reinterpret_cast<const uint4*>(tasks + i));   // {tree, start, cnt, nleft}
+		if (raw.z == 0) continue;                                             // node became a leaf
+		if (raw.w >= TF_LONG) mark(lists + (size_t)__ldg(feats + i) * A.stride + raw.y, raw.w, tid, TF_THREADS);
+		else nshort++;
+	}
+	if (nshort) {
+		for (uint32_t i = warp; i < ts.itemCount; i += TF_THREADS / 32) {
+			const uint4 raw = __ldg(reinterpret_cast<const uint4*>(tasks + i));
+			if (raw.z == 0 || raw.w >= TF_LONG) continue;
+			mark(lists + (size_t)__ldg(feats + i) * A.stride + raw.y, raw.w, lane, 32);
+		}
+	}
+	if (bitmapInSmem) {
+		__syncthreads();
+		for (uint32_t w = tid; w < A.flagWords; w += TF_THREADS) out[w] = bm_s[w];
 	}
 }
 
@@ -555,13 +600,15 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 
 	// pass 1: count splits and live children
 	uint32_t nsplit = 0, nlive = 0;
+	unsigned long long searched = 0;   // samples of the nodes that reached findBestSplit this level (SURVEY 8(d) byte count; one atomic per tree)
 	for (uint32_t b = 0; b < ts.itemCount; b += 32) {
 		uint32_t i = b + lane;
 		uint32_t l = 0, s = 0;
 		if (i < ts.itemCount) {
 			SplitDec d = dec[i];
+			const Item it = cur[i];
+			searched += it.npos + it.nneg;
 			if (d.split) {
-				Item it = cur[i];
 				s = 1;
 				l = (node_live(d.lpos, d.lneg) ? 1u : 0u) + (node_live(it.npos - d.lpos, it.nneg - d.lneg) ? 1u : 0u);
 			}
@@ -569,6 +616,8 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 		for (int o = 16; o > 0; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); s += __shfl_xor_sync(0xffffffffu, s, o); }
 		nlive += l; nsplit += s;
 	}
+	for (int o = 16; o > 0; o >>= 1) searched += __shfl_xor_sync(0xffffffffu, searched, o);
+	if (lane == 0) atomicAdd(&A.stats[STAT_SPLIT_BYTES], searched * ((unsigned long long)A.mtry * 8ull + 8ull));
 	if (nsplit == 0) {
 		if (lane == 0) { ts.itemCount = 0; A.ts[tree] = ts; }
 		return;
@@ -734,22 +783,6 @@ __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint3
 	}
 }
 
-// 32 flag bytes -> one word, all trees of the batch
-__global__ void __launch_bounds__(256) pack_flags_kernel(TrainArgs A) {
-	const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= (size_t)A.nTrees * A.flagWords) return;
-	const uint32_t tree = (uint32_t)(w / A.flagWords), wi = (uint32_t)(w % A.flagWords);
-	const uint32_t* src = reinterpret_cast<const uint32_t*>(A.flags + (size_t)tree * A.stride) + (size_t)wi * 8;   // stride % 4 == 0
-	const uint32_t nw = A.stride / 4;
-	uint32_t bits = 0;
-#pragma unroll
-	for (int q = 0; q < 8; q++) {
-		const uint32_t v = (wi * 8 + q < nw) ? __ldg(src + q) : 0u;
-		bits |= ((v & 1u) | ((v >> 7) & 2u) | ((v >> 14) & 4u) | ((v >> 21) & 8u)) << (4 * q);
-	}
-	A.flagBits[w] = bits;
-}
-
 // ------------------------------------------------------------------------------------------ launchers
 void launch_bootstrap(const TrainArgs& A, const uint32_t* forestSeeds, cudaStream_t s) {
 	bootstrap_kernel<<<A.nTrees, 32, 0, s>>>(A, forestSeeds);
@@ -783,9 +816,18 @@ void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStrea
 	if (A.entry32) split_select_kernel<uint32_t><<<(nItems + 3) / 4, 128, 0, s>>>(A, nItems, buf);
 	else split_select_kernel<unsigned long long><<<(nItems + 3) / 4, 128, 0, s>>>(A, nItems, buf);
 }
-void launch_pack_flags(const TrainArgs& A, cudaStream_t s) {
-	size_t words = (size_t)A.nTrees * A.flagWords;
-	pack_flags_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(A);
+int launch_tree_flags(const TrainArgs& A, cudaStream_t s) {
+	const size_t bytes = (size_t)A.flagWords * 4;
+	const int inSmem = bytes <= 160 * 1024;   // 1.3M rows per tree; beyond that the bitmap is updated in place in global memory
+	const size_t smem = inSmem ? bytes : 0;
+	if (A.entry32) {
+		if (smem > 48 * 1024 && cudaFuncSetAttribute(tree_flags_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+		tree_flags_kernel<uint32_t><<<A.nTrees, TF_THREADS, smem, s>>>(A, inSmem);
+	} else {
+		if (smem > 48 * 1024 && cudaFuncSetAttribute(tree_flags_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+		tree_flags_kernel<unsigned long long><<<A.nTrees, TF_THREADS, smem, s>>>(A, inSmem);
+	}
+	return 0;
 }
 void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s) {
 	level_finalize_kernel<<<A.nTrees, 32, tree_smem_bytes(A.m, A.mtry), s>>>(A, buf);
