@@ -135,6 +135,9 @@ int psm_batch_capacity(psm_ctx* ctx, uint32_t nParts, uint32_t fp, uint32_t rati
  *      5 split_search, 6 split_select, 7 level_finalize, 8 partition_lists, 9 predict, 10 curves, 11 gather. --- */
 #define PSM_NUM_KERNEL_CLASSES 12
 int psm_profile_enable(psm_ctx* ctx, int on);
+/* restrict the event timing to the classes whose bit (1u << id) is set (default: all); launch counts are always kept.
+ * Timing one class costs two event records per launch of it, so a throughput run times only the kernel it reports on. */
+int psm_profile_classes(psm_ctx* ctx, uint32_t class_mask);
 int psm_profile_reset(psm_ctx* ctx);
 int psm_profile_get(psm_ctx* ctx, double* ms /*[12]*/, uint64_t* launches /*[12]*/);
 /* algorithmic split-search bytes (sum over searched nodes of n_node*(mtry*8+8)) since last reset */

@@ -81,6 +81,7 @@ def lib():
         L.psm_curves.argtypes = [vp, u32p, dp, u64, C.c_int, dp]
         L.psm_fold_run_partitions.argtypes = [vp] + [u32] * 9 + [i32p]
         L.psm_profile_enable.argtypes = [vp, C.c_int]
+        L.psm_profile_classes.argtypes = [vp, C.c_uint32]
         L.psm_profile_reset.argtypes = [vp]
         L.psm_profile_get.argtypes = [vp, dp, u64p]
         L.psm_stats_get.argtypes = [vp, u64p, u64p, u64p]

@@ -83,6 +83,7 @@ struct psm_ctx {
 
 	// profiling
 	bool profOn = false;
+	uint32_t profMask = 0xFFFFFFFFu;
 	std::vector<ProfPair> profPending;
 	std::vector<cudaEvent_t> evPool;
 	double profMs[PSM_NUM_KERNEL_CLASSES] = {0};
@@ -116,7 +117,7 @@ struct ProfScope {
 	psm_ctx* c; int cls; cudaEvent_t a = nullptr;
 	ProfScope(psm_ctx* c_, int cls_, int launches) : c(c_), cls(cls_) {
 		c->profLaunches[cls] += launches;
-		if (c->profOn) { a = get_event(c); cudaEventRecord(a, c->stream); }
+		if (c->profOn && ((c->profMask >> cls) & 1u)) { a = get_event(c); cudaEventRecord(a, c->stream); }
 	}
 	~ProfScope() {
 		if (a) { cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream); c->profPending.push_back({a, b, cls}); }
@@ -851,6 +852,12 @@ int psm_profile_enable(psm_ctx* ctx, int on) {
 	if (!ctx) return PSM_E_ARG;
 	prof_resolve(ctx);
 	ctx->profOn = on != 0;
+	return PSM_OK;
+}
+int psm_profile_classes(psm_ctx* ctx, uint32_t class_mask) {
+	if (!ctx) return PSM_E_ARG;
+	prof_resolve(ctx);
+	ctx->profMask = class_mask;
 	return PSM_OK;
 }
 int psm_profile_reset(psm_ctx* ctx) {

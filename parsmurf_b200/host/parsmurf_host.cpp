@@ -662,7 +662,9 @@ int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const 
 		if (devHandle && stream) dev.check(psm_set_stream(dev.ctx, stream));
 		dev.check(psm_profile_reset(dev.ctx));
 		if (batchBudget) dev.check(psm_set_batch_budget(dev.ctx, batchBudget));
-		if (profile) dev.check(psm_profile_enable(dev.ctx, 1));
+		// profile: 0 off, 1 every kernel class, 2 only split search (the kernel the roofline is reported on)
+		dev.check(psm_profile_classes(dev.ctx, profile == 2 ? (1u << 5) : 0xFFFFFFFFu));
+		dev.check(psm_profile_enable(dev.ctx, profile != 0));
 		GlibcRand rng(1);
 		struct Pooled {                                     // label / fold-id copies live in recycled buffers too
 			std::vector<uint32_t> v;
