@@ -34,6 +34,8 @@ WORKLOADS = {
     # BASELINE.json configs[2] (Mendelian scale; fp/ratio/k assumed as configs[1]) and configs[3] (high-dimensional)
     "cfg3": dict(n=14_000_000, m=26, npos=400, nFolds=10, nParts=1000, fp=2, ratio=3, k=5, nTrees=10, mtry=5, seed=1, shift=5),
     "cfg4": dict(n=200_000, m=1000, npos=10_000, nFolds=5, nParts=10, fp=2, ratio=3, k=10, nTrees=10, mtry=31, seed=1, shift=50),
+    # configs[2] at a tenth of the rows: same positives / partition shape / tree sizes, 140k test rows per fold (profiling aid, not a bench line)
+    "cfg3s": dict(n=1_400_000, m=26, npos=400, nFolds=10, nParts=100, fp=2, ratio=3, k=5, nTrees=10, mtry=5, seed=1, shift=5),
     # small smoke-sized variant for quick checks (not a bench line)
     "small": dict(n=50_000, m=26, npos=200, nFolds=5, nParts=10, fp=2, ratio=3, k=5, nTrees=10, mtry=5, seed=1, shift=5),
 }

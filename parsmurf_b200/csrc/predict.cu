@@ -216,15 +216,13 @@ __global__ void __launch_bounds__(256) pack_forest_kernel(const Node16* __restri
 	out[i] = o;
 }
 
-#ifndef PSM_TPS
-#define PSM_TPS 1
-#endif
 #ifndef PSM_NBUF
 #define PSM_NBUF 2
 #endif
-constexpr uint32_t TPS = PSM_TPS;    // trees per pipeline stage
 constexpr uint32_t NBUF = PSM_NBUF;   // pipeline depth: the TMA runs NBUF-1 stages ahead of the traversal (deeper pipelines cost occupancy and measured slower)
 
+// TPS = trees per pipeline stage (PSM_PREDICT_TPS=1|2|4|8 overrides the default of 1, see launch_predict).
+template <uint32_t TPS>
 __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __restrict__ x, uint32_t m, const uint32_t* __restrict__ testIdx,
                                                               uint32_t Nte, const Node16* __restrict__ nodes, const Node8* __restrict__ nodes8,
                                                               uint32_t NC, const TreeState* __restrict__ ts, uint32_t nPartsBatch, uint32_t T,
@@ -293,10 +291,13 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 	__syncthreads();
 	const uint32_t row = r0 + tid;
 	const bool valid = row < Nte;
-	const double* xr = x + (size_t)testIdx[valid ? row : 0] * ld;
 	const double Td = (double)T;
 	const uint32_t tileLane = smem_u32(tile) + (uint32_t)tid * 4u;   // shared address of tile[0][tid]; PT*4 = 1024 bytes per feature
+	const uint32_t tbuf32 = smem_u32(tbuf);
+	const uint32_t treeBytes = maxNodes * (uint32_t)sizeof(Node8);
 	double s0 = 0.0, s1 = 0.0;
+	uint32_t tInPart = 0;                                 // trees of the current partition already summed
+	double* outp = scratch + (size_t)p0 * 2 * Nte + row;  // scratch[(pl*2 + c)*Nte + row] of the current partition
 	for (uint32_t st = 0; st < nStages; st++) {
 		const uint32_t b = st % NBUF;
 		if (tid == 0 && st + NBUF - 1 < nStages) {        // its buffer was released by the barrier that ended stage st-1
@@ -305,44 +306,64 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 		}
 		mbar_wait(&bars[b], (st / NBUF) & 1);
 		if (valid) {
+			const uint32_t nq = min(TPS, nT - st * TPS);
+			uint32_t nbase = tbuf32 + b * TPS * treeBytes;
 #pragma unroll 1
-			for (uint32_t q = 0; q < TPS; q++) {
-				const uint32_t i = st * TPS + q;
-				if (i >= nT) break;
-				// hand-scheduled traversal: 32-bit shared addresses, 12 instructions per node visit
-				const uint32_t nbase = smem_u32(tbuf + ((size_t)b * TPS + q) * maxNodes);
-				const Node16* gtree = nodes + (size_t)(g0 + i) * NC;
-				uint32_t idx8 = 0;                               // node index * sizeof(Node8)
-				uint2 nd;
-				bool undecided = false;                          // some visit had float(value) == float(threshold)
-				while (true) {
-					asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nd.x), "=r"(nd.y) : "r"(nbase + idx8));
-					if ((int)nd.y < 0) break;                    // leaf
-					float v;
-					asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(tileLane + ((nd.y >> 10) & 0x1FFC00u)));   // tile[feature][tid]
-					const float thr = __uint_as_float(nd.x);
-					undecided |= (v == thr);
-					idx8 = ((nd.y & 0xFFFFFu) + ((v < thr) ? 0u : 1u)) << 3;   // Tree.cpp:163: left iff value <= split_value
-				}
-				uint32_t idx = idx8 >> 3;
-				if (undecided) {                                 // about one row-tree in 10^6: redo this tree with the exact fp64 values
-					idx = predict_exact_leaf(xr, gtree);
-					nd.x = __float_as_uint(tbuf[((size_t)b * TPS + q) * maxNodes + idx].thr);
-				}
+			for (uint32_t q = 0; q < nq; q++, nbase += treeBytes) {
+				// Hand-written traversal, 11 instructions per node visit (nvcc's version of the same loop: 17; the kernel is
+				// issue-bound, ncu r01).  Node8: .x = float(threshold) | leaf code, .y = left child (bits 0..19) | feature << 20,
+				// sign bit set on leaves.  Go right iff !(value < threshold) (Tree.cpp:163: left iff value <= split_value; the
+				// float compare only differs from the double one when float(value) == float(threshold), tracked in `und`).
+				// (all working registers are PTX-local and the outputs are written once at the end: an output operand may share
+				// its register with an input, so it must not be written while an input is still needed)
+				uint32_t lx, na, und;
+				asm volatile(
+				    "{\n\t"
+				    ".reg .pred pl, pg, pu;\n\t"
+				    ".reg .b32 nx, ny, a, f, fa, c;\n\t"
+				    ".reg .f32 v, t;\n\t"
+				    "setp.ne.u32 pu, 0, 0;\n\t"
+				    "mov.u32 a, %4;\n\t"
+				    "ld.shared.v2.u32 {nx, ny}, [a];\n\t"
+				    "setp.lt.s32 pl, ny, 0;\n\t"
+				    "@pl bra PSM_WALK_DONE;\n"
+				    "PSM_WALK:\n\t"
+				    "shr.u32 f, ny, 20;\n\t"
+				    "mad.lo.u32 fa, f, 1024, %3;\n\t"
+				    "ld.shared.f32 v, [fa];\n\t"
+				    "and.b32 c, ny, 0xFFFFF;\n\t"
+				    "mad.lo.u32 a, c, 8, %4;\n\t"
+				    "mov.b32 t, nx;\n\t"
+				    "setp.geu.f32 pg, v, t;\n\t"
+				    "setp.eq.or.f32 pu, v, t, pu;\n\t"
+				    "@pg add.u32 a, a, 8;\n\t"
+				    "ld.shared.v2.u32 {nx, ny}, [a];\n\t"
+				    "setp.ge.s32 pl, ny, 0;\n\t"
+				    "@pl bra PSM_WALK;\n"
+				    "PSM_WALK_DONE:\n\t"
+				    "mov.u32 %0, nx;\n\t"
+				    "mov.u32 %1, a;\n\t"
+				    "selp.u32 %2, 1, 0, pu;\n\t"
+				    "}"
+				    : "=r"(lx), "=r"(na), "=r"(und)
+				    : "r"(tileLane), "r"(nbase)
+				    : "memory");
 				double f0, f1;
-				if (nd.x < (uint32_t)LEAF_TAB) { f0 = ltab[0][nd.x]; f1 = ltab[1][nd.x]; }
-				else {
+				if (und | (lx >= (uint32_t)LEAF_TAB)) {                       // rare: exact redo and/or an uncoded leaf
+					const Node16* gtree = nodes + (size_t)(g0 + st * TPS + q) * NC;
+					uint32_t idx = (na - nbase) >> 3;
+					if (und) idx = predict_exact_leaf(x + (size_t)testIdx[row] * ld, gtree);   // about one row-tree in 10^6
 					const uint4 raw = __ldg(reinterpret_cast<const uint4*>(gtree + idx));
 					f0 = __hiloint2double((int)raw.y, (int)raw.x);
 					f1 = __hiloint2double((int)(raw.w & 0x7FFFFFFFu), (int)raw.z);
-				}
+				} else { f0 = ltab[0][lx]; f1 = ltab[1][lx]; }
 				s0 = __dadd_rn(s0, f0);                                      // ForestProbability.cpp:136-141
 				s1 = __dadd_rn(s1, f1);
-				if ((i + 1) % T == 0) {
-					const uint32_t pl = p0 + i / T;
-					scratch[((size_t)pl * 2 + 0) * Nte + row] = __ddiv_rn(s0, Td);   // :145-149
-					scratch[((size_t)pl * 2 + 1) * Nte + row] = __ddiv_rn(s1, Td);
-					s0 = 0.0; s1 = 0.0;
+				if (++tInPart == T) {
+					outp[0] = __ddiv_rn(s0, Td);                             // :145-149
+					outp[Nte] = __ddiv_rn(s1, Td);
+					outp += (size_t)2 * Nte;
+					s0 = 0.0; s1 = 0.0; tInPart = 0;
 				}
 			}
 		}
@@ -374,7 +395,11 @@ int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_
 	{
 		// compact path: fp32 tile + 8-byte nodes (feature < 2047, child id < 2^20)
 		const uint32_t mn = (maxNodes + 1u) & ~1u;
-		const size_t smemC = (size_t)m * PT * sizeof(float) + (size_t)NBUF * TPS * mn * sizeof(Node8) + 128;
+		// trees per stage: 1.  Measured on B200 (predict ms per CV): configs[1] 13.3 (1) / 16.6 (2); configs[2] at a tenth of the
+		// rows 14.6 (1) / 16.6 (2) / 20.3 (4) / 26.2 (8) -- larger stages cost resident CTAs, and occupancy is what this kernel needs.
+		uint32_t tps = 1;
+		if (const char* e = getenv("PSM_PREDICT_TPS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) tps = (uint32_t)v; }
+		const size_t smemC = (size_t)m * PT * sizeof(float) + (size_t)NBUF * tps * mn * sizeof(Node8) + 128;
 		if (nodes8 && maxNodes > 0 && m <= 2047 && NC < (1u << 20) && smemC <= 100 * 1024 && !getenv("PSM_PREDICT_WIDE")) {
 			const uint32_t rowTiles = (Nte + PT - 1) / PT;
 			uint32_t ctasPerSm = (uint32_t)((227 * 1024) / (smemC + 1024));
@@ -386,9 +411,18 @@ int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_
 			if (chunks > nPartsBatch) chunks = nPartsBatch;
 			const uint32_t pch = (nPartsBatch + chunks - 1) / chunks;
 			chunks = (nPartsBatch + pch - 1) / pch;
-			if (cudaFuncSetAttribute(predict_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC) != cudaSuccess) return -1;
-			predict_compact_kernel<<<dim3(rowTiles, chunks), PT, smemC, s>>>(x, m, testIdx, Nte, nodes, reinterpret_cast<const Node8*>(nodes8), NC, ts,
-			                                                                  nPartsBatch, T, pch, mn, scratch);
+			const dim3 grid(rowTiles, chunks);
+			const Node8* n8 = reinterpret_cast<const Node8*>(nodes8);
+#define PSM_LAUNCH_COMPACT(K)                                                                                                              \
+	do {                                                                                                                                   \
+		if (cudaFuncSetAttribute(predict_compact_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC) != cudaSuccess) return -1; \
+		predict_compact_kernel<K><<<grid, PT, smemC, s>>>(x, m, testIdx, Nte, nodes, n8, NC, ts, nPartsBatch, T, pch, mn, scratch);        \
+	} while (0)
+			if (tps == 8) PSM_LAUNCH_COMPACT(8);
+			else if (tps == 4) PSM_LAUNCH_COMPACT(4);
+			else if (tps == 2) PSM_LAUNCH_COMPACT(2);
+			else PSM_LAUNCH_COMPACT(1);
+#undef PSM_LAUNCH_COMPACT
 			return 0;
 		}
 	}
