@@ -10,6 +10,7 @@
 // u64 image of the f64 values, payload = row id, ping-pong buffers in global memory (L2 resident: a segment
 // is Ntr*12 B), stable in-tile ranking with __match_any_sync.  Then a block scan turns "value changed" flags
 // into dense ranks.  Byte work only -- no tensor cores.
+#include <cstdlib>
 #include "kernels.cuh"
 
 namespace psm {
@@ -183,6 +184,136 @@ __global__ void __launch_bounds__(BT, 1) feature_sort_smem_kernel(const double* 
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split variant: a bitonic network needs a power-of-two length, and padding Ntr = 9600 (BASELINE configs[1]) to 16384 wastes
+// 41% of every stage.  Here the segment is cut into run A = the largest power of two <= N and run B = the rest (padded to
+// its own power of two Bp <= A).  Both runs go through the same network -- stages with k <= Bp cover A and B, later ones
+// only A -- and a merge-path pass (A first on ties) fuses the two sorted runs, the dense ranks and the entry write-out.
+// For N = 9600: 10240 slots instead of 16384, 91 stages of 4-5 compare-exchanges per thread instead of 105 of 8.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pow2_floor(uint32_t v) { return v ? 1u << (31 - __clz(v)) : 0u; }
+__device__ __host__ inline uint32_t split_slots(uint32_t N) {
+	if (N == 0) return 0;
+	uint32_t A = 1; while (A * 2 <= N) A *= 2;
+	uint32_t nb = N - A, Bp = 0;
+	if (nb) { Bp = 1; while (Bp < nb) Bp *= 2; }
+	return A + Bp;
+}
+
+template <int CEMAX, int MINB>
+__global__ void __launch_bounds__(BT, MINB) feature_sort_split_kernel(const double* __restrict__ Dall, const PartDesc* __restrict__ parts,
+                                                                       uint32_t m, uint32_t slotsMax, entry_t* __restrict__ Sall) {
+	extern __shared__ __align__(16) unsigned char smraw[];
+	unsigned long long* keys = reinterpret_cast<unsigned long long*>(smraw);                 // [slotsMax]
+	unsigned short* ids = reinterpret_cast<unsigned short*>(smraw + (size_t)slotsMax * 8);    // [slotsMax]
+	__shared__ uint32_t wsum[BT / 32];
+	const uint32_t seg = blockIdx.x;
+	const uint32_t pl = seg / m, f = seg % m;
+	const PartDesc pd = parts[pl];
+	const uint32_t N = pd.Ntr;
+	if (N == 0) return;
+	const double* src = Dall + pd.dOffset + (size_t)f * N;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const uint32_t A = pow2_floor(N), nb = N - A;
+	const uint32_t Bp = nb ? (nb > 1 ? 1u << (32 - __clz(nb - 1)) : 1u) : 0u;
+	const uint32_t slots = A + Bp;                            // run B starts at slot A == source index A
+	for (uint32_t i = tid; i < slots; i += BT) {
+		keys[i] = (i < N) ? f64_key(src[i]) : 0xFFFFFFFFFFFFFFFFull;
+		ids[i] = (unsigned short)i;
+	}
+	__syncthreads();
+	for (uint32_t k = 2; k <= A; k <<= 1) {
+		const uint32_t count = (k <= Bp) ? slots / 2 : A / 2;   // compare-exchanges of this stage
+		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+			unsigned long long a[CEMAX], b[CEMAX];
+			uint32_t lo[CEMAX];
+#pragma unroll
+			for (int q = 0; q < CEMAX; q++) {
+				const uint32_t t = tid + q * BT;
+				lo[q] = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+				if (t < count) { a[q] = keys[lo[q]]; b[q] = keys[lo[q] | j]; }
+			}
+#pragma unroll
+			for (int q = 0; q < CEMAX; q++) {
+				const uint32_t t = tid + q * BT;
+				const bool up = ((lo[q] & k) == 0) | (k == A);   // k == A is the last stage of both runs (Bp == A): both end ascending
+				if (t < count && (a[q] > b[q]) == up && a[q] != b[q]) {
+					const uint32_t hi = lo[q] | j;
+					keys[lo[q]] = b[q]; keys[hi] = a[q];
+					const unsigned short ia = ids[lo[q]]; ids[lo[q]] = ids[hi]; ids[hi] = ia;
+				}
+			}
+			__syncthreads();
+		}
+	}
+	// merge-path: thread t produces outputs [o0, o1) of the merged order; i = elements taken from run A, o - i from run B
+	const unsigned long long* kA = keys;
+	const unsigned long long* kB = keys + A;
+	const uint32_t ipt = (N + BT - 1) / BT;
+	const uint32_t o0 = min(N, (uint32_t)tid * ipt), o1 = min(N, o0 + ipt);
+	uint32_t i0;
+	{
+		uint32_t lo2 = o0 > nb ? o0 - nb : 0u, hi2 = min(o0, A);
+		while (lo2 < hi2) {
+			const uint32_t mid = (lo2 + hi2) >> 1;
+			if (kA[mid] <= kB[o0 - mid - 1]) lo2 = mid + 1; else hi2 = mid;
+		}
+		i0 = lo2;
+	}
+	const uint32_t j0 = o0 - i0;
+	unsigned long long prev0 = 0;                                // key of output o0 - 1 (the larger of the two last-taken keys)
+	if (o0 > 0) {
+		const unsigned long long pa = i0 ? kA[i0 - 1] : 0ull, pb = j0 ? kB[j0 - 1] : 0ull;
+		prev0 = pa > pb ? pa : pb;
+	}
+	// pass 1: number of value changes inside this thread's range
+	uint32_t changes = 0;
+	{
+		uint32_t i = i0, j = j0;
+		unsigned long long prev = prev0;
+		for (uint32_t o = o0; o < o1; o++) {
+			const unsigned long long ka = i < A ? kA[i] : 0xFFFFFFFFFFFFFFFFull, kb = j < nb ? kB[j] : 0xFFFFFFFFFFFFFFFFull;
+			const bool takeA = i < A && (j >= nb || ka <= kb);
+			const unsigned long long key = takeA ? ka : kb;
+			i += takeA ? 1u : 0u; j += takeA ? 0u : 1u;
+			changes += (o > 0 && key != prev) ? 1u : 0u;
+			prev = key;
+		}
+	}
+	uint32_t inc = changes;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+	if (lane == 31) wsum[w] = inc;
+	__syncthreads();
+	uint32_t rank = inc - changes;
+	for (int ww = 0; ww < w; ww++) rank += wsum[ww];
+	// pass 2: the same walk, now writing (row, dense rank)
+	entry_t* S = Sall + pd.sOffset + (size_t)f * N;
+	{
+		uint32_t i = i0, j = j0;
+		unsigned long long prev = prev0;
+		for (uint32_t o = o0; o < o1; o++) {
+			const unsigned long long ka = i < A ? kA[i] : 0xFFFFFFFFFFFFFFFFull, kb = j < nb ? kB[j] : 0xFFFFFFFFFFFFFFFFull;
+			const bool takeA = i < A && (j >= nb || ka <= kb);
+			const unsigned long long key = takeA ? ka : kb;
+			const uint32_t id = takeA ? ids[i] : ids[A + j];
+			i += takeA ? 1u : 0u; j += takeA ? 0u : 1u;
+			rank += (o > 0 && key != prev) ? 1u : 0u;
+			prev = key;
+			S[o] = e_make(id, rank, 0, 0);
+		}
+	}
+}
+
+template <int CEMAX, int MINB>
+static int launch_sort_split(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, uint32_t slotsMax, entry_t* Sall,
+                             cudaStream_t s) {
+	const size_t smem = (size_t)slotsMax * 10;
+	if (cudaFuncSetAttribute(feature_sort_split_kernel<CEMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+	feature_sort_split_kernel<CEMAX, MINB><<<nPartsBatch * m, BT, smem, s>>>(Dall, parts, m, slotsMax, Sall);
+	return 0;
+}
+
 template <uint32_t NPAD>
 static int launch_sort_smem_N(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, entry_t* Sall, cudaStream_t s) {
 	const size_t smem = (size_t)NPAD * 10;
@@ -194,6 +325,18 @@ static int launch_sort_smem_N(const double* Dall, const PartDesc* parts, uint32_
 int launch_feature_sort_smem(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, uint32_t maxNtr, entry_t* Sall,
                              cudaStream_t s) {
 	if (maxNtr > 16384) return 1;   // caller falls back to the global-memory radix sort
+	if (!getenv("PSM_SORT_POW2")) {
+		const uint32_t slotsMax = split_slots(maxNtr);        // monotone in N, so every segment of the batch fits
+		const int ce = (int)((slotsMax / 2 + BT - 1) / BT);
+		const bool two = (size_t)slotsMax * 10 <= 110 * 1024 && !getenv("PSM_SORT_ONE_CTA");   // two CTAs per SM when shared memory allows
+#define PSM_SORT_CASE(C)                                                                                        \
+	case C: return two ? launch_sort_split<C, 2>(Dall, parts, nPartsBatch, m, slotsMax, Sall, s)                \
+	                   : launch_sort_split<C, 1>(Dall, parts, nPartsBatch, m, slotsMax, Sall, s);
+		switch (ce < 1 ? 1 : ce) {
+			PSM_SORT_CASE(1) PSM_SORT_CASE(2) PSM_SORT_CASE(3) PSM_SORT_CASE(4) PSM_SORT_CASE(5) PSM_SORT_CASE(6) PSM_SORT_CASE(7) PSM_SORT_CASE(8)
+		}
+#undef PSM_SORT_CASE
+	}
 	if (maxNtr <= 2048) return launch_sort_smem_N<2048>(Dall, parts, nPartsBatch, m, Sall, s);
 	if (maxNtr <= 4096) return launch_sort_smem_N<4096>(Dall, parts, nPartsBatch, m, Sall, s);
 	if (maxNtr <= 8192) return launch_sort_smem_N<8192>(Dall, parts, nPartsBatch, m, Sall, s);

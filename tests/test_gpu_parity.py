@@ -217,6 +217,52 @@ def test_trees_bit_exact_wide_entries(ctx, oracle, monkeypatch):
             assert ok, "partition %d tree %d: %s" % (p, t, why)
 
 
+# feature-sort edge sizes: the split bitonic network sorts run A = largest power of two <= Ntr and run B = the rest
+# (padded to its own power of two) and merges them; cover Ntr a power of two (no run B), run B of one element, run B padded
+# to the size of run A, and a mid-size segment -- each with and without heavy value ties, plus the padded single network.
+SORT_SIZES = [
+    # (n, npos, nFolds, nParts, fp, ratio, expected Ntr)
+    (400, 20, 5, 2, 1, 1, 64),      # Ntr = 2^6
+    (400, 25, 5, 2, 1, 1, 80),      # A = 64, run B = 16
+    (400, 35, 5, 2, 1, 1, 112),     # A = 64, run B = 48 -> padded to 64 == A
+    (330, 20, 5, 4, 0, 0, None),    # ratio 0: Ntr = P + chunk (odd sizes, last partition shorter)
+    (12000, 310, 5, 3, 2, 3, 2976),  # A = 2048, run B = 928 -> 1024
+]
+
+
+@pytest.mark.parametrize("spec", SORT_SIZES)
+@pytest.mark.parametrize("disc", [False, True])
+def test_trees_bit_exact_over_sort_sizes(ctx, oracle, spec, disc):
+    from helpers import synth, folds_strat
+    n, npos, nF, nParts, fp, ratio, want_ntr = spec
+    X, y = synth(n, 9, npos, 5, shift_feats=3, discretize=disc)
+    case = dict(X=X, y=y, f=folds_strat(y, nF, 3), n=n, m=9, nF=nF, nParts=nParts, fp=fp, ratio=ratio, k=3, T=3, mtry=3)
+    x, fd, seeds = _train_case(ctx, oracle, case)
+    sizes = set()
+    for p in range(nParts):
+        tr, sz = ctx.batch_get_training(p)
+        sizes.add(sz["Ntr"])
+        of = oracle.o_forest_train(np.ascontiguousarray(tr.T), case["T"], case["mtry"], int(seeds[p]))
+        for t in range(case["T"]):
+            ok, why = trees_equal(ctx.batch_export_tree(p, t), of.tree(t))
+            assert ok, "Ntr %d partition %d tree %d: %s" % (sz["Ntr"], p, t, why)
+    if want_ntr is not None:
+        assert sizes == {want_ntr}
+
+
+def test_trees_bit_exact_padded_sort_network(ctx, oracle, monkeypatch):
+    """PSM_SORT_POW2 keeps the single padded bitonic network selectable; it must grow the same trees"""
+    monkeypatch.setenv("PSM_SORT_POW2", "1")
+    case = make_case("fy_26")
+    x, fd, seeds = _train_case(ctx, oracle, case)
+    for p in range(case["nParts"]):
+        tr, sz = ctx.batch_get_training(p)
+        of = oracle.o_forest_train(np.ascontiguousarray(tr.T), case["T"], case["mtry"], int(seeds[p]))
+        for t in range(case["T"]):
+            ok, why = trees_equal(ctx.batch_export_tree(p, t), of.tree(t))
+            assert ok, "partition %d tree %d: %s" % (p, t, why)
+
+
 def test_trees_with_injected_draws(ctx, oracle):
     """reference-exported draws injected instead of the device replay: same trees"""
     case = make_case("fy_26")
