@@ -19,6 +19,7 @@
 //     (ping-pong buffers), which keeps all lists sorted without ever sorting again.
 // Node ids are assigned breadth-first in parent-id order exactly like Tree.cpp:294-302, which is what makes
 // the i-th mtry draw of the device stream belong to node i.
+#include <cstdlib>
 #include "kernels.cuh"
 #include "rng.cuh"
 
@@ -724,61 +725,67 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 #define PSM_PL_CH 3
 #endif
 constexpr int PL_FPW = PSM_PL_FPW;   // features per warp (measured: 1 is best -- more, smaller warps win at every level)
-constexpr int PL_CH = PSM_PL_CH;     // 32-entry chunks in flight per feature (measured at BASELINE configs[1]: 1: 39.7, 2: 30.8, 3: 29.6, 4: 31.4, 8: 44.8 ms per CV)
+constexpr int PL_CH_DEFAULT = PSM_PL_CH;     // 32-entry chunks in flight per feature (measured at BASELINE configs[1]: 1: 39.7, 2: 30.8, 3: 29.6, 4: 31.4, 8: 44.8 ms per CV)
 
-template <typename E>
+template <typename E, int PL_CH>
 __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint32_t nItems, int buf) {
 	const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (item >= nItems) return;
 	const uint4 raw = __ldg(reinterpret_cast<const uint4*>(A.ptask + item));
 	const uint32_t tree = raw.x, start = raw.y, cnt = raw.z, nleft = raw.w;
 	if (cnt == 0) return;                                      // node became a leaf
-	const uint32_t f0 = blockIdx.y * PL_FPW;
-	const int lane = lane_id();
+	const uint32_t f = blockIdx.y;
+	const uint32_t lane = lane_id();
 	const unsigned lt = lanemask_lt();
-	const size_t lo = ((size_t)tree * A.m + f0) * A.stride + start;
-	const E* src = reinterpret_cast<const E*>(A.lists[A.listBuf]) + lo;
-	E* dst = reinterpret_cast<E*>(A.lists[A.listBuf ^ 1]) + lo;
-	const uint32_t* fbits = A.flagBits + (size_t)tree * A.flagWords;   // go-left flags, bit-packed per tree (pack_flags_kernel)
-	const uint32_t nf = min((uint32_t)PL_FPW, A.m - f0);
-	uint32_t offL[PL_FPW], offR[PL_FPW];
+	const size_t lo = ((size_t)tree * A.m + f) * A.stride + start;
+	const E* srcp = reinterpret_cast<const E*>(A.lists[A.listBuf]) + lo + lane;
+	E* dstp = reinterpret_cast<E*>(A.lists[A.listBuf ^ 1]) + lo;
+	const uint32_t* fbits = A.flagBits + (size_t)tree * A.flagWords;   // go-left flags, bit-packed per tree (tree_flags_kernel)
+	// keep both bases in registers: otherwise every store / flag load re-derives its 64-bit address from the kernel arguments
+	asm volatile("" : "+l"(dstp));
+	asm volatile("" : "+l"(fbits));
+	// The kernel is issue-bound (ncu r01: 72% issue-active at 44% of DRAM peak, 53 instructions per 32-entry chunk), so the
+	// loop is written for instruction count: 32-bit indices off two base pointers, one ballot per chunk (the valid lanes of a
+	// chunk are a prefix, so a lane's rank among the right-goers is lane - rank among the left-goers), one store per entry,
+	// and an unpredicated flag load (an invalid lane carries entry 0 -> row 0, a legal address).
+	uint32_t offL = 0, offR = nleft;                           // next free slot of the left / right child segment
+	uint32_t b = 0;
+	// full groups of PL_CH * 32 entries: no bounds logic at all (what the long segments of the first levels run)
+	for (; b + 32 * PL_CH <= cnt; b += 32 * PL_CH, srcp += 32 * PL_CH) {
+		E e[PL_CH];
+		uint32_t w[PL_CH];
 #pragma unroll
-	for (int k = 0; k < PL_FPW; k++) { offL[k] = 0; offR[k] = 0; }
-	for (uint32_t b = 0; b < cnt; b += 32 * PL_CH) {
-		E e[PL_FPW][PL_CH];
-		bool gl[PL_FPW][PL_CH];
-		// fully predicated (no branches): measured faster than skipping the empty chunks of short segments with uniform branches
+		for (int c = 0; c < PL_CH; c++) e[c] = __ldg(srcp + c * 32);
 #pragma unroll
-		for (int k = 0; k < PL_FPW; k++)
+		for (int c = 0; c < PL_CH; c++) w[c] = __ldg(fbits + (Ent<E>::row(e[c]) >> 5));
 #pragma unroll
-			for (int c = 0; c < PL_CH; c++) {
-				const uint32_t i = b + c * 32 + lane;
-				e[k][c] = (i < cnt && (uint32_t)k < nf) ? __ldg(src + (size_t)k * A.stride + i) : (E)0;
-			}
+		for (int c = 0; c < PL_CH; c++) {
+			const bool gl = (w[c] >> (Ent<E>::row(e[c]) & 31u)) & 1u;
+			const unsigned mL = __ballot_sync(0xffffffffu, gl);
+			const uint32_t pL = __popc(mL & lt), nL = __popc(mL);
+			dstp[gl ? offL + pL : offR + lane - pL] = e[c];
+			offL += nL; offR += 32 - nL;
+		}
+	}
+	// the remaining (< PL_CH * 32) entries, fully predicated
+	if (b < cnt) {
+		E e[PL_CH];
+		uint32_t w[PL_CH];
 #pragma unroll
-		for (int k = 0; k < PL_FPW; k++)
+		for (int c = 0; c < PL_CH; c++) e[c] = (b + c * 32 + lane < cnt) ? __ldg(srcp + c * 32) : (E)0;
 #pragma unroll
-			for (int c = 0; c < PL_CH; c++) {
-				const uint32_t i = b + c * 32 + lane;
-				const uint32_t r = Ent<E>::row(e[k][c]);
-				gl[k][c] = (i < cnt && (uint32_t)k < nf) && ((__ldg(fbits + (r >> 5)) >> (r & 31u)) & 1u);
-			}
+		for (int c = 0; c < PL_CH; c++) w[c] = __ldg(fbits + (Ent<E>::row(e[c]) >> 5));
 #pragma unroll
-		for (int k = 0; k < PL_FPW; k++) {
-			if ((uint32_t)k < nf) {
-				E* dL = dst + (size_t)k * A.stride;
-				E* dR = dL + nleft;
-#pragma unroll
-				for (int c = 0; c < PL_CH; c++) {
-					const uint32_t i = b + c * 32 + lane;
-					const bool valid = i < cnt;
-					const unsigned mL = __ballot_sync(0xffffffffu, gl[k][c]);
-					const unsigned mR = __ballot_sync(0xffffffffu, valid && !gl[k][c]);
-					if (gl[k][c]) dL[offL[k] + __popc(mL & lt)] = e[k][c];
-					else if (valid) dR[offR[k] + __popc(mR & lt)] = e[k][c];
-					offL[k] += __popc(mL); offR[k] += __popc(mR);
-				}
-			}
+		for (int c = 0; c < PL_CH; c++) {
+			const uint32_t first = b + c * 32;                 // uniform
+			const bool valid = first + lane < cnt;
+			const bool gl = valid && ((w[c] >> (Ent<E>::row(e[c]) & 31u)) & 1u);
+			const unsigned mL = __ballot_sync(0xffffffffu, gl);
+			const uint32_t pL = __popc(mL & lt), nL = __popc(mL);
+			const uint32_t nv = first < cnt ? min(32u, cnt - first) : 0u;
+			const uint32_t idx = gl ? offL + pL : offR + lane - pL;
+			if (valid) dstp[idx] = e[c];
+			offL += nL; offR += nv - nL;
 		}
 	}
 }
@@ -835,9 +842,16 @@ void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s) {
 void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
 	size_t warps = (size_t)nItems * A.m;
 	(void)warps;
-	const dim3 grid((nItems * 32 + 127) / 128, (A.m + PL_FPW - 1) / PL_FPW);   // x: nodes (one warp each), y: feature group
-	if (A.entry32) partition_lists_kernel<uint32_t><<<grid, 128, 0, s>>>(A, nItems, buf);
-	else partition_lists_kernel<unsigned long long><<<grid, 128, 0, s>>>(A, nItems, buf);
+	const dim3 grid((nItems * 32 + 127) / 128, A.m);   // x: nodes (one warp each), y: feature
+	// long segments (the first levels) keep more chunks in flight per warp; short ones would only pay for the predicated slots
+	static const int longCh = getenv("PSM_PL_LONG_CH") ? atoi(getenv("PSM_PL_LONG_CH")) : 0;
+	const bool longSegs = longCh && (uint64_t)nItems * 512 <= (uint64_t)A.nTrees * A.stride;   // average segment >= ~320 in-bag entries
+	if (A.entry32) {
+		if (longSegs && longCh == 6) partition_lists_kernel<uint32_t, 6><<<grid, 128, 0, s>>>(A, nItems, buf);
+		else if (longSegs && longCh == 8) partition_lists_kernel<uint32_t, 8><<<grid, 128, 0, s>>>(A, nItems, buf);
+		else if (longSegs && longCh == 4) partition_lists_kernel<uint32_t, 4><<<grid, 128, 0, s>>>(A, nItems, buf);
+		else partition_lists_kernel<uint32_t, PL_CH_DEFAULT><<<grid, 128, 0, s>>>(A, nItems, buf);
+	} else partition_lists_kernel<unsigned long long, PL_CH_DEFAULT><<<grid, 128, 0, s>>>(A, nItems, buf);
 }
 
 }  // namespace psm
