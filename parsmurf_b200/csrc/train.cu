@@ -713,19 +713,15 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 }
 
 // ------------------------------------------------------------------------------------------ partition
-// one warp per (split node, feature): stable two-way partition of the node's segment into the other buffer.
-// Latency-bound (entry load -> flag lookup -> store), so four independent 32-entry chunks are in flight per warp.
-// The kernel is bound by its chain of dependent loads (task -> entry -> flag word -> store; ncu r01: long-scoreboard stalls,
-// 64 resident warps per SM all waiting), so each warp serves PL_FPW features of its node with PL_CH chunks each in flight:
-// PL_FPW * PL_CH independent entry loads, then as many independent flag loads, per trip of the chain.  grid.y = feature group.
-#ifndef PSM_PL_FPW
-#define PSM_PL_FPW 1
-#endif
+// one warp per (split node, feature): stable two-way partition of the node's segment into the other buffer; grid.y = feature.
+// Each trip of the chain (entry load -> flag word -> store) carries PL_CH independent 32-entry chunks.  History of the
+// measurements at BASELINE configs[1] (ms per CV): with nvcc's first code (53 instructions per chunk, issue-bound) PL_CH
+// 1: 39.7, 2: 30.8, 3: 29.6, 4: 31.4, 8: 44.8, and serving several features per warp was slower still (more, smaller warps
+// win at every level); after the rewrite for instruction count 3: 25.0, 4: 22.6, 6 on the first levels only: 22.7.
 #ifndef PSM_PL_CH
-#define PSM_PL_CH 3
+#define PSM_PL_CH 4
 #endif
-constexpr int PL_FPW = PSM_PL_FPW;   // features per warp (measured: 1 is best -- more, smaller warps win at every level)
-constexpr int PL_CH_DEFAULT = PSM_PL_CH;     // 32-entry chunks in flight per feature (measured at BASELINE configs[1]: 1: 39.7, 2: 30.8, 3: 29.6, 4: 31.4, 8: 44.8 ms per CV)
+constexpr int PL_CH_DEFAULT = PSM_PL_CH;
 
 template <typename E, int PL_CH>
 __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint32_t nItems, int buf) {
@@ -844,8 +840,9 @@ void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaSt
 	(void)warps;
 	const dim3 grid((nItems * 32 + 127) / 128, A.m);   // x: nodes (one warp each), y: feature
 	// long segments (the first levels) keep more chunks in flight per warp; short ones would only pay for the predicated slots
-	static const int longCh = getenv("PSM_PL_LONG_CH") ? atoi(getenv("PSM_PL_LONG_CH")) : 0;
-	const bool longSegs = longCh && (uint64_t)nItems * 512 <= (uint64_t)A.nTrees * A.stride;   // average segment >= ~320 in-bag entries
+	static const int longCh = getenv("PSM_PL_LONG_CH") ? atoi(getenv("PSM_PL_LONG_CH")) : 0;   // off: one variant serves every level (measured below)
+	static const int longAvg = getenv("PSM_PL_LONG_AVG") ? atoi(getenv("PSM_PL_LONG_AVG")) : 512;
+	const bool longSegs = longCh && (uint64_t)nItems * longAvg <= (uint64_t)A.nTrees * A.stride;   // average segment >= ~0.63 * longAvg in-bag entries
 	if (A.entry32) {
 		if (longSegs && longCh == 6) partition_lists_kernel<uint32_t, 6><<<grid, 128, 0, s>>>(A, nItems, buf);
 		else if (longSegs && longCh == 8) partition_lists_kernel<uint32_t, 8><<<grid, 128, 0, s>>>(A, nItems, buf);
