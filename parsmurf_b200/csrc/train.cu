@@ -350,6 +350,18 @@ template <> struct PkOf<unsigned long long> { typedef unsigned long long type; s
 // G = 16 / 8 pack two / four short segments (<= 64 / <= 32 entries of the aligned grid) into one warp: at deep levels
 // most nodes hold a few dozen rows and the kernel is instruction-issue bound (ncu r01), so the per-warp fixed cost is
 // shared by up to four work items.  Every item is processed by exactly one of the three instantiations.
+// Measured alternatives that did NOT pay at BASELINE configs[1] (split search stays at ~14.1 ms per CV in every case; ncu r01
+// at the mid levels: 585 warp instructions per (node, candidate) for an 89-entry segment -- 108 set-up, ~240 per chunk, ~58
+// per exact evaluation, 53 arg-max --, 65% issue-active with 6 warps per scheduler, a quarter of the stall samples on the
+// work-item -> candidate -> list-entry load chain):
+//   * one warp per node walking its mtry candidates (set-up and arg-max paid once, next candidate prefetched, filter bound
+//     carried across candidates): 25% fewer instructions per node, 15.5-17.6 ms -- the five-fold loss of independent warps
+//     costs more than the instructions saved;
+//   * a single shared exact-evaluation block fed by a per-lane pending mask instead of one block per lane slot: same time
+//     (only the taken blocks ever executed);
+//   * no software pipeline (40 registers, 12 CTAs per SM instead of 8): same time -- what the extra warps hide, the exposed
+//     load of every second chunk gives back;
+//   * sub-warp groups (8 / 16 lanes per segment), 2 or 8 entries per lane, other launch bounds: slower (see above).
 template <typename E, int G>
 __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A, uint32_t nItems, int buf) {
 	// grid.y = candidate index, so no integer division is needed to find the work item
