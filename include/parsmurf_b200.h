@@ -88,6 +88,15 @@ int psm_batch_tree_nodes(psm_ctx* ctx, uint32_t p, uint32_t t, uint64_t* nNodes)
  * split var, split value, frac[2*node+c] (NaN for internal nodes; class 0 = positive). */
 int psm_batch_export_tree(psm_ctx* ctx, uint32_t p, uint32_t t, uint64_t* left, uint64_t* right, uint64_t* var,
                           double* value, double* frac);
+/* ---- (6b) forests that were grown earlier (predict mode, src/hyperSMURF.cpp:401-446): the rfRanger(forestFilename, ...)
+ *      constructor (src/rfRanger.cpp:120-168 -> ForestProbability::loadFromFileInternal, ForestProbability.cpp:275-328).
+ *      Installs the forests of partitions [p0, p1), nTrees each, as the current (trained) batch so that
+ *      psm_batch_predict_accumulate can run on them; no training state is needed, only an open fold.  Trees are given in
+ *      the layouts psm_batch_export_tree produces, concatenated tree after tree: nNodes[(p-p0)*nTrees + t] nodes each,
+ *      frac holding 2 doubles per node.  Children must be consecutive (right == left + 1), as ranger creates them. --- */
+int psm_batch_import_forests(psm_ctx* ctx, uint32_t p0, uint32_t p1, uint32_t nTrees, const uint64_t* nNodes,
+                             const uint64_t* left, const uint64_t* right, const uint64_t* var, const double* value,
+                             const double* frac);
 /* bootstrap multiplicities of tree (p,t): counts[Ntr] (parity check of the device mt19937_64 replay) */
 int psm_batch_get_inbag(psm_ctx* ctx, uint32_t p, uint32_t t, uint32_t* counts);
 

@@ -95,6 +95,8 @@ def ref_lib():
         L.ref_forest_tree_nodes.argtypes = [vp, u32]
         L.ref_forest_export_tree.argtypes = [vp, u32, u64p, u64p, u64p, dp, dp]
         L.ref_forest_predict.argtypes = [vp, dp, u32, dp]
+        L.ref_forest_save.argtypes = [vp, u32, C.c_char_p]
+        L.ref_forest_file_predict.argtypes = [C.c_char_p, dp, u32, u32, u32, u32, u32, u32, dp]
         L.ref_curves.argtypes = [u32p, dp, u64, dp]
         L.ref_cv.restype = C.c_double
         L.ref_cv.argtypes = [dp, u32, u32, u32p, u32p] + [u32] * 10 + [i32, i32, C.c_int, dp, dp]
@@ -286,6 +288,22 @@ def r_forest_predict(forest, test_colmajor):
     test_colmajor = np.ascontiguousarray(test_colmajor, np.float64); ld, Nte = test_colmajor.shape
     preds = np.zeros((Nte, 2))
     ref_lib().ref_forest_predict(forest.h, _p(test_colmajor, dp), Nte, _p(preds, dp))
+    return preds
+
+
+def r_forest_save(forest, part, dirname):
+    """reference rfRanger::saveForest -> <dirname>/<part>.out.forest"""
+    rc = ref_lib().ref_forest_save(forest.h, part, str(dirname).encode())
+    assert rc == 0
+    return "%s/%d.out.forest" % (dirname, part)
+
+
+def r_forest_file_predict(filename, test_colmajor, T, mtry, seed, rfThr=1):
+    """reference predict mode: load a .forest file and predict a column-major test matrix [m+1][Nte]"""
+    test_colmajor = np.ascontiguousarray(test_colmajor, np.float64); ld, Nte = test_colmajor.shape
+    preds = np.zeros((Nte, 2))
+    rc = ref_lib().ref_forest_file_predict(str(filename).encode(), _p(test_colmajor, dp), Nte, ld - 1, T, mtry, seed, rfThr, _p(preds, dp))
+    assert rc == 0
     return preds
 
 

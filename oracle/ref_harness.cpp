@@ -215,6 +215,30 @@ int ref_forest_predict(void* h, const double* colmajor, uint32_t Nte, double* pr
 	return 0;
 }
 
+// rfRanger::saveForest (src/rfRanger.cpp:193-203 -> Forest::saveToFile, src/ranger/Forest/Forest.cpp:390-420):
+// writes <dir>/<part>.out.forest in ranger's binary layout (train mode, src/hyperSMURF.cpp:349-360).
+int ref_forest_save(void* h, uint32_t part, const char* dir) {
+	RefForest* f = (RefForest*)h;
+	CoutSilencer quiet;
+	try { f->rf->saveForest(part, dir); } catch (...) { return -1; }
+	return 0;
+}
+
+// predict mode (src/hyperSMURF.cpp:401-446): rfRanger(forestFilename, ...) loads the saved forest, predict() on a
+// column-major test matrix [m+1][Nte] whose label column is 0.  preds = [Nte][2].
+int ref_forest_file_predict(const char* forestFilename, const double* colmajor, uint32_t Nte, uint32_t m, uint32_t T,
+                            uint32_t mtry, uint32_t seed, uint32_t rfThr, double* preds) {
+	CoutSilencer quiet;
+	std::vector<double> copy(colmajor, colmajor + (size_t)Nte * (m + 1));
+	std::unique_ptr<Data> test(new DataDouble(copy, make_names(m, "dependent"), Nte, m + 1));
+	rfRanger rfTest(std::string(forestFilename), m, true, std::move(test), T, mtry, rfThr, seed);
+	rfTest.predict(false);
+	const auto& p = rfTest.forestPred->getPredictions();
+	if (p.empty() || p[0].size() != Nte) return -1;
+	for (uint32_t i = 0; i < Nte; i++) { preds[2 * i] = p[0][i][0]; preds[2 * i + 1] = p[0][i].size() > 1 ? p[0][i][1] : 0.0; }
+	return 0;
+}
+
 // Curves: AUROC first, then AUPRC (order matters, src/hyperSMURF.cpp:382-384). out = {auroc, auprc}.
 void ref_curves(const uint32_t* labels, const double* preds, uint64_t N, double* out) {
 	std::vector<uint32_t> l(labels, labels + N);

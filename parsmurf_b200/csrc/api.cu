@@ -625,6 +625,56 @@ int psm_batch_export_tree(psm_ctx* ctx, uint32_t p, uint32_t t, uint64_t* left, 
 	return PSM_OK;
 }
 
+int psm_batch_import_forests(psm_ctx* ctx, uint32_t p0, uint32_t p1, uint32_t T, const uint64_t* nNodes, const uint64_t* left,
+                             const uint64_t* right, const uint64_t* var, const double* value, const double* frac) {
+	if (!ctx || !ctx->foldOpen) return fail(ctx, PSM_E_ARG, "import_forests: no open fold");
+	if (p1 <= p0 || T == 0 || !nNodes || !left || !right || !var || !value || !frac) return fail(ctx, PSM_E_ARG, "import_forests: bad arguments");
+	CU(cudaSetDevice(ctx->device));
+	const uint32_t nB = p1 - p0;
+	const uint64_t nTrees64 = (uint64_t)nB * T;
+	if (nTrees64 >= (1ull << 31)) return fail(ctx, PSM_E_LIMIT, "import_forests: too many trees in one batch");
+	const uint32_t nTrees = (uint32_t)nTrees64;
+	uint64_t maxN = 0;
+	for (uint32_t t = 0; t < nTrees; t++) {
+		if (nNodes[t] == 0 || nNodes[t] >= (1ull << 31)) return fail(ctx, PSM_E_ARG, "import_forests: a tree has no nodes or too many");
+		maxN = std::max(maxN, nNodes[t]);
+	}
+	const uint32_t NC = (uint32_t)((maxN + 1) & ~1ull);   // even, like the training layout
+	std::vector<Node16> hn((size_t)nTrees * NC);
+	std::vector<TreeState> hts(nTrees);
+	memset(hn.data(), 0, hn.size() * sizeof(Node16));
+	memset(hts.data(), 0, hts.size() * sizeof(TreeState));
+	size_t o = 0;
+	for (uint32_t t = 0; t < nTrees; t++) {
+		const uint64_t N = nNodes[t];
+		hts[t].nNodes = (uint32_t)N;
+		Node16* out = hn.data() + (size_t)t * NC;
+		for (uint64_t i = 0; i < N; i++, o++) {
+			if (left[o] == 0 && right[o] == 0) {                               // terminal: both children 0 (Tree.cpp:152-156)
+				const double f0 = frac[2 * o], f1 = frac[2 * o + 1];
+				if (!(f0 >= 0.0) || !(f1 >= 0.0)) return fail(ctx, PSM_E_ARG, "import_forests: a terminal node has no class fractions");
+				unsigned long long bits; memcpy(&bits, &f1, 8);
+				out[i].a = f0; out[i].b = bits | 0x8000000000000000ull;
+			} else {
+				if (right[o] != left[o] + 1 || right[o] >= N || left[o] <= i) return fail(ctx, PSM_E_ARG, "import_forests: child ids are not ranger's (consecutive, after the parent)");
+				if (var[o] >= ctx->m) return fail(ctx, PSM_E_ARG, "import_forests: split variable out of range");
+				out[i].a = value[o]; out[i].b = (unsigned long long)var[o] | ((unsigned long long)left[o] << 32);
+			}
+		}
+	}
+	ENSURE(ctx->dNodes, hn.size() * sizeof(Node16));
+	ENSURE(ctx->dNodes8, hn.size() * 8);
+	ENSURE(ctx->dTs, (size_t)nTrees * sizeof(TreeState));
+	CU(cudaMemcpyAsync(ctx->dNodes.p, hn.data(), hn.size() * sizeof(Node16), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemcpyAsync(ctx->dTs.p, hts.data(), (size_t)nTrees * sizeof(TreeState), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));   // hn / hts are locals
+	TrainArgs& A = ctx->A;
+	A.nodes = ctx->dNodes.as<Node16>(); A.ts = ctx->dTs.as<TreeState>(); A.NC = NC; A.nTrees = nTrees; A.T = T;
+	ctx->nB = nB; ctx->p0 = p0; ctx->p1 = p1; ctx->T = T; ctx->maxNodes = (uint32_t)maxN;
+	ctx->batchOpen = false; ctx->assembled = false; ctx->trained = true;
+	return PSM_OK;
+}
+
 int psm_batch_get_inbag(psm_ctx* ctx, uint32_t p, uint32_t t, uint32_t* counts) {
 	if (!ctx || !ctx->trained || p < ctx->p0 || p >= ctx->p1 || t >= ctx->T || !counts) return fail(ctx, PSM_E_ARG, "get_inbag: no such trained tree");
 	const size_t tree = (size_t)(p - ctx->p0) * ctx->T + t;

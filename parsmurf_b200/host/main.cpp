@@ -92,6 +92,11 @@ int main(int argc, char** argv) {
 		smurfer.smurfIt();
 		auto t1 = std::chrono::high_resolution_clock::now();
 		double secs = std::chrono::duration<double>(t1 - t0).count();
+		if (cfg.common.wmode == MODE_TRAIN) {                                // src/parSMURF.cpp:128: only cv / predict write predictions
+			printf("forests saved to %s  (%u partitions, %u examples, %u features, %.3f s)\n", cfg.common.forestDirname.c_str(), cfg.grid[0].nParts, n, m, secs);
+			if (!cfg.common.timeFilename.empty()) { std::ofstream tf(cfg.common.timeFilename.c_str(), std::ios::app); tf << secs << std::endl; }
+			return 0;
+		}
 		printf("AUROC: %.9g - AUPRC: %.9g  (%u examples, %u features, %.3f s)\n", smurfer.auroc, smurfer.auprc, n, m, secs);
 		if (!cfg.common.timeFilename.empty()) { std::ofstream tf(cfg.common.timeFilename.c_str(), std::ios::app); tf << secs << std::endl; }
 		std::ofstream of(cfg.common.outfilename.c_str());                    // src/HyperSMURFUtils.cpp:66-86

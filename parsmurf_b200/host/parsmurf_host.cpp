@@ -323,11 +323,128 @@ std::vector<double> SamplerKNN::trngData(uint32_t p) {
 rfRanger::rfRanger(Device* dev_, uint32_t /*m*/, bool prediction_mode_, const SamplerKNN* samp_, uint32_t numTrees_, uint32_t mtry_, uint32_t rfThrd, uint32_t seedBase)
     : dev(dev_), samp(samp_), mtry(mtry_), rfSeed(seedBase), num_threads(rfThrd), numTrees(numTrees_), prediction_mode(prediction_mode_) {}
 void rfRanger::train(bool) {
+	if (!samp) throw Error(PSM_E_ARG, "rfRanger::train: this forest was loaded from a file");
 	std::vector<uint32_t> seeds(samp->p1 - samp->p0);
 	for (uint32_t p = samp->p0; p < samp->p1; p++) seeds[p - samp->p0] = rfSeed + p;
 	dev->check(psm_batch_train(dev->ctx, numTrees, mtry, seeds.data(), nullptr, nullptr, 0));
 }
-void rfRanger::predict(bool) { dev->check(psm_batch_predict_accumulate(dev->ctx, samp->part->nPart)); }
+void rfRanger::predict(bool) { dev->check(psm_batch_predict_accumulate(dev->ctx, samp ? samp->part->nPart : nPartTotal_)); }
+rfRanger::rfRanger(Device* dev_, const std::string& forestDirname, uint32_t p0, uint32_t p1, uint32_t nPartTotal, uint32_t m, uint32_t numTrees_,
+                   uint32_t mtry_, uint32_t rfThrd, uint32_t seed)
+    : dev(dev_), samp(nullptr), mtry(mtry_), rfSeed(seed), num_threads(rfThrd), numTrees(numTrees_), prediction_mode(true), m_(m), nPartTotal_(nPartTotal) {
+	if (p1 <= p0) throw Error(PSM_E_ARG, "rfRanger: empty partition range");
+	std::vector<uint64_t> nNodes, left, right, var;
+	std::vector<double> value, frac;
+	uint64_t T = 0;
+	for (uint32_t p = p0; p < p1; p++) {
+		const std::string fn = forestDirname + "/" + std::to_string(p) + ".out.forest";   // src/hyperSMURF.cpp:421
+		ForestFile ff = ForestFile::read(fn);
+		// the file knows its own num_trees (Forest::loadFromFile); one batch must be uniform
+		if (p == p0) T = ff.trees.size();
+		else if (ff.trees.size() != T) throw Error(PSM_E_ARG, "rfRanger: " + fn + " holds a different number of trees than the first forest of the batch");
+		if (ff.numVariables != (uint64_t)m + 1 || ff.dependentVarID != m) throw Error(PSM_E_ARG, "rfRanger: " + fn + " was grown on data with a different number of features");
+		if (ff.classValues.size() != 2 || ff.classValues[0] != 1.0 || ff.classValues[1] != 2.0)
+			throw Error(PSM_E_ARG, "rfRanger: " + fn + " does not have class values {1, 2} (positive first)");
+		for (const TreeExport& t : ff.trees) {
+			nNodes.push_back(t.left.size());
+			left.insert(left.end(), t.left.begin(), t.left.end()); right.insert(right.end(), t.right.begin(), t.right.end());
+			var.insert(var.end(), t.splitVarIDs.begin(), t.splitVarIDs.end());
+			value.insert(value.end(), t.splitValues.begin(), t.splitValues.end());
+			frac.insert(frac.end(), t.terminalClassCounts.begin(), t.terminalClassCounts.end());
+		}
+	}
+	if (T == 0) throw Error(PSM_E_ARG, "rfRanger: forest file without trees");
+	numTrees = (uint32_t)T;
+	dev->check(psm_batch_import_forests(dev->ctx, p0, p1, numTrees, nNodes.data(), left.data(), right.data(), var.data(), value.data(), frac.data()));
+}
+void rfRanger::saveForest(uint32_t nPart, const std::string& forestDirname) const {
+	if (!samp) throw Error(PSM_E_ARG, "rfRanger::saveForest: this forest was loaded from a file");
+	ForestFile ff;
+	ff.dependentVarID = samp->m; ff.numVariables = (uint64_t)samp->m + 1;    // label column "Labels" is the last one (src/hyperSMURF.cpp:283-291)
+	ff.classValues = {1.0, 2.0};                                            // first-appearance order: the training matrix starts with the positives
+	for (uint32_t t = 0; t < numTrees; t++) ff.trees.push_back(getTree(nPart, t));
+	ff.write(forestDirname + "/" + std::to_string(nPart) + ".out.forest");   // src/rfRanger.cpp:199
+}
+
+// ------------------------------------------------------------------------------------------ ForestFile
+namespace {
+void put64(std::ofstream& f, uint64_t v) { f.write((const char*)&v, 8); }
+template <typename T> void putVec(std::ofstream& f, const std::vector<T>& v) { put64(f, v.size()); f.write((const char*)v.data(), (std::streamsize)(v.size() * sizeof(T))); }
+uint64_t get64(std::ifstream& f, const std::string& path) {
+	uint64_t v = 0;
+	f.read((char*)&v, 8);
+	if (!f) throw Error(PSM_E_ARG, "forest file truncated: " + path);
+	return v;
+}
+template <typename T> void getVec(std::ifstream& f, std::vector<T>& v, const std::string& path) {
+	const uint64_t len = get64(f, path);
+	if (len > (1ull << 32)) throw Error(PSM_E_ARG, "forest file corrupt (vector length): " + path);
+	v.resize(len);
+	f.read((char*)v.data(), (std::streamsize)(len * sizeof(T)));
+	if (!f) throw Error(PSM_E_ARG, "forest file truncated: " + path);
+}
+}  // namespace
+void ForestFile::write(const std::string& path) const {
+	std::ofstream f(path.c_str(), std::ios::binary);
+	if (!f.good()) throw Error(PSM_E_ARG, "Could not write to output file: " + path + ".");   // Forest.cpp:396-398
+	put64(f, dependentVarID);
+	put64(f, trees.size());
+	put64(f, numVariables);                                                  // is_ordered_variable: one byte per column, all ordered
+	for (uint64_t i = 0; i < numVariables; i++) { const char one = 1; f.write(&one, 1); }
+	put64(f, numVariables);                                                  // ForestProbability::saveToFileInternal
+	const uint32_t treetype = 9;                                             // TREE_PROBABILITY (src/ranger/globals.h)
+	f.write((const char*)&treetype, 4);
+	putVec(f, classValues);
+	for (const rfRanger::TreeExport& t : trees) {
+		put64(f, 2);                                                         // child_nodeIDs: [left[], right[]]
+		putVec(f, t.left); putVec(f, t.right);
+		putVec(f, t.splitVarIDs);
+		putVec(f, t.splitValues);
+		std::vector<uint64_t> terminal;                                     // TreeProbability::appendToFileInternal
+		for (uint64_t i = 0; i < t.left.size(); i++) if (t.left[i] == 0 && t.right[i] == 0) terminal.push_back(i);
+		putVec(f, terminal);
+		put64(f, terminal.size());
+		for (uint64_t i : terminal) { put64(f, 2); f.write((const char*)&t.terminalClassCounts[2 * i], 16); }
+	}
+	if (!f.good()) throw Error(PSM_E_ARG, "write error on " + path);
+}
+ForestFile ForestFile::read(const std::string& path) {
+	std::ifstream f(path.c_str(), std::ios::binary);
+	if (!f.good()) throw Error(PSM_E_ARG, "Could not read from input file: " + path + ".");   // Forest.cpp loadFromFile
+	ForestFile ff;
+	ff.dependentVarID = get64(f, path);
+	const uint64_t nTrees = get64(f, path);
+	const uint64_t nOrdered = get64(f, path);
+	if (nTrees > (1ull << 24) || nOrdered > (1ull << 24)) throw Error(PSM_E_ARG, "forest file corrupt (header): " + path);
+	f.ignore((std::streamsize)nOrdered);
+	ff.numVariables = get64(f, path);
+	uint32_t treetype = 0;
+	f.read((char*)&treetype, 4);
+	if (!f || treetype != 9) throw Error(PSM_E_ARG, "Wrong treetype. Loaded file is not a probability estimation forest.");   // ForestProbability.cpp:284-286
+	getVec(f, ff.classValues, path);
+	ff.trees.resize(nTrees);
+	for (rfRanger::TreeExport& t : ff.trees) {
+		if (get64(f, path) != 2) throw Error(PSM_E_ARG, "forest file corrupt (child_nodeIDs): " + path);
+		getVec(f, t.left, path); getVec(f, t.right, path);
+		getVec(f, t.splitVarIDs, path);
+		getVec(f, t.splitValues, path);
+		const size_t N = t.left.size();
+		if (t.right.size() != N || t.splitVarIDs.size() != N || t.splitValues.size() != N) throw Error(PSM_E_ARG, "forest file corrupt (tree vectors): " + path);
+		std::vector<uint64_t> terminal;
+		getVec(f, terminal, path);
+		if (get64(f, path) != terminal.size()) throw Error(PSM_E_ARG, "forest file corrupt (terminal nodes): " + path);
+		t.terminalClassCounts.assign(2 * N, std::nan(""));
+		for (uint64_t id : terminal) {
+			std::vector<double> c;
+			getVec(f, c, path);
+			if (id >= N || c.empty() || c.size() > 2) throw Error(PSM_E_ARG, "forest file corrupt (class counts): " + path);
+			t.terminalClassCounts[2 * id] = c[0];
+			t.terminalClassCounts[2 * id + 1] = c.size() > 1 ? c[1] : 0.0;
+		}
+	}
+	return ff;
+}
+
 rfRanger::TreeExport rfRanger::getTree(uint32_t p, uint32_t t) const {
 	uint64_t nn = 0;
 	dev->check(psm_batch_tree_nodes(dev->ctx, p, t, &nn));
@@ -380,7 +497,9 @@ void hyperSMURF::setGridParams(uint32_t idx) {                              // s
 void hyperSMURF::createPart() { part.reset(new Partition(foldManager, ttd.get(), nPart, fp, ratio, mm, nn)); }
 
 void hyperSMURF::smurfIt() {                                                // src/hyperSMURF.cpp:151-496 (CV paths)
-	if (wmode != MODE_CV) throw Error(PSM_E_ARG, "hyperSMURF::smurfIt: only mode \"cv\" is implemented on the GPU path");
+	if (wmode == MODE_PREDICT) { predictIt(); return; }                     // :401-446
+	if (wmode != MODE_CV && wmode != MODE_TRAIN) throw Error(PSM_E_ARG, "hyperSMURF::smurfIt: unknown mode");
+	if (wmode == MODE_TRAIN && commonParams->forestDirname.empty()) throw Error(PSM_E_ARG, "mode \"train\" needs data.forestDir");
 	uint32_t startingFold = 0, endingFold = nFolds;
 	if (!inInternalCV && commonParams->minFold != (uint32_t)-1) startingFold = commonParams->minFold;
 	if (!inInternalCV && commonParams->maxFold != (uint32_t)-1) endingFold = commonParams->maxFold;
@@ -448,12 +567,17 @@ void hyperSMURF::smurfIt() {                                                // s
 			samp.sample();                                                  // :277
 			rfRanger rf(dev, mm, false, &samp, numTrees, mtry, commonParams->rfThr, seed + currentFold * nPart);   // :273,302
 			{ PhaseScope ps(PH_TRAIN); rf.train(commonParams->rfVerbose); }   // :303
+			if (wmode == MODE_TRAIN) {                                      // :349-360 training only: one forest file per partition
+				for (uint32_t p = b0; p < b1; p++) rf.saveForest(p, commonParams->forestDirname);
+				continue;
+			}
 			samp.copyTestSet();                                             // :316
 			rfRanger rfTest(dev, mm, true, &samp, numTrees, mtry, commonParams->rfThr, 2 * (seed + currentFold * nPart));   // :330
 			{ PhaseScope ps(PH_PREDICT); rfTest.predict(commonParams->rfVerbose); dev->check(psm_sync(dev->ctx)); }   // :331
 			samp.accumulateAndDivideResInProbVect(nPart);                   // :344-346 (done on the device by predict)
 		}
 		{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * (nPart - last)); }
+		if (wmode == MODE_TRAIN) continue;                                   // nothing was predicted
 		if (world > 1 && reduce) {
 			PhaseScope ps(PH_REDUCE);                                          // src/hyperSMURF_MPI.cpp:594-618
 			double* ptr = nullptr; uint32_t nte = 0;
@@ -479,6 +603,7 @@ void hyperSMURF::smurfIt() {                                                // s
 		}
 	}
 
+	if (wmode == MODE_TRAIN) return;
 	{ PhaseScope ps(PH_SCATTER); dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob)); }
 	if (inInternalCV) {                                                     // :456-482
 		std::vector<uint32_t> tl; std::vector<double> tp;
@@ -499,6 +624,42 @@ void hyperSMURF::smurfIt() {                                                // s
 		auprc = r2[1];
 		if (verboseLevel > VERBSILENT && rank == 0) std::cout << "AUROC: " << auroc << " - AUPRC: " << auprc << std::endl;
 	}
+}
+
+// predict mode (src/hyperSMURF.cpp:401-446): every example is a test row of fold 0; partition p is predicted by the forest
+// saved as <forestDir>/<p>.out.forest and the ensemble average is accumulated exactly as in the CV path.
+void hyperSMURF::predictIt() {
+	if (commonParams->forestDirname.empty()) throw Error(PSM_E_ARG, "mode \"predict\" needs data.forestDir");
+	dev->check(psm_labels_upload(dev->ctx, y.data(), nn));
+	dev->check(psm_scores_reset(dev->ctx));
+	{ PhaseScope ps(PH_FOLDS_TTD); part->setFold(0); }
+	dev->invalidateFold();
+	{ PhaseScope ps(PH_FOLD_BEGIN); dev->ensureFold(part.get()); }
+	uint32_t cnt = nPart / world + ((nPart % world) > rank ? 1 : 0);
+	uint32_t first = 0;
+	for (uint32_t r2 = 0; r2 < rank; r2++) first += nPart / world + ((nPart % world) > r2 ? 1 : 0);
+	const uint32_t last = first + cnt;
+	// one batch = as many forests as keep the per-(partition, row) score planes within ~4 GiB
+	const uint64_t nte = (uint64_t)part->testPosNum + part->testNegNum;
+	const uint32_t cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(256, (4ull << 30) / std::max<uint64_t>(1, 16 * nte)));
+	for (uint32_t b0 = first; b0 < last; b0 += cap) {
+		const uint32_t b1 = std::min(last, b0 + cap);
+		rfRanger rfTest(dev, commonParams->forestDirname, b0, b1, nPart, mm, numTrees, mtry, commonParams->rfThr, seed + b0);   // :421-425
+		{ PhaseScope ps(PH_PREDICT); rfTest.predict(commonParams->rfVerbose); dev->check(psm_sync(dev->ctx)); }
+	}
+	if (world > 1 && reduce) {
+		PhaseScope ps(PH_REDUCE);
+		double* ptr = nullptr; uint32_t nte2 = 0;
+		dev->check(psm_fold_scores_devptr(dev->ctx, &ptr, &nte2));
+		dev->check(psm_sync(dev->ctx));
+		reduce(ptr, 2ull * nte2);
+	}
+	{ PhaseScope ps(PH_SCATTER); dev->check(psm_fold_scatter_device(dev->ctx)); dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob)); }
+	PhaseScope ps(PH_CURVES);                                                // :484-488
+	double r2[2];
+	dev->check(psm_scores_curves(dev->ctx, curvesTieMode, r2));
+	auroc = r2[0]; auprc = r2[1];
+	if (verboseLevel > VERBSILENT && rank == 0) std::cout << "AUROC: " << auroc << " - AUPRC: " << auprc << std::endl;
 }
 
 // ------------------------------------------------------------------------------------------ JSON config
@@ -647,7 +808,8 @@ typedef int (*psmh_reduce_fn)(void* user, double* dev_ptr, uint64_t count);
 // Whole CV through the host classes, like parSMURF1's main (src/parSMURF.cpp:97-106) with data already in memory.
 // foldAssign == NULL -> random stratified folds (src/folds.cpp:27-77).  metrics = {auroc, auprc}; foldMetrics [nFolds][2] or NULL.
 // x_is_device != 0: `x` is a device pointer (dataset already resident in HBM).
-int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+static int run_mode(int mode, const char* forestDir, const double* x, int x_is_device, uint32_t n, uint32_t m, const uint32_t* labels,
+                    const uint32_t* foldAssign, uint32_t nFolds,
                 uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed, int device, void* stream,
                 int tieMode, int evalFoldCurves, uint32_t rank, uint32_t world, psmh_reduce_fn reduce, void* reduceUser, uint64_t batchBudget,
                 int profile, double* class1, double* class2, double* metrics, double* foldMetrics, double* kernelMs, uint64_t* kernelLaunches,
@@ -675,7 +837,8 @@ int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const 
 		Folds folds(nFolds, n, y.data(), ff, foldAssign == nullptr, &rng);
 		{ PhaseScope ps(PH_FOLDS_TTD); folds.computeFolds(); }
 		CommonParams cp;
-		cp.nn = n; cp.mm = m; cp.nFolds = nFolds; cp.seed = seed; cp.wmode = MODE_CV; cp.woptimiz = OPT_NO;
+		cp.nn = n; cp.mm = m; cp.nFolds = nFolds; cp.seed = seed; cp.wmode = (uint8_t)mode; cp.woptimiz = OPT_NO;
+		if (forestDir) cp.forestDirname = forestDir;
 		std::vector<GridParams> gp(1);
 		gp[0] = GridParams{nParts, fp, ratio, k, nTrees, mtry, 0, 0};
 		hyperSMURF smurfer(&cp, gp, &folds, &dev, y, class1, class2, &rng);
@@ -687,7 +850,7 @@ int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const 
 		g_phase[PH_SETUP] += now_s() - tSetup;
 		smurfer.smurfIt();
 		if (metrics) { metrics[0] = smurfer.auroc; metrics[1] = smurfer.auprc; }
-		if (foldMetrics) for (uint32_t f = 0; f < nFolds; f++) { foldMetrics[2 * f] = smurfer.foldAuroc[f]; foldMetrics[2 * f + 1] = smurfer.foldAuprc[f]; }
+		if (foldMetrics && mode == MODE_CV) for (uint32_t f = 0; f < nFolds; f++) { foldMetrics[2 * f] = smurfer.foldAuroc[f]; foldMetrics[2 * f + 1] = smurfer.foldAuprc[f]; }
 		if (kernelMs || kernelLaunches) dev.check(psm_profile_get(dev.ctx, kernelMs, kernelLaunches));
 		if (stats3) dev.check(psm_stats_get(dev.ctx, &stats3[0], &stats3[1], &stats3[2]));
 		if (phases) for (int i = 0; i < PH_COUNT; i++) phases[i] = g_phase[i];
@@ -703,6 +866,27 @@ int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const 
 
 // Grid search through the host classes (cfgEx/gridTune.json: exec.optimizer = "grid").  grid = [G][6] {nParts, fp, ratio, k, nTrees,
 // mtry}; gridMetrics [G][2] = {auroc, auprc} of the inner CVs of the last outer fold.  fold<k>.dat files are appended in the CWD.
+int psmh_cv_run(const double* x, int x_is_device, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+                uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed, int device, void* stream,
+                int tieMode, int evalFoldCurves, uint32_t rank, uint32_t world, psmh_reduce_fn reduce, void* reduceUser, uint64_t batchBudget,
+                int profile, double* class1, double* class2, double* metrics, double* foldMetrics, double* kernelMs, uint64_t* kernelLaunches,
+                uint64_t* stats3, double* phases, void* devHandle, char* errbuf, size_t errlen) {
+	return run_mode(parsmurf::MODE_CV, nullptr, x, x_is_device, n, m, labels, foldAssign, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, device, stream,
+	                tieMode, evalFoldCurves, rank, world, reduce, reduceUser, batchBudget, profile, class1, class2, metrics, foldMetrics, kernelMs,
+	                kernelLaunches, stats3, phases, devHandle, errbuf, errlen);
+}
+
+// exec.mode "train" (mode 2: grow one forest per partition on all the data and save it to forestDir) and "predict"
+// (mode 4: score every example with the saved forests); one fold, as ArgHandler_new.cpp forces for these modes.
+int psmh_mode_run(int mode, const char* forestDir, const double* x, uint32_t n, uint32_t m, const uint32_t* labels, uint32_t nParts, uint32_t fp,
+                  uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed, int device, int tieMode, uint32_t rank, uint32_t world,
+                  psmh_reduce_fn reduce, void* reduceUser, double* class1, double* class2, double* metrics, char* errbuf, size_t errlen) {
+	if (mode != parsmurf::MODE_TRAIN && mode != parsmurf::MODE_PREDICT) return PSM_E_ARG;
+	std::vector<uint32_t> ff(n, 0);                                          // a single fold holding every example
+	return run_mode(mode, forestDir, x, 0, n, m, labels, ff.data(), 1, nParts, fp, ratio, k, nTrees, mtry, seed, device, nullptr, tieMode, 0, rank, world,
+	                reduce, reduceUser, 0, 0, class1, class2, metrics, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, errbuf, errlen);
+}
+
 int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
                      const uint32_t* grid, uint32_t G, uint32_t seed, int device, int tieMode, double* class1, double* class2, double* metrics,
                      double* gridMetrics, char* errbuf, size_t errlen) {
@@ -740,6 +924,20 @@ int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* la
 }
 
 // a persistent GPU context (device buffers are reused across psmh_cv_run calls)
+// ForestFile::read followed by ForestFile::write (no GPU involved): lets the tests check the reader and the writer against a
+// forest file written by the reference itself.
+int psmh_forest_file_rewrite(const char* inPath, const char* outPath, uint64_t* nTreesOut, char* errbuf, size_t errlen) {
+	try {
+		parsmurf::ForestFile ff = parsmurf::ForestFile::read(inPath);
+		if (nTreesOut) *nTreesOut = ff.trees.size();
+		ff.write(outPath);
+		return 0;
+	} catch (const std::exception& e) {
+		if (errbuf && errlen) { strncpy(errbuf, e.what(), errlen - 1); errbuf[errlen - 1] = 0; }
+		return -1;
+	}
+}
+
 void* psmh_device_create(int device, void* stream) {
 	try { return new parsmurf::Device(device, stream); } catch (...) { return nullptr; }
 }

@@ -180,15 +180,37 @@ private:
 class rfRanger {
 public:
 	rfRanger(Device* dev, uint32_t m, bool prediction_mode, const SamplerKNN* samp, uint32_t numTrees, uint32_t mtry, uint32_t rfThrd, uint32_t seedBase);
+	// predict mode (src/rfRanger.cpp:120-168): the forests of partitions [p0, p1) are read from <forestDirname>/<p>.out.forest
+	// and installed on the device; predict() then accumulates pred * (1/nPartTotal) like the in-memory constructor
+	rfRanger(Device* dev, const std::string& forestDirname, uint32_t p0, uint32_t p1, uint32_t nPartTotal, uint32_t m, uint32_t numTrees,
+	         uint32_t mtry, uint32_t rfThrd, uint32_t seed);
 	void train(bool verbose);     // forest seed of partition p = seedBase + p  (seedBase = seed + fold*nPart, src/hyperSMURF.cpp:273)
 	void predict(bool verbose);   // predict the fold's test rows and accumulate pred * (1/nPart) into the fold score buffer
 	// ranger getter layouts (src/ranger/Forest/Forest.h:82-101, ForestProbability.h:40-44)
 	struct TreeExport { std::vector<uint64_t> left, right, splitVarIDs; std::vector<double> splitValues, terminalClassCounts; };
 	TreeExport getTree(uint32_t p, uint32_t t) const;
+	// train mode (src/rfRanger.cpp:193-203): writes <forestDirname>/<nPart>.out.forest in ranger's binary forest layout,
+	// byte for byte what Forest::saveToFile produces for the same forest.  (saveImportance has no counterpart: permutation
+	// importance is not computed on the GPU path)
+	void saveForest(uint32_t nPart, const std::string& forestDirname) const;
 	Device* const dev;
 	const SamplerKNN* const samp;
 	uint32_t mtry, rfSeed, min_node_size = 10, num_threads, numTrees;
 	bool prediction_mode;
+private:
+	uint32_t m_ = 0, nPartTotal_ = 0;
+};
+
+// ranger's binary forest file for a probability forest (src/ranger/Forest/Forest.cpp:390-420, ForestProbability.cpp:262-328,
+// Tree.cpp:234-243, TreeProbability.cpp:65-79, utility.h:58-140): dependent_varID, num_trees, is_ordered_variable,
+// num_variables, treetype 9, class_values, then per tree child_nodeIDs[2], split_varIDs, split_values, terminal node ids and
+// their class fractions.  All integers are 64-bit little endian, vectors are length-prefixed.
+struct ForestFile {
+	uint64_t dependentVarID = 0, numVariables = 0;
+	std::vector<double> classValues;
+	std::vector<rfRanger::TreeExport> trees;
+	void write(const std::string& path) const;
+	static ForestFile read(const std::string& path);
 };
 
 // reference src/curves.h:12-21
@@ -217,7 +239,7 @@ public:
 	void initInternalCV(uint32_t foldToJump);
 	void setGridParams(uint32_t idx);
 	void createPart();
-	void smurfIt();
+	void smurfIt();     // modes "cv" and "train" (src/hyperSMURF.cpp:151-396); mode "predict" -> predictIt (:401-446)
 
 	// multi-GPU: this rank handles partitions [rank*.., ..) of every fold (src/MPIHelper.cpp:29-37) and `reduce`
 	// sums the fold score buffer [2*Nte] f64 across ranks in place (the MPI_Gather + master sum of
@@ -229,6 +251,7 @@ public:
 	double auroc = 0, auprc = 0;
 
 private:
+	void predictIt();
 	const CommonParams* const commonParams;
 	std::vector<GridParams>& gridParams;
 	Folds* const foldManager;

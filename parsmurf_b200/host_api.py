@@ -83,6 +83,52 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
                 host_phases_s={k_: float(ph[i]) for i, k_ in enumerate(PHASES)})
 
 
+def _mode_run(mode, forest_dir, x, labels, nParts, fp, ratio, k, nTrees, mtry, seed, device, tie_mode, rank, world, reduce):
+    L = hlib()
+    L.psmh_mode_run.argtypes = [C.c_int, C.c_char_p, vp, u32, u32, u32p] + [u32] * 7 + [C.c_int, C.c_int, u32, u32, REDUCE_FN, vp, dp, dp, dp, C.c_char_p, C.c_size_t]
+    assert x.dtype == np.float64 and x.flags.c_contiguous
+    n, m = x.shape[0], x.shape[1] - 1
+    labels = np.ascontiguousarray(labels, np.uint32)
+    c1 = np.zeros(n); c2 = np.zeros(n); met = np.zeros(2)
+    err = C.create_string_buffer(512)
+
+    def _cb(user, ptr, count):
+        try:
+            reduce(ptr, count)
+            return 0
+        except Exception as e:   # never unwind through C
+            print("reduce callback failed:", e)
+            return 1
+    cb = REDUCE_FN(_cb) if reduce is not None else REDUCE_FN()
+    rc = L.psmh_mode_run(mode, str(forest_dir).encode(), vp(x.ctypes.data), n, m, _p(labels, u32p), nParts, fp, ratio, k, nTrees, mtry, seed, device,
+                         tie_mode, rank, world, cb, None, _p(c1, dp), _p(c2, dp), _p(met, dp), err, 512)
+    if rc != 0:
+        raise PsmError(rc, err.value.decode())
+    return dict(class1=c1, class2=c2, auroc=float(met[0]), auprc=float(met[1]))
+
+
+def train_run(x, labels, forest_dir, nParts, fp, ratio, k, nTrees, mtry, seed, device=0, rank=0, world=1):
+    """exec.mode "train" (src/hyperSMURF.cpp:349-360): one forest per partition grown on all the data, written as
+    <forest_dir>/<p>.out.forest in ranger's binary forest layout.  With world > 1 every rank writes its own partitions."""
+    _mode_run(2, forest_dir, x, labels, nParts, fp, ratio, k, nTrees, mtry, seed, device, 0, rank, world, None)
+
+
+def predict_run(x, labels, forest_dir, nParts, nTrees, mtry, seed, device=0, tie_mode=0, rank=0, world=1, reduce=None):
+    """exec.mode "predict" (src/hyperSMURF.cpp:401-446): score every example with the forests saved in forest_dir."""
+    return _mode_run(4, forest_dir, x, labels, nParts, 0, 0, 0, nTrees, mtry, seed, device, tie_mode, rank, world, reduce)
+
+
+def forest_file_rewrite(in_path, out_path):
+    """read a ranger .forest file with the host library's reader and write it back with its writer; returns the tree count"""
+    L = hlib()
+    L.psmh_forest_file_rewrite.argtypes = [C.c_char_p, C.c_char_p, u64p, C.c_char_p, C.c_size_t]
+    nt = np.zeros(1, np.uint64); err = C.create_string_buffer(512)
+    rc = L.psmh_forest_file_rewrite(str(in_path).encode(), str(out_path).encode(), _p(nt, u64p), err, 512)
+    if rc != 0:
+        raise PsmError(rc, err.value.decode())
+    return int(nt[0])
+
+
 def cv_grid_run(x, labels, folds, nFolds, grid, seed, device=0, tie_mode=0):
     """Grid search like cfgEx/gridTune.json (exec.optimizer "grid"): grid = list of (nParts, fp, ratio, k, nTrees, mtry).
     Appends fold<k>.dat files to a scratch directory.  Returns dict(class1, class2, auroc, auprc, grid_metrics)."""

@@ -58,3 +58,35 @@ def test_cli_cv_matches_host_api(tmp_path):
     assert pred.shape == (case["n"], 3)
     assert np.allclose(pred[:, 0], c1, rtol=1e-5, atol=1e-12) and np.array_equal(pred[:, 2].astype(int), case["y"].astype(int))
     assert os.path.exists(tmp_path / "time.txt")
+
+
+@pytest.mark.gpu
+def test_cli_train_then_predict_modes(tmp_path):
+    """exec.mode "train" writes one ranger forest file per partition into data.forestDir; exec.mode "predict" scores every
+    example with them -- the same numbers as the host API's predict mode"""
+    from oracle import pyoracle as O
+    from parsmurf_b200 import host_api as H
+    case = make_case("fy_26")
+    cfg_path = _write_case(tmp_path, case, "cli_modes")
+    cfg = json.loads(open(cfg_path).read())
+    fdir = tmp_path / "forests"
+    fdir.mkdir()
+    cfg["data"]["forestDir"] = str(fdir)
+    del cfg["data"]["foldFile"]                               # train / predict use one fold holding every example
+    for mode in ("train", "predict"):
+        cfg["exec"]["mode"] = mode
+        (tmp_path / ("cfg_%s.json" % mode)).write_text(json.dumps(cfg, indent=1))
+    r = subprocess.run([BIN, "--cfg", str(tmp_path / "cfg_train.json")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "forests saved" in r.stdout and not os.path.exists(tmp_path / "predictions.txt")
+    assert sorted(os.listdir(fdir)) == ["%d.out.forest" % p for p in range(case["nParts"])]
+    r = subprocess.run([BIN, "--cfg", str(tmp_path / "cfg_predict.json")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    mt = re.search(r"AUROC: ([0-9.eE+-]+) - AUPRC: ([0-9.eE+-]+)", r.stdout)
+    assert mt, r.stdout
+    x = O.make_x(case["X"], case["y"])
+    out = H.predict_run(x, case["y"], fdir, case["nParts"], case["T"], case["mtry"], 7)
+    assert abs(float(mt.group(1)) - out["auroc"]) < 1e-8 and abs(float(mt.group(2)) - out["auprc"]) < 1e-8
+    pred = np.loadtxt(tmp_path / "predictions.txt")
+    assert np.allclose(pred[:, 0], out["class1"], rtol=1e-5, atol=1e-12)
+    assert out["auroc"] > 0.9                                  # resubstitution: the forests have seen these rows
