@@ -65,6 +65,7 @@ struct psm_ctx {
 	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dNodes8, dSplitFeat, dFlagBits, dItems0, dItems1, dCand, dRes, dDec, dPtask, dCounters, dStats, dSeeds,
 	    dInjBoot, dInjBootOff, dInjCand;
 	uint32_t* hCounters = nullptr;   // pinned
+	cudaEvent_t evLevel = nullptr;
 	void* hStage = nullptr;          // pinned D2H staging
 	size_t hStageCap = 0;
 	uint64_t statSplitBytes = 0, statNodes = 0, statLevels = 0;
@@ -189,6 +190,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	for (auto& p : ctx->profPending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
 	for (auto e : ctx->evPool) cudaEventDestroy(e);
 	if (ctx->hCounters) cudaFreeHost(ctx->hCounters);
+	if (ctx->evLevel) cudaEventDestroy(ctx->evLevel);
 	if (ctx->hStage) cudaFreeHost(ctx->hStage);
 	delete ctx;
 	return PSM_OK;
@@ -523,9 +525,14 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 
 	int buf = 0;
 	uint64_t levels = 0;
+	// The next level's item count is read back right after level_finalize and BEFORE the list partition is queued, and the
+	// host waits on an event instead of the stream: the round trip (copy, wake-up, five launches) overlaps the partition
+	// kernel of the level that is still running instead of leaving the GPU idle between levels.
+	if (!ctx->evLevel) CU(cudaEventCreateWithFlags(&ctx->evLevel, cudaEventDisableTiming));
+	CU(cudaMemcpyAsync(ctx->hCounters, A.counters, CNT_COUNT * 4, cudaMemcpyDeviceToHost, s));
+	CU(cudaEventRecord(ctx->evLevel, s));
 	while (true) {
-		CU(cudaMemcpyAsync(ctx->hCounters, A.counters, CNT_COUNT * 4, cudaMemcpyDeviceToHost, s));
-		CU(cudaStreamSynchronize(s));
+		CU(cudaEventSynchronize(ctx->evLevel));
 		const uint32_t nItems = ctx->hCounters[CNT_NEXT_ITEMS];
 		const uint32_t e = ctx->hCounters[CNT_ERROR];
 		if (e & ERR_COUNT_LIMIT) return fail(ctx, PSM_E_LIMIT, "batch_train: a bootstrap multiplicity exceeds 32767");
@@ -548,6 +555,8 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		if (trace) cudaEventRecord(tev[2], s);
 		{ ProfScope ps(ctx, K_FINALIZE, 1); launch_level_finalize(A, buf, s); }
 		if (trace) cudaEventRecord(tev[3], s);
+		CU(cudaMemcpyAsync(ctx->hCounters, A.counters, CNT_COUNT * 4, cudaMemcpyDeviceToHost, s));   // nItems of the next level
+		CU(cudaEventRecord(ctx->evLevel, s));
 		{ ProfScope ps(ctx, K_PARTITION, 1); launch_partition_lists(A, nItems, buf, s); }
 		if (trace) {
 			cudaEventRecord(tev[4], s);
