@@ -108,6 +108,25 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(launches_per_step):
+    """DRAM bytes per split-search launch from the committed ncu capture of the same command (profiles/<tag>_summary.json,
+    written by scripts/summarize_profiles.py: dram__bytes_read.sum + dram__bytes_write.sum over every split-search launch of
+    one CV), expressed per launch of this run."""
+    import glob
+    best = None
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_summary.json"))):
+        try:
+            d = json.load(open(p)).get("split_search_dram")
+        except Exception:
+            d = None
+        if d:
+            best = (d, os.path.basename(p))
+    if not best or launches_per_step <= 0:
+        return None, None
+    d, name = best
+    return (d["dram_read_bytes"] + d["dram_write_bytes"]) / launches_per_step, "profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum over the %d split-search launches of one CV)" % (name, d["launches"])
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_sample(w, x, y, f, parts_sample, threads):
     """Time the reference's own CPU code (oracle/_ref, unmodified classes) on a bounded sample: `parts_sample` partitions of
@@ -187,10 +206,11 @@ def run_ours(args, w):
         dist.all_reduce(t)
         torch.cuda.current_stream().synchronize()
 
+    # fold lanes: how many folds of the CV are in flight at once (None = the library default); the timed steps run without
+    # per-kernel events, the roofline kernel is timed in its own region below with the folds one after the other
     common = dict(labels=y, folds=f, nFolds=w["nFolds"], nParts=w["nParts"], fp=w["fp"], ratio=w["ratio"], k=w["k"], nTrees=w["nTrees"], mtry=w["mtry"],
                   seed=w["seed"], device=local, stream=stream.cuda_stream, tie_mode=1, eval_fold_curves=True, rank=rank, world=world,
-                  reduce=reduce if world > 1 else None,
-                  profile=2)   # timed steps: CUDA events around the split-search launches only (the roofline kernel)
+                  reduce=reduce if world > 1 else None, profile=0, fold_lanes=args.fold_lanes)
 
     def barrier():
         if world > 1:
@@ -224,9 +244,15 @@ def run_ours(args, w):
     for _ in range(min(args.warmup, 1)):
         run_e2e()
     ms_e2e, outs_e2e = timed(run_e2e, args.steps)
+    # roofline kernel: its own timed region of the same K steps, CUDA events around every split-search launch (on the stream it
+    # is launched on), folds one after the other -- with several fold lanes in flight the kernels of different folds share the
+    # SMs and an event pair around one launch also measures the others' work
+    run_roof = lambda: hdev.cv_run(None, x_device_ptr=x_dev.data_ptr(), n=n, m=m, out=scores, **dict(common, profile=2, fold_lanes=1))
+    run_roof()
+    ms_roof, outs_roof = timed(run_roof, args.steps)
     # one more, untimed, step with every kernel class under events: the per-kernel breakdown reported next to the roofline
-    # (timing all ~1200 launches of a step costs ~4% of it, so it stays out of the timed region)
-    brk = hdev.cv_run(None, x_device_ptr=x_dev.data_ptr(), n=n, m=m, out=scores, **dict(common, profile=1))
+    # (timing all ~1200 launches of a step costs ~4% of it, so it stays out of the timed regions)
+    brk = hdev.cv_run(None, x_device_ptr=x_dev.data_ptr(), n=n, m=m, out=scores, **dict(common, profile=1, fold_lanes=1))
 
     parts = w["nParts"] * w["nFolds"]
     value = parts * args.steps / (ms_dev / 1000.0)
@@ -239,20 +265,24 @@ def run_ours(args, w):
     d2h = 16 * n + (w["nFolds"] + 1) * 16 + 16 * int(sum(o["stats"]["levels"] for o in outs_e2e) / max(args.steps, 1))
 
     # roofline of the dominant training kernel over the timed region (this rank's kernels)
-    km = {k_: sum(o["kernel_ms"][k_] for o in outs) for k_ in outs[0]["kernel_ms"]}
+    km = {k_: sum(o["kernel_ms"][k_] for o in outs_roof) for k_ in outs_roof[0]["kernel_ms"]}
     kl = {k_: sum(o["kernel_launches"][k_] for o in outs) for k_ in outs[0]["kernel_launches"]}
-    split_bytes = sum(o["stats"]["split_bytes"] for o in outs)
+    kl_roof = sum(o["kernel_launches"]["split_search"] for o in outs_roof)
+    split_bytes = sum(o["stats"]["split_bytes"] for o in outs_roof)
+    assert split_bytes == sum(o["stats"]["split_bytes"] for o in outs), "the roofline region did not do the work of the timed region"
     peak, peak_src = peaks()
-    ss_ms, ss_launches = km["split_search"], max(kl["split_search"], 1)
+    ss_ms, ss_launches = km["split_search"], max(kl_roof, 1)
     achieved = split_bytes / (ss_ms / 1000.0) / 1e9 if ss_ms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic(kl_roof / max(args.steps, 1)) if args.workload == "cfg2" and world == 1 else (None, None)
     roofline = {"kernel": "split_search_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": split_bytes / ss_launches,
-                "avg_launch_ms": ss_ms / ss_launches, "launches": kl["split_search"],
-                "kernel_ms_per_step": dict(brk["kernel_ms"]), "kernel_ms_per_step_source": "one extra untimed step with all kernel classes under CUDA events"}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": split_bytes / ss_launches,
+                "avg_launch_ms": ss_ms / ss_launches, "launches": kl_roof,
+                "timed_region": "%d steps with the folds one after the other (fold lanes = 1), %.2f ms per step; events around every split-search launch" % (args.steps, ms_roof / args.steps),
+                "kernel_ms_per_step": dict(brk["kernel_ms"]), "kernel_ms_per_step_source": "one extra untimed step (fold lanes = 1) with all kernel classes under CUDA events"}
     if rank == 0:
         line = {"metric": "partitions/sec", "value": value, "unit": "partitions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(args, w), "clocks": clocks,
+                "config": dict(workload_config(args, w), fold_lanes=outs[0].get("fold_lanes")), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "partitions/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(sum(kl.values())), "roofline": roofline,
                 "examples_per_sec": n * args.steps / (ms_dev / 1000.0),
@@ -290,6 +320,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fold-lanes", type=int, default=None, help="folds in flight at once (default: the library's)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -43,6 +43,16 @@ int psm_set_stream(psm_ctx* ctx, void* cuda_stream);
 /* Device-memory budget (bytes) for one partition batch of the training kernels; 0 = default (24 GiB). */
 int psm_set_batch_budget(psm_ctx* ctx, uint64_t bytes);
 int psm_sync(psm_ctx* ctx);
+/* Fold lanes: folds of one cross-validation are independent until the final score merge (src/hyperSMURF.cpp:161-396 runs
+ * them one after the other), so a host may drive several folds at once, one context per lane on the same device, each from
+ * its own host thread.  psm_ctx_own_stream gives the context a private non-blocking stream (destroyed with the context);
+ * psm_dataset_devptr returns the device copy of x so that the other lanes can psm_dataset_attach_device it instead of
+ * uploading it again; psm_scores_merge adds src's device class1Prob/class2Prob[n] into dst's (test sets of different folds
+ * are disjoint, so every element receives at most one non-zero term and the sum is exact) after src's stream has drained. */
+int psm_ctx_own_stream(psm_ctx* ctx);
+int psm_ctx_bind_thread(psm_ctx* ctx);   /* make the context's device current in the calling host thread */
+int psm_dataset_devptr(psm_ctx* ctx, const double** x_dev);
+int psm_scores_merge(psm_ctx* dst, psm_ctx* src);
 
 /* ---- (2) dataset: `x` of hyperSMURF's ctor (src/hyperSMURF.h:26-28): row-major f64 [n][m+1], column m is
  *      1.0 for positives / 2.0 for negatives (src/fileImport.cpp:88-91).  Uploaded once. ------------------- */

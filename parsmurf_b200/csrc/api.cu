@@ -37,6 +37,7 @@ struct ProfPair { cudaEvent_t a, b; int cls; };
 struct psm_ctx {
 	int device = 0;
 	cudaStream_t stream = 0;
+	cudaStream_t ownStream = nullptr;   // psm_ctx_own_stream
 	uint64_t budget = 24ull << 30;
 	std::string err;
 
@@ -62,7 +63,7 @@ struct psm_ctx {
 	// train
 	uint32_t T = 0, mtry = 0;
 	TrainArgs A;
-	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dNodes8, dSplitFeat, dFlagBits, dItems0, dItems1, dCand, dRes, dDec, dPtask, dCounters, dStats, dSeeds,
+	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dNodes8, dSplitFeat, dFlagBits, dItems0, dItems1, dCls, dCand, dRes, dDec, dPtask, dCounters, dStats, dSeeds,
 	    dInjBoot, dInjBootOff, dInjCand;
 	uint32_t* hCounters = nullptr;   // pinned
 	cudaEvent_t evLevel = nullptr;
@@ -182,7 +183,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf* bufs[] = {&ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dClass12,
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
-	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dSplitFeat, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1,
+	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dSplitFeat, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1, &ctx->dCls,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dPtask, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
 	                  &ctx->dInjCand, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
 	                  &ctx->cScores, &ctx->cKeysA, &ctx->cKeysB, &ctx->cValsA, &ctx->cValsB, &ctx->cHist};
@@ -192,6 +193,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	if (ctx->hCounters) cudaFreeHost(ctx->hCounters);
 	if (ctx->evLevel) cudaEventDestroy(ctx->evLevel);
 	if (ctx->hStage) cudaFreeHost(ctx->hStage);
+	if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
 	delete ctx;
 	return PSM_OK;
 }
@@ -201,6 +203,23 @@ const char* psm_last_error(psm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null
 int psm_set_stream(psm_ctx* ctx, void* s) {
 	if (!ctx) return PSM_E_ARG;
 	ctx->stream = (cudaStream_t)s;
+	return PSM_OK;
+}
+int psm_ctx_own_stream(psm_ctx* ctx) {
+	if (!ctx) return PSM_E_ARG;
+	CU(cudaSetDevice(ctx->device));
+	if (!ctx->ownStream) CU(cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking));
+	ctx->stream = ctx->ownStream;
+	return PSM_OK;
+}
+int psm_ctx_bind_thread(psm_ctx* ctx) {
+	if (!ctx) return PSM_E_ARG;
+	CU(cudaSetDevice(ctx->device));
+	return PSM_OK;
+}
+int psm_dataset_devptr(psm_ctx* ctx, const double** x_dev) {
+	if (!ctx || !x_dev || !ctx->x) return fail(ctx, PSM_E_ARG, "dataset_devptr: no dataset");
+	*x_dev = ctx->x;
 	return PSM_OK;
 }
 int psm_set_batch_budget(psm_ctx* ctx, uint64_t bytes) {
@@ -438,6 +457,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	const uint32_t flagWords = (stride + 31) / 32;
 	ENSURE(ctx->dFlagBits, (size_t)nTrees * flagWords * 4);
 	ENSURE(ctx->dItems0, (size_t)itemCap * sizeof(Item)); ENSURE(ctx->dItems1, (size_t)itemCap * sizeof(Item));
+	ENSURE(ctx->dCls, (size_t)2 * NCLS * itemCap * 4);
 	ENSURE(ctx->dCand, (size_t)itemCap * mtry * 4);
 	ENSURE(ctx->dRes, (size_t)itemCap * mtry * sizeof(SearchRes));
 	ENSURE(ctx->dDec, (size_t)itemCap * sizeof(SplitDec));
@@ -456,6 +476,9 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	A.nodes = ctx->dNodes.as<Node16>();
 	A.flagBits = ctx->dFlagBits.as<uint32_t>(); A.flagWords = flagWords;
 	A.items[0] = ctx->dItems0.as<Item>(); A.items[1] = ctx->dItems1.as<Item>();
+	for (int b2 = 0; b2 < 2; b2++)
+		for (int k = 0; k < NCLS; k++) A.clsItems[b2][k] = ctx->dCls.as<uint32_t>() + ((size_t)b2 * NCLS + k) * itemCap;
+	A.useClasses = getenv("PSM_NO_SIZE_CLASSES") ? 0 : 1;
 	A.cand = ctx->dCand.as<uint32_t>(); A.res = ctx->dRes.as<SearchRes>(); A.dec = ctx->dDec.as<SplitDec>(); A.ptask = ctx->dPtask.as<PartTask>(); A.splitFeat = ctx->dSplitFeat.as<uint32_t>();
 	A.counters = ctx->dCounters.as<uint32_t>(); A.stats = ctx->dStats.as<unsigned long long>();
 	A.injCand = nullptr;
@@ -540,12 +563,18 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		if (e & ERR_INJ_CAND) return fail(ctx, PSM_E_ARG, "batch_train: injected candidate table has fewer nodes than a tree grew");
 		if (nItems == 0) break;
 		if (nItems > itemCap) return fail(ctx, PSM_E_OVERFLOW, "batch_train: work-item pool overflow");
-		CU(cudaMemsetAsync(A.counters + CNT_NEXT_ITEMS, 0, 4, s));
+		uint32_t clsCount[NCLS], clsSum = 0;
+		for (int k = 0; k < NCLS; k++) { clsCount[k] = ctx->hCounters[CNT_CLS0 + k]; clsSum += clsCount[k]; }
+		if (clsSum != nItems) return fail(ctx, PSM_E_OVERFLOW, "batch_train: size-class lists do not add up to the level's work items");
+		static_assert(CNT_NEXT_ITEMS == 0 && CNT_CLS0 == 1, "the per-level counters are cleared with one memset");
+		CU(cudaMemsetAsync(A.counters, 0, (1 + NCLS) * 4, s));
+		int nzCls = 0;                                   // one split-search launch per non-empty size class
+		for (int k = 0; k < NCLS; k++) nzCls += clsCount[k] != 0;
 		const bool trace = getenv("PSM_TRACE_LEVELS") != nullptr;
 		cudaEvent_t tev[5];
 		if (trace) for (auto& e : tev) cudaEventCreate(&e);
 		if (trace) cudaEventRecord(tev[0], s);
-		{ ProfScope ps(ctx, K_SEARCH, 1); launch_split_search(A, nItems, buf, s); }
+		{ ProfScope ps(ctx, K_SEARCH, nzCls); launch_split_search(A, clsCount, buf, s); }
 		if (trace) cudaEventRecord(tev[1], s);
 		{
 			ProfScope ps(ctx, K_SELECT, 2);
@@ -855,6 +884,16 @@ int psm_scores_get(psm_ctx* ctx, double* class1Prob, double* class2Prob) {
 	CU(cudaStreamSynchronize(ctx->stream));
 	for (uint32_t i = 0; i < ctx->n; i++) class1Prob[i] += h[i];
 	if (class2Prob) for (uint32_t i = 0; i < ctx->n; i++) class2Prob[i] += h[(size_t)ctx->n + i];
+	return PSM_OK;
+}
+
+int psm_scores_merge(psm_ctx* ctx, psm_ctx* src) {
+	if (!ctx || !src || !ctx->haveLabels || !src->haveLabels || ctx->n != src->n || ctx->device != src->device)
+		return fail(ctx, PSM_E_ARG, "scores_merge: both contexts need device scores of the same dataset on the same device");
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(src->stream));
+	launch_add_f64(ctx->dGlob.as<double>(), src->dGlob.as<double>(), (size_t)ctx->n * 2, ctx->stream);
+	CU(cudaGetLastError());
 	return PSM_OK;
 }
 

@@ -97,9 +97,10 @@ struct SplitDec {
 struct __align__(16) PartTask {
 	uint32_t tree;
 	uint32_t start;
-	uint32_t cnt;     // 0 = node does not split
+	uint32_t cnt;     // 0 = nothing to move (no split, or both children terminal); top bits: PT_DEAD_LEFT / PT_DEAD_RIGHT
 	uint32_t nleft;
 };
+constexpr uint32_t PT_DEAD_LEFT = 1u << 31, PT_DEAD_RIGHT = 1u << 30, PT_CNT_MASK = (1u << 30) - 1u;   // rows per matrix < 2^24
 
 // per-tree growth state
 struct TreeState {
@@ -110,6 +111,17 @@ struct TreeState {
 	uint32_t nEntries;    // in-bag distinct rows
 	uint32_t overflow;
 };
+
+// Opt a kernel in to the full 227 KB of dynamic shared memory.  The attribute belongs to the function, not to the calling
+// thread or stream: several host threads (fold lanes) launch the same kernel with different sizes, so every caller sets the
+// SAME ceiling instead of its own size -- setting the exact size would let one thread lower it under another's launch.
+constexpr int kMaxSmemOptin = 227 * 1024;   // per block, static + dynamic
+template <typename F> inline cudaError_t allow_max_dyn_smem(F* fn) {
+	cudaFuncAttributes a;
+	cudaError_t e = cudaFuncGetAttributes(&a, (const void*)fn);
+	if (e != cudaSuccess) return e;
+	return cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin - (int)a.sharedSizeBytes);
+}
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {

@@ -49,6 +49,15 @@ void launch_scatter_scores(const double* class12, const uint32_t* testIdx, uint3
 	scatter_scores_kernel<<<(Nte + 255) / 256, 256, 0, s>>>(class12, testIdx, Nte, n, glob);
 }
 
+__global__ void add_f64_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t count) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) dst[i] = __dadd_rn(dst[i], src[i]);
+}
+void launch_add_f64(double* dst, const double* src, size_t count, cudaStream_t s) {
+	if (!count) return;
+	add_f64_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(dst, src, count);
+}
+
 __device__ __forceinline__ uint32_t block_reduce_u32(uint32_t v, uint32_t* sh) {
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;

@@ -4,7 +4,13 @@
 
 namespace psm {
 
-enum { CNT_NEXT_ITEMS = 0, CNT_ERROR = 1, CNT_COUNT = 4 };
+// counters[CNT_NEXT_ITEMS] = open nodes of the next level; counters[CNT_CLS0 + k] = how many of them fall in size class k
+// (level_finalize appends their item ids to clsItems[next][k]); both are cleared by the host before the next level_finalize
+constexpr int NCLS = 4;
+enum { CNT_NEXT_ITEMS = 0, CNT_CLS0 = 1, CNT_ERROR = 5, CNT_COUNT = 8 };
+// Size class of a work item by its segment length (+3: worst-case shift of the 16-byte aligned load grid):
+//   0: <= 32 grid entries (8 lanes x 4)   1: <= 64 (16 lanes)   2: <= 128 (one warp, one chunk)   3: longer (chunk loop)
+__host__ __device__ __forceinline__ uint32_t size_class(uint32_t cnt) { return cnt <= 29u ? 0u : cnt <= 61u ? 1u : cnt <= 125u ? 2u : 3u; }
 enum { ERR_COUNT_LIMIT = 1, ERR_POOL_OVERFLOW = 2, ERR_INJ_CAND = 4 };
 enum { STAT_SPLIT_BYTES = 0, STAT_NODES = 1, STAT_COUNT = 4 };
 
@@ -31,6 +37,8 @@ struct TrainArgs {
 	uint32_t* flagBits;   // [tree][flagWords] go-left flag per in-bag row, bit-packed (tree_flags_kernel -> partition_lists_kernel)
 	uint32_t flagWords;
 	Item* items[2];
+	uint32_t* clsItems[2][NCLS];   // [buf][class][itemCap] item ids of each size class (same ping-pong as items)
+	int useClasses;       // 0: every item goes to class 3 (one generic launch per level)
 	uint32_t* cand;       // [itemCap][mtry]
 	SearchRes* res;       // [itemCap][mtry]
 	SplitDec* dec;        // [itemCap]
@@ -59,7 +67,7 @@ void launch_bootstrap(const TrainArgs& A, const uint32_t* forestSeeds, cudaStrea
 void launch_inbag_from_ids(const TrainArgs& A, const unsigned long long* ids, const uint64_t* idOffsets, cudaStream_t s);
 void launch_build_lists(const TrainArgs& A, cudaStream_t s);
 int launch_init_trees(const TrainArgs& A, cudaStream_t s);
-void launch_split_search(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
+void launch_split_search(const TrainArgs& A, const uint32_t* clsCount, int buf, cudaStream_t s);
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
 void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s);
 int launch_tree_flags(const TrainArgs& A, cudaStream_t s);
@@ -76,6 +84,7 @@ void launch_accumulate(const double* scratch, uint32_t Nte, uint32_t nPartsBatch
 int launch_curves(const unsigned char* labelsSorted, uint64_t N, uint32_t totP, uint32_t totN, uint32_t* tpScratch,
                   double* partials, size_t partialsCap, double* out2, cudaStream_t s);
 void launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint64_t N, uint32_t* out, cudaStream_t s);
+void launch_add_f64(double* dst, const double* src, size_t count, cudaStream_t s);
 void launch_scatter_scores(const double* class12, const uint32_t* testIdx, uint32_t Nte, uint32_t n, double* glob, cudaStream_t s);
 void launch_gather_labels(const uint32_t* labels, const uint32_t* perm, uint64_t N, unsigned char* out, cudaStream_t s);
 int launch_sort_scores_desc(const double* scores, uint64_t N, unsigned long long* keysA, unsigned long long* keysB, uint32_t* valsA,

@@ -173,6 +173,11 @@ __global__ void __launch_bounds__(PT) predict_tma_kernel(const double* __restric
 // visit in 10^7).  Decisions are therefore identical to ranger's fp64 `value <= split_value` (Tree.cpp:163), while shared
 // memory per CTA drops from 88 KB to 44 KB (5 CTAs/SM instead of 2) and a node visit costs LDS.64 + LDS.32 instead of
 // LDS.128 + LDS.64 (ncu r01: the 16-byte-node kernel is bound by shared-memory wavefronts and LDS latency).
+// Half of the lane-cycles of the walk are lost to depth divergence (a warp is busy for the deepest of its 32 paths).  Visiting
+// the test rows in an order that groups similar rows was tried and does not help: keyed by the total path length in the
+// first 8 trees of the fold, or by the leaf reached in the first tree (probe kernel + counting sort, scores unchanged), the
+// kernel ran 5-8% SLOWER at BASELINE configs[1] and configs[2] -- a row's depth in one tree says little about its depth in
+// another (the trees split on random candidates among 21 noise features), so the warp maximum stays where it is.
 // Leaf payloads are the exact fp64 fractions count_c / n (TreeProbability.cpp:47-63).  Almost every leaf is pure or has
 // n <= 10 samples (min_node_size), so its pair of fractions is one of the 66 values p/n, n <= 10: the leaf stores the code
 // n*11+p and the kernel looks the two doubles up in a shared-memory table built with the same IEEE division; the rare other
@@ -415,7 +420,7 @@ int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_
 			const Node8* n8 = reinterpret_cast<const Node8*>(nodes8);
 #define PSM_LAUNCH_COMPACT(K)                                                                                                              \
 	do {                                                                                                                                   \
-		if (cudaFuncSetAttribute(predict_compact_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC) != cudaSuccess) return -1; \
+		if (allow_max_dyn_smem(predict_compact_kernel<K>) != cudaSuccess) return -1; \
 		predict_compact_kernel<K><<<grid, PT, smemC, s>>>(x, m, testIdx, Nte, nodes, n8, NC, ts, nPartsBatch, T, pch, mn, scratch);        \
 	} while (0)
 			if (tps == 8) PSM_LAUNCH_COMPACT(8);
@@ -441,7 +446,7 @@ int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_
 			if (chunks > nPartsBatch) chunks = nPartsBatch;
 			const uint32_t pch = (nPartsBatch + chunks - 1) / chunks;
 			chunks = (nPartsBatch + pch - 1) / pch;
-			if (cudaFuncSetAttribute(predict_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT) != cudaSuccess) return -1;
+			if (allow_max_dyn_smem(predict_tma_kernel) != cudaSuccess) return -1;
 			predict_tma_kernel<<<dim3(rowTiles, chunks), PT, smemT, s>>>(x, m, testIdx, Nte, nodes, NC, ts, nPartsBatch, T, pch, maxNodes, scratch);
 			return 0;
 		}
@@ -461,7 +466,7 @@ int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_
 	dim3 grid(rowTiles, chunks);
 	if (useSmem) {
 		if (smem > 48 * 1024)
-			if (cudaFuncSetAttribute(predict_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+			if (allow_max_dyn_smem(predict_kernel<true>) != cudaSuccess) return -1;
 		predict_kernel<true><<<grid, PT, smem, s>>>(x, m, testIdx, Nte, nodes, NC, nPartsBatch, T, pch, scratch);
 	} else {
 		predict_kernel<false><<<grid, PT, 0, s>>>(x, m, testIdx, Nte, nodes, NC, nPartsBatch, T, pch, scratch);

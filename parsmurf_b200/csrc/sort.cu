@@ -309,7 +309,7 @@ template <int CEMAX, int MINB>
 static int launch_sort_split(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, uint32_t slotsMax, entry_t* Sall,
                              cudaStream_t s) {
 	const size_t smem = (size_t)slotsMax * 10;
-	if (cudaFuncSetAttribute(feature_sort_split_kernel<CEMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+	if (allow_max_dyn_smem(feature_sort_split_kernel<CEMAX, MINB>) != cudaSuccess) return -1;
 	feature_sort_split_kernel<CEMAX, MINB><<<nPartsBatch * m, BT, smem, s>>>(Dall, parts, m, slotsMax, Sall);
 	return 0;
 }
@@ -317,7 +317,7 @@ static int launch_sort_split(const double* Dall, const PartDesc* parts, uint32_t
 template <uint32_t NPAD>
 static int launch_sort_smem_N(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, entry_t* Sall, cudaStream_t s) {
 	const size_t smem = (size_t)NPAD * 10;
-	if (cudaFuncSetAttribute(feature_sort_smem_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+	if (allow_max_dyn_smem(feature_sort_smem_kernel<NPAD>) != cudaSuccess) return -1;
 	feature_sort_smem_kernel<NPAD><<<nPartsBatch * m, BT, smem, s>>>(Dall, parts, m, Sall);
 	return 0;
 }

@@ -276,6 +276,8 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 		if (lane == 0) {
 			Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = ts.nEntries; it.npos = npos; it.nneg = nneg; it.nPosOut = pd.nPosOut; it.pad = 0;
 			A.items[0][item] = it;
+			const uint32_t k = A.useClasses ? size_class(ts.nEntries) : (uint32_t)(NCLS - 1);
+			A.clsItems[0][k][atomicAdd(&A.counters[CNT_CLS0 + k], 1u)] = item;
 		}
 	} else if (lane == 0) {
 		write_leaf(&nodes[0], npos, nneg);
@@ -342,43 +344,78 @@ __device__ __forceinline__ void ss_load(const E* __restrict__ base, uint32_t v, 
 	}
 }
 
+// single-chunk variant: the whole aligned vector is loaded whenever any of its entries is valid (the surrounding entries
+// belong to neighbouring segments of the same list, or to the list's padding: start - off is a multiple of the vector
+// length and the stride is a multiple of 4, so the load never leaves the allocation) and the invalid slots are zeroed
+// afterwards -- no divergent per-entry path for the lanes that straddle the segment ends.
+template <typename E>
+__device__ __forceinline__ void ss_load_single(const E* __restrict__ base, uint32_t v, uint32_t lo, uint32_t hi, E (&e)[SS_IPL]) {
+#pragma unroll
+	for (int j = 0; j < SS_IPL; j++) e[j] = (E)0;
+	if (v < hi && v + SS_IPL > lo) ss_vec(base + v, e);
+#pragma unroll
+	for (int j = 0; j < SS_IPL; j++) e[j] = (v + j >= lo && v + j < hi) ? e[j] : (E)0;
+}
+
 template <typename E> struct PkOf;
 template <> struct PkOf<uint32_t> { typedef uint32_t type; static constexpr int shift = 16; };
 template <> struct PkOf<unsigned long long> { typedef unsigned long long type; static constexpr int shift = 32; };
 
-// G = lanes per (node, candidate) work item.  G = 32 streams long segments chunk by chunk (128 entries per iteration);
-// G = 16 / 8 pack two / four short segments (<= 64 / <= 32 entries of the aligned grid) into one warp: at deep levels
-// most nodes hold a few dozen rows and the kernel is instruction-issue bound (ncu r01), so the per-warp fixed cost is
-// shared by up to four work items.  Every item is processed by exactly one of the three instantiations.
-// Measured alternatives that did NOT pay at BASELINE configs[1] (split search stays at ~14.1 ms per CV in every case; ncu r01
-// at the mid levels: 585 warp instructions per (node, candidate) for an 89-entry segment -- 108 set-up, ~240 per chunk, ~58
-// per exact evaluation, 53 arg-max --, 65% issue-active with 6 warps per scheduler, a quarter of the stall samples on the
-// work-item -> candidate -> list-entry load chain):
+// group collectives: all 32 lanes of a warp always take part (an idle group of a sub-warp instantiation recomputes the
+// last work item and only skips the store), so the shuffles run with the full member mask and a segment width -- a partial
+// runtime mask would make nvcc wrap every collective in a WARPSYNC/COLLECTIVE region
+template <int G> __device__ __forceinline__ uint32_t grp_max(uint32_t v) {
+	if constexpr (G == 32) return __reduce_max_sync(0xffffffffu, v);
+	else {
+#pragma unroll
+		for (int o = G / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+		return v;
+	}
+}
+template <int G> __device__ __forceinline__ uint32_t grp_min(uint32_t v) {
+	if constexpr (G == 32) return __reduce_min_sync(0xffffffffu, v);
+	else {
+#pragma unroll
+		for (int o = G / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+		return v;
+	}
+}
+
+// G = lanes per (node, candidate) work item, MULTI = the segment may span several chunks of G*SS_IPL entries.
+// level_finalize sorts the open nodes of a level into four size classes (kernels.cuh: size_class) and every class is
+// launched over its own compact item list with the instantiation that fits it:
+//   class 0 (<= 32 grid entries): G = 8, four work items per warp      class 1 (<= 64): G = 16, two per warp
+//   class 2 (<= 128): G = 32, one chunk, straight-line code             class 3: G = 32, chunk loop with prefetch
+// At the mid and deep levels most nodes hold a few dozen rows and the kernel is instruction-issue bound (ncu r01: 557 warp
+// instructions per (node, candidate) for an 89-entry segment, 65% issue-active), so the per-warp fixed cost -- work-item
+// set-up, the scan, the exact block, the arg-max -- is what the small classes share between two or four items.
+// (An earlier attempt launched the three G variants over ALL items and let the non-matching warps exit: the extra item
+// loads and empty warps cost more than the packing saved; the compact per-class lists are what makes it pay.)
+// Measured alternatives that did NOT pay at BASELINE configs[1] (split search stayed at ~14.1 ms per CV in every case):
 //   * one warp per node walking its mtry candidates (set-up and arg-max paid once, next candidate prefetched, filter bound
 //     carried across candidates): 25% fewer instructions per node, 15.5-17.6 ms -- the five-fold loss of independent warps
 //     costs more than the instructions saved;
 //   * a single shared exact-evaluation block fed by a per-lane pending mask instead of one block per lane slot: same time
 //     (only the taken blocks ever executed);
 //   * no software pipeline (40 registers, 12 CTAs per SM instead of 8): same time -- what the extra warps hide, the exposed
-//     load of every second chunk gives back;
-//   * sub-warp groups (8 / 16 lanes per segment), 2 or 8 entries per lane, other launch bounds: slower (see above).
-template <typename E, int G>
-__global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A, uint32_t nItems, int buf) {
+//     load of every second chunk gives back.
+template <typename E, int G, bool MULTI>
+__global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A, const uint32_t* __restrict__ list, uint32_t nList, int buf) {
 	// grid.y = candidate index, so no integer division is needed to find the work item
-	const uint32_t item = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
-	if (item >= nItems) return;
+	uint32_t li = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
+	const bool idle = li >= nList;
+	if (G == 32) { if (idle) return; }
+	else if (idle) li = nList - 1;                            // keep the warp whole (see grp_max)
+	const uint32_t item = __ldg(list + li);
 	const uint32_t c = blockIdx.y;
 	const Item it = A.items[buf][item];
 	constexpr uint32_t APE = (SS_IPL * sizeof(E) < 16 ? SS_IPL * sizeof(E) : 16) / sizeof(E);   // entries per aligned vector load
 	const uint32_t off = it.start % APE;                      // A.stride % 4 == 0, so list + start - off is 16-byte aligned
 	const uint32_t lo = off, hi = it.cnt + off;                // valid index range in the aligned grid
-	// size classes (only used when the sub-warp instantiations are launched; measured slower than G = 32 alone at
-	// BASELINE configs[1], where mid-level segments hold ~100 entries, so launch_split_search launches G = 32 for everything)
-	if (G == 8 && hi > 32) return;
-	if (G == 16 && (hi <= 32 || hi > 64)) return;
 	const int lane = lane_id();
 	const int gl = lane % G;
-	const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));
+	const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));   // this group's lanes (ballot filter only)
+	constexpr unsigned FULL = 0xffffffffu;
 	const uint32_t f = A.cand[(size_t)item * A.mtry + c];
 	const uint32_t nPosOut = it.nPosOut;
 	const E* base = reinterpret_cast<const E*>(A.lists[A.listBuf]) + ((size_t)it.tree * A.m + f) * A.stride + (it.start - off);
@@ -388,10 +425,12 @@ __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A,
 	float wbound = 0.0f;                                      // group-uniform: (best exact score of earlier chunks) * (1 - 4e-6)
 	uint32_t bpos = 0xFFFFFFFFu, blp = 0, bln = 0;
 	E e[SS_IPL], nx[SS_IPL];
-	ss_load<E>(base, gl * SS_IPL, lo, hi, e);
-	for (uint32_t b = 0; b < hi; b += G * SS_IPL) {
+	if (MULTI) ss_load<E>(base, gl * SS_IPL, lo, hi, e);
+	else ss_load_single<E>(base, gl * SS_IPL, lo, hi, e);
+	uint32_t b = 0;
+	do {
 		const uint32_t v0 = b + gl * SS_IPL;
-		if (G == 32) ss_load<E>(base, v0 + G * SS_IPL, lo, hi, nx);   // prefetch the next chunk (short segments have none)
+		if (MULTI) ss_load<E>(base, v0 + G * SS_IPL, lo, hi, nx);   // prefetch the next chunk
 		else {
 #pragma unroll
 			for (int j = 0; j < SS_IPL; j++) nx[j] = (E)0;
@@ -411,12 +450,12 @@ __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A,
 		pk_t inc = run;
 #pragma unroll
 		for (int o = 1; o < G; o <<= 1) {
-			pk_t t = __shfl_up_sync(gm, inc, o, G);
+			pk_t t = __shfl_up_sync(FULL, inc, o, G);
 			if (gl >= o) inc += t;
 		}
 		const pk_t excl = inc - run;
-		const uint32_t rfirst_next_lane = Ent<E>::rank(__shfl_down_sync(gm, e[0], 1, G));
-		const uint32_t rfirst_next_chunk = Ent<E>::rank(__shfl_sync(gm, nx[0], 0, G));
+		const uint32_t rfirst_next_lane = Ent<E>::rank(__shfl_down_sync(FULL, e[0], 1, G));
+		const uint32_t rfirst_next_chunk = MULTI ? Ent<E>::rank(__shfl_sync(FULL, nx[0], 0, G)) : 0u;
 		// phase 1: fp32 estimate of the Gini proxy at every candidate position of the chunk (no divisions, no branches).
 		// sum_c L_c^2/n_L + sum_c R_c^2/n_R  ==  n - 2 (L0 L1 / n_L + R0 R1 / n_R)   (two classes), which needs half the conversions.
 		float est[SS_IPL];
@@ -439,11 +478,11 @@ __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A,
 		// estimate of this chunk, or of the best exact score of earlier chunks, can be the arg-max: evaluate those
 		// exactly (two IEEE fp64 divisions, TreeProbability.cpp:337).  Estimates are >= 0, so their bit patterns order
 		// like unsigned integers and one redux gives the group maximum.
-		const float cmax = __uint_as_float(__reduce_max_sync(gm, __float_as_uint(emax)));
+		const float cmax = __uint_as_float(grp_max<G>(__float_as_uint(emax)));
 		const float thr = fmaxf(cmax * 0.999996f, wbound);
 #pragma unroll
 		for (int j = 0; j < SS_IPL; j++) {
-			if (__any_sync(gm, est[j] >= thr)) {
+			if (__ballot_sync(FULL, est[j] >= thr) & gm) {
 				if (est[j] >= thr) {
 					const pk_t tot = excl + pk[j];
 					const uint32_t lpi = lp + (uint32_t)(tot >> PKS), lni = ln + (uint32_t)(tot & (((pk_t)1 << PKS) - 1));
@@ -456,38 +495,36 @@ __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A,
 				}
 			}
 		}
-		if (G == 32) {
+		if (MULTI) {
 			// group-uniform bound for the following chunks: a later position must strictly beat the best exact score so far
 			const float bf = best > 0.0 ? __double2float_rd(best) : 0.0f;
-			const float wb = __uint_as_float(__reduce_max_sync(gm, __float_as_uint(bf)));
+			const float wb = __uint_as_float(grp_max<G>(__float_as_uint(bf)));
 			wbound = wb * 0.999996f;
-			const pk_t tot = __shfl_sync(gm, inc, G - 1, G);
+			const pk_t tot = __shfl_sync(FULL, inc, G - 1, G);
 			lp += (uint32_t)(tot >> PKS); ln += (uint32_t)(tot & (((pk_t)1 << PKS) - 1));
 #pragma unroll
 			for (int j = 0; j < SS_IPL; j++) e[j] = nx[j];
 		}
-	}
+		b += G * SS_IPL;
+	} while (MULTI && b < hi);
 	// arg-max over the group's lanes: highest score, then lowest position (ascending value order, strict '>').
 	// Scores are positive doubles, so their two 32-bit halves order like unsigned integers: three redux steps.
 	{
 		const unsigned long long sb = best > 0.0 ? (unsigned long long)__double_as_longlong(best) : 0ull;
-		const uint32_t mhi = __reduce_max_sync(gm, (uint32_t)(sb >> 32));
+		const uint32_t mhi = grp_max<G>((uint32_t)(sb >> 32));
 		const bool c1 = (uint32_t)(sb >> 32) == mhi && sb != 0ull;
-		const uint32_t mlo = __reduce_max_sync(gm, c1 ? (uint32_t)sb : 0u);
+		const uint32_t mlo = grp_max<G>(c1 ? (uint32_t)sb : 0u);
 		const bool c2 = c1 && (uint32_t)sb == mlo;
-		const uint32_t mpos = __reduce_min_sync(gm, c2 ? bpos : 0xFFFFFFFFu);
-		const unsigned win = __ballot_sync(gm, c2 && bpos == mpos) & gm;
-		if (win) {
-			const int src = __ffs(win) - 1;
-			best = __shfl_sync(gm, best, src);
-			blp = __shfl_sync(gm, blp, src);
-			bln = __shfl_sync(gm, bln, src);
-			bpos = mpos;
-		} else {
-			best = -1.0; bpos = 0xFFFFFFFFu;
-		}
+		const uint32_t mpos = grp_min<G>(c2 ? bpos : 0xFFFFFFFFu);
+		const unsigned win = __ballot_sync(FULL, c2 && bpos == mpos) & gm;
+		// (the shuffles are unconditional: groups of one warp may disagree on `win`)
+		const int src = win ? __ffs(win) - 1 : lane;
+		const double wbest = __shfl_sync(FULL, best, src);
+		const uint32_t wlp = __shfl_sync(FULL, blp, src), wln = __shfl_sync(FULL, bln, src);
+		if (win) { best = wbest; blp = wlp; bln = wln; bpos = mpos; }
+		else { best = -1.0; bpos = 0xFFFFFFFFu; }
 	}
-	if (gl == 0) {
+	if (gl == 0 && !idle) {
 		SearchRes r; r.score = best; r.pos = bpos; r.lpos = blp; r.lneg = bln; r.pad = 0;
 		A.res[(size_t)item * A.mtry + c] = r;
 	}
@@ -535,7 +572,11 @@ __global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t
 		*node = v;
 		d.split = 1; d.nleft = r.pos + 1; d.lpos = r.lpos; d.lneg = r.lneg;
 		A.dec[item] = d;
-		PartTask pt; pt.tree = it.tree; pt.start = it.start; pt.cnt = it.cnt; pt.nleft = d.nleft;
+		// list partition: a terminal child's entries are never read again (level_finalize writes its leaf payload from
+		// the class counts), so they are not moved; with two terminal children the node is skipped entirely
+		const bool deadL = !node_live(d.lpos, d.lneg), deadR = !node_live(it.npos - d.lpos, it.nneg - d.lneg);
+		PartTask pt; pt.tree = it.tree; pt.start = it.start; pt.nleft = d.nleft;
+		pt.cnt = (deadL && deadR) ? 0u : (it.cnt | (deadL ? PT_DEAD_LEFT : 0u) | (deadR ? PT_DEAD_RIGHT : 0u));
 		A.ptask[item] = pt;
 		A.splitFeat[item] = f;
 	}
@@ -678,6 +719,25 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 				nextItems[o] = c; sm.child[2 * sp + 1] = o;
 			} else { write_leaf(&nodes[leftId + 1], rpos, rneg); sm.child[2 * sp + 1] = 0xFFFFFFFFu; }
 		}
+		{
+			// size-class lists of the next level (one warp-aggregated atomic per class and batch of 32 parents)
+			const uint32_t big = (uint32_t)(NCLS - 1);
+			const uint32_t kL = liveL ? (A.useClasses ? size_class(d.nleft) : big) : (uint32_t)NCLS;
+			const uint32_t kR = liveR ? (A.useClasses ? size_class(it.cnt - d.nleft) : big) : (uint32_t)NCLS;
+			const uint32_t oL = myOff, oR = myOff + (liveL ? 1u : 0u);
+#pragma unroll
+			for (uint32_t k = 0; k < (uint32_t)NCLS; k++) {
+				const unsigned mL = __ballot_sync(0xffffffffu, kL == k), mR = __ballot_sync(0xffffffffu, kR == k);
+				const uint32_t tot = __popc(mL) + __popc(mR);
+				if (tot == 0) continue;
+				uint32_t cb = 0;
+				if (lane == 0) cb = atomicAdd(&A.counters[CNT_CLS0 + k], tot);
+				cb = __shfl_sync(0xffffffffu, cb, 0);
+				uint32_t* cl = A.clsItems[buf ^ 1][k];
+				if (kL == k) cl[cb + __popc(mL & lt)] = oL;
+				if (kR == k) cl[cb + __popc(mL) + __popc(mR & lt)] = oR;
+			}
+		}
 		__syncwarp();
 		const uint32_t nchild = 2 * __popc(smask);
 		const bool laneFY = !A.injCand && A.mtry <= FY_MAX && !(A.mtry < (A.m + 1) / 10);
@@ -735,13 +795,40 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 #endif
 constexpr int PL_CH_DEFAULT = PSM_PL_CH;
 
+// the last (< NCH * 32) entries of a segment, fully predicated; NCH = chunk slots compiled in
+template <typename E, int NCH>
+__device__ __forceinline__ void partition_tail(const E* srcp, E* dstp, const uint32_t* fbits, uint32_t b, uint32_t cnt, uint32_t lane, unsigned lt,
+                                               uint32_t offL, uint32_t offR, bool keepL, bool keepR) {
+	E e[NCH];
+	uint32_t w[NCH];
+#pragma unroll
+	for (int c = 0; c < NCH; c++) e[c] = (b + c * 32 + lane < cnt) ? __ldg(srcp + c * 32) : (E)0;
+#pragma unroll
+	for (int c = 0; c < NCH; c++) w[c] = __ldg(fbits + (Ent<E>::row(e[c]) >> 5));
+#pragma unroll
+	for (int c = 0; c < NCH; c++) {
+		const uint32_t first = b + c * 32;                 // uniform
+		const bool valid = first + lane < cnt;
+		const bool gl = valid && ((w[c] >> (Ent<E>::row(e[c]) & 31u)) & 1u);
+		const unsigned mL = __ballot_sync(0xffffffffu, gl);
+		const uint32_t pL = __popc(mL & lt), nL = __popc(mL);
+		const uint32_t nv = first < cnt ? min(32u, cnt - first) : 0u;
+		const uint32_t idx = gl ? offL + pL : offR + lane - pL;
+		if (valid && (gl ? keepL : keepR)) dstp[idx] = e[c];
+		offL += nL; offR += nv - nL;
+	}
+}
+
 template <typename E, int PL_CH>
 __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint32_t nItems, int buf) {
 	const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (item >= nItems) return;
 	const uint4 raw = __ldg(reinterpret_cast<const uint4*>(A.ptask + item));
-	const uint32_t tree = raw.x, start = raw.y, cnt = raw.z, nleft = raw.w;
-	if (cnt == 0) return;                                      // node became a leaf
+	// PartTask: cnt carries two flags in its top bits -- a child that is terminal (<= 10 samples or pure) is never read
+	// again, so its entries are not written; a node with two terminal children is skipped altogether (split_select)
+	const uint32_t tree = raw.x, start = raw.y, cnt = raw.z & PT_CNT_MASK, nleft = raw.w;
+	if (cnt == 0) return;                                      // node became a leaf, or neither child will be searched
+	const bool keepL = !(raw.z & PT_DEAD_LEFT), keepR = !(raw.z & PT_DEAD_RIGHT);
 	const uint32_t f = blockIdx.y;
 	const uint32_t lane = lane_id();
 	const unsigned lt = lanemask_lt();
@@ -756,6 +843,10 @@ __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint3
 	// loop is written for instruction count: 32-bit indices off two base pointers, one ballot per chunk (the valid lanes of a
 	// chunk are a prefix, so a lane's rank among the right-goers is lane - rank among the left-goers), one store per entry,
 	// and an unpredicated flag load (an invalid lane carries entry 0 -> row 0, a legal address).
+	// Short segments (the mid and deep levels: ncu r01 shows 180 warp instructions for an 89-entry segment because all
+	// PL_CH predicated slots of the tail are issued) take a tail with only as many chunk slots as they need.
+	if (cnt <= 32) { partition_tail<E, 1>(srcp, dstp, fbits, 0, cnt, lane, lt, 0, nleft, keepL, keepR); return; }
+	if (cnt <= 64) { partition_tail<E, 2>(srcp, dstp, fbits, 0, cnt, lane, lt, 0, nleft, keepL, keepR); return; }
 	uint32_t offL = 0, offR = nleft;                           // next free slot of the left / right child segment
 	uint32_t b = 0;
 	// full groups of PL_CH * 32 entries: no bounds logic at all (what the long segments of the first levels run)
@@ -771,30 +862,13 @@ __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint3
 			const bool gl = (w[c] >> (Ent<E>::row(e[c]) & 31u)) & 1u;
 			const unsigned mL = __ballot_sync(0xffffffffu, gl);
 			const uint32_t pL = __popc(mL & lt), nL = __popc(mL);
-			dstp[gl ? offL + pL : offR + lane - pL] = e[c];
+			if (gl ? keepL : keepR) dstp[gl ? offL + pL : offR + lane - pL] = e[c];
 			offL += nL; offR += 32 - nL;
 		}
 	}
-	// the remaining (< PL_CH * 32) entries, fully predicated
 	if (b < cnt) {
-		E e[PL_CH];
-		uint32_t w[PL_CH];
-#pragma unroll
-		for (int c = 0; c < PL_CH; c++) e[c] = (b + c * 32 + lane < cnt) ? __ldg(srcp + c * 32) : (E)0;
-#pragma unroll
-		for (int c = 0; c < PL_CH; c++) w[c] = __ldg(fbits + (Ent<E>::row(e[c]) >> 5));
-#pragma unroll
-		for (int c = 0; c < PL_CH; c++) {
-			const uint32_t first = b + c * 32;                 // uniform
-			const bool valid = first + lane < cnt;
-			const bool gl = valid && ((w[c] >> (Ent<E>::row(e[c]) & 31u)) & 1u);
-			const unsigned mL = __ballot_sync(0xffffffffu, gl);
-			const uint32_t pL = __popc(mL & lt), nL = __popc(mL);
-			const uint32_t nv = first < cnt ? min(32u, cnt - first) : 0u;
-			const uint32_t idx = gl ? offL + pL : offR + lane - pL;
-			if (valid) dstp[idx] = e[c];
-			offL += nL; offR += nv - nL;
-		}
+		if (cnt - b <= 64) partition_tail<E, 2>(srcp, dstp, fbits, b, cnt, lane, lt, offL, offR, keepL, keepR);
+		else partition_tail<E, PL_CH>(srcp, dstp, fbits, b, cnt, lane, lt, offL, offR, keepL, keepR);
 	}
 }
 
@@ -814,18 +888,31 @@ void launch_build_lists(const TrainArgs& A, cudaStream_t s) {
 int launch_init_trees(const TrainArgs& A, cudaStream_t s) {
 	size_t smem = tree_smem_bytes(A.m, A.mtry);
 	if (smem > 48 * 1024) {
-		if (cudaFuncSetAttribute(init_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-		if (cudaFuncSetAttribute(level_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+		if (allow_max_dyn_smem(init_trees_kernel) != cudaSuccess) return -1;
+		if (allow_max_dyn_smem(level_finalize_kernel) != cudaSuccess) return -1;
 	}
 	init_trees_kernel<<<A.nTrees, 32, smem, s>>>(A);
 	return 0;
 }
-void launch_split_search(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
-	size_t warps = (size_t)nItems * A.mtry;
-	(void)warps;
-	const dim3 grid((nItems * 32 + 127) / 128, A.mtry);   // x: nodes (one warp each), y: candidate
-	if (A.entry32) split_search_kernel<uint32_t, 32><<<grid, 128, 0, s>>>(A, nItems, buf);
-	else split_search_kernel<unsigned long long, 32><<<grid, 128, 0, s>>>(A, nItems, buf);
+// one launch per non-empty size class (kernels.cuh: size_class); clsCount[k] = items in clsItems[buf][k]
+void launch_split_search(const TrainArgs& A, const uint32_t* clsCount, int buf, cudaStream_t s) {
+	for (int k = 0; k < NCLS; k++) {
+		const uint32_t nl = clsCount[k];
+		if (nl == 0) continue;
+		const uint32_t* list = A.clsItems[buf][k];
+		const uint32_t G = k == 0 ? 8u : k == 1 ? 16u : 32u;
+		const dim3 grid((unsigned)(((size_t)nl * G + 127) / 128), A.mtry);   // x: nodes (G lanes each), y: candidate
+#define PSM_SS(E)                                                                                            \
+	do {                                                                                                     \
+		if (k == 0) split_search_kernel<E, 8, false><<<grid, 128, 0, s>>>(A, list, nl, buf);                 \
+		else if (k == 1) split_search_kernel<E, 16, false><<<grid, 128, 0, s>>>(A, list, nl, buf);           \
+		else if (k == 2) split_search_kernel<E, 32, false><<<grid, 128, 0, s>>>(A, list, nl, buf);           \
+		else split_search_kernel<E, 32, true><<<grid, 128, 0, s>>>(A, list, nl, buf);                        \
+	} while (0)
+		if (A.entry32) PSM_SS(uint32_t);
+		else PSM_SS(unsigned long long);
+#undef PSM_SS
+	}
 }
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
 	if (A.entry32) split_select_kernel<uint32_t><<<(nItems + 3) / 4, 128, 0, s>>>(A, nItems, buf);
@@ -836,10 +923,10 @@ int launch_tree_flags(const TrainArgs& A, cudaStream_t s) {
 	const int inSmem = bytes <= 160 * 1024;   // 1.3M rows per tree; beyond that the bitmap is updated in place in global memory
 	const size_t smem = inSmem ? bytes : 0;
 	if (A.entry32) {
-		if (smem > 48 * 1024 && cudaFuncSetAttribute(tree_flags_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+		if (smem > 48 * 1024 && allow_max_dyn_smem(tree_flags_kernel<uint32_t>) != cudaSuccess) return -1;
 		tree_flags_kernel<uint32_t><<<A.nTrees, TF_THREADS, smem, s>>>(A, inSmem);
 	} else {
-		if (smem > 48 * 1024 && cudaFuncSetAttribute(tree_flags_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+		if (smem > 48 * 1024 && allow_max_dyn_smem(tree_flags_kernel<unsigned long long>) != cudaSuccess) return -1;
 		tree_flags_kernel<unsigned long long><<<A.nTrees, TF_THREADS, smem, s>>>(A, inSmem);
 	}
 	return 0;
@@ -847,20 +934,13 @@ int launch_tree_flags(const TrainArgs& A, cudaStream_t s) {
 void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s) {
 	level_finalize_kernel<<<A.nTrees, 32, tree_smem_bytes(A.m, A.mtry), s>>>(A, buf);
 }
+// one launch over all work items in item order (neighbouring segments of a list stay neighbours in time: launching the
+// partition per size class like split search measured 8% slower -- the short segments lose the sector sharing with their
+// neighbours -- so the per-size variants are dispatched inside the kernel instead)
 void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
-	size_t warps = (size_t)nItems * A.m;
-	(void)warps;
-	const dim3 grid((nItems * 32 + 127) / 128, A.m);   // x: nodes (one warp each), y: feature
-	// long segments (the first levels) keep more chunks in flight per warp; short ones would only pay for the predicated slots
-	static const int longCh = getenv("PSM_PL_LONG_CH") ? atoi(getenv("PSM_PL_LONG_CH")) : 0;   // off: one variant serves every level (measured below)
-	static const int longAvg = getenv("PSM_PL_LONG_AVG") ? atoi(getenv("PSM_PL_LONG_AVG")) : 512;
-	const bool longSegs = longCh && (uint64_t)nItems * longAvg <= (uint64_t)A.nTrees * A.stride;   // average segment >= ~0.63 * longAvg in-bag entries
-	if (A.entry32) {
-		if (longSegs && longCh == 6) partition_lists_kernel<uint32_t, 6><<<grid, 128, 0, s>>>(A, nItems, buf);
-		else if (longSegs && longCh == 8) partition_lists_kernel<uint32_t, 8><<<grid, 128, 0, s>>>(A, nItems, buf);
-		else if (longSegs && longCh == 4) partition_lists_kernel<uint32_t, 4><<<grid, 128, 0, s>>>(A, nItems, buf);
-		else partition_lists_kernel<uint32_t, PL_CH_DEFAULT><<<grid, 128, 0, s>>>(A, nItems, buf);
-	} else partition_lists_kernel<unsigned long long, PL_CH_DEFAULT><<<grid, 128, 0, s>>>(A, nItems, buf);
+	const dim3 grid((unsigned)(((size_t)nItems * 32 + 127) / 128), A.m);   // x: nodes (one warp each), y: feature
+	if (A.entry32) partition_lists_kernel<uint32_t, PL_CH_DEFAULT><<<grid, 128, 0, s>>>(A, nItems, buf);
+	else partition_lists_kernel<unsigned long long, PL_CH_DEFAULT><<<grid, 128, 0, s>>>(A, nItems, buf);
 }
 
 }  // namespace psm

@@ -11,14 +11,17 @@
 #include <sstream>
 #include <thread>
 
+#include <atomic>
 #include <chrono>
+#include <exception>
 
 namespace parsmurf {
 
 double g_phase[PH_COUNT] = {0};
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 PhaseScope::PhaseScope(int p) : ph(p), t0(now_s()) {}
-PhaseScope::~PhaseScope() { g_phase[ph] += now_s() - t0; }
+static std::mutex g_phaseMtx;   // fold lanes account their phases concurrently (the sums then exceed the wall time)
+PhaseScope::~PhaseScope() { const double dt = now_s() - t0; std::lock_guard<std::mutex> lk(g_phaseMtx); g_phase[ph] += dt; }
 
 // ------------------------------------------------------------------------------------------ GlibcRand
 // glibc stdlib/random_r.c: TYPE_3 (x^31 + x^3 + 1), seeded through the 16807 Park-Miller LCG, first 310 discarded
@@ -252,7 +255,7 @@ void Partition::setFold(uint32_t f) {
 }
 
 // ------------------------------------------------------------------------------------------ Device
-Device::Device(int device, void* cudaStream) {
+Device::Device(int device, void* cudaStream) : deviceId(device) {
 	int rc = psm_ctx_create(device, &ctx);
 	if (rc) throw Error(rc, "parsmurf_b200: no usable CUDA device (there is no CPU fallback)");
 	if (cudaStream) check(psm_set_stream(ctx, cudaStream));
@@ -261,6 +264,13 @@ Device::~Device() { if (ctx) psm_ctx_destroy(ctx); }
 void Device::check(int rc) const { if (rc) throw Error(rc, psm_last_error(ctx)); }
 void Device::upload(const double* x, uint32_t n_, uint32_t m_) { check(psm_dataset_upload(ctx, x, n_, m_)); n = n_; m = m_; foldTag = nullptr; }
 void Device::attachDevice(const double* x, uint32_t n_, uint32_t m_) { check(psm_dataset_attach_device(ctx, x, n_, m_)); n = n_; m = m_; foldTag = nullptr; }
+void Device::setLaneCount(uint32_t lanes) {
+	while (laneCount() < lanes) {
+		std::unique_ptr<Device> d(new Device(deviceId, nullptr));
+		d->check(psm_ctx_own_stream(d->ctx));
+		extra.push_back(std::move(d));
+	}
+}
 void Device::ensureFold(const Partition* part) {
 	if (foldTag == (const void*)part->ttd && foldId == part->currentFold) return;
 	check(psm_fold_begin(ctx, part->trngPosIdx, part->trngPosNum, part->trngNegIdx, part->trngNegNum, part->testPosIdx, part->testPosNum,
@@ -509,12 +519,16 @@ void hyperSMURF::smurfIt() {                                                // s
 	// caller's host arrays once, at the end
 	dev->check(psm_labels_upload(dev->ctx, y.data(), nn));
 	dev->check(psm_scores_reset(dev->ctx));
+	// fold lanes only where every fold runs with the same parameters and nothing is flushed to the host between folds
+	const uint32_t lanesHere = (wmode == MODE_CV && woptimiz == OPT_NO && !(commonParams->customCV && !inInternalCV) && endingFold > startingFold + 1)
+	                               ? std::min<uint32_t>(std::max<uint32_t>(foldLanes, 1), endingFold - startingFold) : 1;
 
 	for (uint32_t currentFold = startingFold; currentFold < endingFold; currentFold++) {
 		if (woptimiz == OPT_GRID) {                                         // :176-228 grid exploration on the inner folds
 			hyperSMURF inner(commonParams, gridParams, foldManager, dev, y, tempcl1.data(), tempcl2.data(), rng);
 			inner.setSharding(rank, world, reduce);
 			inner.curvesTieMode = curvesTieMode;
+			inner.foldLanes = foldLanes;
 			inner.initInternalCV(currentFold);
 			std::string statFileName = "fold" + std::to_string(currentFold) + ".dat";
 			for (uint32_t i = 0; i < gridParams.size(); i++) {
@@ -546,61 +560,8 @@ void hyperSMURF::smurfIt() {                                                // s
 			nPart = g.nParts; fp = g.fp; ratio = g.ratio; k = g.k; numTrees = g.nTrees; mtry = g.mtry;
 			part->nPart = nPart; part->fp = fp; part->ratio = ratio;
 		}
-		{ PhaseScope ps(PH_FOLDS_TTD); part->setFold(currentFold); }      // :255 (waits for the fold's background build + shuffle)
-		dev->invalidateFold();
-		{ PhaseScope ps(PH_FOLD_BEGIN); dev->ensureFold(part.get()); }
-
-		// this rank's contiguous chunk of partitions (src/MPIHelper.cpp:29-37)
-		uint32_t cnt = nPart / world + ((nPart % world) > rank ? 1 : 0);
-		uint32_t first = 0;
-		for (uint32_t r2 = 0; r2 < rank; r2++) first += nPart / world + ((nPart % world) > r2 ? 1 : 0);
-		const uint32_t last = first + cnt;
-		const uint64_t perPartDraws = (uint64_t)part->trngPosNum * fp * (mm + 1);
-		auto skipDraws = [&](uint64_t count) { rng->discard(count); };      // keep the one SMOTE stream in partition order on every rank
-		{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * first); }
-		uint32_t cap = 1;
-		if (cnt) dev->check(psm_batch_capacity(dev->ctx, nPart, fp, ratio, numTrees, mtry, first, &cap));
-		for (uint32_t b0 = first; b0 < last; b0 += cap) {                   // the `#pragma omp for` over partitions (:257-261), as batches
-			const uint32_t b1 = std::min(last, b0 + cap);
-			SamplerKNN samp(part.get(), wmode, dev, mm, nn, k, rng);        // :275
-			samp.setPartitionRange(b0, b1);                                 // :276
-			samp.sample();                                                  // :277
-			rfRanger rf(dev, mm, false, &samp, numTrees, mtry, commonParams->rfThr, seed + currentFold * nPart);   // :273,302
-			{ PhaseScope ps(PH_TRAIN); rf.train(commonParams->rfVerbose); }   // :303
-			if (wmode == MODE_TRAIN) {                                      // :349-360 training only: one forest file per partition
-				for (uint32_t p = b0; p < b1; p++) rf.saveForest(p, commonParams->forestDirname);
-				continue;
-			}
-			samp.copyTestSet();                                             // :316
-			rfRanger rfTest(dev, mm, true, &samp, numTrees, mtry, commonParams->rfThr, 2 * (seed + currentFold * nPart));   // :330
-			{ PhaseScope ps(PH_PREDICT); rfTest.predict(commonParams->rfVerbose); dev->check(psm_sync(dev->ctx)); }   // :331
-			samp.accumulateAndDivideResInProbVect(nPart);                   // :344-346 (done on the device by predict)
-		}
-		{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * (nPart - last)); }
-		if (wmode == MODE_TRAIN) continue;                                   // nothing was predicted
-		if (world > 1 && reduce) {
-			PhaseScope ps(PH_REDUCE);                                          // src/hyperSMURF_MPI.cpp:594-618
-			double* ptr = nullptr; uint32_t nte = 0;
-			dev->check(psm_fold_scores_devptr(dev->ctx, &ptr, &nte));
-			dev->check(psm_sync(dev->ctx));
-			reduce(ptr, 2ull * nte);
-		}
-		{ PhaseScope ps(PH_SCATTER); dev->check(psm_fold_scatter_device(dev->ctx)); }   // :344-346 scatter by example id, on the device
-
-		if (woptimiz != OPT_NO) {                                          // grid mode: flush this fold's scores to the host now (see above)
-			PhaseScope ps(PH_SCATTER);
-			dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob));
-			dev->check(psm_scores_reset(dev->ctx));
-		}
-		if (evalFoldCurves && !inInternalCV) {                              // :365-396 per-fold AUROC / AUPRC (labels y[idx], scores class1Prob[idx])
-			PhaseScope ps(PH_CURVES);
-			double r2[2];
-			dev->check(psm_fold_curves(dev->ctx, curvesTieMode, r2));       // Curves(tempLabels, tempPreds): AUROC first, then AUPRC (:382-384)
-			foldAuroc[currentFold] = r2[0];
-			foldAuprc[currentFold] = r2[1];
-			if (verboseLevel > VERBSILENT && rank == 0)
-				std::cout << "External CV on fold " << currentFold << " -> AUROC: " << foldAuroc[currentFold] << " - AUPRC: " << foldAuprc[currentFold] << std::endl;
-		}
+		if (lanesHere > 1) { runFoldsInLanes(startingFold, endingFold, lanesHere); break; }
+		runFold(currentFold, dev, part.get(), rng, nullptr);
 	}
 
 	if (wmode == MODE_TRAIN) return;
@@ -624,6 +585,146 @@ void hyperSMURF::smurfIt() {                                                // s
 		auprc = r2[1];
 		if (verboseLevel > VERBSILENT && rank == 0) std::cout << "AUROC: " << auroc << " - AUPRC: " << auprc << std::endl;
 	}
+}
+
+// one fold of the CV loop (src/hyperSMURF.cpp:255-396) on Device lane `d`: `prt` is this lane's Partition view, `r` the
+// rand() replica positioned at the fold's first SMOTE draw
+struct hyperSMURF::FoldGate {
+	std::mutex m;
+	std::condition_variable cv;
+	std::vector<int> state;            // per fold: 0 running, 1 scores ready for the cross-rank reduce, 2 reduced
+	std::vector<double*> ptr;
+	std::vector<uint64_t> count;
+	bool failed = false;
+};
+
+void hyperSMURF::runFold(uint32_t currentFold, Device* d, Partition* prt, GlibcRand* r, FoldGate* gate) {
+	{ PhaseScope ps(PH_FOLDS_TTD); prt->setFold(currentFold); }      // :255 (waits for the fold's background build + shuffle)
+	d->invalidateFold();
+	{ PhaseScope ps(PH_FOLD_BEGIN); d->ensureFold(prt); }
+
+	// this rank's contiguous chunk of partitions (src/MPIHelper.cpp:29-37)
+	uint32_t cnt = nPart / world + ((nPart % world) > rank ? 1 : 0);
+	uint32_t first = 0;
+	for (uint32_t r2 = 0; r2 < rank; r2++) first += nPart / world + ((nPart % world) > r2 ? 1 : 0);
+	const uint32_t last = first + cnt;
+	const uint64_t perPartDraws = (uint64_t)prt->trngPosNum * fp * (mm + 1);
+	auto skipDraws = [&](uint64_t count) { r->discard(count); };      // keep the one SMOTE stream in partition order on every rank
+	{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * first); }
+	uint32_t cap = 1;
+	if (cnt) d->check(psm_batch_capacity(d->ctx, nPart, fp, ratio, numTrees, mtry, first, &cap));
+	for (uint32_t b0 = first; b0 < last; b0 += cap) {                   // the `#pragma omp for` over partitions (:257-261), as batches
+		const uint32_t b1 = std::min(last, b0 + cap);
+		SamplerKNN samp(prt, wmode, d, mm, nn, k, r);                   // :275
+		samp.setPartitionRange(b0, b1);                                 // :276
+		samp.sample();                                                  // :277
+		rfRanger rf(d, mm, false, &samp, numTrees, mtry, commonParams->rfThr, seed + currentFold * nPart);   // :273,302
+		{ PhaseScope ps(PH_TRAIN); rf.train(commonParams->rfVerbose); }   // :303
+		if (wmode == MODE_TRAIN) {                                      // :349-360 training only: one forest file per partition
+			for (uint32_t p = b0; p < b1; p++) rf.saveForest(p, commonParams->forestDirname);
+			continue;
+		}
+		samp.copyTestSet();                                             // :316
+		rfRanger rfTest(d, mm, true, &samp, numTrees, mtry, commonParams->rfThr, 2 * (seed + currentFold * nPart));   // :330
+		{ PhaseScope ps(PH_PREDICT); rfTest.predict(commonParams->rfVerbose); d->check(psm_sync(d->ctx)); }   // :331
+		samp.accumulateAndDivideResInProbVect(nPart);                   // :344-346 (done on the device by predict)
+	}
+	{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * (nPart - last)); }
+	if (wmode == MODE_TRAIN) return;                                     // nothing was predicted
+	if (world > 1 && reduce) {
+		PhaseScope ps(PH_REDUCE);                                          // src/hyperSMURF_MPI.cpp:594-618
+		double* ptr = nullptr; uint32_t nte = 0;
+		d->check(psm_fold_scores_devptr(d->ctx, &ptr, &nte));
+		d->check(psm_sync(d->ctx));
+		if (!gate) reduce(ptr, 2ull * nte);
+		else {
+			// fold lanes: every rank must issue its collectives in the same order, so the calling thread of smurfIt does
+			// the reduces in fold order (runFoldsInLanes) and this lane waits for its turn
+			std::unique_lock<std::mutex> lk(gate->m);
+			gate->ptr[currentFold] = ptr; gate->count[currentFold] = 2ull * nte; gate->state[currentFold] = 1;
+			gate->cv.notify_all();
+			gate->cv.wait(lk, [&] { return gate->state[currentFold] == 2 || gate->failed; });
+			if (gate->failed) throw Error(PSM_E_CUDA, "hyperSMURF: another fold lane failed");
+		}
+	}
+	{ PhaseScope ps(PH_SCATTER); d->check(psm_fold_scatter_device(d->ctx)); }   // :344-346 scatter by example id, on the device
+
+	if (woptimiz != OPT_NO) {                                          // grid mode: flush this fold's scores to the host now (see above)
+		PhaseScope ps(PH_SCATTER);
+		d->check(psm_scores_get(d->ctx, class1Prob, class2Prob));
+		d->check(psm_scores_reset(d->ctx));
+	}
+	if (evalFoldCurves && !inInternalCV) {                              // :365-396 per-fold AUROC / AUPRC (labels y[idx], scores class1Prob[idx])
+		PhaseScope ps(PH_CURVES);
+		double r2[2];
+		d->check(psm_fold_curves(d->ctx, curvesTieMode, r2));       // Curves(tempLabels, tempPreds): AUROC first, then AUPRC (:382-384)
+		foldAuroc[currentFold] = r2[0];
+		foldAuprc[currentFold] = r2[1];
+		if (verboseLevel > VERBSILENT && rank == 0)
+			std::cout << "External CV on fold " << currentFold << " -> AUROC: " << foldAuroc[currentFold] << " - AUPRC: " << foldAuprc[currentFold] << std::endl;
+	}
+}
+
+void hyperSMURF::runFoldsInLanes(uint32_t startingFold, uint32_t endingFold, uint32_t lanes) {
+	dev->setLaneCount(lanes);
+	// where every fold starts in the one SMOTE rand() stream: a fold consumes nPart * P_fold * fp * (m+1) draws whatever
+	// share of its partitions this rank assembles (runFold skips the others), and P_fold is known before anything is built
+	std::vector<uint64_t> off(endingFold + 1, 0);
+	for (uint32_t f = startingFold; f < endingFold; f++) off[f + 1] = off[f] + (uint64_t)nPart * ttd->trngPosNum[f] * fp * (mm + 1);
+	const GlibcRand base = *rng;
+	const double* xdev = nullptr;
+	dev->check(psm_dataset_devptr(dev->ctx, &xdev));
+	std::atomic<uint32_t> next(startingFold);
+	FoldGate gate;
+	gate.state.assign(endingFold, 0); gate.ptr.assign(endingFold, nullptr); gate.count.assign(endingFold, 0);
+	const bool gated = world > 1 && (bool)reduce;
+	std::exception_ptr err;
+	auto fail = [&]() {
+		std::lock_guard<std::mutex> lk(gate.m);
+		if (!err) err = std::current_exception();
+		gate.failed = true;
+		gate.cv.notify_all();
+	};
+	auto worker = [&](uint32_t li) {
+		try {
+			Device* d = dev->lane(li);
+			d->check(psm_ctx_bind_thread(d->ctx));
+			if (li) {                                                          // the extra lanes borrow lane 0's copy of x and keep their own score arrays
+				d->attachDevice(xdev, nn, mm);
+				d->check(psm_labels_upload(d->ctx, y.data(), nn));
+				d->check(psm_scores_reset(d->ctx));
+			}
+			Partition prt(foldManager, ttd.get(), nPart, fp, ratio, mm, nn);
+			for (;;) {
+				const uint32_t f = next.fetch_add(1);
+				if (f >= endingFold) break;
+				{ std::lock_guard<std::mutex> lk(gate.m); if (gate.failed) break; }
+				GlibcRand r = base;
+				r.discard(off[f]);
+				runFold(f, d, &prt, &r, gated ? &gate : nullptr);
+			}
+			d->check(psm_sync(d->ctx));
+		} catch (...) { fail(); }
+	};
+	std::vector<std::thread> threads;
+	for (uint32_t li = 0; li < lanes; li++) threads.emplace_back(worker, li);
+	if (gated) {
+		for (uint32_t f = startingFold; f < endingFold; f++) {                  // cross-rank reduces in fold order, on the caller's thread
+			std::unique_lock<std::mutex> lk(gate.m);
+			gate.cv.wait(lk, [&] { return gate.state[f] == 1 || gate.failed; });
+			if (gate.failed) break;
+			double* p = gate.ptr[f]; const uint64_t c = gate.count[f];
+			lk.unlock();
+			try { reduce(p, c); } catch (...) { fail(); break; }
+			lk.lock();
+			gate.state[f] = 2;
+			gate.cv.notify_all();
+		}
+	}
+	for (auto& t : threads) t.join();
+	if (err) std::rethrow_exception(err);
+	rng->discard(off[endingFold]);
+	for (uint32_t li = 1; li < lanes; li++) dev->check(psm_scores_merge(dev->ctx, dev->lane(li)->ctx));
 }
 
 // predict mode (src/hyperSMURF.cpp:401-446): every example is a test row of fold 0; partition p is predicted by the forest
@@ -805,6 +906,19 @@ extern "C" {
 
 typedef int (*psmh_reduce_fn)(void* user, double* dev_ptr, uint64_t count);
 
+// Fold lanes of the CV entry points (hyperSMURF::foldLanes): psmh_set_fold_lanes(n) fixes the count for this process,
+// otherwise the environment variable PSM_FOLD_LANES, otherwise kDefaultFoldLanes.
+static constexpr uint32_t kDefaultFoldLanes = 4;
+static std::atomic<uint32_t> g_foldLanes{0};
+void psmh_set_fold_lanes(uint32_t lanes) { g_foldLanes = lanes; }
+static uint32_t fold_lanes_default();
+uint32_t psmh_get_fold_lanes(void) { return fold_lanes_default(); }
+static uint32_t fold_lanes_default() {
+	uint32_t v = g_foldLanes.load();
+	if (v == 0) { const char* e = getenv("PSM_FOLD_LANES"); v = e ? (uint32_t)atoi(e) : kDefaultFoldLanes; }
+	return std::min<uint32_t>(std::max<uint32_t>(v, 1), 16);
+}
+
 // Whole CV through the host classes, like parSMURF1's main (src/parSMURF.cpp:97-106) with data already in memory.
 // foldAssign == NULL -> random stratified folds (src/folds.cpp:27-77).  metrics = {auroc, auprc}; foldMetrics [nFolds][2] or NULL.
 // x_is_device != 0: `x` is a device pointer (dataset already resident in HBM).
@@ -822,11 +936,18 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		if (!devHandle) owned.reset(new Device(device, stream));
 		Device& dev = devHandle ? *(Device*)devHandle : *owned;
 		if (devHandle && stream) dev.check(psm_set_stream(dev.ctx, stream));
-		dev.check(psm_profile_reset(dev.ctx));
-		if (batchBudget) dev.check(psm_set_batch_budget(dev.ctx, batchBudget));
-		// profile: 0 off, 1 every kernel class, 2 only split search (the kernel the roofline is reported on)
-		dev.check(psm_profile_classes(dev.ctx, profile == 2 ? (1u << 5) : 0xFFFFFFFFu));
-		dev.check(psm_profile_enable(dev.ctx, profile != 0));
+		const uint32_t lanes = mode == MODE_CV ? std::min<uint32_t>(fold_lanes_default(), std::max<uint32_t>(nFolds, 1)) : 1;
+		dev.setLaneCount(lanes);
+		for (uint32_t li = 0; li < dev.laneCount(); li++) {
+			Device* d = dev.lane(li);
+			d->check(psm_profile_reset(d->ctx));
+			// every lane holds its own partition batch: keep the sum of the budgets within one GPU's memory
+			const uint64_t perLane = batchBudget ? batchBudget : std::min<uint64_t>(24ull << 30, (120ull << 30) / lanes);
+			d->check(psm_set_batch_budget(d->ctx, perLane));
+			// profile: 0 off, 1 every kernel class, 2 only split search (the kernel the roofline is reported on)
+			d->check(psm_profile_classes(d->ctx, profile == 2 ? (1u << 5) : 0xFFFFFFFFu));
+			d->check(psm_profile_enable(d->ctx, profile != 0));
+		}
 		GlibcRand rng(1);
 		struct Pooled {                                     // label / fold-id copies live in recycled buffers too
 			std::vector<uint32_t> v;
@@ -843,6 +964,7 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		gp[0] = GridParams{nParts, fp, ratio, k, nTrees, mtry, 0, 0};
 		hyperSMURF smurfer(&cp, gp, &folds, &dev, y, class1, class2, &rng);
 		smurfer.curvesTieMode = tieMode; smurfer.evalFoldCurves = evalFoldCurves != 0;
+		smurfer.foldLanes = lanes;
 		if (world > 1) smurfer.setSharding(rank, world, [&](double* p, uint64_t c) { if (reduce && reduce(reduceUser, p, c)) throw Error(PSM_E_CUDA, "reduce callback failed"); });
 		smurfer.initStandard();                             // starts the per-fold index builders in the background ...
 		tSetup = now_s();
@@ -851,8 +973,17 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		smurfer.smurfIt();
 		if (metrics) { metrics[0] = smurfer.auroc; metrics[1] = smurfer.auprc; }
 		if (foldMetrics && mode == MODE_CV) for (uint32_t f = 0; f < nFolds; f++) { foldMetrics[2 * f] = smurfer.foldAuroc[f]; foldMetrics[2 * f + 1] = smurfer.foldAuprc[f]; }
-		if (kernelMs || kernelLaunches) dev.check(psm_profile_get(dev.ctx, kernelMs, kernelLaunches));
-		if (stats3) dev.check(psm_stats_get(dev.ctx, &stats3[0], &stats3[1], &stats3[2]));
+		if (kernelMs) for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) kernelMs[i] = 0;
+		if (kernelLaunches) for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) kernelLaunches[i] = 0;
+		if (stats3) stats3[0] = stats3[1] = stats3[2] = 0;
+		for (uint32_t li = 0; li < dev.laneCount(); li++) {                  // kernel times / counts / byte statistics summed over the fold lanes
+			Device* d = dev.lane(li);
+			double ms[PSM_NUM_KERNEL_CLASSES]; uint64_t ln[PSM_NUM_KERNEL_CLASSES]; uint64_t st[3];
+			d->check(psm_profile_get(d->ctx, ms, ln));
+			d->check(psm_stats_get(d->ctx, &st[0], &st[1], &st[2]));
+			for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) { if (kernelMs) kernelMs[i] += ms[i]; if (kernelLaunches) kernelLaunches[i] += ln[i]; }
+			if (stats3) for (int i = 0; i < 3; i++) stats3[i] += st[i];
+		}
 		if (phases) for (int i = 0; i < PH_COUNT; i++) phases[i] = g_phase[i];
 		return 0;
 	} catch (const parsmurf::Error& e) {
@@ -908,6 +1039,7 @@ int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* la
 		for (uint32_t i = 0; i < G; i++) gp[i] = GridParams{grid[6 * i], grid[6 * i + 1], grid[6 * i + 2], grid[6 * i + 3], grid[6 * i + 4], grid[6 * i + 5], 0, 0};
 		hyperSMURF smurfer(&cp, gp, &folds, &dev, y, class1, class2, &rng);
 		smurfer.curvesTieMode = tieMode;
+		smurfer.foldLanes = std::min<uint32_t>(fold_lanes_default(), nFolds > 1 ? nFolds - 1 : 1);   // the inner CVs run their folds in lanes
 		smurfer.initStandard();
 		dev.upload(x, n, m);
 		smurfer.smurfIt();

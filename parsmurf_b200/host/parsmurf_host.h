@@ -146,7 +146,14 @@ public:
 	void ensureKnn(uint32_t k);
 	void invalidateFold() { foldTag = nullptr; }
 	void check(int rc) const;
+	// fold lanes: lane 0 is this context; lanes 1.. are extra contexts on the same GPU with private streams, created on
+	// demand and kept for the life of the Device (their buffers are reused like this one's)
+	void setLaneCount(uint32_t lanes);
+	uint32_t laneCount() const { return 1 + (uint32_t)extra.size(); }
+	Device* lane(uint32_t i) { return i == 0 ? this : extra[i - 1].get(); }
 	psm_ctx* ctx = nullptr;
+	int deviceId = 0;
+	std::vector<std::unique_ptr<Device>> extra;
 	uint32_t n = 0, m = 0;
 	const void* foldTag = nullptr;
 	uint32_t foldId = (uint32_t)-1, knnK = 0;
@@ -247,11 +254,19 @@ public:
 	void setSharding(uint32_t rank, uint32_t world, std::function<void(double* dev_ptr, uint64_t count)> reduce);
 	int curvesTieMode = 0;
 	bool evalFoldCurves = true;
+	// Folds of a CV are independent until the score merge: with foldLanes > 1 that many folds are in flight at once, each
+	// on its own Device lane (context + stream) driven by its own host thread, so one fold's host-side work and its
+	// latency-bound deep tree levels overlap the other folds' kernels.  Results are identical to foldLanes = 1: the
+	// SMOTE rand() position of every fold is known up front (jump-ahead) and cross-rank reduces stay in fold order.
+	uint32_t foldLanes = 1;
 	std::vector<double> foldAuroc, foldAuprc;
 	double auroc = 0, auprc = 0;
 
 private:
+	struct FoldGate;
 	void predictIt();
+	void runFold(uint32_t currentFold, Device* d, Partition* prt, GlibcRand* r, FoldGate* gate);
+	void runFoldsInLanes(uint32_t startingFold, uint32_t endingFold, uint32_t lanes);
 	const CommonParams* const commonParams;
 	std::vector<GridParams>& gridParams;
 	Folds* const foldManager;

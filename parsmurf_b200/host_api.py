@@ -22,6 +22,9 @@ def hlib():
         L = C.CDLL(_capi.HOST_LIB_PATH)
         L.psmh_cv_run.argtypes = [vp, C.c_int, u32, u32, u32p, u32p] + [u32] * 8 + [C.c_int, vp, C.c_int, C.c_int, u32, u32, REDUCE_FN, vp, u64,
                                   C.c_int, dp, dp, dp, dp, dp, u64p, u64p, dp, vp, C.c_char_p, C.c_size_t]
+        L.psmh_set_fold_lanes.argtypes = [u32]
+        L.psmh_set_fold_lanes.restype = None
+        L.psmh_get_fold_lanes.restype = u32
         L.psmh_device_create.restype = vp
         L.psmh_device_create.argtypes = [C.c_int, vp]
         L.psmh_device_destroy.argtypes = [vp]
@@ -34,7 +37,8 @@ def hlib():
 
 
 def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, device=0, stream=None, tie_mode=0, eval_fold_curves=True,
-           rank=0, world=1, reduce=None, batch_budget=0, profile=False, x_device_ptr=None, n=None, m=None, dev_handle=None, out=None):
+           rank=0, world=1, reduce=None, batch_budget=0, profile=False, x_device_ptr=None, n=None, m=None, dev_handle=None, out=None,
+           fold_lanes=None):
     """Run the whole CV on one GPU (or this rank's share of the partitions when world > 1).
 
     x: host row-major float64 [n][m+1] (label column 1.0/2.0), or None with x_device_ptr/n/m for a dataset already in HBM.
@@ -42,8 +46,11 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     reduce(dev_ptr, count): sums `count` float64 at device pointer `dev_ptr` across ranks in place (world > 1).
     out: optional (class1, class2) float64 arrays of length n to reuse; they are zeroed and filled (a fresh 8 MB array costs
     more in first-touch page faults than the copy into it).
+    fold_lanes: how many folds are in flight at once (one context + stream + host thread each, same results); None keeps the
+    library default (PSM_FOLD_LANES or 4).  Kernel times / launch counts are summed over the lanes.
     Returns dict(class1, class2, auroc, auprc, fold_metrics, kernel_ms, kernel_launches, stats)."""
     L = hlib()
+    L.psmh_set_fold_lanes(0 if fold_lanes is None else int(fold_lanes))
     if x is not None:
         assert x.dtype == np.float64 and x.flags.c_contiguous
         n, m = x.shape[0], x.shape[1] - 1
@@ -79,7 +86,7 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     return dict(class1=c1, class2=c2, auroc=float(met[0]), auprc=float(met[1]), fold_metrics=fm,
                 kernel_ms={k_: float(kms[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
                 kernel_launches={k_: int(kl[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
-                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2])),
+                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2])), fold_lanes=min(int(L.psmh_get_fold_lanes()), max(int(nFolds), 1)),
                 host_phases_s={k_: float(ph[i]) for i, k_ in enumerate(PHASES)})
 
 

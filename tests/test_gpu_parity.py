@@ -106,6 +106,42 @@ def test_cv_through_host_classes_bit_exact(oracle):
         assert np.array_equal(out2["class1"].view(np.uint64), o1.view(np.uint64)), name
 
 
+def test_fold_lanes_give_identical_bits(oracle):
+    """folds in flight concurrently (one context + stream + host thread per lane) == folds one after the other, bit for bit:
+    scores, per-fold and global curves; also for a rank's share of a sharded run (the gated reduce path)"""
+    from parsmurf_b200 import host_api as H
+    for name in ("fy_26", "ties_ratio0"):
+        case = make_case(name)
+        x = oracle.make_x(case["X"], case["y"])
+        args = (x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
+        one = H.cv_run(*args, tie_mode=0, fold_lanes=1)
+        for lanes in (2, 3, 8):
+            out = H.cv_run(*args, tie_mode=0, fold_lanes=lanes)
+            assert np.array_equal(out["class1"].view(np.uint64), one["class1"].view(np.uint64)), (name, lanes)
+            assert np.array_equal(out["class2"].view(np.uint64), one["class2"].view(np.uint64)), (name, lanes)
+            assert np.array_equal(out["fold_metrics"], one["fold_metrics"]) and out["auroc"] == one["auroc"] and out["auprc"] == one["auprc"]
+            assert out["stats"] == one["stats"] and out["kernel_launches"]["split_search"] == one["kernel_launches"]["split_search"]
+        calls = []
+        a1 = H.cv_run(*args, tie_mode=0, rank=1, world=2, reduce=lambda ptr, count: None, eval_fold_curves=False, fold_lanes=1)
+        a3 = H.cv_run(*args, tie_mode=0, rank=1, world=2, reduce=lambda ptr, count: calls.append(count), eval_fold_curves=False, fold_lanes=3)
+        assert np.array_equal(a1["class1"].view(np.uint64), a3["class1"].view(np.uint64)), name
+        assert len(calls) == case["nF"]            # one reduce per fold, issued from the calling thread in fold order
+
+
+def test_size_classes_do_not_change_the_trees(oracle, monkeypatch):
+    """split search / list partition launched per size class (sub-warp groups for short segments) vs one generic launch"""
+    from parsmurf_b200 import host_api as H
+    case = make_case("fy_26")
+    x = oracle.make_x(case["X"], case["y"])
+    args = (x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
+    a = H.cv_run(*args, tie_mode=0)
+    monkeypatch.setenv("PSM_NO_SIZE_CLASSES", "1")
+    b = H.cv_run(*args, tie_mode=0)
+    assert np.array_equal(a["class1"].view(np.uint64), b["class1"].view(np.uint64))
+    assert a["stats"] == b["stats"]
+    assert a["kernel_launches"]["split_search"] > b["kernel_launches"]["split_search"] == b["stats"]["levels"]
+
+
 def test_two_rank_shares_on_one_gpu(oracle):
     """partition sharding (rank r of 2 handles its contiguous chunk and skips the other rank's SMOTE draws): the two
     partial results add up to the single-rank CV; emulated as two sequential runs on one GPU, no collective needed"""
