@@ -170,7 +170,9 @@ def run_reference(args, w):
 def workload_config(args, w):
     return {"workload": "BASELINE.json %s: synthetic %dx%d imbalanced 1:%d, nParts=%d, fp=%d, ratio=%d, k=%d, nTrees=%d, mtry=%d, %d-fold CV"
             % ({"cfg2": "configs[1]", "cfg3": "configs[2]", "cfg4": "configs[3]"}.get(args.workload, args.workload), w["n"], w["m"], w["n"] // w["npos"], w["nParts"], w["fp"], w["ratio"], w["k"], w["nTrees"], w["mtry"], w["nFolds"]),
-            "partitions_per_step": w["nParts"] * w["nFolds"], "parallelism": "partitions sharded over %d GPU(s), dataset replicated, one NCCL all-reduce of fold scores per fold" % args.gpus,
+            "partitions_per_step": w["nParts"] * w["nFolds"], "parallelism": ("single GPU" if args.gpus == 1 else
+                            "%d GPUs, dataset replicated, %s" % (args.gpus, "contiguous ranges of the nFolds x nParts (fold, partition) units per rank, ONE NCCL all-reduce of the score arrays [2n] f64 at the end (+ one of the per-fold metrics)"
+                                                                if args.shard != "fold" else "every rank takes its chunk of every fold's partitions (the reference's MPI rule), one NCCL all-reduce of the fold scores per fold")),
             "l2_policy": "inputs larger than L2 (dataset 216 MB + per-fold training batch ~2.7 GB >> 126 MB L2); no explicit flush",
             "curves_tie_mode": "device radix sort (stable)"}
 
@@ -210,7 +212,7 @@ def run_ours(args, w):
     # per-kernel events, the roofline kernel is timed in its own region below with the folds one after the other
     common = dict(labels=y, folds=f, nFolds=w["nFolds"], nParts=w["nParts"], fp=w["fp"], ratio=w["ratio"], k=w["k"], nTrees=w["nTrees"], mtry=w["mtry"],
                   seed=w["seed"], device=local, stream=stream.cuda_stream, tie_mode=1, eval_fold_curves=True, rank=rank, world=world,
-                  reduce=reduce if world > 1 else None, profile=0, fold_lanes=args.fold_lanes)
+                  reduce=reduce if world > 1 else None, profile=0, fold_lanes=args.fold_lanes, shard=args.shard)
 
     def barrier():
         if world > 1:
@@ -321,6 +323,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fold-lanes", type=int, default=None, help="folds in flight at once (default: the library's)")
+    ap.add_argument("--shard", default="unit", choices=["unit", "fold"], help="multi-GPU sharding rule (see host_api.cv_run)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -133,6 +133,18 @@ int psm_fold_scatter_device(psm_ctx* ctx);
 int psm_fold_curves(psm_ctx* ctx, int tie_mode, double* out);
 int psm_scores_get(psm_ctx* ctx, double* class1Prob, double* class2Prob);
 int psm_scores_curves(psm_ctx* ctx, int tie_mode, double* out);
+/* Unit-sharded multi-GPU runs (every rank owns a contiguous range of the nFolds x nParts (fold, partition) units and only
+ * opens the folds it has units of): the per-rank partial class1Prob/class2Prob[n] arrays are summed ONCE, in place, through
+ * psm_scores_devptr (device pointer of [2][n] f64), and the per-fold AUROC/AUPRC (src/hyperSMURF.cpp:365-396) are then
+ * computed from the summed arrays for the fold whose test rows are given (positives first, then negatives).
+ * psm_scratch_f64 returns a small zeroed device buffer that psm_scratch_write / psm_scratch_read fill and read back, so
+ * that a few host doubles (per-fold metrics) can go through the same device all-reduce as the scores. */
+int psm_scores_devptr(psm_ctx* ctx, double** class12Prob_dev, uint32_t* n);
+int psm_scores_fold_curves(psm_ctx* ctx, const uint32_t* testPosIdx, uint32_t testPosNum, const uint32_t* testNegIdx,
+                           uint32_t testNegNum, int tie_mode, double* out);
+int psm_scratch_f64(psm_ctx* ctx, uint32_t count, double** dev);
+int psm_scratch_write(psm_ctx* ctx, const double* host, uint32_t count);
+int psm_scratch_read(psm_ctx* ctx, double* host, uint32_t count);
 
 /* ---- (9) curves: Curves ctor + evalAUROC_ok + evalAUPRC (src/curves.cpp:7-36,77-122). out = {auroc, auprc}.
  *      tie_mode 0: descending order from the identical host std::sort call (bit-parity with the reference's

@@ -81,7 +81,7 @@ struct psm_ctx {
 	bool haveLabels = false, foldLabelsReady = false;
 
 	// curves
-	DevBuf cLabels, cPerm, cSorted, cTp, cPartials, cOut, cScores, cKeysA, cKeysB, cValsA, cValsB, cHist;
+	DevBuf cIdx, cFoldScores, cScratch, cLabels, cPerm, cSorted, cTp, cPartials, cOut, cScores, cKeysA, cKeysB, cValsA, cValsB, cHist;
 
 	// profiling
 	bool profOn = false;
@@ -185,7 +185,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
 	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dSplitFeat, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1, &ctx->dCls,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dPtask, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
-	                  &ctx->dInjCand, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
+	                  &ctx->dInjCand, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cIdx, &ctx->cFoldScores, &ctx->cScratch, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
 	                  &ctx->cScores, &ctx->cKeysA, &ctx->cKeysB, &ctx->cValsA, &ctx->cValsB, &ctx->cHist};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& p : ctx->profPending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -903,6 +903,52 @@ int psm_scores_curves(psm_ctx* ctx, int tie_mode, double* out) {
 	uint32_t totP = 0, totN = 0;
 	for (uint32_t i = 0; i < ctx->n; i++) { totP += ctx->hLabels[i] == 1; totN += ctx->hLabels[i] == 0; }
 	return curves_core(ctx, ctx->dLabels.as<uint32_t>(), ctx->dGlob.as<double>(), nullptr, ctx->n, totP, totN, tie_mode, out);
+}
+
+int psm_scores_devptr(psm_ctx* ctx, double** dev, uint32_t* n) {
+	if (!ctx || !ctx->haveLabels || !dev || !n) return fail(ctx, PSM_E_ARG, "scores_devptr: no device scores");
+	*dev = ctx->dGlob.as<double>();
+	*n = ctx->n;
+	return PSM_OK;
+}
+
+int psm_scores_fold_curves(psm_ctx* ctx, const uint32_t* testPosIdx, uint32_t nTP, const uint32_t* testNegIdx, uint32_t nTN, int tie_mode, double* out) {
+	const uint64_t N = (uint64_t)nTP + nTN;
+	if (!ctx || !ctx->haveLabels || !out || N == 0 || (nTP && !testPosIdx) || (nTN && !testNegIdx)) return fail(ctx, PSM_E_ARG, "scores_fold_curves: bad arguments");
+	CU(cudaSetDevice(ctx->device));
+	ENSURE(ctx->cIdx, N * 4); ENSURE(ctx->cFoldScores, N * 8); ENSURE(ctx->dFoldLabels, N * 4);
+	uint32_t totP = 0, totN = 0;
+	for (uint32_t i = 0; i < nTP; i++) { if (testPosIdx[i] >= ctx->n) return fail(ctx, PSM_E_ARG, "scores_fold_curves: index out of range"); const uint32_t l = ctx->hLabels[testPosIdx[i]]; totP += l == 1; totN += l == 0; }
+	for (uint32_t i = 0; i < nTN; i++) { if (testNegIdx[i] >= ctx->n) return fail(ctx, PSM_E_ARG, "scores_fold_curves: index out of range"); const uint32_t l = ctx->hLabels[testNegIdx[i]]; totP += l == 1; totN += l == 0; }
+	if (nTP) CU(cudaMemcpyAsync(ctx->cIdx.p, testPosIdx, (size_t)nTP * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (nTN) CU(cudaMemcpyAsync(ctx->cIdx.as<uint32_t>() + nTP, testNegIdx, (size_t)nTN * 4, cudaMemcpyHostToDevice, ctx->stream));
+	{
+		ProfScope ps(ctx, K_GATHER, 2);
+		launch_gather_u32(ctx->dLabels.as<uint32_t>(), ctx->cIdx.as<uint32_t>(), N, ctx->dFoldLabels.as<uint32_t>(), ctx->stream);
+		launch_gather_f64(ctx->dGlob.as<double>(), ctx->cIdx.as<uint32_t>(), N, ctx->cFoldScores.as<double>(), ctx->stream);   // class1Prob[idx]
+	}
+	return curves_core(ctx, ctx->dFoldLabels.as<uint32_t>(), ctx->cFoldScores.as<double>(), nullptr, N, totP, totN, tie_mode, out);   // syncs: the index arrays are only borrowed
+}
+
+int psm_scratch_f64(psm_ctx* ctx, uint32_t count, double** dev) {
+	if (!ctx || !dev || count == 0) return fail(ctx, PSM_E_ARG, "scratch_f64: bad arguments");
+	CU(cudaSetDevice(ctx->device));
+	ENSURE(ctx->cScratch, (size_t)count * 8);
+	CU(cudaMemsetAsync(ctx->cScratch.p, 0, (size_t)count * 8, ctx->stream));
+	*dev = ctx->cScratch.as<double>();
+	return PSM_OK;
+}
+int psm_scratch_write(psm_ctx* ctx, const double* host, uint32_t count) {
+	if (!ctx || !host || (size_t)count * 8 > ctx->cScratch.cap) return fail(ctx, PSM_E_ARG, "scratch_write: bad arguments");
+	CU(cudaMemcpyAsync(ctx->cScratch.p, host, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return PSM_OK;
+}
+int psm_scratch_read(psm_ctx* ctx, double* host, uint32_t count) {
+	if (!ctx || !host || (size_t)count * 8 > ctx->cScratch.cap) return fail(ctx, PSM_E_ARG, "scratch_read: bad arguments");
+	CU(cudaMemcpyAsync(host, ctx->cScratch.p, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return PSM_OK;
 }
 
 // ------------------------------------------------------------------------------------------ convenience

@@ -35,6 +35,14 @@ void launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint64_t N, uin
 	if (!N) return;
 	gather_u32_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(src, idx, N, out);
 }
+__global__ void gather_f64_kernel(const double* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t N, double* __restrict__ out) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < N) out[i] = src[idx[i]];
+}
+void launch_gather_f64(const double* src, const uint32_t* idx, uint64_t N, double* out, cudaStream_t s) {
+	if (!N) return;
+	gather_f64_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(src, idx, N, out);
+}
 // classXProb[testIdx[i]] += fold scores (sampler.cpp:121-132 scatter by original example id)
 __global__ void scatter_scores_kernel(const double* __restrict__ class12, const uint32_t* __restrict__ testIdx, uint32_t Nte, uint32_t n,
                                       double* __restrict__ glob) {

@@ -20,6 +20,12 @@ namespace parsmurf {
 double g_phase[PH_COUNT] = {0};
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 PhaseScope::PhaseScope(int p) : ph(p), t0(now_s()) {}
+// PSM_TIMELINE=1: wall-clock marks of one run (ms since its start), printed by the C entry point -- shows where a rank of
+// a multi-GPU run waits
+static std::vector<std::pair<std::string, double>> g_marks;
+static std::mutex g_markMtx;
+static const bool g_trace = getenv("PSM_TIMELINE") != nullptr;
+static void trace_mark(const std::string& what) { if (!g_trace) return; std::lock_guard<std::mutex> lk(g_markMtx); g_marks.emplace_back(what, now_s()); }
 static std::mutex g_phaseMtx;   // fold lanes account their phases concurrently (the sums then exceed the wall time)
 PhaseScope::~PhaseScope() { const double dt = now_s() - t0; std::lock_guard<std::mutex> lk(g_phaseMtx); g_phase[ph] += dt; }
 
@@ -166,52 +172,42 @@ void Folds::computeFolds() {
 }
 
 // ------------------------------------------------------------------------------------------ TestTrainDivider
-void TestTrainDivider::build(uint32_t i, uint32_t cur, int64_t jump) {
+static void ttd_blk(std::vector<uint32_t>& dst, const std::vector<uint32_t>& src, const std::vector<uint32_t>& off, uint32_t f) {
+	dst.insert(dst.end(), src.begin() + off[f], src.begin() + off[f + 1]);
+}
+void TestTrainDivider::buildTest(uint32_t i, uint32_t cur) {
 	const Folds* F = folds;
-	auto blk = [](std::vector<uint32_t>& dst, const std::vector<uint32_t>& src, const std::vector<uint32_t>& off, uint32_t f) {
-		dst.insert(dst.end(), src.begin() + off[f], src.begin() + off[f + 1]);
-	};
-	const uint32_t jumpPos = jump >= 0 ? F->nPos[jump] : 0, jumpNeg = jump >= 0 ? F->nNeg[jump] : 0;
 	testPosIdx[i] = g_pool.take(F->nPos[cur]); testNegIdx[i] = g_pool.take(F->nNeg[cur]);
+	ttd_blk(testPosIdx[i], F->posList, F->posOff, cur); ttd_blk(testNegIdx[i], F->negList, F->negOff, cur);
+}
+void TestTrainDivider::buildTrain(uint32_t i, uint32_t cur, int64_t jump) {
+	const Folds* F = folds;
+	const uint32_t jumpPos = jump >= 0 ? F->nPos[jump] : 0, jumpNeg = jump >= 0 ? F->nNeg[jump] : 0;
 	trngPosIdx[i] = g_pool.take(F->totPos - F->nPos[cur] - jumpPos); trngNegIdx[i] = g_pool.take(F->totNeg - F->nNeg[cur] - jumpNeg);
-	blk(testPosIdx[i], F->posList, F->posOff, cur); blk(testNegIdx[i], F->negList, F->negOff, cur);
 	for (uint32_t kf = 0; kf < F->nFolds; kf++) {                            // ascending fold order, as src/testtraindivider.cpp:57-80
 		if (kf == cur || (int64_t)kf == jump) continue;
-		blk(trngPosIdx[i], F->posList, F->posOff, kf); blk(trngNegIdx[i], F->negList, F->negOff, kf);
+		ttd_blk(trngPosIdx[i], F->posList, F->posOff, kf); ttd_blk(trngNegIdx[i], F->negList, F->negOff, kf);
 	}
 }
 
 // src/testtraindivider.cpp:5-106
-TestTrainDivider::TestTrainDivider(const Folds* folds_, uint8_t wmode_, GlibcRand* rng) : folds(folds_), wmode(wmode_), nFolds(folds_->nFolds) {
+TestTrainDivider::TestTrainDivider(const Folds* folds_, uint8_t wmode_, GlibcRand* rng) : folds(folds_), wmode(wmode_), nFolds(folds_->nFolds), lazy(true), start(*rng) {
 	testPosIdx.resize(nFolds); testNegIdx.resize(nFolds); trngPosIdx.resize(nFolds); trngNegIdx.resize(nFolds);
+	testState.assign(nFolds, 0); trainState.assign(nFolds, 0);
 	// Fold i's std::random_shuffle (:90) consumes trngNeg_i - 1 rand() calls, so its place in the one rand() stream is known
-	// up front; with the generator's jump-ahead the folds are built concurrently and still shuffle exactly like the
-	// sequential reference.
-	std::vector<uint64_t> off(nFolds + 1, 0);
+	// up front; with the generator's jump-ahead the folds are built independently of each other (concurrently, or not at
+	// all) and still shuffle exactly like the sequential reference.
+	shuffleOff.assign(nFolds + 1, 0);
 	for (uint32_t i = 0; i < nFolds; i++) {
 		uint64_t nneg = folds->totNeg - folds->nNeg[i];
-		off[i + 1] = off[i] + (nneg > 0 ? nneg - 1 : 0);
+		shuffleOff[i + 1] = shuffleOff[i] + (nneg > 0 ? nneg - 1 : 0);
 	}
 	for (uint32_t i = 0; i < nFolds; i++) {                                  // counts are known without building anything
 		testPosNum.push_back(folds->nPos[i]); testNegNum.push_back(folds->nNeg[i]);
 		trngPosNum.push_back(folds->totPos - folds->nPos[i]); trngNegNum.push_back(folds->totNeg - folds->nNeg[i]);
 	}
 	if (wmode == MODE_TRAIN) { trngPosNum[0] = testPosNum[0]; trngNegNum[0] = testNegNum[0]; }   // :33-36
-	// Fold f is needed ~one fold of GPU work after fold f-1, so one thread building them in order keeps fold 0's latency
-	// at a single build + shuffle and never competes with itself for cores.
-	const GlibcRand start = *rng;
-	worker = std::thread([this, start, off]() {
-		for (uint32_t i = 0; i < nFolds; i++) {
-			GlibcRand local = start;
-			local.discard(off[i]);
-			build(i, i, -1);
-			local.shuffle(trngNegIdx[i].data(), trngNegIdx[i].size());      // :90
-			if (this->wmode == MODE_TRAIN && i == 0) { trngPosIdx[0] = testPosIdx[0]; trngNegIdx[0] = testNegIdx[0]; }   // :101-104
-			{ std::lock_guard<std::mutex> lk(mtx); nReady = i + 1; }
-			cv.notify_all();
-		}
-	});
-	rng->discard(off[nFolds]);
+	rng->discard(shuffleOff[nFolds]);
 }
 
 TestTrainDivider::~TestTrainDivider() {
@@ -219,10 +215,49 @@ TestTrainDivider::~TestTrainDivider() {
 	for (auto* vv : {&testPosIdx, &testNegIdx, &trngPosIdx, &trngNegIdx})
 		for (auto& v : *vv) g_pool.give(v);
 }
-void TestTrainDivider::ensure(uint32_t fold) const {
-	if (!worker.joinable()) return;                                         // inner-CV constructor builds synchronously
+
+void TestTrainDivider::prefetch(std::vector<uint32_t> order) {
+	if (!lazy || worker.joinable()) return;
+	worker = std::thread([this, order]() { for (uint32_t f : order) if (f < nFolds) ensure(f); });
+}
+
+void TestTrainDivider::ensureTest(uint32_t fold) const {
+	if (!lazy) return;                                                      // inner-CV constructor builds synchronously
 	std::unique_lock<std::mutex> lk(mtx);
-	cv.wait(lk, [&] { return nReady > fold || nReady >= nFolds; });
+	if (testState[fold] == 0) {
+		testState[fold] = 1;
+		lk.unlock();
+		const_cast<TestTrainDivider*>(this)->buildTest(fold, fold);
+		lk.lock();
+		testState[fold] = 2;
+		cv.notify_all();
+	} else {
+		cv.wait(lk, [&] { return testState[fold] == 2; });
+	}
+}
+
+void TestTrainDivider::ensure(uint32_t fold) const {
+	if (!lazy) return;
+	ensureTest(fold);
+	std::unique_lock<std::mutex> lk(mtx);
+	if (trainState[fold] == 0) {
+		trainState[fold] = 1;
+		lk.unlock();
+		TestTrainDivider* self = const_cast<TestTrainDivider*>(this);
+		if (wmode == MODE_TRAIN && fold == 0) {                              // :101-104 training on everything: the "training" arrays are the fold itself
+			self->trngPosIdx[0] = testPosIdx[0]; self->trngNegIdx[0] = testNegIdx[0];
+		} else {
+			self->buildTrain(fold, fold, -1);
+			GlibcRand local = start;
+			local.discard(shuffleOff[fold]);
+			local.shuffle(self->trngNegIdx[fold].data(), self->trngNegIdx[fold].size());   // :90
+		}
+		lk.lock();
+		trainState[fold] = 2;
+		cv.notify_all();
+	} else {
+		cv.wait(lk, [&] { return trainState[fold] == 2; });
+	}
 }
 
 // src/testtraindivider.cpp:126-236 -- inner CV: fold `foldToJump` is left out entirely, no shuffle
@@ -231,7 +266,8 @@ TestTrainDivider::TestTrainDivider(const Folds* folds_, uint8_t wmode_, uint32_t
 	uint32_t cur = 0;
 	for (uint32_t i = 0; i < nFolds; i++) {
 		if (cur == foldToJump) cur++;
-		build(i, cur, foldToJump);
+		buildTest(i, cur);
+		buildTrain(i, cur, foldToJump);
 		cur++;
 	}
 	for (uint32_t i = 0; i < nFolds; i++) {
@@ -492,6 +528,20 @@ void hyperSMURF::initStandard() {                                           // s
 	wmode = commonParams->wmode; woptimiz = commonParams->woptimiz; inInternalCV = false;
 	{ PhaseScope ps(PH_FOLDS_TTD); ttd.reset(new TestTrainDivider(foldManager, wmode, rng)); }
 	part.reset(new Partition(foldManager, ttd.get(), nPart, fp, ratio, mm, nn));
+	// start building the folds this rank will train on, in the order it will need them (overlaps the upload of x)
+	uint32_t f0 = 0, f1 = nFolds;
+	if (commonParams->minFold != (uint32_t)-1) f0 = commonParams->minFold;
+	if (commonParams->maxFold != (uint32_t)-1) f1 = std::min(commonParams->maxFold, nFolds);
+	std::vector<uint32_t> order;
+	for (uint32_t f = f0; f < f1; f++) {
+		uint32_t a = 0, b = 0;
+		partRange(willShardUnits(), f1 - f0, nPart, world, rank, f - f0, &a, &b);
+		if (b > a || !willShardUnits()) order.push_back(f);
+	}
+	ttd->prefetch(order);
+}
+bool hyperSMURF::willShardUnits() const {
+	return shardUnits && world > 1 && (bool)reduce && commonParams->wmode == MODE_CV && commonParams->woptimiz == OPT_NO && !inInternalCV && !commonParams->customCV;
 }
 void hyperSMURF::initInternalCV(uint32_t jump) {                            // src/hyperSMURF.cpp:53-78
 	nn = commonParams->nn; mm = commonParams->mm; nFolds = commonParams->nFolds - 1;
@@ -520,6 +570,8 @@ void hyperSMURF::smurfIt() {                                                // s
 	dev->check(psm_labels_upload(dev->ctx, y.data(), nn));
 	dev->check(psm_scores_reset(dev->ctx));
 	// fold lanes only where every fold runs with the same parameters and nothing is flushed to the host between folds
+	foldBase = startingFold; foldsRun = endingFold - startingFold;
+	unitMode = willShardUnits();
 	const uint32_t lanesHere = (wmode == MODE_CV && woptimiz == OPT_NO && !(commonParams->customCV && !inInternalCV) && endingFold > startingFold + 1)
 	                               ? std::min<uint32_t>(std::max<uint32_t>(foldLanes, 1), endingFold - startingFold) : 1;
 
@@ -560,12 +612,48 @@ void hyperSMURF::smurfIt() {                                                // s
 			nPart = g.nParts; fp = g.fp; ratio = g.ratio; k = g.k; numTrees = g.nTrees; mtry = g.mtry;
 			part->nPart = nPart; part->fp = fp; part->ratio = ratio;
 		}
-		if (lanesHere > 1) { runFoldsInLanes(startingFold, endingFold, lanesHere); break; }
-		runFold(currentFold, dev, part.get(), rng, nullptr);
+		if (lanesHere > 1 || unitMode) { runFoldsInLanes(startingFold, endingFold, lanesHere); trace_mark("lanes joined, scores merged"); break; }
+		uint32_t first = 0, last = 0;
+		partRange(false, foldsRun, nPart, world, rank, currentFold - foldBase, &first, &last);
+		runFold(currentFold, first, last, dev, part.get(), rng, nullptr);
 	}
 
 	if (wmode == MODE_TRAIN) return;
+	if (unitMode) {
+		{
+			PhaseScope ps(PH_REDUCE);                                          // the one cross-rank sum of a unit-sharded CV
+			double* ptr = nullptr; uint32_t cntN = 0;
+			dev->check(psm_scores_devptr(dev->ctx, &ptr, &cntN));
+			dev->check(psm_sync(dev->ctx));
+			trace_mark("own work done (stream drained)");
+			reduce(ptr, 2ull * cntN);
+			trace_mark("scores all-reduced");
+		}
+		if (evalFoldCurves) {                                               // :365-396 per-fold AUROC / AUPRC, fold f on rank f % world
+			PhaseScope ps(PH_CURVES);
+			std::vector<double> fm(2 * (size_t)nFolds, 0.0);
+			for (uint32_t f = startingFold; f < endingFold; f++) {
+				if ((f - startingFold) % world != rank) continue;
+				ttd->ensureTest(f);
+				double r2[2];
+				dev->check(psm_scores_fold_curves(dev->ctx, ttd->testPosIdx[f].data(), ttd->testPosNum[f], ttd->testNegIdx[f].data(), ttd->testNegNum[f], curvesTieMode, r2));
+				fm[2 * f] = r2[0]; fm[2 * f + 1] = r2[1];
+			}
+			double* sp = nullptr;
+			dev->check(psm_scratch_f64(dev->ctx, 2 * nFolds, &sp));
+			dev->check(psm_scratch_write(dev->ctx, fm.data(), 2 * nFolds));
+			reduce(sp, 2ull * nFolds);
+			dev->check(psm_scratch_read(dev->ctx, fm.data(), 2 * nFolds));
+			for (uint32_t f = startingFold; f < endingFold; f++) {
+				foldAuroc[f] = fm[2 * f]; foldAuprc[f] = fm[2 * f + 1];
+				if (verboseLevel > VERBSILENT && rank == 0)
+					std::cout << "External CV on fold " << f << " -> AUROC: " << foldAuroc[f] << " - AUPRC: " << foldAuprc[f] << std::endl;
+			}
+		}
+	}
+	trace_mark("fold curves done");
 	{ PhaseScope ps(PH_SCATTER); dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob)); }
+	trace_mark("scores on the host");
 	if (inInternalCV) {                                                     // :456-482
 		std::vector<uint32_t> tl; std::vector<double> tp;
 		for (uint32_t f = 0; f < nFolds; f++) {
@@ -598,16 +686,27 @@ struct hyperSMURF::FoldGate {
 	bool failed = false;
 };
 
-void hyperSMURF::runFold(uint32_t currentFold, Device* d, Partition* prt, GlibcRand* r, FoldGate* gate) {
+void hyperSMURF::partRange(bool units, uint32_t nFoldsRun, uint32_t nPart, uint32_t world, uint32_t rank, uint32_t foldIdx, uint32_t* first, uint32_t* last) {
+	auto chunk = [&](uint64_t total, uint64_t* a, uint64_t* b) {           // total/world (+1 for the first total%world ranks), contiguous
+		const uint64_t base = total / world, rem = total % world;
+		*a = base * rank + std::min<uint64_t>(rank, rem);
+		*b = *a + base + (rank < rem ? 1 : 0);
+	};
+	uint64_t a, b;
+	if (!units) { chunk(nPart, &a, &b); *first = (uint32_t)a; *last = (uint32_t)b; return; }
+	chunk((uint64_t)nFoldsRun * nPart, &a, &b);
+	const uint64_t f0 = (uint64_t)foldIdx * nPart, f1 = f0 + nPart;
+	const uint64_t lo = std::max(a, f0), hi = std::min(b, f1);
+	if (lo >= hi) { *first = *last = 0; return; }
+	*first = (uint32_t)(lo - f0); *last = (uint32_t)(hi - f0);
+}
+
+// partitions [first, last) of fold `currentFold` (this rank's share of it, or one piece of the share)
+void hyperSMURF::runFold(uint32_t currentFold, uint32_t first, uint32_t last, Device* d, Partition* prt, GlibcRand* r, FoldGate* gate) {
+	const uint32_t cnt = last - first;
 	{ PhaseScope ps(PH_FOLDS_TTD); prt->setFold(currentFold); }      // :255 (waits for the fold's background build + shuffle)
 	d->invalidateFold();
 	{ PhaseScope ps(PH_FOLD_BEGIN); d->ensureFold(prt); }
-
-	// this rank's contiguous chunk of partitions (src/MPIHelper.cpp:29-37)
-	uint32_t cnt = nPart / world + ((nPart % world) > rank ? 1 : 0);
-	uint32_t first = 0;
-	for (uint32_t r2 = 0; r2 < rank; r2++) first += nPart / world + ((nPart % world) > r2 ? 1 : 0);
-	const uint32_t last = first + cnt;
 	const uint64_t perPartDraws = (uint64_t)prt->trngPosNum * fp * (mm + 1);
 	auto skipDraws = [&](uint64_t count) { r->discard(count); };      // keep the one SMOTE stream in partition order on every rank
 	{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * first); }
@@ -631,6 +730,11 @@ void hyperSMURF::runFold(uint32_t currentFold, Device* d, Partition* prt, GlibcR
 	}
 	{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * (nPart - last)); }
 	if (wmode == MODE_TRAIN) return;                                     // nothing was predicted
+	if (unitMode) {                                                      // partial fold scores -> this rank's class1Prob/class2Prob; summed once at the end
+		PhaseScope ps(PH_SCATTER);
+		d->check(psm_fold_scatter_device(d->ctx));
+		return;
+	}
 	if (world > 1 && reduce) {
 		PhaseScope ps(PH_REDUCE);                                          // src/hyperSMURF_MPI.cpp:594-618
 		double* ptr = nullptr; uint32_t nte = 0;
@@ -671,13 +775,32 @@ void hyperSMURF::runFoldsInLanes(uint32_t startingFold, uint32_t endingFold, uin
 	// share of its partitions this rank assembles (runFold skips the others), and P_fold is known before anything is built
 	std::vector<uint64_t> off(endingFold + 1, 0);
 	for (uint32_t f = startingFold; f < endingFold; f++) off[f + 1] = off[f] + (uint64_t)nPart * ttd->trngPosNum[f] * fp * (mm + 1);
+	// the pieces of work the lanes take, in order: this rank's share of every fold; unit sharding cuts a share further
+	struct Piece { uint32_t fold, first, last; };
+	std::vector<Piece> pieces;
+	{
+		uint64_t mine = 0;
+		for (uint32_t f = startingFold; f < endingFold; f++) {
+			uint32_t a = 0, b = 0;
+			partRange(unitMode, foldsRun, nPart, world, rank, f - foldBase, &a, &b);
+			mine += b - a;
+		}
+		const uint32_t maxPiece = unitMode ? (uint32_t)std::max<uint64_t>(32, (mine + lanes - 1) / lanes) : nPart;
+		for (uint32_t f = startingFold; f < endingFold; f++) {
+			uint32_t a = 0, b = 0;
+			partRange(unitMode, foldsRun, nPart, world, rank, f - foldBase, &a, &b);
+			if (!unitMode) { pieces.push_back({f, a, b}); continue; }          // fold rule: one piece per fold, even an empty one (its reduce still happens)
+			const uint32_t np = (b - a + maxPiece - 1) / maxPiece;              // equal pieces of the fold share
+			for (uint32_t i = 0; i < np; i++) pieces.push_back({f, a + (uint32_t)((uint64_t)(b - a) * i / np), a + (uint32_t)((uint64_t)(b - a) * (i + 1) / np)});
+		}
+	}
 	const GlibcRand base = *rng;
 	const double* xdev = nullptr;
 	dev->check(psm_dataset_devptr(dev->ctx, &xdev));
-	std::atomic<uint32_t> next(startingFold);
+	std::atomic<uint32_t> next(0);
 	FoldGate gate;
 	gate.state.assign(endingFold, 0); gate.ptr.assign(endingFold, nullptr); gate.count.assign(endingFold, 0);
-	const bool gated = world > 1 && (bool)reduce;
+	const bool gated = world > 1 && (bool)reduce && !unitMode;
 	std::exception_ptr err;
 	auto fail = [&]() {
 		std::lock_guard<std::mutex> lk(gate.m);
@@ -696,12 +819,16 @@ void hyperSMURF::runFoldsInLanes(uint32_t startingFold, uint32_t endingFold, uin
 			}
 			Partition prt(foldManager, ttd.get(), nPart, fp, ratio, mm, nn);
 			for (;;) {
-				const uint32_t f = next.fetch_add(1);
-				if (f >= endingFold) break;
+				const uint32_t pi = next.fetch_add(1);
+				if (pi >= pieces.size()) break;
 				{ std::lock_guard<std::mutex> lk(gate.m); if (gate.failed) break; }
+				const Piece& pc = pieces[pi];
 				GlibcRand r = base;
-				r.discard(off[f]);
-				runFold(f, d, &prt, &r, gated ? &gate : nullptr);
+				r.discard(off[pc.fold]);
+				const std::string tag = "lane " + std::to_string(li) + " fold " + std::to_string(pc.fold) + " [" + std::to_string(pc.first) + "," + std::to_string(pc.last) + ")";
+				trace_mark(tag + " begin");
+				runFold(pc.fold, pc.first, pc.last, d, &prt, &r, gated ? &gate : nullptr);
+				trace_mark(tag + " end");
 			}
 			d->check(psm_sync(d->ctx));
 		} catch (...) { fail(); }
@@ -911,6 +1038,19 @@ typedef int (*psmh_reduce_fn)(void* user, double* dev_ptr, uint64_t count);
 static constexpr uint32_t kDefaultFoldLanes = 4;
 static std::atomic<uint32_t> g_foldLanes{0};
 void psmh_set_fold_lanes(uint32_t lanes) { g_foldLanes = lanes; }
+// Sharding rule of multi-rank CV runs (hyperSMURF::shardUnits): psmh_set_shard_units(1 / 0) fixes it for this process (-1 =
+// back to the default), otherwise PSM_SHARD=unit|fold, otherwise unit sharding.
+static std::atomic<int> g_shardUnits{-1};
+void psmh_set_shard_units(int v) { g_shardUnits = v; }
+static bool shard_units_default() {
+	const int v = g_shardUnits.load();
+	if (v >= 0) return v != 0;
+	const char* e = getenv("PSM_SHARD");
+	return !(e && std::string(e) == "fold");
+}
+void psmh_part_range(int units, uint32_t nFoldsRun, uint32_t nPart, uint32_t world, uint32_t rank, uint32_t foldIdx, uint32_t* first, uint32_t* last) {
+	parsmurf::hyperSMURF::partRange(units != 0, nFoldsRun, nPart, world, rank, foldIdx, first, last);
+}
 static uint32_t fold_lanes_default();
 uint32_t psmh_get_fold_lanes(void) { return fold_lanes_default(); }
 static uint32_t fold_lanes_default() {
@@ -932,6 +1072,8 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 	try {
 		for (int i = 0; i < PH_COUNT; i++) g_phase[i] = 0;
 		double tSetup = now_s();
+		{ std::lock_guard<std::mutex> lk(g_markMtx); g_marks.clear(); }
+		trace_mark("start");
 		std::unique_ptr<Device> owned;
 		if (!devHandle) owned.reset(new Device(device, stream));
 		Device& dev = devHandle ? *(Device*)devHandle : *owned;
@@ -957,6 +1099,7 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		std::vector<uint32_t>& y = yBuf.v; std::vector<uint32_t>& ff = ffBuf.v;
 		Folds folds(nFolds, n, y.data(), ff, foldAssign == nullptr, &rng);
 		{ PhaseScope ps(PH_FOLDS_TTD); folds.computeFolds(); }
+		trace_mark("folds computed");
 		CommonParams cp;
 		cp.nn = n; cp.mm = m; cp.nFolds = nFolds; cp.seed = seed; cp.wmode = (uint8_t)mode; cp.woptimiz = OPT_NO;
 		if (forestDir) cp.forestDirname = forestDir;
@@ -965,12 +1108,22 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		hyperSMURF smurfer(&cp, gp, &folds, &dev, y, class1, class2, &rng);
 		smurfer.curvesTieMode = tieMode; smurfer.evalFoldCurves = evalFoldCurves != 0;
 		smurfer.foldLanes = lanes;
+		smurfer.shardUnits = shard_units_default();
 		if (world > 1) smurfer.setSharding(rank, world, [&](double* p, uint64_t c) { if (reduce && reduce(reduceUser, p, c)) throw Error(PSM_E_CUDA, "reduce callback failed"); });
 		smurfer.initStandard();                             // starts the per-fold index builders in the background ...
 		tSetup = now_s();
 		if (x_is_device) dev.attachDevice(x, n, m); else dev.upload(x, n, m);   // ... which overlap the H2D copy of x
 		g_phase[PH_SETUP] += now_s() - tSetup;
+		trace_mark("dataset attached");
 		smurfer.smurfIt();
+		trace_mark("smurfIt done");
+		if (g_trace) {
+			std::lock_guard<std::mutex> lk(g_markMtx);
+			std::string line = "[psm timeline rank " + std::to_string(rank) + "]";
+			char buf[96];
+			for (auto& mk : g_marks) { snprintf(buf, sizeof buf, " %.2f", 1e3 * (mk.second - g_marks[0].second)); line += " | " + mk.first + buf; }
+			fprintf(stderr, "%s\n", line.c_str());
+		}
 		if (metrics) { metrics[0] = smurfer.auroc; metrics[1] = smurfer.auprc; }
 		if (foldMetrics && mode == MODE_CV) for (uint32_t f = 0; f < nFolds; f++) { foldMetrics[2 * f] = smurfer.foldAuroc[f]; foldMetrics[2 * f + 1] = smurfer.foldAuprc[f]; }
 		if (kernelMs) for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) kernelMs[i] = 0;

@@ -102,20 +102,29 @@ public:
 	TestTrainDivider(const Folds* folds, uint8_t wmode, GlibcRand* rng);
 	TestTrainDivider(const Folds* folds, uint8_t wmode, uint32_t foldToJump);
 	~TestTrainDivider();
-	// the per-fold index arrays are built (and shuffled) in fold order by one background thread; the counts are valid
-	// immediately, the arrays of fold f after ensure(f)
+	// The counts are valid immediately; the index arrays of fold f after ensure(f) (test + shuffled training arrays) or
+	// ensureTest(f) (test arrays only).  A fold is built by whoever asks first -- the calling thread (fold lanes build their
+	// folds concurrently) or the prefetch thread, which walks the folds given to prefetch() in order, one fold ahead of a
+	// caller that consumes them one after the other.  Only folds somebody asks for are ever built: a rank of a unit-sharded
+	// run touches one or two of them.
 	void ensure(uint32_t fold) const;
+	void ensureTest(uint32_t fold) const;
+	void prefetch(std::vector<uint32_t> foldsInOrder);
 	const Folds* const folds;
 	const uint8_t wmode;
 	uint32_t nFolds;
 	std::vector<std::vector<uint32_t>> testPosIdx, testNegIdx, trngPosIdx, trngNegIdx;
 	std::vector<uint32_t> testPosNum, testNegNum, trngPosNum, trngNegNum;
 private:
-	void build(uint32_t i, uint32_t currFoldIdx, int64_t foldToJump);
-	mutable std::thread worker;
+	void buildTest(uint32_t i, uint32_t currFoldIdx);
+	void buildTrain(uint32_t i, uint32_t currFoldIdx, int64_t foldToJump);
+	std::thread worker;                       // prefetch
 	mutable std::mutex mtx;
 	mutable std::condition_variable cv;
-	uint32_t nReady = 0;   // folds [0, nReady) are complete (guarded by mtx)
+	mutable std::vector<uint8_t> testState, trainState;   // per fold: 0 not built, 1 being built, 2 ready (guarded by mtx)
+	bool lazy = false;                        // outer-CV constructor: folds are built on demand
+	GlibcRand start;                          // rand() state before the first fold's shuffle
+	std::vector<uint64_t> shuffleOff;         // where fold i's shuffle starts in that stream
 };
 
 // reference src/partition.h:7-36
@@ -252,6 +261,17 @@ public:
 	// sums the fold score buffer [2*Nte] f64 across ranks in place (the MPI_Gather + master sum of
 	// src/hyperSMURF_MPI.cpp:594-618).  Default: single rank, no reduce.
 	void setSharding(uint32_t rank, uint32_t world, std::function<void(double* dev_ptr, uint64_t count)> reduce);
+	// How the work of a plain CV is cut between the ranks.  false: the reference's MPI rule -- every rank takes its
+	// contiguous chunk of the partitions of EVERY fold and the fold scores are summed once per fold.  true (unit sharding):
+	// the nFolds x nParts (fold, partition) units are cut into `world` contiguous ranges, so a rank opens only the one or two
+	// folds it has units of (their index upload, kNN and fold set-up are not repeated on every rank, and its partition
+	// batches are nFolds times larger); the class1Prob/class2Prob arrays are summed ONCE at the end and the per-fold curves
+	// are computed from the summed arrays, fold f on rank f % world.  Same sums up to the fp64 addition order across ranks.
+	// A rank's share of a fold is further cut into pieces of at most max(32, share / foldLanes) partitions, one piece per
+	// fold lane at a time, so that a rank that owns only one or two folds still keeps several lanes busy.
+	bool shardUnits = false;
+	// [first, last) of fold `fold`'s partitions that belong to `rank` under either rule (src/MPIHelper.cpp:29-37 for the first)
+	static void partRange(bool units, uint32_t nFoldsRun, uint32_t nPart, uint32_t world, uint32_t rank, uint32_t foldIdx, uint32_t* first, uint32_t* last);
 	int curvesTieMode = 0;
 	bool evalFoldCurves = true;
 	// Folds of a CV are independent until the score merge: with foldLanes > 1 that many folds are in flight at once, each
@@ -265,7 +285,10 @@ public:
 private:
 	struct FoldGate;
 	void predictIt();
-	void runFold(uint32_t currentFold, Device* d, Partition* prt, GlibcRand* r, FoldGate* gate);
+	bool willShardUnits() const;
+	void runFold(uint32_t currentFold, uint32_t first, uint32_t last, Device* d, Partition* prt, GlibcRand* r, FoldGate* gate);
+	bool unitMode = false;      // this smurfIt call shards by (fold, partition) unit
+	uint32_t foldBase = 0, foldsRun = 0;   // first fold and number of folds of this smurfIt call
 	void runFoldsInLanes(uint32_t startingFold, uint32_t endingFold, uint32_t lanes);
 	const CommonParams* const commonParams;
 	std::vector<GridParams>& gridParams;

@@ -25,6 +25,10 @@ def hlib():
         L.psmh_set_fold_lanes.argtypes = [u32]
         L.psmh_set_fold_lanes.restype = None
         L.psmh_get_fold_lanes.restype = u32
+        L.psmh_set_shard_units.argtypes = [C.c_int]
+        L.psmh_set_shard_units.restype = None
+        L.psmh_part_range.argtypes = [C.c_int, u32, u32, u32, u32, u32, u32p, u32p]
+        L.psmh_part_range.restype = None
         L.psmh_device_create.restype = vp
         L.psmh_device_create.argtypes = [C.c_int, vp]
         L.psmh_device_destroy.argtypes = [vp]
@@ -38,7 +42,7 @@ def hlib():
 
 def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, device=0, stream=None, tie_mode=0, eval_fold_curves=True,
            rank=0, world=1, reduce=None, batch_budget=0, profile=False, x_device_ptr=None, n=None, m=None, dev_handle=None, out=None,
-           fold_lanes=None):
+           fold_lanes=None, shard=None):
     """Run the whole CV on one GPU (or this rank's share of the partitions when world > 1).
 
     x: host row-major float64 [n][m+1] (label column 1.0/2.0), or None with x_device_ptr/n/m for a dataset already in HBM.
@@ -48,9 +52,14 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     more in first-touch page faults than the copy into it).
     fold_lanes: how many folds are in flight at once (one context + stream + host thread each, same results); None keeps the
     library default (PSM_FOLD_LANES or 4).  Kernel times / launch counts are summed over the lanes.
+    shard (world > 1): "unit" -- the nFolds x nParts (fold, partition) units are cut into contiguous ranges, one per rank, and
+    `reduce` is called once for the summed score arrays [2n] and once for the per-fold metrics [2 nFolds]; "fold" -- the
+    reference's MPI rule: every rank takes its chunk of every fold's partitions, `reduce` is called once per fold [2 Nte].
+    None keeps the library default (PSM_SHARD or "unit").
     Returns dict(class1, class2, auroc, auprc, fold_metrics, kernel_ms, kernel_launches, stats)."""
     L = hlib()
     L.psmh_set_fold_lanes(0 if fold_lanes is None else int(fold_lanes))
+    L.psmh_set_shard_units(-1 if shard is None else {"unit": 1, "fold": 0}[shard])
     if x is not None:
         assert x.dtype == np.float64 and x.flags.c_contiguous
         n, m = x.shape[0], x.shape[1] - 1
@@ -195,6 +204,13 @@ def ttd_fold(labels, folds, nFolds, fold, fold_to_jump=-1):
     a = [np.zeros(int(v), np.uint32) for v in s]
     L.psmh_ttd_fold(_p(labels, u32p), _p(folds, u32p), len(labels), nFolds, fold, fold_to_jump, _p(s, u32p), *[_p(v, u32p) for v in a])
     return dict(trngPos=a[0], trngNeg=a[1], testPos=a[2], testNeg=a[3])
+
+
+def part_range(units, n_folds, n_parts, world, rank, fold):
+    """[first, last) of `fold`'s partitions owned by `rank` (hyperSMURF::partRange)"""
+    a = np.zeros(1, np.uint32); b = np.zeros(1, np.uint32)
+    hlib().psmh_part_range(int(bool(units)), n_folds, n_parts, world, rank, fold, _p(a, u32p), _p(b, u32p))
+    return int(a[0]), int(b[0])
 
 
 def rand_fill(seed, count):

@@ -122,8 +122,8 @@ def test_fold_lanes_give_identical_bits(oracle):
             assert np.array_equal(out["fold_metrics"], one["fold_metrics"]) and out["auroc"] == one["auroc"] and out["auprc"] == one["auprc"]
             assert out["stats"] == one["stats"] and out["kernel_launches"]["split_search"] == one["kernel_launches"]["split_search"]
         calls = []
-        a1 = H.cv_run(*args, tie_mode=0, rank=1, world=2, reduce=lambda ptr, count: None, eval_fold_curves=False, fold_lanes=1)
-        a3 = H.cv_run(*args, tie_mode=0, rank=1, world=2, reduce=lambda ptr, count: calls.append(count), eval_fold_curves=False, fold_lanes=3)
+        a1 = H.cv_run(*args, tie_mode=0, rank=1, world=2, reduce=lambda ptr, count: None, eval_fold_curves=False, fold_lanes=1, shard="fold")
+        a3 = H.cv_run(*args, tie_mode=0, rank=1, world=2, reduce=lambda ptr, count: calls.append(count), eval_fold_curves=False, fold_lanes=3, shard="fold")
         assert np.array_equal(a1["class1"].view(np.uint64), a3["class1"].view(np.uint64)), name
         assert len(calls) == case["nF"]            # one reduce per fold, issued from the calling thread in fold order
 
@@ -151,13 +151,57 @@ def test_two_rank_shares_on_one_gpu(oracle):
     args = (x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
     full = H.cv_run(*args, tie_mode=0)
     noop = lambda ptr, count: None
-    a = H.cv_run(*args, tie_mode=0, rank=0, world=2, reduce=noop, eval_fold_curves=False)
-    b = H.cv_run(*args, tie_mode=0, rank=1, world=2, reduce=noop, eval_fold_curves=False)
+    a = H.cv_run(*args, tie_mode=0, rank=0, world=2, reduce=noop, eval_fold_curves=False, shard="fold")
+    b = H.cv_run(*args, tie_mode=0, rank=1, world=2, reduce=noop, eval_fold_curves=False, shard="fold")
     assert np.allclose(a["class1"] + b["class1"], full["class1"], rtol=0, atol=1e-15)
     assert np.allclose(a["class2"] + b["class2"], full["class2"], rtol=0, atol=1e-15)
     assert np.abs(a["class1"]).sum() > 0 and np.abs(b["class1"]).sum() > 0
     rc, o1, o2 = oracle.o_cv_parts(*args, 0, 2)
     assert np.array_equal(a["class1"].view(np.uint64), o1.view(np.uint64))
+
+
+def test_unit_sharded_ranks_reproduce_the_single_rank_cv(oracle):
+    """unit sharding (contiguous ranges of the nFolds x nParts units; ONE sum of the score arrays at the end; per-fold curves
+    from the summed arrays, fold f on rank f % world), three ranks emulated one after the other on one GPU: the reduce
+    callback of a rank adds the other ranks' contributions, captured from earlier passes, into the device buffer"""
+    import torch
+    from parsmurf_b200 import host_api as H
+
+    class _Arr:
+        def __init__(self, ptr, count):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+    # (world, nParts, nTrees): the second shape gives a rank more than 32 units of one fold, so its share is cut into pieces
+    for W, nParts, T in ((3, 4, 10), (2, 80, 2)):
+      case = make_case("fy_26")
+      x = oracle.make_x(case["X"], case["y"])
+      args = (x, case["y"], case["f"], case["nF"], nParts, case["fp"], case["ratio"], case["k"], T, case["mtry"], 7)
+      n, nF = len(case["y"]), case["nF"]
+      full = H.cv_run(*args, tie_mode=0, fold_lanes=1)
+      for lanes in (1, 3):
+          def run(rank, add_scores=None, add_metrics=None):
+              got = []
+              def reduce(ptr, count):
+                  t = torch.as_tensor(_Arr(ptr, count), device="cuda")
+                  got.append(t.cpu().numpy().copy())
+                  extra = add_scores if count == 2 * n else add_metrics
+                  assert count in (2 * n, 2 * nF)
+                  if extra is not None:
+                      t += torch.from_numpy(extra).cuda()
+                  torch.cuda.synchronize()
+              out = H.cv_run(*args, tie_mode=0, rank=rank, world=W, reduce=reduce, shard="unit", fold_lanes=lanes)
+              return out, got
+          partial = [run(r)[1][0] for r in range(W)]                          # pass 1: every rank's partial class1Prob/class2Prob
+          assert all(np.abs(p).sum() > 0 for p in partial)
+          tot = sum(partial)
+          assert np.allclose(tot[:n], full["class1"], rtol=0, atol=1e-13) and np.allclose(tot[n:], full["class2"], rtol=0, atol=1e-13)   # fp64 addition order across ranks
+          others = lambda r, xs: sum(xs[q] for q in range(W) if q != r)
+          metrics = [run(r, add_scores=others(r, partial))[1][1] for r in range(W)]   # pass 2: own folds' metrics from the summed scores
+          for r in range(W):
+              out, _ = run(r, add_scores=others(r, partial), add_metrics=others(r, metrics))   # pass 3: what rank r returns in a real run
+              assert np.allclose(out["class1"], full["class1"], rtol=0, atol=1e-13) and np.allclose(out["class2"], full["class2"], rtol=0, atol=1e-13)
+              assert np.allclose(out["fold_metrics"], full["fold_metrics"], rtol=0, atol=1e-4), (r, out["fold_metrics"], full["fold_metrics"])   # 1-ulp score differences reorder exact ties (no tie grouping, SURVEY fact #8)
+              assert abs(out["auroc"] - full["auroc"]) < 1e-4 and abs(out["auprc"] - full["auprc"]) < 1e-4
 
 
 def test_cuda_path_against_committed_golden_fixtures(oracle):

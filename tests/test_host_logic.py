@@ -123,3 +123,24 @@ def test_config_surface():
         H.config_parse('{"exec": {"mode": "bogus"}}')
     with pytest.raises(psm.PsmError):
         H.config_parse('{"exec": ')
+
+
+def test_rank_sharding_rules_cover_every_partition_once():
+    """both rules of hyperSMURF::partRange: per-fold chunks (src/MPIHelper.cpp:29-37) and contiguous (fold, partition) units"""
+    from parsmurf_b200 import host_api as H
+    for nF, nP in ((5, 100), (10, 1000), (3, 7), (4, 1), (1, 5)):
+        for world in (1, 2, 3, 4, 8, 16):
+            for units in (False, True):
+                sizes = []
+                for f in range(nF):
+                    r = [H.part_range(units, nF, nP, world, k, f) for k in range(world)]
+                    owned = [(a, b) for a, b in r if b > a]
+                    assert owned[0][0] == 0 and owned[-1][1] == nP and all(owned[i][1] == owned[i + 1][0] for i in range(len(owned) - 1)), (nF, nP, world, units, f, r)
+                    sizes.append([b - a for a, b in r])
+                tot = np.array(sizes).sum(axis=0)
+                assert tot.sum() == nF * nP
+                if units:
+                    assert tot.max() - tot.min() <= 1                      # units balanced over the ranks
+                    assert all(sum(1 for f in range(nF) if sizes[f][k] > 0) <= (nF + world - 1) // world + 1 for k in range(world))   # a rank opens few folds
+                else:
+                    assert all(max(srow) - min(srow) <= 1 for srow in sizes)   # every fold balanced over the ranks
