@@ -64,6 +64,25 @@ int psm_fold_begin(psm_ctx* ctx, const uint32_t* trngPosIdx, uint32_t trngPosNum
                    uint32_t trngNegNum, const uint32_t* testPosIdx, uint32_t testPosNum,
                    const uint32_t* testNegIdx, uint32_t testNegNum);
 
+/* ---- (3b) folds on the device: replaces TestTrainDivider's per-fold index arrays and their std::random_shuffle
+ *      (src/testtraindivider.cpp:5-106).  psm_folds_upload takes, once per CV, the examples of every fold split by class in
+ *      the order Folds::computeFolds leaves them (src/folds.cpp:26-117): posList / negList with nFolds+1 offsets each.
+ *      psm_fold_begin_device(fold, window) then opens `fold` like psm_fold_begin, but builds the four index arrays on the
+ *      device: test = the fold's positives then its negatives; training = the other folds' blocks in ascending fold order
+ *      (:57-80); and, when shuffle_window31 != NULL, the training negatives shuffled exactly like
+ *      std::random_shuffle(trngNeg.begin(), trngNeg.end()) driven by glibc rand() whose last 31 state words (oldest first)
+ *      are `shuffle_window31` (:90) -- the draws are replayed on the device and the swap chain is resolved per output slot
+ *      (csrc/shuffle.cu), so nothing of size n is built, shuffled or uploaded by the host.
+ *      psm_folds_attach shares src's device lists (fold lanes); psm_fold_indices_get copies the open fold's arrays back
+ *      (sizes4 = {trngPos, trngNeg, testPos, testNeg}; pointers may be NULL); psm_scores_fold_curves_device is
+ *      psm_scores_fold_curves for a fold of the uploaded lists. */
+int psm_folds_upload(psm_ctx* ctx, uint32_t nFolds, const uint32_t* posList, const uint32_t* posOff, const uint32_t* negList,
+                     const uint32_t* negOff);
+int psm_folds_attach(psm_ctx* ctx, psm_ctx* src);
+int psm_fold_begin_device(psm_ctx* ctx, uint32_t fold, const uint32_t* shuffle_window31);
+int psm_fold_indices_get(psm_ctx* ctx, uint32_t* sizes4, uint32_t* trngPos, uint32_t* trngNeg, uint32_t* testPos, uint32_t* testNeg);
+int psm_scores_fold_curves_device(psm_ctx* ctx, uint32_t fold, int tie_mode, double* out);
+
 /* ---- (4) kNN: replaces ANNkd_tree + annkSearch in SamplerKNN::minOversample (src/samplerKNN.cpp:60-93).
  *      Exact brute force over the fold's positives; zero distances excluded; ascending (distance, index);
  *      missing slots = -1 / +inf.  localk = min(k, P).  Computed once per fold (fact: pos is the same for

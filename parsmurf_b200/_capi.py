@@ -61,6 +61,9 @@ def lib():
         L.psm_dataset_upload.argtypes = [vp, dp, u32, u32]
         L.psm_dataset_attach_device.argtypes = [vp, vp, u32, u32]
         L.psm_fold_begin.argtypes = [vp, u32p, u32, u32p, u32, u32p, u32, u32p, u32]
+        L.psm_folds_upload.argtypes = [vp, u32, u32p, u32p, u32p, u32p]
+        L.psm_fold_begin_device.argtypes = [vp, u32, u32p]
+        L.psm_fold_indices_get.argtypes = [vp, u32p, u32p, u32p, u32p, u32p]
         L.psm_fold_knn.argtypes = [vp, u32]
         L.psm_fold_knn_get.argtypes = [vp, i32p, dp]
         L.psm_fold_knn_set.argtypes = [vp, i32p, u32]
@@ -127,6 +130,21 @@ class Context:
     def _ck(self, rc):
         if rc != 0:
             raise PsmError(rc, self.L.psm_last_error(self.h).decode())
+
+    def folds_upload(self, pos_list, pos_off, neg_list, neg_off):
+        a = [np.ascontiguousarray(v, np.uint32) for v in (pos_list, pos_off, neg_list, neg_off)]
+        self._ck(self.L.psm_folds_upload(self.h, len(a[1]) - 1, _p(a[0], u32p), _p(a[1], u32p), _p(a[2], u32p), _p(a[3], u32p)))
+
+    def fold_begin_device(self, fold, shuffle_window31=None):
+        w = None if shuffle_window31 is None else np.ascontiguousarray(shuffle_window31, np.uint32)
+        self._ck(self.L.psm_fold_begin_device(self.h, fold, _p(w, u32p)))
+
+    def fold_indices_get(self):
+        s = np.zeros(4, np.uint32)
+        self._ck(self.L.psm_fold_indices_get(self.h, _p(s, u32p), None, None, None, None))
+        a = [np.zeros(int(v), np.uint32) for v in s]
+        self._ck(self.L.psm_fold_indices_get(self.h, _p(s, u32p), *[_p(v, u32p) for v in a]))
+        return dict(trngPos=a[0], trngNeg=a[1], testPos=a[2], testNeg=a[3])
 
     def close(self):
         if getattr(self, "h", None):

@@ -53,6 +53,13 @@ struct psm_ctx {
 	std::vector<uint32_t> hTestIdx;
 	DevBuf dPos, dNeg, dTest, dXp, dNN, dNNd, dKnnScratch, dClass12;
 
+	// folds on the device (psm_folds_upload): examples of every fold by class; shuffle scratch
+	DevBuf dPosList, dNegList, sKeysA, sKeysB, sValsA, sValsB, sHist, sJ, sDraws, sIn;
+	const uint32_t* fPos = nullptr;    // device lists (own buffers or another context's, psm_folds_attach)
+	const uint32_t* fNeg = nullptr;
+	std::vector<uint32_t> fPosOff, fNegOff;
+	bool foldFromLists = false;        // the open fold was built by psm_fold_begin_device (no host copy of the test ids)
+
 	// batch
 	bool batchOpen = false, assembled = false, trained = false;
 	uint32_t nParts = 0, fp = 0, ratio = 0, p0 = 0, p1 = 0, nB = 0, maxNtr = 0;
@@ -181,7 +188,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	if (!ctx) return PSM_E_ARG;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	DevBuf* bufs[] = {&ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dClass12,
+	DevBuf* bufs[] = {&ctx->dPosList, &ctx->dNegList, &ctx->sKeysA, &ctx->sKeysB, &ctx->sValsA, &ctx->sValsB, &ctx->sHist, &ctx->sJ, &ctx->sDraws, &ctx->sIn, &ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dClass12,
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
 	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dSplitFeat, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1, &ctx->dCls,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dPtask, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
@@ -276,7 +283,104 @@ int psm_fold_begin(psm_ctx* ctx, const uint32_t* trngPosIdx, uint32_t P, const u
 	if (ctx->Nte) CU(cudaMemcpyAsync(ctx->dTest.p, ctx->hTestIdx.data(), (size_t)ctx->Nte * 4, cudaMemcpyHostToDevice, ctx->stream));
 	CU(cudaMemsetAsync(ctx->dClass12.p, 0, std::max<size_t>(16, (size_t)ctx->Nte * 16), ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	ctx->foldOpen = true;
+	ctx->foldOpen = true; ctx->foldFromLists = false;
+	return PSM_OK;
+}
+
+int psm_folds_upload(psm_ctx* ctx, uint32_t nFolds, const uint32_t* posList, const uint32_t* posOff, const uint32_t* negList, const uint32_t* negOff) {
+	if (!ctx || !ctx->x || nFolds == 0 || !posOff || !negOff) return fail(ctx, PSM_E_ARG, "folds_upload: bad arguments");
+	CU(cudaSetDevice(ctx->device));
+	const uint32_t totPos = posOff[nFolds], totNeg = negOff[nFolds];
+	if ((totPos && !posList) || (totNeg && !negList) || (uint64_t)totPos + totNeg > ctx->n) return fail(ctx, PSM_E_ARG, "folds_upload: lists do not match the dataset");
+	for (uint32_t f = 0; f < nFolds; f++) if (posOff[f] > posOff[f + 1] || negOff[f] > negOff[f + 1]) return fail(ctx, PSM_E_ARG, "folds_upload: offsets not ascending");
+	ENSURE(ctx->dPosList, std::max<size_t>(4, (size_t)totPos * 4));
+	ENSURE(ctx->dNegList, std::max<size_t>(4, (size_t)totNeg * 4));
+	if (totPos) CU(cudaMemcpyAsync(ctx->dPosList.p, posList, (size_t)totPos * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (totNeg) CU(cudaMemcpyAsync(ctx->dNegList.p, negList, (size_t)totNeg * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));   // the host lists are only borrowed
+	ctx->fPos = ctx->dPosList.as<uint32_t>(); ctx->fNeg = ctx->dNegList.as<uint32_t>();
+	ctx->fPosOff.assign(posOff, posOff + nFolds + 1); ctx->fNegOff.assign(negOff, negOff + nFolds + 1);
+	ctx->foldOpen = false;
+	return PSM_OK;
+}
+
+int psm_folds_attach(psm_ctx* ctx, psm_ctx* src) {
+	if (!ctx || !src || !src->fPos || ctx->device != src->device || ctx->n != src->n) return fail(ctx, PSM_E_ARG, "folds_attach: source has no fold lists for this dataset");
+	ctx->fPos = src->fPos; ctx->fNeg = src->fNeg; ctx->fPosOff = src->fPosOff; ctx->fNegOff = src->fNegOff;
+	ctx->foldOpen = false;
+	return PSM_OK;
+}
+
+int psm_fold_begin_device(psm_ctx* ctx, uint32_t fold, const uint32_t* window31) {
+	if (!ctx || !ctx->x || !ctx->fPos || fold + 1 >= ctx->fPosOff.size()) return fail(ctx, PSM_E_ARG, "fold_begin_device: upload the fold lists first");
+	CU(cudaSetDevice(ctx->device));
+	const std::vector<uint32_t>&po = ctx->fPosOff, &no = ctx->fNegOff;
+	const uint32_t nF = (uint32_t)po.size() - 1;
+	const uint32_t nTP = po[fold + 1] - po[fold], nTN = no[fold + 1] - no[fold];
+	const uint32_t P = po[nF] - nTP, Nneg = no[nF] - nTN;
+	ctx->P = P; ctx->Nneg = Nneg; ctx->nTP = nTP; ctx->nTN = nTN; ctx->Nte = nTP + nTN;
+	ctx->haveKnn = false; ctx->batchOpen = false; ctx->localk = 0; ctx->foldLabelsReady = false;
+	ctx->hTestIdx.clear();
+	ENSURE(ctx->dPos, std::max<size_t>(4, (size_t)P * 4));
+	ENSURE(ctx->dNeg, std::max<size_t>(4, (size_t)Nneg * 4));
+	ENSURE(ctx->dTest, std::max<size_t>(4, (size_t)ctx->Nte * 4));
+	ENSURE(ctx->dClass12, std::max<size_t>(16, (size_t)ctx->Nte * 16));
+	const bool shuffle = window31 != nullptr && Nneg > 1;
+	if (shuffle) ENSURE(ctx->sIn, (size_t)Nneg * 4);
+	cudaStream_t s = ctx->stream;
+	// training arrays: the other folds' blocks in ascending fold order (testtraindivider.cpp:57-80)
+	uint32_t* tp = ctx->dPos.as<uint32_t>();
+	uint32_t* tn = shuffle ? ctx->sIn.as<uint32_t>() : ctx->dNeg.as<uint32_t>();
+	size_t op = 0, on = 0;
+	for (uint32_t kf = 0; kf < nF; kf++) {
+		if (kf == fold) continue;
+		const size_t cp = po[kf + 1] - po[kf], cn = no[kf + 1] - no[kf];
+		if (cp) CU(cudaMemcpyAsync(tp + op, ctx->fPos + po[kf], cp * 4, cudaMemcpyDeviceToDevice, s));
+		if (cn) CU(cudaMemcpyAsync(tn + on, ctx->fNeg + no[kf], cn * 4, cudaMemcpyDeviceToDevice, s));
+		op += cp; on += cn;
+	}
+	// test rows: positives first, then negatives (sampler.cpp:90-95)
+	if (nTP) CU(cudaMemcpyAsync(ctx->dTest.p, ctx->fPos + po[fold], (size_t)nTP * 4, cudaMemcpyDeviceToDevice, s));
+	if (nTN) CU(cudaMemcpyAsync(ctx->dTest.as<uint32_t>() + nTP, ctx->fNeg + no[fold], (size_t)nTN * 4, cudaMemcpyDeviceToDevice, s));
+	if (shuffle) {                                                              // testtraindivider.cpp:90 on the device (shuffle.cu)
+		const uint64_t rBlocks = ((uint64_t)Nneg + 4095) / 4096;
+		ENSURE(ctx->sKeysA, (size_t)Nneg * 8); ENSURE(ctx->sKeysB, (size_t)Nneg * 8);
+		ENSURE(ctx->sValsA, (size_t)Nneg * 4); ENSURE(ctx->sValsB, (size_t)Nneg * 4);
+		ENSURE(ctx->sHist, rBlocks * 256 * 4); ENSURE(ctx->sJ, (size_t)Nneg * 4); ENSURE(ctx->sDraws, (size_t)Nneg * 4);
+		ENSURE(ctx->dRandScratch, (61 + 64 * 31) * 4);
+		ProfScope ps(ctx, K_GATHER, 3 + 3 * 8);
+		if (launch_glibc_rand_fill(window31, (unsigned long long)Nneg - 1, ctx->dRandScratch.as<uint32_t>(), ctx->sDraws.as<int32_t>(), s))
+			return fail(ctx, PSM_E_CUDA, "fold_begin_device: rand replay launch failed");
+		if (launch_device_shuffle(ctx->sDraws.as<int32_t>(), ctx->sIn.as<uint32_t>(), Nneg, ctx->sKeysA.as<unsigned long long>(), ctx->sKeysB.as<unsigned long long>(),
+		                          ctx->sValsA.as<uint32_t>(), ctx->sValsB.as<uint32_t>(), ctx->sHist.as<uint32_t>(), ctx->sJ.as<uint32_t>(), ctx->dNeg.as<uint32_t>(), s))
+			return fail(ctx, PSM_E_CUDA, "fold_begin_device: shuffle launch failed");
+	}
+	CU(cudaMemsetAsync(ctx->dClass12.p, 0, std::max<size_t>(16, (size_t)ctx->Nte * 16), s));
+	CU(cudaGetLastError());
+	ctx->foldOpen = true; ctx->foldFromLists = true;
+	return PSM_OK;
+}
+
+// host copy of the open fold's test ids (psm_fold_begin keeps one; psm_fold_begin_device fetches it only when somebody asks)
+static int ensure_host_test_ids(psm_ctx* ctx) {
+	if (ctx->hTestIdx.size() == ctx->Nte) return PSM_OK;
+	ctx->hTestIdx.resize(ctx->Nte);
+	if (ctx->Nte) {
+		CU(cudaMemcpyAsync(ctx->hTestIdx.data(), ctx->dTest.p, (size_t)ctx->Nte * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+	}
+	return PSM_OK;
+}
+
+int psm_fold_indices_get(psm_ctx* ctx, uint32_t* sizes4, uint32_t* trngPos, uint32_t* trngNeg, uint32_t* testPos, uint32_t* testNeg) {
+	if (!ctx || !ctx->foldOpen) return fail(ctx, PSM_E_ARG, "fold_indices_get: no open fold");
+	if (sizes4) { sizes4[0] = ctx->P; sizes4[1] = ctx->Nneg; sizes4[2] = ctx->nTP; sizes4[3] = ctx->nTN; }
+	cudaStream_t s = ctx->stream;
+	if (trngPos && ctx->P) CU(cudaMemcpyAsync(trngPos, ctx->dPos.p, (size_t)ctx->P * 4, cudaMemcpyDeviceToHost, s));
+	if (trngNeg && ctx->Nneg) CU(cudaMemcpyAsync(trngNeg, ctx->dNeg.p, (size_t)ctx->Nneg * 4, cudaMemcpyDeviceToHost, s));
+	if (testPos && ctx->nTP) CU(cudaMemcpyAsync(testPos, ctx->dTest.p, (size_t)ctx->nTP * 4, cudaMemcpyDeviceToHost, s));
+	if (testNeg && ctx->nTN) CU(cudaMemcpyAsync(testNeg, ctx->dTest.as<uint32_t>() + ctx->nTP, (size_t)ctx->nTN * 4, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
 	return PSM_OK;
 }
 
@@ -759,6 +863,7 @@ int psm_fold_scatter_host(psm_ctx* ctx, double* class1Prob, double* class2Prob) 
 	if (!ctx || !ctx->foldOpen || !class1Prob) return fail(ctx, PSM_E_ARG, "fold_scatter_host: no open fold");
 	std::vector<double> c((size_t)ctx->Nte * 2);
 	if (ctx->Nte == 0) return PSM_OK;
+	{ int rc = ensure_host_test_ids(ctx); if (rc) return rc; }
 	CU(cudaMemcpyAsync(c.data(), ctx->dClass12.p, c.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	for (uint32_t i = 0; i < ctx->Nte; i++) {
@@ -862,7 +967,8 @@ int psm_fold_curves(psm_ctx* ctx, int tie_mode, double* out) {
 	CU(cudaSetDevice(ctx->device));
 	ENSURE(ctx->dFoldLabels, (size_t)ctx->Nte * 4);
 	uint32_t totP = 0, totN = 0;
-	for (uint32_t i = 0; i < ctx->Nte; i++) { uint32_t l = ctx->hLabels[ctx->hTestIdx[i]]; totP += l == 1; totN += l == 0; }
+	if (ctx->foldFromLists) { totP = ctx->nTP; totN = ctx->nTN; }             // the fold lists are split by label (0/1): no host pass needed
+	else for (uint32_t i = 0; i < ctx->Nte; i++) { uint32_t l = ctx->hLabels[ctx->hTestIdx[i]]; totP += l == 1; totN += l == 0; }
 	{
 		ProfScope ps(ctx, K_GATHER, 1);
 		launch_gather_u32(ctx->dLabels.as<uint32_t>(), ctx->dTest.as<uint32_t>(), ctx->Nte, ctx->dFoldLabels.as<uint32_t>(), ctx->stream);
@@ -928,6 +1034,23 @@ int psm_scores_fold_curves(psm_ctx* ctx, const uint32_t* testPosIdx, uint32_t nT
 		launch_gather_f64(ctx->dGlob.as<double>(), ctx->cIdx.as<uint32_t>(), N, ctx->cFoldScores.as<double>(), ctx->stream);   // class1Prob[idx]
 	}
 	return curves_core(ctx, ctx->dFoldLabels.as<uint32_t>(), ctx->cFoldScores.as<double>(), nullptr, N, totP, totN, tie_mode, out);   // syncs: the index arrays are only borrowed
+}
+
+int psm_scores_fold_curves_device(psm_ctx* ctx, uint32_t fold, int tie_mode, double* out) {
+	if (!ctx || !ctx->haveLabels || !out || !ctx->fPos || fold + 1 >= ctx->fPosOff.size()) return fail(ctx, PSM_E_ARG, "scores_fold_curves_device: need device scores and fold lists");
+	CU(cudaSetDevice(ctx->device));
+	const uint32_t nTP = ctx->fPosOff[fold + 1] - ctx->fPosOff[fold], nTN = ctx->fNegOff[fold + 1] - ctx->fNegOff[fold];
+	const uint64_t N = (uint64_t)nTP + nTN;
+	if (N == 0) return fail(ctx, PSM_E_ARG, "scores_fold_curves_device: empty fold");
+	ENSURE(ctx->cIdx, N * 4); ENSURE(ctx->cFoldScores, N * 8); ENSURE(ctx->dFoldLabels, N * 4);
+	if (nTP) CU(cudaMemcpyAsync(ctx->cIdx.p, ctx->fPos + ctx->fPosOff[fold], (size_t)nTP * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+	if (nTN) CU(cudaMemcpyAsync(ctx->cIdx.as<uint32_t>() + nTP, ctx->fNeg + ctx->fNegOff[fold], (size_t)nTN * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+	{
+		ProfScope ps(ctx, K_GATHER, 2);
+		launch_gather_u32(ctx->dLabels.as<uint32_t>(), ctx->cIdx.as<uint32_t>(), N, ctx->dFoldLabels.as<uint32_t>(), ctx->stream);
+		launch_gather_f64(ctx->dGlob.as<double>(), ctx->cIdx.as<uint32_t>(), N, ctx->cFoldScores.as<double>(), ctx->stream);
+	}
+	return curves_core(ctx, ctx->dFoldLabels.as<uint32_t>(), ctx->cFoldScores.as<double>(), nullptr, N, nTP, nTN, tie_mode, out);
 }
 
 int psm_scratch_f64(psm_ctx* ctx, uint32_t count, double** dev) {

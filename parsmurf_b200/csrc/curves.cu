@@ -283,4 +283,23 @@ int launch_sort_scores_desc(const double* scores, uint64_t N, unsigned long long
 	return 0;
 }
 
+// generic entry: ascending LSD sort of prefilled (keysA, valsA) on the low 8*passes key bits; passes must be even so that the
+// result is back in keysA / valsA.  hist: ((N + 4095) / 4096) * 256 uint32.
+int launch_radix_sort_u64(unsigned long long* keysA, unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, uint64_t N, int passes,
+                          uint32_t* hist, cudaStream_t s) {
+	if (N == 0) return 0;
+	if (N >= (1ull << 32) || passes <= 0 || passes > 8 || (passes & 1)) return -1;
+	const uint32_t nBlocks = (uint32_t)((N + RCHUNK - 1) / RCHUNK);
+	unsigned long long *kin = keysA, *kout = keysB;
+	uint32_t *vin = valsA, *vout = valsB;
+	for (int pass = 0; pass < passes; pass++) {
+		radix_hist_kernel<<<nBlocks, RB, 0, s>>>(kin, N, pass * 8, nBlocks, hist);
+		scan_blocksums_kernel<<<1, 1024, 0, s>>>(hist, 256u * nBlocks);
+		radix_scatter_kernel<<<nBlocks, RB, 0, s>>>(kin, vin, N, pass * 8, nBlocks, hist, kout, vout);
+		unsigned long long* tk = kin; kin = kout; kout = tk;
+		uint32_t* tv = vin; vin = vout; vout = tv;
+	}
+	return 0;
+}
+
 }  // namespace psm

@@ -216,6 +216,12 @@ TestTrainDivider::~TestTrainDivider() {
 		for (auto& v : *vv) g_pool.give(v);
 }
 
+void TestTrainDivider::shuffleWindow(uint32_t fold, uint32_t* w31) const {
+	GlibcRand local = start;
+	local.discard(shuffleOff.empty() ? 0 : shuffleOff[fold]);
+	local.window(w31);
+}
+
 void TestTrainDivider::prefetch(std::vector<uint32_t> order) {
 	if (!lazy || worker.joinable()) return;
 	worker = std::thread([this, order]() { for (uint32_t f : order) if (f < nFolds) ensure(f); });
@@ -290,6 +296,12 @@ void Partition::setFold(uint32_t f) {
 	testPosIdx = ttd->testPosIdx[f].data(); testNegIdx = ttd->testNegIdx[f].data();
 }
 
+void Partition::setFoldCounts(uint32_t f) {
+	currentFold = f;
+	trngPosNum = ttd->trngPosNum[f]; trngNegNum = ttd->trngNegNum[f]; testPosNum = ttd->testPosNum[f]; testNegNum = ttd->testNegNum[f];
+	trngPosIdx = trngNegIdx = testPosIdx = testNegIdx = nullptr;
+}
+
 // ------------------------------------------------------------------------------------------ Device
 Device::Device(int device, void* cudaStream) : deviceId(device) {
 	int rc = psm_ctx_create(device, &ctx);
@@ -311,6 +323,17 @@ void Device::ensureFold(const Partition* part) {
 	if (foldTag == (const void*)part->ttd && foldId == part->currentFold) return;
 	check(psm_fold_begin(ctx, part->trngPosIdx, part->trngPosNum, part->trngNegIdx, part->trngNegNum, part->testPosIdx, part->testPosNum,
 	                     part->testNegIdx, part->testNegNum));
+	foldTag = part->ttd; foldId = part->currentFold; knnK = 0;
+}
+void Device::uploadFolds(const Folds* F) {
+	check(psm_folds_upload(ctx, F->nFolds, F->posList.data(), F->posOff.data(), F->negList.data(), F->negOff.data()));
+	foldTag = nullptr;
+}
+void Device::attachFolds(const Device* src) { check(psm_folds_attach(ctx, src->ctx)); foldTag = nullptr; }
+void Device::beginFoldOnDevice(const Partition* part) {
+	uint32_t w[31];
+	part->ttd->shuffleWindow(part->currentFold, w);
+	check(psm_fold_begin_device(ctx, part->currentFold, w));
 	foldTag = part->ttd; foldId = part->currentFold; knnK = 0;
 }
 void Device::ensureKnn(uint32_t k) {
@@ -538,7 +561,10 @@ void hyperSMURF::initStandard() {                                           // s
 		partRange(willShardUnits(), f1 - f0, nPart, world, rank, f - f0, &a, &b);
 		if (b > a || !willShardUnits()) order.push_back(f);
 	}
-	ttd->prefetch(order);
+	if (!foldsOnDevice()) ttd->prefetch(order);
+}
+bool hyperSMURF::foldsOnDevice() const {
+	return deviceFolds && commonParams->wmode == MODE_CV && !inInternalCV && ttd && ttd->builtOnDemand();
 }
 bool hyperSMURF::willShardUnits() const {
 	return shardUnits && world > 1 && (bool)reduce && commonParams->wmode == MODE_CV && commonParams->woptimiz == OPT_NO && !inInternalCV && !commonParams->customCV;
@@ -570,6 +596,7 @@ void hyperSMURF::smurfIt() {                                                // s
 	dev->check(psm_labels_upload(dev->ctx, y.data(), nn));
 	dev->check(psm_scores_reset(dev->ctx));
 	// fold lanes only where every fold runs with the same parameters and nothing is flushed to the host between folds
+	if (foldsOnDevice()) { PhaseScope ps(PH_FOLD_BEGIN); dev->uploadFolds(foldManager); }
 	foldBase = startingFold; foldsRun = endingFold - startingFold;
 	unitMode = willShardUnits();
 	const uint32_t lanesHere = (wmode == MODE_CV && woptimiz == OPT_NO && !(commonParams->customCV && !inInternalCV) && endingFold > startingFold + 1)
@@ -634,9 +661,12 @@ void hyperSMURF::smurfIt() {                                                // s
 			std::vector<double> fm(2 * (size_t)nFolds, 0.0);
 			for (uint32_t f = startingFold; f < endingFold; f++) {
 				if ((f - startingFold) % world != rank) continue;
-				ttd->ensureTest(f);
 				double r2[2];
-				dev->check(psm_scores_fold_curves(dev->ctx, ttd->testPosIdx[f].data(), ttd->testPosNum[f], ttd->testNegIdx[f].data(), ttd->testNegNum[f], curvesTieMode, r2));
+				if (foldsOnDevice()) dev->check(psm_scores_fold_curves_device(dev->ctx, f, curvesTieMode, r2));
+				else {
+					ttd->ensureTest(f);
+					dev->check(psm_scores_fold_curves(dev->ctx, ttd->testPosIdx[f].data(), ttd->testPosNum[f], ttd->testNegIdx[f].data(), ttd->testNegNum[f], curvesTieMode, r2));
+				}
 				fm[2 * f] = r2[0]; fm[2 * f + 1] = r2[1];
 			}
 			double* sp = nullptr;
@@ -704,9 +734,15 @@ void hyperSMURF::partRange(bool units, uint32_t nFoldsRun, uint32_t nPart, uint3
 // partitions [first, last) of fold `currentFold` (this rank's share of it, or one piece of the share)
 void hyperSMURF::runFold(uint32_t currentFold, uint32_t first, uint32_t last, Device* d, Partition* prt, GlibcRand* r, FoldGate* gate) {
 	const uint32_t cnt = last - first;
-	{ PhaseScope ps(PH_FOLDS_TTD); prt->setFold(currentFold); }      // :255 (waits for the fold's background build + shuffle)
 	d->invalidateFold();
-	{ PhaseScope ps(PH_FOLD_BEGIN); d->ensureFold(prt); }
+	if (foldsOnDevice()) {                                                 // :255 with the index arrays built (and shuffled) on the device
+		PhaseScope ps(PH_FOLD_BEGIN);
+		prt->setFoldCounts(currentFold);
+		d->beginFoldOnDevice(prt);
+	} else {
+		{ PhaseScope ps(PH_FOLDS_TTD); prt->setFold(currentFold); }  // :255 (builds + shuffles the fold on the host if nobody has yet)
+		{ PhaseScope ps(PH_FOLD_BEGIN); d->ensureFold(prt); }
+	}
 	const uint64_t perPartDraws = (uint64_t)prt->trngPosNum * fp * (mm + 1);
 	auto skipDraws = [&](uint64_t count) { r->discard(count); };      // keep the one SMOTE stream in partition order on every rank
 	{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * first); }
@@ -816,6 +852,7 @@ void hyperSMURF::runFoldsInLanes(uint32_t startingFold, uint32_t endingFold, uin
 				d->attachDevice(xdev, nn, mm);
 				d->check(psm_labels_upload(d->ctx, y.data(), nn));
 				d->check(psm_scores_reset(d->ctx));
+				if (foldsOnDevice()) d->attachFolds(dev);
 			}
 			Partition prt(foldManager, ttd.get(), nPart, fp, ratio, mm, nn);
 			for (;;) {
@@ -1109,6 +1146,7 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		smurfer.curvesTieMode = tieMode; smurfer.evalFoldCurves = evalFoldCurves != 0;
 		smurfer.foldLanes = lanes;
 		smurfer.shardUnits = shard_units_default();
+		smurfer.deviceFolds = getenv("PSM_HOST_FOLDS") == nullptr;
 		if (world > 1) smurfer.setSharding(rank, world, [&](double* p, uint64_t c) { if (reduce && reduce(reduceUser, p, c)) throw Error(PSM_E_CUDA, "reduce callback failed"); });
 		smurfer.initStandard();                             // starts the per-fold index builders in the background ...
 		tSetup = now_s();
@@ -1193,6 +1231,7 @@ int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* la
 		hyperSMURF smurfer(&cp, gp, &folds, &dev, y, class1, class2, &rng);
 		smurfer.curvesTieMode = tieMode;
 		smurfer.foldLanes = std::min<uint32_t>(fold_lanes_default(), nFolds > 1 ? nFolds - 1 : 1);   // the inner CVs run their folds in lanes
+		smurfer.deviceFolds = getenv("PSM_HOST_FOLDS") == nullptr;
 		smurfer.initStandard();
 		dev.upload(x, n, m);
 		smurfer.smurfIt();

@@ -110,6 +110,8 @@ public:
 	void ensure(uint32_t fold) const;
 	void ensureTest(uint32_t fold) const;
 	void prefetch(std::vector<uint32_t> foldsInOrder);
+	bool builtOnDemand() const { return lazy; }            // outer-CV constructor (folds can also be built on the device)
+	void shuffleWindow(uint32_t fold, uint32_t* w31) const;   // rand() state (psm_fold_begin_device layout) before fold's shuffle
 	const Folds* const folds;
 	const uint8_t wmode;
 	uint32_t nFolds;
@@ -132,6 +134,7 @@ class Partition {
 public:
 	Partition(const Folds* folds, const TestTrainDivider* ttd, uint32_t nPart, uint32_t fp, uint32_t ratio, uint32_t m, uint32_t n);
 	void setFold(uint32_t currentFold);
+	void setFoldCounts(uint32_t currentFold);              // counts only: the index arrays live on the device (Device::beginFoldOnDevice)
 	const Folds* const folds;
 	const TestTrainDivider* const ttd;
 	uint32_t nPart, fp, ratio;
@@ -152,6 +155,10 @@ public:
 	void attachDevice(const double* x_dev, uint32_t n, uint32_t m);
 	// begins the fold on the device if it is not the current one (upload index arrays, zero fold scores, drop kNN)
 	void ensureFold(const Partition* part);
+	// the same from the device-resident fold lists (psm_folds_upload / psm_fold_begin_device): nothing is built on the host
+	void uploadFolds(const Folds* folds);
+	void attachFolds(const Device* src);
+	void beginFoldOnDevice(const Partition* part);
 	void ensureKnn(uint32_t k);
 	void invalidateFold() { foldTag = nullptr; }
 	void check(int rc) const;
@@ -279,6 +286,9 @@ public:
 	// latency-bound deep tree levels overlap the other folds' kernels.  Results are identical to foldLanes = 1: the
 	// SMOTE rand() position of every fold is known up front (jump-ahead) and cross-rank reduces stay in fold order.
 	uint32_t foldLanes = 1;
+	// Build every fold's index arrays (and shuffle its training negatives) on the device instead of on the host
+	// (TestTrainDivider); applies to plain and grid-outer CV folds, the inner CVs and train/predict modes keep the host path.
+	bool deviceFolds = true;
 	std::vector<double> foldAuroc, foldAuprc;
 	double auroc = 0, auprc = 0;
 
@@ -286,6 +296,7 @@ private:
 	struct FoldGate;
 	void predictIt();
 	bool willShardUnits() const;
+	bool foldsOnDevice() const;
 	void runFold(uint32_t currentFold, uint32_t first, uint32_t last, Device* d, Partition* prt, GlibcRand* r, FoldGate* gate);
 	bool unitMode = false;      // this smurfIt call shards by (fold, partition) unit
 	uint32_t foldBase = 0, foldsRun = 0;   // first fold and number of folds of this smurfIt call

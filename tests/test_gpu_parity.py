@@ -89,6 +89,47 @@ def test_device_rand_replay_equals_host_draws(ctx, oracle):
         assert np.array_equal(got.view(np.uint64), want[p].view(np.uint64))
 
 
+def test_device_folds_equal_the_host_test_train_divider(ctx, oracle):
+    """psm_fold_begin_device: the four index arrays of every fold, built from the per-class fold lists on the device, with the
+    training negatives shuffled by the device replay of std::random_shuffle on glibc rand() (csrc/shuffle.cu) == the host
+    TestTrainDivider == the reference's arrays (tests/test_host_logic.py::test_ttd_matches_oracle pins the host ones)"""
+    from parsmurf_b200 import _capi as psm
+    from parsmurf_b200 import host_api as H
+    rng = np.random.default_rng(5)
+    for n, npos, nF in ((3000, 100, 5), (20011, 37, 3), (257, 9, 4), (70000, 1200, 10)):
+        y = np.zeros(n, np.uint32); y[rng.choice(n, npos, replace=False)] = 1
+        f = rng.integers(0, nF, n).astype(np.uint32)
+        x = oracle.make_x(rng.standard_normal((n, 3)), y)
+        ctx.dataset_upload(x)
+        pos = [np.flatnonzero((f == k) & (y == 1)).astype(np.uint32) for k in range(nF)]
+        neg = [np.flatnonzero((f == k) & (y == 0)).astype(np.uint32) for k in range(nF)]
+        off = lambda parts: np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.uint32)
+        ctx.folds_upload(np.concatenate(pos), off(pos), np.concatenate(neg), off(neg))
+        w = psm.glibc_initial_window(1)
+        for k in range(nF):
+            want = H.ttd_fold(y, f, nF, k)
+            ctx.fold_begin_device(k, w)
+            got = ctx.fold_indices_get()
+            for key in ("trngPos", "trngNeg", "testPos", "testNeg"):
+                assert np.array_equal(got[key], want[key]), (n, k, key)
+            assert not np.array_equal(got["trngNeg"], np.sort(got["trngNeg"]))          # really shuffled
+            w = psm.glibc_jump(w, max(len(want["trngNeg"]) - 1, 0))                      # fold k's shuffle consumed trngNeg - 1 draws
+        ctx.fold_begin_device(0, None)                                                   # no window: training negatives in list order
+        got = ctx.fold_indices_get()
+        assert np.array_equal(got["trngNeg"], np.concatenate(neg[1:]))
+
+
+def test_host_and_device_folds_give_the_same_cv(oracle, monkeypatch):
+    from parsmurf_b200 import host_api as H
+    case = make_case("fy_26")
+    x = oracle.make_x(case["X"], case["y"])
+    args = (x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
+    a = H.cv_run(*args, tie_mode=0)
+    monkeypatch.setenv("PSM_HOST_FOLDS", "1")
+    c = H.cv_run(*args, tie_mode=0)
+    assert np.array_equal(a["class1"].view(np.uint64), c["class1"].view(np.uint64)) and np.array_equal(a["fold_metrics"], c["fold_metrics"])
+
+
 def test_cv_through_host_classes_bit_exact(oracle):
     """the whole CV through the C++ host mirror (hyperSMURF::smurfIt) == the oracle == the reference at ensThrd 1"""
     from parsmurf_b200 import host_api as H
