@@ -88,6 +88,11 @@ int psm_scores_fold_curves_device(psm_ctx* ctx, uint32_t fold, int tie_mode, dou
  *      missing slots = -1 / +inf.  localk = min(k, P).  Computed once per fold (fact: pos is the same for
  *      every partition, src/sampler.cpp:69). ---------------------------------------------------------------- */
 int psm_fold_knn(psm_ctx* ctx, uint32_t k);
+/* How the last psm_fold_knn ran: *path = 0 exact fp64 kernel; 1 tensor-core candidate search (tcgen05 3xTF32 distance GEMM)
+ * + exact fp64 rerank, proven complete for every query; 2 the tensor path left *incomplete queries unproven and the fold was
+ * redone with the exact kernel.  The neighbour table is the same in all three cases.  The tensor path is taken when
+ * P*P*m >= 2^33 and m >= 64 and k <= 28, or forced / forbidden with the environment variable PSM_KNN_TENSOR=1 / 0. */
+int psm_fold_knn_path(psm_ctx* ctx, int* path, uint32_t* incomplete);
 int psm_fold_knn_get(psm_ctx* ctx, int32_t* nnIdx /*[P][localk]*/, double* nnDist /*[P][localk] or NULL*/);
 int psm_fold_knn_set(psm_ctx* ctx, const int32_t* nnIdx, uint32_t localk);   /* inject a neighbour table */
 

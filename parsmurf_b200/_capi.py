@@ -66,6 +66,7 @@ def lib():
         L.psm_fold_indices_get.argtypes = [vp, u32p, u32p, u32p, u32p, u32p]
         L.psm_fold_knn.argtypes = [vp, u32]
         L.psm_fold_knn_get.argtypes = [vp, i32p, dp]
+        L.psm_fold_knn_path.argtypes = [vp, C.POINTER(C.c_int), u32p]
         L.psm_fold_knn_set.argtypes = [vp, i32p, u32]
         L.psm_batch_begin.argtypes = [vp, u32, u32, u32, u32, u32]
         L.psm_batch_assemble.argtypes = [vp, i32p, u64]
@@ -185,6 +186,12 @@ class Context:
     def fold_knn(self, k):
         self._ck(self.L.psm_fold_knn(self.h, k))
         self.localk = min(k, self.P)
+
+    def fold_knn_path(self):
+        """(path, incomplete): 0 exact kernel, 1 tensor-core candidates + exact rerank proven complete, 2 tensor path fell back"""
+        path = C.c_int(0); bad = np.zeros(1, np.uint32)
+        self._ck(self.L.psm_fold_knn_path(self.h, C.byref(path), _p(bad, u32p)))
+        return int(path.value), int(bad[0])
 
     def fold_knn_get(self):
         idx = np.zeros((self.P, self.localk), np.int32); dist = np.zeros((self.P, self.localk))

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace psm;
@@ -51,7 +52,9 @@ struct psm_ctx {
 	uint32_t P = 0, Nneg = 0, nTP = 0, nTN = 0, Nte = 0, localk = 0;
 	bool haveKnn = false;
 	std::vector<uint32_t> hTestIdx;
-	DevBuf dPos, dNeg, dTest, dXp, dNN, dNNd, dKnnScratch, dClass12;
+	DevBuf dPos, dNeg, dTest, dXp, dNN, dNNd, dKnnScratch, dKnnTc, dClass12;
+	int knnPath = 0;
+	uint32_t knnIncomplete = 0;
 
 	// folds on the device (psm_folds_upload): examples of every fold by class; shuffle scratch
 	DevBuf dPosList, dNegList, sKeysA, sKeysB, sValsA, sValsB, sHist, sJ, sDraws, sIn;
@@ -188,7 +191,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	if (!ctx) return PSM_E_ARG;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	DevBuf* bufs[] = {&ctx->dPosList, &ctx->dNegList, &ctx->sKeysA, &ctx->sKeysB, &ctx->sValsA, &ctx->sValsB, &ctx->sHist, &ctx->sJ, &ctx->sDraws, &ctx->sIn, &ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dClass12,
+	DevBuf* bufs[] = {&ctx->dPosList, &ctx->dNegList, &ctx->sKeysA, &ctx->sKeysB, &ctx->sValsA, &ctx->sValsB, &ctx->sHist, &ctx->sJ, &ctx->sDraws, &ctx->sIn, &ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dKnnTc, &ctx->dClass12,
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
 	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dSplitFeat, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1, &ctx->dCls,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dPtask, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
@@ -394,12 +397,35 @@ int psm_fold_knn(psm_ctx* ctx, uint32_t k) {
 	ENSURE(ctx->dXp, (size_t)P * m * 8);
 	ENSURE(ctx->dNN, (size_t)P * localk * 4);
 	ENSURE(ctx->dNNd, (size_t)P * localk * 8);
-	size_t scratchElems = std::min<size_t>((size_t)P * P, std::max<size_t>((size_t)P * 64, (size_t)1 << 27));
-	ENSURE(ctx->dKnnScratch, scratchElems * 8);
 	{
 		ProfScope ps(ctx, K_GATHER, 1);
 		launch_gather_rows(ctx->x, m + 1, m, ctx->dPos.as<uint32_t>(), P, ctx->dXp.as<double>(), ctx->stream);
 	}
+	// large folds: candidates from the tensor cores, exact fp64 rerank (knn_tc.cu); the exact kernel below is the fallback
+	ctx->knnPath = 0; ctx->knnIncomplete = 0;
+	const int C = knn_tensor_candidates((int)localk);
+	const char* envT = getenv("PSM_KNN_TENSOR");
+	const bool tensor = C > 0 && (envT ? atoi(envT) != 0 : ((uint64_t)P * P * m >= (1ull << 33) && m >= 64));
+	if (tensor) {
+		ENSURE(ctx->dKnnTc, knn_tensor_workspace_bytes((int)P, (int)m, C) + 256);
+		ENSURE(ctx->dErr, 16);
+		const uint64_t nKb = (m + 31) / 32, nBlk = (P + 127) / 128;
+		{
+			ProfScope ps(ctx, K_KNN, 5);
+			if (launch_knn_tensor(ctx->dXp.as<double>(), (int)P, (int)m, (int)localk, ctx->dKnnTc.p, ctx->dNN.as<int32_t>(), ctx->dNNd.as<double>(),
+			                      ctx->dErr.as<uint32_t>() + 2, ctx->stream))
+				return fail(ctx, PSM_E_CUDA, "fold_knn: tensor-core launch failed");
+		}
+		(void)nKb; (void)nBlk;
+		uint32_t bad = 0;
+		CU(cudaMemcpyAsync(&bad, ctx->dErr.as<uint32_t>() + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		ctx->knnIncomplete = bad;
+		ctx->knnPath = bad ? 2 : 1;
+		if (!bad) { ctx->localk = localk; ctx->haveKnn = true; return PSM_OK; }
+	}
+	size_t scratchElems = std::min<size_t>((size_t)P * P, std::max<size_t>((size_t)P * 64, (size_t)1 << 27));
+	ENSURE(ctx->dKnnScratch, scratchElems * 8);
 	{
 		size_t qb = std::min<size_t>(scratchElems / P, P);
 		ProfScope ps(ctx, K_KNN, (int)(2 * ((P + qb - 1) / qb)));
@@ -409,6 +435,13 @@ int psm_fold_knn(psm_ctx* ctx, uint32_t k) {
 	}
 	CU(cudaGetLastError());
 	ctx->localk = localk; ctx->haveKnn = true;
+	return PSM_OK;
+}
+
+int psm_fold_knn_path(psm_ctx* ctx, int* path, uint32_t* incomplete) {
+	if (!ctx || !ctx->haveKnn) return fail(ctx, PSM_E_ARG, "fold_knn_path: no neighbour table");
+	if (path) *path = ctx->knnPath;
+	if (incomplete) *incomplete = ctx->knnIncomplete;
 	return PSM_OK;
 }
 
@@ -988,8 +1021,19 @@ int psm_scores_get(psm_ctx* ctx, double* class1Prob, double* class2Prob) {
 	const double* h = (const double*)ctx->hStage;
 	CU(cudaMemcpyAsync(ctx->hStage, ctx->dGlob.p, need, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	for (uint32_t i = 0; i < ctx->n; i++) class1Prob[i] += h[i];
-	if (class2Prob) for (uint32_t i = 0; i < ctx->n; i++) class2Prob[i] += h[(size_t)ctx->n + i];
+	// the add is a pure memory stream (28M doubles at BASELINE configs[2]): a few host threads instead of one
+	const uint32_t n = ctx->n;
+	const uint32_t nThreads = n >= (1u << 20) ? 4u : 1u;
+	auto addRange = [&](uint32_t a, uint32_t b) {
+		for (uint32_t i = a; i < b; i++) class1Prob[i] += h[i];
+		if (class2Prob) for (uint32_t i = a; i < b; i++) class2Prob[i] += h[(size_t)n + i];
+	};
+	if (nThreads == 1) addRange(0, n);
+	else {
+		std::vector<std::thread> th;
+		for (uint32_t t = 0; t < nThreads; t++) th.emplace_back(addRange, (uint32_t)((uint64_t)n * t / nThreads), (uint32_t)((uint64_t)n * (t + 1) / nThreads));
+		for (auto& x : th) x.join();
+	}
 	return PSM_OK;
 }
 

@@ -52,6 +52,11 @@ struct TrainArgs {
 // knn.cu
 void launch_gather_rows(const double* x, uint32_t ld, uint32_t m, const uint32_t* idx, uint32_t count, double* out, cudaStream_t s);
 int launch_knn(const double* Xp, int P, int m, int localk, double* Dscratch, size_t scratchElems, int32_t* nnIdx, double* nnDist, cudaStream_t s);
+// knn_tc.cu (tcgen05 3xTF32 candidate search + exact fp64 rerank)
+int knn_tensor_candidates(int localk);
+size_t knn_tensor_workspace_bytes(int P, int m, int C);
+int launch_knn_tensor(const double* Xp, int P, int m, int localk, void* workspace, int32_t* nnIdx, double* nnDist, uint32_t* nIncompleteDev,
+                      cudaStream_t s);
 // assemble.cu
 void launch_assemble(const double* x, uint32_t m, const uint32_t* posIdx, uint32_t P, const uint32_t* negIdx, const int32_t* nn,
                      uint32_t localk, uint32_t fp, const int32_t* draws, const PartDesc* parts, uint32_t nPartsBatch,

@@ -150,22 +150,47 @@ void Folds::computeFolds() {
 		}
 	} else {
 		if (fromFile.size() < classSize) throw Error(PSM_E_ARG, "Folds: fold assignment shorter than the label vector");
-		std::vector<uint32_t> hist(nFolds, 0);
-		for (uint32_t i = 0; i < classSize; i++) {
-			const uint32_t v = fromFile[i];
-			if (v >= nFolds) throw Error(PSM_E_ARG, "Folds: fold id out of range");
-			hist[v]++;
-			nPos[v] += labels[i] > 0;
-		}
+		// two passes (count, then place) over contiguous slices of the examples, a few host threads on large inputs: slice t
+		// writes after everything slices < t write, so every fold keeps ascending example order (src/folds.cpp:93-110)
+		const uint32_t nT = classSize >= (1u << 21) ? 4u : 1u;
+		std::vector<std::vector<uint32_t>> hP(nT, std::vector<uint32_t>(nFolds, 0)), hN(nT, std::vector<uint32_t>(nFolds, 0));
+		std::atomic<bool> bad(false);
+		auto slice = [&](uint32_t t, uint32_t* a, uint32_t* b) { *a = (uint32_t)((uint64_t)classSize * t / nT); *b = (uint32_t)((uint64_t)classSize * (t + 1) / nT); };
+		auto run = [&](const std::function<void(uint32_t)>& fn) {
+			if (nT == 1) { fn(0); return; }
+			std::vector<std::thread> th;
+			for (uint32_t t = 0; t < nT; t++) th.emplace_back(fn, t);
+			for (auto& x : th) x.join();
+		};
+		run([&](uint32_t t) {
+			uint32_t a, b; slice(t, &a, &b);
+			for (uint32_t i = a; i < b; i++) {
+				const uint32_t v = fromFile[i];
+				if (v >= nFolds) { bad = true; return; }
+				if (labels[i] > 0) hP[t][v]++; else hN[t][v]++;
+			}
+		});
+		if (bad) throw Error(PSM_E_ARG, "Folds: fold id out of range");
 		foldsIdx[0] = 0;
-		for (uint32_t f = 0; f < nFolds; f++) { nNeg[f] = hist[f] - nPos[f]; foldsIdx[f + 1] = foldsIdx[f] + hist[f]; }
-		offsets();
-		std::vector<uint32_t> cf(foldsIdx.begin(), foldsIdx.end() - 1), cp(posOff.begin(), posOff.end() - 1), cn(negOff.begin(), negOff.end() - 1);
-		for (uint32_t i = 0; i < classSize; i++) {                            // one pass: every fold keeps ascending example order (src/folds.cpp:93-110)
-			const uint32_t bin = fromFile[i];
-			folds[cf[bin]++] = i;
-			if (labels[i] > 0) posList[cp[bin]++] = i; else negList[cn[bin]++] = i;
+		for (uint32_t f = 0; f < nFolds; f++) {
+			for (uint32_t t = 0; t < nT; t++) { nPos[f] += hP[t][f]; nNeg[f] += hN[t][f]; }
+			foldsIdx[f + 1] = foldsIdx[f] + nPos[f] + nNeg[f];
 		}
+		offsets();
+		run([&](uint32_t t) {
+			std::vector<uint32_t> cf(nFolds), cp(nFolds), cn(nFolds);
+			for (uint32_t f = 0; f < nFolds; f++) {
+				uint32_t bp = 0, bn = 0;
+				for (uint32_t q = 0; q < t; q++) { bp += hP[q][f]; bn += hN[q][f]; }
+				cp[f] = posOff[f] + bp; cn[f] = negOff[f] + bn; cf[f] = foldsIdx[f] + bp + bn;
+			}
+			uint32_t a, b; slice(t, &a, &b);
+			for (uint32_t i = a; i < b; i++) {
+				const uint32_t bin = fromFile[i];
+				folds[cf[bin]++] = i;
+				if (labels[i] > 0) posList[cp[bin]++] = i; else negList[cn[bin]++] = i;
+			}
+		});
 	}
 	maxPos = *std::max_element(nPos.begin(), nPos.end());
 	maxNeg = *std::max_element(nNeg.begin(), nNeg.end());

@@ -46,6 +46,40 @@ def test_knn_duplicates_and_missing(ctx, oracle):
     assert np.isinf(dist[0, 4]) and np.isinf(dist[0, 5])
 
 
+def test_tensor_core_knn_gives_the_exact_table(ctx, oracle, monkeypatch):
+    """knn_tc.cu: candidates from the tcgen05 3xTF32 distance GEMM, exact fp64 rerank, completeness proof -- the neighbour
+    table (indices AND fp64 distances) must be the exact kernel's bit for bit, on small folds (every point a candidate),
+    on folds with several 128-row tiles and a ragged feature count, with duplicates, and with near-degenerate data"""
+    rng = np.random.default_rng(17)
+    shapes = [(90, 26, 5), (700, 26, 5), (1500, 200, 10), (1030, 77, 12), (2100, 333, 20), (300, 1000, 10)]
+    paths = []
+    for P, m, k in shapes:
+        n = P + 50
+        X = rng.standard_normal((n, m))
+        if P == 1030:
+            X[:40] = X[40:80]                     # exact duplicates among the positives (zero distances are excluded)
+            X[100:140] = X[140:180] + 1e-9        # near duplicates: distances far below the fp32 error of the candidate search
+        y = np.zeros(n, np.uint32); y[:P] = 1
+        x = oracle.make_x(X, y)
+        ctx.dataset_upload(x)
+        pos = np.arange(P, dtype=np.uint32); neg = np.arange(P, n, dtype=np.uint32)
+        ctx.fold_begin(pos, neg, pos[:1], neg[:1])
+        monkeypatch.setenv("PSM_KNN_TENSOR", "0")
+        ctx.fold_knn(k)
+        assert ctx.fold_knn_path()[0] == 0
+        i0, d0 = ctx.fold_knn_get()
+        monkeypatch.setenv("PSM_KNN_TENSOR", "1")
+        ctx.fold_knn(k)
+        path, bad = ctx.fold_knn_path()
+        i1, d1 = ctx.fold_knn_get()
+        assert path in (1, 2)
+        assert np.array_equal(i0, i1), (P, m, k, path, bad)
+        assert np.array_equal(d0.view(np.uint64), d1.view(np.uint64)), (P, m, k, path, bad)
+        paths.append((P, m, path, bad))
+    # well-separated random data must be proven complete by the tensor path itself (no fallback)
+    assert all(path == 1 for P, m, path, bad in paths if P != 1030), paths
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_assemble_bit_exact(ctx, oracle, name):
     case = make_case(name)

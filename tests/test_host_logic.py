@@ -144,3 +144,20 @@ def test_rank_sharding_rules_cover_every_partition_once():
                     assert all(sum(1 for f in range(nF) if sizes[f][k] > 0) <= (nF + world - 1) // world + 1 for k in range(world))   # a rank opens few folds
                 else:
                     assert all(max(srow) - min(srow) <= 1 for srow in sizes)   # every fold balanced over the ranks
+
+
+def test_folds_from_assignment_large_input_threaded_pass():
+    """n >= 2^21 takes the multi-threaded count/place passes of Folds::computeFolds: same arrays as the definition
+    (every fold in ascending example order, src/folds.cpp:93-110)"""
+    from parsmurf_b200 import host_api as H
+    rng = np.random.default_rng(11)
+    n, nF = 2_300_017, 3
+    y = (rng.random(n) < 0.01).astype(np.uint32)
+    f = rng.integers(0, nF, n).astype(np.uint32)
+    for k in range(nF):
+        got = H.ttd_fold(y, f, nF, k)
+        assert np.array_equal(got["testPos"], np.flatnonzero((f == k) & (y == 1)))
+        assert np.array_equal(got["testNeg"], np.flatnonzero((f == k) & (y == 0)))
+        others = [q for q in range(nF) if q != k]
+        assert np.array_equal(got["trngPos"], np.concatenate([np.flatnonzero((f == q) & (y == 1)) for q in others]))
+        assert np.array_equal(np.sort(got["trngNeg"]), np.sort(np.concatenate([np.flatnonzero((f == q) & (y == 0)) for q in others])))
