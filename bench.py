@@ -236,6 +236,13 @@ def run_ours(args, w):
     run_dev = lambda: hdev.cv_run(None, x_device_ptr=x_dev.data_ptr(), n=n, m=m, out=scores, **common)
     run_e2e = lambda: hdev.cv_run(x_host, out=scores, **common)
 
+    if args.single:   # profiling aid (scripts/collect_profiles.sh): just the CVs, no timing regions, no JSON line
+        for _ in range(max(args.steps, 1)):
+            run_dev()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for _ in range(args.warmup):
         run_dev()
     sampler = ClockSampler(local)
@@ -323,6 +330,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fold-lanes", type=int, default=None, help="folds in flight at once (default: the library's)")
+    ap.add_argument("--single", action="store_true", help="run only --steps CVs and exit (for ncu passes)")
     ap.add_argument("--shard", default="unit", choices=["unit", "fold"], help="multi-GPU sharding rule (see host_api.cv_run)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

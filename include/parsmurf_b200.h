@@ -156,6 +156,8 @@ int psm_scores_reset(psm_ctx* ctx);
 int psm_fold_scatter_device(psm_ctx* ctx);
 int psm_fold_curves(psm_ctx* ctx, int tie_mode, double* out);
 int psm_scores_get(psm_ctx* ctx, double* class1Prob, double* class2Prob);
+/* the same, but the host arrays are overwritten instead of added to (no zero-fill and no read-modify-write of 2n doubles) */
+int psm_scores_read(psm_ctx* ctx, double* class1Prob, double* class2Prob);
 int psm_scores_curves(psm_ctx* ctx, int tie_mode, double* out);
 /* Unit-sharded multi-GPU runs (every rank owns a contiguous range of the nFolds x nParts (fold, partition) units and only
  * opens the folds it has units of): the per-rank partial class1Prob/class2Prob[n] arrays are summed ONCE, in place, through

@@ -1009,7 +1009,10 @@ int psm_fold_curves(psm_ctx* ctx, int tie_mode, double* out) {
 	return curves_core(ctx, ctx->dFoldLabels.as<uint32_t>(), ctx->dClass12.as<double>(), nullptr, ctx->Nte, totP, totN, tie_mode, out);
 }
 
-int psm_scores_get(psm_ctx* ctx, double* class1Prob, double* class2Prob) {
+static int scores_fetch(psm_ctx* ctx, double* class1Prob, double* class2Prob, bool overwrite);
+int psm_scores_get(psm_ctx* ctx, double* class1Prob, double* class2Prob) { return scores_fetch(ctx, class1Prob, class2Prob, false); }
+int psm_scores_read(psm_ctx* ctx, double* class1Prob, double* class2Prob) { return scores_fetch(ctx, class1Prob, class2Prob, true); }
+static int scores_fetch(psm_ctx* ctx, double* class1Prob, double* class2Prob, bool overwrite) {
 	if (!ctx || !ctx->haveLabels || !class1Prob) return fail(ctx, PSM_E_ARG, "scores_get: no device scores");
 	const size_t need = (size_t)ctx->n * 16;
 	if (ctx->hStageCap < need) {                       // pinned staging buffer, reused across calls
@@ -1023,8 +1026,13 @@ int psm_scores_get(psm_ctx* ctx, double* class1Prob, double* class2Prob) {
 	CU(cudaStreamSynchronize(ctx->stream));
 	// the add is a pure memory stream (28M doubles at BASELINE configs[2]): a few host threads instead of one
 	const uint32_t n = ctx->n;
-	const uint32_t nThreads = n >= (1u << 20) ? 4u : 1u;
+	const uint32_t nThreads = n >= (1u << 18) ? 4u : 1u;
 	auto addRange = [&](uint32_t a, uint32_t b) {
+		if (overwrite) {
+			memcpy(class1Prob + a, h + a, (size_t)(b - a) * 8);
+			if (class2Prob) memcpy(class2Prob + a, h + (size_t)n + a, (size_t)(b - a) * 8);
+			return;
+		}
 		for (uint32_t i = a; i < b; i++) class1Prob[i] += h[i];
 		if (class2Prob) for (uint32_t i = a; i < b; i++) class2Prob[i] += h[(size_t)n + i];
 	};

@@ -152,7 +152,7 @@ void Folds::computeFolds() {
 		if (fromFile.size() < classSize) throw Error(PSM_E_ARG, "Folds: fold assignment shorter than the label vector");
 		// two passes (count, then place) over contiguous slices of the examples, a few host threads on large inputs: slice t
 		// writes after everything slices < t write, so every fold keeps ascending example order (src/folds.cpp:93-110)
-		const uint32_t nT = classSize >= (1u << 21) ? 4u : 1u;
+		const uint32_t nT = classSize >= (1u << 18) ? 4u : 1u;
 		std::vector<std::vector<uint32_t>> hP(nT, std::vector<uint32_t>(nFolds, 0)), hN(nT, std::vector<uint32_t>(nFolds, 0));
 		std::atomic<bool> bad(false);
 		auto slice = [&](uint32_t t, uint32_t* a, uint32_t* b) { *a = (uint32_t)((uint64_t)classSize * t / nT); *b = (uint32_t)((uint64_t)classSize * (t + 1) / nT); };
@@ -664,7 +664,17 @@ void hyperSMURF::smurfIt() {                                                // s
 			nPart = g.nParts; fp = g.fp; ratio = g.ratio; k = g.k; numTrees = g.nTrees; mtry = g.mtry;
 			part->nPart = nPart; part->fp = fp; part->ratio = ratio;
 		}
-		if (lanesHere > 1 || unitMode) { runFoldsInLanes(startingFold, endingFold, lanesHere); trace_mark("lanes joined, scores merged"); break; }
+		if (lanesHere > 1 || unitMode) {
+			uint32_t lanesNow = lanesHere;
+			if (unitMode) {                                                 // a lane is only worth its set-up with ~48 or more partitions of its own
+				uint64_t mine = 0;
+				for (uint32_t f = startingFold; f < endingFold; f++) { uint32_t a = 0, b = 0; partRange(true, foldsRun, nPart, world, rank, f - foldBase, &a, &b); mine += b - a; }
+				lanesNow = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(mine / 48, 1), std::max<uint32_t>(foldLanes, 1));
+			}
+			runFoldsInLanes(startingFold, endingFold, lanesNow);
+			trace_mark("lanes joined, scores merged");
+			break;
+		}
 		uint32_t first = 0, last = 0;
 		partRange(false, foldsRun, nPart, world, rank, currentFold - foldBase, &first, &last);
 		runFold(currentFold, first, last, dev, part.get(), rng, nullptr);
@@ -707,7 +717,11 @@ void hyperSMURF::smurfIt() {                                                // s
 		}
 	}
 	trace_mark("fold curves done");
-	{ PhaseScope ps(PH_SCATTER); dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob)); }
+	{
+		PhaseScope ps(PH_SCATTER);
+		if (scoresAreOutputs && woptimiz == OPT_NO && !inInternalCV) dev->check(psm_scores_read(dev->ctx, class1Prob, class2Prob));
+		else dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob));
+	}
 	trace_mark("scores on the host");
 	if (inInternalCV) {                                                     // :456-482
 		std::vector<uint32_t> tl; std::vector<double> tp;
@@ -1172,6 +1186,7 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		smurfer.foldLanes = lanes;
 		smurfer.shardUnits = shard_units_default();
 		smurfer.deviceFolds = getenv("PSM_HOST_FOLDS") == nullptr;
+		smurfer.scoresAreOutputs = mode == MODE_CV;          // class1 / class2 of psmh_cv_run are outputs
 		if (world > 1) smurfer.setSharding(rank, world, [&](double* p, uint64_t c) { if (reduce && reduce(reduceUser, p, c)) throw Error(PSM_E_CUDA, "reduce callback failed"); });
 		smurfer.initStandard();                             // starts the per-fold index builders in the background ...
 		tSetup = now_s();

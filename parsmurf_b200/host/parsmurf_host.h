@@ -289,6 +289,9 @@ public:
 	// Build every fold's index arrays (and shuffle its training negatives) on the device instead of on the host
 	// (TestTrainDivider); applies to plain and grid-outer CV folds, the inner CVs and train/predict modes keep the host path.
 	bool deviceFolds = true;
+	// class1Prob / class2Prob are pure outputs of this run (nothing to accumulate onto): the final fetch overwrites them, so
+	// the caller need not zero them (the reference's main() zero-fills and every partition adds, src/parSMURF.cpp:90-93)
+	bool scoresAreOutputs = false;
 	std::vector<double> foldAuroc, foldAuprc;
 	double auroc = 0, auprc = 0;
 

@@ -48,7 +48,7 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     x: host row-major float64 [n][m+1] (label column 1.0/2.0), or None with x_device_ptr/n/m for a dataset already in HBM.
     folds: per-example fold ids, or None for the reference's random stratified folds.
     reduce(dev_ptr, count): sums `count` float64 at device pointer `dev_ptr` across ranks in place (world > 1).
-    out: optional (class1, class2) float64 arrays of length n to reuse; they are zeroed and filled (a fresh 8 MB array costs
+    out: optional (class1, class2) float64 arrays of length n to reuse; they are overwritten (a fresh 8 MB array costs
     more in first-touch page faults than the copy into it).
     fold_lanes: how many folds are in flight at once (one context + stream + host thread each, same results); None keeps the
     library default (PSM_FOLD_LANES or 4).  Kernel times / launch counts are summed over the lanes.
@@ -71,9 +71,9 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     if out is not None:
         c1, c2 = out
         assert c1.dtype == np.float64 and c2.dtype == np.float64 and c1.shape == (n,) and c2.shape == (n,) and c1.flags.c_contiguous and c2.flags.c_contiguous
-        c1.fill(0.0); c2.fill(0.0)
+        # (no zero-fill: psmh_cv_run overwrites both arrays)
     else:
-        c1 = np.zeros(n); c2 = np.zeros(n)
+        c1 = np.empty(n); c2 = np.empty(n)
     met = np.zeros(2); fm = np.zeros((nFolds, 2))
     kms = np.zeros(len(KERNEL_CLASSES)); kl = np.zeros(len(KERNEL_CLASSES), np.uint64); st = np.zeros(3, np.uint64)
     err = C.create_string_buffer(512)

@@ -147,7 +147,7 @@ def test_rank_sharding_rules_cover_every_partition_once():
 
 
 def test_folds_from_assignment_large_input_threaded_pass():
-    """n >= 2^21 takes the multi-threaded count/place passes of Folds::computeFolds: same arrays as the definition
+    """n >= 2^18 takes the multi-threaded count/place passes of Folds::computeFolds: same arrays as the definition
     (every fold in ascending example order, src/folds.cpp:93-110)"""
     from parsmurf_b200 import host_api as H
     rng = np.random.default_rng(11)
