@@ -795,8 +795,9 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 #endif
 constexpr int PL_CH_DEFAULT = PSM_PL_CH;
 
-// the last (< NCH * 32) entries of a segment, fully predicated; NCH = chunk slots compiled in
-template <typename E, int NCH>
+// the last (< NCH * 32) entries of a segment, fully predicated; NCH = chunk slots compiled in.  PRED = some child of the node is
+// terminal and its entries are not written (keepL / keepR); without it the two flags are compile-time true.
+template <typename E, int NCH, bool PRED>
 __device__ __forceinline__ void partition_tail(const E* srcp, E* dstp, const uint32_t* fbits, uint32_t b, uint32_t cnt, uint32_t lane, unsigned lt,
                                                uint32_t offL, uint32_t offR, bool keepL, bool keepR) {
 	E e[NCH];
@@ -814,8 +815,40 @@ __device__ __forceinline__ void partition_tail(const E* srcp, E* dstp, const uin
 		const uint32_t pL = __popc(mL & lt), nL = __popc(mL);
 		const uint32_t nv = first < cnt ? min(32u, cnt - first) : 0u;
 		const uint32_t idx = gl ? offL + pL : offR + lane - pL;
-		if (valid && (gl ? keepL : keepR)) dstp[idx] = e[c];
+		if (valid && (!PRED || (gl ? keepL : keepR))) dstp[idx] = e[c];
 		offL += nL; offR += nv - nL;
+	}
+}
+
+template <typename E, int PL_CH, bool PRED>
+__device__ __forceinline__ void partition_segment(const E* srcp, E* dstp, const uint32_t* fbits, uint32_t cnt, uint32_t nleft, uint32_t lane, unsigned lt,
+                                                  bool keepL, bool keepR) {
+	// Short segments (the mid and deep levels: ncu r01 shows 180 warp instructions for an 89-entry segment because all
+	// PL_CH predicated slots of the tail are issued) take a tail with only as many chunk slots as they need.
+	if (cnt <= 32) { partition_tail<E, 1, PRED>(srcp, dstp, fbits, 0, cnt, lane, lt, 0, nleft, keepL, keepR); return; }
+	if (cnt <= 64) { partition_tail<E, 2, PRED>(srcp, dstp, fbits, 0, cnt, lane, lt, 0, nleft, keepL, keepR); return; }
+	uint32_t offL = 0, offR = nleft;                           // next free slot of the left / right child segment
+	uint32_t b = 0;
+	// full groups of PL_CH * 32 entries: no bounds logic at all (what the long segments of the first levels run)
+	for (; b + 32 * PL_CH <= cnt; b += 32 * PL_CH, srcp += 32 * PL_CH) {
+		E e[PL_CH];
+		uint32_t w[PL_CH];
+#pragma unroll
+		for (int c = 0; c < PL_CH; c++) e[c] = __ldg(srcp + c * 32);
+#pragma unroll
+		for (int c = 0; c < PL_CH; c++) w[c] = __ldg(fbits + (Ent<E>::row(e[c]) >> 5));
+#pragma unroll
+		for (int c = 0; c < PL_CH; c++) {
+			const bool gl = (w[c] >> (Ent<E>::row(e[c]) & 31u)) & 1u;
+			const unsigned mL = __ballot_sync(0xffffffffu, gl);
+			const uint32_t pL = __popc(mL & lt), nL = __popc(mL);
+			if (!PRED || (gl ? keepL : keepR)) dstp[gl ? offL + pL : offR + lane - pL] = e[c];
+			offL += nL; offR += 32 - nL;
+		}
+	}
+	if (b < cnt) {
+		if (cnt - b <= 64) partition_tail<E, 2, PRED>(srcp, dstp, fbits, b, cnt, lane, lt, offL, offR, keepL, keepR);
+		else partition_tail<E, PL_CH, PRED>(srcp, dstp, fbits, b, cnt, lane, lt, offL, offR, keepL, keepR);
 	}
 }
 
@@ -842,34 +875,11 @@ __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint3
 	// The kernel is issue-bound (ncu r01: 72% issue-active at 44% of DRAM peak, 53 instructions per 32-entry chunk), so the
 	// loop is written for instruction count: 32-bit indices off two base pointers, one ballot per chunk (the valid lanes of a
 	// chunk are a prefix, so a lane's rank among the right-goers is lane - rank among the left-goers), one store per entry,
-	// and an unpredicated flag load (an invalid lane carries entry 0 -> row 0, a legal address).
-	// Short segments (the mid and deep levels: ncu r01 shows 180 warp instructions for an 89-entry segment because all
-	// PL_CH predicated slots of the tail are issued) take a tail with only as many chunk slots as they need.
-	if (cnt <= 32) { partition_tail<E, 1>(srcp, dstp, fbits, 0, cnt, lane, lt, 0, nleft, keepL, keepR); return; }
-	if (cnt <= 64) { partition_tail<E, 2>(srcp, dstp, fbits, 0, cnt, lane, lt, 0, nleft, keepL, keepR); return; }
-	uint32_t offL = 0, offR = nleft;                           // next free slot of the left / right child segment
-	uint32_t b = 0;
-	// full groups of PL_CH * 32 entries: no bounds logic at all (what the long segments of the first levels run)
-	for (; b + 32 * PL_CH <= cnt; b += 32 * PL_CH, srcp += 32 * PL_CH) {
-		E e[PL_CH];
-		uint32_t w[PL_CH];
-#pragma unroll
-		for (int c = 0; c < PL_CH; c++) e[c] = __ldg(srcp + c * 32);
-#pragma unroll
-		for (int c = 0; c < PL_CH; c++) w[c] = __ldg(fbits + (Ent<E>::row(e[c]) >> 5));
-#pragma unroll
-		for (int c = 0; c < PL_CH; c++) {
-			const bool gl = (w[c] >> (Ent<E>::row(e[c]) & 31u)) & 1u;
-			const unsigned mL = __ballot_sync(0xffffffffu, gl);
-			const uint32_t pL = __popc(mL & lt), nL = __popc(mL);
-			if (gl ? keepL : keepR) dstp[gl ? offL + pL : offR + lane - pL] = e[c];
-			offL += nL; offR += 32 - nL;
-		}
-	}
-	if (b < cnt) {
-		if (cnt - b <= 64) partition_tail<E, 2>(srcp, dstp, fbits, b, cnt, lane, lt, offL, offR, keepL, keepR);
-		else partition_tail<E, PL_CH>(srcp, dstp, fbits, b, cnt, lane, lt, offL, offR, keepL, keepR);
-	}
+	// and an unpredicated flag load (an invalid lane carries entry 0 -> row 0, a legal address).  The store predicate of the
+	// terminal-child case costs ~20% more instructions in the main loop (ncu r01), so nodes whose children both live on --
+	// all the long segments of the first levels -- run the copy of the code without it.
+	if (keepL && keepR) partition_segment<E, PL_CH, false>(srcp, dstp, fbits, cnt, nleft, lane, lt, true, true);
+	else partition_segment<E, PL_CH, true>(srcp, dstp, fbits, cnt, nleft, lane, lt, keepL, keepR);
 }
 
 // ------------------------------------------------------------------------------------------ launchers
