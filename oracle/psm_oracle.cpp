@@ -403,12 +403,14 @@ void psmo_curves(const uint32_t* labels, const double* preds, uint64_t N, double
 
 static int cv_impl(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
             uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
-            uint32_t fold0, uint32_t fold1, uint32_t nthreads, uint32_t part0, uint32_t part1, double* class1, double* class2) {
+            uint32_t fold0, uint32_t fold1, uint32_t nthreads, uint32_t part0, uint32_t part1, double* class1, double* class2,
+            const uint32_t* firstOfFold = nullptr, const uint32_t* lastOfFold = nullptr) {
 	GlibcRand g(1);                                                  // rand() is never seeded for seed != 0 (fact #5)
 	OTTD* ttd = build_ttd(labels, foldAssign, n, nFolds, &g);
 	const size_t ld = (size_t)m + 1;
 	int rc = 0;
 	for (uint32_t f = fold0; f < fold1 && rc == 0; f++) {
+		if (firstOfFold) { part0 = firstOfFold[f]; part1 = lastOfFold[f]; }   // per-fold share (unit-sharded ranks)
 		const auto& tp = ttd->trngPos[f]; const auto& tn = ttd->trngNeg[f];
 		const uint32_t P = tp.size();
 		const uint32_t localk = std::min<uint32_t>(k, P);               // samplerKNN.cpp:52
@@ -471,6 +473,14 @@ int psmo_cv_parts(const double* x, uint32_t n, uint32_t m, const uint32_t* label
                   uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
                   uint32_t part0, uint32_t part1, double* class1, double* class2) {
 	return cv_impl(x, n, m, labels, foldAssign, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, 0, nFolds, 1, part0, part1, class1, class2);
+}
+
+// the same with a partition range per fold: [first[f], last[f]) of fold f (the share of one rank when the nFolds x nParts units
+// are cut into contiguous ranges, parsmurf::hyperSMURF::partRange)
+int psmo_cv_ranges(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+                   uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
+                   const uint32_t* first, const uint32_t* last, double* class1, double* class2) {
+	return cv_impl(x, n, m, labels, foldAssign, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, 0, nFolds, 1, 0, 0, class1, class2, first, last);
 }
 
 }  // extern "C"

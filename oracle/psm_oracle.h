@@ -80,6 +80,9 @@ int psmo_cv(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, con
 int psmo_cv_parts(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
                   uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
                   uint32_t part0, uint32_t part1, double* class1, double* class2);
+int psmo_cv_ranges(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+                   uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
+                   const uint32_t* first, const uint32_t* last, double* class1, double* class2);
 
 #ifdef __cplusplus
 }

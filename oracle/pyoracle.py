@@ -66,6 +66,7 @@ def oracle_lib():
         L.psmo_curves.argtypes = [u32p, dp, u64, dp, u64p]
         L.psmo_cv.argtypes = [dp, u32, u32, u32p, u32p] + [u32] * 11 + [dp, dp]
         L.psmo_cv_parts.argtypes = [dp, u32, u32, u32p, u32p] + [u32] * 10 + [dp, dp]
+        L.psmo_cv_ranges.argtypes = [dp, u32, u32, u32p, u32p] + [u32] * 8 + [u32p, u32p, dp, dp]
         _oracle = L
     return _oracle
 
@@ -234,6 +235,17 @@ def o_cv_parts(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, see
     c1 = np.zeros(n); c2 = np.zeros(n)
     rc = oracle_lib().psmo_cv_parts(_p(x, dp), n, ld - 1, _p(labels, u32p), _p(folds, u32p), nFolds, nParts, fp, ratio, k, nTrees, mtry, seed,
                                     part0, part1, _p(c1, dp), _p(c2, dp))
+    return rc, c1, c2
+
+
+def o_cv_ranges(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, first, last):
+    """only partitions [first[f], last[f]) of fold f contribute (a unit-sharded rank's share)"""
+    n, ld = x.shape
+    labels = np.ascontiguousarray(labels, np.uint32); folds = np.ascontiguousarray(folds, np.uint32)
+    first = np.ascontiguousarray(first, np.uint32); last = np.ascontiguousarray(last, np.uint32)
+    c1 = np.zeros(n); c2 = np.zeros(n)
+    rc = oracle_lib().psmo_cv_ranges(_p(x, dp), n, ld - 1, _p(labels, u32p), _p(folds, u32p), nFolds, nParts, fp, ratio, k, nTrees, mtry, seed,
+                                     _p(first, u32p), _p(last, u32p), _p(c1, dp), _p(c2, dp))
     return rc, c1, c2
 
 

@@ -409,14 +409,12 @@ int psm_fold_knn(psm_ctx* ctx, uint32_t k) {
 	if (tensor) {
 		ENSURE(ctx->dKnnTc, knn_tensor_workspace_bytes((int)P, (int)m, C) + 256);
 		ENSURE(ctx->dErr, 16);
-		const uint64_t nKb = (m + 31) / 32, nBlk = (P + 127) / 128;
 		{
 			ProfScope ps(ctx, K_KNN, 5);
 			if (launch_knn_tensor(ctx->dXp.as<double>(), (int)P, (int)m, (int)localk, ctx->dKnnTc.p, ctx->dNN.as<int32_t>(), ctx->dNNd.as<double>(),
 			                      ctx->dErr.as<uint32_t>() + 2, ctx->stream))
 				return fail(ctx, PSM_E_CUDA, "fold_knn: tensor-core launch failed");
 		}
-		(void)nKb; (void)nBlk;
 		uint32_t bad = 0;
 		CU(cudaMemcpyAsync(&bad, ctx->dErr.as<uint32_t>() + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
 		CU(cudaStreamSynchronize(ctx->stream));

@@ -268,6 +268,11 @@ def test_unit_sharded_ranks_reproduce_the_single_rank_cv(oracle):
               return out, got
           partial = [run(r)[1][0] for r in range(W)]                          # pass 1: every rank's partial class1Prob/class2Prob
           assert all(np.abs(p).sum() > 0 for p in partial)
+          if lanes == 1 and nParts == 4:                                      # a whole-fold share per lane: the rank's partial sums are the oracle's, bit for bit
+              for r in range(W):
+                  rng_ = [H.part_range(True, nF, nParts, W, r, f) for f in range(nF)]
+                  rc, o1, o2 = oracle.o_cv_ranges(*args, [a for a, b in rng_], [b for a, b in rng_])
+                  assert np.array_equal(partial[r][:n].view(np.uint64), o1.view(np.uint64)) and np.array_equal(partial[r][n:].view(np.uint64), o2.view(np.uint64)), r
           tot = sum(partial)
           assert np.allclose(tot[:n], full["class1"], rtol=0, atol=1e-13) and np.allclose(tot[n:], full["class2"], rtol=0, atol=1e-13)   # fp64 addition order across ranks
           others = lambda r, xs: sum(xs[q] for q in range(W) if q != r)

@@ -21,6 +21,26 @@ def chunk(nParts, world, rank):
     return first, first + cnt[rank]
 
 
+def _unit_worker(rank, world, port, q):
+    """unit sharding (the default of the GPU path): contiguous ranges of the nFolds x nParts units, ONE all-reduce of the score arrays"""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import make_case
+    from oracle import pyoracle as O
+    from parsmurf_b200 import host_api as H
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c = make_case("fy_26")
+    x = O.make_x(c["X"], c["y"])
+    rng = [H.part_range(True, c["nF"], c["nParts"], world, rank, f) for f in range(c["nF"])]
+    rc, c1, c2 = O.o_cv_ranges(x, c["y"], c["f"], c["nF"], c["nParts"], c["fp"], c["ratio"], c["k"], c["T"], c["mtry"], 7, [a for a, b in rng], [b for a, b in rng])
+    t = torch.from_numpy(np.stack([c1, c2]))
+    dist.all_reduce(t)                                                  # the one cross-rank sum of a unit-sharded CV
+    if rank == 0:
+        q.put(t.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import make_case
@@ -56,6 +76,26 @@ def test_two_rank_gloo_allreduce_equals_single_rank():
     q = ctx.Queue()
     port = 29500 + os.getpid() % 2000
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    c = make_case("fy_26")
+    x = O.make_x(c["X"], c["y"])
+    rc, c1, c2 = O.o_cv(x, c["y"], c["f"], c["nF"], c["nParts"], c["fp"], c["ratio"], c["k"], c["T"], c["mtry"], 7)
+    assert np.allclose(got[0], c1, rtol=0, atol=1e-15) and np.allclose(got[1], c2, rtol=0, atol=1e-15)
+
+
+def test_three_rank_gloo_unit_sharding_equals_single_rank():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import make_case
+    from oracle import pyoracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_unit_worker, args=(r, 3, port, q)) for r in range(3)]
     for p in procs:
         p.start()
     got = q.get(timeout=240)
