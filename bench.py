@@ -266,12 +266,13 @@ def run_ours(args, w):
     parts = w["nParts"] * w["nFolds"]
     value = parts * args.steps / (ms_dev / 1000.0)
     e2e_value = parts * args.steps / (ms_e2e / 1000.0)
-    # per-step traffic of the e2e path, counted from what is copied: x once, the 0/1 labels once, per fold the four index
-    # arrays (train pos/neg, test pos/neg) plus the test index list; SMOTE draws are generated on the device (no H2D).
-    nte = n // w["nFolds"]
-    h2d = x.nbytes + 4 * n + w["nFolds"] * 4 * (n + nte)
-    # back: class1Prob/class2Prob once (2 x n f64), AUROC/AUPRC per fold and global, a 16-byte status word per tree level
-    d2h = 16 * n + (w["nFolds"] + 1) * 16 + 16 * int(sum(o["stats"]["levels"] for o in outs_e2e) / max(args.steps, 1))
+    # per-step traffic of the e2e path (this rank), counted from what is copied: x once, the 0/1 labels once per fold lane, the
+    # per-class fold lists once (n example ids: every fold's index arrays are assembled and shuffled on the device); SMOTE and
+    # shuffle draws are generated on the device (no H2D).
+    lanes = outs_e2e[0].get("fold_lanes") or 1
+    h2d = x.nbytes + 4 * n * lanes + 4 * n
+    # back: class1Prob/class2Prob once (2 x n f64), AUROC/AUPRC per fold and global, a 32-byte status word per tree level
+    d2h = 16 * n + (w["nFolds"] + 1) * 16 + 32 * int(sum(o["stats"]["levels"] for o in outs_e2e) / max(args.steps, 1))
 
     # roofline of the dominant training kernel over the timed region (this rank's kernels)
     km = {k_: sum(o["kernel_ms"][k_] for o in outs_roof) for k_ in outs_roof[0]["kernel_ms"]}
