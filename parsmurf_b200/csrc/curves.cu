@@ -85,26 +85,29 @@ __global__ void __launch_bounds__(CB) tp_blocksum_kernel(const unsigned char* __
 	if (threadIdx.x == 0) blockSums[blockIdx.x] = t;
 }
 
-// single block: exclusive scan of blockSums in place
+// single block: exclusive scan of `a` in place.  Every thread owns a contiguous run of counters (serial sum, one block scan of the
+// 1024 run totals, serial write-back): three barriers in all.  (The first version walked the array 1024 counters at a time with
+// two barriers per step -- 33 us for the 63k digit counters of a 1M-key radix pass, 78 such launches per BASELINE configs[1] CV.)
 __global__ void __launch_bounds__(1024) scan_blocksums_kernel(uint32_t* __restrict__ a, uint32_t n) {
 	__shared__ uint32_t wsum[32];
-	__shared__ uint32_t carry;
-	if (threadIdx.x == 0) carry = 0;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const uint32_t per = (n + 1023) / 1024;
+	const uint32_t b = min(tid * per, n), e = min(b + per, n);
+	uint32_t tot = 0;
+	for (uint32_t i = b; i < e; i++) tot += a[i];
+	uint32_t inc = tot;
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += t; }
+	if (lane == 31) wsum[w] = inc;
 	__syncthreads();
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	for (uint32_t b = 0; b < n; b += 1024) {
-		uint32_t i = b + threadIdx.x;
-		uint32_t v = i < n ? a[i] : 0, inc = v;
-		for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-		if (lane == 31) wsum[w] = inc;
-		__syncthreads();
-		uint32_t off = carry;
-		for (int ww = 0; ww < w; ww++) off += wsum[ww];
-		if (i < n) a[i] = off + inc - v;
-		__syncthreads();
-		if (threadIdx.x == 1023) carry = off + inc;
-		__syncthreads();
+	if (w == 0) {
+		const uint32_t v = wsum[lane];
+		uint32_t s = v;
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= (uint32_t)o) s += t; }
+		wsum[lane] = s - v;                                // exclusive prefix of the warp totals
 	}
+	__syncthreads();
+	uint32_t off = wsum[w] + inc - tot;
+	for (uint32_t i = b; i < e; i++) { const uint32_t v = a[i]; a[i] = off; off += v; }
 }
 
 // TP[i] (inclusive) for a block's tile, element order i = b0 + t*CI + k (thread-contiguous so the scan is a

@@ -92,16 +92,26 @@ __global__ void __launch_bounds__(128) build_lists_kernel(TrainArgs A) {
 	E* out = reinterpret_cast<E*>(A.lists[0]) + ((size_t)tree * A.m + f) * A.stride;
 	uint32_t off = 0;
 	bool bad = false;
-	for (uint32_t b = 0; b < pd.Ntr; b += 32) {
-		uint32_t i = b + lane;
-		entry_t e = (i < pd.Ntr) ? S[i] : 0;
-		uint32_t row = e_row(e);
-		uint32_t c = (i < pd.Ntr) ? cnt[row] : 0;
-		bool keep = c > 0;
-		if (c > Ent<E>::kMaxCountE) bad = true;
-		unsigned mk = __ballot_sync(0xffffffffu, keep);
-		if (keep) out[off + __popc(mk & lanemask_lt())] = Ent<E>::make(row, e_rank(e), c, row >= pd.nPosOut ? 1u : 0u);
-		off += __popc(mk);
+	// four 32-entry groups per trip: the in-bag lookups are dependent gathers (ncu r01: 36% issue-active, L1-bound), so the loads
+	// of all four groups are issued before the first compaction
+	constexpr int BL_U = 4;
+	const unsigned lt = lanemask_lt();
+	for (uint32_t b = 0; b < pd.Ntr; b += 32 * BL_U) {
+		entry_t e[BL_U];
+		uint32_t c[BL_U];
+#pragma unroll
+		for (int u = 0; u < BL_U; u++) { const uint32_t i = b + u * 32 + lane; e[u] = (i < pd.Ntr) ? S[i] : 0; }
+#pragma unroll
+		for (int u = 0; u < BL_U; u++) { const uint32_t i = b + u * 32 + lane; c[u] = (i < pd.Ntr) ? cnt[e_row(e[u])] : 0; }
+#pragma unroll
+		for (int u = 0; u < BL_U; u++) {
+			const uint32_t row = e_row(e[u]);
+			const bool keep = c[u] > 0;
+			if (c[u] > Ent<E>::kMaxCountE) bad = true;
+			const unsigned mk = __ballot_sync(0xffffffffu, keep);
+			if (keep) out[off + __popc(mk & lt)] = Ent<E>::make(row, e_rank(e[u]), c[u], row >= pd.nPosOut ? 1u : 0u);
+			off += __popc(mk);
+		}
 	}
 	if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&A.counters[CNT_ERROR], ERR_COUNT_LIMIT);
 	if (f == 0 && lane == 0) A.ts[tree].nEntries = off;
