@@ -88,6 +88,9 @@ def ref_lib():
         L.ref_partition_maxsize.argtypes = [vp, u32, u32, u32]
         L.ref_sample_partition.restype = C.c_int64
         L.ref_sample_partition.argtypes = [vp, u32, u32, u32, u32, u32, u32, dp, u64, u32p, i32p, u64]
+        L.ref_import.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, u64p, dp, u32p, u32p]
+        L.ref_save.argtypes = [dp, dp, u32, u32p, C.c_char_p]
+        L.ref_save.restype = None
         L.ref_knn.argtypes = [dp, C.c_int, C.c_int, C.c_int, i32p, dp, C.c_int]
         L.ref_forest_train.restype = vp
         L.ref_forest_train.argtypes = [dp, u32, u32, u32, u32, u32, u32]
@@ -250,6 +253,24 @@ def o_cv_ranges(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, se
 
 
 # --------------------------------------------------------------------------- reference API
+def ref_import(data_file, label_file, fold_file=None):
+    """the reference's Importer::import -> (x flat with the label column appended per row, y, f, nFolds)"""
+    L = ref_lib()
+    sz = np.zeros(4, np.uint64)
+    enc = lambda s: None if s is None else str(s).encode()
+    if L.ref_import(enc(data_file), enc(label_file), enc(fold_file), _p(sz, u64p), None, None, None) != 0:
+        raise RuntimeError("reference importer failed")
+    x = np.zeros(int(sz[0])); y = np.zeros(int(sz[1]), np.uint32); f = np.zeros(int(sz[2]), np.uint32)
+    L.ref_import(enc(data_file), enc(label_file), enc(fold_file), _p(sz, u64p), _p(x, dp), _p(y, u32p), _p(f, u32p))
+    return x, y, f, int(sz[3])
+
+
+def ref_save(c1, c2, labels, path):
+    c1 = np.ascontiguousarray(c1, np.float64); c2 = np.ascontiguousarray(c2, np.float64)
+    lab = None if labels is None else np.ascontiguousarray(labels, np.uint32)
+    ref_lib().ref_save(_p(c1, dp), _p(c2, dp), len(c1), _p(lab, u32p), str(path).encode())
+
+
 class RefCtx:
     def __init__(self, x, labels, folds, nFolds, reset_rand=True):
         self.L = ref_lib()

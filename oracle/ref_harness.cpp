@@ -31,6 +31,7 @@
 #include "ForestProbability.h"
 #include "DataDouble.h"
 #include "hyperSMURF.h"
+#include "fileImport.h"
 #include "ANN.h"
 
 // ---------------------------------------------------------------- rand() recorder
@@ -354,5 +355,33 @@ double ref_run_partitions(void* h, uint32_t fold, uint32_t p0, uint32_t p1, uint
 }
 
 int ref_num_procs(void) { return omp_get_num_procs(); }
+
+// Importer::import (src/fileImport.cpp:5-100) on the three text files; sizes = {x.size(), y.size(), f.size(), nFolds}.
+// Call once with x = NULL to get the sizes, then with buffers of those sizes.  (The reference's progress messages go to stdout.)
+int ref_import(const char* dataFile, const char* labelFile, const char* foldFile, uint64_t* sizes, double* x, uint32_t* y, uint32_t* f) {
+	try {
+		std::vector<GridParams> gp;
+		char prog[] = "ref"; char* argv[] = {prog, nullptr};
+		ArgHandle ah(1, argv, gp);
+		ah.dataFilename = dataFile; ah.labelFilename = labelFile; ah.foldFilename = foldFile ? foldFile : "";
+		std::vector<double> xx; std::vector<uint32_t> yy, ff;
+		uint32_t nFolds = 0;
+		std::streambuf* old = std::cout.rdbuf(nullptr);          // silence the importer's chatter
+		try { Importer::import(&ah, xx, yy, ff, &nFolds); } catch (...) { std::cout.rdbuf(old); throw; }
+		std::cout.rdbuf(old);
+		sizes[0] = xx.size(); sizes[1] = yy.size(); sizes[2] = ff.size(); sizes[3] = nFolds;
+		if (x) std::memcpy(x, xx.data(), xx.size() * sizeof(double));
+		if (y) std::memcpy(y, yy.data(), yy.size() * sizeof(uint32_t));
+		if (f) std::memcpy(f, ff.data(), ff.size() * sizeof(uint32_t));
+		return 0;
+	} catch (...) { return -1; }
+}
+
+// saveToFile (src/HyperSMURFUtils.cpp:66-86); labels == NULL -> the two-column form main() writes for data read from files
+void ref_save(const double* c1, const double* c2, uint32_t n, const uint32_t* labels, const char* path) {
+	std::vector<uint32_t> lab;
+	if (labels) lab.assign(labels, labels + n);
+	saveToFile(c1, c2, n, &lab, path);
+}
 
 }  // extern "C"

@@ -1,6 +1,6 @@
 // parsmurf_b200_cv -- command-line driver with parSMURF1's configuration surface:  parsmurf_b200_cv --cfg file.json
-// (reference src/parSMURF.cpp:23-140, src/ArgHandler_new.cpp:19-82).  Text ingest is deliberately minimal
-// (whitespace/comma separated; one example per line) -- data import is outside the accelerated path.
+// (reference src/parSMURF.cpp:23-140, src/ArgHandler_new.cpp:19-82).  Data files are read by parsmurf::Importer (the reference's
+// text format, or the PSMB1 binary side channel), predictions are written by parsmurf::saveToFile (ingest.cpp).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -13,22 +13,6 @@
 #include "parsmurf_host.h"
 
 using namespace parsmurf;
-
-static std::vector<double> read_numbers(const std::string& path, size_t* firstLineCols) {
-	std::ifstream f(path.c_str());
-	if (!f) throw Error(PSM_E_ARG, "cannot open " + path);
-	std::vector<double> out;
-	std::string line;
-	bool first = true;
-	while (std::getline(f, line)) {
-		for (char& c : line) if (c == ',' || c == '\t') c = ' ';
-		std::istringstream ss(line);
-		double v; size_t cols = 0;
-		while (ss >> v) { out.push_back(v); cols++; }
-		if (first && cols) { if (firstLineCols) *firstLineCols = cols; first = false; }
-	}
-	return out;
-}
 
 int main(int argc, char** argv) {
 	std::string cfgPath; int device = 0, tieMode = 0;
@@ -57,26 +41,11 @@ int main(int argc, char** argv) {
 				x[(size_t)i * (m + 1) + m] = y[i] ? 1.0 : 2.0;
 			}
 		} else {
-			std::vector<double> lab = read_numbers(cfg.labelFilename, nullptr);
-			n = (uint32_t)lab.size();
-			y.resize(n);
-			for (uint32_t i = 0; i < n; i++) y[i] = lab[i] > 0;
-			size_t cols = 0;
-			std::vector<double> d = read_numbers(cfg.dataFilename, &cols);
-			if (n == 0 || d.size() % n) throw Error(PSM_E_ARG, "size mismatch between label and data file");
-			m = (uint32_t)(d.size() / n);
-			x.resize((size_t)n * (m + 1));
-			for (uint32_t i = 0; i < n; i++) {
-				memcpy(&x[(size_t)i * (m + 1)], &d[(size_t)i * m], m * sizeof(double));
-				x[(size_t)i * (m + 1) + m] = y[i] ? 1.0 : 2.0;               // src/fileImport.cpp:88-91
-			}
-			if (!cfg.foldFilename.empty()) {
-				std::vector<double> fv = read_numbers(cfg.foldFilename, nullptr);
-				if (fv.size() != n) throw Error(PSM_E_ARG, "fold file size mismatch");
-				ff.resize(n);
-				for (uint32_t i = 0; i < n; i++) ff[i] = (uint32_t)fv[i];
-				cfg.common.nFolds = *std::max_element(ff.begin(), ff.end()) + 1;
-			}
+			uint32_t nFoldsFromFile = 0;
+			Importer::import(cfg.dataFilename, cfg.labelFilename, cfg.foldFilename, x, y, ff, &nFoldsFromFile, &m);   // src/parSMURF.cpp:68-77
+			n = (uint32_t)y.size();
+			for (auto& v : y) v = v > 0;                                     // labels are used as 0 / 1 from here on
+			if (!ff.empty()) cfg.common.nFolds = nFoldsFromFile;
 		}
 		cfg.common.nn = n; cfg.common.mm = m;
 		cfg.processMtry(m);
@@ -99,8 +68,8 @@ int main(int argc, char** argv) {
 		}
 		printf("AUROC: %.9g - AUPRC: %.9g  (%u examples, %u features, %.3f s)\n", smurfer.auroc, smurfer.auprc, n, m, secs);
 		if (!cfg.common.timeFilename.empty()) { std::ofstream tf(cfg.common.timeFilename.c_str(), std::ios::app); tf << secs << std::endl; }
-		std::ofstream of(cfg.common.outfilename.c_str());                    // src/HyperSMURFUtils.cpp:66-86
-		for (uint32_t i = 0; i < n; i++) of << class1[i] << "\t" << class2[i] << "\t" << y[i] << std::endl;
+		std::vector<uint32_t> none;                                          // src/parSMURF.cpp:128-137: the label column only for simulated data
+		saveToFile(class1.data(), class2.data(), n, cfg.simulate ? &y : &none, cfg.common.outfilename);
 		return 0;
 	} catch (const Error& e) {
 		fprintf(stderr, "error (%d): %s\n", e.code, e.what());

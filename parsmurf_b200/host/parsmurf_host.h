@@ -323,6 +323,20 @@ private:
 	std::vector<double> tempcl1, tempcl2;
 };
 
+// reference src/fileImport.h:14-23 (Importer::import) and src/HyperSMURFUtils.h (saveToFile) -- ingest.cpp
+struct Importer {
+	// x comes back row-major [n][m+1] with the label column appended (1.0 for label > 0, else 2.0), y / f as read; *nFolds is only
+	// written when a fold file is given (max id + 1).  threads == 0: as many as the file is worth (<= 16).  A data file that starts
+	// with the magic "PSMB1" is read as the binary side channel (labels / folds inside; the other two names are ignored).
+	static void import(const std::string& dataFilename, const std::string& labelFilename, const std::string& foldFilename, std::vector<double>& x,
+	                   std::vector<uint32_t>& y, std::vector<uint32_t>& f, uint32_t* nFolds, uint32_t* m, unsigned threads = 0);
+	static bool isBinary(const std::string& dataFilename);
+	static void importBinary(const std::string& path, std::vector<double>& x, std::vector<uint32_t>& y, std::vector<uint32_t>& f, uint32_t* nFolds, uint32_t* m);
+	static void exportBinary(const std::string& path, const double* xRowMajorWithLabel, uint32_t n, uint32_t m, const uint32_t* y, const uint32_t* folds);
+};
+// "cl1<TAB>cl2[<TAB>label]" per example, byte-identical to the reference's text output; a name ending in ".bin" gets raw f64 arrays
+void saveToFile(const double* cl1, const double* cl2, uint32_t nn, const std::vector<uint32_t>* labels, const std::string& outFilename, unsigned threads = 0);
+
 // JSON configuration surface of cfgEx/*.json (reference src/ArgHandler_new.cpp:84-141, 294-375)
 struct Config {
 	CommonParams common;

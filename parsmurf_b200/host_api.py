@@ -228,3 +228,38 @@ def config_parse(text):
     d = {k_: int(out[i]) for i, k_ in enumerate(keys)}
     d["grid"] = [dict(zip(["nParts", "fp", "ratio", "k", "nTrees", "mtry"], [int(v) for v in row])) for row in grid[: d["gridSize"]]]
     return d
+
+
+def import_files(data_file, label_file=None, fold_file=None, threads=0):
+    """parsmurf::Importer::import (text files in the reference's format, or a PSMB1 binary data file) ->
+    dict(x [n][m+1] with the label column appended, y, f, nFolds, m)"""
+    L = hlib()
+    L.psmh_import.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint, u64p, dp, u32p, u32p, C.c_char_p, C.c_size_t]
+    enc = lambda s: None if s is None else str(s).encode()
+    sz = np.zeros(5, np.uint64); err = C.create_string_buffer(512)
+    if L.psmh_import(enc(data_file), enc(label_file), enc(fold_file), threads, _p(sz, u64p), None, None, None, err, 512) != 0:
+        raise PsmError(-2, err.value.decode())
+    x = np.zeros(int(sz[0])); y = np.zeros(int(sz[1]), np.uint32); f = np.zeros(int(sz[2]), np.uint32)
+    if L.psmh_import(enc(data_file), enc(label_file), enc(fold_file), threads, _p(sz, u64p), _p(x, dp), _p(y, u32p), _p(f, u32p), err, 512) != 0:
+        raise PsmError(-2, err.value.decode())
+    m = int(sz[4])
+    return dict(x=x.reshape(len(y), m + 1), y=y, f=f, nFolds=int(sz[3]), m=m)
+
+
+def save_predictions(path, class1, class2, labels=None, threads=0):
+    """parsmurf::saveToFile: the reference's text output (byte-identical), or raw f64 arrays when the name ends in .bin"""
+    L = hlib()
+    L.psmh_save.argtypes = [dp, dp, u32, u32p, C.c_char_p, C.c_uint]
+    c1 = np.ascontiguousarray(class1, np.float64); c2 = np.ascontiguousarray(class2, np.float64)
+    lab = None if labels is None else np.ascontiguousarray(labels, np.uint32)
+    if L.psmh_save(_p(c1, dp), _p(c2, dp), len(c1), _p(lab, u32p), str(path).encode(), threads) != 0:
+        raise PsmError(-2, "cannot write %s" % path)
+
+
+def export_binary(path, x_with_label, y, folds=None):
+    L = hlib()
+    L.psmh_export_binary.argtypes = [C.c_char_p, dp, u32, u32, u32p, u32p]
+    x = np.ascontiguousarray(x_with_label, np.float64); y = np.ascontiguousarray(y, np.uint32)
+    f = None if folds is None else np.ascontiguousarray(folds, np.uint32)
+    if L.psmh_export_binary(str(path).encode(), _p(x, dp), x.shape[0], x.shape[1] - 1, _p(y, u32p), _p(f, u32p)) != 0:
+        raise PsmError(-2, "cannot write %s" % path)

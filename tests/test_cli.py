@@ -54,9 +54,9 @@ def test_cli_cv_matches_host_api(tmp_path):
     rc, c1, c2 = O.o_cv(x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
     want = O.o_curves(case["y"], c1)
     assert abs(float(mt.group(1)) - want[0]) < 1e-8 and abs(float(mt.group(2)) - want[1]) < 1e-8
-    pred = np.loadtxt(tmp_path / "predictions.txt")          # P(pos) \t P(neg) \t label  (src/HyperSMURFUtils.cpp:79-84)
-    assert pred.shape == (case["n"], 3)
-    assert np.allclose(pred[:, 0], c1, rtol=1e-5, atol=1e-12) and np.array_equal(pred[:, 2].astype(int), case["y"].astype(int))
+    pred = np.loadtxt(tmp_path / "predictions.txt")          # P(pos) \t P(neg); the label column only for simulated data (src/parSMURF.cpp:128-137)
+    assert pred.shape == (case["n"], 2)
+    assert np.allclose(pred[:, 0], c1, rtol=1e-5, atol=1e-12) and np.allclose(pred[:, 1], c2, rtol=1e-5, atol=1e-12)
     assert os.path.exists(tmp_path / "time.txt")
 
 
