@@ -161,3 +161,37 @@ def test_folds_from_assignment_large_input_threaded_pass():
         others = [q for q in range(nF) if q != k]
         assert np.array_equal(got["trngPos"], np.concatenate([np.flatnonzero((f == q) & (y == 1)) for q in others]))
         assert np.array_equal(np.sort(got["trngNeg"]), np.sort(np.concatenate([np.flatnonzero((f == q) & (y == 0)) for q in others])))
+
+
+def test_backward_resolution_of_random_shuffle_equals_the_sequential_walk():
+    """the algorithm of csrc/shuffle.cu, restated in numpy: the result of  for i in 1..n-1: swap(a[i], a[rand() % (i+1)])  is
+    recovered per output slot by walking the steps backwards (largest later step that targets the slot ends the walk, else the
+    slot's own step redirects), with 'largest step <= t with j_i == s' as one binary search in the sorted (j, i) pairs"""
+    import bisect
+    from parsmurf_b200 import host_api as H
+    for n in (1, 2, 3, 17, 1000, 20000):
+        draws = H.rand_fill(1, max(n - 1, 1)).astype(np.int64)
+        a = np.arange(100, 100 + n)
+        seq = a.copy()
+        j = np.zeros(n, np.int64)
+        for i in range(1, n):
+            j[i] = draws[i - 1] % (i + 1)
+            seq[i], seq[j[i]] = seq[j[i]], seq[i]
+        shift = 24
+        keys = sorted((int(j[i]) << shift) | i for i in range(1, n))
+        out = np.empty(n, a.dtype)
+        hops = 0
+        for k in range(n):
+            s, t = k, n - 1
+            while True:
+                hops += 1
+                lo = bisect.bisect_right(keys, (s << shift) | t)
+                if lo > 0 and (keys[lo - 1] >> shift) == s and (keys[lo - 1] & ((1 << shift) - 1)) > s:
+                    s = keys[lo - 1] & ((1 << shift) - 1)
+                    break
+                if s == 0 or j[s] == s:
+                    break
+                t, s = s - 1, int(j[s])
+            out[k] = a[s]
+        assert np.array_equal(out, seq), n
+        assert hops <= 3 * n + 3                                          # ~2 hops per slot
