@@ -112,9 +112,10 @@ IndexPool g_pool;
 // ------------------------------------------------------------------------------------------ Folds (src/folds.cpp:26-117)
 Folds::Folds(uint32_t numberOfFolds, uint32_t classSize_, const uint32_t* labels_, std::vector<uint32_t>& ff, bool randomFold_, GlibcRand* rng_)
     : classSize(classSize_), nFolds(numberOfFolds), labels(labels_), fromFile(ff), nPos(numberOfFolds), nNeg(numberOfFolds),
-      foldsIdx(numberOfFolds + 1), randomFold(randomFold_), rng(rng_) {
-	folds = g_pool.take(classSize); folds.resize(classSize);
-}
+      foldsIdx(numberOfFolds + 1), randomFold(randomFold_), rng(rng_), ids(ff.data()), nIds(ff.size()) {}
+Folds::Folds(uint32_t numberOfFolds, uint32_t classSize_, const uint32_t* labels_, const uint32_t* ids_, size_t nIds_, bool randomFold_, GlibcRand* rng_)
+    : classSize(classSize_), nFolds(numberOfFolds), labels(labels_), fromFile(noIds), nPos(numberOfFolds), nNeg(numberOfFolds),
+      foldsIdx(numberOfFolds + 1), randomFold(randomFold_), rng(rng_), ids(ids_), nIds(ids_ ? nIds_ : 0) {}
 Folds::~Folds() { g_pool.give(folds); g_pool.give(posList); g_pool.give(negList); }
 
 void Folds::computeFolds() {
@@ -127,6 +128,7 @@ void Folds::computeFolds() {
 		posList = g_pool.take(totPos); posList.resize(totPos);
 		negList = g_pool.take(totNeg); negList.resize(totNeg);
 	};
+	if (randomFold || keepFoldsArray) { folds = g_pool.take(classSize); folds.resize(classSize); }
 	if (randomFold) {
 		std::vector<uint32_t> pos = g_pool.take(classSize), neg = g_pool.take(classSize);
 		struct Back { std::vector<uint32_t>& v; ~Back() { g_pool.give(v); } } backPos{pos}, backNeg{neg};
@@ -149,7 +151,9 @@ void Folds::computeFolds() {
 			std::copy(folds.begin() + foldsIdx[f] + nPos[f], folds.begin() + foldsIdx[f + 1], negList.begin() + negOff[f]);
 		}
 	} else {
-		if (fromFile.size() < classSize) throw Error(PSM_E_ARG, "Folds: fold assignment shorter than the label vector");
+		if (&fromFile != &noIds) { ids = fromFile.data(); nIds = fromFile.size(); }   // the caller may have filled the vector after construction
+		if (nIds < classSize) throw Error(PSM_E_ARG, "Folds: fold assignment shorter than the label vector");
+		const bool fillFolds = keepFoldsArray;
 		// two passes (count, then place) over contiguous slices of the examples, a few host threads on large inputs: slice t
 		// writes after everything slices < t write, so every fold keeps ascending example order (src/folds.cpp:93-110)
 		const uint32_t nT = classSize >= (1u << 18) ? 4u : 1u;
@@ -165,7 +169,7 @@ void Folds::computeFolds() {
 		run([&](uint32_t t) {
 			uint32_t a, b; slice(t, &a, &b);
 			for (uint32_t i = a; i < b; i++) {
-				const uint32_t v = fromFile[i];
+				const uint32_t v = ids[i];
 				if (v >= nFolds) { bad = true; return; }
 				if (labels[i] > 0) hP[t][v]++; else hN[t][v]++;
 			}
@@ -186,8 +190,8 @@ void Folds::computeFolds() {
 			}
 			uint32_t a, b; slice(t, &a, &b);
 			for (uint32_t i = a; i < b; i++) {
-				const uint32_t bin = fromFile[i];
-				folds[cf[bin]++] = i;
+				const uint32_t bin = ids[i];
+				if (fillFolds) folds[cf[bin]++] = i;
 				if (labels[i] > 0) posList[cp[bin]++] = i; else negList[cn[bin]++] = i;
 			}
 		});
@@ -1167,13 +1171,13 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 			d->check(psm_profile_enable(d->ctx, profile != 0));
 		}
 		GlibcRand rng(1);
-		struct Pooled {                                     // label / fold-id copies live in recycled buffers too
+		struct Pooled {                                     // the label copy lives in a recycled buffer too
 			std::vector<uint32_t> v;
 			Pooled(const uint32_t* src, size_t cnt) { if (src) { v = g_pool.take(cnt); v.assign(src, src + cnt); } }
 			~Pooled() { g_pool.give(v); }
-		} yBuf(labels, n), ffBuf(foldAssign, n);
-		std::vector<uint32_t>& y = yBuf.v; std::vector<uint32_t>& ff = ffBuf.v;
-		Folds folds(nFolds, n, y.data(), ff, foldAssign == nullptr, &rng);
+		} yBuf(labels, n);
+		std::vector<uint32_t>& y = yBuf.v;
+		Folds folds(nFolds, n, y.data(), foldAssign, n, foldAssign == nullptr, &rng);   // the fold ids are only borrowed for the call
 		{ PhaseScope ps(PH_FOLDS_TTD); folds.computeFolds(); }
 		trace_mark("folds computed");
 		CommonParams cp;
@@ -1256,13 +1260,13 @@ int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* la
 	try {
 		Device dev(device, nullptr);
 		GlibcRand rng(1);
-		struct Pooled {                                     // label / fold-id copies live in recycled buffers too
+		struct Pooled {                                     // the label copy lives in a recycled buffer too
 			std::vector<uint32_t> v;
 			Pooled(const uint32_t* src, size_t cnt) { if (src) { v = g_pool.take(cnt); v.assign(src, src + cnt); } }
 			~Pooled() { g_pool.give(v); }
-		} yBuf(labels, n), ffBuf(foldAssign, n);
-		std::vector<uint32_t>& y = yBuf.v; std::vector<uint32_t>& ff = ffBuf.v;
-		Folds folds(nFolds, n, y.data(), ff, foldAssign == nullptr, &rng);
+		} yBuf(labels, n);
+		std::vector<uint32_t>& y = yBuf.v;
+		Folds folds(nFolds, n, y.data(), foldAssign, n, foldAssign == nullptr, &rng);   // the fold ids are only borrowed for the call
 		folds.computeFolds();
 		CommonParams cp;
 		cp.nn = n; cp.mm = m; cp.nFolds = nFolds; cp.seed = seed; cp.wmode = MODE_CV; cp.woptimiz = OPT_GRID;
@@ -1316,9 +1320,7 @@ int psmh_ttd_fold(const uint32_t* labels, const uint32_t* foldAssign, uint32_t n
 	using namespace parsmurf;
 	try {
 		GlibcRand rng(1);
-		std::vector<uint32_t> ff;
-		if (foldAssign) ff.assign(foldAssign, foldAssign + n);
-		Folds folds(nFolds, n, labels, ff, foldAssign == nullptr, &rng);
+		Folds folds(nFolds, n, labels, foldAssign, n, foldAssign == nullptr, &rng);   // borrowed ids, like psmh_cv_run
 		folds.computeFolds();
 		std::unique_ptr<TestTrainDivider> t(foldToJump < 0 ? new TestTrainDivider(&folds, MODE_CV, &rng) : new TestTrainDivider(&folds, MODE_CV, (uint32_t)foldToJump));
 		if (fold >= t->nFolds) return PSM_E_ARG;

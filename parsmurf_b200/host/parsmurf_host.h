@@ -80,12 +80,17 @@ private:
 class Folds {
 public:
 	Folds(uint32_t numberOfFolds, uint32_t classSize, const uint32_t* labels, std::vector<uint32_t>& ff, bool randomFold, GlibcRand* rng);
+	// the same with a borrowed fold-id array (no copy of n ids); `ids` must outlive the object
+	Folds(uint32_t numberOfFolds, uint32_t classSize, const uint32_t* labels, const uint32_t* ids, size_t nIds, bool randomFold, GlibcRand* rng);
 	~Folds();
 	Folds(const Folds&) = delete;
 	void computeFolds();
 	const uint32_t classSize, nFolds;
 	const uint32_t* labels;
 	std::vector<uint32_t>& fromFile;
+	// `folds` (every fold's examples, src/folds.h) is only filled on request when the assignment comes from a file: nothing on
+	// the GPU path reads it (the per-class lists below are what the train / test arrays are assembled from)
+	bool keepFoldsArray = false;
 	uint32_t totPos = 0, totNeg = 0;
 	std::vector<uint32_t> nPos, nNeg, foldsIdx, folds;
 	uint32_t maxPos = 0, maxNeg = 0;
@@ -94,6 +99,10 @@ public:
 	std::vector<uint32_t> posOff, negOff, posList, negList;
 	bool randomFold;
 	GlibcRand* rng;
+private:
+	std::vector<uint32_t> noIds;           // what `fromFile` refers to when the ids are borrowed
+	const uint32_t* ids = nullptr;         // fold id per example (fromFile.data() or the borrowed array)
+	size_t nIds = 0;
 };
 
 // reference src/testtraindivider.h:13-36 (both constructors)
