@@ -175,8 +175,14 @@ int psm_scratch_read(psm_ctx* ctx, double* host, uint32_t count);
 /* ---- (9) curves: Curves ctor + evalAUROC_ok + evalAUPRC (src/curves.cpp:7-36,77-122). out = {auroc, auprc}.
  *      tie_mode 0: descending order from the identical host std::sort call (bit-parity with the reference's
  *      tie order); tie_mode 1: stable device radix sort (ties in index order; may differ from the reference by
- *      more than 1e-6 on heavily tied scores). --------------------------------------------- */
+ *      more than 1e-6 on heavily tied scores); tie_mode 2: see psm_curves_info. -------------- */
 int psm_curves(psm_ctx* ctx, const uint32_t* labels, const double* scores, uint64_t N, int tie_mode, double* out);
+/* tie_mode 2 ("auto"): the stable device sort, then a count of the adjacent pairs of EQUAL score and DIFFERENT label.  With
+ * none, every run of tied scores is single-label, its internal order cannot change a TP/FP prefix, and the result is provably
+ * the reference's whatever order its std::sort leaves ties in; otherwise the permutation is redone with the host std::sort
+ * of tie_mode 0.  psm_curves_info reports, for the last curves call of the context, that pair count and whether the host
+ * sort ran. */
+int psm_curves_info(psm_ctx* ctx, uint64_t* mixed_tie_pairs, int* used_host_sort);
 
 /* ---- convenience: steps (5)-(7) for partitions [p0,p1) of the current fold, batched under the memory budget.
  *      draws_host as in psm_batch_assemble for [p0,p1) (or NULL when fp == 0). ------------------------------ */

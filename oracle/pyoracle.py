@@ -92,6 +92,7 @@ def ref_lib():
         L.ref_save.argtypes = [dp, dp, u32, u32p, C.c_char_p]
         L.ref_save.restype = None
         L.ref_knn.argtypes = [dp, C.c_int, C.c_int, C.c_int, i32p, dp, C.c_int]
+        L.ref_knn_queries.argtypes = [dp, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i32p, dp]
         L.ref_forest_train.restype = vp
         L.ref_forest_train.argtypes = [dp, u32, u32, u32, u32, u32, u32]
         L.ref_forest_destroy.argtypes = [vp]
@@ -106,8 +107,13 @@ def ref_lib():
         L.ref_cv.argtypes = [dp, u32, u32, u32p, u32p] + [u32] * 10 + [i32, i32, C.c_int, dp, dp]
         L.ref_run_partitions.restype = C.c_double
         L.ref_run_partitions.argtypes = [vp] + [u32] * 12 + [dp, dp]
+        L.ref_run_partitions_ex.restype = C.c_double
+        L.ref_run_partitions_ex.argtypes = [vp] + [u32] * 12 + [dp, dp, i32p, u64, dp]
         L.ref_cv_grid.restype = C.c_double
         L.ref_cv_grid.argtypes = [dp, u32, u32, u32p, u32p, u32, u32p, u32, u32, u32, u32, C.c_int, dp, dp, dp]
+        L.ref_mode_train.restype = C.c_double
+        L.ref_mode_train.argtypes = [dp, u32, u32, u32p] + [u32] * 9 + [C.c_char_p, C.c_int]
+        L.ref_config_parse.argtypes = [C.c_char_p, u32p, u32p, u32]
         L.ref_num_procs.restype = C.c_int
         _ref = L
     return _ref
@@ -300,14 +306,71 @@ class RefCtx:
         secs = self.L.ref_run_partitions(self.h, fold, p0, p1, nParts, fp, ratio, k, nTrees, mtry, seed, nThr, rfThr, _p(c1, dp), _p(c2, dp))
         return secs, c1, c2
 
+    def run_partitions_ex(self, fold, p0, p1, nParts, fp, ratio, k, nTrees, mtry, seed, nThr, rfThr=1):
+        """run_partitions that also exports, per partition, the rand() draws its SamplerKNN::sample() consumed ([p1-p0][P*fp*(m+1)])
+        and the reference's raw predictions ([p1-p0][Nte][2]) -- what makes a multi-threaded reference run comparable bit for bit"""
+        fd = self.fold(fold)
+        P, Nte = len(fd["trngPos"]), len(fd["testPos"]) + len(fd["testNeg"])
+        per = P * fp * (self.m + 1)
+        c1 = np.zeros(self.n); c2 = np.zeros(self.n)
+        draws = np.zeros((p1 - p0, max(per, 1)), np.int32); preds = np.zeros((p1 - p0, Nte, 2))
+        secs = self.L.ref_run_partitions_ex(self.h, fold, p0, p1, nParts, fp, ratio, k, nTrees, mtry, seed, nThr, rfThr, _p(c1, dp), _p(c2, dp),
+                                            _p(draws, i32p), per, _p(preds, dp))
+        if per and (draws[:, 0] == -2).any():
+            raise RuntimeError("reference consumed a different number of rand() draws than P*fp*(m+1)")
+        return secs, c1, c2, draws[:, :per], preds, fd
+
     def __del__(self):
         self.L.ref_ctx_destroy(self.h)
+
+
+def scale_parity(gpu_ctx, fd, draws, preds, p0, p1, nParts, fp, ratio, k, nTrees, mtry, seed, fold, ref_class1=None):
+    """CHECKER.  `gpu_ctx` is a product context (parsmurf_b200.Context, dataset already uploaded / attached); `fd`, `draws`,
+    `preds` come from RefCtx.run_partitions_ex for partitions [p0, p1) of `fold`.  The CUDA path runs the same partitions with
+    the reference's draws injected; its partial fold scores must equal, BIT FOR BIT, the reference's per-partition
+    predictions times 1/nParts summed in ascending partition order from zero (src/sampler.cpp:116-133 at ensThrd 1).
+    Returns dict(partitions, rows, max_abs_diff, mismatching_rows[, max_abs_diff_vs_reference_sum])."""
+    gpu_ctx.fold_begin(fd["trngPos"], fd["trngNeg"], fd["testPos"], fd["testNeg"])
+    gpu_ctx.fold_knn(k)
+    gpu_ctx.fold_run_partitions(nParts, fp, ratio, nTrees, mtry, seed, fold, p0, p1, np.ascontiguousarray(draws).reshape(-1) if fp else None)
+    g1, g2 = gpu_ctx.fold_scores_get()
+    inv = 1.0 / nParts
+    e1 = np.zeros(preds.shape[1]); e2 = np.zeros(preds.shape[1])
+    for i in range(preds.shape[0]):                       # ascending partition order, one rounding per multiply and per add
+        e1 = e1 + preds[i, :, 0] * inv
+        e2 = e2 + preds[i, :, 1] * inv
+    d = max(float(np.abs(g1 - e1).max(initial=0.0)), float(np.abs(g2 - e2).max(initial=0.0)))
+    bad = int(np.count_nonzero((g1.view(np.uint64) != e1.view(np.uint64)) | (g2.view(np.uint64) != e2.view(np.uint64))))
+    out = dict(partitions=int(p1 - p0), rows=int(preds.shape[1]), max_abs_diff=d, mismatching_rows=bad)
+    if ref_class1 is not None:   # the reference's own accumulation (completion order under the lock when multi-threaded)
+        test = np.concatenate([fd["testPos"], fd["testNeg"]])
+        out["max_abs_diff_vs_reference_sum"] = float(np.abs(g1 - ref_class1[test]).max(initial=0.0))
+    return out
+
+
+def r_config_parse(path):
+    """the reference's ArgHandle on `--cfg path` (exit()s the process on an invalid configuration: call it in a child process)"""
+    out = np.zeros(10, np.uint32); grid = np.zeros((4096, 6), np.uint32)
+    ref_lib().ref_config_parse(str(path).encode(), _p(out, u32p), _p(grid, u32p), 4096)
+    keys = ["nFolds", "seed", "wmode", "woptimiz", "gridSize", "ensThrd", "rfThrd", "simulate", "n", "m"]
+    d = {k_: int(out[i]) for i, k_ in enumerate(keys)}
+    d["grid"] = [dict(zip(["nParts", "fp", "ratio", "k", "nTrees", "mtry"], [int(v) for v in row])) for row in grid[: d["gridSize"]]]
+    return d
 
 
 def r_knn(pts, k, brute=False):
     pts = np.ascontiguousarray(pts, np.float64); P, dim = pts.shape
     idx = np.zeros((P, k), np.int32); dist = np.zeros((P, k))
     ref_lib().ref_knn(_p(pts, dp), P, dim, k, _p(idx, i32p), _p(dist, dp), int(brute))
+    return idx, dist
+
+
+def r_knn_queries(pts, k, queries):
+    """the reference's ANN kd-tree over all of `pts`, searched for the query rows `queries` only"""
+    pts = np.ascontiguousarray(pts, np.float64); P, dim = pts.shape
+    q = np.ascontiguousarray(queries, np.int32)
+    idx = np.zeros((len(q), k), np.int32); dist = np.zeros((len(q), k))
+    ref_lib().ref_knn_queries(_p(pts, dp), P, dim, k, _p(q, i32p), len(q), _p(idx, i32p), _p(dist, dp))
     return idx, dist
 
 
@@ -355,6 +418,14 @@ def r_cv(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, nTh
     secs = ref_lib().ref_cv(_p(x, dp), n, ld - 1, _p(labels, u32p), _p(folds, u32p), nFolds, nParts, fp, ratio, k, nTrees, mtry, seed,
                             nThr, rfThr, minFold, maxFold, int(reset_rand), _p(c1, dp), _p(c2, dp))
     return secs, c1, c2
+
+
+def r_mode_train(x, labels, forest_dir, nParts, fp, ratio, k, nTrees, mtry, seed, nThr=1, rfThr=1):
+    """the reference's exec.mode "train" as its main() drives it (one randomly generated fold holding every example): writes
+    <forest_dir>/<p>.out.forest for every partition"""
+    n, ld = x.shape
+    x = np.ascontiguousarray(x, np.float64); labels = np.ascontiguousarray(labels, np.uint32)
+    return ref_lib().ref_mode_train(_p(x, dp), n, ld - 1, _p(labels, u32p), nParts, fp, ratio, k, nTrees, mtry, seed, nThr, rfThr, str(forest_dir).encode(), 1)
 
 
 def r_cv_grid(x, labels, folds, nFolds, grid, seed, nThr=1, rfThr=1):

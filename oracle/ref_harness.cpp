@@ -20,6 +20,7 @@
 #include <sstream>
 #include <iostream>
 #include <omp.h>
+#include <getopt.h>
 
 #include "HyperSMURFUtils.h"
 #include "folds.h"
@@ -165,6 +166,25 @@ int ref_knn(const double* pts, int P, int dim, int k, int32_t* nnIdx, double* nn
 	return 0;
 }
 
+// the same kd-tree over all P points, but only the `nq` query points q[] are searched (large folds: a 1000-dimensional
+// kd-tree search scans almost every point, so all P queries take minutes; the tree and the search code are the reference's)
+int ref_knn_queries(const double* pts, int P, int dim, int k, const int32_t* q, int nq, int32_t* nnIdx, double* nnDist) {
+	ANNpointArray dataPts = annAllocPts(P, dim);
+	for (int i = 0; i < P; i++) std::memcpy(dataPts[i], pts + (size_t)i * dim, sizeof(double) * dim);
+	std::vector<ANNidx> idx(k);
+	std::vector<ANNdist> dd(k);
+	{
+		ANNkd_tree kd(dataPts, P, dim);
+		for (int i = 0; i < nq; i++) {
+			kd.annkSearch(dataPts[q[i]], k, idx.data(), dd.data(), 0);
+			for (int j = 0; j < k; j++) { nnIdx[(size_t)i * k + j] = idx[j]; nnDist[(size_t)i * k + j] = dd[j]; }
+		}
+	}
+	annDeallocPts(dataPts);
+	annClose();
+	return 0;
+}
+
 // rfRanger train ctor + train() on a column-major matrix [m+1][Ntr] (src/hyperSMURF.cpp:289-303).
 void* ref_forest_train(const double* colmajor, uint32_t Ntr, uint32_t m, uint32_t T, uint32_t mtry,
                        uint32_t seed, uint32_t rfThr) {
@@ -279,6 +299,38 @@ double ref_cv(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, c
 	return t.duration();
 }
 
+// exec.mode "train" exactly as parSMURF1's main drives it (src/parSMURF.cpp:97-106 with ArgHandler_new.cpp:153-176: one fold, the fold
+// file ignored -> random fold generation, src/folds.cpp:27-77): Folds(1, n, y, ff, true) -> hyperSMURF::initStandard -> smurfIt, which
+// writes <forestDir>/<p>.out.forest (+ .importance) for every partition.  Returns wall seconds of smurfIt.
+double ref_mode_train(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, uint32_t nParts, uint32_t fp, uint32_t ratio, uint32_t k,
+                      uint32_t nTrees, uint32_t mtry, uint32_t seed, uint32_t nThr, uint32_t rfThr, const char* forestDir, int reset_rand) {
+	CoutSilencer quiet;
+	std::vector<double> xx(x, x + (size_t)n * (m + 1));
+	std::vector<uint32_t> yy(labels, labels + n);
+	std::vector<uint32_t> ff(n, 0);
+	double* class1 = new double[n](); double* class2 = new double[n]();
+	CommonParams cp;
+	cp.nn = n; cp.mm = m; cp.nFolds = 1; cp.seed = seed; cp.verboseLevel = VERBSILENT;
+	cp.nThr = nThr; cp.rfThr = rfThr; cp.wmode = MODE_TRAIN; cp.woptimiz = OPT_NO; cp.rfVerbose = false;
+	cp.verboseMPI = false; cp.noMtSender = false; cp.customCV = false;
+	cp.minFold = (uint32_t)-1; cp.maxFold = (uint32_t)-1;
+	cp.forestDirname = forestDir;
+	std::vector<GridParams> gp(1);
+	gp[0].nParts = nParts; gp[0].fp = fp; gp[0].ratio = ratio; gp[0].k = k; gp[0].nTrees = nTrees; gp[0].mtry = mtry;
+	gp[0].auroc = gp[0].auprc = 0;
+	omp_set_num_threads(nThr);
+	if (reset_rand) srand(1);
+	Folds foldManager(1, n, yy.data(), ff, true);
+	foldManager.computeFolds();
+	hyperSMURF smurfer(&cp, gp, &foldManager, xx, yy, class1, class2);
+	smurfer.initStandard();
+	Timer t; t.startTime();
+	smurfer.smurfIt();
+	t.endTime();
+	delete[] class1; delete[] class2;
+	return t.duration();
+}
+
 // Grid search (exec.optimizer = "grid", src/hyperSMURF.cpp:176-228): every outer fold runs an inner (nFolds-1)-fold CV per grid
 // point, then the outer fold with the arg-max-AUPRC parameters.  The reference appends fold<k>.dat files to the CWD, so the
 // caller should chdir to a scratch directory.  grid = [G][6] {nParts, fp, ratio, k, nTrees, mtry}; gridMetrics [G][2] receives
@@ -316,9 +368,25 @@ double ref_cv_grid(const double* x, uint32_t n, uint32_t m, const uint32_t* labe
 // Bounded CPU-baseline sample: partitions [p0, p1) of one fold through the reference classes in the
 // order of src/hyperSMURF.cpp:261-346, `nThr` OpenMP threads over partitions (as the reference does).
 // Accumulates into class1/class2 (length n).  Returns wall seconds.
+// `drawsOut` (optional): the rand() values each partition's SamplerKNN::sample() consumed, [p1-p0][perPartDraws] with
+// perPartDraws = P*fp*(m+1) -- with several OpenMP threads the threads interleave on the one global rand() stream
+// (SURVEY fact #5), so the draws a partition saw are only known by recording them (thread-local sink of the rand wrapper).
+// `predsOut` (optional): the reference's raw forestPred->getPredictions() of each partition, [p1-p0][Nte][2], copied before
+// anything is added to anything.  With both, the CUDA path can be given the same draws and compared bit for bit whatever
+// the thread interleaving was (bench.py `parity`, tests/test_gpu_scale_parity.py).
+double ref_run_partitions_ex(void* h, uint32_t fold, uint32_t p0, uint32_t p1, uint32_t nParts, uint32_t fp,
+                             uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
+                             uint32_t nThr, uint32_t rfThr, double* class1, double* class2, int32_t* drawsOut, uint64_t perPartDraws,
+                             double* predsOut);
 double ref_run_partitions(void* h, uint32_t fold, uint32_t p0, uint32_t p1, uint32_t nParts, uint32_t fp,
                           uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
                           uint32_t nThr, uint32_t rfThr, double* class1, double* class2) {
+	return ref_run_partitions_ex(h, fold, p0, p1, nParts, fp, ratio, k, nTrees, mtry, seed, nThr, rfThr, class1, class2, nullptr, 0, nullptr);
+}
+double ref_run_partitions_ex(void* h, uint32_t fold, uint32_t p0, uint32_t p1, uint32_t nParts, uint32_t fp,
+                             uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed,
+                             uint32_t nThr, uint32_t rfThr, double* class1, double* class2, int32_t* drawsOut, uint64_t perPartDraws,
+                             double* predsOut) {
 	RefCtx* c = (RefCtx*)h;
 	CoutSilencer quiet;
 	Partition part(c->folds.get(), c->ttd.get(), nParts, fp, ratio, c->m, c->n);
@@ -332,7 +400,15 @@ double ref_run_partitions(void* h, uint32_t fold, uint32_t p0, uint32_t p1, uint
 		uint32_t seedCustom = seed + cp + fold * nParts;
 		SamplerKNN samp(&part, MODE_CV, c->x.data(), mm, c->n, k);
 		samp.setPartition(cp);
+		std::vector<int32_t> sink;
+		if (drawsOut) { sink.reserve(perPartDraws); g_rand_sink = &sink; }
 		samp.sample();
+		g_rand_sink = nullptr;
+		if (drawsOut) {
+			int32_t* dst = drawsOut + (size_t)(cp - (int32_t)p0) * perPartDraws;
+			for (uint64_t i = 0; i < perPartDraws; i++) dst[i] = i < sink.size() ? sink[i] : -1;
+			if (sink.size() != perPartDraws) dst[0] = -2;   // caller checks: draw count differs from P*fp*(m+1)
+		}
 		std::vector<double> trng((size_t)samp.lineLen * (mm + 1));
 		transposeMatrix(trng.data(), samp.trngData, samp.lineLen, mm + 1);
 		std::unique_ptr<Data> input(new DataDouble(trng, make_names(mm, "Labels"), samp.trngSize, mm + 1));
@@ -348,6 +424,10 @@ double ref_run_partitions(void* h, uint32_t fold, uint32_t p0, uint32_t p1, uint
 		omp_set_lock(&lock);
 		samp.accumulateAndDivideResInProbVect(predictions, class1, class2, nParts);
 		omp_unset_lock(&lock);
+		if (predsOut) {
+			double* dst = predsOut + (size_t)(cp - (int32_t)p0) * samp.testSize * 2;
+			for (uint32_t i = 0; i < samp.testSize; i++) { dst[2 * i] = predictions[0][i][0]; dst[2 * i + 1] = predictions[0][i][1]; }
+		}
 	}
 	t.endTime();
 	omp_destroy_lock(&lock);
@@ -375,6 +455,27 @@ int ref_import(const char* dataFile, const char* labelFile, const char* foldFile
 		if (f) std::memcpy(f, ff.data(), ff.size() * sizeof(uint32_t));
 		return 0;
 	} catch (...) { return -1; }
+}
+
+// ArgHandle::processCommandLine on `--cfg path` (src/ArgHandler_new.cpp:19-82: jsonImport + checkCommonConfig + checkConfig).
+// out10 = {nFolds, seed, wmode, woptimiz, gridSize, ensThrd, rfThrd, simulate, n, m}; grid [gridSize][6] = {nParts, fp, ratio, k,
+// nTrees, mtry}.  The reference exit()s on an invalid configuration, so tests call this in a child process.
+int ref_config_parse(const char* path, uint32_t* out10, uint32_t* grid, uint32_t gridCap) {
+	CoutSilencer quiet;
+	std::vector<GridParams> gp;
+	char prog[] = "ref", opt[] = "--cfg";
+	std::string p(path);
+	char* argv[] = {prog, opt, &p[0], nullptr};
+	optind = 1;
+	ArgHandle ah(3, argv, gp);
+	ah.processCommandLine(1);     // rank 1: no logo / messages
+	out10[0] = ah.nFolds; out10[1] = ah.seed; out10[2] = ah.wmode; out10[3] = ah.woptimiz; out10[4] = (uint32_t)gp.size();
+	out10[5] = ah.ensThreads; out10[6] = ah.rfThreads; out10[7] = ah.simulate; out10[8] = ah.n; out10[9] = ah.m;
+	for (size_t i = 0; i < gp.size() && i < gridCap; i++) {
+		uint32_t* r = grid + 6 * i;
+		r[0] = gp[i].nParts; r[1] = gp[i].fp; r[2] = gp[i].ratio; r[3] = gp[i].k; r[4] = gp[i].nTrees; r[5] = gp[i].mtry;
+	}
+	return 0;
 }
 
 // saveToFile (src/HyperSMURFUtils.cpp:66-86); labels == NULL -> the two-column form main() writes for data read from files

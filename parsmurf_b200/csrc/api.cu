@@ -91,6 +91,8 @@ struct psm_ctx {
 	bool haveLabels = false, foldLabelsReady = false;
 
 	// curves
+	uint64_t curvesMixedPairs = 0;
+	int curvesUsedHostSort = 0;
 	DevBuf cIdx, cFoldScores, cScratch, cLabels, cPerm, cSorted, cTp, cPartials, cOut, cScores, cKeysA, cKeysB, cValsA, cValsB, cHist;
 
 	// profiling
@@ -908,49 +910,73 @@ int psm_fold_scatter_host(psm_ctx* ctx, double* class1Prob, double* class2Prob) 
 // core: labels (u32) and scores (f64) already on the device; hScores (host copy) is only needed for tie_mode 0
 static int curves_core(psm_ctx* ctx, const uint32_t* dLabels, const double* dScores, const double* hScores, uint64_t N, uint32_t totP, uint32_t totN,
                        int tie_mode, double* out) {
+	if (tie_mode < 0 || tie_mode > 2) return fail(ctx, PSM_E_ARG, "curves: tie_mode must be 0 (host std::sort), 1 (stable device sort) or 2 (auto)");
 	cudaStream_t s = ctx->stream;
 	ENSURE(ctx->cSorted, N + 64);
 	const uint64_t nBlocks = (N + 4095) / 4096;
-	ENSURE(ctx->cTp, (nBlocks + 1) * 4); ENSURE(ctx->cPartials, nBlocks * 16); ENSURE(ctx->cOut, 16);
-	const uint32_t* dPerm = nullptr;
-	std::vector<uint32_t> perm;
-	std::vector<double> tmp;
-	if (tie_mode == 0) {
-		if (!hScores) {
-			tmp.resize(N);
-			CU(cudaMemcpyAsync(tmp.data(), dScores, N * 8, cudaMemcpyDeviceToHost, s));
-			CU(cudaStreamSynchronize(s));
-			hScores = tmp.data();
+	ENSURE(ctx->cTp, (nBlocks + 1) * 4); ENSURE(ctx->cPartials, nBlocks * 16); ENSURE(ctx->cOut, 32);
+	ctx->curvesMixedPairs = 0; ctx->curvesUsedHostSort = 0;
+	// tie_mode 2 runs the device path first and falls back to the host permutation only when a run of tied scores holds both
+	// labels (curves.cu: tie_mixed_count_kernel) -- the only case in which the tie order can change the curves at all
+	for (int attempt = 0; attempt < 2; attempt++) {
+		const bool host = tie_mode == 0 || (tie_mode == 2 && attempt == 1);
+		const uint32_t* dPerm = nullptr;
+		std::vector<uint32_t> perm;
+		std::vector<double> tmp;
+		if (host) {
+			if (!hScores) {
+				tmp.resize(N);
+				CU(cudaMemcpyAsync(tmp.data(), dScores, N * 8, cudaMemcpyDeviceToHost, s));
+				CU(cudaStreamSynchronize(s));
+				hScores = tmp.data();
+			}
+			// the identical call the reference makes (curves.cpp:31-33): same libstdc++ introsort => same tie order
+			std::vector<size_t> idx(N);
+			std::iota(idx.begin(), idx.end(), 0);
+			std::sort(idx.begin(), idx.end(), [&](size_t i, size_t j) { return hScores[i] > hScores[j]; });
+			perm.resize(N);
+			for (uint64_t i = 0; i < N; i++) perm[i] = (uint32_t)idx[i];
+			ENSURE(ctx->cPerm, N * 4);
+			CU(cudaMemcpyAsync(ctx->cPerm.p, perm.data(), N * 4, cudaMemcpyHostToDevice, s));
+			dPerm = ctx->cPerm.as<uint32_t>();
+			ctx->curvesUsedHostSort = 1;
+		} else {
+			ENSURE(ctx->cKeysA, N * 8); ENSURE(ctx->cKeysB, N * 8); ENSURE(ctx->cValsA, N * 4); ENSURE(ctx->cValsB, N * 4);
+			const uint64_t rBlocks = (N + 4095) / 4096;
+			ENSURE(ctx->cHist, rBlocks * 256 * 4);
+			ProfScope ps(ctx, K_CURVES, 1 + 3 * 8);
+			if (launch_sort_scores_desc(dScores, N, ctx->cKeysA.as<unsigned long long>(), ctx->cKeysB.as<unsigned long long>(),
+			                            ctx->cValsA.as<uint32_t>(), ctx->cValsB.as<uint32_t>(), ctx->cHist.as<uint32_t>(), s))
+				return fail(ctx, PSM_E_ARG, "curves: sort launch failed");
+			dPerm = ctx->cValsA.as<uint32_t>();
 		}
-		// the identical call the reference makes (curves.cpp:31-33): same libstdc++ introsort => same tie order
-		std::vector<size_t> idx(N);
-		std::iota(idx.begin(), idx.end(), 0);
-		std::sort(idx.begin(), idx.end(), [&](size_t i, size_t j) { return hScores[i] > hScores[j]; });
-		perm.resize(N);
-		for (uint64_t i = 0; i < N; i++) perm[i] = (uint32_t)idx[i];
-		ENSURE(ctx->cPerm, N * 4);
-		CU(cudaMemcpyAsync(ctx->cPerm.p, perm.data(), N * 4, cudaMemcpyHostToDevice, s));
-		dPerm = ctx->cPerm.as<uint32_t>();
-	} else {
-		ENSURE(ctx->cKeysA, N * 8); ENSURE(ctx->cKeysB, N * 8); ENSURE(ctx->cValsA, N * 4); ENSURE(ctx->cValsB, N * 4);
-		const uint64_t rBlocks = (N + 4095) / 4096;
-		ENSURE(ctx->cHist, rBlocks * 256 * 4);
-		ProfScope ps(ctx, K_CURVES, 1 + 3 * 8);
-		if (launch_sort_scores_desc(dScores, N, ctx->cKeysA.as<unsigned long long>(), ctx->cKeysB.as<unsigned long long>(),
-		                            ctx->cValsA.as<uint32_t>(), ctx->cValsB.as<uint32_t>(), ctx->cHist.as<uint32_t>(), s))
-			return fail(ctx, PSM_E_ARG, "curves: sort launch failed");
-		dPerm = ctx->cValsA.as<uint32_t>();
+		{
+			ProfScope ps(ctx, K_CURVES, 5 + (tie_mode == 2 && !host ? 1 : 0));
+			launch_gather_labels(dLabels, dPerm, N, ctx->cSorted.as<unsigned char>(), s);
+			if (tie_mode == 2 && !host)
+				launch_tie_mixed_count(ctx->cKeysA.as<unsigned long long>(), ctx->cSorted.as<unsigned char>(), N, ctx->cOut.as<unsigned long long>() + 2, s);
+			if (launch_curves(ctx->cSorted.as<unsigned char>(), N, totP, totN, ctx->cTp.as<uint32_t>(), ctx->cPartials.as<double>(), nBlocks * 2,
+			                  ctx->cOut.as<double>(), s))
+				return fail(ctx, PSM_E_ARG, "curves: launch failed");
+		}
+		CU(cudaGetLastError());
+		unsigned long long res[3] = {0, 0, 0};
+		CU(cudaMemcpyAsync(res, ctx->cOut.p, tie_mode == 2 && !host ? 24 : 16, cudaMemcpyDeviceToHost, s));
+		CU(cudaStreamSynchronize(s));   // also keeps `perm` alive until the upload is done
+		memcpy(out, res, 16);
+		if (tie_mode == 2 && !host) {
+			ctx->curvesMixedPairs = res[2];
+			if (res[2] != 0) continue;    // a tied run with both labels: redo with the reference's own tie order
+		}
+		break;
 	}
-	{
-		ProfScope ps(ctx, K_CURVES, 5);
-		launch_gather_labels(dLabels, dPerm, N, ctx->cSorted.as<unsigned char>(), s);
-		if (launch_curves(ctx->cSorted.as<unsigned char>(), N, totP, totN, ctx->cTp.as<uint32_t>(), ctx->cPartials.as<double>(), nBlocks * 2,
-		                  ctx->cOut.as<double>(), s))
-			return fail(ctx, PSM_E_ARG, "curves: launch failed");
-	}
-	CU(cudaGetLastError());
-	CU(cudaMemcpyAsync(out, ctx->cOut.p, 16, cudaMemcpyDeviceToHost, s));
-	CU(cudaStreamSynchronize(s));   // also keeps `perm` alive until the upload is done
+	return PSM_OK;
+}
+
+int psm_curves_info(psm_ctx* ctx, uint64_t* mixed_tie_pairs, int* used_host_sort) {
+	if (!ctx) return PSM_E_ARG;
+	if (mixed_tie_pairs) *mixed_tie_pairs = ctx->curvesMixedPairs;
+	if (used_host_sort) *used_host_sort = ctx->curvesUsedHostSort;
 	return PSM_OK;
 }
 

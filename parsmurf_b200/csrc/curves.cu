@@ -194,6 +194,23 @@ __global__ void __launch_bounds__(256) curve_final_kernel(const double* __restri
 	if (threadIdx.x == 0) { out2[0] = sh[0][0]; out2[1] = sh[1][0]; }
 }
 
+// tie_mode 2 ("auto"): after the stable device sort, count the adjacent pairs with EQUAL score and DIFFERENT label.  A run of
+// equal scores holds both labels iff it contains such a pair; if there is none, every run of tied scores is single-label, the
+// order inside it cannot change any TP/FP prefix, and the curves are provably those of the reference's std::sort whatever its
+// tie order (src/curves.cpp:31-33).  Otherwise the caller redoes the permutation with the identical host std::sort call.
+__global__ void __launch_bounds__(256) tie_mixed_count_kernel(const unsigned long long* __restrict__ keysSorted, const unsigned char* __restrict__ l,
+                                                               uint64_t N, unsigned long long* __restrict__ counter) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool mixed = (i + 1 < N) && keysSorted[i] == keysSorted[i + 1] && l[i] != l[i + 1];
+	const unsigned b = __ballot_sync(0xffffffffu, mixed);
+	if (b && (threadIdx.x & 31) == 0) atomicAdd(counter, (unsigned long long)__popc(b));
+}
+void launch_tie_mixed_count(const unsigned long long* keysSorted, const unsigned char* labelsSorted, uint64_t N, unsigned long long* counter, cudaStream_t s) {
+	cudaMemsetAsync(counter, 0, 8, s);
+	if (N < 2) return;
+	tie_mixed_count_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(keysSorted, labelsSorted, N, counter);
+}
+
 // block sums must use the same element->block mapping as curve_terms_kernel (contiguous CTILE per block): they do.
 int launch_curves(const unsigned char* labelsSorted, uint64_t N, uint32_t totP, uint32_t totN, uint32_t* tpScratch, double* partials,
                   size_t partialsCap, double* out2, cudaStream_t s) {

@@ -88,6 +88,7 @@ void launch_accumulate(const double* scratch, uint32_t Nte, uint32_t nPartsBatch
 // curves.cu
 int launch_curves(const unsigned char* labelsSorted, uint64_t N, uint32_t totP, uint32_t totN, uint32_t* tpScratch,
                   double* partials, size_t partialsCap, double* out2, cudaStream_t s);
+void launch_tie_mixed_count(const unsigned long long* keysSorted, const unsigned char* labelsSorted, uint64_t N, unsigned long long* counter, cudaStream_t s);
 void launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint64_t N, uint32_t* out, cudaStream_t s);
 void launch_gather_f64(const double* src, const uint32_t* idx, uint64_t N, double* out, cudaStream_t s);
 void launch_add_f64(double* dst, const double* src, size_t count, cudaStream_t s);

@@ -15,17 +15,18 @@
 using namespace parsmurf;
 
 int main(int argc, char** argv) {
-	std::string cfgPath; int device = 0, tieMode = 0;
+	std::string cfgPath; int device = 0, tieMode = 2;   // 2 = auto: device sort, host std::sort only when a run of tied scores holds both labels
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "--cfg") && i + 1 < argc) cfgPath = argv[++i];
 		else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--tie-mode") && i + 1 < argc) tieMode = atoi(argv[++i]);
-		else if (!strcmp(argv[i], "--help")) { printf("usage: %s --cfg <file.json> [--device N] [--tie-mode 0|1]\n", argv[0]); return 0; }
+		else if (!strcmp(argv[i], "--help")) { printf("usage: %s --cfg <file.json> [--device N] [--tie-mode 0|1|2]\n", argv[0]); return 0; }
 	}
 	if (cfgPath.empty()) { fprintf(stderr, "usage: %s --cfg <file.json>\n", argv[0]); return 2; }
 	try {
 		Config cfg = Config::fromFile(cfgPath);
 		GlibcRand rng(1);
+		if (cfg.seedFromClock) rng.srand(cfg.common.seed);                   // the only case in which the reference seeds rand() (ArgHandler_new.cpp:257-262)
 		std::vector<double> x; std::vector<uint32_t> y, ff;
 		uint32_t n = 0, m = 0;
 		if (cfg.simulate) {

@@ -13,6 +13,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <ctime>
 #include <exception>
 
 namespace parsmurf {
@@ -228,7 +229,10 @@ TestTrainDivider::TestTrainDivider(const Folds* folds_, uint8_t wmode_, GlibcRan
 	// all) and still shuffle exactly like the sequential reference.
 	shuffleOff.assign(nFolds + 1, 0);
 	for (uint32_t i = 0; i < nFolds; i++) {
-		uint64_t nneg = folds->totNeg - folds->nNeg[i];
+		// exec.mode "train": the reference overrides trngNegNum[0] with testNegNum[0] BEFORE the shuffle (:33-36,90), so fold 0's
+		// std::random_shuffle runs over that many (still unfilled) slots and burns their rand() draws although the arrays are
+		// overwritten with the unshuffled fold afterwards (:101-104)
+		uint64_t nneg = (wmode == MODE_TRAIN && i == 0) ? folds->nNeg[0] : folds->totNeg - folds->nNeg[i];
 		shuffleOff[i + 1] = shuffleOff[i] + (nneg > 0 ? nneg - 1 : 0);
 	}
 	for (uint32_t i = 0; i < nFolds; i++) {                                  // counts are known without building anything
@@ -573,6 +577,11 @@ void hyperSMURF::setSharding(uint32_t rank_, uint32_t world_, std::function<void
 	rank = rank_; world = world_ ? world_ : 1; reduce = std::move(reduce_);
 }
 
+void hyperSMURF::noteCurves(Device* d) {
+	uint64_t mixed = 0; int host = 0;
+	if (psm_curves_info(d->ctx, &mixed, &host) == PSM_OK) { curvesMixedPairs += mixed; curvesHostSorts += (uint64_t)host; }
+}
+
 void hyperSMURF::initStandard() {                                           // src/hyperSMURF.cpp:22-51
 	nn = commonParams->nn; mm = commonParams->mm; nFolds = commonParams->nFolds;
 	setGridParams(0);
@@ -706,6 +715,7 @@ void hyperSMURF::smurfIt() {                                                // s
 					ttd->ensureTest(f);
 					dev->check(psm_scores_fold_curves(dev->ctx, ttd->testPosIdx[f].data(), ttd->testPosNum[f], ttd->testNegIdx[f].data(), ttd->testNegNum[f], curvesTieMode, r2));
 				}
+				noteCurves(dev);
 				fm[2 * f] = r2[0]; fm[2 * f + 1] = r2[1];
 			}
 			double* sp = nullptr;
@@ -742,6 +752,7 @@ void hyperSMURF::smurfIt() {                                                // s
 		double r2[2];
 		if (woptimiz == OPT_NO) dev->check(psm_scores_curves(dev->ctx, curvesTieMode, r2));        // Curves(y, class1Prob), scores still on the device
 		else dev->check(psm_curves(dev->ctx, y.data(), class1Prob, nn, curvesTieMode, r2));
+		noteCurves(dev);
 		auroc = r2[0];
 		auprc = r2[1];
 		if (verboseLevel > VERBSILENT && rank == 0) std::cout << "AUROC: " << auroc << " - AUPRC: " << auprc << std::endl;
@@ -841,6 +852,7 @@ void hyperSMURF::runFold(uint32_t currentFold, uint32_t first, uint32_t last, De
 		PhaseScope ps(PH_CURVES);
 		double r2[2];
 		d->check(psm_fold_curves(d->ctx, curvesTieMode, r2));       // Curves(tempLabels, tempPreds): AUROC first, then AUPRC (:382-384)
+		noteCurves(d);
 		foldAuroc[currentFold] = r2[0];
 		foldAuprc[currentFold] = r2[1];
 		if (verboseLevel > VERBSILENT && rank == 0)
@@ -966,6 +978,7 @@ void hyperSMURF::predictIt() {
 	PhaseScope ps(PH_CURVES);                                                // :484-488
 	double r2[2];
 	dev->check(psm_scores_curves(dev->ctx, curvesTieMode, r2));
+	noteCurves(dev);
 	auroc = r2[0]; auprc = r2[1];
 	if (verboseLevel > VERBSILENT && rank == 0) std::cout << "AUROC: " << auroc << " - AUPRC: " << auprc << std::endl;
 }
@@ -1069,7 +1082,8 @@ Config Config::fromString(const std::string& text) {
 	c.common.nFolds = jnum<uint32_t>(flds, "nFolds", 3);
 	c.common.minFold = jnum<uint32_t>(flds, "startingFold", (uint32_t)-1);
 	c.common.maxFold = jnum<uint32_t>(flds, "endingFold", (uint32_t)-1);
-	c.common.seed = jnum<uint32_t>(exec, "seed", 1);
+	c.common.seed = jnum<uint32_t>(exec, "seed", 0);
+	if (c.common.seed == 0) { c.common.seed = (uint32_t)time(nullptr); c.seedFromClock = true; }   // ArgHandler_new.cpp:257-262 (the caller also srand()s it)
 	c.common.verboseLevel = jnum<uint32_t>(exec, "verboseLevel", 0);
 	c.common.nThr = jnum<uint32_t>(exec, "ensThrd", 1);
 	c.common.rfThr = jnum<uint32_t>(exec, "rfThrd", 1);
@@ -1079,6 +1093,7 @@ Config Config::fromString(const std::string& text) {
 	else if (mode == "train") { c.common.wmode = MODE_TRAIN; c.common.nFolds = 1; }
 	else if (mode == "predict") { c.common.wmode = MODE_PREDICT; c.common.nFolds = 1; }
 	else throw Error(PSM_E_ARG, "Invalid prediction mode. Please specify either 'cv', 'train' or 'predict'");
+	if (c.common.wmode != MODE_CV) c.foldFilename.clear();                  // "Ignoring fold filename in train or test mode" (ArgHandler_new.cpp:172-176)
 	if (optim == "no") c.common.woptimiz = OPT_NO;
 	else if (optim == "grid") c.common.woptimiz = OPT_GRID;
 	else if (optim == "autogp") c.common.woptimiz = OPT_AUTOGP;
@@ -1210,7 +1225,7 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		if (foldMetrics && mode == MODE_CV) for (uint32_t f = 0; f < nFolds; f++) { foldMetrics[2 * f] = smurfer.foldAuroc[f]; foldMetrics[2 * f + 1] = smurfer.foldAuprc[f]; }
 		if (kernelMs) for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) kernelMs[i] = 0;
 		if (kernelLaunches) for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) kernelLaunches[i] = 0;
-		if (stats3) stats3[0] = stats3[1] = stats3[2] = 0;
+		if (stats3) { stats3[0] = stats3[1] = stats3[2] = 0; stats3[3] = smurfer.curvesMixedPairs; stats3[4] = smurfer.curvesHostSorts; }
 		for (uint32_t li = 0; li < dev.laneCount(); li++) {                  // kernel times / counts / byte statistics summed over the fold lanes
 			Device* d = dev.lane(li);
 			double ms[PSM_NUM_KERNEL_CLASSES]; uint64_t ln[PSM_NUM_KERNEL_CLASSES]; uint64_t st[3];
@@ -1248,17 +1263,32 @@ int psmh_mode_run(int mode, const char* forestDir, const double* x, uint32_t n, 
                   uint32_t ratio, uint32_t k, uint32_t nTrees, uint32_t mtry, uint32_t seed, int device, int tieMode, uint32_t rank, uint32_t world,
                   psmh_reduce_fn reduce, void* reduceUser, double* class1, double* class2, double* metrics, char* errbuf, size_t errlen) {
 	if (mode != parsmurf::MODE_TRAIN && mode != parsmurf::MODE_PREDICT) return PSM_E_ARG;
-	std::vector<uint32_t> ff(n, 0);                                          // a single fold holding every example
-	return run_mode(mode, forestDir, x, 0, n, m, labels, ff.data(), 1, nParts, fp, ratio, k, nTrees, mtry, seed, device, nullptr, tieMode, 0, rank, world,
+	// a single fold holding every example, generated like the reference's main does in these modes (the fold file is ignored,
+	// ArgHandler_new.cpp:172-176, so Folds runs its random generation: src/folds.cpp:27-77)
+	return run_mode(mode, forestDir, x, 0, n, m, labels, nullptr, 1, nParts, fp, ratio, k, nTrees, mtry, seed, device, nullptr, tieMode, 0, rank, world,
 	                reduce, reduceUser, 0, 0, class1, class2, metrics, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, errbuf, errlen);
 }
 
-int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
-                     const uint32_t* grid, uint32_t G, uint32_t seed, int device, int tieMode, double* class1, double* class2, double* metrics,
-                     double* gridMetrics, char* errbuf, size_t errlen) {
+// psmh_cv_grid_run_ex: the same with the dataset optionally resident in HBM (x_is_device), a persistent device handle, the
+// multi-rank sharding of psmh_cv_run (rank / world / reduce) and the launch statistics; psmh_cv_grid_run is the single-GPU form.
+int psmh_cv_grid_run_ex(const double* x, int x_is_device, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+                        const uint32_t* grid, uint32_t G, uint32_t seed, int device, void* stream, int tieMode, uint32_t rank, uint32_t world,
+                        psmh_reduce_fn reduce, void* reduceUser, double* class1, double* class2, double* metrics, double* gridMetrics,
+                        uint64_t* kernelLaunches, uint64_t* stats5, void* devHandle, char* errbuf, size_t errlen) {
 	using namespace parsmurf;
 	try {
-		Device dev(device, nullptr);
+		std::unique_ptr<Device> owned;
+		if (!devHandle) owned.reset(new Device(device, stream));
+		Device& dev = devHandle ? *(Device*)devHandle : *owned;
+		if (devHandle && stream) dev.check(psm_set_stream(dev.ctx, stream));
+		const uint32_t lanes = std::min<uint32_t>(fold_lanes_default(), nFolds > 1 ? nFolds - 1 : 1);   // the inner CVs run their folds in lanes
+		dev.setLaneCount(lanes);
+		for (uint32_t li = 0; li < dev.laneCount(); li++) {
+			Device* d = dev.lane(li);
+			d->check(psm_profile_reset(d->ctx));
+			d->check(psm_set_batch_budget(d->ctx, std::min<uint64_t>(24ull << 30, (120ull << 30) / lanes)));
+			d->check(psm_profile_enable(d->ctx, 0));
+		}
 		GlibcRand rng(1);
 		struct Pooled {                                     // the label copy lives in a recycled buffer too
 			std::vector<uint32_t> v;
@@ -1274,13 +1304,25 @@ int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* la
 		for (uint32_t i = 0; i < G; i++) gp[i] = GridParams{grid[6 * i], grid[6 * i + 1], grid[6 * i + 2], grid[6 * i + 3], grid[6 * i + 4], grid[6 * i + 5], 0, 0};
 		hyperSMURF smurfer(&cp, gp, &folds, &dev, y, class1, class2, &rng);
 		smurfer.curvesTieMode = tieMode;
-		smurfer.foldLanes = std::min<uint32_t>(fold_lanes_default(), nFolds > 1 ? nFolds - 1 : 1);   // the inner CVs run their folds in lanes
+		smurfer.foldLanes = lanes;
+		smurfer.shardUnits = shard_units_default();
 		smurfer.deviceFolds = getenv("PSM_HOST_FOLDS") == nullptr;
+		if (world > 1) smurfer.setSharding(rank, world, [&](double* p, uint64_t c) { if (reduce && reduce(reduceUser, p, c)) throw Error(PSM_E_CUDA, "reduce callback failed"); });
 		smurfer.initStandard();
-		dev.upload(x, n, m);
+		if (x_is_device) dev.attachDevice(x, n, m); else dev.upload(x, n, m);
 		smurfer.smurfIt();
 		if (metrics) { metrics[0] = smurfer.auroc; metrics[1] = smurfer.auprc; }
 		if (gridMetrics) for (uint32_t i = 0; i < G; i++) { gridMetrics[2 * i] = gp[i].auroc; gridMetrics[2 * i + 1] = gp[i].auprc; }
+		if (kernelLaunches) for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) kernelLaunches[i] = 0;
+		if (stats5) { stats5[0] = stats5[1] = stats5[2] = 0; stats5[3] = smurfer.curvesMixedPairs; stats5[4] = smurfer.curvesHostSorts; }
+		for (uint32_t li = 0; li < dev.laneCount(); li++) {
+			Device* d = dev.lane(li);
+			uint64_t ln[PSM_NUM_KERNEL_CLASSES]; uint64_t st[3];
+			d->check(psm_profile_get(d->ctx, nullptr, ln));
+			d->check(psm_stats_get(d->ctx, &st[0], &st[1], &st[2]));
+			if (kernelLaunches) for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) kernelLaunches[i] += ln[i];
+			if (stats5) for (int i = 0; i < 3; i++) stats5[i] += st[i];
+		}
 		return 0;
 	} catch (const parsmurf::Error& e) {
 		if (errbuf && errlen) { strncpy(errbuf, e.what(), errlen - 1); errbuf[errlen - 1] = 0; }
@@ -1289,6 +1331,12 @@ int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* la
 		if (errbuf && errlen) { strncpy(errbuf, e.what(), errlen - 1); errbuf[errlen - 1] = 0; }
 		return -1;
 	}
+}
+int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* labels, const uint32_t* foldAssign, uint32_t nFolds,
+                     const uint32_t* grid, uint32_t G, uint32_t seed, int device, int tieMode, double* class1, double* class2, double* metrics,
+                     double* gridMetrics, char* errbuf, size_t errlen) {
+	return psmh_cv_grid_run_ex(x, 0, n, m, labels, foldAssign, nFolds, grid, G, seed, device, nullptr, tieMode, 0, 1, nullptr, nullptr, class1, class2, metrics,
+	                           gridMetrics, nullptr, nullptr, nullptr, errbuf, errlen);
 }
 
 // a persistent GPU context (device buffers are reused across psmh_cv_run calls)

@@ -13,6 +13,7 @@
 //   * errors throw parsmurf::Error (the reference abort()s or swallows exceptions, src/samplerKNN.cpp:38-48,
 //     src/rfRanger.cpp:51-53); Error::code is the PSM_E_* value.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <functional>
 #include <memory>
@@ -303,10 +304,14 @@ public:
 	bool scoresAreOutputs = false;
 	std::vector<double> foldAuroc, foldAuprc;
 	double auroc = 0, auprc = 0;
+	// curvesTieMode 2 ("auto", psm_curves_info): over all the curves calls of this run, the adjacent (equal score, different
+	// label) pairs the device sort met, and how many calls had to be redone with the host std::sort
+	std::atomic<uint64_t> curvesMixedPairs{0}, curvesHostSorts{0};
 
 private:
 	struct FoldGate;
 	void predictIt();
+	void noteCurves(Device* d);
 	bool willShardUnits() const;
 	bool foldsOnDevice() const;
 	void runFold(uint32_t currentFold, uint32_t first, uint32_t last, Device* d, Partition* prt, GlibcRand* r, FoldGate* gate);
@@ -354,6 +359,7 @@ struct Config {
 	bool simulate = false;
 	double prob = 0.0;
 	bool printCfg = false;
+	bool seedFromClock = false;      // no exec.seed (or 0): seed = time(NULL) and the caller srand()s it (ArgHandler_new.cpp:257-262)
 	static Config fromFile(const std::string& path);
 	static Config fromString(const std::string& json);
 	void processMtry(uint32_t mm);   // mtry 0 or > m -> (uint32_t)sqrt(m)

@@ -75,7 +75,7 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     else:
         c1 = np.empty(n); c2 = np.empty(n)
     met = np.zeros(2); fm = np.zeros((nFolds, 2))
-    kms = np.zeros(len(KERNEL_CLASSES)); kl = np.zeros(len(KERNEL_CLASSES), np.uint64); st = np.zeros(3, np.uint64)
+    kms = np.zeros(len(KERNEL_CLASSES)); kl = np.zeros(len(KERNEL_CLASSES), np.uint64); st = np.zeros(5, np.uint64)
     err = C.create_string_buffer(512)
     ph = np.zeros(len(PHASES))
 
@@ -95,7 +95,7 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     return dict(class1=c1, class2=c2, auroc=float(met[0]), auprc=float(met[1]), fold_metrics=fm,
                 kernel_ms={k_: float(kms[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
                 kernel_launches={k_: int(kl[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
-                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2])), fold_lanes=min(int(L.psmh_get_fold_lanes()), max(int(nFolds), 1)),
+                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2]), mixed_tie_pairs=int(st[3]), curves_host_sorts=int(st[4])), fold_lanes=min(int(L.psmh_get_fold_lanes()), max(int(nFolds), 1)),
                 host_phases_s={k_: float(ph[i]) for i, k_ in enumerate(PHASES)})
 
 
@@ -145,29 +145,50 @@ def forest_file_rewrite(in_path, out_path):
     return int(nt[0])
 
 
-def cv_grid_run(x, labels, folds, nFolds, grid, seed, device=0, tie_mode=0):
+def cv_grid_run(x, labels, folds, nFolds, grid, seed, device=0, tie_mode=0, stream=None, rank=0, world=1, reduce=None, x_device_ptr=None, n=None, m=None,
+                dev_handle=None):
     """Grid search like cfgEx/gridTune.json (exec.optimizer "grid"): grid = list of (nParts, fp, ratio, k, nTrees, mtry).
-    Appends fold<k>.dat files to a scratch directory.  Returns dict(class1, class2, auroc, auprc, grid_metrics)."""
+    Appends fold<k>.dat files to a scratch directory.  x / x_device_ptr, rank / world / reduce and dev_handle as in cv_run.
+    Returns dict(class1, class2, auroc, auprc, grid_metrics, kernel_launches, stats)."""
     import tempfile
     L = hlib()
-    assert x.dtype == np.float64 and x.flags.c_contiguous
-    n, m = x.shape[0], x.shape[1] - 1
+    L.psmh_cv_grid_run_ex.argtypes = [vp, C.c_int, u32, u32, u32p, u32p, u32, u32p, u32, u32, C.c_int, vp, C.c_int, u32, u32, REDUCE_FN, vp, dp, dp, dp, dp,
+                                      u64p, u64p, vp, C.c_char_p, C.c_size_t]
+    if x is not None:
+        assert x.dtype == np.float64 and x.flags.c_contiguous
+        n, m = x.shape[0], x.shape[1] - 1
+        xptr, isdev = x.ctypes.data, 0
+    else:
+        xptr, isdev = x_device_ptr, 1
     labels = np.ascontiguousarray(labels, np.uint32)
     folds = None if folds is None else np.ascontiguousarray(folds, np.uint32)
     g = np.ascontiguousarray(np.array(grid, np.uint32).reshape(-1, 6))
     c1 = np.zeros(n); c2 = np.zeros(n); met = np.zeros(2); gm = np.zeros((len(g), 2))
+    kl = np.zeros(len(KERNEL_CLASSES), np.uint64); st = np.zeros(5, np.uint64)
     err = C.create_string_buffer(512)
+
+    def _cb(user, ptr, count):
+        try:
+            reduce(ptr, count)
+            return 0
+        except Exception as e:   # never unwind through C
+            print("reduce callback failed:", e)
+            return 1
+    cb = REDUCE_FN(_cb) if reduce is not None else REDUCE_FN()
     cwd = os.getcwd()
     with tempfile.TemporaryDirectory() as d:
         os.chdir(d)
         try:
-            rc = L.psmh_cv_grid_run(_p(x, dp), n, m, _p(labels, u32p), _p(folds, u32p), nFolds, _p(g, u32p), len(g), seed, device, tie_mode,
-                                    _p(c1, dp), _p(c2, dp), _p(met, dp), _p(gm, dp), err, 512)
+            rc = L.psmh_cv_grid_run_ex(vp(xptr), isdev, n, m, _p(labels, u32p), _p(folds, u32p), nFolds, _p(g, u32p), len(g), seed, device,
+                                       vp(stream) if stream else None, tie_mode, rank, world, cb, None, _p(c1, dp), _p(c2, dp), _p(met, dp), _p(gm, dp),
+                                       _p(kl, u64p), _p(st, u64p), vp(dev_handle) if dev_handle else None, err, 512)
         finally:
             os.chdir(cwd)
     if rc != 0:
         raise PsmError(rc, err.value.decode())
-    return dict(class1=c1, class2=c2, auroc=float(met[0]), auprc=float(met[1]), grid_metrics=gm)
+    return dict(class1=c1, class2=c2, auroc=float(met[0]), auprc=float(met[1]), grid_metrics=gm,
+                kernel_launches={k_: int(kl[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
+                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2]), mixed_tie_pairs=int(st[3]), curves_host_sorts=int(st[4])))
 
 
 class HostDevice:
@@ -180,6 +201,9 @@ class HostDevice:
 
     def cv_run(self, *a, **kw):
         return cv_run(*a, dev_handle=self.h, **kw)
+
+    def cv_grid_run(self, *a, **kw):
+        return cv_grid_run(*a, dev_handle=self.h, **kw)
 
     def close(self):
         if self.h:

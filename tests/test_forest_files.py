@@ -46,20 +46,12 @@ def test_train_mode_files_equal_the_reference_and_predict_mode_reads_them(oracle
     ours = tmp_path / "ours"; ref = tmp_path / "ref"
     ours.mkdir(); ref.mkdir()
     H.train_run(x, y, ours, nParts, fp, ratio, k, T, mtry, seed)
-    # the same training matrices through the C ABI (train mode: one fold, training set = every example, no shuffle),
-    # grown and saved by the reference
+    # the reference's own exec.mode "train", driven like its main() (one randomly generated fold, the rand() draws its
+    # std::random_shuffle calls burn before the first SMOTE draw included): the files must be the same bytes
+    oracle.r_mode_train(x, y, ref, nParts, fp, ratio, k, T, mtry, seed)
     pos, neg = np.flatnonzero(y == 1).astype(np.uint32), np.flatnonzero(y == 0).astype(np.uint32)
-    ctx.dataset_upload(x)
-    ctx.fold_begin(pos, neg, pos, neg)
-    ctx.fold_knn(k)
-    draws = oracle.GlibcRand(1).fill(len(pos) * fp * (m + 1) * nParts)
-    ctx.batch_begin(nParts, fp, ratio, 0, nParts)
-    ctx.batch_assemble(draws)
     for p in range(nParts):
-        tr, sz = ctx.batch_get_training(p)
-        f = oracle.r_forest_train(np.ascontiguousarray(tr.T), T, mtry, seed + p)
-        ref_fn = oracle.r_forest_save(f, p, ref)
-        assert open(ref_fn, "rb").read() == open(ours / ("%d.out.forest" % p), "rb").read(), "partition %d" % p
+        assert open(ref / ("%d.out.forest" % p), "rb").read() == open(ours / ("%d.out.forest" % p), "rb").read(), "partition %d" % p
     # predict mode on our files == the reference's predict mode on our files, accumulated in ascending partition order
     out = H.predict_run(x, y, ours, nParts, T, mtry, seed, tie_mode=0)
     order = np.r_[pos, neg]                                   # copyTestSet: positives first, then negatives
