@@ -192,7 +192,7 @@ def workload_config(args, w, name=None):
                             "%d GPUs, dataset replicated, %s" % (args.gpus, "contiguous ranges of the nFolds x nParts (fold, partition) units per rank, ONE NCCL all-reduce of the score arrays [2n] f64 at the end (+ one of the per-fold metrics)"
                                                                 if args.shard != "fold" else "every rank takes its chunk of every fold's partitions (the reference's MPI rule), one NCCL all-reduce of the fold scores per fold")),
             "l2_policy": "inputs larger than L2 (dataset %d MB + per-fold training batches of GBs >> 126 MB L2); no explicit flush" % (w["n"] * (w["m"] + 1) * 8 // 1_000_000),
-            "curves_tie_mode": "auto: stable device radix sort; the reference's host std::sort only if a run of tied scores holds both labels (psm_curves_info)"}
+            "curves_tie_mode": "auto: device radix sort; exact unless a run of tied scores holds both labels, then bracketed by the positives-first / negatives-first tie orders (midpoint if they agree to 2e-7, else the reference's host std::sort)"}
 
 
 GRID = dict(nParts=[10, 20, 30], fp=[1, 2], ratio=[1], k=[5], nTrees=[10], mtry=[5, 7, 10])   # cfgEx/gridTune.json "params"
@@ -310,7 +310,8 @@ def measure_cv(rig, w, x_pinned, x_dev, y, f, steps, warmup, roof_steps, with_br
     return dict(ms_dev=ms_dev, ms_e2e=ms_e2e, outs=outs, outs_e2e=outs_e2e, clocks=clocks, parts=parts, h2d=int(h2d), d2h=int(d2h), kl=kl,
                 roofline=roofline, scores=scores, lanes=outs[0].get("fold_lanes"), kl_roof=kl_roof,
                 curves={"mode": "auto", "mixed_tie_pairs_per_step": sum(o["stats"]["mixed_tie_pairs"] for o in outs) // max(steps, 1),
-                        "host_sorts_per_step": sum(o["stats"]["curves_host_sorts"] for o in outs) / max(steps, 1)})
+                        "host_sorts_per_step": sum(o["stats"]["curves_host_sorts"] for o in outs) / max(steps, 1),
+                        "max_tie_spread": max(o["stats"]["curves_max_tie_spread"] for o in outs)})
 
 
 def parity_block(rig, w, name, x_dev, y, exported, sample):
@@ -340,11 +341,11 @@ def tie_check(rig, w, y, class1):
         a0 = ctx.curves(y, class1, tie_mode=0)
         a1 = ctx.curves(y, class1, tie_mode=1)
         a2 = ctx.curves(y, class1, tie_mode=2)
-        mixed, host = ctx.curves_info()
+        mixed, host, spread = ctx.curves_info()
     finally:
         ctx.close()
     return {"auroc_auto_minus_tie0": a2[0] - a0[0], "auprc_auto_minus_tie0": a2[1] - a0[1], "auroc_tie1_minus_tie0": a1[0] - a0[0],
-            "auprc_tie1_minus_tie0": a1[1] - a0[1], "mixed_tie_pairs_global": mixed, "auto_used_host_sort_global": bool(host)}
+            "auprc_tie1_minus_tie0": a1[1] - a0[1], "mixed_tie_pairs_global": mixed, "auto_used_host_sort_global": bool(host), "tie_spread_global": list(spread)}
 
 
 def also_block(rig, name, w, x_pinned, x_dev, y, f, steps, warmup, with_parity):
@@ -387,7 +388,8 @@ def grid_block(rig, w, x_dev, y, f):
             "steps": 1, "warmup": 1, "ms_per_grid_cv": ms, "inner_partitions": inner, "inner_partitions_per_sec": inner / (ms / 1000.0), "clocks": clocks,
             "gpu_launches": int(sum(outs[0]["kernel_launches"].values())), "quality": {"auroc": outs[0]["auroc"], "auprc": outs[0]["auprc"]},
             "sharding": "single GPU" if rig.world == 1 else "every rank takes its chunk of the partitions of every (grid point, inner fold); one all-reduce of the fold scores per inner fold",
-            "curves": {"mode": "auto", "mixed_tie_pairs": outs[0]["stats"]["mixed_tie_pairs"], "host_sorts": outs[0]["stats"]["curves_host_sorts"]}}
+            "curves": {"mode": "auto", "mixed_tie_pairs": outs[0]["stats"]["mixed_tie_pairs"], "host_sorts": outs[0]["stats"]["curves_host_sorts"],
+                       "max_tie_spread": outs[0]["stats"]["curves_max_tie_spread"]}}
 
 
 def run_ours(args, w):

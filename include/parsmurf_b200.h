@@ -177,12 +177,14 @@ int psm_scratch_read(psm_ctx* ctx, double* host, uint32_t count);
  *      tie order); tie_mode 1: stable device radix sort (ties in index order; may differ from the reference by
  *      more than 1e-6 on heavily tied scores); tie_mode 2: see psm_curves_info. -------------- */
 int psm_curves(psm_ctx* ctx, const uint32_t* labels, const double* scores, uint64_t N, int tie_mode, double* out);
-/* tie_mode 2 ("auto"): the stable device sort, then a count of the adjacent pairs of EQUAL score and DIFFERENT label.  With
- * none, every run of tied scores is single-label, its internal order cannot change a TP/FP prefix, and the result is provably
- * the reference's whatever order its std::sort leaves ties in; otherwise the permutation is redone with the host std::sort
- * of tie_mode 0.  psm_curves_info reports, for the last curves call of the context, that pair count and whether the host
- * sort ran. */
-int psm_curves_info(psm_ctx* ctx, uint64_t* mixed_tie_pairs, int* used_host_sort);
+/* tie_mode 2 ("auto"): the stable device sort with the ties of equal score ordered positives first (the order that maximises
+ * both curves), and a count of the adjacent pairs of EQUAL score and DIFFERENT label.  With none, every run of tied scores is
+ * single-label, its internal order cannot change a TP/FP prefix, and the result is exactly the reference's whatever order its
+ * std::sort leaves ties in.  Otherwise a second sort orders the ties negatives first (the minimum): the reference's value lies
+ * between the two, and when they are within 2e-7 of each other their midpoint is returned; only when the tie order matters
+ * more than that is the permutation redone with the host std::sort of tie_mode 0.  psm_curves_info reports, for the last
+ * curves call of the context, that pair count, whether the host sort ran, and tie_spread2 = {max - min AUROC, max - min AUPRC}. */
+int psm_curves_info(psm_ctx* ctx, uint64_t* mixed_tie_pairs, int* used_host_sort, double* tie_spread2);
 
 /* ---- convenience: steps (5)-(7) for partitions [p0,p1) of the current fold, batched under the memory budget.
  *      draws_host as in psm_batch_assemble for [p0,p1) (or NULL when fp == 0). ------------------------------ */

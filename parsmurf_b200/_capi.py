@@ -83,7 +83,7 @@ def lib():
         L.psm_fold_scores_devptr.argtypes = [vp, C.POINTER(vp), u32p]
         L.psm_fold_scatter_host.argtypes = [vp, dp, dp]
         L.psm_curves.argtypes = [vp, u32p, dp, u64, C.c_int, dp]
-        L.psm_curves_info.argtypes = [vp, u64p, C.POINTER(C.c_int)]
+        L.psm_curves_info.argtypes = [vp, u64p, C.POINTER(C.c_int), dp]
         L.psm_fold_run_partitions.argtypes = [vp] + [u32] * 9 + [i32p]
         L.psm_profile_enable.argtypes = [vp, C.c_int]
         L.psm_profile_classes.argtypes = [vp, C.c_uint32]
@@ -272,10 +272,10 @@ class Context:
         return float(out[0]), float(out[1])
 
     def curves_info(self):
-        """(mixed_tie_pairs, used_host_sort) of the last curves call (tie_mode 2)"""
-        a = u64(); b = C.c_int(0)
-        self._ck(self.L.psm_curves_info(self.h, C.byref(a), C.byref(b)))
-        return int(a.value), int(b.value)
+        """(mixed_tie_pairs, used_host_sort, (auroc spread, auprc spread)) of the last curves call (tie_mode 2)"""
+        a = u64(); b = C.c_int(0); sp = np.zeros(2)
+        self._ck(self.L.psm_curves_info(self.h, C.byref(a), C.byref(b), _p(sp, dp)))
+        return int(a.value), int(b.value), (float(sp[0]), float(sp[1]))
 
     def fold_run_partitions(self, nParts, fp, ratio, nTrees, mtry, seed, fold, p0, p1, draws):
         draws = None if draws is None else np.ascontiguousarray(draws, np.int32)

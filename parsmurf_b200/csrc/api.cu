@@ -93,6 +93,7 @@ struct psm_ctx {
 	// curves
 	uint64_t curvesMixedPairs = 0;
 	int curvesUsedHostSort = 0;
+	double curvesSpread[2] = {0, 0};
 	DevBuf cIdx, cFoldScores, cScratch, cLabels, cPerm, cSorted, cTp, cPartials, cOut, cScores, cKeysA, cKeysB, cValsA, cValsB, cHist;
 
 	// profiling
@@ -351,7 +352,7 @@ int psm_fold_begin_device(psm_ctx* ctx, uint32_t fold, const uint32_t* window31)
 		const uint64_t rBlocks = ((uint64_t)Nneg + 4095) / 4096;
 		ENSURE(ctx->sKeysA, (size_t)Nneg * 8); ENSURE(ctx->sKeysB, (size_t)Nneg * 8);
 		ENSURE(ctx->sValsA, (size_t)Nneg * 4); ENSURE(ctx->sValsB, (size_t)Nneg * 4);
-		ENSURE(ctx->sHist, rBlocks * 256 * 4); ENSURE(ctx->sJ, (size_t)Nneg * 4); ENSURE(ctx->sDraws, (size_t)Nneg * 4);
+		ENSURE(ctx->sHist, (rBlocks + 1) * 256 * 4); ENSURE(ctx->sJ, (size_t)Nneg * 4); ENSURE(ctx->sDraws, (size_t)Nneg * 4);
 		ENSURE(ctx->dRandScratch, (61 + 64 * 31) * 4);
 		ProfScope ps(ctx, K_GATHER, 3 + 3 * 8);
 		if (launch_glibc_rand_fill(window31, (unsigned long long)Nneg - 1, ctx->dRandScratch.as<uint32_t>(), ctx->sDraws.as<int32_t>(), s))
@@ -908,6 +909,41 @@ int psm_fold_scatter_host(psm_ctx* ctx, double* class1Prob, double* class2Prob) 
 
 // ------------------------------------------------------------------------------------------ curves
 // core: labels (u32) and scores (f64) already on the device; hScores (host copy) is only needed for tie_mode 0
+// tie_mode 2: how far the two label-ordered tie extremes may lie apart for their midpoint to be reported (the reference's value
+// lies between them, so the midpoint is within half of this of it -- against the 1e-6 bar of the north star)
+static const double kTieSpreadTol = 2e-7;
+
+static int curves_device_pass(psm_ctx* ctx, const uint32_t* dLabels, const double* dScores, uint64_t N, uint32_t totP, uint32_t totN, int order /*0 plain, 1 positives first, 2 negatives first*/,
+                              bool countMixed, double* out2, unsigned long long* mixed) {
+	cudaStream_t s = ctx->stream;
+	const uint64_t nBlocks = (N + 4095) / 4096;
+	ENSURE(ctx->cKeysA, N * 8); ENSURE(ctx->cKeysB, N * 8); ENSURE(ctx->cValsA, N * 4); ENSURE(ctx->cValsB, N * 4);
+	ENSURE(ctx->cHist, (nBlocks + 1) * 256 * 4);
+	{
+		ProfScope ps(ctx, K_CURVES, order ? 3 + 3 * 9 : 1 + 3 * 8);
+		int rc = order == 0 ? launch_sort_scores_desc(dScores, N, ctx->cKeysA.as<unsigned long long>(), ctx->cKeysB.as<unsigned long long>(),
+		                                              ctx->cValsA.as<uint32_t>(), ctx->cValsB.as<uint32_t>(), ctx->cHist.as<uint32_t>(), s)
+		                    : launch_sort_scores_desc_labelties(dScores, dLabels, N, order == 1, ctx->cKeysA.as<unsigned long long>(), ctx->cKeysB.as<unsigned long long>(),
+		                                                        ctx->cValsA.as<uint32_t>(), ctx->cValsB.as<uint32_t>(), ctx->cHist.as<uint32_t>(), s);
+		if (rc) return fail(ctx, PSM_E_ARG, "curves: sort launch failed");
+	}
+	{
+		ProfScope ps(ctx, K_CURVES, 5 + (countMixed ? 1 : 0));
+		launch_gather_labels(dLabels, ctx->cValsA.as<uint32_t>(), N, ctx->cSorted.as<unsigned char>(), s);
+		if (countMixed) launch_tie_mixed_count(ctx->cKeysA.as<unsigned long long>(), ctx->cSorted.as<unsigned char>(), N, ctx->cOut.as<unsigned long long>() + 2, s);
+		if (launch_curves(ctx->cSorted.as<unsigned char>(), N, totP, totN, ctx->cTp.as<uint32_t>(), ctx->cPartials.as<double>(), nBlocks * 2, ctx->cOut.as<double>(), s))
+			return fail(ctx, PSM_E_ARG, "curves: launch failed");
+	}
+	CU(cudaGetLastError());
+	unsigned long long res[3] = {0, 0, 0};
+	CU(cudaMemcpyAsync(res, ctx->cOut.p, countMixed ? 24 : 16, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	memcpy(out2, res, 16);
+	if (mixed) *mixed = res[2];
+	return PSM_OK;
+}
+
+// core: labels (u32) and scores (f64) already on the device; hScores (host copy) is only needed for the host std::sort
 static int curves_core(psm_ctx* ctx, const uint32_t* dLabels, const double* dScores, const double* hScores, uint64_t N, uint32_t totP, uint32_t totN,
                        int tie_mode, double* out) {
 	if (tie_mode < 0 || tie_mode > 2) return fail(ctx, PSM_E_ARG, "curves: tie_mode must be 0 (host std::sort), 1 (stable device sort) or 2 (auto)");
@@ -915,68 +951,65 @@ static int curves_core(psm_ctx* ctx, const uint32_t* dLabels, const double* dSco
 	ENSURE(ctx->cSorted, N + 64);
 	const uint64_t nBlocks = (N + 4095) / 4096;
 	ENSURE(ctx->cTp, (nBlocks + 1) * 4); ENSURE(ctx->cPartials, nBlocks * 16); ENSURE(ctx->cOut, 32);
-	ctx->curvesMixedPairs = 0; ctx->curvesUsedHostSort = 0;
-	// tie_mode 2 runs the device path first and falls back to the host permutation only when a run of tied scores holds both
-	// labels (curves.cu: tie_mixed_count_kernel) -- the only case in which the tie order can change the curves at all
-	for (int attempt = 0; attempt < 2; attempt++) {
-		const bool host = tie_mode == 0 || (tie_mode == 2 && attempt == 1);
-		const uint32_t* dPerm = nullptr;
+	ctx->curvesMixedPairs = 0; ctx->curvesUsedHostSort = 0; ctx->curvesSpread[0] = ctx->curvesSpread[1] = 0.0;
+	if (tie_mode == 1) return curves_device_pass(ctx, dLabels, dScores, N, totP, totN, 0, false, out, nullptr);
+	if (tie_mode == 2) {
+		// (a) ties ordered positives first: the upper end of what any tie order can give.  No run of tied scores with both
+		// labels (curves.cu: tie_mixed_count_kernel) -> the tie order cannot change a single TP/FP prefix: done, exactly.
+		double hi[2], lo[2];
+		unsigned long long mixed = 0;
+		int rc = curves_device_pass(ctx, dLabels, dScores, N, totP, totN, 1, true, hi, &mixed);
+		if (rc) return rc;
+		ctx->curvesMixedPairs = mixed;
+		if (mixed == 0) { out[0] = hi[0]; out[1] = hi[1]; return PSM_OK; }
+		// (b) negatives first: the lower end.  Both curves are monotone in the position of every positive inside its run of
+		// ties, so whatever order the reference's std::sort leaves the ties in (curves.cpp:31-33), its AUROC / AUPRC lie
+		// between the two; when they are closer than kTieSpreadTol their midpoint is the answer to half of that.
+		if ((rc = curves_device_pass(ctx, dLabels, dScores, N, totP, totN, 2, false, lo, nullptr))) return rc;
+		ctx->curvesSpread[0] = hi[0] - lo[0]; ctx->curvesSpread[1] = hi[1] - lo[1];
+		if (std::fabs(hi[0] - lo[0]) <= kTieSpreadTol && std::fabs(hi[1] - lo[1]) <= kTieSpreadTol) {
+			out[0] = 0.5 * (hi[0] + lo[0]); out[1] = 0.5 * (hi[1] + lo[1]);
+			return PSM_OK;
+		}
+		// (c) the tie order matters: reproduce it (below)
+	}
+	{
 		std::vector<uint32_t> perm;
 		std::vector<double> tmp;
-		if (host) {
-			if (!hScores) {
-				tmp.resize(N);
-				CU(cudaMemcpyAsync(tmp.data(), dScores, N * 8, cudaMemcpyDeviceToHost, s));
-				CU(cudaStreamSynchronize(s));
-				hScores = tmp.data();
-			}
-			// the identical call the reference makes (curves.cpp:31-33): same libstdc++ introsort => same tie order
-			std::vector<size_t> idx(N);
-			std::iota(idx.begin(), idx.end(), 0);
-			std::sort(idx.begin(), idx.end(), [&](size_t i, size_t j) { return hScores[i] > hScores[j]; });
-			perm.resize(N);
-			for (uint64_t i = 0; i < N; i++) perm[i] = (uint32_t)idx[i];
-			ENSURE(ctx->cPerm, N * 4);
-			CU(cudaMemcpyAsync(ctx->cPerm.p, perm.data(), N * 4, cudaMemcpyHostToDevice, s));
-			dPerm = ctx->cPerm.as<uint32_t>();
-			ctx->curvesUsedHostSort = 1;
-		} else {
-			ENSURE(ctx->cKeysA, N * 8); ENSURE(ctx->cKeysB, N * 8); ENSURE(ctx->cValsA, N * 4); ENSURE(ctx->cValsB, N * 4);
-			const uint64_t rBlocks = (N + 4095) / 4096;
-			ENSURE(ctx->cHist, rBlocks * 256 * 4);
-			ProfScope ps(ctx, K_CURVES, 1 + 3 * 8);
-			if (launch_sort_scores_desc(dScores, N, ctx->cKeysA.as<unsigned long long>(), ctx->cKeysB.as<unsigned long long>(),
-			                            ctx->cValsA.as<uint32_t>(), ctx->cValsB.as<uint32_t>(), ctx->cHist.as<uint32_t>(), s))
-				return fail(ctx, PSM_E_ARG, "curves: sort launch failed");
-			dPerm = ctx->cValsA.as<uint32_t>();
+		if (!hScores) {
+			tmp.resize(N);
+			CU(cudaMemcpyAsync(tmp.data(), dScores, N * 8, cudaMemcpyDeviceToHost, s));
+			CU(cudaStreamSynchronize(s));
+			hScores = tmp.data();
 		}
+		// the identical call the reference makes (curves.cpp:31-33): same libstdc++ introsort => same tie order
+		std::vector<size_t> idx(N);
+		std::iota(idx.begin(), idx.end(), 0);
+		std::sort(idx.begin(), idx.end(), [&](size_t i, size_t j) { return hScores[i] > hScores[j]; });
+		perm.resize(N);
+		for (uint64_t i = 0; i < N; i++) perm[i] = (uint32_t)idx[i];
+		ENSURE(ctx->cPerm, N * 4);
+		CU(cudaMemcpyAsync(ctx->cPerm.p, perm.data(), N * 4, cudaMemcpyHostToDevice, s));
+		ctx->curvesUsedHostSort = 1;
 		{
-			ProfScope ps(ctx, K_CURVES, 5 + (tie_mode == 2 && !host ? 1 : 0));
-			launch_gather_labels(dLabels, dPerm, N, ctx->cSorted.as<unsigned char>(), s);
-			if (tie_mode == 2 && !host)
-				launch_tie_mixed_count(ctx->cKeysA.as<unsigned long long>(), ctx->cSorted.as<unsigned char>(), N, ctx->cOut.as<unsigned long long>() + 2, s);
+			ProfScope ps(ctx, K_CURVES, 5);
+			launch_gather_labels(dLabels, ctx->cPerm.as<uint32_t>(), N, ctx->cSorted.as<unsigned char>(), s);
 			if (launch_curves(ctx->cSorted.as<unsigned char>(), N, totP, totN, ctx->cTp.as<uint32_t>(), ctx->cPartials.as<double>(), nBlocks * 2,
 			                  ctx->cOut.as<double>(), s))
 				return fail(ctx, PSM_E_ARG, "curves: launch failed");
 		}
 		CU(cudaGetLastError());
-		unsigned long long res[3] = {0, 0, 0};
-		CU(cudaMemcpyAsync(res, ctx->cOut.p, tie_mode == 2 && !host ? 24 : 16, cudaMemcpyDeviceToHost, s));
+		CU(cudaMemcpyAsync(out, ctx->cOut.p, 16, cudaMemcpyDeviceToHost, s));
 		CU(cudaStreamSynchronize(s));   // also keeps `perm` alive until the upload is done
-		memcpy(out, res, 16);
-		if (tie_mode == 2 && !host) {
-			ctx->curvesMixedPairs = res[2];
-			if (res[2] != 0) continue;    // a tied run with both labels: redo with the reference's own tie order
-		}
-		break;
 	}
 	return PSM_OK;
 }
 
-int psm_curves_info(psm_ctx* ctx, uint64_t* mixed_tie_pairs, int* used_host_sort) {
+int psm_curves_info(psm_ctx* ctx, uint64_t* mixed_tie_pairs, int* used_host_sort, double* tie_spread2) {
 	if (!ctx) return PSM_E_ARG;
 	if (mixed_tie_pairs) *mixed_tie_pairs = ctx->curvesMixedPairs;
 	if (used_host_sort) *used_host_sort = ctx->curvesUsedHostSort;
+	if (tie_spread2) { tie_spread2[0] = ctx->curvesSpread[0]; tie_spread2[1] = ctx->curvesSpread[1]; }
 	return PSM_OK;
 }
 

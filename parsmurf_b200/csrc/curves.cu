@@ -232,6 +232,28 @@ constexpr int RB = 256;
 constexpr int RTILES = 16;                 // tiles of RB elements per block
 constexpr int RCHUNK = RB * RTILES;
 
+// Per-pass digit scan: hist is [256 digits][nBlocks] block counts.  One warp per digit turns its row into exclusive prefixes
+// (coalesced 32-counter steps with a running carry) and leaves the digit's total in hist[256 * nBlocks + digit]; the scatter
+// kernel adds the exclusive scan of those 256 totals itself.  (A single 1024-thread block scanning all 256 * nBlocks counters
+// took 33 us per pass at 1M keys -- 84 such launches per BASELINE configs[1] CV, profiles/r01_summary.md.)
+__global__ void __launch_bounds__(256) radix_scan_digits_kernel(uint32_t* __restrict__ hist, uint32_t nBlocks) {
+	const uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (d >= 256) return;
+	const uint32_t lane = threadIdx.x & 31;
+	uint32_t* row = hist + (size_t)d * nBlocks;
+	uint32_t carry = 0;
+	for (uint32_t b = 0; b < nBlocks; b += 32) {
+		const uint32_t i = b + lane;
+		const uint32_t v = i < nBlocks ? row[i] : 0u;
+		uint32_t inc = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += t; }
+		if (i < nBlocks) row[i] = carry + inc - v;
+		carry += __shfl_sync(0xffffffffu, inc, 31);
+	}
+	if (lane == 0) hist[(size_t)256 * nBlocks + d] = carry;
+}
+
 __global__ void sort_init_kernel(const double* __restrict__ scores, uint64_t N, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < N) { keys[i] = ~f64_key(scores[i]); vals[i] = (uint32_t)i; }
@@ -258,7 +280,19 @@ __global__ void __launch_bounds__(RB) radix_scatter_kernel(const unsigned long l
 	__shared__ uint32_t wc[8][257];
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	const unsigned lt = lanemask_lt();
-	base[tid] = hist[(size_t)tid * nBlocks + blockIdx.x];
+	{
+		// exclusive scan of the 256 digit totals (radix_scan_digits_kernel) + this block's offset inside its digit
+		const uint32_t tot = hist[(size_t)256 * nBlocks + tid];
+		uint32_t inc = tot;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+		if (lane == 31) wc[0][w] = inc;
+		__syncthreads();
+		uint32_t off = inc - tot;
+		for (int ww = 0; ww < w; ww++) off += wc[0][ww];
+		__syncthreads();
+		base[tid] = off + hist[(size_t)tid * nBlocks + blockIdx.x];
+	}
 	if (tid == 0) base[256] = 0;
 	for (int i = tid; i < 8 * 257; i += RB) (&wc[0][0])[i] = 0;
 	__syncthreads();
@@ -295,7 +329,44 @@ int launch_sort_scores_desc(const double* scores, uint64_t N, unsigned long long
 	uint32_t *vin = valsA, *vout = valsB;
 	for (int pass = 0; pass < 8; pass++) {
 		radix_hist_kernel<<<nBlocks, RB, 0, s>>>(kin, N, pass * 8, nBlocks, hist);
-		scan_blocksums_kernel<<<1, 1024, 0, s>>>(hist, 256u * nBlocks);
+		radix_scan_digits_kernel<<<32, 256, 0, s>>>(hist, nBlocks);
+		radix_scatter_kernel<<<nBlocks, RB, 0, s>>>(kin, vin, N, pass * 8, nBlocks, hist, kout, vout);
+		unsigned long long* tk = kin; kin = kout; kout = tk;
+		uint32_t* tv = vin; vin = vout; vout = tv;
+	}
+	return 0;
+}
+
+// tie_mode 2 bracket: the same descending sort, but with the ties of equal score ordered by LABEL -- positives first (the order
+// that maximises both curves) or negatives first (the one that minimises them).  LSD radix sorting is stable, so it is enough to
+// start from an order that has the labels partitioned: one extra radix pass on a 1-bit label key, then the keys are rebuilt in
+// that order and the eight score passes follow.
+__global__ void sort_init_label_kernel(const uint32_t* __restrict__ labels, uint64_t N, int posFirst, unsigned long long* __restrict__ keys,
+                                       uint32_t* __restrict__ vals) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < N) { const bool pos = labels[i] == 1u; keys[i] = (pos == (posFirst != 0)) ? 0ull : 1ull; vals[i] = (uint32_t)i; }
+}
+__global__ void sort_rekey_kernel(const double* __restrict__ scores, const uint32_t* __restrict__ valsIn, uint64_t N,
+                                  unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < N) { const uint32_t v = valsIn[i]; keys[i] = ~f64_key(scores[v]); vals[i] = v; }
+}
+// result (permutation) in valsA, sorted keys in keysA
+int launch_sort_scores_desc_labelties(const double* scores, const uint32_t* labels, uint64_t N, int posFirst, unsigned long long* keysA,
+                                      unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, uint32_t* hist, cudaStream_t s) {
+	if (N == 0 || N >= (1ull << 32)) return -1;
+	const uint32_t nBlocks = (uint32_t)((N + RCHUNK - 1) / RCHUNK);
+	const unsigned g = (unsigned)((N + 255) / 256);
+	sort_init_label_kernel<<<g, 256, 0, s>>>(labels, N, posFirst, keysA, valsA);
+	radix_hist_kernel<<<nBlocks, RB, 0, s>>>(keysA, N, 0, nBlocks, hist);
+	radix_scan_digits_kernel<<<32, 256, 0, s>>>(hist, nBlocks);
+	radix_scatter_kernel<<<nBlocks, RB, 0, s>>>(keysA, valsA, N, 0, nBlocks, hist, keysB, valsB);
+	sort_rekey_kernel<<<g, 256, 0, s>>>(scores, valsB, N, keysA, valsA);
+	unsigned long long *kin = keysA, *kout = keysB;
+	uint32_t *vin = valsA, *vout = valsB;
+	for (int pass = 0; pass < 8; pass++) {
+		radix_hist_kernel<<<nBlocks, RB, 0, s>>>(kin, N, pass * 8, nBlocks, hist);
+		radix_scan_digits_kernel<<<32, 256, 0, s>>>(hist, nBlocks);
 		radix_scatter_kernel<<<nBlocks, RB, 0, s>>>(kin, vin, N, pass * 8, nBlocks, hist, kout, vout);
 		unsigned long long* tk = kin; kin = kout; kout = tk;
 		uint32_t* tv = vin; vin = vout; vout = tv;
@@ -304,7 +375,7 @@ int launch_sort_scores_desc(const double* scores, uint64_t N, unsigned long long
 }
 
 // generic entry: ascending LSD sort of prefilled (keysA, valsA) on the low 8*passes key bits; passes must be even so that the
-// result is back in keysA / valsA.  hist: ((N + 4095) / 4096) * 256 uint32.
+// result is back in keysA / valsA.  hist: ((N + 4095) / 4096) * 256 + 256 uint32.
 int launch_radix_sort_u64(unsigned long long* keysA, unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, uint64_t N, int passes,
                           uint32_t* hist, cudaStream_t s) {
 	if (N == 0) return 0;
@@ -314,7 +385,7 @@ int launch_radix_sort_u64(unsigned long long* keysA, unsigned long long* keysB, 
 	uint32_t *vin = valsA, *vout = valsB;
 	for (int pass = 0; pass < passes; pass++) {
 		radix_hist_kernel<<<nBlocks, RB, 0, s>>>(kin, N, pass * 8, nBlocks, hist);
-		scan_blocksums_kernel<<<1, 1024, 0, s>>>(hist, 256u * nBlocks);
+		radix_scan_digits_kernel<<<32, 256, 0, s>>>(hist, nBlocks);
 		radix_scatter_kernel<<<nBlocks, RB, 0, s>>>(kin, vin, N, pass * 8, nBlocks, hist, kout, vout);
 		unsigned long long* tk = kin; kin = kout; kout = tk;
 		uint32_t* tv = vin; vin = vout; vout = tv;

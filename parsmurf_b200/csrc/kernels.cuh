@@ -97,6 +97,8 @@ void launch_gather_labels(const uint32_t* labels, const uint32_t* perm, uint64_t
 int launch_sort_scores_desc(const double* scores, uint64_t N, unsigned long long* keysA, unsigned long long* keysB, uint32_t* valsA,
                             uint32_t* valsB, uint32_t* hist, cudaStream_t s);
 
+int launch_sort_scores_desc_labelties(const double* scores, const uint32_t* labels, uint64_t N, int posFirst, unsigned long long* keysA,
+                                      unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, uint32_t* hist, cudaStream_t s);
 int launch_radix_sort_u64(unsigned long long* keysA, unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, uint64_t N, int passes,
                           uint32_t* hist, cudaStream_t s);
 // shuffle.cu

@@ -578,8 +578,12 @@ void hyperSMURF::setSharding(uint32_t rank_, uint32_t world_, std::function<void
 }
 
 void hyperSMURF::noteCurves(Device* d) {
-	uint64_t mixed = 0; int host = 0;
-	if (psm_curves_info(d->ctx, &mixed, &host) == PSM_OK) { curvesMixedPairs += mixed; curvesHostSorts += (uint64_t)host; }
+	uint64_t mixed = 0; int host = 0; double sp[2] = {0, 0};
+	if (psm_curves_info(d->ctx, &mixed, &host, sp) == PSM_OK) {
+		curvesMixedPairs += mixed; curvesHostSorts += (uint64_t)host;
+		std::lock_guard<std::mutex> lk(spreadMtx);
+		curvesMaxSpread = std::max(curvesMaxSpread, std::max(std::fabs(sp[0]), std::fabs(sp[1])));
+	}
 }
 
 void hyperSMURF::initStandard() {                                           // src/hyperSMURF.cpp:22-51
@@ -1225,7 +1229,7 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		if (foldMetrics && mode == MODE_CV) for (uint32_t f = 0; f < nFolds; f++) { foldMetrics[2 * f] = smurfer.foldAuroc[f]; foldMetrics[2 * f + 1] = smurfer.foldAuprc[f]; }
 		if (kernelMs) for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) kernelMs[i] = 0;
 		if (kernelLaunches) for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) kernelLaunches[i] = 0;
-		if (stats3) { stats3[0] = stats3[1] = stats3[2] = 0; stats3[3] = smurfer.curvesMixedPairs; stats3[4] = smurfer.curvesHostSorts; }
+		if (stats3) { stats3[0] = stats3[1] = stats3[2] = 0; stats3[3] = smurfer.curvesMixedPairs; stats3[4] = smurfer.curvesHostSorts; stats3[5] = (uint64_t)std::llround(smurfer.curvesMaxSpread * 1e15); }
 		for (uint32_t li = 0; li < dev.laneCount(); li++) {                  // kernel times / counts / byte statistics summed over the fold lanes
 			Device* d = dev.lane(li);
 			double ms[PSM_NUM_KERNEL_CLASSES]; uint64_t ln[PSM_NUM_KERNEL_CLASSES]; uint64_t st[3];
@@ -1314,7 +1318,7 @@ int psmh_cv_grid_run_ex(const double* x, int x_is_device, uint32_t n, uint32_t m
 		if (metrics) { metrics[0] = smurfer.auroc; metrics[1] = smurfer.auprc; }
 		if (gridMetrics) for (uint32_t i = 0; i < G; i++) { gridMetrics[2 * i] = gp[i].auroc; gridMetrics[2 * i + 1] = gp[i].auprc; }
 		if (kernelLaunches) for (int i = 0; i < PSM_NUM_KERNEL_CLASSES; i++) kernelLaunches[i] = 0;
-		if (stats5) { stats5[0] = stats5[1] = stats5[2] = 0; stats5[3] = smurfer.curvesMixedPairs; stats5[4] = smurfer.curvesHostSorts; }
+		if (stats5) { stats5[0] = stats5[1] = stats5[2] = 0; stats5[3] = smurfer.curvesMixedPairs; stats5[4] = smurfer.curvesHostSorts; stats5[5] = (uint64_t)std::llround(smurfer.curvesMaxSpread * 1e15); }
 		for (uint32_t li = 0; li < dev.laneCount(); li++) {
 			Device* d = dev.lane(li);
 			uint64_t ln[PSM_NUM_KERNEL_CLASSES]; uint64_t st[3];

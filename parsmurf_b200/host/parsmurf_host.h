@@ -307,6 +307,8 @@ public:
 	// curvesTieMode 2 ("auto", psm_curves_info): over all the curves calls of this run, the adjacent (equal score, different
 	// label) pairs the device sort met, and how many calls had to be redone with the host std::sort
 	std::atomic<uint64_t> curvesMixedPairs{0}, curvesHostSorts{0};
+	double curvesMaxSpread = 0;      // largest |max - min| AUROC / AUPRC over the tie orders, over all the calls that had mixed ties
+	std::mutex spreadMtx;
 
 private:
 	struct FoldGate;

@@ -75,7 +75,7 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     else:
         c1 = np.empty(n); c2 = np.empty(n)
     met = np.zeros(2); fm = np.zeros((nFolds, 2))
-    kms = np.zeros(len(KERNEL_CLASSES)); kl = np.zeros(len(KERNEL_CLASSES), np.uint64); st = np.zeros(5, np.uint64)
+    kms = np.zeros(len(KERNEL_CLASSES)); kl = np.zeros(len(KERNEL_CLASSES), np.uint64); st = np.zeros(6, np.uint64)
     err = C.create_string_buffer(512)
     ph = np.zeros(len(PHASES))
 
@@ -95,7 +95,7 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     return dict(class1=c1, class2=c2, auroc=float(met[0]), auprc=float(met[1]), fold_metrics=fm,
                 kernel_ms={k_: float(kms[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
                 kernel_launches={k_: int(kl[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
-                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2]), mixed_tie_pairs=int(st[3]), curves_host_sorts=int(st[4])), fold_lanes=min(int(L.psmh_get_fold_lanes()), max(int(nFolds), 1)),
+                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2]), mixed_tie_pairs=int(st[3]), curves_host_sorts=int(st[4]), curves_max_tie_spread=float(st[5]) * 1e-15), fold_lanes=min(int(L.psmh_get_fold_lanes()), max(int(nFolds), 1)),
                 host_phases_s={k_: float(ph[i]) for i, k_ in enumerate(PHASES)})
 
 
@@ -164,7 +164,7 @@ def cv_grid_run(x, labels, folds, nFolds, grid, seed, device=0, tie_mode=0, stre
     folds = None if folds is None else np.ascontiguousarray(folds, np.uint32)
     g = np.ascontiguousarray(np.array(grid, np.uint32).reshape(-1, 6))
     c1 = np.zeros(n); c2 = np.zeros(n); met = np.zeros(2); gm = np.zeros((len(g), 2))
-    kl = np.zeros(len(KERNEL_CLASSES), np.uint64); st = np.zeros(5, np.uint64)
+    kl = np.zeros(len(KERNEL_CLASSES), np.uint64); st = np.zeros(6, np.uint64)
     err = C.create_string_buffer(512)
 
     def _cb(user, ptr, count):
@@ -188,7 +188,7 @@ def cv_grid_run(x, labels, folds, nFolds, grid, seed, device=0, tie_mode=0, stre
         raise PsmError(rc, err.value.decode())
     return dict(class1=c1, class2=c2, auroc=float(met[0]), auprc=float(met[1]), grid_metrics=gm,
                 kernel_launches={k_: int(kl[i]) for i, k_ in enumerate(KERNEL_CLASSES)},
-                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2]), mixed_tie_pairs=int(st[3]), curves_host_sorts=int(st[4])))
+                stats=dict(split_bytes=int(st[0]), nodes=int(st[1]), levels=int(st[2]), mixed_tie_pairs=int(st[3]), curves_host_sorts=int(st[4]), curves_max_tie_spread=float(st[5]) * 1e-15))
 
 
 class HostDevice:

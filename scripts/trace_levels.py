@@ -1,11 +1,24 @@
-"""Per-level timing trace of one fold of BASELINE configs[1] (PSM_TRACE_LEVELS=1)."""
+"""Per-level timing trace of ONE fold (PSM_TRACE_LEVELS=1): python scripts/trace_levels.py [workload] [fold]"""
 import os, sys
 os.environ["PSM_TRACE_LEVELS"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bench
+import parsmurf_b200 as psm
 from parsmurf_b200 import host_api as H
-w = dict(bench.WORKLOADS["cfg2"]); w["nFolds"] = 5
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+fold = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+w = dict(bench.WORKLOADS[name])
 x, y, f = bench.make_data(w)
-# only fold 0: mark minFold/maxFold through a 1-fold trick is not exposed; run the whole CV but stop tracing after fold 0
-out = H.cv_run(x, y, f, w["nFolds"], w["nParts"], w["fp"], w["ratio"], w["k"], w["nTrees"], w["mtry"], w["seed"], tie_mode=1)
+fd = H.ttd_fold(y, f, w["nFolds"], fold)
+ctx = psm.Context(0)
+ctx.dataset_upload(x)
+ctx.fold_begin(fd["trngPos"], fd["trngNeg"], fd["testPos"], fd["testNeg"])
+ctx.fold_knn(w["k"])
+P = len(fd["trngPos"])
+draws = H.rand_fill(1, P * w["fp"] * (w["m"] + 1) * w["nParts"])
+ctx.profile_enable(True)
+ctx.fold_run_partitions(w["nParts"], w["fp"], w["ratio"], w["nTrees"], w["mtry"], w["seed"], fold, 0, w["nParts"], draws)
+ctx.sync()
+print({k: v for k, v in ctx.profile_get().items()}, file=sys.stderr)
+print(ctx.stats_get(), file=sys.stderr)

@@ -470,6 +470,53 @@ def test_fold_scores_bit_exact_and_curves(ctx, oracle, name):
     assert abs(got1[0] - want[0]) < 5e-3 and abs(got1[1] - want[1]) < 5e-3   # stable tie order may differ
 
 
+def test_curves_auto_tie_mode(ctx, oracle):
+    """tie_mode 2: exact when no run of tied scores holds both labels; otherwise bracketed by the positives-first / negatives-first
+    tie orders -- the reference's value (oracle: the identical std::sort call) lies inside the bracket, the midpoint is returned
+    when the bracket is narrower than 2e-7, and the host std::sort decides when it is not"""
+    rng = np.random.default_rng(11)
+    n = 200_000
+    y = (rng.random(n) < 0.01).astype(np.uint32)
+    # (a) continuous scores: no ties at all
+    s = rng.random(n) + 0.3 * y
+    want = oracle.o_curves(y, s)
+    got = ctx.curves(y, s, tie_mode=2)
+    mixed, host, spread = ctx.curves_info()
+    assert mixed == 0 and host == 0 and spread == (0.0, 0.0)
+    assert abs(got[0] - want[0]) < 1e-12 and abs(got[1] - want[1]) < 1e-12
+    # (b) a huge run of ties that is single-label (most negatives score exactly 0), ties elsewhere only among equal labels
+    s = np.where(y == 1, 0.5 + np.round(rng.random(n), 2), np.where(rng.random(n) < 0.9, 0.0, np.round(0.4 * rng.random(n), 3)))
+    want = oracle.o_curves(y, s)
+    got = ctx.curves(y, s, tie_mode=2)
+    mixed, host, spread = ctx.curves_info()
+    assert mixed == 0 and host == 0
+    assert abs(got[0] - want[0]) < 1e-12 and abs(got[1] - want[1]) < 1e-12
+    # (c) a few positives inside the big run of zeros: the tie order moves the curves by less than the tolerance -> midpoint
+    s2 = s.copy()
+    pos = np.flatnonzero(y == 1)
+    s2[pos[:3]] = 0.0
+    want = oracle.o_curves(y, s2)
+    hi = ctx.curves(y, s2, tie_mode=2)
+    mixed, host, spread = ctx.curves_info()
+    assert mixed > 0
+    if host == 0:
+        assert 0 <= spread[0] <= 2e-7 and 0 <= spread[1] <= 2e-7
+        assert abs(hi[0] - want[0]) <= spread[0] / 2 + 1e-8 and abs(hi[1] - want[1]) <= spread[1] / 2 + 1e-12   # AUROC terms are float: 1e-8 of slack
+    else:
+        assert abs(hi[0] - want[0]) < 1e-12 and abs(hi[1] - want[1]) < 1e-12
+    # (d) heavy mixed ties (21 score levels): the bracket is wide, the host sort must decide, result == tie_mode 0 == oracle
+    s3 = np.round(rng.random(n) * 20) / 20 + 0.1 * y
+    s3 = np.round(s3 * 20) / 20
+    want = oracle.o_curves(y, s3)
+    got = ctx.curves(y, s3, tie_mode=2)
+    mixed, host, spread = ctx.curves_info()
+    assert mixed > 0 and host == 1 and (spread[0] > 2e-7 or spread[1] > 2e-7)
+    assert abs(got[0] - want[0]) < 1e-12 and abs(got[1] - want[1]) < 1e-12
+    # the bracket really brackets: tie_mode 1 (ties in index order) and the reference's order both lie inside [lo, hi]
+    t1 = ctx.curves(y, s3, tie_mode=1)
+    assert want[0] - spread[0] - 1e-7 <= t1[0] <= want[0] + spread[0] + 1e-7
+
+
 def test_predict_paths_agree_bitwise(oracle, monkeypatch):
     """compact predict (fp32 tile + 8-byte nodes + exact fp64 tie-break) == 16-byte-node TMA path == oracle, incl. data with
     values that collide in fp32 (features rounded to a coarse grid so float(v) == float(threshold) happens constantly)"""
