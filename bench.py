@@ -192,7 +192,7 @@ def workload_config(args, w, name=None):
                             "%d GPUs, dataset replicated, %s" % (args.gpus, "contiguous ranges of the nFolds x nParts (fold, partition) units per rank, ONE NCCL all-reduce of the score arrays [2n] f64 at the end (+ one of the per-fold metrics)"
                                                                 if args.shard != "fold" else "every rank takes its chunk of every fold's partitions (the reference's MPI rule), one NCCL all-reduce of the fold scores per fold")),
             "l2_policy": "inputs larger than L2 (dataset %d MB + per-fold training batches of GBs >> 126 MB L2); no explicit flush" % (w["n"] * (w["m"] + 1) * 8 // 1_000_000),
-            "curves_tie_mode": "auto: device radix sort; exact unless a run of tied scores holds both labels, then bracketed by the positives-first / negatives-first tie orders (midpoint if they agree to 2e-7, else the reference's host std::sort)"}
+            "curves_tie_mode": "auto: device radix sort; exact unless a run of tied scores holds both labels, then bracketed by the positives-first / negatives-first tie orders (midpoint if they agree to 1e-6, else the reference's host std::sort)"}
 
 
 GRID = dict(nParts=[10, 20, 30], fp=[1, 2], ratio=[1], k=[5], nTrees=[10], mtry=[5, 7, 10])   # cfgEx/gridTune.json "params"

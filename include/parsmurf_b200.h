@@ -181,10 +181,15 @@ int psm_curves(psm_ctx* ctx, const uint32_t* labels, const double* scores, uint6
  * both curves), and a count of the adjacent pairs of EQUAL score and DIFFERENT label.  With none, every run of tied scores is
  * single-label, its internal order cannot change a TP/FP prefix, and the result is exactly the reference's whatever order its
  * std::sort leaves ties in.  Otherwise a second sort orders the ties negatives first (the minimum): the reference's value lies
- * between the two, and when they are within 2e-7 of each other their midpoint is returned; only when the tie order matters
+ * between the two, and when they are within 1e-6 of each other their midpoint is returned (error <= 5e-7); only when the tie order matters
  * more than that is the permutation redone with the host std::sort of tie_mode 0.  psm_curves_info reports, for the last
  * curves call of the context, that pair count, whether the host sort ran, and tie_spread2 = {max - min AUROC, max - min AUPRC}. */
 int psm_curves_info(psm_ctx* ctx, uint64_t* mixed_tie_pairs, int* used_host_sort, double* tie_spread2);
+/* Host only (no device needed): the permutation std::sort leaves an index vector in under the reference's comparator
+ * (src/curves.cpp:31-33: descending score, ties wherever libstdc++'s introsort puts them), computed on `threads` host threads
+ * (0 = up to 16) with libstdc++'s own partition / insertion / heap steps.  This is what tie_mode 0 (and the fallback of
+ * tie_mode 2) uploads. */
+int psm_host_sort_permutation(const double* scores, uint64_t N, uint32_t* perm, int threads);
 
 /* ---- convenience: steps (5)-(7) for partitions [p0,p1) of the current fold, batched under the memory budget.
  *      draws_host as in psm_batch_assemble for [p0,p1) (or NULL when fp == 0). ------------------------------ */

@@ -8,8 +8,10 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libparsmurf_b200.so")
-HOST_LIB_PATH = os.path.join(_HERE, "_build", "libparsmurf_host.so")
+# PSM_BUILD_DIR: an alternative in-tree build directory (kernel experiments built with `make OUT=... EXTRA=-D...`)
+_BUILD = os.environ.get("PSM_BUILD_DIR") or os.path.join(_HERE, "_build")
+LIB_PATH = os.path.join(_BUILD, "libparsmurf_b200.so")
+HOST_LIB_PATH = os.path.join(_BUILD, "libparsmurf_host.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "parsmurf_b200.h")
 
 KERNEL_CLASSES = ["knn", "assemble", "feature_sort", "bootstrap", "build_lists", "split_search", "split_select",

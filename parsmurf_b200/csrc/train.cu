@@ -316,41 +316,39 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 // counts need ONE warp scan per chunk; the next chunk's loads are issued before the current chunk is evaluated.
 // The exact fp64 score (two IEEE divisions) is only evaluated for positions whose fp32 estimate could still beat the
 // lane's running best: estimate error < 1e-6 relative, filter margin 5e-6, so no winner is ever skipped.
-#ifndef PSM_SS_IPL
-#define PSM_SS_IPL 4
-#endif
-constexpr int SS_IPL = PSM_SS_IPL;   // entries per lane per chunk (multiple of 4)
 #ifndef SS_MINB
 #define SS_MINB 8
 #endif
+#ifndef SS_MINB_MULTI
+#define SS_MINB_MULTI 6      // the chunk loop keeps 78 registers live (two chunks of entries in flight)
+#endif
 
-__device__ __forceinline__ void ss_vec(const unsigned long long* p, unsigned long long (&e)[SS_IPL]) {
+// entries per lane and chunk: the compact 4-byte entries take 8 (two 16-byte loads, 256-entry chunks) in the chunk loop of the
+// long segments and 4 in the single-chunk classes; the 8-byte entries always 4
+template <typename E, bool MULTI> struct SsIpl { static constexpr int v = (MULTI && sizeof(E) == 4) ? 8 : 4; };
+
+template <int IPL> __device__ __forceinline__ void ss_vec(const unsigned long long* p, unsigned long long (&e)[IPL]) {
 #pragma unroll
-	for (int q = 0; q < SS_IPL / 2; q++) {
+	for (int q = 0; q < IPL / 2; q++) {
 		const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(p + 2 * q));
 		e[2 * q] = a.x; e[2 * q + 1] = a.y;
 	}
 }
-__device__ __forceinline__ void ss_vec(const uint32_t* p, uint32_t (&e)[SS_IPL]) {
-	if (SS_IPL == 2) {
-		const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
-		e[0] = a.x; e[1 % SS_IPL] = a.y;
-	} else {
+template <int IPL> __device__ __forceinline__ void ss_vec(const uint32_t* p, uint32_t (&e)[IPL]) {
 #pragma unroll
-		for (int q = 0; q < SS_IPL / 4; q++) {
-			const uint4 a = __ldg(reinterpret_cast<const uint4*>(p + 4 * q));
-			e[(4 * q) % SS_IPL] = a.x; e[(4 * q + 1) % SS_IPL] = a.y; e[(4 * q + 2) % SS_IPL] = a.z; e[(4 * q + 3) % SS_IPL] = a.w;
-		}
+	for (int q = 0; q < IPL / 4; q++) {
+		const uint4 a = __ldg(reinterpret_cast<const uint4*>(p + 4 * q));
+		e[4 * q] = a.x; e[4 * q + 1] = a.y; e[4 * q + 2] = a.z; e[4 * q + 3] = a.w;
 	}
 }
-template <typename E>
-__device__ __forceinline__ void ss_load(const E* __restrict__ base, uint32_t v, uint32_t lo, uint32_t hi, E (&e)[SS_IPL]) {
-	// entries v..v+3 of the aligned grid; valid iff lo <= index < hi
-	if (v >= lo && v + SS_IPL <= hi) {
-		ss_vec(base + v, e);
+template <typename E, int IPL>
+__device__ __forceinline__ void ss_load(const E* __restrict__ base, uint32_t v, uint32_t lo, uint32_t hi, E (&e)[IPL]) {
+	// entries v..v+IPL-1 of the aligned grid; valid iff lo <= index < hi
+	if (v >= lo && v + IPL <= hi) {
+		ss_vec<IPL>(base + v, e);
 	} else {
 #pragma unroll
-		for (int j = 0; j < SS_IPL; j++) e[j] = (v + j >= lo && v + j < hi) ? __ldg(base + v + j) : (E)0;
+		for (int j = 0; j < IPL; j++) e[j] = (v + j >= lo && v + j < hi) ? __ldg(base + v + j) : (E)0;
 	}
 }
 
@@ -358,18 +356,33 @@ __device__ __forceinline__ void ss_load(const E* __restrict__ base, uint32_t v, 
 // belong to neighbouring segments of the same list, or to the list's padding: start - off is a multiple of the vector
 // length and the stride is a multiple of 4, so the load never leaves the allocation) and the invalid slots are zeroed
 // afterwards -- no divergent per-entry path for the lanes that straddle the segment ends.
-template <typename E>
-__device__ __forceinline__ void ss_load_single(const E* __restrict__ base, uint32_t v, uint32_t lo, uint32_t hi, E (&e)[SS_IPL]) {
+template <typename E, int IPL>
+__device__ __forceinline__ void ss_load_single(const E* __restrict__ base, uint32_t v, uint32_t lo, uint32_t hi, E (&e)[IPL]) {
 #pragma unroll
-	for (int j = 0; j < SS_IPL; j++) e[j] = (E)0;
-	if (v < hi && v + SS_IPL > lo) ss_vec(base + v, e);
+	for (int j = 0; j < IPL; j++) e[j] = (E)0;
+	if (v < hi && v + IPL > lo) ss_vec<IPL>(base + v, e);
 #pragma unroll
-	for (int j = 0; j < SS_IPL; j++) e[j] = (v + j >= lo && v + j < hi) ? e[j] : (E)0;
+	for (int j = 0; j < IPL; j++) e[j] = (v + j >= lo && v + j < hi) ? e[j] : (E)0;
 }
 
+// Packed running class counts (positives in the high half, negatives in the low half of one word) and their conversion to
+// fp32 WITHOUT the conversion unit: counts are below 2^23, so (count | 0x4B000000) read as a float is 2^23 + count exactly and
+// one FADD gives the float.  For the 16+16 packing of the compact entries the two halves are picked with byte permutes (one
+// ALU instruction each); I2F runs at a quarter of the ALU rate and the old kernel issued two per entry (ncu r01).
 template <typename E> struct PkOf;
-template <> struct PkOf<uint32_t> { typedef uint32_t type; static constexpr int shift = 16; };
-template <> struct PkOf<unsigned long long> { typedef unsigned long long type; static constexpr int shift = 32; };
+template <> struct PkOf<uint32_t> {
+	typedef uint32_t type; static constexpr int shift = 16;
+	static __device__ __forceinline__ float hi_f(uint32_t pk) { return __uint_as_float(__byte_perm(pk, 0x4B000000u, 0x7432)) - 8388608.0f; }
+	static __device__ __forceinline__ float lo_f(uint32_t pk) { return __uint_as_float(__byte_perm(pk, 0x4B000000u, 0x7410)) - 8388608.0f; }
+	// "entries j and j+1 hold different values": ranks differ (bits 14..27)
+	static __device__ __forceinline__ bool rank_differs(uint32_t a, uint32_t b) { return ((a ^ b) & 0x0FFFC000u) != 0u; }
+};
+template <> struct PkOf<unsigned long long> {
+	typedef unsigned long long type; static constexpr int shift = 32;
+	static __device__ __forceinline__ float hi_f(unsigned long long pk) { return __uint_as_float((uint32_t)(pk >> 32) | 0x4B000000u) - 8388608.0f; }
+	static __device__ __forceinline__ float lo_f(unsigned long long pk) { return __uint_as_float((uint32_t)pk | 0x4B000000u) - 8388608.0f; }
+	static __device__ __forceinline__ bool rank_differs(unsigned long long a, unsigned long long b) { return ((a ^ b) & 0x0000FFFFFF000000ull) != 0ull; }
+};
 
 // group collectives: all 32 lanes of a warp always take part (an idle group of a sub-warp instantiation recomputes the
 // last work item and only skips the store), so the shuffles run with the full member mask and a segment width -- a partial
@@ -391,7 +404,7 @@ template <int G> __device__ __forceinline__ uint32_t grp_min(uint32_t v) {
 	}
 }
 
-// G = lanes per (node, candidate) work item, MULTI = the segment may span several chunks of G*SS_IPL entries.
+// G = lanes per (node, candidate) work item, MULTI = the segment may span several chunks of G*IPL entries.
 // level_finalize sorts the open nodes of a level into four size classes (kernels.cuh: size_class) and every class is
 // launched over its own compact item list with the instantiation that fits it:
 //   class 0 (<= 32 grid entries): G = 8, four work items per warp      class 1 (<= 64): G = 16, two per warp
@@ -401,7 +414,15 @@ template <int G> __device__ __forceinline__ uint32_t grp_min(uint32_t v) {
 // set-up, the scan, the exact block, the arg-max -- is what the small classes share between two or four items.
 // (An earlier attempt launched the three G variants over ALL items and let the non-matching warps exit: the extra item
 // loads and empty warps cost more than the packing saved; the compact per-class lists are what makes it pay.)
-// Measured alternatives that did NOT pay at BASELINE configs[1] (split search stayed at ~14.1 ms per CV in every case):
+//
+// The score of a split position.  ranger maximises  sum_c L_c^2/n_L + sum_c R_c^2/n_R  (TreeProbability.cpp:337), which for two
+// classes equals  n - 2 g  with  g = L0 L1/n_L + R0 R1/n_R  >= 0: the arg-max of the score is the arg-min of g.  Every position gets
+// an fp32 ESTIMATE of g in the single-division form  (L0 L1 n_R + R0 R1 n_L) * rcp(n_L n_R)  -- eight roundings and one approximate
+// reciprocal, relative error below 1e-6 of the score -- and only the positions whose estimate is within 4e-6 of the best estimate
+// of their chunk (or of the best exact score of earlier chunks) are evaluated exactly as ranger does, with its two IEEE fp64
+// divisions.  r02: one MUFU per position instead of two, no integer-to-float conversions (PkOf), 256-entry chunks without
+// range checks away from the segment ends, the exact block and the pruning bound behind ONE vote per chunk.
+// Measured alternatives that did NOT pay at BASELINE configs[1] (r01, split search stayed at ~14.1 ms per CV in every case):
 //   * one warp per node walking its mtry candidates (set-up and arg-max paid once, next candidate prefetched, filter bound
 //     carried across candidates): 25% fewer instructions per node, 15.5-17.6 ms -- the five-fold loss of independent warps
 //     costs more than the instructions saved;
@@ -410,7 +431,12 @@ template <int G> __device__ __forceinline__ uint32_t grp_min(uint32_t v) {
 //   * no software pipeline (40 registers, 12 CTAs per SM instead of 8): same time -- what the extra warps hide, the exposed
 //     load of every second chunk gives back.
 template <typename E, int G, bool MULTI>
-__global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A, const uint32_t* __restrict__ list, uint32_t nList, int buf) {
+__global__ void __launch_bounds__(128, MULTI ? SS_MINB_MULTI : SS_MINB) split_search_kernel(TrainArgs A, const uint32_t* __restrict__ list, uint32_t nList, int buf) {
+	constexpr int IPL = SsIpl<E, MULTI>::v;
+	typedef PkOf<E> PK;
+	typedef typename PK::type pk_t;
+	constexpr int PKS = PK::shift;
+	constexpr pk_t LOMASK = ((pk_t)1 << PKS) - 1;
 	// grid.y = candidate index, so no integer division is needed to find the work item
 	uint32_t li = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
 	const bool idle = li >= nList;
@@ -419,7 +445,7 @@ __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A,
 	const uint32_t item = __ldg(list + li);
 	const uint32_t c = blockIdx.y;
 	const Item it = A.items[buf][item];
-	constexpr uint32_t APE = (SS_IPL * sizeof(E) < 16 ? SS_IPL * sizeof(E) : 16) / sizeof(E);   // entries per aligned vector load
+	constexpr uint32_t APE = 16 / sizeof(E);                  // entries per aligned 16-byte vector
 	const uint32_t off = it.start % APE;                      // A.stride % 4 == 0, so list + start - off is 16-byte aligned
 	const uint32_t lo = off, hi = it.cnt + off;                // valid index range in the aligned grid
 	const int lane = lane_id();
@@ -430,29 +456,29 @@ __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A,
 	const uint32_t nPosOut = it.nPosOut;
 	const E* base = reinterpret_cast<const E*>(A.lists[A.listBuf]) + ((size_t)it.tree * A.m + f) * A.stride + (it.start - off);
 	const uint32_t n = it.npos + it.nneg;
-	uint32_t lp = 0, ln = 0;
+	const float fP = (float)it.npos, fN = (float)it.nneg, fn = (float)n;
+	pk_t absBase = 0;                                         // class counts left of the current chunk, packed
 	double best = -1.0;
 	float wbound = 0.0f;                                      // group-uniform: (best exact score of earlier chunks) * (1 - 4e-6)
-	uint32_t bpos = 0xFFFFFFFFu, blp = 0, bln = 0;
-	E e[SS_IPL], nx[SS_IPL];
-	if (MULTI) ss_load<E>(base, gl * SS_IPL, lo, hi, e);
-	else ss_load_single<E>(base, gl * SS_IPL, lo, hi, e);
+	uint32_t bpos = 0xFFFFFFFFu;
+	pk_t babs = 0;
+	E e[IPL], nx[IPL];
+	if (MULTI) ss_load<E, IPL>(base, gl * IPL, lo, hi, e);
+	else ss_load_single<E, IPL>(base, gl * IPL, lo, hi, e);
 	uint32_t b = 0;
 	do {
-		const uint32_t v0 = b + gl * SS_IPL;
-		if (MULTI) ss_load<E>(base, v0 + G * SS_IPL, lo, hi, nx);   // prefetch the next chunk
+		const uint32_t v0 = b + gl * IPL;
+		if (MULTI) ss_load<E, IPL>(base, v0 + G * IPL, lo, hi, nx);   // prefetch the next chunk
 		else {
 #pragma unroll
-			for (int j = 0; j < SS_IPL; j++) nx[j] = (E)0;
+			for (int j = 0; j < IPL; j++) nx[j] = (E)0;
 		}
 		// lane-local inclusive prefix of (positives, negatives) packed in one word: 16+16 bits for the compact entries
-		// (a 128-entry chunk holds at most 128*15 samples), 32+32 bits for the wide ones
-		typedef typename PkOf<E>::type pk_t;
-		constexpr int PKS = PkOf<E>::shift;
-		pk_t pk[SS_IPL];
+		// (a 256-entry chunk holds at most 256*15 samples, a whole tree at most 16384), 32+32 bits for the wide ones
+		pk_t pk[IPL];
 		pk_t run = 0;
 #pragma unroll
-		for (int j = 0; j < SS_IPL; j++) {
+		for (int j = 0; j < IPL; j++) {
 			const pk_t w = (pk_t)Ent<E>::count(e[j]);             // 0 for masked entries
 			run += Ent<E>::neg(e[j], nPosOut) ? w : (w << PKS);
 			pk[j] = run;
@@ -463,62 +489,70 @@ __global__ void __launch_bounds__(128, SS_MINB) split_search_kernel(TrainArgs A,
 			pk_t t = __shfl_up_sync(FULL, inc, o, G);
 			if (gl >= o) inc += t;
 		}
-		const pk_t excl = inc - run;
-		const uint32_t rfirst_next_lane = Ent<E>::rank(__shfl_down_sync(FULL, e[0], 1, G));
-		const uint32_t rfirst_next_chunk = MULTI ? Ent<E>::rank(__shfl_sync(FULL, nx[0], 0, G)) : 0u;
-		// phase 1: fp32 estimate of the Gini proxy at every candidate position of the chunk (no divisions, no branches).
-		// sum_c L_c^2/n_L + sum_c R_c^2/n_R  ==  n - 2 (L0 L1 / n_L + R0 R1 / n_R)   (two classes), which needs half the conversions.
-		float est[SS_IPL];
-		float emax = 0.0f;
-		const float fP = (float)it.npos, fN = (float)it.nneg, fn = (float)n;
+		const pk_t excl = absBase + inc - run;
+		// the entry that follows this lane's last one: first entry of the next lane, or of the next chunk for the last lane
+		E enext = __shfl_down_sync(FULL, e[0], 1, G);
+		if (MULTI) { const E c0 = __shfl_sync(FULL, nx[0], 0, G); if (gl == G - 1) enext = c0; }
+		else if (gl == G - 1) enext = (E)0;
+		// chunks that touch a segment end check the position range; the others run without (MULTI only: a single chunk always does)
+		const bool edge = !MULTI || (b == 0 && off != 0) || (b + G * IPL >= hi);
+		float g[IPL];
+		float gmin = __int_as_float(0x7F800000);
 #pragma unroll
-		for (int j = 0; j < SS_IPL; j++) {
-			const uint32_t v = v0 + j;
-			const uint32_t rk = Ent<E>::rank(e[j]);
-			const uint32_t rnext = (j + 1 < SS_IPL) ? Ent<E>::rank(e[(j + 1) % SS_IPL]) : (gl == G - 1 ? rfirst_next_chunk : rfirst_next_lane);
-			const pk_t tot = excl + pk[j];
-			const float fl = (float)(lp + (uint32_t)(tot >> PKS)), fq = (float)(ln + (uint32_t)(tot & (((pk_t)1 << PKS) - 1)));
+		for (int j = 0; j < IPL; j++) {
+			const pk_t a = excl + pk[j];
+			const float fl = PK::hi_f(a), fq = PK::lo_f(a);
 			const float nl = fl + fq, nr = fn - nl;
-			const float g2 = __fdividef(fl * fq, nl) + __fdividef((fP - fl) * (fN - fq), nr);
-			const bool ok = v >= lo && v + 1 < hi && rk != rnext;
-			est[j] = ok ? fmaf(-2.0f, g2, fn) : -1.0f;
-			emax = fmaxf(emax, est[j]);
+			const float num = fmaf(fl * fq, nr, ((fP - fl) * (fN - fq)) * nl);
+			float gj = num * __frcp_rn(nl * nr);
+			bool ok = PK::rank_differs(e[j], j + 1 < IPL ? e[(j + 1) % IPL] : enext);
+			if (edge) { const uint32_t v = v0 + j; ok = ok && v >= lo && v + 1 < hi; }
+			gj = ok ? gj : __int_as_float(0x7F800000);
+			g[j] = gj;
+			gmin = fminf(gmin, gj);
 		}
 		// Only positions whose estimate is within the estimate's error (< 1e-6 relative; margin 4e-6) of the best
 		// estimate of this chunk, or of the best exact score of earlier chunks, can be the arg-max: evaluate those
-		// exactly (two IEEE fp64 divisions, TreeProbability.cpp:337).  Estimates are >= 0, so their bit patterns order
-		// like unsigned integers and one redux gives the group maximum.
-		const float cmax = __uint_as_float(grp_max<G>(__float_as_uint(emax)));
-		const float thr = fmaxf(cmax * 0.999996f, wbound);
+		// exactly (two IEEE fp64 divisions, TreeProbability.cpp:337).  Estimates are >= 0 (or +inf), so their bit patterns
+		// order like unsigned integers and one redux gives the group minimum.
+		const float cmin = __uint_as_float(grp_min<G>(__float_as_uint(gmin)));
+		const float thrScore = fmaxf(fmaf(-2.0f, cmin, fn) * 0.999996f, wbound);
+		const float gthr = (fn - thrScore) * 0.5f;                // score >= thrScore  <=>  g <= gthr
+		bool cand = false;
 #pragma unroll
-		for (int j = 0; j < SS_IPL; j++) {
-			if (__ballot_sync(FULL, est[j] >= thr) & gm) {
-				if (est[j] >= thr) {
-					const pk_t tot = excl + pk[j];
-					const uint32_t lpi = lp + (uint32_t)(tot >> PKS), lni = ln + (uint32_t)(tot & (((pk_t)1 << PKS) - 1));
-					const uint32_t nl = lpi + lni, nr = n - nl;
-					const uint32_t rp = it.npos - lpi, rn = it.nneg - lni;
-					const unsigned long long sli = (unsigned long long)lpi * lpi + (unsigned long long)lni * lni;
-					const unsigned long long sri = (unsigned long long)rp * rp + (unsigned long long)rn * rn;
-					const double score = __dadd_rn(__ddiv_rn((double)sri, (double)nr), __ddiv_rn((double)sli, (double)nl));
-					if (score > best) { best = score; bpos = v0 + j - off; blp = lpi; bln = lni; }
+		for (int j = 0; j < IPL; j++) cand = cand || (g[j] <= gthr);
+		if (__ballot_sync(FULL, cand) & gm) {
+			if (cand) {
+#pragma unroll
+				for (int j = 0; j < IPL; j++) {
+					if (g[j] <= gthr) {
+						const pk_t a = excl + pk[j];
+						const uint32_t lpi = (uint32_t)(a >> PKS), lni = (uint32_t)(a & LOMASK);
+						const uint32_t nl = lpi + lni, nr = n - nl;
+						const uint32_t rp = it.npos - lpi, rn = it.nneg - lni;
+						const unsigned long long sli = (unsigned long long)lpi * lpi + (unsigned long long)lni * lni;
+						const unsigned long long sri = (unsigned long long)rp * rp + (unsigned long long)rn * rn;
+						const double score = __dadd_rn(__ddiv_rn((double)sri, (double)nr), __ddiv_rn((double)sli, (double)nl));
+						if (score > best) { best = score; bpos = v0 + j - off; babs = a; }
+					}
 				}
+			}
+			if (MULTI) {
+				// group-uniform bound for the following chunks: a later position must strictly beat the best exact score so far
+				const float bf = best > 0.0 ? __double2float_rd(best) : 0.0f;
+				wbound = __uint_as_float(grp_max<G>(__float_as_uint(bf))) * 0.999996f;
 			}
 		}
 		if (MULTI) {
-			// group-uniform bound for the following chunks: a later position must strictly beat the best exact score so far
-			const float bf = best > 0.0 ? __double2float_rd(best) : 0.0f;
-			const float wb = __uint_as_float(grp_max<G>(__float_as_uint(bf)));
-			wbound = wb * 0.999996f;
-			const pk_t tot = __shfl_sync(FULL, inc, G - 1, G);
-			lp += (uint32_t)(tot >> PKS); ln += (uint32_t)(tot & (((pk_t)1 << PKS) - 1));
+			absBase += __shfl_sync(FULL, inc, G - 1, G);
 #pragma unroll
-			for (int j = 0; j < SS_IPL; j++) e[j] = nx[j];
+			for (int j = 0; j < IPL; j++) e[j] = nx[j];
 		}
-		b += G * SS_IPL;
+		b += G * IPL;
 	} while (MULTI && b < hi);
 	// arg-max over the group's lanes: highest score, then lowest position (ascending value order, strict '>').
 	// Scores are positive doubles, so their two 32-bit halves order like unsigned integers: three redux steps.
+	uint32_t blp = (uint32_t)(babs >> PKS), bln = (uint32_t)(babs & LOMASK);
 	{
 		const unsigned long long sb = best > 0.0 ? (unsigned long long)__double_as_longlong(best) : 0ull;
 		const uint32_t mhi = grp_max<G>((uint32_t)(sb >> 32));

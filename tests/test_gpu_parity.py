@@ -473,7 +473,7 @@ def test_fold_scores_bit_exact_and_curves(ctx, oracle, name):
 def test_curves_auto_tie_mode(ctx, oracle):
     """tie_mode 2: exact when no run of tied scores holds both labels; otherwise bracketed by the positives-first / negatives-first
     tie orders -- the reference's value (oracle: the identical std::sort call) lies inside the bracket, the midpoint is returned
-    when the bracket is narrower than 2e-7, and the host std::sort decides when it is not"""
+    when the bracket is narrower than 1e-6, and the host std::sort decides when it is not"""
     rng = np.random.default_rng(11)
     n = 200_000
     y = (rng.random(n) < 0.01).astype(np.uint32)
@@ -500,7 +500,7 @@ def test_curves_auto_tie_mode(ctx, oracle):
     mixed, host, spread = ctx.curves_info()
     assert mixed > 0
     if host == 0:
-        assert 0 <= spread[0] <= 2e-7 and 0 <= spread[1] <= 2e-7
+        assert 0 <= spread[0] <= 1e-6 and 0 <= spread[1] <= 1e-6
         assert abs(hi[0] - want[0]) <= spread[0] / 2 + 1e-8 and abs(hi[1] - want[1]) <= spread[1] / 2 + 1e-12   # AUROC terms are float: 1e-8 of slack
     else:
         assert abs(hi[0] - want[0]) < 1e-12 and abs(hi[1] - want[1]) < 1e-12
@@ -510,7 +510,7 @@ def test_curves_auto_tie_mode(ctx, oracle):
     want = oracle.o_curves(y, s3)
     got = ctx.curves(y, s3, tie_mode=2)
     mixed, host, spread = ctx.curves_info()
-    assert mixed > 0 and host == 1 and (spread[0] > 2e-7 or spread[1] > 2e-7)
+    assert mixed > 0 and host == 1 and (spread[0] > 1e-6 or spread[1] > 1e-6)
     assert abs(got[0] - want[0]) < 1e-12 and abs(got[1] - want[1]) < 1e-12
     # the bracket really brackets: tie_mode 1 (ties in index order) and the reference's order both lie inside [lo, hi]
     t1 = ctx.curves(y, s3, tie_mode=1)

@@ -195,3 +195,28 @@ def test_backward_resolution_of_random_shuffle_equals_the_sequential_walk():
             out[k] = a[s]
         assert np.array_equal(out, seq), n
         assert hops <= 3 * n + 3                                          # ~2 hops per slot
+
+
+def test_parallel_sort_replica_equals_std_sort(oracle):
+    """psm_host_sort_permutation (parallel replica of the reference's std::sort call, csrc/api.cu) == the permutation the oracle's
+    identical std::sort call produces (oracle psmo_curves exports it), for continuous scores, heavy ties, all-equal and sorted
+    inputs, on 1 and on several threads"""
+    import ctypes as C
+    import parsmurf_b200 as psm
+    L = psm.lib()
+    L.psm_host_sort_permutation.argtypes = [C.POINTER(C.c_double), C.c_uint64, C.POINTER(C.c_uint32), C.c_int]
+    rng = np.random.default_rng(5)
+    cases = []
+    for n in (1, 2, 15, 16, 17, 33, 1000, 70_001, 400_000):
+        cases.append(rng.random(n))
+        cases.append(np.round(rng.random(n) * 20) / 20)               # 21 score levels
+        cases.append(np.where(rng.random(n) < 0.9, 0.0, rng.random(n)))  # one huge run of ties
+    cases += [np.zeros(100_000), np.arange(100_000, dtype=float), -np.arange(100_000, dtype=float)]
+    for s in cases:
+        s = np.ascontiguousarray(s, np.float64)
+        labels = np.zeros(len(s), np.uint32); labels[:1] = 1
+        _, _, want = oracle.o_curves(labels, s, want_perm=True)
+        for threads in (1, 6):
+            perm = np.zeros(len(s), np.uint32)
+            assert L.psm_host_sort_permutation(s.ctypes.data_as(C.POINTER(C.c_double)), len(s), perm.ctypes.data_as(C.POINTER(C.c_uint32)), threads) == 0
+            assert np.array_equal(perm.astype(np.uint64), want), (len(s), threads)
