@@ -76,7 +76,7 @@ struct psm_ctx {
 	uint32_t T = 0, mtry = 0;
 	TrainArgs A;
 	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dNodes8, dSplitFeat, dFlagBits, dItems0, dItems1, dCls, dCand, dRes, dDec, dPtask, dCounters, dStats, dSeeds,
-	    dInjBoot, dInjBootOff, dInjCand;
+	    dInjBoot, dInjBootOff, dInjCand, dSortFlags;
 	uint32_t* hCounters = nullptr;   // pinned
 	cudaEvent_t evLevel = nullptr;
 	void* hStage = nullptr;          // pinned D2H staging
@@ -200,7 +200,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
 	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dSplitFeat, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1, &ctx->dCls,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dPtask, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
-	                  &ctx->dInjCand, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cIdx, &ctx->cFoldScores, &ctx->cScratch, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
+	                  &ctx->dInjCand, &ctx->dSortFlags, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cIdx, &ctx->cFoldScores, &ctx->cScratch, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
 	                  &ctx->cScores, &ctx->cKeysA, &ctx->cKeysB, &ctx->cValsA, &ctx->cValsB, &ctx->cHist};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& p : ctx->profPending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -638,7 +638,8 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 	{
 		ProfScope ps(ctx, K_SORT, 1);
 		if (sortInSmem) {
-			if (launch_feature_sort_smem(A.Dall, A.parts, nB, m, ctx->maxNtr, ctx->dS.as<entry_t>(), s))
+			ENSURE(ctx->dSortFlags, (size_t)nB * m * 4);
+			if (launch_feature_sort_smem(A.Dall, A.parts, nB, m, ctx->maxNtr, ctx->dS.as<entry_t>(), ctx->dSortFlags.as<uint32_t>(), s))
 				return fail(ctx, PSM_E_CUDA, "batch_train: cannot configure the shared-memory sort");
 		} else {
 			launch_feature_sort(A.Dall, A.parts, nB, m, ctx->dKeysA.as<unsigned long long>(), ctx->dKeysB.as<unsigned long long>(),

@@ -65,7 +65,7 @@ void launch_assemble(const double* x, uint32_t m, const uint32_t* posIdx, uint32
 void launch_feature_sort(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, unsigned long long* keysA,
                          unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, entry_t* Sall, cudaStream_t s);
 int launch_feature_sort_smem(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, uint32_t maxNtr, entry_t* Sall,
-                             cudaStream_t s);
+                             uint32_t* slowFlags /*[nPartsBatch * m] scratch, or NULL: bitonic network only*/, cudaStream_t s);
 // train.cu
 size_t tree_smem_bytes(uint32_t m, uint32_t mtry);
 void launch_bootstrap(const TrainArgs& A, const uint32_t* forestSeeds, cudaStream_t s);

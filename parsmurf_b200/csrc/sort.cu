@@ -202,12 +202,14 @@ __device__ __host__ inline uint32_t split_slots(uint32_t N) {
 
 template <int CEMAX, int MINB>
 __global__ void __launch_bounds__(BT, MINB) feature_sort_split_kernel(const double* __restrict__ Dall, const PartDesc* __restrict__ parts,
-                                                                       uint32_t m, uint32_t slotsMax, entry_t* __restrict__ Sall) {
+                                                                       uint32_t m, uint32_t slotsMax, entry_t* __restrict__ Sall,
+                                                                       const uint32_t* __restrict__ onlyFlagged) {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	unsigned long long* keys = reinterpret_cast<unsigned long long*>(smraw);                 // [slotsMax]
 	unsigned short* ids = reinterpret_cast<unsigned short*>(smraw + (size_t)slotsMax * 8);    // [slotsMax]
 	__shared__ uint32_t wsum[BT / 32];
 	const uint32_t seg = blockIdx.x;
+	if (onlyFlagged && onlyFlagged[seg] == 0u) return;     // second pass after the radix kernel: only the segments it gave up on
 	const uint32_t pl = seg / m, f = seg % m;
 	const PartDesc pd = parts[pl];
 	const uint32_t N = pd.Ntr;
@@ -305,12 +307,135 @@ __global__ void __launch_bounds__(BT, MINB) feature_sort_split_kernel(const doub
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Radix variant (r02; the default for Ntr <= 16384).  The bitonic network above costs Ntr*log^2(Ntr) compare-exchanges:
+// 2.0e9 warp instructions per BASELINE configs[1] CV, 76% issue-active (profiles/r01_summary.md).  Here the segment is sorted by
+// the HIGH word of the order-preserving u64 image of the values (sign, exponent, 20 mantissa bits) with a stable LSD radix sort
+// in shared memory -- 4 passes of 8 bits, every warp owning a contiguous slice of the segment and private digit counters, ranks
+// inside a warp from __match_any_sync -- and the few neighbours that agree in the high word are then put in order by the LOW
+// word with an odd-even transposition that only ever exchanges elements of one such run (two quiet phases end it).  Runs that
+// are still moving after kFixIters phases (thousands of values that differ only below 2^-20 relative: adversarial) flag the
+// segment, and the bitonic kernel redoes exactly the flagged segments.
+// Shared memory: 12 bytes per element (u32 key + u16 row id, ping-pong) + 32 KB of counters.
+// ------------------------------------------------------------------------------------------------
+constexpr int RXT = 1024, RXW = RXT / 32;
+constexpr int kFixIters = 48;
+
+__global__ void __launch_bounds__(RXT, 1) feature_sort_radix_kernel(const double* __restrict__ Dall, const PartDesc* __restrict__ parts, uint32_t m,
+                                                                     uint32_t maxNp, entry_t* __restrict__ Sall, uint32_t* __restrict__ slowFlags) {
+	extern __shared__ __align__(16) unsigned char smraw[];
+	uint32_t* kA = reinterpret_cast<uint32_t*>(smraw);                 // [maxNp]
+	uint32_t* kB = kA + maxNp;                                         // [maxNp]
+	unsigned short* idA = reinterpret_cast<unsigned short*>(kB + maxNp);   // [maxNp]
+	unsigned short* idB = idA + maxNp;                                 // [maxNp]
+	uint32_t* wc = reinterpret_cast<uint32_t*>(idB + maxNp);           // [RXW][256] per-warp digit counters -> offsets inside the digit
+	__shared__ uint32_t base[256];
+	__shared__ uint32_t wsum[RXW];
+	__shared__ uint32_t carry_s;
+	const uint32_t seg = blockIdx.x;
+	const uint32_t pl = seg / m, f = seg % m;
+	const PartDesc pd = parts[pl];
+	const uint32_t N = pd.Ntr;
+	if (N == 0) return;
+	const double* src = Dall + pd.dOffset + (size_t)f * N;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const unsigned lt = lanemask_lt();
+	for (uint32_t i = tid; i < N; i += RXT) { kA[i] = (uint32_t)(f64_key(src[i]) >> 32); idA[i] = (unsigned short)i; }
+	// every warp owns `chunk` consecutive elements (a multiple of 32, so that all its rounds but the last are full)
+	const uint32_t chunk = (((N + RXW - 1) / RXW) + 31u) & ~31u;
+	const uint32_t c0 = min(N, (uint32_t)w * chunk), c1 = min(N, c0 + chunk);
+	uint32_t* myc = wc + w * 256;
+	for (int pass = 0; pass < 4; pass++) {
+		const int shift = pass * 8;
+		for (int i = tid; i < RXW * 256; i += RXT) wc[i] = 0;
+		__syncthreads();
+		for (uint32_t i = c0 + lane; i < c1; i += 32) atomicAdd(&myc[(kA[i] >> shift) & 255u], 1u);
+		__syncthreads();
+		if (tid < 256) {
+			// digit tid: counts of the 32 warps -> exclusive offsets inside the digit, then the digit's base
+			uint32_t run = 0;
+#pragma unroll 8
+			for (int ww = 0; ww < RXW; ww++) { const uint32_t c = wc[ww * 256 + tid]; wc[ww * 256 + tid] = run; run += c; }
+			uint32_t inc = run;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+			if (lane == 31) wsum[w] = inc;
+			base[tid] = inc - run;                       // exclusive inside the warp of 32 digits
+		}
+		__syncthreads();
+		if (tid < 256) { uint32_t off = 0; for (int ww = 0; ww < w; ww++) off += wsum[ww]; base[tid] += off; }
+		__syncthreads();
+		for (uint32_t i0 = c0; i0 < c1; i0 += 32) {
+			const uint32_t i = i0 + lane;
+			const bool valid = i < c1;
+			const uint32_t key = valid ? kA[i] : 0u;
+			const unsigned short id = valid ? idA[i] : (unsigned short)0;
+			const uint32_t d = valid ? ((key >> shift) & 255u) : (256u + (uint32_t)lane);   // invalid lanes match nobody
+			const unsigned peers = __match_any_sync(0xffffffffu, d);
+			const uint32_t rk = __popc(peers & lt);
+			uint32_t pos = 0;
+			if (valid) pos = base[d] + myc[d] + rk;
+			__syncwarp();
+			if (valid && rk == 0) myc[d] += __popc(peers);
+			__syncwarp();
+			if (valid) { kB[pos] = key; idB[pos] = id; }
+		}
+		__syncthreads();
+		{ uint32_t* tk = kA; kA = kB; kB = tk; unsigned short* ti = idA; idA = idB; idB = ti; }
+	}
+	// sorted by the high word (back in the first pair of arrays); low words of the sorted order into the free key array
+	for (uint32_t i = tid; i < N; i += RXT) kB[i] = (uint32_t)f64_key(src[idA[i]]);
+	__syncthreads();
+	// odd-even transposition restricted to runs of equal high words
+	bool settled = false;
+	{
+		int quiet = 0;
+		for (int it = 0; it < kFixIters; it++) {
+			const uint32_t phase = (uint32_t)it & 1u;
+			int moved = 0;
+			for (uint32_t i = 2u * tid + phase; i + 1 < N; i += 2u * RXT) {
+				if (kA[i] == kA[i + 1] && kB[i] > kB[i + 1]) {
+					const uint32_t t = kB[i]; kB[i] = kB[i + 1]; kB[i + 1] = t;
+					const unsigned short u = idA[i]; idA[i] = idA[i + 1]; idA[i + 1] = u;
+					moved = 1;
+				}
+			}
+			if (__syncthreads_or(moved)) quiet = 0;
+			else if (++quiet == 2) { settled = true; break; }
+		}
+	}
+	if (!settled) {                                   // uniform: every thread saw the same votes
+		if (tid == 0) slowFlags[seg] = 1u;
+		return;
+	}
+	// dense ranks (equal doubles share a rank) and the (rank, row) entries
+	entry_t* S = Sall + pd.sOffset + (size_t)f * N;
+	if (tid == 0) carry_s = 0;
+	__syncthreads();
+	for (uint32_t t0 = 0; t0 < N; t0 += RXT) {
+		const uint32_t i = t0 + tid;
+		const uint32_t flag = (i > 0 && i < N) ? ((kA[i] != kA[i - 1] || kB[i] != kB[i - 1]) ? 1u : 0u) : 0u;
+		uint32_t inc = flag;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+		if (lane == 31) wsum[w] = inc;
+		__syncthreads();
+		uint32_t off = carry_s;
+		for (int ww = 0; ww < w; ww++) off += wsum[ww];
+		const uint32_t rank = off + inc;
+		if (i < N) S[i] = e_make(idA[i], rank, 0, 0);
+		__syncthreads();
+		if (tid == RXT - 1) carry_s = rank;
+		__syncthreads();
+	}
+}
+
 template <int CEMAX, int MINB>
 static int launch_sort_split(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, uint32_t slotsMax, entry_t* Sall,
-                             cudaStream_t s) {
+                             const uint32_t* onlyFlagged, cudaStream_t s) {
 	const size_t smem = (size_t)slotsMax * 10;
 	if (allow_max_dyn_smem(feature_sort_split_kernel<CEMAX, MINB>) != cudaSuccess) return -1;
-	feature_sort_split_kernel<CEMAX, MINB><<<nPartsBatch * m, BT, smem, s>>>(Dall, parts, m, slotsMax, Sall);
+	feature_sort_split_kernel<CEMAX, MINB><<<nPartsBatch * m, BT, smem, s>>>(Dall, parts, m, slotsMax, Sall, onlyFlagged);
 	return 0;
 }
 
@@ -323,15 +448,24 @@ static int launch_sort_smem_N(const double* Dall, const PartDesc* parts, uint32_
 }
 
 int launch_feature_sort_smem(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, uint32_t maxNtr, entry_t* Sall,
-                             cudaStream_t s) {
+                             uint32_t* slowFlags, cudaStream_t s) {
 	if (maxNtr > 16384) return 1;   // caller falls back to the global-memory radix sort
-	if (!getenv("PSM_SORT_POW2")) {
+	const uint32_t* onlyFlagged = nullptr;
+	if (slowFlags && !getenv("PSM_SORT_BITONIC")) {
+		const uint32_t maxNp = (maxNtr + 3u) & ~3u;
+		const size_t smemR = (size_t)maxNp * 12 + (size_t)RXW * 256 * 4;
+		if (allow_max_dyn_smem(feature_sort_radix_kernel) != cudaSuccess) return -1;
+		cudaMemsetAsync(slowFlags, 0, (size_t)nPartsBatch * m * 4, s);
+		feature_sort_radix_kernel<<<nPartsBatch * m, RXT, smemR, s>>>(Dall, parts, m, maxNp, Sall, slowFlags);
+		onlyFlagged = slowFlags;       // the bitonic kernel below then only redoes what the radix kernel flagged
+	}
+	if (!getenv("PSM_SORT_POW2") || onlyFlagged) {
 		const uint32_t slotsMax = split_slots(maxNtr);        // monotone in N, so every segment of the batch fits
 		const int ce = (int)((slotsMax / 2 + BT - 1) / BT);
 		const bool two = (size_t)slotsMax * 10 <= 110 * 1024 && !getenv("PSM_SORT_ONE_CTA");   // two CTAs per SM when shared memory allows
 #define PSM_SORT_CASE(C)                                                                                        \
-	case C: return two ? launch_sort_split<C, 2>(Dall, parts, nPartsBatch, m, slotsMax, Sall, s)                \
-	                   : launch_sort_split<C, 1>(Dall, parts, nPartsBatch, m, slotsMax, Sall, s);
+	case C: return two ? launch_sort_split<C, 2>(Dall, parts, nPartsBatch, m, slotsMax, Sall, onlyFlagged, s)   \
+	                   : launch_sort_split<C, 1>(Dall, parts, nPartsBatch, m, slotsMax, Sall, onlyFlagged, s);
 		switch (ce < 1 ? 1 : ce) {
 			PSM_SORT_CASE(1) PSM_SORT_CASE(2) PSM_SORT_CASE(3) PSM_SORT_CASE(4) PSM_SORT_CASE(5) PSM_SORT_CASE(6) PSM_SORT_CASE(7) PSM_SORT_CASE(8)
 		}

@@ -20,6 +20,7 @@
 // Node ids are assigned breadth-first in parent-id order exactly like Tree.cpp:294-302, which is what makes
 // the i-th mtry draw of the device stream belong to node i.
 #include <cstdlib>
+#include <type_traits>
 #include "kernels.cuh"
 #include "rng.cuh"
 
@@ -320,12 +321,15 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 #define SS_MINB 8
 #endif
 #ifndef SS_MINB_MULTI
-#define SS_MINB_MULTI 6      // the chunk loop keeps 78 registers live (two chunks of entries in flight)
+#define SS_MINB_MULTI 7      // the chunk loop keeps ~75 registers live (two chunks of entries in flight); 7 CTAs x 128 threads x 73 registers fill the file
 #endif
 
 // entries per lane and chunk: the compact 4-byte entries take 8 (two 16-byte loads, 256-entry chunks) in the chunk loop of the
 // long segments and 4 in the single-chunk classes; the 8-byte entries always 4
-template <typename E, bool MULTI> struct SsIpl { static constexpr int v = (MULTI && sizeof(E) == 4) ? 8 : 4; };
+#ifndef PSM_SS_IPL_MULTI
+#define PSM_SS_IPL_MULTI 8
+#endif
+template <typename E, bool MULTI> struct SsIpl { static constexpr int v = (MULTI && sizeof(E) == 4) ? PSM_SS_IPL_MULTI : 4; };
 
 template <int IPL> __device__ __forceinline__ void ss_vec(const unsigned long long* p, unsigned long long (&e)[IPL]) {
 #pragma unroll
@@ -343,12 +347,22 @@ template <int IPL> __device__ __forceinline__ void ss_vec(const uint32_t* p, uin
 }
 template <typename E, int IPL>
 __device__ __forceinline__ void ss_load(const E* __restrict__ base, uint32_t v, uint32_t lo, uint32_t hi, E (&e)[IPL]) {
-	// entries v..v+IPL-1 of the aligned grid; valid iff lo <= index < hi
+	// entries v..v+IPL-1 of the aligned grid; valid iff lo <= index < hi.  A vector that straddles a segment end is loaded whole
+	// (16-byte pieces that hold at least one valid entry: the neighbouring entries belong to the same list or its padding, see
+	// ss_load_single) and masked afterwards -- no per-entry loads.
 	if (v >= lo && v + IPL <= hi) {
 		ss_vec<IPL>(base + v, e);
 	} else {
+		constexpr int APE = 16 / (int)sizeof(E);
 #pragma unroll
-		for (int j = 0; j < IPL; j++) e[j] = (v + j >= lo && v + j < hi) ? __ldg(base + v + j) : (E)0;
+		for (int q = 0; q < IPL / APE; q++) {
+			E t[APE];
+#pragma unroll
+			for (int j = 0; j < APE; j++) t[j] = (E)0;
+			if (v + q * APE < hi && v + (q + 1) * APE > lo) ss_vec<APE>(base + v + q * APE, t);
+#pragma unroll
+			for (int j = 0; j < APE; j++) { const uint32_t i = v + q * APE + j; e[q * APE + j] = (i >= lo && i < hi) ? t[j] : (E)0; }
+		}
 	}
 }
 
@@ -383,6 +397,13 @@ template <> struct PkOf<unsigned long long> {
 	static __device__ __forceinline__ float lo_f(unsigned long long pk) { return __uint_as_float((uint32_t)pk | 0x4B000000u) - 8388608.0f; }
 	static __device__ __forceinline__ bool rank_differs(unsigned long long a, unsigned long long b) { return ((a ^ b) & 0x0000FFFFFF000000ull) != 0ull; }
 };
+
+// MUFU.RCP, 1 ulp (__frcp_rn is the correctly rounded one: a Newton step and a guarded slow path around the same MUFU)
+__device__ __forceinline__ float rcp_approx(float x) {
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
 
 // group collectives: all 32 lanes of a warp always take part (an idle group of a sub-warp instantiation recomputes the
 // last work item and only skips the store), so the shuffles run with the full member mask and a segment width -- a partial
@@ -498,19 +519,23 @@ __global__ void __launch_bounds__(128, MULTI ? SS_MINB_MULTI : SS_MINB) split_se
 		const bool edge = !MULTI || (b == 0 && off != 0) || (b + G * IPL >= hi);
 		float g[IPL];
 		float gmin = __int_as_float(0x7F800000);
+		auto estimate = [&](auto edgeTag) {
+			constexpr bool EDGE = decltype(edgeTag)::value;
 #pragma unroll
-		for (int j = 0; j < IPL; j++) {
-			const pk_t a = excl + pk[j];
-			const float fl = PK::hi_f(a), fq = PK::lo_f(a);
-			const float nl = fl + fq, nr = fn - nl;
-			const float num = fmaf(fl * fq, nr, ((fP - fl) * (fN - fq)) * nl);
-			float gj = num * __frcp_rn(nl * nr);
-			bool ok = PK::rank_differs(e[j], j + 1 < IPL ? e[(j + 1) % IPL] : enext);
-			if (edge) { const uint32_t v = v0 + j; ok = ok && v >= lo && v + 1 < hi; }
-			gj = ok ? gj : __int_as_float(0x7F800000);
-			g[j] = gj;
-			gmin = fminf(gmin, gj);
-		}
+			for (int j = 0; j < IPL; j++) {
+				const pk_t a = excl + pk[j];
+				const float fl = PK::hi_f(a), fq = PK::lo_f(a);
+				const float nl = fl + fq, nr = fn - nl;
+				const float num = fmaf(fl * fq, nr, ((fP - fl) * (fN - fq)) * nl);
+				float gj = num * rcp_approx(nl * nr);
+				bool ok = PK::rank_differs(e[j], j + 1 < IPL ? e[(j + 1) % IPL] : enext);
+				if (EDGE) { const uint32_t v = v0 + j; ok = ok && v >= lo && v + 1 < hi; }
+				gj = ok ? gj : __int_as_float(0x7F800000);
+				g[j] = gj;
+				gmin = fminf(gmin, gj);
+			}
+		};
+		if (edge) estimate(std::true_type()); else estimate(std::false_type());
 		// Only positions whose estimate is within the estimate's error (< 1e-6 relative; margin 4e-6) of the best
 		// estimate of this chunk, or of the best exact score of earlier chunks, can be the arg-max: evaluate those
 		// exactly (two IEEE fp64 divisions, TreeProbability.cpp:337).  Estimates are >= 0 (or +inf), so their bit patterns
