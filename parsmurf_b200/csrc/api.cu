@@ -639,7 +639,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		ProfScope ps(ctx, K_SORT, 1);
 		if (sortInSmem) {
 			ENSURE(ctx->dSortFlags, (size_t)nB * m * 4);
-			if (launch_feature_sort_smem(A.Dall, A.parts, nB, m, ctx->maxNtr, ctx->dS.as<entry_t>(), ctx->dSortFlags.as<uint32_t>(), s))
+			if (launch_feature_sort_smem(A.Dall, A.parts, nB, m, ctx->maxNtr, ctx->dS.as<entry_t>(), ctx->dSortFlags.as<uint32_t>(), nullptr, s))
 				return fail(ctx, PSM_E_CUDA, "batch_train: cannot configure the shared-memory sort");
 		} else {
 			launch_feature_sort(A.Dall, A.parts, nB, m, ctx->dKeysA.as<unsigned long long>(), ctx->dKeysB.as<unsigned long long>(),

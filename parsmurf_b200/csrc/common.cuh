@@ -76,7 +76,7 @@ struct Item {
 	uint32_t npos;    // samples (with multiplicity) of class 0
 	uint32_t nneg;    // samples of class 1
 	uint32_t nPosOut; // rows below this id are positives (label of compact list entries)
-	uint32_t pad;
+	uint32_t pl;      // partition index inside the batch (tree / T), carried from the root item
 };
 
 struct SearchRes {
@@ -84,7 +84,7 @@ struct SearchRes {
 	uint32_t pos;     // best split after list position `pos` (relative to segment start)
 	uint32_t lpos;    // left class-0 samples
 	uint32_t lneg;    // left class-1 samples
-	uint32_t pad;
+	uint32_t rows;    // small mode: row at `pos` (low 16 bits) and the row that follows it in the candidate's order (high 16 bits)
 };
 
 struct SplitDec {
@@ -100,7 +100,10 @@ struct __align__(16) PartTask {
 	uint32_t cnt;     // 0 = nothing to move (no split, or both children terminal); top bits: PT_DEAD_LEFT / PT_DEAD_RIGHT
 	uint32_t nleft;
 };
-constexpr uint32_t PT_DEAD_LEFT = 1u << 31, PT_DEAD_RIGHT = 1u << 30, PT_CNT_MASK = (1u << 30) - 1u;   // rows per matrix < 2^24
+// rows per matrix < 2^24.  PT_SMALL: the node is in small mode (one row list, in the slot of feature 0); PT_SMALL_LEFT / RIGHT: that
+// child will be (its entries are only needed in the list of feature 0).
+constexpr uint32_t PT_DEAD_LEFT = 1u << 31, PT_DEAD_RIGHT = 1u << 30, PT_SMALL = 1u << 29, PT_SMALL_LEFT = 1u << 28, PT_SMALL_RIGHT = 1u << 27,
+                   PT_CNT_MASK = (1u << 24) - 1u;
 
 // per-tree growth state
 struct TreeState {

@@ -44,6 +44,11 @@ struct TrainArgs {
 	SplitDec* dec;        // [itemCap]
 	PartTask* ptask;      // [itemCap]
 	uint32_t* splitFeat;  // [itemCap] winning feature of each split node
+	uint32_t* splitAux;   // [itemCap] small mode: the row whose value is the last one that goes left
+	// Small mode (compact entries only; nullptr = off): dense rank of every row in every feature, [partition][m][Ntr] u16 at the
+	// element offsets of Sall.  A node whose segment fits one warp chunk (size classes 0-2) keeps ONE row list -- in the slot of
+	// feature 0 -- and its candidates' orders are rebuilt on demand: ranks gathered from this table, sorted inside the lane group.
+	const unsigned short* rankTab;
 	uint32_t* counters;   // [CNT_COUNT]
 	unsigned long long* stats;   // [STAT_COUNT]
 	const uint32_t* injCand;     // [tree][injCandNodes][mtry] or nullptr
@@ -65,7 +70,8 @@ void launch_assemble(const double* x, uint32_t m, const uint32_t* posIdx, uint32
 void launch_feature_sort(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, unsigned long long* keysA,
                          unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, entry_t* Sall, cudaStream_t s);
 int launch_feature_sort_smem(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, uint32_t maxNtr, entry_t* Sall,
-                             uint32_t* slowFlags /*[nPartsBatch * m] scratch, or NULL: bitonic network only*/, cudaStream_t s);
+                             uint32_t* slowFlags /*[nPartsBatch * m] scratch, or NULL: bitonic network only*/,
+                             unsigned short* rankTab /*[element offsets of Sall] dense rank by row, or NULL*/, cudaStream_t s);
 // train.cu
 size_t tree_smem_bytes(uint32_t m, uint32_t mtry);
 void launch_bootstrap(const TrainArgs& A, const uint32_t* forestSeeds, cudaStream_t s);

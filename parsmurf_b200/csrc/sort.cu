@@ -121,7 +121,7 @@ constexpr int BT = 1024;
 // fully unrolled so their shared-memory loads are issued back to back.
 template <uint32_t NPAD>
 __global__ void __launch_bounds__(BT, 1) feature_sort_smem_kernel(const double* __restrict__ Dall, const PartDesc* __restrict__ parts,
-                                                                   uint32_t m, entry_t* __restrict__ Sall) {
+                                                                   uint32_t m, entry_t* __restrict__ Sall, unsigned short* __restrict__ rankTab) {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	unsigned long long* keys = reinterpret_cast<unsigned long long*>(smraw);            // [NPAD]
 	unsigned short* ids = reinterpret_cast<unsigned short*>(smraw + (size_t)NPAD * 8);   // [NPAD]
@@ -177,7 +177,10 @@ __global__ void __launch_bounds__(BT, 1) feature_sort_smem_kernel(const double* 
 		uint32_t off = carry_s;
 		for (int ww = 0; ww < w; ww++) off += wsum[ww];
 		const uint32_t rank = off + inc;
-		if (i < N) S[i] = e_make(ids[i], rank, 0, 0);
+		if (i < N) {
+			S[i] = e_make(ids[i], rank, 0, 0);
+			if (rankTab) rankTab[pd.sOffset + (size_t)f * N + ids[i]] = (unsigned short)rank;
+		}
 		__syncthreads();
 		if (tid == BT - 1) carry_s = rank;
 		__syncthreads();
@@ -203,7 +206,7 @@ __device__ __host__ inline uint32_t split_slots(uint32_t N) {
 template <int CEMAX, int MINB>
 __global__ void __launch_bounds__(BT, MINB) feature_sort_split_kernel(const double* __restrict__ Dall, const PartDesc* __restrict__ parts,
                                                                        uint32_t m, uint32_t slotsMax, entry_t* __restrict__ Sall,
-                                                                       const uint32_t* __restrict__ onlyFlagged) {
+                                                                       const uint32_t* __restrict__ onlyFlagged, unsigned short* __restrict__ rankTab) {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	unsigned long long* keys = reinterpret_cast<unsigned long long*>(smraw);                 // [slotsMax]
 	unsigned short* ids = reinterpret_cast<unsigned short*>(smraw + (size_t)slotsMax * 8);    // [slotsMax]
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(BT, MINB) feature_sort_split_kernel(const doub
 			rank += (o > 0 && key != prev) ? 1u : 0u;
 			prev = key;
 			S[o] = e_make(id, rank, 0, 0);
+			if (rankTab) rankTab[pd.sOffset + (size_t)f * N + id] = (unsigned short)rank;
 		}
 	}
 }
@@ -322,7 +326,8 @@ constexpr int RXT = 1024, RXW = RXT / 32;
 constexpr int kFixIters = 48;
 
 __global__ void __launch_bounds__(RXT, 1) feature_sort_radix_kernel(const double* __restrict__ Dall, const PartDesc* __restrict__ parts, uint32_t m,
-                                                                     uint32_t maxNp, entry_t* __restrict__ Sall, uint32_t* __restrict__ slowFlags) {
+                                                                     uint32_t maxNp, entry_t* __restrict__ Sall, uint32_t* __restrict__ slowFlags,
+                                                                     unsigned short* __restrict__ rankTab) {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	uint32_t* kA = reinterpret_cast<uint32_t*>(smraw);                 // [maxNp]
 	uint32_t* kB = kA + maxNp;                                         // [maxNp]
@@ -423,7 +428,10 @@ __global__ void __launch_bounds__(RXT, 1) feature_sort_radix_kernel(const double
 		uint32_t off = carry_s;
 		for (int ww = 0; ww < w; ww++) off += wsum[ww];
 		const uint32_t rank = off + inc;
-		if (i < N) S[i] = e_make(idA[i], rank, 0, 0);
+		if (i < N) {
+			S[i] = e_make(idA[i], rank, 0, 0);
+			if (rankTab) rankTab[pd.sOffset + (size_t)f * N + idA[i]] = (unsigned short)rank;
+		}
 		__syncthreads();
 		if (tid == RXT - 1) carry_s = rank;
 		__syncthreads();
@@ -432,23 +440,24 @@ __global__ void __launch_bounds__(RXT, 1) feature_sort_radix_kernel(const double
 
 template <int CEMAX, int MINB>
 static int launch_sort_split(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, uint32_t slotsMax, entry_t* Sall,
-                             const uint32_t* onlyFlagged, cudaStream_t s) {
+                             const uint32_t* onlyFlagged, unsigned short* rankTab, cudaStream_t s) {
 	const size_t smem = (size_t)slotsMax * 10;
 	if (allow_max_dyn_smem(feature_sort_split_kernel<CEMAX, MINB>) != cudaSuccess) return -1;
-	feature_sort_split_kernel<CEMAX, MINB><<<nPartsBatch * m, BT, smem, s>>>(Dall, parts, m, slotsMax, Sall, onlyFlagged);
+	feature_sort_split_kernel<CEMAX, MINB><<<nPartsBatch * m, BT, smem, s>>>(Dall, parts, m, slotsMax, Sall, onlyFlagged, rankTab);
 	return 0;
 }
 
 template <uint32_t NPAD>
-static int launch_sort_smem_N(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, entry_t* Sall, cudaStream_t s) {
+static int launch_sort_smem_N(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, entry_t* Sall, unsigned short* rankTab,
+                             cudaStream_t s) {
 	const size_t smem = (size_t)NPAD * 10;
 	if (allow_max_dyn_smem(feature_sort_smem_kernel<NPAD>) != cudaSuccess) return -1;
-	feature_sort_smem_kernel<NPAD><<<nPartsBatch * m, BT, smem, s>>>(Dall, parts, m, Sall);
+	feature_sort_smem_kernel<NPAD><<<nPartsBatch * m, BT, smem, s>>>(Dall, parts, m, Sall, rankTab);
 	return 0;
 }
 
 int launch_feature_sort_smem(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, uint32_t maxNtr, entry_t* Sall,
-                             uint32_t* slowFlags, cudaStream_t s) {
+                             uint32_t* slowFlags, unsigned short* rankTab, cudaStream_t s) {
 	if (maxNtr > 16384) return 1;   // caller falls back to the global-memory radix sort
 	const uint32_t* onlyFlagged = nullptr;
 	if (slowFlags && !getenv("PSM_SORT_BITONIC")) {
@@ -456,7 +465,7 @@ int launch_feature_sort_smem(const double* Dall, const PartDesc* parts, uint32_t
 		const size_t smemR = (size_t)maxNp * 12 + (size_t)RXW * 256 * 4;
 		if (allow_max_dyn_smem(feature_sort_radix_kernel) != cudaSuccess) return -1;
 		cudaMemsetAsync(slowFlags, 0, (size_t)nPartsBatch * m * 4, s);
-		feature_sort_radix_kernel<<<nPartsBatch * m, RXT, smemR, s>>>(Dall, parts, m, maxNp, Sall, slowFlags);
+		feature_sort_radix_kernel<<<nPartsBatch * m, RXT, smemR, s>>>(Dall, parts, m, maxNp, Sall, slowFlags, rankTab);
 		onlyFlagged = slowFlags;       // the bitonic kernel below then only redoes what the radix kernel flagged
 	}
 	if (!getenv("PSM_SORT_POW2") || onlyFlagged) {
@@ -464,17 +473,17 @@ int launch_feature_sort_smem(const double* Dall, const PartDesc* parts, uint32_t
 		const int ce = (int)((slotsMax / 2 + BT - 1) / BT);
 		const bool two = (size_t)slotsMax * 10 <= 110 * 1024 && !getenv("PSM_SORT_ONE_CTA");   // two CTAs per SM when shared memory allows
 #define PSM_SORT_CASE(C)                                                                                        \
-	case C: return two ? launch_sort_split<C, 2>(Dall, parts, nPartsBatch, m, slotsMax, Sall, onlyFlagged, s)   \
-	                   : launch_sort_split<C, 1>(Dall, parts, nPartsBatch, m, slotsMax, Sall, onlyFlagged, s);
+	case C: return two ? launch_sort_split<C, 2>(Dall, parts, nPartsBatch, m, slotsMax, Sall, onlyFlagged, rankTab, s)   \
+	                   : launch_sort_split<C, 1>(Dall, parts, nPartsBatch, m, slotsMax, Sall, onlyFlagged, rankTab, s);
 		switch (ce < 1 ? 1 : ce) {
 			PSM_SORT_CASE(1) PSM_SORT_CASE(2) PSM_SORT_CASE(3) PSM_SORT_CASE(4) PSM_SORT_CASE(5) PSM_SORT_CASE(6) PSM_SORT_CASE(7) PSM_SORT_CASE(8)
 		}
 #undef PSM_SORT_CASE
 	}
-	if (maxNtr <= 2048) return launch_sort_smem_N<2048>(Dall, parts, nPartsBatch, m, Sall, s);
-	if (maxNtr <= 4096) return launch_sort_smem_N<4096>(Dall, parts, nPartsBatch, m, Sall, s);
-	if (maxNtr <= 8192) return launch_sort_smem_N<8192>(Dall, parts, nPartsBatch, m, Sall, s);
-	return launch_sort_smem_N<16384>(Dall, parts, nPartsBatch, m, Sall, s);
+	if (maxNtr <= 2048) return launch_sort_smem_N<2048>(Dall, parts, nPartsBatch, m, Sall, rankTab, s);
+	if (maxNtr <= 4096) return launch_sort_smem_N<4096>(Dall, parts, nPartsBatch, m, Sall, rankTab, s);
+	if (maxNtr <= 8192) return launch_sort_smem_N<8192>(Dall, parts, nPartsBatch, m, Sall, rankTab, s);
+	return launch_sort_smem_N<16384>(Dall, parts, nPartsBatch, m, Sall, rankTab, s);
 }
 
 void launch_feature_sort(const double* Dall, const PartDesc* parts, uint32_t nPartsBatch, uint32_t m, unsigned long long* keysA,

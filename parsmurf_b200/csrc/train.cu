@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 		if (lane == 0) item = atomicAdd(&A.counters[CNT_NEXT_ITEMS], 1u);
 		item = __shfl_sync(0xffffffffu, item, 0);
 		if (lane == 0) {
-			Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = ts.nEntries; it.npos = npos; it.nneg = nneg; it.nPosOut = pd.nPosOut; it.pad = 0;
+			Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = ts.nEntries; it.npos = npos; it.nneg = nneg; it.nPosOut = pd.nPosOut; it.pl = pl;
 			A.items[0][item] = it;
 			const uint32_t k = A.useClasses ? size_class(ts.nEntries) : (uint32_t)(NCLS - 1);
 			A.clsItems[0][k][atomicAdd(&A.counters[CNT_CLS0 + k], 1u)] = item;
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(128, MULTI ? SS_MINB_MULTI : SS_MINB) split_se
 		else { best = -1.0; bpos = 0xFFFFFFFFu; }
 	}
 	if (gl == 0 && !idle) {
-		SearchRes r; r.score = best; r.pos = bpos; r.lpos = blp; r.lneg = bln; r.pad = 0;
+		SearchRes r; r.score = best; r.pos = bpos; r.lpos = blp; r.lneg = bln; r.rows = 0;
 		A.res[(size_t)item * A.mtry + c] = r;
 	}
 }
@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 	for (uint32_t b = 0; b < ts.itemCount; b += 32) {
 		uint32_t i = b + lane;
 		SplitDec d; d.split = 0; d.nleft = 0; d.lpos = 0; d.lneg = 0;
-		Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = 0; it.npos = 0; it.nneg = 0; it.nPosOut = 0; it.pad = 0;
+		Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = 0; it.npos = 0; it.nneg = 0; it.nPosOut = 0; it.pl = 0;
 		if (i < ts.itemCount) { d = dec[i]; it = cur[i]; }
 		const unsigned smask = __ballot_sync(0xffffffffu, d.split != 0);
 		const uint32_t sp = __popc(smask & lt);
@@ -780,11 +780,11 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 			nodes[it.node].b = (nodes[it.node].b & 0xFFFFFFFFull) | ((unsigned long long)leftId << 32);   // Tree.cpp:294-302
 			uint32_t o = myOff;
 			if (liveL) {
-				Item c; c.tree = tree; c.node = leftId; c.start = it.start; c.cnt = d.nleft; c.npos = d.lpos; c.nneg = d.lneg; c.nPosOut = it.nPosOut; c.pad = 0;
+				Item c; c.tree = tree; c.node = leftId; c.start = it.start; c.cnt = d.nleft; c.npos = d.lpos; c.nneg = d.lneg; c.nPosOut = it.nPosOut; c.pl = it.pl;
 				nextItems[o] = c; sm.child[2 * sp] = o; o++;
 			} else { write_leaf(&nodes[leftId], d.lpos, d.lneg); sm.child[2 * sp] = 0xFFFFFFFFu; }
 			if (liveR) {
-				Item c; c.tree = tree; c.node = leftId + 1; c.start = it.start + d.nleft; c.cnt = it.cnt - d.nleft; c.npos = rpos; c.nneg = rneg; c.nPosOut = it.nPosOut; c.pad = 0;
+				Item c; c.tree = tree; c.node = leftId + 1; c.start = it.start + d.nleft; c.cnt = it.cnt - d.nleft; c.npos = rpos; c.nneg = rneg; c.nPosOut = it.nPosOut; c.pl = it.pl;
 				nextItems[o] = c; sm.child[2 * sp + 1] = o;
 			} else { write_leaf(&nodes[leftId + 1], rpos, rneg); sm.child[2 * sp + 1] = 0xFFFFFFFFu; }
 		}
