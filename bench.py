@@ -189,7 +189,7 @@ def workload_config(args, w, name=None):
     return {"workload": "BASELINE.json %s: synthetic %dx%d imbalanced 1:%d, nParts=%d, fp=%d, ratio=%d, k=%d, nTrees=%d, mtry=%d, %d-fold CV"
             % (WL_NAMES.get(name, name), w["n"], w["m"], w["n"] // w["npos"], w["nParts"], w["fp"], w["ratio"], w["k"], w["nTrees"], w["mtry"], w["nFolds"]),
             "partitions_per_step": w["nParts"] * w["nFolds"], "parallelism": ("single GPU" if args.gpus == 1 else
-                            "%d GPUs, dataset replicated, %s" % (args.gpus, "contiguous ranges of the nFolds x nParts (fold, partition) units per rank, ONE NCCL all-reduce of the score arrays [2n] f64 at the end (+ one of the per-fold metrics)"
+                            "%d GPUs, dataset replicated, %s" % (args.gpus, "contiguous ranges of the nFolds x nParts (fold, partition) units per rank, ONE NCCL all-reduce of the score arrays [2n] f64 at the end (+ one of the per-fold metrics), issued by the library (psm_comm_allreduce_sum_f64); only rank 0 fetches the scores"
                                                                 if args.shard != "fold" else "every rank takes its chunk of every fold's partitions (the reference's MPI rule), one NCCL all-reduce of the fold scores per fold")),
             "l2_policy": "inputs larger than L2 (dataset %d MB + per-fold training batches of GBs >> 126 MB L2); no explicit flush" % (w["n"] * (w["m"] + 1) * 8 // 1_000_000),
             "curves_tie_mode": "auto: device radix sort; exact unless a run of tied scores holds both labels, then bracketed by the positives-first / negatives-first tie orders (midpoint if they agree to 1e-6, else the reference's host std::sort)"}
@@ -217,6 +217,16 @@ class Rig:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
         self.stream = torch.cuda.current_stream()
         self.hdev = H.HostDevice(self.local, self.stream.cuda_stream)   # one long-lived GPU context, as in a long-lived host process
+        # the cross-rank sum runs inside the library (psm_comm_*: NCCL bound by the C ABI); torch.distributed only carries the
+        # 128-byte communicator id from rank 0 to the others.  --reduce torch keeps the old callback around dist.all_reduce.
+        self.lib_reduce = self.world > 1 and args.reduce == "library"
+        if self.lib_reduce:
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if self.rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(H.HostDevice.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            self.hdev.comm_init(bytes(idt.cpu().numpy().tobytes()), self.rank, self.world)
+            self.comm = self.hdev.comm_info()
 
     def reduce(self, ptr, count):
         torch = self.torch
@@ -261,7 +271,8 @@ def measure_cv(rig, w, x_pinned, x_dev, y, f, steps, warmup, roof_steps, with_br
     x_host = x_pinned.numpy()
     common = dict(labels=y, folds=f, nFolds=w["nFolds"], nParts=w["nParts"], fp=w["fp"], ratio=w["ratio"], k=w["k"], nTrees=w["nTrees"], mtry=w["mtry"],
                   seed=w["seed"], device=rig.local, stream=rig.stream.cuda_stream, tie_mode=2, eval_fold_curves=True, rank=rig.rank, world=rig.world,
-                  reduce=rig.reduce if rig.world > 1 else None, profile=0, fold_lanes=args.fold_lanes, shard=args.shard)
+                  reduce=rig.reduce if (rig.world > 1 and not rig.lib_reduce) else None, profile=0, fold_lanes=args.fold_lanes, shard=args.shard,
+                  scores_root_only=rig.world > 1)
     scores = (np.zeros(n), np.zeros(n))               # class1Prob / class2Prob host arrays, reused by every step
     run_dev = lambda: rig.hdev.cv_run(None, x_device_ptr=x_dev.data_ptr(), n=n, m=m, out=scores, **common)
     run_e2e = lambda: rig.hdev.cv_run(x_host, out=scores, **common)
@@ -375,7 +386,7 @@ def grid_block(rig, w, x_dev, y, f):
     import itertools
     grid = [(a, b, c, d, e, g) for a, b, c, d, e, g in itertools.product(GRID["nParts"], GRID["fp"], GRID["ratio"], GRID["k"], GRID["nTrees"], GRID["mtry"])]
     run = lambda: rig.hdev.cv_grid_run(None, y, f, w["nFolds"], grid, w["seed"], device=rig.local, tie_mode=2, stream=rig.stream.cuda_stream, rank=rig.rank,
-                                       world=rig.world, reduce=rig.reduce if rig.world > 1 else None, x_device_ptr=x_dev.data_ptr(), n=w["n"], m=w["m"])
+                                       world=rig.world, reduce=rig.reduce if (rig.world > 1 and not rig.lib_reduce) else None, x_device_ptr=x_dev.data_ptr(), n=w["n"], m=w["m"])
     run()
     sampler = ClockSampler(rig.local)
     if rig.rank == 0:
@@ -403,7 +414,8 @@ def run_ours(args, w):
     if args.single:   # profiling aid (scripts/collect_profiles.sh): just the CVs, no timing regions, no JSON line
         common = dict(labels=y, folds=f, nFolds=w["nFolds"], nParts=w["nParts"], fp=w["fp"], ratio=w["ratio"], k=w["k"], nTrees=w["nTrees"], mtry=w["mtry"],
                       seed=w["seed"], device=rig.local, stream=rig.stream.cuda_stream, tie_mode=2, eval_fold_curves=True, rank=rank, world=world,
-                      reduce=rig.reduce if world > 1 else None, profile=0, fold_lanes=args.fold_lanes, shard=args.shard)
+                      reduce=rig.reduce if (world > 1 and not rig.lib_reduce) else None, profile=0, fold_lanes=args.fold_lanes, shard=args.shard,
+                      scores_root_only=world > 1)
         scores = (np.zeros(n), np.zeros(n))
         for _ in range(max(args.steps, 1)):
             rig.hdev.cv_run(None, x_device_ptr=x_dev.data_ptr(), n=n, m=m, out=scores, **common)
@@ -432,6 +444,8 @@ def run_ours(args, w):
                 "host_phases_ms_per_step": {k_: 1000.0 * sum(o["host_phases_s"][k_] for o in outs) / args.steps for k_ in outs[0]["host_phases_s"]},
                 "host_phases_ms_per_step_e2e": {k_: 1000.0 * sum(o["host_phases_s"][k_] for o in outs_e2e) / args.steps for k_ in outs_e2e[0]["host_phases_s"]},
                 "mpi_baseline": mpi_probe()}
+        if rig.lib_reduce:
+            line["comm"] = dict(rig.comm, where="inside libparsmurf_b200.so: psm_comm_init / psm_comm_allreduce_sum_f64 (ncclAllReduce on the context's stream)")
         if world == 1:
             try:
                 line["curves"].update(tie_check(rig, w, y, r["scores"][0]))
@@ -503,6 +517,7 @@ def main():
     ap.add_argument("--fold-lanes", type=int, default=None, help="folds in flight at once (default: the library's)")
     ap.add_argument("--single", action="store_true", help="run only --steps CVs and exit (for ncu passes)")
     ap.add_argument("--shard", default="unit", choices=["unit", "fold"], help="multi-GPU sharding rule (see host_api.cv_run)")
+    ap.add_argument("--reduce", default="library", choices=["library", "torch"], help="multi-GPU sum: the library's own NCCL communicator (psm_comm_*) or a callback around torch.distributed.all_reduce")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -172,6 +172,21 @@ int psm_scratch_f64(psm_ctx* ctx, uint32_t count, double** dev);
 int psm_scratch_write(psm_ctx* ctx, const double* host, uint32_t count);
 int psm_scratch_read(psm_ctx* ctx, double* host, uint32_t count);
 
+/* ---- (8b) cross-rank sum inside the library: the MPI_Gather + master sum of the score vectors
+ *      (src/hyperSMURF_MPI.cpp:594-646; communicator set-up src/MPIHelper.cpp:29-37) as ONE NCCL all-reduce over
+ *      NVLink / NVSwitch, issued on the context's stream.  One rank calls psm_comm_unique_id and hands the 128 bytes to the
+ *      others by whatever bootstrap the host has (MPI_Bcast, torch.distributed, a file, shared memory of a multi-threaded
+ *      process); every rank then calls psm_comm_init (collective: returns when all `world` ranks have joined).  NCCL is
+ *      loaded at the first call (dlopen of libnccl.so.2 -- the copy the process already holds, if any), so a single-GPU
+ *      host never needs it.  psm_comm_allreduce_sum_f64 sums `count` doubles at device pointer `dev` across the ranks, in
+ *      place, and returns when the result is visible to the stream (it synchronises the stream). ------------------------- */
+#define PSM_COMM_ID_BYTES 128
+int psm_comm_unique_id(void* id128);
+int psm_comm_init(psm_ctx* ctx, const void* id128, uint32_t rank, uint32_t world);
+int psm_comm_info(psm_ctx* ctx, uint32_t* rank, uint32_t* world, int* nccl_version);
+int psm_comm_allreduce_sum_f64(psm_ctx* ctx, double* dev, uint64_t count);
+int psm_comm_destroy(psm_ctx* ctx);
+
 /* ---- (9) curves: Curves ctor + evalAUROC_ok + evalAUPRC (src/curves.cpp:7-36,77-122). out = {auroc, auprc}.
  *      tie_mode 0: descending order from the identical host std::sort call (bit-parity with the reference's
  *      tie order); tie_mode 1: stable device radix sort (ties in index order; may differ from the reference by

@@ -3,6 +3,8 @@
 #include "../../include/parsmurf_b200.h"
 #include "kernels.cuh"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -90,6 +92,7 @@ struct psm_ctx {
 	// device-resident labels / global scores
 	DevBuf dLabels, dFoldLabels, dGlob;
 	std::vector<uint32_t> hLabels;
+	uint32_t labelsPos = 0, labelsNeg = 0;   // class totals of hLabels
 	bool haveLabels = false, foldLabelsReady = false;
 
 	// curves
@@ -97,6 +100,10 @@ struct psm_ctx {
 	int curvesUsedHostSort = 0;
 	double curvesSpread[2] = {0, 0};
 	DevBuf cIdx, cFoldScores, cScratch, cLabels, cPerm, cSorted, cTp, cPartials, cOut, cScores, cKeysA, cKeysB, cValsA, cValsB, cHist;
+
+	// cross-rank communicator (psm_comm_init)
+	void* comm = nullptr;            // ncclComm_t
+	uint32_t commRank = 0, commWorld = 1;
 
 	// profiling
 	bool profOn = false;
@@ -208,6 +215,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	if (ctx->hCounters) cudaFreeHost(ctx->hCounters);
 	if (ctx->evLevel) cudaEventDestroy(ctx->evLevel);
 	if (ctx->hStage) cudaFreeHost(ctx->hStage);
+	if (ctx->comm) psm_comm_destroy(ctx);
 	if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
 	delete ctx;
 	return PSM_OK;
@@ -259,6 +267,7 @@ int psm_dataset_upload(psm_ctx* ctx, const double* x_host, uint32_t n, uint32_t 
 	ctx->x = ctx->xOwned.as<double>();
 	ctx->n = n; ctx->m = m;
 	ctx->foldOpen = ctx->batchOpen = false;
+	ctx->haveLabels = false;   // a new dataset copy: its labels are uploaded again too (psm_labels_upload keeps them otherwise)
 	return PSM_OK;
 }
 
@@ -1088,11 +1097,18 @@ int psm_curves(psm_ctx* ctx, const uint32_t* labels, const double* scores, uint6
 int psm_labels_upload(psm_ctx* ctx, const uint32_t* labels, uint32_t n) {
 	if (!ctx || !labels || n == 0 || n != ctx->n) return fail(ctx, PSM_E_ARG, "labels_upload: need the dataset first and n labels");
 	CU(cudaSetDevice(ctx->device));
+	ENSURE(ctx->dGlob, (size_t)n * 16);
+	CU(cudaMemsetAsync(ctx->dGlob.p, 0, (size_t)n * 16, ctx->stream));
+	// a host that runs one CV after the other hands in the same labels every time: the device copy and the class totals are
+	// kept when the vector is unchanged (one memcmp instead of a host copy, an H2D copy and two O(n) counting passes per CV)
+	if (ctx->haveLabels && ctx->hLabels.size() == n && memcmp(ctx->hLabels.data(), labels, (size_t)n * 4) == 0) return PSM_OK;
+	ctx->haveLabels = false;
 	ctx->hLabels.assign(labels, labels + n);
 	ENSURE(ctx->dLabels, (size_t)n * 4);
-	ENSURE(ctx->dGlob, (size_t)n * 16);
-	CU(cudaMemcpyAsync(ctx->dLabels.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-	CU(cudaMemsetAsync(ctx->dGlob.p, 0, (size_t)n * 16, ctx->stream));
+	CU(cudaMemcpyAsync(ctx->dLabels.p, ctx->hLabels.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	uint32_t totP = 0, totN = 0;
+	for (uint32_t i = 0; i < n; i++) { totP += labels[i] == 1; totN += labels[i] == 0; }
+	ctx->labelsPos = totP; ctx->labelsNeg = totN;
 	CU(cudaStreamSynchronize(ctx->stream));
 	ctx->haveLabels = true;
 	return PSM_OK;
@@ -1138,27 +1154,42 @@ static int scores_fetch(psm_ctx* ctx, double* class1Prob, double* class2Prob, bo
 		CU(cudaMallocHost(&ctx->hStage, need));
 		ctx->hStageCap = need;
 	}
+	// The copy out of the pinned staging buffer is a pure memory stream (28M doubles at BASELINE configs[2]) that costs as much
+	// as the D2H copy itself, so the two are pipelined: the device arrays come over in chunks, each followed by an event, and a
+	// few host threads move (or add) chunk k while chunk k+1 is still on the bus.
 	const double* h = (const double*)ctx->hStage;
-	CU(cudaMemcpyAsync(ctx->hStage, ctx->dGlob.p, need, cudaMemcpyDeviceToHost, ctx->stream));
-	CU(cudaStreamSynchronize(ctx->stream));
-	// the add is a pure memory stream (28M doubles at BASELINE configs[2]): a few host threads instead of one
 	const uint32_t n = ctx->n;
-	const uint32_t nThreads = n >= (1u << 18) ? 4u : 1u;
-	auto addRange = [&](uint32_t a, uint32_t b) {
-		if (overwrite) {
-			memcpy(class1Prob + a, h + a, (size_t)(b - a) * 8);
-			if (class2Prob) memcpy(class2Prob + a, h + (size_t)n + a, (size_t)(b - a) * 8);
-			return;
+	const size_t total = (size_t)n * (class2Prob ? 2 : 1);                    // doubles wanted: class1 [n], then class2 [n]
+	const uint32_t nChunks = total >= (1u << 20) ? 16u : 1u;
+	std::vector<cudaEvent_t> ev(nChunks);
+	for (uint32_t c = 0; c < nChunks; c++) {
+		const size_t a0 = total * c / nChunks, a1 = total * (c + 1) / nChunks;
+		CU(cudaMemcpyAsync((double*)ctx->hStage + a0, ctx->dGlob.as<double>() + a0, (a1 - a0) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		ev[c] = get_event(ctx);
+		CU(cudaEventRecord(ev[c], ctx->stream));
+	}
+	auto outPtr = [&](size_t i) { return i < n ? class1Prob + i : class2Prob + (i - n); };
+	auto moveChunk = [&](uint32_t c) {
+		cudaEventSynchronize(ev[c]);
+		size_t a0 = total * c / nChunks;
+		const size_t a1 = total * (c + 1) / nChunks;
+		while (a0 < a1) {                                                      // a chunk may straddle the class1 / class2 boundary
+			const size_t e = (a0 < n && a1 > n) ? n : a1;
+			double* dst = outPtr(a0);
+			if (overwrite) memcpy(dst, h + a0, (e - a0) * 8);
+			else for (size_t i = a0; i < e; i++) dst[i - a0] += h[i];
+			a0 = e;
 		}
-		for (uint32_t i = a; i < b; i++) class1Prob[i] += h[i];
-		if (class2Prob) for (uint32_t i = a; i < b; i++) class2Prob[i] += h[(size_t)n + i];
 	};
-	if (nThreads == 1) addRange(0, n);
+	const uint32_t nThreads = std::min<uint32_t>(nChunks, 4);
+	if (nThreads == 1) moveChunk(0);
 	else {
+		const int device = ctx->device;
 		std::vector<std::thread> th;
-		for (uint32_t t = 0; t < nThreads; t++) th.emplace_back(addRange, (uint32_t)((uint64_t)n * t / nThreads), (uint32_t)((uint64_t)n * (t + 1) / nThreads));
+		for (uint32_t t = 0; t < nThreads; t++) th.emplace_back([&, t]() { cudaSetDevice(device); for (uint32_t c = t; c < nChunks; c += nThreads) moveChunk(c); });
 		for (auto& x : th) x.join();
 	}
+	for (auto e : ev) ctx->evPool.push_back(e);
 	return PSM_OK;
 }
 
@@ -1175,9 +1206,7 @@ int psm_scores_merge(psm_ctx* ctx, psm_ctx* src) {
 int psm_scores_curves(psm_ctx* ctx, int tie_mode, double* out) {
 	if (!ctx || !ctx->haveLabels || !out) return fail(ctx, PSM_E_ARG, "scores_curves: no device scores");
 	CU(cudaSetDevice(ctx->device));
-	uint32_t totP = 0, totN = 0;
-	for (uint32_t i = 0; i < ctx->n; i++) { totP += ctx->hLabels[i] == 1; totN += ctx->hLabels[i] == 0; }
-	return curves_core(ctx, ctx->dLabels.as<uint32_t>(), ctx->dGlob.as<double>(), nullptr, ctx->n, totP, totN, tie_mode, out);
+	return curves_core(ctx, ctx->dLabels.as<uint32_t>(), ctx->dGlob.as<double>(), nullptr, ctx->n, ctx->labelsPos, ctx->labelsNeg, tie_mode, out);
 }
 
 int psm_scores_devptr(psm_ctx* ctx, double** dev, uint32_t* n) {
@@ -1241,6 +1270,103 @@ int psm_scratch_read(psm_ctx* ctx, double* host, uint32_t count) {
 	CU(cudaMemcpyAsync(host, ctx->cScratch.p, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	return PSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ cross-rank sum (NCCL)
+// The reference's multi-node build gathers every worker's score vectors on the master and sums them there
+// (src/hyperSMURF_MPI.cpp:594-646, communicator src/MPIHelper.cpp:29-37).  Here the ranks are GPUs of one NVSwitch domain and
+// the sum is one ncclAllReduce on the context's stream.  NCCL is bound at run time: libnccl.so.2 is dlopen'ed at the first
+// communicator call (a host process that already loaded a copy -- torch's -- gets that copy back), so the library has no
+// link-time dependency and single-GPU hosts never touch it.  Only the few entry points used are declared (ABI of nccl.h 2.x).
+namespace {
+typedef struct { char internal[PSM_COMM_ID_BYTES]; } NcclId;
+struct NcclApi {
+	void* lib = nullptr;
+	int (*GetVersion)(int*) = nullptr;
+	int (*GetUniqueId)(NcclId*) = nullptr;
+	int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	int (*CommDestroy)(void*) = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+	std::string err;
+};
+NcclApi* nccl_api() {
+	static NcclApi api;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		const char* names[] = {"libnccl.so.2", "libnccl.so"};
+		for (const char* nm : names) { api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+		if (!api.lib) { api.err = std::string("NCCL not found: ") + dlerror(); return; }
+		auto sym = [&](const char* n) { void* f = dlsym(api.lib, n); if (!f && api.err.empty()) api.err = std::string("NCCL symbol missing: ") + n; return f; };
+		api.GetVersion = (int (*)(int*))sym("ncclGetVersion");
+		api.GetUniqueId = (int (*)(NcclId*))sym("ncclGetUniqueId");
+		api.CommInitRank = (int (*)(void**, int, NcclId, int))sym("ncclCommInitRank");
+		api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+		api.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+		api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+	});
+	return &api;
+}
+int nccl_fail(psm_ctx* ctx, NcclApi* a, int rc, const char* where) {
+	return fail(ctx, PSM_E_CUDA, std::string(where) + ": " + (a->GetErrorString ? a->GetErrorString(rc) : "NCCL error"));
+}
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values of nccl.h
+}  // namespace
+
+int psm_comm_unique_id(void* id128) {
+	if (!id128) return PSM_E_ARG;
+	NcclApi* a = nccl_api();
+	if (!a->err.empty()) return PSM_E_CUDA;
+	NcclId id;
+	if (a->GetUniqueId(&id) != 0) return PSM_E_CUDA;
+	memcpy(id128, &id, sizeof(id));
+	return PSM_OK;
+}
+
+int psm_comm_init(psm_ctx* ctx, const void* id128, uint32_t rank, uint32_t world) {
+	if (!ctx || !id128 || world == 0 || rank >= world) return fail(ctx, PSM_E_ARG, "comm_init: bad arguments");
+	NcclApi* a = nccl_api();
+	if (!a->err.empty()) return fail(ctx, PSM_E_CUDA, "comm_init: " + a->err);
+	if (ctx->comm) { int rc = psm_comm_destroy(ctx); if (rc) return rc; }
+	CU(cudaSetDevice(ctx->device));
+	NcclId id;
+	memcpy(&id, id128, sizeof(id));
+	void* comm = nullptr;
+	const int rc = a->CommInitRank(&comm, (int)world, id, (int)rank);
+	if (rc != 0) return nccl_fail(ctx, a, rc, "comm_init: ncclCommInitRank");
+	ctx->comm = comm; ctx->commRank = rank; ctx->commWorld = world;
+	return PSM_OK;
+}
+
+int psm_comm_info(psm_ctx* ctx, uint32_t* rank, uint32_t* world, int* nccl_version) {
+	if (!ctx) return PSM_E_ARG;
+	if (rank) *rank = ctx->commRank;
+	if (world) *world = ctx->comm ? ctx->commWorld : 0;
+	if (nccl_version) { *nccl_version = 0; NcclApi* a = nccl_api(); if (a->err.empty() && a->GetVersion) a->GetVersion(nccl_version); }
+	return PSM_OK;
+}
+
+int psm_comm_allreduce_sum_f64(psm_ctx* ctx, double* dev, uint64_t count) {
+	if (!ctx || !ctx->comm) return fail(ctx, PSM_E_ARG, "comm_allreduce: no communicator (psm_comm_init first)");
+	if (count == 0) return PSM_OK;
+	if (!dev) return fail(ctx, PSM_E_ARG, "comm_allreduce: null buffer");
+	NcclApi* a = nccl_api();
+	CU(cudaSetDevice(ctx->device));
+	const int rc = a->AllReduce(dev, dev, (size_t)count, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+	if (rc != 0) return nccl_fail(ctx, a, rc, "comm_allreduce: ncclAllReduce");
+	CU(cudaStreamSynchronize(ctx->stream));
+	return PSM_OK;
+}
+
+int psm_comm_destroy(psm_ctx* ctx) {
+	if (!ctx) return PSM_E_ARG;
+	if (!ctx->comm) return PSM_OK;
+	NcclApi* a = nccl_api();
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	const int rc = a->CommDestroy(ctx->comm);
+	ctx->comm = nullptr; ctx->commWorld = 1; ctx->commRank = 0;
+	return rc == 0 ? PSM_OK : nccl_fail(ctx, a, rc, "comm_destroy: ncclCommDestroy");
 }
 
 // ------------------------------------------------------------------------------------------ convenience

@@ -84,7 +84,7 @@ struct SearchRes {
 	uint32_t pos;     // best split after list position `pos` (relative to segment start)
 	uint32_t lpos;    // left class-0 samples
 	uint32_t lneg;    // left class-1 samples
-	uint32_t rows;    // small mode: row at `pos` (low 16 bits) and the row that follows it in the candidate's order (high 16 bits)
+	uint32_t pad;
 };
 
 struct SplitDec {
@@ -100,10 +100,9 @@ struct __align__(16) PartTask {
 	uint32_t cnt;     // 0 = nothing to move (no split, or both children terminal); top bits: PT_DEAD_LEFT / PT_DEAD_RIGHT
 	uint32_t nleft;
 };
-// rows per matrix < 2^24.  PT_SMALL: the node is in small mode (one row list, in the slot of feature 0); PT_SMALL_LEFT / RIGHT: that
-// child will be (its entries are only needed in the list of feature 0).
-constexpr uint32_t PT_DEAD_LEFT = 1u << 31, PT_DEAD_RIGHT = 1u << 30, PT_SMALL = 1u << 29, PT_SMALL_LEFT = 1u << 28, PT_SMALL_RIGHT = 1u << 27,
-                   PT_CNT_MASK = (1u << 24) - 1u;
+// rows per matrix < 2^24.  PT_TAIL: the tree leaves the level loop after this level (tree_tail_kernel finishes it from ONE row list),
+// so only the list of feature 0 is partitioned.
+constexpr uint32_t PT_DEAD_LEFT = 1u << 31, PT_DEAD_RIGHT = 1u << 30, PT_TAIL = 1u << 29, PT_CNT_MASK = (1u << 24) - 1u;
 
 // per-tree growth state
 struct TreeState {
@@ -113,6 +112,8 @@ struct TreeState {
 	uint32_t mtPos;       // next unread index in the mt19937_64 state block (0..312)
 	uint32_t nEntries;    // in-bag distinct rows
 	uint32_t overflow;
+	uint32_t tailCount;   // > 0: the tree left the level loop with this many open nodes (items in its window of tailItems[0])
+	uint32_t pad;
 };
 
 // Opt a kernel in to the full 227 KB of dynamic shared memory.  The attribute belongs to the function, not to the calling

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) build_lists_kernel(TrainArgs A) {
 		}
 	}
 	if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&A.counters[CNT_ERROR], ERR_COUNT_LIMIT);
-	if (f == 0 && lane == 0) A.ts[tree].nEntries = off;
+	if (f == 0 && lane == 0) { A.ts[tree].nEntries = off; atomicMax(&A.counters[CNT_MAX_ENTRIES], off); }
 }
 
 // ------------------------------------------------------------------------------------------ candidates
@@ -281,31 +281,39 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 	Node16* nodes = A.nodes + (size_t)tree * A.NC;
 	const bool live = node_live(npos, nneg);
 	uint32_t item = 0xFFFFFFFFu;
+	const bool toTail = live && A.tailCap && ts.nEntries <= A.tailCap;   // a root that small goes straight to tree_tail_kernel
+	uint32_t* candBase = toTail ? A.tailCand + (size_t)tree * A.tailStride * A.mtry : A.cand;
 	if (live) {
-		if (lane == 0) item = atomicAdd(&A.counters[CNT_NEXT_ITEMS], 1u);
+		if (lane == 0) item = toTail ? 0u : atomicAdd(&A.counters[CNT_NEXT_ITEMS], 1u);
 		item = __shfl_sync(0xffffffffu, item, 0);
 		if (lane == 0) {
 			Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = ts.nEntries; it.npos = npos; it.nneg = nneg; it.nPosOut = pd.nPosOut; it.pl = pl;
-			A.items[0][item] = it;
-			const uint32_t k = A.useClasses ? size_class(ts.nEntries) : (uint32_t)(NCLS - 1);
-			A.clsItems[0][k][atomicAdd(&A.counters[CNT_CLS0 + k], 1u)] = item;
+			if (toTail) {
+				A.tailItems[0][(size_t)tree * A.tailStride] = it;
+				A.tailList[atomicAdd(&A.counters[CNT_TAIL], 1u)] = tree;
+			} else {
+				A.items[0][item] = it;
+				const uint32_t k = A.useClasses ? size_class(ts.nEntries) : (uint32_t)(NCLS - 1);
+				A.clsItems[0][k][atomicAdd(&A.counters[CNT_CLS0 + k], 1u)] = item;
+			}
 		}
 	} else if (lane == 0) {
 		write_leaf(&nodes[0], npos, nneg);
 	}
 	if (A.injCand) {
-		if (live) for (uint32_t q = lane; q < A.mtry; q += 32) A.cand[(size_t)item * A.mtry + q] = A.injCand[((size_t)tree * A.injCandNodes + 0) * A.mtry + q];
+		if (live) for (uint32_t q = lane; q < A.mtry; q += 32) candBase[(size_t)item * A.mtry + q] = A.injCand[((size_t)tree * A.injCandNodes + 0) * A.mtry + q];
 	} else {
 		unsigned long long* g = A.mt + (size_t)tree * MT_N;
 		for (int i = lane; i < MT_N; i += 32) sm.mt[i] = g[i];
 		init_perm(sm.perm, A.m, A.mtry);
 		uint32_t pos = ts.mtPos;
-		gen_candidates(sm.mt, pos, A.m, A.mtry, sm.perm, sm.jbuf, live ? A.cand + (size_t)item * A.mtry : nullptr);
+		gen_candidates(sm.mt, pos, A.m, A.mtry, sm.perm, sm.jbuf, live ? candBase + (size_t)item * A.mtry : nullptr);
 		for (int i = lane; i < MT_N; i += 32) g[i] = sm.mt[i];
 		ts.mtPos = pos;
 	}
 	if (lane == 0) {
-		ts.nNodes = 1; ts.itemBase = live ? item : 0; ts.itemCount = live ? 1 : 0; ts.overflow = 0;
+		ts.nNodes = 1; ts.itemBase = (live && !toTail) ? item : 0; ts.itemCount = (live && !toTail) ? 1 : 0; ts.overflow = 0;
+		ts.tailCount = toTail ? 1u : 0u;
 		A.ts[tree] = ts;
 	}
 }
@@ -594,7 +602,7 @@ __global__ void __launch_bounds__(128, MULTI ? SS_MINB_MULTI : SS_MINB) split_se
 		else { best = -1.0; bpos = 0xFFFFFFFFu; }
 	}
 	if (gl == 0 && !idle) {
-		SearchRes r; r.score = best; r.pos = bpos; r.lpos = blp; r.lneg = bln; r.rows = 0;
+		SearchRes r; r.score = best; r.pos = bpos; r.lpos = blp; r.lneg = bln; r.pad = 0;
 		A.res[(size_t)item * A.mtry + c] = r;
 	}
 }
@@ -706,6 +714,45 @@ __global__ void __launch_bounds__(TF_THREADS) tree_flags_kernel(TrainArgs A, int
 }
 
 // ------------------------------------------------------------------------------------------ level finalize
+// The mtry draws of the `nchild` nodes created by up to 32 parents, in node-id order (ids childBase .. childBase + nchild - 1);
+// sm.child[c] = work-item slot of child c (its candidates go to candBase + slot * mtry) or 0xFFFFFFFF for a terminal child,
+// whose draws are consumed but not stored.  Warp-cooperative; shared by level_finalize_kernel and tree_tail_kernel.
+__device__ __forceinline__ void draw_children(const TrainArgs& A, const TreeSmem& sm, uint32_t& pos, uint32_t tree, uint32_t childBase,
+                                              uint32_t nchild, uint32_t* candBase, const int lane) {
+	const bool laneFY = !A.injCand && A.mtry <= FY_MAX && !(A.mtry < (A.m + 1) / 10);
+	if (laneFY) {
+		// one node per lane: stage the next 32*mtry stream outputs (tempered) and draw up to 32 nodes at once
+		for (uint32_t c0 = 0; c0 < nchild; c0 += 32) {
+			const uint32_t nc = min(32u, nchild - c0);
+			uint32_t need = nc * A.mtry, got = 0;
+			while (got < need) {
+				if (pos == MT_N) { mt_twist(sm.mt); pos = 0; }
+				const uint32_t take = min(need - got, (uint32_t)MT_N - pos);
+				for (uint32_t q = lane; q < take; q += 32) sm.ubuf[got + q] = mt_temper(sm.mt[pos + q]);
+				got += take; pos += take;
+			}
+			__syncwarp();
+			if ((uint32_t)lane < nc) {
+				const uint32_t ci = sm.child[c0 + lane];
+				fy_lane(sm.ubuf + (size_t)lane * A.mtry, A.m, A.mtry, ci != 0xFFFFFFFFu ? candBase + (size_t)ci * A.mtry : nullptr);
+			}
+			__syncwarp();
+		}
+	} else {
+		for (uint32_t c = 0; c < nchild; c++) {
+			const uint32_t ci = sm.child[c];
+			if (A.injCand) {
+				if (ci != 0xFFFFFFFFu)
+					for (uint32_t q = lane; q < A.mtry; q += 32)
+						candBase[(size_t)ci * A.mtry + q] = A.injCand[((size_t)tree * A.injCandNodes + (childBase + c)) * A.mtry + q];
+			} else {
+				gen_candidates(sm.mt, pos, A.m, A.mtry, sm.perm, sm.jbuf, ci != 0xFFFFFFFFu ? candBase + (size_t)ci * A.mtry : nullptr);
+			}
+		}
+	}
+	__syncwarp();
+}
+
 // one warp per tree: breadth-first child ids in parent-id order, child work items, leaf payloads of trivially
 // terminal children, and the mtry draw of every new node in node-id order.
 __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf) {
@@ -718,26 +765,28 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 	const unsigned lt = lanemask_lt();
 	const Item* cur = A.items[buf] + ts.itemBase;
 	const SplitDec* dec = A.dec + ts.itemBase;
-	Item* nextItems = A.items[buf ^ 1];
 	Node16* nodes = A.nodes + (size_t)tree * A.NC;
 
 	// pass 1: count splits and live children
-	uint32_t nsplit = 0, nlive = 0;
+	uint32_t nsplit = 0, nlive = 0, maxChild = 0;
 	unsigned long long searched = 0;   // samples of the nodes that reached findBestSplit this level (SURVEY 8(d) byte count; one atomic per tree)
 	for (uint32_t b = 0; b < ts.itemCount; b += 32) {
 		uint32_t i = b + lane;
-		uint32_t l = 0, s = 0;
+		uint32_t l = 0, s = 0, mc = 0;
 		if (i < ts.itemCount) {
 			SplitDec d = dec[i];
 			const Item it = cur[i];
 			searched += it.npos + it.nneg;
 			if (d.split) {
 				s = 1;
-				l = (node_live(d.lpos, d.lneg) ? 1u : 0u) + (node_live(it.npos - d.lpos, it.nneg - d.lneg) ? 1u : 0u);
+				const bool liveL = node_live(d.lpos, d.lneg), liveR = node_live(it.npos - d.lpos, it.nneg - d.lneg);
+				l = (liveL ? 1u : 0u) + (liveR ? 1u : 0u);
+				mc = max(liveL ? d.nleft : 0u, liveR ? it.cnt - d.nleft : 0u);
 			}
 		}
 		for (int o = 16; o > 0; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); s += __shfl_xor_sync(0xffffffffu, s, o); }
 		nlive += l; nsplit += s;
+		maxChild = max(maxChild, __reduce_max_sync(0xffffffffu, mc));
 	}
 	for (int o = 16; o > 0; o >>= 1) searched += __shfl_xor_sync(0xffffffffu, searched, o);
 	if (lane == 0) atomicAdd(&A.stats[STAT_SPLIT_BYTES], searched * ((unsigned long long)A.mtry * 8ull + 8ull));
@@ -745,13 +794,18 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 		if (lane == 0) { ts.itemCount = 0; A.ts[tree] = ts; }
 		return;
 	}
+	// Every open node of the next level fits the tail kernel: the tree leaves the level loop.  Its work items and candidate draws
+	// go to the tree's own window, and this level's list partition only moves the list of feature 0 (PT_TAIL).
+	const bool toTail = A.tailCap && nlive > 0 && maxChild <= A.tailCap && nlive <= A.tailStride;
 	uint32_t nextBase = 0;
-	if (lane == 0) nextBase = atomicAdd(&A.counters[CNT_NEXT_ITEMS], nlive);
+	if (lane == 0 && !toTail) nextBase = atomicAdd(&A.counters[CNT_NEXT_ITEMS], nlive);
 	nextBase = __shfl_sync(0xffffffffu, nextBase, 0);
-	if (nextBase + nlive > A.itemCap || ts.nNodes + 2 * nsplit > A.NC) {
+	if ((!toTail && nextBase + nlive > A.itemCap) || ts.nNodes + 2 * nsplit > A.NC) {
 		if (lane == 0) { atomicOr(&A.counters[CNT_ERROR], ERR_POOL_OVERFLOW); ts.itemCount = 0; ts.overflow = 1; A.ts[tree] = ts; }
 		return;
 	}
+	Item* nextItems = toTail ? A.tailItems[0] + (size_t)tree * A.tailStride : A.items[buf ^ 1];
+	uint32_t* candBase = toTail ? A.tailCand + (size_t)tree * A.tailStride * A.mtry : A.cand;
 	uint32_t pos = ts.mtPos;
 	unsigned long long* g = A.mt + (size_t)tree * MT_N;
 	if (!A.injCand) {
@@ -787,8 +841,9 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 				Item c; c.tree = tree; c.node = leftId + 1; c.start = it.start + d.nleft; c.cnt = it.cnt - d.nleft; c.npos = rpos; c.nneg = rneg; c.nPosOut = it.nPosOut; c.pl = it.pl;
 				nextItems[o] = c; sm.child[2 * sp + 1] = o;
 			} else { write_leaf(&nodes[leftId + 1], rpos, rneg); sm.child[2 * sp + 1] = 0xFFFFFFFFu; }
+			if (toTail) A.ptask[ts.itemBase + i].cnt |= PT_TAIL;
 		}
-		{
+		if (!toTail) {
 			// size-class lists of the next level (one warp-aggregated atomic per class and batch of 32 parents)
 			const uint32_t big = (uint32_t)(NCLS - 1);
 			const uint32_t kL = liveL ? (A.useClasses ? size_class(d.nleft) : big) : (uint32_t)NCLS;
@@ -809,46 +864,17 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 		}
 		__syncwarp();
 		const uint32_t nchild = 2 * __popc(smask);
-		const bool laneFY = !A.injCand && A.mtry <= FY_MAX && !(A.mtry < (A.m + 1) / 10);
-		if (laneFY) {
-			// one node per lane: stage the next 32*mtry stream outputs (tempered) and draw up to 32 nodes at once
-			for (uint32_t c0 = 0; c0 < nchild; c0 += 32) {
-				const uint32_t nc = min(32u, nchild - c0);
-				uint32_t need = nc * A.mtry, got = 0;
-				while (got < need) {
-					if (pos == MT_N) { mt_twist(sm.mt); pos = 0; }
-					const uint32_t take = min(need - got, (uint32_t)MT_N - pos);
-					for (uint32_t q = lane; q < take; q += 32) sm.ubuf[got + q] = mt_temper(sm.mt[pos + q]);
-					got += take; pos += take;
-				}
-				__syncwarp();
-				if ((uint32_t)lane < nc) {
-					const uint32_t ci = sm.child[c0 + lane];
-					fy_lane(sm.ubuf + (size_t)lane * A.mtry, A.m, A.mtry, ci != 0xFFFFFFFFu ? A.cand + (size_t)ci * A.mtry : nullptr);
-				}
-				__syncwarp();
-			}
-		} else {
-			for (uint32_t c = 0; c < nchild; c++) {
-				const uint32_t ci = sm.child[c];
-				if (A.injCand) {
-					if (ci != 0xFFFFFFFFu)
-						for (uint32_t q = lane; q < A.mtry; q += 32)
-							A.cand[(size_t)ci * A.mtry + q] = A.injCand[((size_t)tree * A.injCandNodes + (childBase + c)) * A.mtry + q];
-				} else {
-					gen_candidates(sm.mt, pos, A.m, A.mtry, sm.perm, sm.jbuf, ci != 0xFFFFFFFFu ? A.cand + (size_t)ci * A.mtry : nullptr);
-				}
-			}
-		}
-		__syncwarp();
+		draw_children(A, sm, pos, tree, childBase, nchild, candBase, lane);
 		childBase += nchild;
 		liveOff += __shfl_sync(0xffffffffu, inc, 31);
 	}
 	if (!A.injCand) for (int i = lane; i < MT_N; i += 32) g[i] = sm.mt[i];
 	if (lane == 0) {
 		if (A.injCand && childBase > A.injCandNodes) atomicOr(&A.counters[CNT_ERROR], ERR_INJ_CAND);
-		ts.nNodes = childBase; ts.itemBase = nextBase; ts.itemCount = nlive; ts.mtPos = pos;
+		ts.nNodes = childBase; ts.itemBase = toTail ? 0u : nextBase; ts.itemCount = toTail ? 0u : nlive; ts.mtPos = pos;
+		ts.tailCount = toTail ? nlive : 0u;
 		A.ts[tree] = ts;
+		if (toTail) A.tailList[atomicAdd(&A.counters[CNT_TAIL], 1u)] = tree;
 		atomicAdd(&A.stats[STAT_NODES], (unsigned long long)(2 * nsplit));
 	}
 }
@@ -932,6 +958,7 @@ __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint3
 	if (cnt == 0) return;                                      // node became a leaf, or neither child will be searched
 	const bool keepL = !(raw.z & PT_DEAD_LEFT), keepR = !(raw.z & PT_DEAD_RIGHT);
 	const uint32_t f = blockIdx.y;
+	if ((raw.z & PT_TAIL) && f != 0) return;                   // the tree leaves the level loop: tree_tail_kernel only reads the list of feature 0
 	const uint32_t lane = lane_id();
 	const unsigned lt = lanemask_lt();
 	const size_t lo = ((size_t)tree * A.m + f) * A.stride + start;

@@ -157,7 +157,8 @@ void Folds::computeFolds() {
 		const bool fillFolds = keepFoldsArray;
 		// two passes (count, then place) over contiguous slices of the examples, a few host threads on large inputs: slice t
 		// writes after everything slices < t write, so every fold keeps ascending example order (src/folds.cpp:93-110)
-		const uint32_t nT = classSize >= (1u << 18) ? 4u : 1u;
+		const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+		const uint32_t nT = classSize >= (1u << 18) ? std::min<uint32_t>(std::min<uint32_t>(std::max<uint32_t>(4u, classSize >> 20), 16u), std::max(4u, hw / 2)) : 1u;
 		std::vector<std::vector<uint32_t>> hP(nT, std::vector<uint32_t>(nFolds, 0)), hN(nT, std::vector<uint32_t>(nFolds, 0));
 		std::atomic<bool> bad(false);
 		auto slice = [&](uint32_t t, uint32_t* a, uint32_t* b) { *a = (uint32_t)((uint64_t)classSize * t / nT); *b = (uint32_t)((uint64_t)classSize * (t + 1) / nT); };
@@ -343,6 +344,10 @@ Device::Device(int device, void* cudaStream) : deviceId(device) {
 }
 Device::~Device() { if (ctx) psm_ctx_destroy(ctx); }
 void Device::check(int rc) const { if (rc) throw Error(rc, psm_last_error(ctx)); }
+void Device::commUniqueId(void* id128) { if (psm_comm_unique_id(id128)) throw Error(PSM_E_CUDA, "NCCL is not available (libnccl.so.2 could not be loaded)"); }
+void Device::commInit(const void* id128, uint32_t rank, uint32_t world) { check(psm_comm_init(ctx, id128, rank, world)); }
+bool Device::hasComm() const { uint32_t w = 0; return psm_comm_info(ctx, nullptr, &w, nullptr) == PSM_OK && w > 0; }
+void Device::allReduce(double* dev_ptr, uint64_t count) { check(psm_comm_allreduce_sum_f64(ctx, dev_ptr, count)); }
 void Device::upload(const double* x, uint32_t n_, uint32_t m_) { check(psm_dataset_upload(ctx, x, n_, m_)); n = n_; m = m_; foldTag = nullptr; }
 void Device::attachDevice(const double* x, uint32_t n_, uint32_t m_) { check(psm_dataset_attach_device(ctx, x, n_, m_)); n = n_; m = m_; foldTag = nullptr; }
 void Device::setLaneCount(uint32_t lanes) {
@@ -737,7 +742,9 @@ void hyperSMURF::smurfIt() {                                                // s
 	trace_mark("fold curves done");
 	{
 		PhaseScope ps(PH_SCATTER);
-		if (scoresAreOutputs && woptimiz == OPT_NO && !inInternalCV) dev->check(psm_scores_read(dev->ctx, class1Prob, class2Prob));
+		const bool skipFetch = scoresOnRootOnly && world > 1 && rank != 0 && woptimiz == OPT_NO && !inInternalCV;
+		if (skipFetch) {}
+		else if (scoresAreOutputs && woptimiz == OPT_NO && !inInternalCV) dev->check(psm_scores_read(dev->ctx, class1Prob, class2Prob));
 		else dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob));
 	}
 	trace_mark("scores on the host");
@@ -801,6 +808,7 @@ void hyperSMURF::runFold(uint32_t currentFold, uint32_t first, uint32_t last, De
 		{ PhaseScope ps(PH_FOLDS_TTD); prt->setFold(currentFold); }  // :255 (builds + shuffles the fold on the host if nobody has yet)
 		{ PhaseScope ps(PH_FOLD_BEGIN); d->ensureFold(prt); }
 	}
+	trace_mark("  fold " + std::to_string(currentFold) + " begun");
 	const uint64_t perPartDraws = (uint64_t)prt->trngPosNum * fp * (mm + 1);
 	auto skipDraws = [&](uint64_t count) { r->discard(count); };      // keep the one SMOTE stream in partition order on every rank
 	{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * first); }
@@ -811,8 +819,10 @@ void hyperSMURF::runFold(uint32_t currentFold, uint32_t first, uint32_t last, De
 		SamplerKNN samp(prt, wmode, d, mm, nn, k, r);                   // :275
 		samp.setPartitionRange(b0, b1);                                 // :276
 		samp.sample();                                                  // :277
+		trace_mark("  batch [" + std::to_string(b0) + "," + std::to_string(b1) + ") sampled");
 		rfRanger rf(d, mm, false, &samp, numTrees, mtry, commonParams->rfThr, seed + currentFold * nPart);   // :273,302
 		{ PhaseScope ps(PH_TRAIN); rf.train(commonParams->rfVerbose); }   // :303
+		trace_mark("  trained");
 		if (wmode == MODE_TRAIN) {                                      // :349-360 training only: one forest file per partition
 			for (uint32_t p = b0; p < b1; p++) rf.saveForest(p, commonParams->forestDirname);
 			continue;
@@ -820,6 +830,7 @@ void hyperSMURF::runFold(uint32_t currentFold, uint32_t first, uint32_t last, De
 		samp.copyTestSet();                                             // :316
 		rfRanger rfTest(d, mm, true, &samp, numTrees, mtry, commonParams->rfThr, 2 * (seed + currentFold * nPart));   // :330
 		{ PhaseScope ps(PH_PREDICT); rfTest.predict(commonParams->rfVerbose); d->check(psm_sync(d->ctx)); }   // :331
+		trace_mark("  predicted");
 		samp.accumulateAndDivideResInProbVect(nPart);                   // :344-346 (done on the device by predict)
 	}
 	{ PhaseScope ps(PH_DRAWS); skipDraws(perPartDraws * (nPart - last)); }
@@ -1141,6 +1152,16 @@ void psmh_set_fold_lanes(uint32_t lanes) { g_foldLanes = lanes; }
 // back to the default), otherwise PSM_SHARD=unit|fold, otherwise unit sharding.
 static std::atomic<int> g_shardUnits{-1};
 void psmh_set_shard_units(int v) { g_shardUnits = v; }
+// hyperSMURF::scoresOnRootOnly of the CV entry points (multi-rank runs: only rank 0 fetches the final score arrays)
+static std::atomic<int> g_scoresRootOnly{0};
+void psmh_set_scores_root_only(int v) { g_scoresRootOnly = v; }
+// NCCL inside the library (psm_comm_*): 128-byte id from one rank, then a collective init on every rank's device handle
+int psmh_comm_unique_id(void* id128) { return psm_comm_unique_id(id128); }
+int psmh_device_comm_init(void* devHandle, const void* id128, uint32_t rank, uint32_t world, char* errbuf, size_t errlen) {
+	try { ((parsmurf::Device*)devHandle)->commInit(id128, rank, world); return 0; }
+	catch (const std::exception& e) { if (errbuf && errlen) { strncpy(errbuf, e.what(), errlen - 1); errbuf[errlen - 1] = 0; } return -1; }
+}
+int psmh_device_comm_info(void* devHandle, uint32_t* rank, uint32_t* world, int* ncclVersion) { return psm_comm_info(((parsmurf::Device*)devHandle)->ctx, rank, world, ncclVersion); }
 static bool shard_units_default() {
 	const int v = g_shardUnits.load();
 	if (v >= 0) return v != 0;
@@ -1210,7 +1231,13 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		smurfer.shardUnits = shard_units_default();
 		smurfer.deviceFolds = getenv("PSM_HOST_FOLDS") == nullptr;
 		smurfer.scoresAreOutputs = mode == MODE_CV;          // class1 / class2 of psmh_cv_run are outputs
-		if (world > 1) smurfer.setSharding(rank, world, [&](double* p, uint64_t c) { if (reduce && reduce(reduceUser, p, c)) throw Error(PSM_E_CUDA, "reduce callback failed"); });
+		// the cross-rank sum: the caller's callback if it gave one, else the library's own NCCL communicator (Device::commInit)
+		if (world > 1 && !reduce && !dev.hasComm()) throw Error(PSM_E_ARG, "multi-rank run without a reduce callback: initialise the device's communicator first (psmh_device_comm_init)");
+		if (world > 1) smurfer.setSharding(rank, world, [&](double* p, uint64_t c) {
+			if (!reduce) { dev.allReduce(p, c); return; }
+			if (reduce(reduceUser, p, c)) throw Error(PSM_E_CUDA, "reduce callback failed");
+		});
+		smurfer.scoresOnRootOnly = g_scoresRootOnly.load() != 0;
 		smurfer.initStandard();                             // starts the per-fold index builders in the background ...
 		tSetup = now_s();
 		if (x_is_device) dev.attachDevice(x, n, m); else dev.upload(x, n, m);   // ... which overlap the H2D copy of x
@@ -1311,7 +1338,11 @@ int psmh_cv_grid_run_ex(const double* x, int x_is_device, uint32_t n, uint32_t m
 		smurfer.foldLanes = lanes;
 		smurfer.shardUnits = shard_units_default();
 		smurfer.deviceFolds = getenv("PSM_HOST_FOLDS") == nullptr;
-		if (world > 1) smurfer.setSharding(rank, world, [&](double* p, uint64_t c) { if (reduce && reduce(reduceUser, p, c)) throw Error(PSM_E_CUDA, "reduce callback failed"); });
+		if (world > 1 && !reduce && !dev.hasComm()) throw Error(PSM_E_ARG, "multi-rank run without a reduce callback: initialise the device's communicator first (psmh_device_comm_init)");
+		if (world > 1) smurfer.setSharding(rank, world, [&](double* p, uint64_t c) {
+			if (!reduce) { dev.allReduce(p, c); return; }
+			if (reduce(reduceUser, p, c)) throw Error(PSM_E_CUDA, "reduce callback failed");
+		});
 		smurfer.initStandard();
 		if (x_is_device) dev.attachDevice(x, n, m); else dev.upload(x, n, m);
 		smurfer.smurfIt();

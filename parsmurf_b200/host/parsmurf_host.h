@@ -172,6 +172,12 @@ public:
 	void ensureKnn(uint32_t k);
 	void invalidateFold() { foldTag = nullptr; }
 	void check(int rc) const;
+	// cross-rank communicator of this GPU (NCCL inside the library, psm_comm_init): id128 from commUniqueId() of one rank,
+	// handed to the others by the host's own bootstrap.  allReduce sums `count` doubles at `dev_ptr` over the ranks, in place.
+	static void commUniqueId(void* id128);
+	void commInit(const void* id128, uint32_t rank, uint32_t world);
+	bool hasComm() const;
+	void allReduce(double* dev_ptr, uint64_t count);
 	// fold lanes: lane 0 is this context; lanes 1.. are extra contexts on the same GPU with private streams, created on
 	// demand and kept for the life of the Device (their buffers are reused like this one's)
 	void setLaneCount(uint32_t lanes);
@@ -302,6 +308,10 @@ public:
 	// class1Prob / class2Prob are pure outputs of this run (nothing to accumulate onto): the final fetch overwrites them, so
 	// the caller need not zero them (the reference's main() zero-fills and every partition adds, src/parSMURF.cpp:90-93)
 	bool scoresAreOutputs = false;
+	// multi-rank runs: only rank 0 copies the final class1Prob / class2Prob to its host arrays, like the master of the
+	// reference's MPI build, which alone holds and writes the predictions (src/hyperSMURF_MPI.cpp:594-646, src/parSMURFn.cpp);
+	// the other ranks' arrays are left untouched.  false: every rank fetches them (2n doubles over PCIe per rank).
+	bool scoresOnRootOnly = false;
 	std::vector<double> foldAuroc, foldAuprc;
 	double auroc = 0, auprc = 0;
 	// curvesTieMode 2 ("auto", psm_curves_info): over all the curves calls of this run, the adjacent (equal score, different

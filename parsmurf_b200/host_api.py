@@ -32,6 +32,11 @@ def hlib():
         L.psmh_device_create.restype = vp
         L.psmh_device_create.argtypes = [C.c_int, vp]
         L.psmh_device_destroy.argtypes = [vp]
+        L.psmh_set_scores_root_only.argtypes = [C.c_int]
+        L.psmh_set_scores_root_only.restype = None
+        L.psmh_comm_unique_id.argtypes = [vp]
+        L.psmh_device_comm_init.argtypes = [vp, vp, u32, u32, C.c_char_p, C.c_size_t]
+        L.psmh_device_comm_info.argtypes = [vp, u32p, u32p, C.POINTER(C.c_int)]
         L.psmh_cv_grid_run.argtypes = [dp, u32, u32, u32p, u32p, u32, u32p, u32, u32, C.c_int, C.c_int, dp, dp, dp, dp, C.c_char_p, C.c_size_t]
         L.psmh_rand_fill.argtypes = [u32, i32p, u64]
         L.psmh_ttd_fold.argtypes = [u32p, u32p, u32, u32, u32, C.c_int64, u32p, u32p, u32p, u32p, u32p]
@@ -42,7 +47,7 @@ def hlib():
 
 def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, device=0, stream=None, tie_mode=0, eval_fold_curves=True,
            rank=0, world=1, reduce=None, batch_budget=0, profile=False, x_device_ptr=None, n=None, m=None, dev_handle=None, out=None,
-           fold_lanes=None, shard=None):
+           fold_lanes=None, shard=None, scores_root_only=False):
     """Run the whole CV on one GPU (or this rank's share of the partitions when world > 1).
 
     x: host row-major float64 [n][m+1] (label column 1.0/2.0), or None with x_device_ptr/n/m for a dataset already in HBM.
@@ -56,10 +61,14 @@ def cv_run(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, seed, d
     `reduce` is called once for the summed score arrays [2n] and once for the per-fold metrics [2 nFolds]; "fold" -- the
     reference's MPI rule: every rank takes its chunk of every fold's partitions, `reduce` is called once per fold [2 Nte].
     None keeps the library default (PSM_SHARD or "unit").
+    reduce=None with world > 1: the sum goes through the library's own NCCL communicator (HostDevice.comm_init first).
+    scores_root_only (world > 1): only rank 0 copies the final class1/class2 arrays to the host, like the master of the
+    reference's MPI build; on the other ranks the returned arrays are not written.
     Returns dict(class1, class2, auroc, auprc, fold_metrics, kernel_ms, kernel_launches, stats)."""
     L = hlib()
     L.psmh_set_fold_lanes(0 if fold_lanes is None else int(fold_lanes))
     L.psmh_set_shard_units(-1 if shard is None else {"unit": 1, "fold": 0}[shard])
+    L.psmh_set_scores_root_only(1 if scores_root_only else 0)
     if x is not None:
         assert x.dtype == np.float64 and x.flags.c_contiguous
         n, m = x.shape[0], x.shape[1] - 1
@@ -201,6 +210,27 @@ class HostDevice:
 
     def cv_run(self, *a, **kw):
         return cv_run(*a, dev_handle=self.h, **kw)
+
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id (bytes): call on one rank, hand to the others (torch.distributed broadcast, MPI, a file ...)"""
+        buf = C.create_string_buffer(128)
+        if hlib().psmh_comm_unique_id(C.cast(buf, vp)) != 0:
+            raise PsmError(-1, "NCCL is not available (libnccl.so.2 could not be loaded)")
+        return buf.raw
+
+    def comm_init(self, id128, rank, world):
+        """collective: joins this GPU to the library's NCCL communicator; cv_run(..., world > 1, reduce=None) then sums through it"""
+        assert len(id128) == 128
+        err = C.create_string_buffer(512)
+        buf = C.create_string_buffer(bytes(id128), 128)
+        if hlib().psmh_device_comm_init(self.h, C.cast(buf, vp), rank, world, err, 512) != 0:
+            raise PsmError(-1, err.value.decode())
+
+    def comm_info(self):
+        r = np.zeros(1, np.uint32); w = np.zeros(1, np.uint32); v = C.c_int(0)
+        hlib().psmh_device_comm_info(self.h, _p(r, u32p), _p(w, u32p), C.byref(v))
+        return dict(rank=int(r[0]), world=int(w[0]), nccl_version=int(v.value))
 
     def cv_grid_run(self, *a, **kw):
         return cv_grid_run(*a, dev_handle=self.h, **kw)
