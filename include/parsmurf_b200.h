@@ -79,6 +79,14 @@ int psm_fold_begin(psm_ctx* ctx, const uint32_t* trngPosIdx, uint32_t trngPosNum
 int psm_folds_upload(psm_ctx* ctx, uint32_t nFolds, const uint32_t* posList, const uint32_t* posOff, const uint32_t* negList,
                      const uint32_t* negOff);
 int psm_folds_attach(psm_ctx* ctx, psm_ctx* src);
+/* The per-class fold lists of Folds::computeFolds' "folds from a file" branch (src/folds.cpp:79-117) built on the device from
+ * the per-example fold ids: one stable two-pass radix sort of the example ids by (class, fold), so every fold keeps ascending
+ * example order, positives and negatives apart -- what psm_folds_upload would have been given.  Needs psm_labels_upload first
+ * (labels > 0 = positive).  fold_ids (host, [n]) stay resident and are uploaded again only when they change; the lists are
+ * rebuilt on every call.  nPos / nNeg [nFolds] receive the fold sizes; psm_folds_download copies the lists to the host
+ * (posList [sum nPos], negList [sum nNeg]) for callers that still want them (inner CVs, train mode). */
+int psm_folds_build_device(psm_ctx* ctx, const uint32_t* fold_ids, uint32_t nFolds, uint32_t* nPos, uint32_t* nNeg);
+int psm_folds_download(psm_ctx* ctx, uint32_t* posList, uint32_t* negList);
 int psm_fold_begin_device(psm_ctx* ctx, uint32_t fold, const uint32_t* shuffle_window31);
 int psm_fold_indices_get(psm_ctx* ctx, uint32_t* sizes4, uint32_t* trngPos, uint32_t* trngNeg, uint32_t* testPos, uint32_t* testNeg);
 int psm_scores_fold_curves_device(psm_ctx* ctx, uint32_t fold, int tie_mode, double* out);

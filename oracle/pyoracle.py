@@ -115,6 +115,8 @@ def ref_lib():
         L.ref_mode_train.argtypes = [dp, u32, u32, u32p] + [u32] * 9 + [C.c_char_p, C.c_int]
         L.ref_config_parse.argtypes = [C.c_char_p, u32p, u32p, u32]
         L.ref_num_procs.restype = C.c_int
+        L.ref_generate_random_set.argtypes = [u32, u32, C.c_double, u32, dp, u32p]
+        L.ref_generate_random_set.restype = None
         _ref = L
     return _ref
 
@@ -259,6 +261,14 @@ def o_cv_ranges(x, labels, folds, nFolds, nParts, fp, ratio, k, nTrees, mtry, se
 
 
 # --------------------------------------------------------------------------- reference API
+def ref_generate_random_set(n, m, prob, seed):
+    """the reference's generateRandomSet (src/HyperSMURFUtils.cpp:40-63)"""
+    L = ref_lib()
+    x = np.empty((n, m + 1)); y = np.empty(n, np.uint32)
+    L.ref_generate_random_set(n, m, prob, seed, _p(x, dp), _p(y, u32p))
+    return x, y
+
+
 def ref_import(data_file, label_file, fold_file=None):
     """the reference's Importer::import -> (x flat with the label column appended per row, y, f, nFolds)"""
     L = ref_lib()

@@ -485,4 +485,13 @@ void ref_save(const double* c1, const double* c2, uint32_t n, const uint32_t* la
 	saveToFile(c1, c2, n, &lab, path);
 }
 
+// generateRandomSet (src/HyperSMURFUtils.cpp:40-63), the simulated data set of cfgEx/simulCV.json: x row-major [n][m+1], y [n]
+void ref_generate_random_set(uint32_t n, uint32_t m, double prob, uint32_t seed, double* x, uint32_t* y) {
+	std::vector<double> xx((size_t)n * (m + 1));
+	std::vector<uint32_t> yy(n);
+	generateRandomSet(n, m, xx, yy, prob, seed);
+	memcpy(x, xx.data(), xx.size() * sizeof(double));
+	memcpy(y, yy.data(), yy.size() * sizeof(uint32_t));
+}
+
 }  // extern "C"

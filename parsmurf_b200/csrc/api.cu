@@ -62,13 +62,15 @@ struct psm_ctx {
 
 	// folds on the device (psm_folds_upload): examples of every fold by class; shuffle scratch
 	DevBuf dPosList, dNegList, sKeysA, sKeysB, sValsA, sValsB, sHist, sJ, sDraws, sIn;
+	DevBuf fbKeysA, fbKeysB, fbValsA, fbValsB, fbHist, fbCounts, dFoldIds;   // psm_folds_build_device
+	std::vector<uint32_t> hFoldIds;    // the fold ids resident in dFoldIds
 	const uint32_t* fPos = nullptr;    // device lists (own buffers or another context's, psm_folds_attach)
 	const uint32_t* fNeg = nullptr;
 	std::vector<uint32_t> fPosOff, fNegOff;
 	bool foldFromLists = false;        // the open fold was built by psm_fold_begin_device (no host copy of the test ids)
 
 	// batch
-	bool batchOpen = false, assembled = false, trained = false;
+	bool batchOpen = false, assembled = false, trained = false, inbagValid = false;
 	uint32_t nParts = 0, fp = 0, ratio = 0, p0 = 0, p1 = 0, nB = 0, maxNtr = 0;
 	std::vector<PartDesc> hParts;
 	uint64_t totalD = 0, totalS = 0, totalDraws = 0;
@@ -203,7 +205,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	if (!ctx) return PSM_E_ARG;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	DevBuf* bufs[] = {&ctx->dPosList, &ctx->dNegList, &ctx->sKeysA, &ctx->sKeysB, &ctx->sValsA, &ctx->sValsB, &ctx->sHist, &ctx->sJ, &ctx->sDraws, &ctx->sIn, &ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dKnnTc, &ctx->dClass12,
+	DevBuf* bufs[] = {&ctx->fbKeysA, &ctx->fbKeysB, &ctx->fbValsA, &ctx->fbValsB, &ctx->fbHist, &ctx->fbCounts, &ctx->dFoldIds, &ctx->dPosList, &ctx->dNegList, &ctx->sKeysA, &ctx->sKeysB, &ctx->sValsA, &ctx->sValsB, &ctx->sHist, &ctx->sJ, &ctx->sDraws, &ctx->sIn, &ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dKnnTc, &ctx->dClass12,
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
 	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dSplitFeat, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1, &ctx->dCls,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dPtask, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
@@ -267,7 +269,8 @@ int psm_dataset_upload(psm_ctx* ctx, const double* x_host, uint32_t n, uint32_t 
 	ctx->x = ctx->xOwned.as<double>();
 	ctx->n = n; ctx->m = m;
 	ctx->foldOpen = ctx->batchOpen = false;
-	ctx->haveLabels = false;   // a new dataset copy: its labels are uploaded again too (psm_labels_upload keeps them otherwise)
+	ctx->haveLabels = false;   // a new dataset copy: its labels and fold ids are uploaded again too (kept resident otherwise)
+	ctx->hFoldIds.clear();
 	return PSM_OK;
 }
 
@@ -284,7 +287,6 @@ int psm_fold_begin(psm_ctx* ctx, const uint32_t* trngPosIdx, uint32_t P, const u
 	if (!ctx || !ctx->x) return fail(ctx, PSM_E_ARG, "fold_begin: no dataset");
 	if ((P && !trngPosIdx) || (Nneg && !trngNegIdx) || (nTP && !testPosIdx) || (nTN && !testNegIdx)) return fail(ctx, PSM_E_ARG, "fold_begin: null index array");
 	CU(cudaSetDevice(ctx->device));
-	for (uint32_t i = 0; i < P; i++) if (trngPosIdx[i] >= ctx->n) return fail(ctx, PSM_E_ARG, "fold_begin: index out of range");
 	ctx->P = P; ctx->Nneg = Nneg; ctx->nTP = nTP; ctx->nTN = nTN; ctx->Nte = nTP + nTN;
 	ctx->haveKnn = false; ctx->batchOpen = false; ctx->localk = 0; ctx->foldLabelsReady = false;
 	ENSURE(ctx->dPos, std::max<size_t>(4, (size_t)P * 4));
@@ -299,7 +301,16 @@ int psm_fold_begin(psm_ctx* ctx, const uint32_t* trngPosIdx, uint32_t P, const u
 	if (Nneg) CU(cudaMemcpyAsync(ctx->dNeg.p, trngNegIdx, (size_t)Nneg * 4, cudaMemcpyHostToDevice, ctx->stream));
 	if (ctx->Nte) CU(cudaMemcpyAsync(ctx->dTest.p, ctx->hTestIdx.data(), (size_t)ctx->Nte * 4, cudaMemcpyHostToDevice, ctx->stream));
 	CU(cudaMemsetAsync(ctx->dClass12.p, 0, std::max<size_t>(16, (size_t)ctx->Nte * 16), ctx->stream));
+	// every id of all four arrays must name an example: they index x in the assemble / predict kernels and the score arrays
+	ENSURE(ctx->dErr, 16);
+	uint32_t bad = 0;
+	CU(cudaMemsetAsync(ctx->dErr.as<uint32_t>() + 3, 0, 4, ctx->stream));
+	launch_check_ids(ctx->dPos.as<uint32_t>(), P, ctx->n, ctx->dErr.as<uint32_t>() + 3, ctx->stream);
+	launch_check_ids(ctx->dNeg.as<uint32_t>(), Nneg, ctx->n, ctx->dErr.as<uint32_t>() + 3, ctx->stream);
+	launch_check_ids(ctx->dTest.as<uint32_t>(), ctx->Nte, ctx->n, ctx->dErr.as<uint32_t>() + 3, ctx->stream);
+	CU(cudaMemcpyAsync(&bad, ctx->dErr.as<uint32_t>() + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	if (bad) { ctx->foldOpen = false; return fail(ctx, PSM_E_ARG, "fold_begin: index out of range"); }
 	ctx->foldOpen = true; ctx->foldFromLists = false;
 	return PSM_OK;
 }
@@ -314,10 +325,82 @@ int psm_folds_upload(psm_ctx* ctx, uint32_t nFolds, const uint32_t* posList, con
 	ENSURE(ctx->dNegList, std::max<size_t>(4, (size_t)totNeg * 4));
 	if (totPos) CU(cudaMemcpyAsync(ctx->dPosList.p, posList, (size_t)totPos * 4, cudaMemcpyHostToDevice, ctx->stream));
 	if (totNeg) CU(cudaMemcpyAsync(ctx->dNegList.p, negList, (size_t)totNeg * 4, cudaMemcpyHostToDevice, ctx->stream));
+	ENSURE(ctx->dErr, 16);
+	uint32_t bad = 0;
+	CU(cudaMemsetAsync(ctx->dErr.as<uint32_t>() + 3, 0, 4, ctx->stream));
+	launch_check_ids(ctx->dPosList.as<uint32_t>(), totPos, ctx->n, ctx->dErr.as<uint32_t>() + 3, ctx->stream);
+	launch_check_ids(ctx->dNegList.as<uint32_t>(), totNeg, ctx->n, ctx->dErr.as<uint32_t>() + 3, ctx->stream);
+	CU(cudaMemcpyAsync(&bad, ctx->dErr.as<uint32_t>() + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));   // the host lists are only borrowed
+	if (bad) { ctx->fPos = ctx->fNeg = nullptr; return fail(ctx, PSM_E_ARG, "folds_upload: example id out of range"); }
 	ctx->fPos = ctx->dPosList.as<uint32_t>(); ctx->fNeg = ctx->dNegList.as<uint32_t>();
 	ctx->fPosOff.assign(posOff, posOff + nFolds + 1); ctx->fNegOff.assign(negOff, negOff + nFolds + 1);
 	ctx->foldOpen = false;
+	return PSM_OK;
+}
+
+// equality of two u32 arrays, a few host threads on large inputs (14M ids at BASELINE configs[2]: one thread needs ~5 ms)
+static bool same_u32(const uint32_t* a, const uint32_t* b, size_t n) {
+	if (n < (1u << 20)) return memcmp(a, b, n * 4) == 0;
+	const unsigned nT = 4;
+	std::atomic<bool> same(true);
+	std::vector<std::thread> th;
+	for (unsigned t = 0; t < nT; t++)
+		th.emplace_back([&, t]() { const size_t lo = n * t / nT, hi = n * (t + 1) / nT; if (memcmp(a + lo, b + lo, (hi - lo) * 4) != 0) same = false; });
+	for (auto& x : th) x.join();
+	return same;
+}
+
+int psm_folds_build_device(psm_ctx* ctx, const uint32_t* fold_ids, uint32_t nFolds, uint32_t* nPos, uint32_t* nNeg) {
+	if (!ctx || !ctx->x || !ctx->haveLabels || !fold_ids || nFolds == 0 || !nPos || !nNeg) return fail(ctx, PSM_E_ARG, "folds_build_device: need the dataset, the labels and the fold ids");
+	if (2ull * nFolds > 2048) return fail(ctx, PSM_E_LIMIT, "folds_build_device: more than 1024 folds");
+	CU(cudaSetDevice(ctx->device));
+	const uint32_t n = ctx->n;
+	cudaStream_t s = ctx->stream;
+	if (!(ctx->hFoldIds.size() == n && same_u32(ctx->hFoldIds.data(), fold_ids, n))) {
+		ctx->hFoldIds.assign(fold_ids, fold_ids + n);
+		ENSURE(ctx->dFoldIds, (size_t)n * 4);
+		CU(cudaMemcpyAsync(ctx->dFoldIds.p, ctx->hFoldIds.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+	}
+	const uint64_t rBlocks = ((uint64_t)n + 4095) / 4096;
+	ENSURE(ctx->fbKeysA, (size_t)n * 8); ENSURE(ctx->fbKeysB, (size_t)n * 8);
+	ENSURE(ctx->fbValsA, (size_t)n * 4); ENSURE(ctx->fbValsB, (size_t)n * 4);
+	ENSURE(ctx->fbHist, (rBlocks + 1) * 256 * 4);
+	ENSURE(ctx->fbCounts, (size_t)(2 * nFolds + 1) * 4);
+	uint32_t* counts = ctx->fbCounts.as<uint32_t>();
+	CU(cudaMemsetAsync(counts, 0, (size_t)(2 * nFolds + 1) * 4, s));
+	{
+		ProfScope ps(ctx, K_GATHER, 1 + 3 * 2);
+		launch_fold_keys(ctx->dLabels.as<uint32_t>(), ctx->dFoldIds.as<uint32_t>(), n, nFolds, ctx->fbKeysA.as<unsigned long long>(), ctx->fbValsA.as<uint32_t>(), counts,
+		                 counts + 2 * nFolds, s);
+		if (launch_radix_sort_u64(ctx->fbKeysA.as<unsigned long long>(), ctx->fbKeysB.as<unsigned long long>(), ctx->fbValsA.as<uint32_t>(), ctx->fbValsB.as<uint32_t>(), n, 2,
+		                          ctx->fbHist.as<uint32_t>(), s))
+			return fail(ctx, PSM_E_CUDA, "folds_build_device: sort launch failed");
+	}
+	std::vector<uint32_t> hc(2 * nFolds + 1);
+	CU(cudaMemcpyAsync(hc.data(), counts, hc.size() * 4, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	if (hc[2 * nFolds]) { ctx->fPos = ctx->fNeg = nullptr; return fail(ctx, PSM_E_ARG, "folds_build_device: fold id out of range"); }
+	ctx->fPosOff.assign(nFolds + 1, 0); ctx->fNegOff.assign(nFolds + 1, 0);
+	for (uint32_t f = 0; f < nFolds; f++) {
+		nPos[f] = hc[f]; nNeg[f] = hc[nFolds + f];
+		ctx->fPosOff[f + 1] = ctx->fPosOff[f] + nPos[f];
+		ctx->fNegOff[f + 1] = ctx->fNegOff[f] + nNeg[f];
+	}
+	// sorted by (class, fold), example ids ascending inside every key: the positives' lists, then the negatives'
+	ctx->fPos = ctx->fbValsA.as<uint32_t>();
+	ctx->fNeg = ctx->fbValsA.as<uint32_t>() + ctx->fPosOff[nFolds];
+	ctx->foldOpen = false;
+	return PSM_OK;
+}
+
+int psm_folds_download(psm_ctx* ctx, uint32_t* posList, uint32_t* negList) {
+	if (!ctx || !ctx->fPos || ctx->fPosOff.empty()) return fail(ctx, PSM_E_ARG, "folds_download: no device fold lists");
+	CU(cudaSetDevice(ctx->device));
+	const size_t tp = ctx->fPosOff.back(), tn = ctx->fNegOff.back();
+	if (posList && tp) CU(cudaMemcpyAsync(posList, ctx->fPos, tp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (negList && tn) CU(cudaMemcpyAsync(negList, ctx->fNeg, tn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
 	return PSM_OK;
 }
 
@@ -698,6 +781,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 
 	int buf = 0;
 	uint64_t levels = 0;
+	unsigned long long tracePrevBytes = 0;   // PSM_TRACE_LEVELS: split bytes up to the previous level (per call: fold lanes train concurrently)
 	// The next level's item count is read back right after level_finalize and BEFORE the list partition is queued, and the
 	// host waits on an event instead of the stream: the round trip (copy, wake-up, five launches) overlaps the partition
 	// kernel of the level that is still running instead of leaving the GPU idle between levels.
@@ -744,8 +828,8 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 			for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
 			unsigned long long hs2[STAT_COUNT];
 			cudaMemcpy(hs2, A.stats, STAT_COUNT * 8, cudaMemcpyDeviceToHost);
-			static unsigned long long prevBytes = 0;
-			if (levels == 0) prevBytes = 0;
+			if (levels == 0) tracePrevBytes = 0;
+			unsigned long long& prevBytes = tracePrevBytes;
 			const unsigned long long samples = (hs2[STAT_SPLIT_BYTES] - prevBytes) / ((unsigned long long)mtry * 8ull + 8ull);
 			prevBytes = hs2[STAT_SPLIT_BYTES];
 			fprintf(stderr, "[psm level %3llu] items %7u samples %9llu  search %8.1f us  select %7.1f us  finalize %7.1f us  partition %8.1f us\n",
@@ -768,7 +852,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		ctx->maxNodes = 0;
 		for (const TreeState& t : hts) ctx->maxNodes = std::max(ctx->maxNodes, t.nNodes);
 	}
-	ctx->trained = true;
+	ctx->trained = true; ctx->inbagValid = true;
 	return PSM_OK;
 }
 
@@ -786,6 +870,7 @@ static int fetch_tree(psm_ctx* ctx, uint32_t p, uint32_t t, TreeState* ts, std::
 }
 
 int psm_batch_tree_nodes(psm_ctx* ctx, uint32_t p, uint32_t t, uint64_t* nNodes) {
+	if (!nNodes) return fail(ctx, PSM_E_ARG, "tree_nodes: null output");
 	TreeState ts;
 	int rc = fetch_tree(ctx, p, t, &ts, nullptr);
 	if (rc) return rc;
@@ -860,11 +945,13 @@ int psm_batch_import_forests(psm_ctx* ctx, uint32_t p0, uint32_t p1, uint32_t T,
 	A.nodes = ctx->dNodes.as<Node16>(); A.ts = ctx->dTs.as<TreeState>(); A.NC = NC; A.nTrees = nTrees; A.T = T;
 	ctx->nB = nB; ctx->p0 = p0; ctx->p1 = p1; ctx->T = T; ctx->maxNodes = (uint32_t)maxN;
 	ctx->batchOpen = false; ctx->assembled = false; ctx->trained = true;
+	ctx->inbagValid = false;   // imported forests carry no bootstrap counts (psm_batch_get_inbag refuses)
 	return PSM_OK;
 }
 
 int psm_batch_get_inbag(psm_ctx* ctx, uint32_t p, uint32_t t, uint32_t* counts) {
-	if (!ctx || !ctx->trained || p < ctx->p0 || p >= ctx->p1 || t >= ctx->T || !counts) return fail(ctx, PSM_E_ARG, "get_inbag: no such trained tree");
+	if (!ctx || !ctx->trained || !ctx->inbagValid || p < ctx->p0 || p >= ctx->p1 || t >= ctx->T || !counts || (size_t)(p - ctx->p0) >= ctx->hParts.size())
+		return fail(ctx, PSM_E_ARG, "get_inbag: no such tree trained in this context (imported forests have no bootstrap counts)");
 	const size_t tree = (size_t)(p - ctx->p0) * ctx->T + t;
 	CU(cudaMemcpyAsync(counts, ctx->A.inbag + tree * ctx->A.stride, (size_t)ctx->hParts[p - ctx->p0].Ntr * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
@@ -1101,7 +1188,7 @@ int psm_labels_upload(psm_ctx* ctx, const uint32_t* labels, uint32_t n) {
 	CU(cudaMemsetAsync(ctx->dGlob.p, 0, (size_t)n * 16, ctx->stream));
 	// a host that runs one CV after the other hands in the same labels every time: the device copy and the class totals are
 	// kept when the vector is unchanged (one memcmp instead of a host copy, an H2D copy and two O(n) counting passes per CV)
-	if (ctx->haveLabels && ctx->hLabels.size() == n && memcmp(ctx->hLabels.data(), labels, (size_t)n * 4) == 0) return PSM_OK;
+	if (ctx->haveLabels && ctx->hLabels.size() == n && same_u32(ctx->hLabels.data(), labels, n)) return PSM_OK;
 	ctx->haveLabels = false;
 	ctx->hLabels.assign(labels, labels + n);
 	ENSURE(ctx->dLabels, (size_t)n * 4);

@@ -10,6 +10,8 @@
 // scan (TP) -> per-element trapezoid terms -> deterministic two-level fp64 reduction.  HBM-bound byte work.
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace psm {
 
 constexpr int CB = 256;          // threads
@@ -34,6 +36,16 @@ __global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32
 void launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint64_t N, uint32_t* out, cudaStream_t s) {
 	if (!N) return;
 	gather_u32_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(src, idx, N, out);
+}
+// example ids handed in through the C ABI: *bad becomes non-zero if any id is >= n (checked on the device: the arrays are
+// already there, and a host loop over the 14M ids of BASELINE configs[2] would cost more than the fold set-up itself)
+__global__ void check_ids_kernel(const uint32_t* __restrict__ ids, uint64_t N, uint32_t n, uint32_t* __restrict__ bad) {
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < N && ids[i] >= n) atomicOr(bad, 1u);
+}
+void launch_check_ids(const uint32_t* ids, uint64_t N, uint32_t n, uint32_t* bad, cudaStream_t s) {
+	if (!N) return;
+	check_ids_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(ids, N, n, bad);
 }
 __global__ void gather_f64_kernel(const double* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t N, double* __restrict__ out) {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,6 +384,33 @@ int launch_sort_scores_desc_labelties(const double* scores, const uint32_t* labe
 		uint32_t* tv = vin; vin = vout; vout = tv;
 	}
 	return 0;
+}
+
+// (class, fold) key of every example for the device-built fold lists (psm_folds_build_device); the per-key counts go through
+// shared memory (2 * nFolds <= FK_BINS bins)
+constexpr uint32_t FK_BINS = 2048;
+__global__ void __launch_bounds__(256) fold_keys_kernel(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ foldIds, uint32_t n, uint32_t nFolds,
+                                                         unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ counts,
+                                                         uint32_t* __restrict__ bad) {
+	__shared__ uint32_t h[FK_BINS];
+	const uint32_t K = 2 * nFolds;
+	for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) h[k] = 0;
+	__syncthreads();
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		uint32_t f = foldIds[i];
+		if (f >= nFolds) { atomicOr(bad, 1u); f = 0; }
+		const uint32_t key = (labels[i] > 0 ? 0u : nFolds) + f;
+		keys[i] = key; vals[i] = i;
+		atomicAdd(&h[key], 1u);
+	}
+	__syncthreads();
+	for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) if (h[k]) atomicAdd(&counts[k], h[k]);
+}
+void launch_fold_keys(const uint32_t* labels, const uint32_t* foldIds, uint32_t n, uint32_t nFolds, unsigned long long* keys, uint32_t* vals, uint32_t* counts,
+                      uint32_t* bad, cudaStream_t s) {
+	if (!n) return;
+	const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)n + 4095) / 4096, 148 * 8);
+	fold_keys_kernel<<<blocks, 256, 0, s>>>(labels, foldIds, n, nFolds, keys, vals, counts, bad);
 }
 
 // generic entry: ascending LSD sort of prefilled (keysA, valsA) on the low 8*passes key bits; passes must be even so that the

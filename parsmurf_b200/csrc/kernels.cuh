@@ -105,6 +105,7 @@ int launch_curves(const unsigned char* labelsSorted, uint64_t N, uint32_t totP, 
                   double* partials, size_t partialsCap, double* out2, cudaStream_t s);
 void launch_tie_mixed_count(const unsigned long long* keysSorted, const unsigned char* labelsSorted, uint64_t N, unsigned long long* counter, cudaStream_t s);
 void launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint64_t N, uint32_t* out, cudaStream_t s);
+void launch_check_ids(const uint32_t* ids, uint64_t N, uint32_t n, uint32_t* bad /*device word, OR-ed*/, cudaStream_t s);
 void launch_gather_f64(const double* src, const uint32_t* idx, uint64_t N, double* out, cudaStream_t s);
 void launch_add_f64(double* dst, const double* src, size_t count, cudaStream_t s);
 void launch_scatter_scores(const double* class12, const uint32_t* testIdx, uint32_t Nte, uint32_t n, double* glob, cudaStream_t s);
@@ -114,6 +115,9 @@ int launch_sort_scores_desc(const double* scores, uint64_t N, unsigned long long
 
 int launch_sort_scores_desc_labelties(const double* scores, const uint32_t* labels, uint64_t N, int posFirst, unsigned long long* keysA,
                                       unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, uint32_t* hist, cudaStream_t s);
+// fold keys: keys[i] = (labels[i] > 0 ? 0 : nFolds) + foldIds[i], vals[i] = i, counts[key]++ (counts zeroed by the caller); *bad |= 1 if a fold id >= nFolds
+void launch_fold_keys(const uint32_t* labels, const uint32_t* foldIds, uint32_t n, uint32_t nFolds, unsigned long long* keys, uint32_t* vals, uint32_t* counts,
+                      uint32_t* bad, cudaStream_t s);
 int launch_radix_sort_u64(unsigned long long* keysA, unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, uint64_t N, int passes,
                           uint32_t* hist, cudaStream_t s);
 // shuffle.cu

@@ -4,6 +4,8 @@
 #include "parsmurf_host.h"
 
 #include <algorithm>
+#include <numeric>
+#include <random>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -200,6 +202,35 @@ void Folds::computeFolds() {
 	}
 	maxPos = *std::max_element(nPos.begin(), nPos.end());
 	maxNeg = *std::max_element(nNeg.begin(), nNeg.end());
+	hostListsValid = true; devBuilt = nullptr;
+}
+
+void Folds::computeFoldsOnDevice(Device* dev) {
+	if (randomFold) throw Error(PSM_E_ARG, "Folds::computeFoldsOnDevice: random folds are generated on the host");
+	if (&fromFile != &noIds) { ids = fromFile.data(); nIds = fromFile.size(); }
+	if (nIds < classSize) throw Error(PSM_E_ARG, "Folds: fold assignment shorter than the label vector");
+	dev->check(psm_folds_build_device(dev->ctx, ids, nFolds, nPos.data(), nNeg.data()));
+	posOff.assign(nFolds + 1, 0); negOff.assign(nFolds + 1, 0);
+	foldsIdx[0] = 0;
+	for (uint32_t f = 0; f < nFolds; f++) {
+		posOff[f + 1] = posOff[f] + nPos[f]; negOff[f + 1] = negOff[f] + nNeg[f];
+		foldsIdx[f + 1] = foldsIdx[f] + nPos[f] + nNeg[f];
+	}
+	totPos = posOff[nFolds]; totNeg = negOff[nFolds];
+	maxPos = *std::max_element(nPos.begin(), nPos.end());
+	maxNeg = *std::max_element(nNeg.begin(), nNeg.end());
+	devBuilt = dev; hostListsValid = false;
+}
+
+void Folds::hostLists() const {
+	std::lock_guard<std::mutex> lk(hostListsMtx);
+	if (hostListsValid) return;
+	if (!devBuilt) throw Error(PSM_E_ARG, "Folds: computeFolds has not run");
+	Folds* self = const_cast<Folds*>(this);
+	self->posList = g_pool.take(totPos); self->posList.resize(totPos);
+	self->negList = g_pool.take(totNeg); self->negList.resize(totNeg);
+	devBuilt->check(psm_folds_download(devBuilt->ctx, self->posList.data(), self->negList.data()));
+	hostListsValid = true;
 }
 
 // ------------------------------------------------------------------------------------------ TestTrainDivider
@@ -208,11 +239,13 @@ static void ttd_blk(std::vector<uint32_t>& dst, const std::vector<uint32_t>& src
 }
 void TestTrainDivider::buildTest(uint32_t i, uint32_t cur) {
 	const Folds* F = folds;
+	F->hostLists();
 	testPosIdx[i] = g_pool.take(F->nPos[cur]); testNegIdx[i] = g_pool.take(F->nNeg[cur]);
 	ttd_blk(testPosIdx[i], F->posList, F->posOff, cur); ttd_blk(testNegIdx[i], F->negList, F->negOff, cur);
 }
 void TestTrainDivider::buildTrain(uint32_t i, uint32_t cur, int64_t jump) {
 	const Folds* F = folds;
+	F->hostLists();
 	const uint32_t jumpPos = jump >= 0 ? F->nPos[jump] : 0, jumpNeg = jump >= 0 ? F->nNeg[jump] : 0;
 	trngPosIdx[i] = g_pool.take(F->totPos - F->nPos[cur] - jumpPos); trngNegIdx[i] = g_pool.take(F->totNeg - F->nNeg[cur] - jumpNeg);
 	for (uint32_t kf = 0; kf < F->nFolds; kf++) {                            // ascending fold order, as src/testtraindivider.cpp:57-80
@@ -364,6 +397,8 @@ void Device::ensureFold(const Partition* part) {
 	foldTag = part->ttd; foldId = part->currentFold; knnK = 0;
 }
 void Device::uploadFolds(const Folds* F) {
+	if (F->builtOn() == this) { foldTag = nullptr; return; }                 // the lists were built here (Folds::computeFoldsOnDevice)
+	F->hostLists();
 	check(psm_folds_upload(ctx, F->nFolds, F->posList.data(), F->posOff.data(), F->negList.data(), F->negOff.data()));
 	foldTag = nullptr;
 }
@@ -561,6 +596,20 @@ rfRanger::TreeExport rfRanger::getTree(uint32_t p, uint32_t t) const {
 	return e;
 }
 
+// ------------------------------------------------------------------------------------------ simulated data
+void generateRandomSet(uint32_t nn, uint32_t mm, std::vector<double>& xx, std::vector<uint32_t>& yy, double prob, uint32_t seed) {
+	std::default_random_engine gen(seed);
+	std::normal_distribution<> neg(0, 1), pos(5, 1);
+	std::bernoulli_distribution lab(prob);
+	yy.resize(nn); xx.resize((size_t)nn * (mm + 1));
+	for (auto& v : yy) v = lab(gen);                                         // all the labels first, then the rows in order
+	for (uint32_t i = 0; i < nn; i++) {
+		double* row = xx.data() + (size_t)i * (mm + 1);
+		for (uint32_t j = 0; j < mm; j++) row[j] = yy[i] > 0 ? pos(gen) : neg(gen);
+		row[mm] = yy[i] > 0 ? 1.0 : 2.0;
+	}
+}
+
 // ------------------------------------------------------------------------------------------ Curves
 Curves::Curves(Device* dev_, const std::vector<uint32_t>& labels, const double* predictions, int tieMode_)
     : dev(dev_), labls(labels), preds(predictions), tieMode(tieMode_) {}
@@ -629,6 +678,7 @@ void hyperSMURF::setGridParams(uint32_t idx) {                              // s
 }
 void hyperSMURF::createPart() { part.reset(new Partition(foldManager, ttd.get(), nPart, fp, ratio, mm, nn)); }
 
+static uint32_t laneMinUnits();
 void hyperSMURF::smurfIt() {                                                // src/hyperSMURF.cpp:151-496 (CV paths)
 	if (wmode == MODE_PREDICT) { predictIt(); return; }                     // :401-446
 	if (wmode != MODE_CV && wmode != MODE_TRAIN) throw Error(PSM_E_ARG, "hyperSMURF::smurfIt: unknown mode");
@@ -652,24 +702,71 @@ void hyperSMURF::smurfIt() {                                                // s
 	for (uint32_t currentFold = startingFold; currentFold < endingFold; currentFold++) {
 		if (woptimiz == OPT_GRID) {                                         // :176-228 grid exploration on the inner folds
 			hyperSMURF inner(commonParams, gridParams, foldManager, dev, y, tempcl1.data(), tempcl2.data(), rng);
-			inner.setSharding(rank, world, reduce);
+			// Multi-rank: the grid points of one outer fold are independent inner CVs, so each rank runs WHOLE inner CVs (its
+			// share of the grid points, balanced by cost) without any communication, and one all-reduce of the [G][2] metric
+			// table -- every entry written by exactly one rank, zeros elsewhere, so the sum is exact -- gives every rank the
+			// table a single rank would have computed.  The one rand() stream the inner CVs draw their SMOTE samples from is
+			// entered at each grid point's own offset (an inner CV consumes sum_f nPart * P_f * fp * (m+1) draws, known up front).
+			const bool shardGrid = shardGridPoints && world > 1 && (bool)reduce;
+			if (shardGrid) inner.setSharding(0, 1, nullptr); else inner.setSharding(rank, world, reduce);
 			inner.curvesTieMode = curvesTieMode;
 			inner.foldLanes = foldLanes;
 			inner.initInternalCV(currentFold);
+			const uint32_t G = (uint32_t)gridParams.size();
+			std::vector<uint64_t> drawOff(G + 1, 0);
+			{
+				uint64_t posSum = 0;
+				for (uint32_t f = 0; f + 1 < nFolds; f++) posSum += inner.ttd->trngPosNum[f];
+				for (uint32_t i = 0; i < G; i++) drawOff[i + 1] = drawOff[i] + (uint64_t)gridParams[i].nParts * posSum * gridParams[i].fp * (mm + 1);
+			}
+			std::vector<uint32_t> owner(G, 0);
+			if (shardGrid) {                                                   // longest-processing-time first; cost ~ partitions x training rows
+				std::vector<uint32_t> order(G);
+				std::iota(order.begin(), order.end(), 0u);
+				auto cost = [&](uint32_t i) { return (uint64_t)gridParams[i].nParts * (gridParams[i].fp + 1) * (gridParams[i].ratio ? gridParams[i].ratio + 1 : 4) * gridParams[i].nTrees; };
+				std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost(a) > cost(b); });
+				std::vector<uint64_t> load(world, 0);
+				for (uint32_t i : order) {
+					const uint32_t r = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+					owner[i] = r; load[r] += cost(i);
+				}
+			}
+			const GlibcRand base = *rng;
+			GlibcRand local = base;
+			if (shardGrid) inner.rng = &local;
 			std::string statFileName = "fold" + std::to_string(currentFold) + ".dat";
-			for (uint32_t i = 0; i < gridParams.size(); i++) {
+			auto statLine = [&](uint32_t i) {
+				std::ofstream tf(statFileName.c_str(), std::ios::app);   // :191-199
+				tf << std::to_string(i) << " " << std::to_string(gridParams[i].nParts) << " " << std::to_string(gridParams[i].fp) << " "
+				   << std::to_string(gridParams[i].ratio) << " " << std::to_string(gridParams[i].k) << " " << std::to_string(gridParams[i].nTrees) << " "
+				   << std::to_string(gridParams[i].mtry) << " " << std::to_string(gridParams[i].auroc) << " " << std::to_string(gridParams[i].auprc) << " "
+				   << std::endl;
+			};
+			for (uint32_t i = 0; i < G; i++) {
+				if (shardGrid) {
+					if (owner[i] != rank) { gridParams[i].auroc = 0; gridParams[i].auprc = 0; continue; }
+					local = base;
+					local.discard(drawOff[i]);
+				}
 				std::fill(tempcl1.begin(), tempcl1.end(), 0.0);
 				std::fill(tempcl2.begin(), tempcl2.end(), 0.0);
 				inner.setGridParams(i);
 				inner.createPart();
 				inner.smurfIt();
-				if (rank == 0) {
-					std::ofstream tf(statFileName.c_str(), std::ios::app);   // :191-199
-					tf << std::to_string(i) << " " << std::to_string(gridParams[i].nParts) << " " << std::to_string(gridParams[i].fp) << " "
-					   << std::to_string(gridParams[i].ratio) << " " << std::to_string(gridParams[i].k) << " " << std::to_string(gridParams[i].nTrees) << " "
-					   << std::to_string(gridParams[i].mtry) << " " << std::to_string(gridParams[i].auroc) << " " << std::to_string(gridParams[i].auprc) << " "
-					   << std::endl;
-				}
+				if (rank == 0 && !shardGrid) statLine(i);
+			}
+			if (shardGrid) {
+				PhaseScope ps(PH_REDUCE);
+				std::vector<double> gm(2 * (size_t)G);
+				for (uint32_t i = 0; i < G; i++) { gm[2 * i] = gridParams[i].auroc; gm[2 * i + 1] = gridParams[i].auprc; }
+				double* sp = nullptr;
+				dev->check(psm_scratch_f64(dev->ctx, 2 * G, &sp));
+				dev->check(psm_scratch_write(dev->ctx, gm.data(), 2 * G));
+				reduce(sp, 2ull * G);
+				dev->check(psm_scratch_read(dev->ctx, gm.data(), 2 * G));
+				for (uint32_t i = 0; i < G; i++) { gridParams[i].auroc = gm[2 * i]; gridParams[i].auprc = gm[2 * i + 1]; if (rank == 0) statLine(i); }
+				*rng = base;
+				rng->discard(drawOff[G]);
 			}
 			// the inner CVs used the device score arrays: start the outer fold from a clean device state (the outer scores of
 			// earlier folds were already added into the host arrays below)
@@ -688,10 +785,10 @@ void hyperSMURF::smurfIt() {                                                // s
 		}
 		if (lanesHere > 1 || unitMode) {
 			uint32_t lanesNow = lanesHere;
-			if (unitMode) {                                                 // a lane is only worth its set-up with ~48 or more partitions of its own
+			if (unitMode) {                                                 // a lane is only worth its set-up with ~16 or more partitions of its own
 				uint64_t mine = 0;
 				for (uint32_t f = startingFold; f < endingFold; f++) { uint32_t a = 0, b = 0; partRange(true, foldsRun, nPart, world, rank, f - foldBase, &a, &b); mine += b - a; }
-				lanesNow = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(mine / 48, 1), std::max<uint32_t>(foldLanes, 1));
+				lanesNow = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(mine / laneMinUnits(), 1), std::max<uint32_t>(foldLanes, 1));
 			}
 			runFoldsInLanes(startingFold, endingFold, lanesNow);
 			trace_mark("lanes joined, scores merged");
@@ -875,6 +972,7 @@ void hyperSMURF::runFold(uint32_t currentFold, uint32_t first, uint32_t last, De
 	}
 }
 
+static uint32_t laneMinUnits() { static const uint32_t v = getenv("PSM_LANE_MIN_UNITS") ? (uint32_t)std::max(1, atoi(getenv("PSM_LANE_MIN_UNITS"))) : 12u; return v; }
 void hyperSMURF::runFoldsInLanes(uint32_t startingFold, uint32_t endingFold, uint32_t lanes) {
 	dev->setLaneCount(lanes);
 	// where every fold starts in the one SMOTE rand() stream: a fold consumes nPart * P_fold * fp * (m+1) draws whatever
@@ -891,7 +989,10 @@ void hyperSMURF::runFoldsInLanes(uint32_t startingFold, uint32_t endingFold, uin
 			partRange(unitMode, foldsRun, nPart, world, rank, f - foldBase, &a, &b);
 			mine += b - a;
 		}
-		const uint32_t maxPiece = unitMode ? (uint32_t)std::max<uint64_t>(32, (mine + lanes - 1) / lanes) : nPart;
+		// pieces: about two per lane, so that the lanes finish together whatever the fold boundaries do to the shares; one per
+		// lane when the share is small (a piece costs a few ms whatever its size: fold set-up and the latency of ~30 tree levels)
+		const uint64_t perLane = (mine + lanes - 1) / lanes;
+		const uint32_t maxPiece = unitMode ? (uint32_t)std::max<uint64_t>(laneMinUnits(), perLane >= 64 ? (perLane + 1) / 2 : perLane) : nPart;
 		for (uint32_t f = startingFold; f < endingFold; f++) {
 			uint32_t a = 0, b = 0;
 			partRange(unitMode, foldsRun, nPart, world, rank, f - foldBase, &a, &b);
@@ -1218,7 +1319,18 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		} yBuf(labels, n);
 		std::vector<uint32_t>& y = yBuf.v;
 		Folds folds(nFolds, n, y.data(), foldAssign, n, foldAssign == nullptr, &rng);   // the fold ids are only borrowed for the call
-		{ PhaseScope ps(PH_FOLDS_TTD); folds.computeFolds(); }
+		// folds from an assignment: the per-class lists are built in HBM (one stable device sort) once the dataset and the labels
+		// are there; random folds are a rand()-driven shuffle and stay on the host
+		const bool foldsOnDev = foldAssign != nullptr && mode == MODE_CV && getenv("PSM_HOST_FOLDS") == nullptr;
+		if (foldsOnDev) {
+			tSetup = now_s();
+			if (x_is_device) dev.attachDevice(x, n, m); else dev.upload(x, n, m);
+			g_phase[PH_SETUP] += now_s() - tSetup;
+			trace_mark("dataset attached");
+			PhaseScope ps(PH_FOLDS_TTD);
+			dev.check(psm_labels_upload(dev.ctx, y.data(), n));
+			folds.computeFoldsOnDevice(&dev);
+		} else { PhaseScope ps(PH_FOLDS_TTD); folds.computeFolds(); }
 		trace_mark("folds computed");
 		CommonParams cp;
 		cp.nn = n; cp.mm = m; cp.nFolds = nFolds; cp.seed = seed; cp.wmode = (uint8_t)mode; cp.woptimiz = OPT_NO;
@@ -1239,10 +1351,12 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 		});
 		smurfer.scoresOnRootOnly = g_scoresRootOnly.load() != 0;
 		smurfer.initStandard();                             // starts the per-fold index builders in the background ...
-		tSetup = now_s();
-		if (x_is_device) dev.attachDevice(x, n, m); else dev.upload(x, n, m);   // ... which overlap the H2D copy of x
-		g_phase[PH_SETUP] += now_s() - tSetup;
-		trace_mark("dataset attached");
+		if (!foldsOnDev) {
+			tSetup = now_s();
+			if (x_is_device) dev.attachDevice(x, n, m); else dev.upload(x, n, m);   // ... which overlap the H2D copy of x
+			g_phase[PH_SETUP] += now_s() - tSetup;
+			trace_mark("dataset attached");
+		}
 		smurfer.smurfIt();
 		trace_mark("smurfIt done");
 		if (g_trace) {
@@ -1377,6 +1491,13 @@ int psmh_cv_grid_run(const double* x, uint32_t n, uint32_t m, const uint32_t* la
 // a persistent GPU context (device buffers are reused across psmh_cv_run calls)
 // ForestFile::read followed by ForestFile::write (no GPU involved): lets the tests check the reader and the writer against a
 // forest file written by the reference itself.
+// generateRandomSet through the C boundary: x [n][m+1], y [n]
+void psmh_generate_random_set(uint32_t n, uint32_t m, double prob, uint32_t seed, double* x, uint32_t* y) {
+	std::vector<double> xx; std::vector<uint32_t> yy;
+	parsmurf::generateRandomSet(n, m, xx, yy, prob, seed);
+	memcpy(x, xx.data(), xx.size() * sizeof(double));
+	memcpy(y, yy.data(), yy.size() * sizeof(uint32_t));
+}
 int psmh_forest_file_rewrite(const char* inPath, const char* outPath, uint64_t* nTreesOut, char* errbuf, size_t errlen) {
 	try {
 		parsmurf::ForestFile ff = parsmurf::ForestFile::read(inPath);

@@ -78,6 +78,7 @@ private:
 };
 
 // reference src/folds.h:10-40
+class Device;
 class Folds {
 public:
 	Folds(uint32_t numberOfFolds, uint32_t classSize, const uint32_t* labels, std::vector<uint32_t>& ff, bool randomFold, GlibcRand* rng);
@@ -86,6 +87,12 @@ public:
 	~Folds();
 	Folds(const Folds&) = delete;
 	void computeFolds();
+	// "Folds from a file" on the device (psm_folds_build_device): the per-class lists are built in HBM from the fold ids by one
+	// stable sort and never exist on the host unless somebody asks (hostLists()); only the fold sizes come back.  `dev` must
+	// hold the dataset and the labels.  Random folds (no fold file) keep the host path: they are a rand()-driven shuffle.
+	void computeFoldsOnDevice(Device* dev);
+	const Device* builtOn() const { return devBuilt; }
+	void hostLists() const;                // make posList / negList valid on the host (a D2H copy after computeFoldsOnDevice)
 	const uint32_t classSize, nFolds;
 	const uint32_t* labels;
 	std::vector<uint32_t>& fromFile;
@@ -101,6 +108,9 @@ public:
 	bool randomFold;
 	GlibcRand* rng;
 private:
+	Device* devBuilt = nullptr;            // computeFoldsOnDevice: where the lists live
+	mutable bool hostListsValid = false;
+	mutable std::mutex hostListsMtx;
 	std::vector<uint32_t> noIds;           // what `fromFile` refers to when the ids are borrowed
 	const uint32_t* ids = nullptr;         // fold id per example (fromFile.data() or the borrowed array)
 	size_t nIds = 0;
@@ -252,6 +262,11 @@ struct ForestFile {
 	static ForestFile read(const std::string& path);
 };
 
+// The simulated data set of cfgEx/simulCV.json ("simulate" block): labels Bernoulli(prob), features N(5,1) for positives and
+// N(0,1) for negatives, column m = 1.0 / 2.0 -- the same engine (std::default_random_engine), distribution objects and draw
+// order as generateRandomSet (src/HyperSMURFUtils.cpp:40-63), so with the same libstdc++ the set is the reference's.
+void generateRandomSet(uint32_t nn, uint32_t mm, std::vector<double>& xx, std::vector<uint32_t>& yy, double prob, uint32_t seed);
+
 // reference src/curves.h:12-21
 class Curves {
 public:
@@ -293,6 +308,10 @@ public:
 	// A rank's share of a fold is further cut into pieces of at most max(32, share / foldLanes) partitions, one piece per
 	// fold lane at a time, so that a rank that owns only one or two folds still keeps several lanes busy.
 	bool shardUnits = false;
+	// Grid search (exec.optimizer "grid", src/hyperSMURF.cpp:176-228) on several ranks: true -- every rank runs whole inner CVs,
+	// its cost-balanced share of the grid points of each outer fold, and the [G][2] metric table is summed once per outer fold;
+	// false -- every inner fold's partitions are chunked over the ranks (the MPI rule), one reduce per inner fold.
+	bool shardGridPoints = true;
 	// [first, last) of fold `fold`'s partitions that belong to `rank` under either rule (src/MPIHelper.cpp:29-37 for the first)
 	static void partRange(bool units, uint32_t nFoldsRun, uint32_t nPart, uint32_t world, uint32_t rank, uint32_t foldIdx, uint32_t* first, uint32_t* last);
 	int curvesTieMode = 0;

@@ -154,12 +154,42 @@ def forest_file_rewrite(in_path, out_path):
     return int(nt[0])
 
 
+class _ScratchCwd:
+    """the grid search appends fold<k>.dat to the working directory like the reference (src/hyperSMURF.cpp:191-199): run it in a
+    scratch directory.  The working directory is process-wide, so concurrent callers (ranks emulated as threads) share one:
+    the first one in creates and enters it, the last one out restores the old directory and removes it."""
+
+    def __init__(self):
+        import threading
+        self.lock, self.users, self.tmp, self.cwd = threading.Lock(), 0, None, None
+
+    def __enter__(self):
+        import tempfile
+        with self.lock:
+            if self.users == 0:
+                self.cwd = os.getcwd()
+                self.tmp = tempfile.TemporaryDirectory()
+                os.chdir(self.tmp.name)
+            self.users += 1
+
+    def __exit__(self, *exc):
+        with self.lock:
+            self.users -= 1
+            if self.users == 0:
+                os.chdir(self.cwd)
+                self.tmp.cleanup()
+                self.tmp = None
+        return False
+
+
+_scratch_cwd = _ScratchCwd()
+
+
 def cv_grid_run(x, labels, folds, nFolds, grid, seed, device=0, tie_mode=0, stream=None, rank=0, world=1, reduce=None, x_device_ptr=None, n=None, m=None,
                 dev_handle=None):
     """Grid search like cfgEx/gridTune.json (exec.optimizer "grid"): grid = list of (nParts, fp, ratio, k, nTrees, mtry).
     Appends fold<k>.dat files to a scratch directory.  x / x_device_ptr, rank / world / reduce and dev_handle as in cv_run.
     Returns dict(class1, class2, auroc, auprc, grid_metrics, kernel_launches, stats)."""
-    import tempfile
     L = hlib()
     L.psmh_cv_grid_run_ex.argtypes = [vp, C.c_int, u32, u32, u32p, u32p, u32, u32p, u32, u32, C.c_int, vp, C.c_int, u32, u32, REDUCE_FN, vp, dp, dp, dp, dp,
                                       u64p, u64p, vp, C.c_char_p, C.c_size_t]
@@ -184,15 +214,10 @@ def cv_grid_run(x, labels, folds, nFolds, grid, seed, device=0, tie_mode=0, stre
             print("reduce callback failed:", e)
             return 1
     cb = REDUCE_FN(_cb) if reduce is not None else REDUCE_FN()
-    cwd = os.getcwd()
-    with tempfile.TemporaryDirectory() as d:
-        os.chdir(d)
-        try:
-            rc = L.psmh_cv_grid_run_ex(vp(xptr), isdev, n, m, _p(labels, u32p), _p(folds, u32p), nFolds, _p(g, u32p), len(g), seed, device,
-                                       vp(stream) if stream else None, tie_mode, rank, world, cb, None, _p(c1, dp), _p(c2, dp), _p(met, dp), _p(gm, dp),
-                                       _p(kl, u64p), _p(st, u64p), vp(dev_handle) if dev_handle else None, err, 512)
-        finally:
-            os.chdir(cwd)
+    with _scratch_cwd:
+        rc = L.psmh_cv_grid_run_ex(vp(xptr), isdev, n, m, _p(labels, u32p), _p(folds, u32p), nFolds, _p(g, u32p), len(g), seed, device,
+                                   vp(stream) if stream else None, tie_mode, rank, world, cb, None, _p(c1, dp), _p(c2, dp), _p(met, dp), _p(gm, dp),
+                                   _p(kl, u64p), _p(st, u64p), vp(dev_handle) if dev_handle else None, err, 512)
     if rc != 0:
         raise PsmError(rc, err.value.decode())
     return dict(class1=c1, class2=c2, auroc=float(met[0]), auprc=float(met[1]), grid_metrics=gm,
@@ -245,6 +270,16 @@ class HostDevice:
             self.close()
         except Exception:
             pass
+
+
+def generate_random_set(n, m, prob, seed):
+    """the simulated data set of cfgEx/simulCV.json (parsmurf::generateRandomSet): x [n][m+1] with the label column, y [n]"""
+    L = hlib()
+    L.psmh_generate_random_set.argtypes = [u32, u32, C.c_double, u32, dp, u32p]
+    L.psmh_generate_random_set.restype = None
+    x = np.empty((n, m + 1)); y = np.empty(n, np.uint32)
+    L.psmh_generate_random_set(n, m, prob, seed, _p(x, dp), _p(y, u32p))
+    return x, y
 
 
 def ttd_fold(labels, folds, nFolds, fold, fold_to_jump=-1):

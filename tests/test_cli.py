@@ -61,6 +61,30 @@ def test_cli_cv_matches_host_api(tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_two_gpus_through_the_library_communicator(tmp_path):
+    """--gpus 2: one rank per GPU inside one process, units sharded, scores summed by psm_comm_allreduce_sum_f64 (NCCL bound by
+    the C ABI -- no torch.distributed anywhere); rank 0 writes the same predictions as the single-GPU run up to the fp64
+    addition order across ranks"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    case = make_case("fy_26")
+    cfg = _write_case(tmp_path, case, "cli_2gpu")
+    r1 = subprocess.run([BIN, "--cfg", cfg], capture_output=True, text=True)
+    assert r1.returncode == 0, r1.stderr
+    p1 = np.loadtxt(tmp_path / "predictions.txt")
+    os.remove(tmp_path / "predictions.txt")
+    r2 = subprocess.run([BIN, "--cfg", cfg, "--gpus", "2"], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    assert "2 GPUs" in r2.stdout
+    p2 = np.loadtxt(tmp_path / "predictions.txt")
+    assert p1.shape == p2.shape and np.allclose(p1, p2, rtol=1e-5, atol=1e-12)
+    m1 = re.search(r"AUROC: ([0-9.eE+-]+) - AUPRC: ([0-9.eE+-]+)", r1.stdout)
+    m2 = re.search(r"AUROC: ([0-9.eE+-]+) - AUPRC: ([0-9.eE+-]+)", r2.stdout)
+    assert abs(float(m1.group(1)) - float(m2.group(1))) < 1e-4 and abs(float(m1.group(2)) - float(m2.group(2))) < 1e-4
+
+
+@pytest.mark.gpu
 def test_cli_train_then_predict_modes(tmp_path):
     """exec.mode "train" writes one ranger forest file per partition into data.forestDir; exec.mode "predict" scores every
     example with them -- the same numbers as the host API's predict mode"""

@@ -321,6 +321,77 @@ def test_grid_search_matches_reference_golden():
     assert abs(out["auroc"] - float(g["auroc"])) < 1e-12 and abs(out["auprc"] - float(g["auprc"])) < 1e-12
 
 
+def _threaded_ranks(W, fn):
+    """W ranks of one multi-rank run as W host threads on one GPU: reduce(ptr, count) is a real all-reduce between the threads
+    (every rank's buffer is read, summed in rank order, written back), so every collective the run issues is exercised in order"""
+    import threading
+    import torch
+
+    class _Arr:
+        def __init__(self, ptr, count):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    bar = threading.Barrier(W)
+    bufs, outs, errs, counts = [None] * W, [None] * W, [], [[] for _ in range(W)]
+
+    def reducer(r):
+        def reduce(ptr, count):
+            t = torch.as_tensor(_Arr(ptr, count), device="cuda")
+            torch.cuda.synchronize()
+            bufs[r] = t.clone()
+            counts[r].append(count)
+            bar.wait(timeout=120)
+            tot = bufs[0].clone()
+            for q in range(1, W):
+                tot += bufs[q]
+            torch.cuda.synchronize()
+            bar.wait(timeout=120)
+            t.copy_(tot)
+            torch.cuda.synchronize()
+        return reduce
+
+    def work(r):
+        try:
+            outs[r] = fn(r, reducer(r))
+        except Exception as e:   # a dead rank must not leave the others waiting
+            errs.append((r, e))
+            bar.abort()
+    th = [threading.Thread(target=work, args=(r,)) for r in range(W)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    assert all(c == counts[0] for c in counts), "the ranks issued different collectives"
+    return outs, counts[0]
+
+
+def test_grid_search_sharded_by_grid_point_equals_the_single_rank_run():
+    """multi-rank grid search: every rank runs whole inner CVs (its share of the grid points, SMOTE stream entered at each point's
+    offset) and the [G][2] metric table is summed once per outer fold -- the table, the winners and therefore the outer folds
+    must be those of one rank; the outer folds themselves are chunked over the ranks (sum order differs: 1e-13)"""
+    import os
+    from parsmurf_b200 import host_api as H
+    from oracle import pyoracle as O
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grid_fy_26.npz"))
+    c = make_case("fy_26")
+    x = O.make_x(c["X"], c["y"])
+    grid = [tuple(int(v) for v in r) for r in g["grid"]]
+    n, G, nF = len(c["y"]), len(grid), c["nF"]
+    for W in (2, 3):
+        devs = [H.HostDevice(0) for _ in range(W)]
+        try:
+            outs, counts = _threaded_ranks(W, lambda r, red: devs[r].cv_grid_run(x, c["y"], c["f"], nF, grid, 7, tie_mode=0, rank=r, world=W, reduce=red))
+        finally:
+            for d in devs:
+                d.close()
+        assert counts.count(2 * G) == nF, counts                                # one metric-table reduce per outer fold, none per inner fold
+        assert len(counts) == 2 * nF, counts                                   # + one score reduce per outer fold
+        for out in outs:
+            assert np.allclose(out["grid_metrics"], g["grid_metrics"], rtol=0, atol=1e-12)
+            assert np.allclose(out["class1"], g["class1"], rtol=0, atol=1e-13) and np.allclose(out["class2"], g["class2"], rtol=0, atol=1e-13)
+            assert abs(out["auroc"] - float(g["auroc"])) < 1e-4 and abs(out["auprc"] - float(g["auprc"])) < 1e-4
+
+
 def _train_case(ctx, oracle, case, fold=0, seed=7):
     x, fd, rnd = _fold_setup(ctx, oracle, case, fold)
     ctx.fold_knn(case["k"])

@@ -35,3 +35,16 @@ def test_recorded_draws_reproduce_a_multithreaded_reference_run(oracle, name, th
     for p in range(c["nParts"]):
         e = e + preds[p, :, 0] * (1.0 / c["nParts"])
     assert np.abs(e - c1[test]).max() < 1e-15
+
+
+def test_simulated_set_is_the_references():
+    """cfgEx/simulCV.json's "simulate" block: parsmurf::generateRandomSet == the reference's (src/HyperSMURFUtils.cpp:40-63), value for value"""
+    from oracle import pyoracle as O
+    from parsmurf_b200 import host_api as H
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    for n, m, prob, seed in ((1000, 10, 0.01, 1), (777, 3, 0.3, 4242)):
+        xr, yr = O.ref_generate_random_set(n, m, prob, seed)
+        x, y = H.generate_random_set(n, m, prob, seed)
+        assert np.array_equal(y, yr)
+        assert np.array_equal(x.view(np.uint64), xr.view(np.uint64))
