@@ -398,7 +398,7 @@ def grid_block(rig, w, x_dev, y, f):
                         % (GRID["nParts"], GRID["fp"], GRID["mtry"], len(grid), w["nFolds"], w["nFolds"] - 1),
             "steps": 1, "warmup": 1, "ms_per_grid_cv": ms, "inner_partitions": inner, "inner_partitions_per_sec": inner / (ms / 1000.0), "clocks": clocks,
             "gpu_launches": int(sum(outs[0]["kernel_launches"].values())), "quality": {"auroc": outs[0]["auroc"], "auprc": outs[0]["auprc"]},
-            "sharding": "single GPU" if rig.world == 1 else "every rank takes its chunk of the partitions of every (grid point, inner fold); one all-reduce of the fold scores per inner fold",
+            "sharding": "single GPU" if rig.world == 1 else "every rank runs whole inner CVs -- its cost-balanced share of the 18 grid points of each outer fold -- and the [18][2] metric table is summed once per outer fold; the outer folds' partitions are chunked over the ranks",
             "curves": {"mode": "auto", "mixed_tie_pairs": outs[0]["stats"]["mixed_tie_pairs"], "host_sorts": outs[0]["stats"]["curves_host_sorts"],
                        "max_tie_spread": outs[0]["stats"]["curves_max_tie_spread"]}}
 

@@ -810,13 +810,12 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		if (trace) cudaEventRecord(tev[0], s);
 		{ ProfScope ps(ctx, K_SEARCH, nzCls); launch_split_search(A, clsCount, buf, s); }
 		if (trace) cudaEventRecord(tev[1], s);
-		{
-			ProfScope ps(ctx, K_SELECT, 2);
-			launch_split_select(A, nItems, buf, s);
-			if (launch_tree_flags(A, s)) return fail(ctx, PSM_E_CUDA, "batch_train: cannot configure the flag bitmap");
-		}
+		{ ProfScope ps(ctx, K_SELECT, 1); launch_split_select(A, nItems, buf, s); }
 		if (trace) cudaEventRecord(tev[2], s);
-		{ ProfScope ps(ctx, K_FINALIZE, 1); launch_level_finalize(A, buf, s); }
+		{
+			ProfScope ps(ctx, K_FINALIZE, 1);
+			if (launch_tree_level(A, buf, s)) return fail(ctx, PSM_E_CUDA, "batch_train: cannot configure the flag bitmap");
+		}
 		if (trace) cudaEventRecord(tev[3], s);
 		CU(cudaMemcpyAsync(ctx->hCounters, A.counters, CNT_COUNT * 4, cudaMemcpyDeviceToHost, s));   // nItems of the next level
 		CU(cudaEventRecord(ctx->evLevel, s));

@@ -100,9 +100,7 @@ struct __align__(16) PartTask {
 	uint32_t cnt;     // 0 = nothing to move (no split, or both children terminal); top bits: PT_DEAD_LEFT / PT_DEAD_RIGHT
 	uint32_t nleft;
 };
-// rows per matrix < 2^24.  PT_TAIL: the tree leaves the level loop after this level (tree_tail_kernel finishes it from ONE row list),
-// so only the list of feature 0 is partitioned.
-constexpr uint32_t PT_DEAD_LEFT = 1u << 31, PT_DEAD_RIGHT = 1u << 30, PT_TAIL = 1u << 29, PT_CNT_MASK = (1u << 24) - 1u;
+constexpr uint32_t PT_DEAD_LEFT = 1u << 31, PT_DEAD_RIGHT = 1u << 30, PT_CNT_MASK = (1u << 24) - 1u;   // rows per matrix < 2^24
 
 // per-tree growth state
 struct TreeState {
@@ -112,8 +110,7 @@ struct TreeState {
 	uint32_t mtPos;       // next unread index in the mt19937_64 state block (0..312)
 	uint32_t nEntries;    // in-bag distinct rows
 	uint32_t overflow;
-	uint32_t tailCount;   // > 0: the tree left the level loop with this many open nodes (items in its window of tailItems[0])
-	uint32_t pad;
+	uint32_t pad[2];
 };
 
 // Opt a kernel in to the full 227 KB of dynamic shared memory.  The attribute belongs to the function, not to the calling

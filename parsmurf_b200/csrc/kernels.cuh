@@ -7,14 +7,12 @@ namespace psm {
 // counters[CNT_NEXT_ITEMS] = open nodes of the next level; counters[CNT_CLS0 + k] = how many of them fall in size class k
 // (level_finalize appends their item ids to clsItems[next][k]); both are cleared by the host before the next level_finalize
 constexpr int NCLS = 4;
-// counters[CNT_TAIL] = trees handed to tree_tail_kernel so far (cumulative; their ids are appended to tailList), counters[CNT_MAX_ENTRIES] =
-// largest in-bag row count of a tree (sizes the tail kernel's shared-memory row list)
-enum { CNT_NEXT_ITEMS = 0, CNT_CLS0 = 1, CNT_ERROR = 5, CNT_TAIL = 6, CNT_MAX_ENTRIES = 7, CNT_COUNT = 8 };
+enum { CNT_NEXT_ITEMS = 0, CNT_CLS0 = 1, CNT_ERROR = 5, CNT_COUNT = 8 };
 // Size class of a work item by its segment length (+3: worst-case shift of the 16-byte aligned load grid):
 //   0: <= 32 grid entries (8 lanes x 4)   1: <= 64 (16 lanes)   2: <= 128 (one warp, one chunk)   3: longer (chunk loop)
 __host__ __device__ __forceinline__ uint32_t size_class(uint32_t cnt) { return cnt <= 29u ? 0u : cnt <= 61u ? 1u : cnt <= 125u ? 2u : 3u; }
 enum { ERR_COUNT_LIMIT = 1, ERR_POOL_OVERFLOW = 2, ERR_INJ_CAND = 4 };
-enum { STAT_SPLIT_BYTES = 0, STAT_NODES = 1, STAT_TAIL_BYTES = 2, STAT_TAIL_LEVELS = 3, STAT_COUNT = 4 };
+enum { STAT_SPLIT_BYTES = 0, STAT_NODES = 1, STAT_COUNT = 4 };
 
 // everything the level kernels need, passed by value
 struct TrainArgs {
@@ -46,16 +44,6 @@ struct TrainArgs {
 	SplitDec* dec;        // [itemCap]
 	PartTask* ptask;      // [itemCap]
 	uint32_t* splitFeat;  // [itemCap] winning feature of each split node
-	// Tree tails (tailCap == 0: off).  Once every open node of a tree holds at most tailCap entries, level_finalize hands the tree to
-	// tree_tail_kernel: one CTA finishes it from ONE row list in shared memory, rebuilding a candidate's order on demand from the
-	// dense ranks  rankTab [partition][m][Ntr] u16 (element offsets of Sall; written by the feature sort).
-	uint32_t tailCap;
-	uint32_t tailStride;  // items per tree window = stride / 11 + 2
-	const unsigned short* rankTab;
-	Item* tailItems[2];   // [tree][tailStride] ping-pong windows
-	uint32_t* tailCand;   // [tree][tailStride][mtry]
-	SplitDec* tailDec;    // [tree][tailStride]
-	uint32_t* tailList;   // [nTrees] tree ids in hand-over order
 	uint32_t* counters;   // [CNT_COUNT]
 	unsigned long long* stats;   // [STAT_COUNT]
 	const uint32_t* injCand;     // [tree][injCandNodes][mtry] or nullptr
@@ -87,11 +75,8 @@ void launch_build_lists(const TrainArgs& A, cudaStream_t s);
 int launch_init_trees(const TrainArgs& A, cudaStream_t s);
 void launch_split_search(const TrainArgs& A, const uint32_t* clsCount, int buf, cudaStream_t s);
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
-void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s);
-int launch_tree_flags(const TrainArgs& A, cudaStream_t s);
+int launch_tree_level(const TrainArgs& A, int buf, cudaStream_t s);   // go-left bitmaps + level bookkeeping, one CTA per tree
 void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
-// trees tailList[first, first + count): srcBuf = which of lists[0/1] holds their open nodes' segments (feature 0 only)
-int launch_tree_tail(const TrainArgs& A, uint32_t first, uint32_t count, int srcBuf, uint32_t rowsCap, cudaStream_t s);
 // glibc_rand.cu
 void glibc_window_jump(uint32_t* w31, uint64_t n);
 int launch_glibc_rand_fill(const uint32_t* w31, unsigned long long count, uint32_t* scratchDev, int32_t* out, cudaStream_t s);

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) build_lists_kernel(TrainArgs A) {
 		}
 	}
 	if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&A.counters[CNT_ERROR], ERR_COUNT_LIMIT);
-	if (f == 0 && lane == 0) { A.ts[tree].nEntries = off; atomicMax(&A.counters[CNT_MAX_ENTRIES], off); }
+	if (f == 0 && lane == 0) A.ts[tree].nEntries = off;
 }
 
 // ------------------------------------------------------------------------------------------ candidates
@@ -281,21 +281,15 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 	Node16* nodes = A.nodes + (size_t)tree * A.NC;
 	const bool live = node_live(npos, nneg);
 	uint32_t item = 0xFFFFFFFFu;
-	const bool toTail = live && A.tailCap && ts.nEntries <= A.tailCap;   // a root that small goes straight to tree_tail_kernel
-	uint32_t* candBase = toTail ? A.tailCand + (size_t)tree * A.tailStride * A.mtry : A.cand;
+	uint32_t* candBase = A.cand;
 	if (live) {
-		if (lane == 0) item = toTail ? 0u : atomicAdd(&A.counters[CNT_NEXT_ITEMS], 1u);
+		if (lane == 0) item = atomicAdd(&A.counters[CNT_NEXT_ITEMS], 1u);
 		item = __shfl_sync(0xffffffffu, item, 0);
 		if (lane == 0) {
 			Item it; it.tree = tree; it.node = 0; it.start = 0; it.cnt = ts.nEntries; it.npos = npos; it.nneg = nneg; it.nPosOut = pd.nPosOut; it.pl = pl;
-			if (toTail) {
-				A.tailItems[0][(size_t)tree * A.tailStride] = it;
-				A.tailList[atomicAdd(&A.counters[CNT_TAIL], 1u)] = tree;
-			} else {
-				A.items[0][item] = it;
-				const uint32_t k = A.useClasses ? size_class(ts.nEntries) : (uint32_t)(NCLS - 1);
-				A.clsItems[0][k][atomicAdd(&A.counters[CNT_CLS0 + k], 1u)] = item;
-			}
+			A.items[0][item] = it;
+			const uint32_t k = A.useClasses ? size_class(ts.nEntries) : (uint32_t)(NCLS - 1);
+			A.clsItems[0][k][atomicAdd(&A.counters[CNT_CLS0 + k], 1u)] = item;
 		}
 	} else if (lane == 0) {
 		write_leaf(&nodes[0], npos, nneg);
@@ -312,8 +306,7 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 		ts.mtPos = pos;
 	}
 	if (lane == 0) {
-		ts.nNodes = 1; ts.itemBase = (live && !toTail) ? item : 0; ts.itemCount = (live && !toTail) ? 1 : 0; ts.overflow = 0;
-		ts.tailCount = toTail ? 1u : 0u;
+		ts.nNodes = 1; ts.itemBase = live ? item : 0; ts.itemCount = live ? 1 : 0; ts.overflow = 0;
 		A.ts[tree] = ts;
 	}
 }
@@ -458,7 +451,12 @@ template <int G> __device__ __forceinline__ uint32_t grp_min(uint32_t v) {
 //   * a single shared exact-evaluation block fed by a per-lane pending mask instead of one block per lane slot: same time
 //     (only the taken blocks ever executed);
 //   * no software pipeline (40 registers, 12 CTAs per SM instead of 8): same time -- what the extra warps hide, the exposed
-//     load of every second chunk gives back.
+//     load of every second chunk gives back;
+//   * (r02) the four warps of a CTA sharing one long segment (> 1021 entries: a quarter each, class counts of the quarters
+//     exchanged through shared memory after a counting pass), to shorten the 24-chunk serial walk of the first levels and the
+//     half-empty second wave of 5 000 warps on 4 144 slots: 11.9 ms re-reading the quarter through L1 / L2, 11.9 ms with the
+//     quarter staged in shared memory, against 10.9 ms -- ncu shows the one-warp loop ~75% issue-bound while its warps are
+//     resident (1.3 warp instructions per entry), so the extra counting pass and the barrier cost more than the tail wave.
 template <typename E, int G, bool MULTI>
 __global__ void __launch_bounds__(128, MULTI ? SS_MINB_MULTI : SS_MINB) split_search_kernel(TrainArgs A, const uint32_t* __restrict__ list, uint32_t nList, int buf) {
 	constexpr int IPL = SsIpl<E, MULTI>::v;
@@ -607,56 +605,58 @@ __global__ void __launch_bounds__(128, MULTI ? SS_MINB_MULTI : SS_MINB) split_se
 	}
 }
 
-// one warp per open node: pick the winning candidate, compute the threshold, mark rows going left
+// eight lanes per open node (four nodes per warp): pick the winning candidate, compute the threshold, describe the list partition.
+// The work per node is a short chain of dependent loads (results -> list entries -> feature values), so the kernel is bound by
+// how many chains are in flight: with one warp per node the 60 000 nodes of a mid level of BASELINE configs[1] needed six waves.
+constexpr int SEL_G = 8;
 template <typename E>
 __global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t nItems, int buf) {
-	const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (item >= nItems) return;
+	uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) / SEL_G;
+	const bool idle = item >= nItems;
+	if (idle) item = nItems - 1;                          // keep the warp whole for the shuffles; an idle group only skips its stores
 	const Item it = A.items[buf][item];
-	const int lane = lane_id();
+	const int gl = lane_id() % SEL_G;
 	double best = -1.0;
 	uint32_t bc = 0xFFFFFFFFu;
-	for (uint32_t c = lane; c < A.mtry; c += 32) {
+	for (uint32_t c = gl; c < A.mtry; c += SEL_G) {
 		double s = A.res[(size_t)item * A.mtry + c].score;
 		if (s > best) { best = s; bc = c; }          // ascending c per lane: first maximum stays
 	}
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		double os = __shfl_xor_sync(0xffffffffu, best, o);
-		uint32_t oc = __shfl_xor_sync(0xffffffffu, bc, o);
+	for (int o = SEL_G / 2; o > 0; o >>= 1) {
+		double os = __shfl_xor_sync(0xffffffffu, best, o, SEL_G);
+		uint32_t oc = __shfl_xor_sync(0xffffffffu, bc, o, SEL_G);
 		if (os > best || (os == best && oc < bc)) { best = os; bc = oc; }
 	}
+	if (idle || gl != 0) return;
 	Node16* node = A.nodes + (size_t)it.tree * A.NC + it.node;
 	SplitDec d; d.split = 0; d.nleft = 0; d.lpos = 0; d.lneg = 0;
 	if (!(best >= 0.0)) {                             // TreeProbability.cpp:184-186: no candidate had two distinct values
-		if (lane == 0) {
-			write_leaf(node, it.npos, it.nneg); A.dec[item] = d;
-			PartTask pt; pt.tree = it.tree; pt.start = it.start; pt.cnt = 0; pt.nleft = 0;
-			A.ptask[item] = pt;
-		}
+		write_leaf(node, it.npos, it.nneg); A.dec[item] = d;
+		PartTask pt; pt.tree = it.tree; pt.start = it.start; pt.cnt = 0; pt.nleft = 0;
+		A.ptask[item] = pt;
 		return;
 	}
 	const SearchRes r = A.res[(size_t)item * A.mtry + bc];
 	const uint32_t f = A.cand[(size_t)item * A.mtry + bc];
 	const E* list = reinterpret_cast<const E*>(A.lists[A.listBuf]) + ((size_t)it.tree * A.m + f) * A.stride + it.start;
-	const PartDesc pd = A.parts[it.tree / A.T];
-	if (lane == 0) {
-		const double* col = A.Dall + pd.dOffset + (size_t)f * pd.Ntr;
-		const double lo = col[Ent<E>::row(list[r.pos])], hi = col[Ent<E>::row(list[r.pos + 1])];
-		double thr = __dmul_rn(__dadd_rn(lo, hi), 0.5);     // TreeProbability.cpp:348
-		if (thr == hi) thr = lo;                            // :353-355
-		Node16 v; v.a = thr; v.b = (unsigned long long)f;   // left child id is filled in by level_finalize
-		*node = v;
-		d.split = 1; d.nleft = r.pos + 1; d.lpos = r.lpos; d.lneg = r.lneg;
-		A.dec[item] = d;
-		// list partition: a terminal child's entries are never read again (level_finalize writes its leaf payload from
-		// the class counts), so they are not moved; with two terminal children the node is skipped entirely
-		const bool deadL = !node_live(d.lpos, d.lneg), deadR = !node_live(it.npos - d.lpos, it.nneg - d.lneg);
-		PartTask pt; pt.tree = it.tree; pt.start = it.start; pt.nleft = d.nleft;
-		pt.cnt = (deadL && deadR) ? 0u : (it.cnt | (deadL ? PT_DEAD_LEFT : 0u) | (deadR ? PT_DEAD_RIGHT : 0u));
-		A.ptask[item] = pt;
-		A.splitFeat[item] = f;
-	}
+	const PartDesc pd = A.parts[it.pl];
+	const double* col = A.Dall + pd.dOffset + (size_t)f * pd.Ntr;
+	const E e0 = list[r.pos], e1 = list[r.pos + 1];
+	const double lo = col[Ent<E>::row(e0)], hi = col[Ent<E>::row(e1)];
+	double thr = __dmul_rn(__dadd_rn(lo, hi), 0.5);     // TreeProbability.cpp:348
+	if (thr == hi) thr = lo;                            // :353-355
+	Node16 v; v.a = thr; v.b = (unsigned long long)f;   // left child id is filled in by level_finalize
+	*node = v;
+	d.split = 1; d.nleft = r.pos + 1; d.lpos = r.lpos; d.lneg = r.lneg;
+	A.dec[item] = d;
+	// list partition: a terminal child's entries are never read again (level_finalize writes its leaf payload from
+	// the class counts), so they are not moved; with two terminal children the node is skipped entirely
+	const bool deadL = !node_live(d.lpos, d.lneg), deadR = !node_live(it.npos - d.lpos, it.nneg - d.lneg);
+	PartTask pt; pt.tree = it.tree; pt.start = it.start; pt.nleft = d.nleft;
+	pt.cnt = (deadL && deadR) ? 0u : (it.cnt | (deadL ? PT_DEAD_LEFT : 0u) | (deadR ? PT_DEAD_RIGHT : 0u));
+	A.ptask[item] = pt;
+	A.splitFeat[item] = f;
 }
 
 // ------------------------------------------------------------------------------------------ go-left flags
@@ -664,19 +664,16 @@ __global__ void __launch_bounds__(128) split_select_kernel(TrainArgs A, uint32_t
 // [0, nleft) of every split node's segment in the winning feature's list is read; the bits are set with shared-memory
 // atomics and the bitmap leaves the SM as one coalesced store.  (Per-row byte stores straight to global memory were bound
 // by scattered-store throughput: ~60 us per level for the 6M rows of a BASELINE configs[1] fold.)
-constexpr int TF_THREADS = 256;
-constexpr uint32_t TF_LONG = 1024;   // segments with at least this many left entries are shared by the whole CTA
+constexpr int TF_THREADS = 128;   // 1 bookkeeping warp + 3 flag warps; 8 CTAs per SM keep the 1000 trees of a BASELINE configs[1] batch in one wave
+constexpr uint32_t TF_LONG = 1024;   // segments with at least this many left entries are shared by all the flag threads
+// the go-left bitmap of one tree, by threads ftid = 0 .. FT-1 (whole warps) of its CTA, which meet at named barrier 1
 template <typename E>
-__global__ void __launch_bounds__(TF_THREADS) tree_flags_kernel(TrainArgs A, int bitmapInSmem) {
-	extern __shared__ uint32_t bm_s[];
-	const uint32_t tree = blockIdx.x;
-	const TreeState ts = A.ts[tree];           // still this level's item range: level_finalize runs after this kernel
-	if (ts.itemCount == 0) return;
+__device__ __forceinline__ void tree_flags_body(const TrainArgs& A, uint32_t tree, const TreeState& ts, uint32_t* bm_s, int bitmapInSmem, int ftid, int FT) {
 	uint32_t* out = A.flagBits + (size_t)tree * A.flagWords;
 	uint32_t* bm = bitmapInSmem ? bm_s : out;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	for (uint32_t w = tid; w < A.flagWords; w += TF_THREADS) bm[w] = 0;
-	__syncthreads();
+	const int lane = ftid & 31, warp = ftid >> 5;
+	for (uint32_t w = ftid; w < A.flagWords; w += FT) bm[w] = 0;
+	asm volatile("bar.sync 1, %0;" ::"r"(FT) : "memory");
 	const PartTask* tasks = A.ptask + ts.itemBase;
 	const uint32_t* feats = A.splitFeat + ts.itemBase;
 	const E* lists = reinterpret_cast<const E*>(A.lists[A.listBuf]) + (size_t)tree * A.m * A.stride;
@@ -697,26 +694,26 @@ __global__ void __launch_bounds__(TF_THREADS) tree_flags_kernel(TrainArgs A, int
 	for (uint32_t i = 0; i < ts.itemCount; i++) {
 		const uint4 raw = __ldg(reinterpret_cast<const uint4*>(tasks + i));   // {tree, start, cnt, nleft}
 		if (raw.z == 0) continue;                                             // node became a leaf
-		if (raw.w >= TF_LONG) mark(lists + (size_t)__ldg(feats + i) * A.stride + raw.y, raw.w, tid, TF_THREADS);
+		if (raw.w >= TF_LONG) mark(lists + (size_t)__ldg(feats + i) * A.stride + raw.y, raw.w, ftid, FT);
 		else nshort++;
 	}
 	if (nshort) {
-		for (uint32_t i = warp; i < ts.itemCount; i += TF_THREADS / 32) {
+		for (uint32_t i = warp; i < ts.itemCount; i += FT / 32) {
 			const uint4 raw = __ldg(reinterpret_cast<const uint4*>(tasks + i));
 			if (raw.z == 0 || raw.w >= TF_LONG) continue;
 			mark(lists + (size_t)__ldg(feats + i) * A.stride + raw.y, raw.w, lane, 32);
 		}
 	}
 	if (bitmapInSmem) {
-		__syncthreads();
-		for (uint32_t w = tid; w < A.flagWords; w += TF_THREADS) out[w] = bm_s[w];
+		asm volatile("bar.sync 1, %0;" ::"r"(FT) : "memory");
+		for (uint32_t w = ftid; w < A.flagWords; w += FT) out[w] = bm_s[w];
 	}
 }
 
 // ------------------------------------------------------------------------------------------ level finalize
 // The mtry draws of the `nchild` nodes created by up to 32 parents, in node-id order (ids childBase .. childBase + nchild - 1);
 // sm.child[c] = work-item slot of child c (its candidates go to candBase + slot * mtry) or 0xFFFFFFFF for a terminal child,
-// whose draws are consumed but not stored.  Warp-cooperative; shared by level_finalize_kernel and tree_tail_kernel.
+// whose draws are consumed but not stored.  Warp-cooperative.
 __device__ __forceinline__ void draw_children(const TrainArgs& A, const TreeSmem& sm, uint32_t& pos, uint32_t tree, uint32_t childBase,
                                               uint32_t nchild, uint32_t* candBase, const int lane) {
 	const bool laneFY = !A.injCand && A.mtry <= FY_MAX && !(A.mtry < (A.m + 1) / 10);
@@ -755,12 +752,7 @@ __device__ __forceinline__ void draw_children(const TrainArgs& A, const TreeSmem
 
 // one warp per tree: breadth-first child ids in parent-id order, child work items, leaf payloads of trivially
 // terminal children, and the mtry draw of every new node in node-id order.
-__global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf) {
-	extern __shared__ __align__(16) unsigned char raw[];
-	TreeSmem sm = carve(raw, A.m, A.mtry);
-	const uint32_t tree = blockIdx.x;
-	TreeState ts = A.ts[tree];
-	if (ts.itemCount == 0) return;
+__device__ __forceinline__ void level_finalize_body(const TrainArgs& A, const TreeSmem& sm, const uint32_t tree, TreeState ts, const int buf) {
 	const int lane = lane_id();
 	const unsigned lt = lanemask_lt();
 	const Item* cur = A.items[buf] + ts.itemBase;
@@ -768,25 +760,22 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 	Node16* nodes = A.nodes + (size_t)tree * A.NC;
 
 	// pass 1: count splits and live children
-	uint32_t nsplit = 0, nlive = 0, maxChild = 0;
+	uint32_t nsplit = 0, nlive = 0;
 	unsigned long long searched = 0;   // samples of the nodes that reached findBestSplit this level (SURVEY 8(d) byte count; one atomic per tree)
 	for (uint32_t b = 0; b < ts.itemCount; b += 32) {
 		uint32_t i = b + lane;
-		uint32_t l = 0, s = 0, mc = 0;
+		uint32_t l = 0, s = 0;
 		if (i < ts.itemCount) {
 			SplitDec d = dec[i];
 			const Item it = cur[i];
 			searched += it.npos + it.nneg;
 			if (d.split) {
 				s = 1;
-				const bool liveL = node_live(d.lpos, d.lneg), liveR = node_live(it.npos - d.lpos, it.nneg - d.lneg);
-				l = (liveL ? 1u : 0u) + (liveR ? 1u : 0u);
-				mc = max(liveL ? d.nleft : 0u, liveR ? it.cnt - d.nleft : 0u);
+				l = (node_live(d.lpos, d.lneg) ? 1u : 0u) + (node_live(it.npos - d.lpos, it.nneg - d.lneg) ? 1u : 0u);
 			}
 		}
 		for (int o = 16; o > 0; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); s += __shfl_xor_sync(0xffffffffu, s, o); }
 		nlive += l; nsplit += s;
-		maxChild = max(maxChild, __reduce_max_sync(0xffffffffu, mc));
 	}
 	for (int o = 16; o > 0; o >>= 1) searched += __shfl_xor_sync(0xffffffffu, searched, o);
 	if (lane == 0) atomicAdd(&A.stats[STAT_SPLIT_BYTES], searched * ((unsigned long long)A.mtry * 8ull + 8ull));
@@ -794,18 +783,15 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 		if (lane == 0) { ts.itemCount = 0; A.ts[tree] = ts; }
 		return;
 	}
-	// Every open node of the next level fits the tail kernel: the tree leaves the level loop.  Its work items and candidate draws
-	// go to the tree's own window, and this level's list partition only moves the list of feature 0 (PT_TAIL).
-	const bool toTail = A.tailCap && nlive > 0 && maxChild <= A.tailCap && nlive <= A.tailStride;
 	uint32_t nextBase = 0;
-	if (lane == 0 && !toTail) nextBase = atomicAdd(&A.counters[CNT_NEXT_ITEMS], nlive);
+	if (lane == 0) nextBase = atomicAdd(&A.counters[CNT_NEXT_ITEMS], nlive);
 	nextBase = __shfl_sync(0xffffffffu, nextBase, 0);
-	if ((!toTail && nextBase + nlive > A.itemCap) || ts.nNodes + 2 * nsplit > A.NC) {
+	if (nextBase + nlive > A.itemCap || ts.nNodes + 2 * nsplit > A.NC) {
 		if (lane == 0) { atomicOr(&A.counters[CNT_ERROR], ERR_POOL_OVERFLOW); ts.itemCount = 0; ts.overflow = 1; A.ts[tree] = ts; }
 		return;
 	}
-	Item* nextItems = toTail ? A.tailItems[0] + (size_t)tree * A.tailStride : A.items[buf ^ 1];
-	uint32_t* candBase = toTail ? A.tailCand + (size_t)tree * A.tailStride * A.mtry : A.cand;
+	Item* nextItems = A.items[buf ^ 1];
+	uint32_t* candBase = A.cand;
 	uint32_t pos = ts.mtPos;
 	unsigned long long* g = A.mt + (size_t)tree * MT_N;
 	if (!A.injCand) {
@@ -841,9 +827,8 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 				Item c; c.tree = tree; c.node = leftId + 1; c.start = it.start + d.nleft; c.cnt = it.cnt - d.nleft; c.npos = rpos; c.nneg = rneg; c.nPosOut = it.nPosOut; c.pl = it.pl;
 				nextItems[o] = c; sm.child[2 * sp + 1] = o;
 			} else { write_leaf(&nodes[leftId + 1], rpos, rneg); sm.child[2 * sp + 1] = 0xFFFFFFFFu; }
-			if (toTail) A.ptask[ts.itemBase + i].cnt |= PT_TAIL;
 		}
-		if (!toTail) {
+		{
 			// size-class lists of the next level (one warp-aggregated atomic per class and batch of 32 parents)
 			const uint32_t big = (uint32_t)(NCLS - 1);
 			const uint32_t kL = liveL ? (A.useClasses ? size_class(d.nleft) : big) : (uint32_t)NCLS;
@@ -871,12 +856,25 @@ __global__ void __launch_bounds__(32) level_finalize_kernel(TrainArgs A, int buf
 	if (!A.injCand) for (int i = lane; i < MT_N; i += 32) g[i] = sm.mt[i];
 	if (lane == 0) {
 		if (A.injCand && childBase > A.injCandNodes) atomicOr(&A.counters[CNT_ERROR], ERR_INJ_CAND);
-		ts.nNodes = childBase; ts.itemBase = toTail ? 0u : nextBase; ts.itemCount = toTail ? 0u : nlive; ts.mtPos = pos;
-		ts.tailCount = toTail ? nlive : 0u;
+		ts.nNodes = childBase; ts.itemBase = nextBase; ts.itemCount = nlive; ts.mtPos = pos;
 		A.ts[tree] = ts;
-		if (toTail) A.tailList[atomicAdd(&A.counters[CNT_TAIL], 1u)] = tree;
 		atomicAdd(&A.stats[STAT_NODES], (unsigned long long)(2 * nsplit));
 	}
+}
+
+// One CTA per tree and level, after split_select: warp 0 runs the level's bookkeeping (level_finalize_body) while the other
+// warps build the go-left bitmap the list partition reads (tree_flags_body).  Both only depend on split_select's output and used
+// to be two launches in a row, each one a 20-40 us latency chain per level (ncu / PSM_TRACE_LEVELS r02: together as long as
+// split search itself at BASELINE configs[1]); merged, the two chains overlap and a level costs one launch less.
+template <typename E>
+__global__ void __launch_bounds__(TF_THREADS, 8) tree_level_kernel(TrainArgs A, int buf, int bitmapInSmem, uint32_t bitmapOffset) {
+	extern __shared__ __align__(16) unsigned char raw[];
+	const uint32_t tree = blockIdx.x;
+	const TreeState ts = A.ts[tree];
+	if (ts.itemCount == 0) return;
+	__syncthreads();                        // every warp holds this level's item range before warp 0 overwrites A.ts[tree]
+	if (threadIdx.x < 32) level_finalize_body(A, carve(raw, A.m, A.mtry), tree, ts, buf);
+	else tree_flags_body<E>(A, tree, ts, reinterpret_cast<uint32_t*>(raw + bitmapOffset), bitmapInSmem, (int)threadIdx.x - 32, TF_THREADS - 32);
 }
 
 // ------------------------------------------------------------------------------------------ partition
@@ -958,7 +956,6 @@ __global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint3
 	if (cnt == 0) return;                                      // node became a leaf, or neither child will be searched
 	const bool keepL = !(raw.z & PT_DEAD_LEFT), keepR = !(raw.z & PT_DEAD_RIGHT);
 	const uint32_t f = blockIdx.y;
-	if ((raw.z & PT_TAIL) && f != 0) return;                   // the tree leaves the level loop: tree_tail_kernel only reads the list of feature 0
 	const uint32_t lane = lane_id();
 	const unsigned lt = lanemask_lt();
 	const size_t lo = ((size_t)tree * A.m + f) * A.stride + start;
@@ -995,7 +992,6 @@ int launch_init_trees(const TrainArgs& A, cudaStream_t s) {
 	size_t smem = tree_smem_bytes(A.m, A.mtry);
 	if (smem > 48 * 1024) {
 		if (allow_max_dyn_smem(init_trees_kernel) != cudaSuccess) return -1;
-		if (allow_max_dyn_smem(level_finalize_kernel) != cudaSuccess) return -1;
 	}
 	init_trees_kernel<<<A.nTrees, 32, smem, s>>>(A);
 	return 0;
@@ -1021,24 +1017,24 @@ void launch_split_search(const TrainArgs& A, const uint32_t* clsCount, int buf, 
 	}
 }
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
-	if (A.entry32) split_select_kernel<uint32_t><<<(nItems + 3) / 4, 128, 0, s>>>(A, nItems, buf);
-	else split_select_kernel<unsigned long long><<<(nItems + 3) / 4, 128, 0, s>>>(A, nItems, buf);
+	const unsigned grid = (unsigned)(((size_t)nItems * SEL_G + 127) / 128);
+	if (A.entry32) split_select_kernel<uint32_t><<<grid, 128, 0, s>>>(A, nItems, buf);
+	else split_select_kernel<unsigned long long><<<grid, 128, 0, s>>>(A, nItems, buf);
 }
-int launch_tree_flags(const TrainArgs& A, cudaStream_t s) {
+// tree_flags + level_finalize of one level (tree_level_kernel)
+int launch_tree_level(const TrainArgs& A, int buf, cudaStream_t s) {
+	const size_t fin = (tree_smem_bytes(A.m, A.mtry) + 15) & ~(size_t)15;
 	const size_t bytes = (size_t)A.flagWords * 4;
-	const int inSmem = bytes <= 160 * 1024;   // 1.3M rows per tree; beyond that the bitmap is updated in place in global memory
-	const size_t smem = inSmem ? bytes : 0;
+	const int inSmem = fin + bytes <= 200 * 1024;   // ~1.5M rows per tree; beyond that the bitmap is updated in place in global memory
+	const size_t smem = fin + (inSmem ? bytes : 0);
 	if (A.entry32) {
-		if (smem > 48 * 1024 && allow_max_dyn_smem(tree_flags_kernel<uint32_t>) != cudaSuccess) return -1;
-		tree_flags_kernel<uint32_t><<<A.nTrees, TF_THREADS, smem, s>>>(A, inSmem);
+		if (smem > 48 * 1024 && allow_max_dyn_smem(tree_level_kernel<uint32_t>) != cudaSuccess) return -1;
+		tree_level_kernel<uint32_t><<<A.nTrees, TF_THREADS, smem, s>>>(A, buf, inSmem, (uint32_t)fin);
 	} else {
-		if (smem > 48 * 1024 && allow_max_dyn_smem(tree_flags_kernel<unsigned long long>) != cudaSuccess) return -1;
-		tree_flags_kernel<unsigned long long><<<A.nTrees, TF_THREADS, smem, s>>>(A, inSmem);
+		if (smem > 48 * 1024 && allow_max_dyn_smem(tree_level_kernel<unsigned long long>) != cudaSuccess) return -1;
+		tree_level_kernel<unsigned long long><<<A.nTrees, TF_THREADS, smem, s>>>(A, buf, inSmem, (uint32_t)fin);
 	}
 	return 0;
-}
-void launch_level_finalize(const TrainArgs& A, int buf, cudaStream_t s) {
-	level_finalize_kernel<<<A.nTrees, 32, tree_smem_bytes(A.m, A.mtry), s>>>(A, buf);
 }
 // one launch over all work items in item order (neighbouring segments of a list stay neighbours in time: launching the
 // partition per size class like split search measured 8% slower -- the short segments lose the sector sharing with their

@@ -990,16 +990,37 @@ void hyperSMURF::runFoldsInLanes(uint32_t startingFold, uint32_t endingFold, uin
 			mine += b - a;
 		}
 		// pieces: about two per lane, so that the lanes finish together whatever the fold boundaries do to the shares; one per
-		// lane when the share is small (a piece costs a few ms whatever its size: fold set-up and the latency of ~30 tree levels)
+		// lane when the share is small (a piece costs a few ms whatever its size: fold set-up and the latency of ~30 tree levels).
+		// The target number of pieces is dealt to the fold shares in proportion to their sizes (at least one each).
 		const uint64_t perLane = (mine + lanes - 1) / lanes;
-		const uint32_t maxPiece = unitMode ? (uint32_t)std::max<uint64_t>(laneMinUnits(), perLane >= 64 ? (perLane + 1) / 2 : perLane) : nPart;
+		const uint32_t target = lanes * (perLane >= 64 ? 2u : 1u);
+		std::vector<uint32_t> share(endingFold, 0), cut(endingFold, 0);
+		uint32_t total = 0;
+		for (uint32_t f = startingFold; f < endingFold; f++) {
+			uint32_t a = 0, b = 0;
+			partRange(unitMode, foldsRun, nPart, world, rank, f - foldBase, &a, &b);
+			share[f] = b - a;
+			if (!share[f] || !unitMode) continue;
+			cut[f] = (uint32_t)std::max<uint64_t>(1, ((uint64_t)share[f] * target + mine / 2) / std::max<uint64_t>(mine, 1));
+			cut[f] = std::min(cut[f], std::max(1u, share[f] / std::max(1u, laneMinUnits() / 2)));   // no crumbs
+			total += cut[f];
+		}
+		while (total > target) {                                               // rounding gave too many: merge where the pieces are smallest
+			uint32_t best = endingFold;
+			for (uint32_t f = startingFold; f < endingFold; f++)
+				if (cut[f] > 1 && (best == endingFold || share[f] / cut[f] < share[best] / cut[best])) best = f;
+			if (best == endingFold) break;
+			cut[best]--; total--;
+		}
 		for (uint32_t f = startingFold; f < endingFold; f++) {
 			uint32_t a = 0, b = 0;
 			partRange(unitMode, foldsRun, nPart, world, rank, f - foldBase, &a, &b);
 			if (!unitMode) { pieces.push_back({f, a, b}); continue; }          // fold rule: one piece per fold, even an empty one (its reduce still happens)
-			const uint32_t np = (b - a + maxPiece - 1) / maxPiece;              // equal pieces of the fold share
+			const uint32_t np = cut[f];                                         // equal pieces of the fold share
 			for (uint32_t i = 0; i < np; i++) pieces.push_back({f, a + (uint32_t)((uint64_t)(b - a) * i / np), a + (uint32_t)((uint64_t)(b - a) * (i + 1) / np)});
 		}
+		// largest first: the lanes take the pieces in this order
+		if (unitMode) std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.last - x.first > y.last - y.first; });
 	}
 	const GlibcRand base = *rng;
 	const double* xdev = nullptr;
