@@ -26,7 +26,7 @@ struct DevBuf {
 	cudaError_t ensure(size_t bytes) {
 		if (bytes <= cap) return cudaSuccess;
 		if (p) { cudaFree(p); p = nullptr; cap = 0; }
-		size_t want = bytes + bytes / 16 + 256;
+		size_t want = bytes + bytes / 8 + 256;     // slack: growing means cudaFree + cudaMalloc, which stall every stream of the device
 		cudaError_t e = cudaMalloc(&p, want);
 		if (e == cudaSuccess) cap = want;
 		return e;

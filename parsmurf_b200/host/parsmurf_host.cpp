@@ -1047,8 +1047,12 @@ void hyperSMURF::runFoldsInLanes(uint32_t startingFold, uint32_t endingFold, uin
 				if (foldsOnDevice()) d->attachFolds(dev);
 			}
 			Partition prt(foldManager, ttd.get(), nPart, fp, ratio, mm, nn);
-			for (;;) {
-				const uint32_t pi = next.fetch_add(1);
+			for (uint32_t round = 0;; round++) {
+				// unit sharding: lane li always takes pieces li, li + lanes, ... of the size-ordered list, so a lane's batch sizes -- and
+				// with them its device buffers -- are the same in every CV of a long-lived host (a lane that meets a larger piece than
+				// before has to grow its buffers, and cudaFree / cudaMalloc stall the whole device for tens of ms: seen as one
+				// straggling rank per step on 8 GPUs).  Whole folds (equal sizes) are handed out dynamically.
+				const uint32_t pi = unitMode ? li + round * lanes : next.fetch_add(1);
 				if (pi >= pieces.size()) break;
 				{ std::lock_guard<std::mutex> lk(gate.m); if (gate.failed) break; }
 				const Piece& pc = pieces[pi];
@@ -1385,7 +1389,11 @@ static int run_mode(int mode, const char* forestDir, const double* x, int x_is_d
 			std::string line = "[psm timeline rank " + std::to_string(rank) + "]";
 			char buf[96];
 			for (auto& mk : g_marks) { snprintf(buf, sizeof buf, " %.2f", 1e3 * (mk.second - g_marks[0].second)); line += " | " + mk.first + buf; }
-			fprintf(stderr, "%s\n", line.c_str());
+			// PSM_TIMELINE=1: stderr; PSM_TIMELINE=<path prefix>: appended to <prefix>.rank<r> (ranks sharing one stderr interleave)
+			const char* tl = getenv("PSM_TIMELINE");
+			FILE* out = (tl && strchr(tl, '/')) ? fopen((std::string(tl) + ".rank" + std::to_string(rank)).c_str(), "a") : nullptr;
+			fprintf(out ? out : stderr, "%s\n", line.c_str());
+			if (out) fclose(out);
 		}
 		if (metrics) { metrics[0] = smurfer.auroc; metrics[1] = smurfer.auprc; }
 		if (foldMetrics && mode == MODE_CV) for (uint32_t f = 0; f < nFolds; f++) { foldMetrics[2 * f] = smurfer.foldAuroc[f]; foldMetrics[2 * f + 1] = smurfer.foldAuprc[f]; }
