@@ -83,6 +83,8 @@ struct psm_ctx {
 	    dInjBoot, dInjBootOff, dInjCand, dSortFlags;
 	uint32_t* hCounters = nullptr;   // pinned
 	cudaEvent_t evLevel = nullptr;
+	cudaStream_t copyStream = nullptr;   // score fetch (scores_fetch)
+	cudaEvent_t evCopy = nullptr;
 	void* hStage = nullptr;          // pinned D2H staging
 	size_t hStageCap = 0;
 	uint64_t statSplitBytes = 0, statNodes = 0, statLevels = 0;
@@ -217,6 +219,8 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	if (ctx->hCounters) cudaFreeHost(ctx->hCounters);
 	if (ctx->evLevel) cudaEventDestroy(ctx->evLevel);
 	if (ctx->hStage) cudaFreeHost(ctx->hStage);
+	if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+	if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
 	if (ctx->comm) psm_comm_destroy(ctx);
 	if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
 	delete ctx;
@@ -1247,12 +1251,19 @@ static int scores_fetch(psm_ctx* ctx, double* class1Prob, double* class2Prob, bo
 	const uint32_t n = ctx->n;
 	const size_t total = (size_t)n * (class2Prob ? 2 : 1);                    // doubles wanted: class1 [n], then class2 [n]
 	const uint32_t nChunks = total >= (1u << 20) ? 16u : 1u;
+	// The copies run on a stream of their own, behind everything queued on the context's stream so far: a host that calls this
+	// from a second thread (hyperSMURF::smurfIt does) overlaps the fetch with the global curves, which only read the arrays.
+	// (private events: the context's event pool belongs to the thread that drives the context's stream)
+	if (!ctx->copyStream) CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+	if (!ctx->evCopy) CU(cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming));
+	CU(cudaEventRecord(ctx->evCopy, ctx->stream));
+	CU(cudaStreamWaitEvent(ctx->copyStream, ctx->evCopy, 0));
 	std::vector<cudaEvent_t> ev(nChunks);
 	for (uint32_t c = 0; c < nChunks; c++) {
 		const size_t a0 = total * c / nChunks, a1 = total * (c + 1) / nChunks;
-		CU(cudaMemcpyAsync((double*)ctx->hStage + a0, ctx->dGlob.as<double>() + a0, (a1 - a0) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-		ev[c] = get_event(ctx);
-		CU(cudaEventRecord(ev[c], ctx->stream));
+		CU(cudaMemcpyAsync((double*)ctx->hStage + a0, ctx->dGlob.as<double>() + a0, (a1 - a0) * 8, cudaMemcpyDeviceToHost, ctx->copyStream));
+		CU(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
+		CU(cudaEventRecord(ev[c], ctx->copyStream));
 	}
 	auto outPtr = [&](size_t i) { return i < n ? class1Prob + i : class2Prob + (i - n); };
 	auto moveChunk = [&](uint32_t c) {
@@ -1275,7 +1286,7 @@ static int scores_fetch(psm_ctx* ctx, double* class1Prob, double* class2Prob, bo
 		for (uint32_t t = 0; t < nThreads; t++) th.emplace_back([&, t]() { cudaSetDevice(device); for (uint32_t c = t; c < nChunks; c += nThreads) moveChunk(c); });
 		for (auto& x : th) x.join();
 	}
-	for (auto e : ev) ctx->evPool.push_back(e);
+	for (auto e : ev) cudaEventDestroy(e);
 	return PSM_OK;
 }
 

@@ -837,14 +837,21 @@ void hyperSMURF::smurfIt() {                                                // s
 		}
 	}
 	trace_mark("fold curves done");
-	{
+	// the final scores come to the host while the global curves are computed from the device arrays (plain CV; the inner CVs
+	// and the grid's outer folds compute their curves from the fetched host arrays, so there the fetch comes first)
+	const bool skipFetch = scoresOnRootOnly && world > 1 && rank != 0 && woptimiz == OPT_NO && !inInternalCV;
+	auto fetch = [&]() {
 		PhaseScope ps(PH_SCATTER);
-		const bool skipFetch = scoresOnRootOnly && world > 1 && rank != 0 && woptimiz == OPT_NO && !inInternalCV;
-		if (skipFetch) {}
-		else if (scoresAreOutputs && woptimiz == OPT_NO && !inInternalCV) dev->check(psm_scores_read(dev->ctx, class1Prob, class2Prob));
+		if (skipFetch) return;
+		if (scoresAreOutputs && woptimiz == OPT_NO && !inInternalCV) dev->check(psm_scores_read(dev->ctx, class1Prob, class2Prob));
 		else dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob));
-	}
-	trace_mark("scores on the host");
+	};
+	std::thread fetcher;
+	std::exception_ptr fetchErr;
+	if (!inInternalCV && woptimiz == OPT_NO && !skipFetch)
+		fetcher = std::thread([&]() { try { dev->check(psm_ctx_bind_thread(dev->ctx)); fetch(); } catch (...) { fetchErr = std::current_exception(); } });
+	else { fetch(); trace_mark("scores on the host"); }
+	struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{fetcher};
 	if (inInternalCV) {                                                     // :456-482
 		std::vector<uint32_t> tl; std::vector<double> tp;
 		for (uint32_t f = 0; f < nFolds; f++) {
@@ -865,6 +872,8 @@ void hyperSMURF::smurfIt() {                                                // s
 		auprc = r2[1];
 		if (verboseLevel > VERBSILENT && rank == 0) std::cout << "AUROC: " << auroc << " - AUPRC: " << auprc << std::endl;
 	}
+	if (fetcher.joinable()) { fetcher.join(); trace_mark("scores on the host"); }
+	if (fetchErr) std::rethrow_exception(fetchErr);
 }
 
 // one fold of the CV loop (src/hyperSMURF.cpp:255-396) on Device lane `d`: `prt` is this lane's Partition view, `r` the
