@@ -79,7 +79,7 @@ struct psm_ctx {
 	// train
 	uint32_t T = 0, mtry = 0;
 	TrainArgs A;
-	DevBuf dLists0, dLists1, dInbag, dMt, dTs, dNodes, dNodes8, dSplitFeat, dFlagBits, dItems0, dItems1, dCls, dCand, dRes, dDec, dPtask, dCounters, dStats, dSeeds,
+	DevBuf dLists0, dLists1, dInbag, dInbagT, dMt, dTs, dNodes, dNodes8, dSplitFeat, dFlagBits, dItems0, dItems1, dCls, dCand, dRes, dDec, dPtask, dCounters, dStats, dSeeds,
 	    dInjBoot, dInjBootOff, dInjCand, dSortFlags;
 	uint32_t* hCounters = nullptr;   // pinned
 	cudaEvent_t evLevel = nullptr;
@@ -209,7 +209,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf* bufs[] = {&ctx->fbKeysA, &ctx->fbKeysB, &ctx->fbValsA, &ctx->fbValsB, &ctx->fbHist, &ctx->fbCounts, &ctx->dFoldIds, &ctx->dPosList, &ctx->dNegList, &ctx->sKeysA, &ctx->sKeysB, &ctx->sValsA, &ctx->sValsB, &ctx->sHist, &ctx->sJ, &ctx->sDraws, &ctx->sIn, &ctx->xOwned, &ctx->dPos, &ctx->dNeg, &ctx->dTest, &ctx->dXp, &ctx->dNN, &ctx->dNNd, &ctx->dKnnScratch, &ctx->dKnnTc, &ctx->dClass12,
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
-	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dSplitFeat, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1, &ctx->dCls,
+	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dInbagT, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dSplitFeat, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1, &ctx->dCls,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dPtask, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
 	                  &ctx->dInjCand, &ctx->dSortFlags, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cIdx, &ctx->cFoldScores, &ctx->cScratch, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
 	                  &ctx->cScores, &ctx->cKeysA, &ctx->cKeysB, &ctx->cValsA, &ctx->cValsB, &ctx->cHist};
@@ -759,9 +759,11 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		launch_inbag_from_ids(A, ctx->dInjBoot.as<unsigned long long>(), ctx->dInjBootOff.as<uint64_t>(), s);
 		CU(cudaStreamSynchronize(s));   // `off` is a local
 	}
+	const bool listsMulti = entry32 && T <= 16 && !getenv("PSM_LISTS_PER_TREE");
+	if (listsMulti) ENSURE(ctx->dInbagT, (size_t)nB * stride * 16);
 	{
-		ProfScope ps(ctx, K_LISTS, 1);
-		launch_build_lists(A, s);
+		ProfScope ps(ctx, K_LISTS, listsMulti ? 2 : 1);
+		launch_build_lists(A, listsMulti ? ctx->dInbagT.as<unsigned char>() : nullptr, s);
 	}
 	if (entry32) {
 		// the compact 4-byte entries hold multiplicities up to 15; fall back to the 8-byte layout if a tree exceeds that
@@ -774,7 +776,7 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 			A.lists[0] = ctx->dLists0.p; A.lists[1] = ctx->dLists1.p; A.entry32 = 0;
 			CU(cudaMemsetAsync(A.counters, 0, CNT_COUNT * 4, s));
 			ProfScope ps(ctx, K_LISTS, 1);
-			launch_build_lists(A, s);
+			launch_build_lists(A, nullptr, s);
 		}
 	}
 	{

@@ -71,7 +71,8 @@ int launch_feature_sort_smem(const double* Dall, const PartDesc* parts, uint32_t
 size_t tree_smem_bytes(uint32_t m, uint32_t mtry);
 void launch_bootstrap(const TrainArgs& A, const uint32_t* forestSeeds, cudaStream_t s);
 void launch_inbag_from_ids(const TrainArgs& A, const unsigned long long* ids, const uint64_t* idOffsets, cudaStream_t s);
-void launch_build_lists(const TrainArgs& A, cudaStream_t s);
+// inbagT: scratch of nParts * stride * 16 bytes for the all-trees-at-once variant (compact entries, T <= 16), or NULL
+void launch_build_lists(const TrainArgs& A, unsigned char* inbagT, cudaStream_t s);
 int launch_init_trees(const TrainArgs& A, cudaStream_t s);
 void launch_split_search(const TrainArgs& A, const uint32_t* clsCount, int buf, cudaStream_t s);
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);

@@ -1,15 +1,15 @@
 #!/bin/bash
 # Collect the round's measurement set on a B200 box (run through gpurun from the repo root):
-#   gpurun --timeout 1500 -- 'bash scripts/collect_profiles.sh r01'
+#   gpurun --timeout 1500 -- 'bash scripts/collect_profiles.sh r02'
 # Every ncu pass only runs after the same command exited 0 without ncu; numbers printed under ncu are never bench values.
 # gpurun copies back at most 64 MiB, so the .ncu-rep files are reduced to CSV on the box (scripts/summarize_profiles.py reads
 # the CSVs).  The ncu passes run the CV with the folds one after the other (--fold-lanes 1): ncu serialises kernels anyway and
 # the launch order then reads level by level.
 set -u
-TAG=${1:-r01}
+TAG=${1:-r02}
 OUT=gpurun_out/profiles_$TAG
 mkdir -p "$OUT"
-B="python bench.py --steps 5 --warmup 3"
+B="python bench.py --steps 5 --warmup 3 --no-also"
 S="python bench.py --steps 1 --warmup 0 --single --fold-lanes 1"
 
 $B > "$OUT/${TAG}_bench_cfg2_1gpu.json" 2> "$OUT/bench.log" || { echo "bench failed"; tail -20 "$OUT/bench.log"; exit 1; }
@@ -24,10 +24,10 @@ ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum 
 	--log-file "$OUT/${TAG}_dram_split_search_all_levels.csv" $S > "$OUT/ncu_dram.log" 2>&1
 
 # full-section captures: a window of launches from the first fold for the per-level kernels, one launch for the per-fold ones
-for K in split_search_kernel partition_lists_kernel predict_compact_kernel feature_sort_split_kernel build_lists_kernel; do
+for K in split_search_kernel partition_lists_kernel predict_compact_kernel feature_sort_radix_kernel build_lists_kernel tree_level_kernel split_select_kernel; do
 	case $K in
 		split_search_kernel) SKIP=0; CNT=24 ;;
-		partition_lists_kernel) SKIP=0; CNT=12 ;;
+		partition_lists_kernel|tree_level_kernel|split_select_kernel) SKIP=0; CNT=12 ;;
 		*) SKIP=0; CNT=1 ;;
 	esac
 	ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip $SKIP --launch-count $CNT \

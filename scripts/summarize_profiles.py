@@ -100,7 +100,8 @@ def main():
                "| kernel | launches | ms | share | live ms (bench, events) |", "|---|---|---|---|---|"]
         live = bench["roofline"]["kernel_ms_per_step"] if bench else {}
         m2 = {"split_search_kernel": "split_search", "partition_lists_kernel": "partition_lists", "feature_sort_split_kernel": "feature_sort", "predict_compact_kernel": "predict",
-              "build_lists_kernel": "build_lists", "level_finalize_kernel": "level_finalize", "bootstrap_kernel": "bootstrap", "assemble_kernel": "assemble"}
+              "build_lists_kernel": "build_lists", "level_finalize_kernel": "level_finalize", "tree_level_kernel": "level_finalize", "split_select_kernel": "split_select",
+              "feature_sort_radix_kernel": "feature_sort", "bootstrap_kernel": "bootstrap", "assemble_kernel": "assemble"}
         for k in sorted(L, key=lambda k_: -L[k_]["ms"]):
             lv = live.get(m2.get(k, ""), None)
             md.append("| %s | %d | %.2f | %.1f%% | %s |" % (k, L[k]["launches"], L[k]["ms"], 100 * L[k]["ms"] / tot, ("%.2f" % lv) if lv is not None else ""))
