@@ -971,10 +971,11 @@ int psm_batch_predict_accumulate(psm_ctx* ctx, uint32_t nPartsTotal) {
 	{
 		ProfScope ps(ctx, K_PREDICT, 3);
 		launch_pack_forest(ctx->A.nodes, ctx->A.ts, ctx->A.NC, ctx->A.nTrees, ctx->dNodes8.p, ctx->stream);
-		if (launch_predict(ctx->x, ctx->m, ctx->dTest.as<uint32_t>(), ctx->Nte, ctx->A.nodes, ctx->dNodes8.p, ctx->A.NC, ctx->A.ts, ctx->maxNodes, ctx->nB, ctx->T,
-		                   ctx->dPredScratch.as<double>(), ctx->stream))
-			return fail(ctx, PSM_E_CUDA, "predict_accumulate: cannot configure shared memory");
-		launch_accumulate(ctx->dPredScratch.as<double>(), ctx->Nte, ctx->nB, 1.0 / (double)nPartsTotal, ctx->dClass12.as<double>(), ctx->stream);
+		const double divider = 1.0 / (double)nPartsTotal;
+		const int how = launch_predict(ctx->x, ctx->m, ctx->dTest.as<uint32_t>(), ctx->Nte, ctx->A.nodes, ctx->dNodes8.p, ctx->A.NC, ctx->A.ts, ctx->maxNodes, ctx->nB, ctx->T,
+		                               ctx->dPredScratch.as<double>(), divider, ctx->dClass12.as<double>(), ctx->stream);
+		if (how < 0) return fail(ctx, PSM_E_CUDA, "predict_accumulate: cannot configure shared memory");
+		if (how == 0) launch_accumulate(ctx->dPredScratch.as<double>(), ctx->Nte, ctx->nB, divider, ctx->dClass12.as<double>(), ctx->stream);
 	}
 	CU(cudaGetLastError());
 	return PSM_OK;

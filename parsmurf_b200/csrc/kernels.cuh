@@ -83,8 +83,10 @@ void glibc_window_jump(uint32_t* w31, uint64_t n);
 int launch_glibc_rand_fill(const uint32_t* w31, unsigned long long count, uint32_t* scratchDev, int32_t* out, cudaStream_t s);
 // predict.cu
 void launch_pack_forest(const Node16* nodes, const TreeState* ts, uint32_t NC, uint32_t nTrees, void* nodes8, cudaStream_t s);
+// > 0: the fold scores class12 were updated directly (skip launch_accumulate); 0: the partition means are in scratch; < 0: error
 int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_t Nte, const Node16* nodes, const void* nodes8, uint32_t NC,
-                   const TreeState* ts, uint32_t maxNodes, uint32_t nPartsBatch, uint32_t T, double* scratch, cudaStream_t s);
+                   const TreeState* ts, uint32_t maxNodes, uint32_t nPartsBatch, uint32_t T, double* scratch, double divider, double* class12,
+                   cudaStream_t s);
 void launch_accumulate(const double* scratch, uint32_t Nte, uint32_t nPartsBatch, double divider, double* class12, cudaStream_t s);
 // curves.cu
 int launch_curves(const unsigned char* labelsSorted, uint64_t N, uint32_t totP, uint32_t totN, uint32_t* tpScratch,

@@ -227,11 +227,15 @@ __global__ void __launch_bounds__(256) pack_forest_kernel(const Node16* __restri
 constexpr uint32_t NBUF = PSM_NBUF;   // pipeline depth: the TMA runs NBUF-1 stages ahead of the traversal (deeper pipelines cost occupancy and measured slower)
 
 // TPS = trees per pipeline stage (PSM_PREDICT_TPS=1|2|4|8 overrides the default of 1, see launch_predict).
-template <uint32_t TPS>
+// DIRECT (one partition chunk: the CTA walks every forest of the batch for its rows): the partition means are added into the
+// fold score buffer right here, in ascending partition order with the arithmetic of accumulate_kernel (sampler.cpp:121-132) --
+// no [partition][row] scratch plane is written and read back (2 x 22 GB per BASELINE configs[2] fold).
+template <uint32_t TPS, bool DIRECT>
 __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __restrict__ x, uint32_t m, const uint32_t* __restrict__ testIdx,
                                                               uint32_t Nte, const Node16* __restrict__ nodes, const Node8* __restrict__ nodes8,
                                                               uint32_t NC, const TreeState* __restrict__ ts, uint32_t nPartsBatch, uint32_t T,
-                                                              uint32_t pch, uint32_t maxNodes, double* __restrict__ scratch) {
+                                                              uint32_t pch, uint32_t maxNodes, double* __restrict__ scratch, double divider,
+                                                              double* __restrict__ class12) {
 	extern __shared__ __align__(128) unsigned char smraw[];
 	float* tile = reinterpret_cast<float*>(smraw);                                     // [m][PT]
 	Node8* tbuf = reinterpret_cast<Node8*>(smraw + (size_t)m * PT * sizeof(float));    // [NBUF][TPS][maxNodes]
@@ -303,6 +307,8 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 	double s0 = 0.0, s1 = 0.0;
 	uint32_t tInPart = 0;                                 // trees of the current partition already summed
 	double* outp = scratch + (size_t)p0 * 2 * Nte + row;  // scratch[(pl*2 + c)*Nte + row] of the current partition
+	double c1 = 0.0, c2 = 0.0;                            // DIRECT: this row's fold scores
+	if (DIRECT && valid) { c1 = class12[row]; c2 = class12[(size_t)Nte + row]; }
 	for (uint32_t st = 0; st < nStages; st++) {
 		const uint32_t b = st % NBUF;
 		if (tid == 0 && st + NBUF - 1 < nStages) {        // its buffer was released by the barrier that ended stage st-1
@@ -365,15 +371,21 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 				s0 = __dadd_rn(s0, f0);                                      // ForestProbability.cpp:136-141
 				s1 = __dadd_rn(s1, f1);
 				if (++tInPart == T) {
-					outp[0] = __ddiv_rn(s0, Td);                             // :145-149
-					outp[Nte] = __ddiv_rn(s1, Td);
-					outp += (size_t)2 * Nte;
+					if (DIRECT) {
+						c1 = __dadd_rn(c1, __dmul_rn(__ddiv_rn(s0, Td), divider));
+						c2 = __dadd_rn(c2, __dmul_rn(__ddiv_rn(s1, Td), divider));
+					} else {
+						outp[0] = __ddiv_rn(s0, Td);                             // :145-149
+						outp[Nte] = __ddiv_rn(s1, Td);
+						outp += (size_t)2 * Nte;
+					}
 					s0 = 0.0; s1 = 0.0; tInPart = 0;
 				}
 			}
 		}
 		__syncthreads();
 	}
+	if (DIRECT && valid) { class12[row] = c1; class12[(size_t)Nte + row] = c2; }
 }
 
 __global__ void __launch_bounds__(256) accumulate_kernel(const double* __restrict__ scratch, uint32_t Nte, uint32_t nPartsBatch,
@@ -394,8 +406,11 @@ void launch_pack_forest(const Node16* nodes, const TreeState* ts, uint32_t NC, u
 	pack_forest_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(nodes, ts, NC, nTrees, reinterpret_cast<Node8*>(nodes8));
 }
 
+// returns 1 when the fold scores were updated directly (no scratch plane: the caller skips launch_accumulate), 0 when the
+// per-partition means are in `scratch`, -1 on a configuration error
 int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_t Nte, const Node16* nodes, const void* nodes8, uint32_t NC,
-                   const TreeState* ts, uint32_t maxNodes, uint32_t nPartsBatch, uint32_t T, double* scratch, cudaStream_t s) {
+                   const TreeState* ts, uint32_t maxNodes, uint32_t nPartsBatch, uint32_t T, double* scratch, double divider, double* class12,
+                   cudaStream_t s) {
 	if (Nte == 0 || nPartsBatch == 0) return 0;
 	{
 		// compact path: fp32 tile + 8-byte nodes (feature < 2047, child id < 2^20)
@@ -418,17 +433,23 @@ int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_
 			chunks = (nPartsBatch + pch - 1) / pch;
 			const dim3 grid(rowTiles, chunks);
 			const Node8* n8 = reinterpret_cast<const Node8*>(nodes8);
+			const bool direct = chunks == 1 && class12 != nullptr && !getenv("PSM_PREDICT_SCRATCH");
 #define PSM_LAUNCH_COMPACT(K)                                                                                                              \
 	do {                                                                                                                                   \
-		if (allow_max_dyn_smem(predict_compact_kernel<K>) != cudaSuccess) return -1; \
-		predict_compact_kernel<K><<<grid, PT, smemC, s>>>(x, m, testIdx, Nte, nodes, n8, NC, ts, nPartsBatch, T, pch, mn, scratch);        \
+		if (direct) {                                                                                                                      \
+			if (allow_max_dyn_smem(predict_compact_kernel<K, true>) != cudaSuccess) return -1;                                             \
+			predict_compact_kernel<K, true><<<grid, PT, smemC, s>>>(x, m, testIdx, Nte, nodes, n8, NC, ts, nPartsBatch, T, pch, mn, scratch, divider, class12);  \
+		} else {                                                                                                                           \
+			if (allow_max_dyn_smem(predict_compact_kernel<K, false>) != cudaSuccess) return -1;                                            \
+			predict_compact_kernel<K, false><<<grid, PT, smemC, s>>>(x, m, testIdx, Nte, nodes, n8, NC, ts, nPartsBatch, T, pch, mn, scratch, divider, class12); \
+		}                                                                                                                                  \
 	} while (0)
 			if (tps == 8) PSM_LAUNCH_COMPACT(8);
 			else if (tps == 4) PSM_LAUNCH_COMPACT(4);
 			else if (tps == 2) PSM_LAUNCH_COMPACT(2);
 			else PSM_LAUNCH_COMPACT(1);
 #undef PSM_LAUNCH_COMPACT
-			return 0;
+			return direct ? 1 : 0;
 		}
 	}
 	{
