@@ -719,18 +719,7 @@ void hyperSMURF::smurfIt() {                                                // s
 				for (uint32_t f = 0; f + 1 < nFolds; f++) posSum += inner.ttd->trngPosNum[f];
 				for (uint32_t i = 0; i < G; i++) drawOff[i + 1] = drawOff[i] + (uint64_t)gridParams[i].nParts * posSum * gridParams[i].fp * (mm + 1);
 			}
-			std::vector<uint32_t> owner(G, 0);
-			if (shardGrid) {                                                   // longest-processing-time first; cost ~ partitions x training rows
-				std::vector<uint32_t> order(G);
-				std::iota(order.begin(), order.end(), 0u);
-				auto cost = [&](uint32_t i) { return (uint64_t)gridParams[i].nParts * (gridParams[i].fp + 1) * (gridParams[i].ratio ? gridParams[i].ratio + 1 : 4) * gridParams[i].nTrees; };
-				std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost(a) > cost(b); });
-				std::vector<uint64_t> load(world, 0);
-				for (uint32_t i : order) {
-					const uint32_t r = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
-					owner[i] = r; load[r] += cost(i);
-				}
-			}
+			const std::vector<uint32_t> owner = shardGrid ? gridOwners(gridParams, world) : std::vector<uint32_t>(G, 0);
 			const GlibcRand base = *rng;
 			GlibcRand local = base;
 			if (shardGrid) inner.rng = &local;
@@ -887,6 +876,46 @@ struct hyperSMURF::FoldGate {
 	bool failed = false;
 };
 
+// which rank runs the inner CV of each grid point: longest-processing-time first over cost ~ partitions x training rows x trees
+std::vector<uint32_t> hyperSMURF::gridOwners(const std::vector<GridParams>& grid, uint32_t world) {
+	const uint32_t G = (uint32_t)grid.size();
+	std::vector<uint32_t> owner(G, 0), order(G);
+	std::iota(order.begin(), order.end(), 0u);
+	auto cost = [&](uint32_t i) { return (uint64_t)grid[i].nParts * (grid[i].fp + 1) * (grid[i].ratio ? grid[i].ratio + 1 : 4) * grid[i].nTrees; };
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost(a) > cost(b); });
+	std::vector<uint64_t> load(std::max(world, 1u), 0);
+	for (uint32_t i : order) {
+		const uint32_t r = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+		owner[i] = r; load[r] += cost(i);
+	}
+	return owner;
+}
+
+// how many pieces each fold share of a unit-sharded rank is cut into for `lanes` fold lanes (see runFoldsInLanes)
+std::vector<uint32_t> hyperSMURF::laneCuts(const std::vector<uint32_t>& share, uint32_t lanes) {
+	uint64_t mine = 0;
+	for (uint32_t v : share) mine += v;
+	std::vector<uint32_t> cut(share.size(), 0);
+	if (!mine || !lanes) return cut;
+	const uint64_t perLane = (mine + lanes - 1) / lanes;
+	const uint32_t target = lanes * (perLane >= 64 ? 2u : 1u);
+	uint32_t total = 0;
+	for (size_t f = 0; f < share.size(); f++) {
+		if (!share[f]) continue;
+		cut[f] = (uint32_t)std::max<uint64_t>(1, ((uint64_t)share[f] * target + mine / 2) / mine);
+		cut[f] = std::min(cut[f], std::max(1u, share[f] / std::max(1u, laneMinUnits() / 2)));   // no crumbs
+		total += cut[f];
+	}
+	while (total > target) {                                               // rounding gave too many: merge where the pieces are smallest
+		size_t best = share.size();
+		for (size_t f = 0; f < share.size(); f++)
+			if (cut[f] > 1 && (best == share.size() || share[f] / cut[f] < share[best] / cut[best])) best = f;
+		if (best == share.size()) break;
+		cut[best]--; total--;
+	}
+	return cut;
+}
+
 void hyperSMURF::partRange(bool units, uint32_t nFoldsRun, uint32_t nPart, uint32_t world, uint32_t rank, uint32_t foldIdx, uint32_t* first, uint32_t* last) {
 	auto chunk = [&](uint64_t total, uint64_t* a, uint64_t* b) {           // total/world (+1 for the first total%world ranks), contiguous
 		const uint64_t base = total / world, rem = total % world;
@@ -992,35 +1021,16 @@ void hyperSMURF::runFoldsInLanes(uint32_t startingFold, uint32_t endingFold, uin
 	struct Piece { uint32_t fold, first, last; };
 	std::vector<Piece> pieces;
 	{
-		uint64_t mine = 0;
-		for (uint32_t f = startingFold; f < endingFold; f++) {
-			uint32_t a = 0, b = 0;
-			partRange(unitMode, foldsRun, nPart, world, rank, f - foldBase, &a, &b);
-			mine += b - a;
-		}
 		// pieces: about two per lane, so that the lanes finish together whatever the fold boundaries do to the shares; one per
 		// lane when the share is small (a piece costs a few ms whatever its size: fold set-up and the latency of ~30 tree levels).
 		// The target number of pieces is dealt to the fold shares in proportion to their sizes (at least one each).
-		const uint64_t perLane = (mine + lanes - 1) / lanes;
-		const uint32_t target = lanes * (perLane >= 64 ? 2u : 1u);
-		std::vector<uint32_t> share(endingFold, 0), cut(endingFold, 0);
-		uint32_t total = 0;
+		std::vector<uint32_t> share(endingFold, 0);
 		for (uint32_t f = startingFold; f < endingFold; f++) {
 			uint32_t a = 0, b = 0;
 			partRange(unitMode, foldsRun, nPart, world, rank, f - foldBase, &a, &b);
-			share[f] = b - a;
-			if (!share[f] || !unitMode) continue;
-			cut[f] = (uint32_t)std::max<uint64_t>(1, ((uint64_t)share[f] * target + mine / 2) / std::max<uint64_t>(mine, 1));
-			cut[f] = std::min(cut[f], std::max(1u, share[f] / std::max(1u, laneMinUnits() / 2)));   // no crumbs
-			total += cut[f];
+			share[f] = unitMode ? b - a : 0;
 		}
-		while (total > target) {                                               // rounding gave too many: merge where the pieces are smallest
-			uint32_t best = endingFold;
-			for (uint32_t f = startingFold; f < endingFold; f++)
-				if (cut[f] > 1 && (best == endingFold || share[f] / cut[f] < share[best] / cut[best])) best = f;
-			if (best == endingFold) break;
-			cut[best]--; total--;
-		}
+		const std::vector<uint32_t> cut = laneCuts(share, lanes);
 		for (uint32_t f = startingFold; f < endingFold; f++) {
 			uint32_t a = 0, b = 0;
 			partRange(unitMode, foldsRun, nPart, world, rank, f - foldBase, &a, &b);
@@ -1302,6 +1312,16 @@ static bool shard_units_default() {
 	if (v >= 0) return v != 0;
 	const char* e = getenv("PSM_SHARD");
 	return !(e && std::string(e) == "fold");
+}
+void psmh_grid_owners(const uint32_t* grid, uint32_t G, uint32_t world, uint32_t* owners) {
+	std::vector<parsmurf::GridParams> gp(G);
+	for (uint32_t i = 0; i < G; i++) gp[i] = parsmurf::GridParams{grid[6 * i], grid[6 * i + 1], grid[6 * i + 2], grid[6 * i + 3], grid[6 * i + 4], grid[6 * i + 5], 0, 0};
+	const std::vector<uint32_t> o = parsmurf::hyperSMURF::gridOwners(gp, world);
+	for (uint32_t i = 0; i < G; i++) owners[i] = o[i];
+}
+void psmh_lane_cuts(const uint32_t* share, uint32_t nShares, uint32_t lanes, uint32_t* cuts) {
+	const std::vector<uint32_t> c = parsmurf::hyperSMURF::laneCuts(std::vector<uint32_t>(share, share + nShares), lanes);
+	for (uint32_t i = 0; i < nShares; i++) cuts[i] = c[i];
 }
 void psmh_part_range(int units, uint32_t nFoldsRun, uint32_t nPart, uint32_t world, uint32_t rank, uint32_t foldIdx, uint32_t* first, uint32_t* last) {
 	parsmurf::hyperSMURF::partRange(units != 0, nFoldsRun, nPart, world, rank, foldIdx, first, last);

@@ -314,6 +314,10 @@ public:
 	bool shardGridPoints = true;
 	// [first, last) of fold `fold`'s partitions that belong to `rank` under either rule (src/MPIHelper.cpp:29-37 for the first)
 	static void partRange(bool units, uint32_t nFoldsRun, uint32_t nPart, uint32_t world, uint32_t rank, uint32_t foldIdx, uint32_t* first, uint32_t* last);
+	// grid search on several ranks: the rank that runs the inner CV of each grid point (cost-balanced, the same on every rank)
+	static std::vector<uint32_t> gridOwners(const std::vector<GridParams>& grid, uint32_t world);
+	// unit sharding with fold lanes: how many pieces each fold share (partitions of fold f owned by this rank) is cut into
+	static std::vector<uint32_t> laneCuts(const std::vector<uint32_t>& share, uint32_t lanes);
 	int curvesTieMode = 0;
 	bool evalFoldCurves = true;
 	// Folds of a CV are independent until the score merge: with foldLanes > 1 that many folds are in flight at once, each

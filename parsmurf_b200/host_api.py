@@ -302,6 +302,28 @@ def part_range(units, n_folds, n_parts, world, rank, fold):
     return int(a[0]), int(b[0])
 
 
+def grid_owners(grid, world):
+    """rank that runs the inner CV of each grid point in a multi-rank grid search (hyperSMURF::gridOwners)"""
+    L = hlib()
+    L.psmh_grid_owners.argtypes = [u32p, u32, u32, u32p]
+    L.psmh_grid_owners.restype = None
+    g = np.ascontiguousarray(np.array(grid, np.uint32).reshape(-1, 6))
+    out = np.zeros(len(g), np.uint32)
+    L.psmh_grid_owners(_p(g, u32p), len(g), world, _p(out, u32p))
+    return out
+
+
+def lane_cuts(shares, lanes):
+    """pieces per fold share of a unit-sharded rank (hyperSMURF::laneCuts)"""
+    L = hlib()
+    L.psmh_lane_cuts.argtypes = [u32p, u32, u32, u32p]
+    L.psmh_lane_cuts.restype = None
+    s_ = np.ascontiguousarray(shares, np.uint32)
+    out = np.zeros(len(s_), np.uint32)
+    L.psmh_lane_cuts(_p(s_, u32p), len(s_), lanes, _p(out, u32p))
+    return out
+
+
 def rand_fill(seed, count):
     out = np.zeros(count, np.int32)
     hlib().psmh_rand_fill(seed, _p(out, i32p), count)

@@ -220,3 +220,39 @@ def test_parallel_sort_replica_equals_std_sort(oracle):
             perm = np.zeros(len(s), np.uint32)
             assert L.psm_host_sort_permutation(s.ctypes.data_as(C.POINTER(C.c_double)), len(s), perm.ctypes.data_as(C.POINTER(C.c_uint32)), threads) == 0
             assert np.array_equal(perm.astype(np.uint64), want), (len(s), threads)
+
+
+def test_grid_points_are_dealt_to_the_ranks_by_cost():
+    """multi-rank grid search (hyperSMURF::gridOwners): every grid point has exactly one owner, the same table on every rank, and the
+    longest-processing-time deal stays within 4/3 of the best possible balance"""
+    import itertools
+    from parsmurf_b200 import host_api as H
+    grid = [(a, b, 1, 5, 10, c) for a, b, c in itertools.product([10, 20, 30], [1, 2], [5, 7, 10])]      # cfgEx/gridTune.json
+    cost = np.array([g[0] * (g[1] + 1) * (g[2] + 1) * g[4] for g in grid], np.float64)
+    for world in (1, 2, 3, 8, 32):
+        own = H.grid_owners(grid, world)
+        assert own.shape == (len(grid),) and own.max() < world
+        assert np.array_equal(own, H.grid_owners(grid, world))
+        load = np.bincount(own, weights=cost, minlength=world)
+        assert load.sum() == cost.sum()
+        assert load.max() <= max(cost.max(), 4.0 / 3.0 * cost.sum() / world + cost.max() / 3.0) + 1e-9
+        if world <= len(grid):
+            assert (load > 0).all()
+
+
+def test_lane_pieces_cover_the_fold_shares():
+    """unit sharding with fold lanes (hyperSMURF::laneCuts): every non-empty fold share gets at least one piece, the pieces never
+    outnumber the target of one or two per lane (unless there are more shares than that), and tiny shares are not crumbled"""
+    from parsmurf_b200 import host_api as H
+    for shares, lanes in (([0, 11, 52, 0, 0], 4), ([63, 0, 0, 0, 0], 4), ([100, 100, 50, 0, 0], 4), ([1000, 250] + [0] * 8, 4), ([5, 5, 5, 5, 5], 2),
+                          ([0, 0, 0], 4), ([37, 26, 0, 0, 0], 1), ([3, 0, 0], 4)):
+        cuts = H.lane_cuts(shares, lanes)
+        mine = sum(shares)
+        for s_, c in zip(shares, cuts):
+            assert (c == 0) == (s_ == 0)
+            assert c <= max(1, s_)
+        if mine:
+            per_lane = -(-mine // lanes)
+            target = lanes * (2 if per_lane >= 64 else 1)
+            assert cuts.sum() <= max(target, sum(1 for s_ in shares if s_))
+    assert list(H.lane_cuts([0, 11, 52, 0, 0], 4)) == [0, 1, 3, 0, 0]          # BASELINE configs[1] on 8 GPUs, rank 3: four pieces for four lanes
