@@ -247,13 +247,18 @@ class Rig:
         torch = self.torch
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]   # one more event per step: the spread of the steps (this rank)
         e0.record(self.stream)
-        outs = [fn() for _ in range(steps)]
+        outs = []
+        for i in range(steps):
+            outs.append(fn())
+            marks[i].record(self.stream)
         e1.record(self.stream)
         self.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
         if self.world > 1:
             self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        self.last_step_ms = [round(([e0] + marks)[i].elapsed_time(marks[i]), 3) for i in range(steps)]
         return float(ms.item()), outs
 
     def stage(self, x):
@@ -282,6 +287,7 @@ def measure_cv(rig, w, x_pinned, x_dev, y, f, steps, warmup, roof_steps, with_br
     if rig.rank == 0:
         sampler.start()
     ms_dev, outs = rig.timed(run_dev, steps)
+    each_dev = list(rig.last_step_ms)
     clocks = sampler.stop() if rig.rank == 0 else None
     for _ in range(min(warmup, 1)):
         run_e2e()
@@ -297,12 +303,12 @@ def measure_cv(rig, w, x_pinned, x_dev, y, f, steps, warmup, roof_steps, with_br
 
     parts = w["nParts"] * w["nFolds"]
     lanes = outs_e2e[0].get("fold_lanes") or 1
-    # per-step traffic of the e2e path (this rank), counted from what is copied: x once, the 0/1 labels once per fold lane, the
-    # per-class fold lists once (n example ids: every fold's index arrays are assembled and shuffled on the device); SMOTE and
-    # shuffle draws are generated on the device (no H2D).  Back: class1Prob/class2Prob once (2 x n f64), AUROC/AUPRC per
-    # fold and global, a 32-byte status word per tree level.
-    h2d = x_host.nbytes + 4 * n * lanes + 4 * n
-    d2h = 16 * n + (w["nFolds"] + 1) * 16 + 32 * int(sum(o["stats"]["levels"] for o in outs_e2e) / max(steps, 1))
+    # per-step traffic of the e2e path (this rank), counted from what is copied: x once, and -- because a new upload of x drops
+    # the resident labels and fold ids -- the 0/1 labels (4n) and the fold ids (4n) once each; the per-class fold lists, every
+    # fold's index arrays and the SMOTE / shuffle draws are built on the device (no H2D).  Back: class1Prob/class2Prob once
+    # (2 x n f64; rank 0 only in multi-rank runs), AUROC/AUPRC per fold and global, the fold sizes, a 32-byte status word per tree level.
+    h2d = x_host.nbytes + 4 * n + 4 * n
+    d2h = (16 * n if rig.rank == 0 else 0) + (w["nFolds"] + 1) * 16 + 8 * w["nFolds"] + 32 * int(sum(o["stats"]["levels"] for o in outs_e2e) / max(steps, 1))
     km = {k_: sum(o["kernel_ms"][k_] for o in outs_roof) for k_ in outs_roof[0]["kernel_ms"]}
     kl = {k_: sum(o["kernel_launches"][k_] for o in outs) for k_ in outs[0]["kernel_launches"]}
     kl_roof = sum(o["kernel_launches"]["split_search"] for o in outs_roof)
@@ -318,7 +324,7 @@ def measure_cv(rig, w, x_pinned, x_dev, y, f, steps, warmup, roof_steps, with_br
     if brk is not None:
         roofline["kernel_ms_per_step"] = dict(brk["kernel_ms"])
         roofline["kernel_ms_per_step_source"] = "one extra untimed step (fold lanes = 1) with all kernel classes under CUDA events"
-    return dict(ms_dev=ms_dev, ms_e2e=ms_e2e, outs=outs, outs_e2e=outs_e2e, clocks=clocks, parts=parts, h2d=int(h2d), d2h=int(d2h), kl=kl,
+    return dict(ms_dev=ms_dev, ms_e2e=ms_e2e, each_dev=each_dev, outs=outs, outs_e2e=outs_e2e, clocks=clocks, parts=parts, h2d=int(h2d), d2h=int(d2h), kl=kl,
                 roofline=roofline, scores=scores, lanes=outs[0].get("fold_lanes"), kl_roof=kl_roof,
                 curves={"mode": "auto", "mixed_tie_pairs_per_step": sum(o["stats"]["mixed_tie_pairs"] for o in outs) // max(steps, 1),
                         "host_sorts_per_step": sum(o["stats"]["curves_host_sorts"] for o in outs) / max(steps, 1),
@@ -435,7 +441,7 @@ def run_ours(args, w):
     line = None
     if rank == 0:
         line = {"metric": "partitions/sec", "value": value, "unit": "partitions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "ms_per_step": ms_dev / args.steps, "ms_each_step_rank0": r["each_dev"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, w), "fold_lanes": r["lanes"], "clocks": r["clocks"],
                 "e2e": {"value": e2e_value, "unit": "partitions/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
                 "gpu_launches": int(sum(r["kl"].values())), "roofline": roofline,
@@ -507,8 +513,8 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
