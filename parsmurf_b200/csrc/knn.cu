@@ -8,6 +8,12 @@
 // subtract / multiply / add (no FMA), i.e. the bit pattern ANN's annDist loop produces, so the neighbour
 // ORDER (which SMOTE indexes by rank, samplerKNN.cpp:95) is the reference's; exact ties are broken by the
 // lower index like ANNbruteForce (src/ann_1.1.2/src/brute.cpp:54-78).
+// Caveats: (1) among EXACTLY equidistant neighbours the reference's kd-tree keeps the first one its traversal visits
+// (ANNmin_k::insert), which depends on the tree layout, not on the index -- with duplicated or discrete feature vectors the
+// rank of two equidistant positives (and which of them falls inside k) may therefore differ from the reference's; continuous
+// data (every BASELINE config) has no such ties.  (2) The reference searches over m+1 coordinates, the label column included
+// (src/samplerKNN.cpp:60-66); every positive carries the same label value 1.0 there (src/fileImport.cpp:88-91), so the extra
+// coordinate adds exactly 0.0 to every distance and the m-coordinate distances here are the same doubles.
 //
 // Two kernels: a 64x64-tiled pairwise distance kernel (fp64 CUDA cores; B200 keeps full-rate FP64) and a
 // warp-per-query top-k selection with register-resident sorted lists merged by warp shuffles.
