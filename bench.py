@@ -307,8 +307,11 @@ def measure_cv(rig, w, x_pinned, x_dev, y, f, steps, warmup, roof_steps, with_br
     # the resident labels and fold ids -- the 0/1 labels (4n) and the fold ids (4n) once each; the per-class fold lists, every
     # fold's index arrays and the SMOTE / shuffle draws are built on the device (no H2D).  Back: class1Prob/class2Prob once
     # (2 x n f64; rank 0 only in multi-rank runs), AUROC/AUPRC per fold and global, the fold sizes, a 32-byte status word per tree level.
-    h2d = x_host.nbytes + 4 * n + 4 * n
-    d2h = (16 * n if rig.rank == 0 else 0) + (w["nFolds"] + 1) * 16 + 8 * w["nFolds"] + 32 * int(sum(o["stats"]["levels"] for o in outs_e2e) / max(steps, 1))
+    # Whole job (all ranks): with the library communicator the ranks share the upload of x -- a 1/world slice each over PCIe, one
+    # NCCL all-gather over NVLink (psm_dataset_upload_sharded) -- otherwise every rank uploads its own copy.
+    x_total = x_host.nbytes if (rig.world == 1 or rig.lib_reduce) else x_host.nbytes * rig.world
+    h2d = x_total + rig.world * (4 * n + 4 * n)
+    d2h = 16 * n + rig.world * ((w["nFolds"] + 1) * 16 + 8 * w["nFolds"] + 32 * int(sum(o["stats"]["levels"] for o in outs_e2e) / max(steps, 1)))
     km = {k_: sum(o["kernel_ms"][k_] for o in outs_roof) for k_ in outs_roof[0]["kernel_ms"]}
     kl = {k_: sum(o["kernel_launches"][k_] for o in outs) for k_ in outs[0]["kernel_launches"]}
     kl_roof = sum(o["kernel_launches"]["split_search"] for o in outs_roof)

@@ -193,6 +193,10 @@ int psm_comm_unique_id(void* id128);
 int psm_comm_init(psm_ctx* ctx, const void* id128, uint32_t rank, uint32_t world);
 int psm_comm_info(psm_ctx* ctx, uint32_t* rank, uint32_t* world, int* nccl_version);
 int psm_comm_allreduce_sum_f64(psm_ctx* ctx, double* dev, uint64_t count);
+/* psm_dataset_upload for a replicated dataset on `world` ranks: every rank copies only its 1/world slice of the rows over
+ * PCIe and one in-place ncclAllGather over NVLink completes all the copies.  Collective (same n, m on every rank); a rank reads
+ * only rows [rank*ceil(n/world), ...) of x_host. */
+int psm_dataset_upload_sharded(psm_ctx* ctx, const double* x_host, uint32_t n, uint32_t m);
 int psm_comm_destroy(psm_ctx* ctx);
 
 /* ---- (9) curves: Curves ctor + evalAUROC_ok + evalAUPRC (src/curves.cpp:7-36,77-122). out = {auroc, auprc}.

@@ -381,7 +381,12 @@ void Device::commUniqueId(void* id128) { if (psm_comm_unique_id(id128)) throw Er
 void Device::commInit(const void* id128, uint32_t rank, uint32_t world) { check(psm_comm_init(ctx, id128, rank, world)); }
 bool Device::hasComm() const { uint32_t w = 0; return psm_comm_info(ctx, nullptr, &w, nullptr) == PSM_OK && w > 0; }
 void Device::allReduce(double* dev_ptr, uint64_t count) { check(psm_comm_allreduce_sum_f64(ctx, dev_ptr, count)); }
-void Device::upload(const double* x, uint32_t n_, uint32_t m_) { check(psm_dataset_upload(ctx, x, n_, m_)); n = n_; m = m_; foldTag = nullptr; }
+void Device::upload(const double* x, uint32_t n_, uint32_t m_) {
+	// with a communicator the ranks share the upload: a slice each over PCIe, the rest over NVLink (psm_dataset_upload_sharded)
+	if (shardedUpload && hasComm()) check(psm_dataset_upload_sharded(ctx, x, n_, m_));
+	else check(psm_dataset_upload(ctx, x, n_, m_));
+	n = n_; m = m_; foldTag = nullptr;
+}
 void Device::attachDevice(const double* x, uint32_t n_, uint32_t m_) { check(psm_dataset_attach_device(ctx, x, n_, m_)); n = n_; m = m_; foldTag = nullptr; }
 void Device::setLaneCount(uint32_t lanes) {
 	while (laneCount() < lanes) {

@@ -172,6 +172,7 @@ public:
 	~Device();
 	Device(const Device&) = delete;
 	void upload(const double* x, uint32_t n, uint32_t m);
+	bool shardedUpload = true;      // ranks of one communicator upload a slice of x each and all-gather it (Device::commInit first)
 	void attachDevice(const double* x_dev, uint32_t n, uint32_t m);
 	// begins the fold on the device if it is not the current one (upload index arrays, zero fold scores, drop kNN)
 	void ensureFold(const Partition* part);
