@@ -794,6 +794,24 @@ void hyperSMURF::smurfIt() {                                                // s
 	}
 
 	if (wmode == MODE_TRAIN) return;
+	// the final scores come to the host (rank 0 only with scoresOnRootOnly) on a thread and a stream of their own, next to the
+	// curves, which read the device arrays (plain CV; the inner CVs and the grid's outer folds compute their curves from the
+	// fetched host arrays, so there the fetch comes first)
+	const bool skipFetch = scoresOnRootOnly && world > 1 && rank != 0 && woptimiz == OPT_NO && !inInternalCV;
+	auto fetch = [&]() {
+		PhaseScope ps(PH_SCATTER);
+		if (skipFetch) return;
+		if (scoresAreOutputs && woptimiz == OPT_NO && !inInternalCV) dev->check(psm_scores_read(dev->ctx, class1Prob, class2Prob));
+		else dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob));
+	};
+	std::thread fetcher;
+	std::exception_ptr fetchErr;
+	const bool overlapFetch = !inInternalCV && woptimiz == OPT_NO && !skipFetch;
+	auto startFetch = [&]() {
+		if (overlapFetch && !fetcher.joinable())
+			fetcher = std::thread([&]() { try { dev->check(psm_ctx_bind_thread(dev->ctx)); fetch(); } catch (...) { fetchErr = std::current_exception(); } });
+	};
+	bool globalCurvesDone = false;
 	if (unitMode) {
 		{
 			PhaseScope ps(PH_REDUCE);                                          // the one cross-rank sum of a unit-sharded CV
@@ -804,46 +822,50 @@ void hyperSMURF::smurfIt() {                                                // s
 			reduce(ptr, 2ull * cntN);
 			trace_mark("scores all-reduced");
 		}
-		if (evalFoldCurves) {                                               // :365-396 per-fold AUROC / AUPRC, fold f on rank f % world
+		startFetch();                                                       // the summed arrays are final from here on
+		{
+			// Curves from the summed arrays, spread over the ranks: the per-fold AUROC / AUPRC (:365-396) of fold f on rank
+			// f % world, the global pair (:484-488) on the next rank (one that has no fold when world > nFolds, and not the rank
+			// that is fetching the scores); one all-reduce of the [nFolds + 1][2] table -- every entry written by one rank,
+			// zeros elsewhere -- hands all of them to everybody.
 			PhaseScope ps(PH_CURVES);
-			std::vector<double> fm(2 * (size_t)nFolds, 0.0);
-			for (uint32_t f = startingFold; f < endingFold; f++) {
-				if ((f - startingFold) % world != rank) continue;
-				double r2[2];
-				if (foldsOnDevice()) dev->check(psm_scores_fold_curves_device(dev->ctx, f, curvesTieMode, r2));
-				else {
-					ttd->ensureTest(f);
-					dev->check(psm_scores_fold_curves(dev->ctx, ttd->testPosIdx[f].data(), ttd->testPosNum[f], ttd->testNegIdx[f].data(), ttd->testNegNum[f], curvesTieMode, r2));
+			std::vector<double> fm(2 * (size_t)nFolds + 2, 0.0);
+			if (evalFoldCurves)
+				for (uint32_t f = startingFold; f < endingFold; f++) {
+					if ((f - startingFold) % world != rank) continue;
+					double r2[2];
+					if (foldsOnDevice()) dev->check(psm_scores_fold_curves_device(dev->ctx, f, curvesTieMode, r2));
+					else {
+						ttd->ensureTest(f);
+						dev->check(psm_scores_fold_curves(dev->ctx, ttd->testPosIdx[f].data(), ttd->testPosNum[f], ttd->testNegIdx[f].data(), ttd->testNegNum[f], curvesTieMode, r2));
+					}
+					noteCurves(dev);
+					fm[2 * f] = r2[0]; fm[2 * f + 1] = r2[1];
 				}
+			const uint32_t globalRank = evalFoldCurves ? foldsRun % world : world - 1;
+			if (rank == globalRank) {
+				double r2[2];
+				dev->check(psm_scores_curves(dev->ctx, curvesTieMode, r2));       // Curves(y, class1Prob), scores on the device
 				noteCurves(dev);
-				fm[2 * f] = r2[0]; fm[2 * f + 1] = r2[1];
+				fm[2 * (size_t)nFolds] = r2[0]; fm[2 * (size_t)nFolds + 1] = r2[1];
 			}
 			double* sp = nullptr;
-			dev->check(psm_scratch_f64(dev->ctx, 2 * nFolds, &sp));
-			dev->check(psm_scratch_write(dev->ctx, fm.data(), 2 * nFolds));
-			reduce(sp, 2ull * nFolds);
-			dev->check(psm_scratch_read(dev->ctx, fm.data(), 2 * nFolds));
-			for (uint32_t f = startingFold; f < endingFold; f++) {
-				foldAuroc[f] = fm[2 * f]; foldAuprc[f] = fm[2 * f + 1];
-				if (verboseLevel > VERBSILENT && rank == 0)
-					std::cout << "External CV on fold " << f << " -> AUROC: " << foldAuroc[f] << " - AUPRC: " << foldAuprc[f] << std::endl;
-			}
+			dev->check(psm_scratch_f64(dev->ctx, 2 * nFolds + 2, &sp));
+			dev->check(psm_scratch_write(dev->ctx, fm.data(), 2 * nFolds + 2));
+			reduce(sp, 2ull * nFolds + 2);
+			dev->check(psm_scratch_read(dev->ctx, fm.data(), 2 * nFolds + 2));
+			if (evalFoldCurves)
+				for (uint32_t f = startingFold; f < endingFold; f++) {
+					foldAuroc[f] = fm[2 * f]; foldAuprc[f] = fm[2 * f + 1];
+					if (verboseLevel > VERBSILENT && rank == 0)
+						std::cout << "External CV on fold " << f << " -> AUROC: " << foldAuroc[f] << " - AUPRC: " << foldAuprc[f] << std::endl;
+				}
+			auroc = fm[2 * (size_t)nFolds]; auprc = fm[2 * (size_t)nFolds + 1];
+			globalCurvesDone = true;
 		}
 	}
 	trace_mark("fold curves done");
-	// the final scores come to the host while the global curves are computed from the device arrays (plain CV; the inner CVs
-	// and the grid's outer folds compute their curves from the fetched host arrays, so there the fetch comes first)
-	const bool skipFetch = scoresOnRootOnly && world > 1 && rank != 0 && woptimiz == OPT_NO && !inInternalCV;
-	auto fetch = [&]() {
-		PhaseScope ps(PH_SCATTER);
-		if (skipFetch) return;
-		if (scoresAreOutputs && woptimiz == OPT_NO && !inInternalCV) dev->check(psm_scores_read(dev->ctx, class1Prob, class2Prob));
-		else dev->check(psm_scores_get(dev->ctx, class1Prob, class2Prob));
-	};
-	std::thread fetcher;
-	std::exception_ptr fetchErr;
-	if (!inInternalCV && woptimiz == OPT_NO && !skipFetch)
-		fetcher = std::thread([&]() { try { dev->check(psm_ctx_bind_thread(dev->ctx)); fetch(); } catch (...) { fetchErr = std::current_exception(); } });
+	if (overlapFetch) startFetch();
 	else { fetch(); trace_mark("scores on the host"); }
 	struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{fetcher};
 	if (inInternalCV) {                                                     // :456-482
@@ -858,12 +880,14 @@ void hyperSMURF::smurfIt() {                                                // s
 		gridParams[idxInGridParams].auprc = c.evalAUPRC();
 	} else {                                                                // :484-488
 		PhaseScope ps(PH_CURVES);
-		double r2[2];
-		if (woptimiz == OPT_NO) dev->check(psm_scores_curves(dev->ctx, curvesTieMode, r2));        // Curves(y, class1Prob), scores still on the device
-		else dev->check(psm_curves(dev->ctx, y.data(), class1Prob, nn, curvesTieMode, r2));
-		noteCurves(dev);
-		auroc = r2[0];
-		auprc = r2[1];
+		if (!globalCurvesDone) {
+			double r2[2];
+			if (woptimiz == OPT_NO) dev->check(psm_scores_curves(dev->ctx, curvesTieMode, r2));        // Curves(y, class1Prob), scores still on the device
+			else dev->check(psm_curves(dev->ctx, y.data(), class1Prob, nn, curvesTieMode, r2));
+			noteCurves(dev);
+			auroc = r2[0];
+			auprc = r2[1];
+		}
 		if (verboseLevel > VERBSILENT && rank == 0) std::cout << "AUROC: " << auroc << " - AUPRC: " << auprc << std::endl;
 	}
 	if (fetcher.joinable()) { fetcher.join(); trace_mark("scores on the host"); }

@@ -260,7 +260,7 @@ def test_unit_sharded_ranks_reproduce_the_single_rank_cv(oracle):
                   t = torch.as_tensor(_Arr(ptr, count), device="cuda")
                   got.append(t.cpu().numpy().copy())
                   extra = add_scores if count == 2 * n else add_metrics
-                  assert count in (2 * n, 2 * nF)
+                  assert count in (2 * n, 2 * nF + 2)                         # the scores; the per-fold metrics + the global pair
                   if extra is not None:
                       t += torch.from_numpy(extra).cuda()
                   torch.cuda.synchronize()
