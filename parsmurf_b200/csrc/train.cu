@@ -454,6 +454,9 @@ template <> struct PkOf<uint32_t> {
 	typedef uint32_t type; static constexpr int shift = 16;
 	static __device__ __forceinline__ float hi_f(uint32_t pk) { return __uint_as_float(__byte_perm(pk, 0x4B000000u, 0x7432)) - 8388608.0f; }
 	static __device__ __forceinline__ float lo_f(uint32_t pk) { return __uint_as_float(__byte_perm(pk, 0x4B000000u, 0x7410)) - 8388608.0f; }
+	// the same before the subtraction of 2^23 (the packed estimate subtracts two at a time)
+	static __device__ __forceinline__ float hi_raw(uint32_t pk) { return __uint_as_float(__byte_perm(pk, 0x4B000000u, 0x7432)); }
+	static __device__ __forceinline__ float lo_raw(uint32_t pk) { return __uint_as_float(__byte_perm(pk, 0x4B000000u, 0x7410)); }
 	// "entries j and j+1 hold different values": ranks differ (bits 14..27)
 	static __device__ __forceinline__ bool rank_differs(uint32_t a, uint32_t b) { return ((a ^ b) & 0x0FFFC000u) != 0u; }
 };
@@ -461,8 +464,19 @@ template <> struct PkOf<unsigned long long> {
 	typedef unsigned long long type; static constexpr int shift = 32;
 	static __device__ __forceinline__ float hi_f(unsigned long long pk) { return __uint_as_float((uint32_t)(pk >> 32) | 0x4B000000u) - 8388608.0f; }
 	static __device__ __forceinline__ float lo_f(unsigned long long pk) { return __uint_as_float((uint32_t)pk | 0x4B000000u) - 8388608.0f; }
+	static __device__ __forceinline__ float hi_raw(unsigned long long pk) { return __uint_as_float((uint32_t)(pk >> 32) | 0x4B000000u); }
+	static __device__ __forceinline__ float lo_raw(unsigned long long pk) { return __uint_as_float((uint32_t)pk | 0x4B000000u); }
 	static __device__ __forceinline__ bool rank_differs(unsigned long long a, unsigned long long b) { return ((a ^ b) & 0x0000FFFFFF000000ull) != 0ull; }
 };
+
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): two positions of the split-score estimate per instruction.  Every lane of a
+// pair is rounded exactly like the scalar operation, so the packed estimate is bit for bit the scalar one.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float a, float b) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void up2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 // MUFU.RCP, 1 ulp (__frcp_rn is the correctly rounded one: a Newton step and a guarded slow path around the same MUFU)
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -592,18 +606,29 @@ __global__ void __launch_bounds__(128, MULTI ? SS_MINB_MULTI : SS_MINB) split_se
 		float gmin = __int_as_float(0x7F800000);
 		auto estimate = [&](auto edgeTag) {
 			constexpr bool EDGE = decltype(edgeTag)::value;
+			static_assert(IPL % 2 == 0, "the estimate works on pairs of positions");
+			const f32x2_t kM23 = pk2(-8388608.0f, -8388608.0f), kM1 = pk2(-1.0f, -1.0f), fn2 = pk2(fn, fn), fP2 = pk2(fP, fP), fN2 = pk2(fN, fN);
 #pragma unroll
-			for (int j = 0; j < IPL; j++) {
-				const pk_t a = excl + pk[j];
-				const float fl = PK::hi_f(a), fq = PK::lo_f(a);
-				const float nl = fl + fq, nr = fn - nl;
-				const float num = fmaf(fl * fq, nr, ((fP - fl) * (fN - fq)) * nl);
-				float gj = num * rcp_approx(nl * nr);
-				bool ok = PK::rank_differs(e[j], j + 1 < IPL ? e[(j + 1) % IPL] : enext);
-				if (EDGE) { const uint32_t v = v0 + j; ok = ok && v >= lo && v + 1 < hi; }
-				gj = ok ? gj : __int_as_float(0x7F800000);
-				g[j] = gj;
-				gmin = fminf(gmin, gj);
+			for (int j = 0; j < IPL; j += 2) {
+				// g = (L0 L1 n_R + R0 R1 n_L) * rcp(n_L n_R) for positions j and j + 1, the operations of the scalar form
+				//   fmaf(fl * fq, nr, ((fP - fl) * (fN - fq)) * nl) * rcp(nl * nr)   in the same order, two at a time
+				const pk_t a0 = excl + pk[j], a1 = excl + pk[j + 1];
+				const f32x2_t fl = add2(pk2(PK::hi_raw(a0), PK::hi_raw(a1)), kM23), fq = add2(pk2(PK::lo_raw(a0), PK::lo_raw(a1)), kM23);
+				const f32x2_t nl = add2(fl, fq), nr = fma2(nl, kM1, fn2);
+				const f32x2_t num = fma2(mul2(fl, fq), nr, mul2(mul2(fma2(fl, kM1, fP2), fma2(fq, kM1, fN2)), nl));
+				float d0, d1;
+				up2(mul2(nl, nr), d0, d1);
+				float gp[2];
+				up2(mul2(num, pk2(rcp_approx(d0), rcp_approx(d1))), gp[0], gp[1]);
+#pragma unroll
+				for (int q = 0; q < 2; q++) {
+					const int jj = j + q;
+					bool ok = PK::rank_differs(e[jj], jj + 1 < IPL ? e[(jj + 1) % IPL] : enext);
+					if (EDGE) { const uint32_t v = v0 + jj; ok = ok && v >= lo && v + 1 < hi; }
+					const float gj = ok ? gp[q] : __int_as_float(0x7F800000);
+					g[jj] = gj;
+					gmin = fminf(gmin, gj);
+				}
 			}
 		};
 		if (edge) estimate(std::true_type()); else estimate(std::false_type());
