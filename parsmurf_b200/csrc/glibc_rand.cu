@@ -2,8 +2,8 @@
 // glibc stdlib/random_r.c TYPE_3: r[i] = r[i-3] + r[i-31] (mod 2^32), output r[i] >> 1).
 //
 // The recurrence is linear over Z/2^32, so the stream can be entered anywhere: x^n mod (x^31 - x^28 - 1) gives the
-// coefficients c_j with r[t+n] = sum_j c_j r[t+j].  Each thread jumps to the start of its own 1024-draw chunk by
-// multiplying precomputed powers x^(1024*2^j), rebuilds the 31-word window there and then steps the plain recurrence.
+// coefficients c_j with r[t+n] = sum_j c_j r[t+j].  Each thread jumps to the start of its own GR_CHUNK-draw chunk by
+// multiplying precomputed powers x^(GR_CHUNK*2^j), rebuilds the 31-word window there and then steps the plain recurrence.
 // This removes the host-side generation of P*fp*(m+1) draws per partition (32M draws per CV at BASELINE configs[1]).
 #include "kernels.cuh"
 
@@ -13,7 +13,8 @@
 namespace psm {
 
 constexpr int GR_DEG = 31;
-constexpr uint32_t GR_CHUNK = 1024;
+constexpr uint32_t GR_ROUNDS = 8;
+constexpr uint32_t GR_CHUNK = GR_ROUNDS * 31;   // draws per thread: whole turns of the 31-word window, so the window stays in registers
 
 // ---- polynomial arithmetic mod x^31 - x^28 - 1 over Z/2^32 (host and device) ----
 __host__ __device__ inline void gr_polymul(const uint32_t* a, const uint32_t* b, uint32_t* out) {
@@ -80,20 +81,29 @@ __global__ void __launch_bounds__(128) glibc_rand_fill_kernel(const uint32_t* __
 		}
 	}
 	uint32_t w[GR_DEG];                                    // window at the chunk start: r[first-31 .. first-1] relative to the stream
-	for (int d = 0; d < GR_DEG; d++) {
-		uint32_t s = 0;
-		for (int j = 0; j < GR_DEG; j++) s += q[j] * w61[d + j];
-		w[d] = s;
+#pragma unroll
+	for (int d = 0; d < GR_DEG; d++) w[d] = 0;
+#pragma unroll 1
+	for (int j = 0; j < GR_DEG; j++) {                     // (j outside, d unrolled: w[] is only ever indexed by constants)
+		const uint32_t qj = q[j];
+#pragma unroll
+		for (int d = 0; d < GR_DEG; d++) w[d] += qj * w61[d + j];
 	}
+	// 248 draws = 8 turns of the window with compile-time indices (w[k] += w[k + 28 mod 31]): the window lives in registers.
+	// (r02: 1024-draw chunks walked a window in local memory -- a dependent load / store chain of ~100 cycles per draw on the
+	// 782 threads of a fold's shuffle draws: 190 us per launch, 1.9 ms per BASELINE configs[1] CV.)
 	const unsigned long long n = (count - first < GR_CHUNK) ? (count - first) : GR_CHUNK;
-	int f = 0, r = GR_DEG - 3;                             // oldest at f, r = f - 3 (mod 31)
 	int32_t* o = out + first;
-	for (unsigned long long i = 0; i < n; i++) {
-		const uint32_t v = w[f] + w[r];
-		w[f] = v;
-		o[i] = (int32_t)(v >> 1);
-		f = (f + 1 == GR_DEG) ? 0 : f + 1;
-		r = (r + 1 == GR_DEG) ? 0 : r + 1;
+#pragma unroll 1
+	for (uint32_t turn = 0; turn < GR_ROUNDS; turn++) {
+		const uint32_t base = turn * GR_DEG;
+		if (base >= n) break;
+#pragma unroll
+		for (int k = 0; k < GR_DEG; k++) {
+			const uint32_t v = w[k] + w[(k + GR_DEG - 3) % GR_DEG];
+			w[k] = v;
+			if (base + k < n) o[base + k] = (int32_t)(v >> 1);
+		}
 	}
 }
 
