@@ -452,7 +452,7 @@ int psm_fold_begin_device(psm_ctx* ctx, uint32_t fold, const uint32_t* window31)
 		ENSURE(ctx->sValsA, (size_t)Nneg * 4); ENSURE(ctx->sValsB, (size_t)Nneg * 4);
 		ENSURE(ctx->sHist, (rBlocks + 1) * 256 * 4); ENSURE(ctx->sJ, (size_t)Nneg * 4); ENSURE(ctx->sDraws, (size_t)Nneg * 4);
 		ENSURE(ctx->dRandScratch, (61 + 64 * 31) * 4);
-		ProfScope ps(ctx, K_GATHER, 3 + 3 * 8);
+		ProfScope ps(ctx, K_GATHER, 3 + 3 * shuffle_sort_passes(Nneg));
 		if (launch_glibc_rand_fill(window31, (unsigned long long)Nneg - 1, ctx->dRandScratch.as<uint32_t>(), ctx->sDraws.as<int32_t>(), s))
 			return fail(ctx, PSM_E_CUDA, "fold_begin_device: rand replay launch failed");
 		if (launch_device_shuffle(ctx->sDraws.as<int32_t>(), ctx->sIn.as<uint32_t>(), Nneg, ctx->sKeysA.as<unsigned long long>(), ctx->sKeysB.as<unsigned long long>(),

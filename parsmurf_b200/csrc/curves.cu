@@ -413,19 +413,19 @@ void launch_fold_keys(const uint32_t* labels, const uint32_t* foldIds, uint32_t 
 	fold_keys_kernel<<<blocks, 256, 0, s>>>(labels, foldIds, n, nFolds, keys, vals, counts, bad);
 }
 
-// generic entry: ascending LSD sort of prefilled (keysA, valsA) on the low 8*passes key bits; passes must be even so that the
-// result is back in keysA / valsA.  hist: ((N + 4095) / 4096) * 256 + 256 uint32.
+// generic entry: ascending (stable) LSD sort of prefilled (keysA, valsA) on the key bits [bit0, bit0 + 8*passes); passes must be even
+// so that the result is back in keysA / valsA.  hist: ((N + 4095) / 4096) * 256 + 256 uint32.
 int launch_radix_sort_u64(unsigned long long* keysA, unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, uint64_t N, int passes,
-                          uint32_t* hist, cudaStream_t s) {
+                          uint32_t* hist, cudaStream_t s, int bit0) {
 	if (N == 0) return 0;
-	if (N >= (1ull << 32) || passes <= 0 || passes > 8 || (passes & 1)) return -1;
+	if (N >= (1ull << 32) || passes <= 0 || passes > 8 || (passes & 1) || bit0 < 0 || bit0 + 8 * passes > 64) return -1;
 	const uint32_t nBlocks = (uint32_t)((N + RCHUNK - 1) / RCHUNK);
 	unsigned long long *kin = keysA, *kout = keysB;
 	uint32_t *vin = valsA, *vout = valsB;
 	for (int pass = 0; pass < passes; pass++) {
-		radix_hist_kernel<<<nBlocks, RB, 0, s>>>(kin, N, pass * 8, nBlocks, hist);
+		radix_hist_kernel<<<nBlocks, RB, 0, s>>>(kin, N, bit0 + pass * 8, nBlocks, hist);
 		radix_scan_digits_kernel<<<32, 256, 0, s>>>(hist, nBlocks);
-		radix_scatter_kernel<<<nBlocks, RB, 0, s>>>(kin, vin, N, pass * 8, nBlocks, hist, kout, vout);
+		radix_scatter_kernel<<<nBlocks, RB, 0, s>>>(kin, vin, N, bit0 + pass * 8, nBlocks, hist, kout, vout);
 		unsigned long long* tk = kin; kin = kout; kout = tk;
 		uint32_t* tv = vin; vin = vout; vout = tv;
 	}

@@ -107,8 +107,9 @@ int launch_sort_scores_desc_labelties(const double* scores, const uint32_t* labe
 void launch_fold_keys(const uint32_t* labels, const uint32_t* foldIds, uint32_t n, uint32_t nFolds, unsigned long long* keys, uint32_t* vals, uint32_t* counts,
                       uint32_t* bad, cudaStream_t s);
 int launch_radix_sort_u64(unsigned long long* keysA, unsigned long long* keysB, uint32_t* valsA, uint32_t* valsB, uint64_t N, int passes,
-                          uint32_t* hist, cudaStream_t s);
+                          uint32_t* hist, cudaStream_t s, int bit0 = 0);
 // shuffle.cu
+int shuffle_sort_passes(uint32_t n);   // radix passes of launch_device_shuffle (kernel launches: 2 + 3 * passes)
 int launch_device_shuffle(const int32_t* draws, const uint32_t* in, uint32_t n, unsigned long long* keysA, unsigned long long* keysB, uint32_t* valsA,
                           uint32_t* valsB, uint32_t* hist, uint32_t* jArr, uint32_t* out, cudaStream_t s);
 
