@@ -103,7 +103,7 @@ struct psm_ctx {
 	uint64_t curvesMixedPairs = 0;
 	int curvesUsedHostSort = 0;
 	double curvesSpread[2] = {0, 0};
-	DevBuf cIdx, cFoldScores, cScratch, cLabels, cPerm, cSorted, cTp, cPartials, cOut, cScores, cKeysA, cKeysB, cValsA, cValsB, cHist;
+	DevBuf cIdx, cFoldScores, cScratch, cLabels, cPerm, cSorted, cSorted2, cTp, cPartials, cOut, cScores, cKeysA, cKeysB, cValsA, cValsB, cHist;
 
 	// cross-rank communicator (psm_comm_init)
 	void* comm = nullptr;            // ncclComm_t
@@ -147,6 +147,7 @@ struct ProfScope {
 		c->profLaunches[cls] += launches;
 		if (c->profOn && ((c->profMask >> cls) & 1u)) { a = get_event(c); cudaEventRecord(a, c->stream); }
 	}
+	void add_launches(int n) { c->profLaunches[cls] += n; }
 	~ProfScope() {
 		if (a) { cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream); c->profPending.push_back({a, b, cls}); }
 	}
@@ -211,7 +212,7 @@ int psm_ctx_destroy(psm_ctx* ctx) {
 	                  &ctx->dParts, &ctx->dD, &ctx->dS, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA, &ctx->dValsB, &ctx->dDraws, &ctx->dErr, &ctx->dRandScratch,
 	                  &ctx->dLists0, &ctx->dLists1, &ctx->dInbag, &ctx->dInbagT, &ctx->dMt, &ctx->dTs, &ctx->dNodes, &ctx->dNodes8, &ctx->dSplitFeat, &ctx->dFlagBits, &ctx->dItems0, &ctx->dItems1, &ctx->dCls,
 	                  &ctx->dCand, &ctx->dRes, &ctx->dDec, &ctx->dPtask, &ctx->dCounters, &ctx->dStats, &ctx->dSeeds, &ctx->dInjBoot, &ctx->dInjBootOff,
-	                  &ctx->dInjCand, &ctx->dSortFlags, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cIdx, &ctx->cFoldScores, &ctx->cScratch, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
+	                  &ctx->dInjCand, &ctx->dSortFlags, &ctx->dPredScratch, &ctx->dLabels, &ctx->dFoldLabels, &ctx->dGlob, &ctx->cIdx, &ctx->cFoldScores, &ctx->cScratch, &ctx->cLabels, &ctx->cPerm, &ctx->cSorted, &ctx->cSorted2, &ctx->cTp, &ctx->cPartials, &ctx->cOut,
 	                  &ctx->cScores, &ctx->cKeysA, &ctx->cKeysB, &ctx->cValsA, &ctx->cValsB, &ctx->cHist};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& p : ctx->profPending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -807,14 +808,13 @@ int psm_batch_train(psm_ctx* ctx, uint32_t T, uint32_t mtry, const uint32_t* for
 		for (int k = 0; k < NCLS; k++) { clsCount[k] = ctx->hCounters[CNT_CLS0 + k]; clsSum += clsCount[k]; }
 		if (clsSum != nItems) return fail(ctx, PSM_E_OVERFLOW, "batch_train: size-class lists do not add up to the level's work items");
 		static_assert(CNT_NEXT_ITEMS == 0 && CNT_CLS0 == 1, "the per-level counters are cleared with one memset");
-		CU(cudaMemsetAsync(A.counters, 0, (1 + NCLS) * 4, s));
-		int nzCls = 0;                                   // one split-search launch per non-empty size class
-		for (int k = 0; k < NCLS; k++) nzCls += clsCount[k] != 0;
+		// (the merged split-search launch clears them itself: one stream operation less per level)
+		if (getenv("PSM_SS_SEPARATE")) CU(cudaMemsetAsync(A.counters, 0, (1 + NCLS) * 4, s));
 		const bool trace = getenv("PSM_TRACE_LEVELS") != nullptr;
 		cudaEvent_t tev[5];
 		if (trace) for (auto& e : tev) cudaEventCreate(&e);
 		if (trace) cudaEventRecord(tev[0], s);
-		{ ProfScope ps(ctx, K_SEARCH, nzCls); launch_split_search(A, clsCount, buf, s); }
+		{ ProfScope ps(ctx, K_SEARCH, 0); ps.add_launches(launch_split_search(A, clsCount, buf, s)); }
 		if (trace) cudaEventRecord(tev[1], s);
 		{ ProfScope ps(ctx, K_SELECT, 1); launch_split_select(A, nItems, buf, s); }
 		if (trace) cudaEventRecord(tev[2], s);
@@ -1130,7 +1130,20 @@ static int curves_core(psm_ctx* ctx, const uint32_t* dLabels, const double* dSco
 		// (b) negatives first: the lower end.  Both curves are monotone in the position of every positive inside its run of
 		// ties, so whatever order the reference's std::sort leaves the ties in (curves.cpp:31-33), its AUROC / AUPRC lie
 		// between the two; when they are closer than kTieSpreadTol their midpoint is the answer to half of that.
-		if ((rc = curves_device_pass(ctx, dLabels, dScores, N, totP, totN, 2, false, lo, nullptr))) return rc;
+		// (the negatives-first label sequence is the positives-first one with every run of ties reversed: no second sort)
+		if (getenv("PSM_CURVES_TWO_SORTS")) { if ((rc = curves_device_pass(ctx, dLabels, dScores, N, totP, totN, 2, false, lo, nullptr))) return rc; }
+		else {
+			ENSURE(ctx->cSorted2, N + 64);
+			{
+				ProfScope ps(ctx, K_CURVES, 6);
+				launch_tie_reverse_labels(ctx->cKeysA.as<unsigned long long>(), ctx->cSorted.as<unsigned char>(), N, ctx->cSorted2.as<unsigned char>(), s);
+				if (launch_curves(ctx->cSorted2.as<unsigned char>(), N, totP, totN, ctx->cTp.as<uint32_t>(), ctx->cPartials.as<double>(), nBlocks * 2, ctx->cOut.as<double>(), s))
+					return fail(ctx, PSM_E_ARG, "curves: launch failed");
+			}
+			CU(cudaGetLastError());
+			CU(cudaMemcpyAsync(lo, ctx->cOut.p, 16, cudaMemcpyDeviceToHost, s));
+			CU(cudaStreamSynchronize(s));
+		}
 		ctx->curvesSpread[0] = hi[0] - lo[0]; ctx->curvesSpread[1] = hi[1] - lo[1];
 		if (std::fabs(hi[0] - lo[0]) <= kTieSpreadTol && std::fabs(hi[1] - lo[1]) <= kTieSpreadTol) {
 			out[0] = 0.5 * (hi[0] + lo[0]); out[1] = 0.5 * (hi[1] + lo[1]);

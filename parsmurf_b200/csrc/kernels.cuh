@@ -6,11 +6,21 @@ namespace psm {
 
 // counters[CNT_NEXT_ITEMS] = open nodes of the next level; counters[CNT_CLS0 + k] = how many of them fall in size class k
 // (level_finalize appends their item ids to clsItems[next][k]); both are cleared by the host before the next level_finalize
-constexpr int NCLS = 4;
-enum { CNT_NEXT_ITEMS = 0, CNT_CLS0 = 1, CNT_ERROR = 5, CNT_COUNT = 8 };
+constexpr int NCLS = 6;
+enum { CNT_NEXT_ITEMS = 0, CNT_CLS0 = 1, CNT_ERROR = 7, CNT_COUNT = 8 };
 // Size class of a work item by its segment length (+3: worst-case shift of the 16-byte aligned load grid):
-//   0: <= 32 grid entries (8 lanes x 4)   1: <= 64 (16 lanes)   2: <= 128 (one warp, one chunk)   3: longer (chunk loop)
-__host__ __device__ __forceinline__ uint32_t size_class(uint32_t cnt) { return cnt <= 29u ? 0u : cnt <= 61u ? 1u : cnt <= 125u ? 2u : 3u; }
+//   0: <= 32 grid entries (8 lanes x 4)   1: <= 64 (16 lanes)   2: <= 128 (one warp, one chunk)
+//   3, 4, 5: longer (one warp, chunk loop), cut at SS_CLS4_MIN and SS_CLS5_MIN entries only so that the merged split-search launch
+//   can start the longest segments first (train.cu: split_search_merged_kernel)
+#ifndef SS_CLS4_MIN
+#define SS_CLS4_MIN 510u
+#endif
+#ifndef SS_CLS5_MIN
+#define SS_CLS5_MIN 2046u
+#endif
+__host__ __device__ __forceinline__ uint32_t size_class(uint32_t cnt) {
+	return cnt <= 29u ? 0u : cnt <= 61u ? 1u : cnt <= 125u ? 2u : cnt < SS_CLS4_MIN ? 3u : cnt < SS_CLS5_MIN ? 4u : 5u;
+}
 enum { ERR_COUNT_LIMIT = 1, ERR_POOL_OVERFLOW = 2, ERR_INJ_CAND = 4 };
 enum { STAT_SPLIT_BYTES = 0, STAT_NODES = 1, STAT_COUNT = 4 };
 
@@ -74,7 +84,7 @@ void launch_inbag_from_ids(const TrainArgs& A, const unsigned long long* ids, co
 // inbagT: scratch of nParts * stride * 16 bytes for the all-trees-at-once variant (compact entries, T <= 16), or NULL
 void launch_build_lists(const TrainArgs& A, unsigned char* inbagT, cudaStream_t s);
 int launch_init_trees(const TrainArgs& A, cudaStream_t s);
-void launch_split_search(const TrainArgs& A, const uint32_t* clsCount, int buf, cudaStream_t s);
+int launch_split_search(const TrainArgs& A, const uint32_t* clsCount, int buf, cudaStream_t s);
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
 int launch_tree_level(const TrainArgs& A, int buf, cudaStream_t s);   // go-left bitmaps + level bookkeeping, one CTA per tree
 void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s);
@@ -91,6 +101,7 @@ void launch_accumulate(const double* scratch, uint32_t Nte, uint32_t nPartsBatch
 // curves.cu
 int launch_curves(const unsigned char* labelsSorted, uint64_t N, uint32_t totP, uint32_t totN, uint32_t* tpScratch,
                   double* partials, size_t partialsCap, double* out2, cudaStream_t s);
+void launch_tie_reverse_labels(const unsigned long long* keysSorted, const unsigned char* labelsSorted, uint64_t N, unsigned char* out, cudaStream_t s);
 void launch_tie_mixed_count(const unsigned long long* keysSorted, const unsigned char* labelsSorted, uint64_t N, unsigned long long* counter, cudaStream_t s);
 void launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint64_t N, uint32_t* out, cudaStream_t s);
 void launch_check_ids(const uint32_t* ids, uint64_t N, uint32_t n, uint32_t* bad /*device word, OR-ed*/, cudaStream_t s);

@@ -395,6 +395,9 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 #ifndef PSM_SS_IPL_MULTI
 #define PSM_SS_IPL_MULTI 8
 #endif
+#ifndef SS_BLOCK_DEFAULT
+#define SS_BLOCK_DEFAULT 64     // threads per CTA of the merged launch (PSM_SS_BLOCK=32|64|128 overrides)
+#endif
 template <typename E, bool MULTI> struct SsIpl { static constexpr int v = (MULTI && sizeof(E) == 4) ? PSM_SS_IPL_MULTI : 4; };
 
 template <int IPL> __device__ __forceinline__ void ss_vec(const unsigned long long* p, unsigned long long (&e)[IPL]) {
@@ -536,20 +539,20 @@ template <int G> __device__ __forceinline__ uint32_t grp_min(uint32_t v) {
 //     half-empty second wave of 5 000 warps on 4 144 slots: 11.9 ms re-reading the quarter through L1 / L2, 11.9 ms with the
 //     quarter staged in shared memory, against 10.9 ms -- ncu shows the one-warp loop ~75% issue-bound while its warps are
 //     resident (1.3 warp instructions per entry), so the extra counting pass and the barrier cost more than the tail wave.
+// tIdx = the thread's index among the threads of its size class (G threads per work item)
 template <typename E, int G, bool MULTI>
-__global__ void __launch_bounds__(128, MULTI ? SS_MINB_MULTI : SS_MINB) split_search_kernel(TrainArgs A, const uint32_t* __restrict__ list, uint32_t nList, int buf) {
+__device__ __forceinline__ void split_search_body(const TrainArgs& A, const uint32_t* __restrict__ list, uint32_t nList, int buf, size_t tIdx, uint32_t c) {
 	constexpr int IPL = SsIpl<E, MULTI>::v;
 	typedef PkOf<E> PK;
 	typedef typename PK::type pk_t;
 	constexpr int PKS = PK::shift;
 	constexpr pk_t LOMASK = ((pk_t)1 << PKS) - 1;
 	// grid.y = candidate index, so no integer division is needed to find the work item
-	uint32_t li = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
+	uint32_t li = (uint32_t)(tIdx / G);
 	const bool idle = li >= nList;
 	if (G == 32) { if (idle) return; }
 	else if (idle) li = nList - 1;                            // keep the warp whole (see grp_max)
 	const uint32_t item = __ldg(list + li);
-	const uint32_t c = blockIdx.y;
 	const Item it = A.items[buf][item];
 	constexpr uint32_t APE = 16 / sizeof(E);                  // entries per aligned 16-byte vector
 	const uint32_t off = it.start % APE;                      // A.stride % 4 == 0, so list + start - off is 16-byte aligned
@@ -692,6 +695,56 @@ __global__ void __launch_bounds__(128, MULTI ? SS_MINB_MULTI : SS_MINB) split_se
 	if (gl == 0 && !idle) {
 		SearchRes r; r.score = best; r.pos = bpos; r.lpos = blp; r.lneg = bln; r.pad = 0;
 		A.res[(size_t)item * A.mtry + c] = r;
+	}
+}
+
+// one size class per launch (PSM_SS_SEPARATE=1: the r01 / early r02 form, kept for A/B measurements)
+template <typename E, int G, bool MULTI>
+__global__ void __launch_bounds__(128, MULTI ? SS_MINB_MULTI : SS_MINB) split_search_kernel(TrainArgs A, const uint32_t* __restrict__ list, uint32_t nList, int buf) {
+	split_search_body<E, G, MULTI>(A, list, nList, buf, (size_t)blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y);   // grid.y = candidate
+}
+
+// All the size classes of a level in ONE launch.  The CTAs are laid out largest class first (the three chunk-loop classes in
+// descending size, then the single-chunk warp class, the 16-lane and the 8-lane groups), so the longest segments start first and
+// the short ones fill the slots they leave (longest-processing-time-first over ~10^5 work items whose lengths span 10 .. 6 000
+// entries at the mid levels), and a level pays one launch instead of up to four: with one launch per class every class ran its
+// own ramp and its own half-empty last wave (ncu r02: warps active 30% of the 44% the registers allow in the chunk-loop class,
+// 6-8 us launch floors for each of the small classes on the ~15 deepest levels).  The kernel has no barrier and no shared
+// memory, so the CTA size is free: SsPlan.block threads (a multiple of 32) -- a CTA only retires with its slowest warp, so small
+// CTAs keep the slots of finished warps from idling next to a long segment.
+struct SsPlan {
+	uint32_t ctaEnd[NCLS];    // exclusive CTA bounds of the classes in launch order (class NCLS-1 first)
+	uint32_t count[NCLS];     // items of the class, same order
+};
+// Registers: the chunk loop wants 72 (SS_MINB_MULTI), but with every class in one launch the resident warps are what hides the
+// latency of the short segments: measured on B200 at BASELINE configs[1] (split search ms per CV, 64-thread CTAs):
+// 72 registers 8.97, 64: 8.33, 56: 7.96, 48 (a few dozen bytes of spills outside the chunk loop): 7.87; one launch per class: 11.95.
+#ifndef SS_MINB_MERGED32
+#define SS_MINB_MERGED32 10     // 4-byte entries: 48 registers
+#endif
+#ifndef SS_MINB_MERGED64
+#define SS_MINB_MERGED64 8      // 8-byte entries: 64 registers
+#endif
+template <typename E>
+__global__ void __launch_bounds__(128, sizeof(E) == 4 ? SS_MINB_MERGED32 : SS_MINB_MERGED64) split_search_merged_kernel(TrainArgs A, SsPlan P, int buf) {
+	// grid = (candidate, work-item CTAs [, overflow of the 65535 limit]): the candidate is the fastest dimension, so CTAs are handed
+	// out in work-item order -- longest class first -- with the mtry candidates of an item side by side
+	const uint32_t bx = blockIdx.z * gridDim.y + blockIdx.y, c = blockIdx.x;
+	// the per-level counters (next level's item count and class sizes) were read by the host before this launch and are next
+	// touched by this level's tree_level_kernel: cleared here instead of by a memset of their own
+	static_assert(CNT_NEXT_ITEMS == 0 && CNT_CLS0 == 1, "the per-level counters are contiguous");
+	if (bx == 0 && c == 0 && threadIdx.x < 1 + NCLS) A.counters[threadIdx.x] = 0;
+	static_assert(NCLS == 6, "launch order below: classes 5, 4, 3 (chunk loop), 2 (one warp, one chunk), 1 (16 lanes), 0 (8 lanes)");
+	if (bx < P.ctaEnd[2]) {
+		const int q = bx < P.ctaEnd[0] ? 0 : bx < P.ctaEnd[1] ? 1 : 2;
+		const uint32_t first = q ? P.ctaEnd[q - 1] : 0u;
+		split_search_body<E, 32, true>(A, A.clsItems[buf][NCLS - 1 - q], P.count[q], buf, (size_t)(bx - first) * blockDim.x + threadIdx.x, c);
+	} else if (bx < P.ctaEnd[3]) {
+		split_search_body<E, 32, false>(A, A.clsItems[buf][2], P.count[3], buf, (size_t)(bx - P.ctaEnd[2]) * blockDim.x + threadIdx.x, c);
+	} else if (bx < P.ctaEnd[4]) {
+		split_search_body<E, 16, false>(A, A.clsItems[buf][1], P.count[4], buf, (size_t)(bx - P.ctaEnd[3]) * blockDim.x + threadIdx.x, c);
+	} else if (bx < P.ctaEnd[5]) {
+		split_search_body<E, 8, false>(A, A.clsItems[buf][0], P.count[5], buf, (size_t)(bx - P.ctaEnd[4]) * blockDim.x + threadIdx.x, c);
 	}
 }
 
@@ -1093,11 +1146,37 @@ int launch_init_trees(const TrainArgs& A, cudaStream_t s) {
 	init_trees_kernel<<<A.nTrees, 32, smem, s>>>(A);
 	return 0;
 }
-// one launch per non-empty size class (kernels.cuh: size_class); clsCount[k] = items in clsItems[buf][k]
-void launch_split_search(const TrainArgs& A, const uint32_t* clsCount, int buf, cudaStream_t s) {
-	for (int k = 0; k < NCLS; k++) {
+// clsCount[k] = items in clsItems[buf][k] (kernels.cuh: size_class).  Returns the number of launches.
+static int ss_env_block() {
+	const char* e = getenv("PSM_SS_BLOCK");
+	const int b = e ? atoi(e) : SS_BLOCK_DEFAULT;
+	return (b == 32 || b == 64 || b == 128) ? b : SS_BLOCK_DEFAULT;
+}
+int launch_split_search(const TrainArgs& A, const uint32_t* clsCount, int buf, cudaStream_t s) {
+	const bool separate = getenv("PSM_SS_SEPARATE") != nullptr;
+	if (!separate) {
+		const uint32_t block = (uint32_t)ss_env_block();
+		SsPlan P;
+		uint32_t end = 0;
+		for (int q = 0; q < NCLS; q++) {
+			const int k = NCLS - 1 - q;
+			const uint32_t G = k == 0 ? 8u : k == 1 ? 16u : 32u;
+			P.count[q] = clsCount[k];
+			end += (uint32_t)(((size_t)clsCount[k] * G + block - 1) / block);
+			P.ctaEnd[q] = end;
+		}
+		if (end == 0) return 0;
+		constexpr uint32_t GY = 32768;                                       // grid.y <= 65535
+		const dim3 grid(A.mtry, end < GY ? end : GY, (end + GY - 1) / GY);   // x: candidate; (z, y): work-item CTAs, largest class first
+		if (A.entry32) split_search_merged_kernel<uint32_t><<<grid, block, 0, s>>>(A, P, buf);
+		else split_search_merged_kernel<unsigned long long><<<grid, block, 0, s>>>(A, P, buf);
+		return 1;
+	}
+	int launches = 0;
+	for (int k = NCLS - 1; k >= 0; k--) {
 		const uint32_t nl = clsCount[k];
 		if (nl == 0) continue;
+		launches++;
 		const uint32_t* list = A.clsItems[buf][k];
 		const uint32_t G = k == 0 ? 8u : k == 1 ? 16u : 32u;
 		const dim3 grid((unsigned)(((size_t)nl * G + 127) / 128), A.mtry);   // x: nodes (G lanes each), y: candidate
@@ -1112,6 +1191,7 @@ void launch_split_search(const TrainArgs& A, const uint32_t* clsCount, int buf, 
 		else PSM_SS(unsigned long long);
 #undef PSM_SS
 	}
+	return launches;
 }
 void launch_split_select(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
 	const unsigned grid = (unsigned)(((size_t)nItems * SEL_G + 127) / 128);

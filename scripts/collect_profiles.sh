@@ -24,7 +24,7 @@ ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum 
 	--log-file "$OUT/${TAG}_dram_split_search_all_levels.csv" $S > "$OUT/ncu_dram.log" 2>&1
 
 # full-section captures: a window of launches from the first fold for the per-level kernels, one launch for the per-fold ones
-for K in split_search_kernel partition_lists_kernel predict_compact_kernel feature_sort_radix_kernel build_lists_kernel tree_level_kernel split_select_kernel; do
+for K in split_search_kernel partition_lists_kernel predict_compact_kernel feature_sort_radix_kernel build_lists_multi_kernel tree_level_kernel split_select_kernel; do
 	case $K in
 		split_search_kernel) SKIP=0; CNT=24 ;;
 		partition_lists_kernel|tree_level_kernel|split_select_kernel) SKIP=0; CNT=12 ;;

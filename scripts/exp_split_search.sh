@@ -1,0 +1,32 @@
+#!/bin/bash
+# A/B measurement of the split-search launch forms on one B200 (run through gpurun from the repo root):
+#   gpurun --timeout 900 -- 'bash scripts/exp_split_search.sh'
+# Every line of gpurun_out/exp_ss/summary.txt: variant, ms per CV, split-search ms per CV (own timed region), roofline.frac.
+set -u
+OUT=gpurun_out/exp_ss
+mkdir -p "$OUT"
+B="python bench.py --steps 6 --warmup 4 --no-also --no-cpu-baseline"
+if [ "${1:-}" = "tests" ]; then
+	timeout 600 python -m pytest tests -m gpu -x -q -k "size_classes or curves or trees_bit_exact or tie or lanes" > "$OUT/pytest.log" 2>&1
+	tail -3 "$OUT/pytest.log"
+fi
+run() {   # name, env assignments...
+	local name=$1; shift
+	env "$@" $B ${BARGS:-} > "$OUT/$name.json" 2> "$OUT/$name.err" || { echo "$name FAILED"; tail -5 "$OUT/$name.err"; return; }
+	python - "$name" "$OUT/$name.json" <<'EOF' | tee -a "$OUT/summary.txt"
+import json, sys
+d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+r = d["roofline"]; k = r.get("kernel_ms_per_step", {})
+print("%-14s %7.2f ms/CV  e2e %7.2f  ss %6.2f ms (%d launches)  frac %.3f  curves %.2f  parity %s  auroc %.8f" % (
+    sys.argv[1], d["ms_per_step"], d["e2e"]["ms_per_step"], r["kernel_ms_per_step_in_region"], r["launches"], r["frac"],
+    k.get("curves", -1), d.get("parity", {}).get("max_abs_diff"), d.get("quality", {}).get("auroc", -1)))
+EOF
+}
+: > "$OUT/summary.txt"
+V=$PWD/parsmurf_b200
+run m8_64 PSM_BUILD_DIR=$V/_build_m8
+run m9_64 PSM_BUILD_DIR=$V/_build_m9
+run m10_64 PSM_BUILD_DIR=$V/_build_m10
+run i4m10_64 PSM_BUILD_DIR=$V/_build_i4m10
+run i4m12_64 PSM_BUILD_DIR=$V/_build_i4m12
+for L in 3 5 6 8; do BARGS="--fold-lanes $L" run m8_lanes$L PSM_BUILD_DIR=$V/_build_m8; done

@@ -204,17 +204,31 @@ def test_fold_lanes_give_identical_bits(oracle):
 
 
 def test_size_classes_do_not_change_the_trees(oracle, monkeypatch):
-    """split search / list partition launched per size class (sub-warp groups for short segments) vs one generic launch"""
+    """split search over the size-class lists (sub-warp groups for short segments; one merged launch per level, largest class
+    first, at every CTA size) vs one launch per class vs one generic class"""
     from parsmurf_b200 import host_api as H
     case = make_case("fy_26")
     x = oracle.make_x(case["X"], case["y"])
     args = (x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
     a = H.cv_run(*args, tie_mode=0)
+    assert a["kernel_launches"]["split_search"] == a["stats"]["levels"]        # merged: one launch per level
+    for block in ("32", "128"):
+        monkeypatch.setenv("PSM_SS_BLOCK", block)
+        c = H.cv_run(*args, tie_mode=0)
+        assert np.array_equal(a["class1"].view(np.uint64), c["class1"].view(np.uint64)) and a["stats"] == c["stats"], block
+    monkeypatch.delenv("PSM_SS_BLOCK")
+    monkeypatch.setenv("PSM_SS_SEPARATE", "1")
+    sep = H.cv_run(*args, tie_mode=0)
+    assert np.array_equal(a["class1"].view(np.uint64), sep["class1"].view(np.uint64)) and a["stats"] == sep["stats"]
+    assert sep["kernel_launches"]["split_search"] > sep["stats"]["levels"]
     monkeypatch.setenv("PSM_NO_SIZE_CLASSES", "1")
     b = H.cv_run(*args, tie_mode=0)
     assert np.array_equal(a["class1"].view(np.uint64), b["class1"].view(np.uint64))
     assert a["stats"] == b["stats"]
-    assert a["kernel_launches"]["split_search"] > b["kernel_launches"]["split_search"] == b["stats"]["levels"]
+    assert b["kernel_launches"]["split_search"] == b["stats"]["levels"]
+    monkeypatch.delenv("PSM_SS_SEPARATE")
+    b2 = H.cv_run(*args, tie_mode=0)                                           # one generic class through the merged kernel
+    assert np.array_equal(a["class1"].view(np.uint64), b2["class1"].view(np.uint64)) and a["stats"] == b2["stats"]
 
 
 def test_two_rank_shares_on_one_gpu(oracle):
