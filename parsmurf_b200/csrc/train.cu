@@ -1030,6 +1030,12 @@ __global__ void __launch_bounds__(TF_THREADS, 8) tree_level_kernel(TrainArgs A, 
 #define PSM_PL_CH 4
 #endif
 constexpr int PL_CH_DEFAULT = PSM_PL_CH;
+// r02, measured and not kept (partition ms per BASELINE configs[1] CV, 20.9 as built): requesting the next group's entries before
+// the current group's flag words (two groups of loads in flight per warp) 23.3 with PL_CH 4 (40 registers), 21.5 / 23.4 with
+// PL_CH 3 / 2; CTAs of 64 threads 25.3, 256: 21.7, 512: 23.7, 1024: 31.3 (a CTA's warps take neighbouring segments of one list).
+#ifndef PSM_PL_BLOCK
+#define PSM_PL_BLOCK 128        // threads per CTA (no barrier, no shared memory: any multiple of 32)
+#endif
 
 // the last (< NCH * 32) entries of a segment, fully predicated; NCH = chunk slots compiled in.  PRED = some child of the node is
 // terminal and its entries are not written (keepL / keepR); without it the two flags are compile-time true.
@@ -1089,7 +1095,7 @@ __device__ __forceinline__ void partition_segment(const E* srcp, E* dstp, const 
 }
 
 template <typename E, int PL_CH>
-__global__ void __launch_bounds__(128) partition_lists_kernel(TrainArgs A, uint32_t nItems, int buf) {
+__global__ void __launch_bounds__(PSM_PL_BLOCK) partition_lists_kernel(TrainArgs A, uint32_t nItems, int buf) {
 	const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (item >= nItems) return;
 	const uint4 raw = __ldg(reinterpret_cast<const uint4*>(A.ptask + item));
@@ -1217,9 +1223,9 @@ int launch_tree_level(const TrainArgs& A, int buf, cudaStream_t s) {
 // partition per size class like split search measured 8% slower -- the short segments lose the sector sharing with their
 // neighbours -- so the per-size variants are dispatched inside the kernel instead)
 void launch_partition_lists(const TrainArgs& A, uint32_t nItems, int buf, cudaStream_t s) {
-	const dim3 grid((unsigned)(((size_t)nItems * 32 + 127) / 128), A.m);   // x: nodes (one warp each), y: feature
-	if (A.entry32) partition_lists_kernel<uint32_t, PL_CH_DEFAULT><<<grid, 128, 0, s>>>(A, nItems, buf);
-	else partition_lists_kernel<unsigned long long, PL_CH_DEFAULT><<<grid, 128, 0, s>>>(A, nItems, buf);
+	const dim3 grid((unsigned)(((size_t)nItems * 32 + PSM_PL_BLOCK - 1) / PSM_PL_BLOCK), A.m);   // x: nodes (one warp each), y: feature
+	if (A.entry32) partition_lists_kernel<uint32_t, PL_CH_DEFAULT><<<grid, PSM_PL_BLOCK, 0, s>>>(A, nItems, buf);
+	else partition_lists_kernel<unsigned long long, PL_CH_DEFAULT><<<grid, PSM_PL_BLOCK, 0, s>>>(A, nItems, buf);
 }
 
 }  // namespace psm

@@ -17,16 +17,12 @@ run() {   # name, env assignments...
 import json, sys
 d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
 r = d["roofline"]; k = r.get("kernel_ms_per_step", {})
-print("%-14s %7.2f ms/CV  e2e %7.2f  ss %6.2f ms (%d launches)  frac %.3f  curves %.2f  parity %s  auroc %.8f" % (
+print("%-14s %7.2f ms/CV  e2e %7.2f  ss %6.2f ms (%d launches)  frac %.3f  partition %.2f  predict %.2f  curves %.2f  auroc %.8f" % (
     sys.argv[1], d["ms_per_step"], d["e2e"]["ms_per_step"], r["kernel_ms_per_step_in_region"], r["launches"], r["frac"],
-    k.get("curves", -1), d.get("parity", {}).get("max_abs_diff"), d.get("quality", {}).get("auroc", -1)))
+    k.get("partition_lists", -1), k.get("predict", -1), k.get("curves", -1), d.get("quality", {}).get("auroc", -1)))
 EOF
 }
 : > "$OUT/summary.txt"
 V=$PWD/parsmurf_b200
-run m8_64 PSM_BUILD_DIR=$V/_build_m8
-run m9_64 PSM_BUILD_DIR=$V/_build_m9
-run m10_64 PSM_BUILD_DIR=$V/_build_m10
-run i4m10_64 PSM_BUILD_DIR=$V/_build_i4m10
-run i4m12_64 PSM_BUILD_DIR=$V/_build_i4m12
-for L in 3 5 6 8; do BARGS="--fold-lanes $L" run m8_lanes$L PSM_BUILD_DIR=$V/_build_m8; done
+run base
+for v in b256 b512 b1024; do run $v PSM_BUILD_DIR=$V/_build_$v; done
