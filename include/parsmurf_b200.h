@@ -115,6 +115,10 @@ int psm_batch_assemble(psm_ctx* ctx, const int32_t* draws_host, uint64_t ndraws)
  * draw of partition p0.  psm_glibc_jump advances such a window by n draws on the host in O(log n). */
 int psm_batch_assemble_glibc(psm_ctx* ctx, const uint32_t* window31);
 int psm_glibc_jump(uint32_t* window31, uint64_t n);
+/* The device replay by itself: generate the next `count` rand() outputs of the stream at `window31` on the GPU (count below
+ * 248 * 2^24) and copy outputs [skip, skip + n_out) to the host -- what srand(seed); rand() ... would return on the reference's
+ * platform (glibc stdlib/random_r.c TYPE_3).  Diagnostic entry: the CV path keeps the draws on the device. */
+int psm_glibc_fill_device(psm_ctx* ctx, const uint32_t* window31, uint64_t count, uint64_t skip, int32_t* out_host, uint64_t n_out);
 /* sizes[3] = {trngPos, trngNeg, Ntr}; out = row-major [Ntr][m+1] like Sampler::trngData (may be NULL) */
 int psm_batch_get_training(psm_ctx* ctx, uint32_t p, uint32_t* sizes, double* out_rowmajor);
 

@@ -74,6 +74,7 @@ def lib():
         L.psm_batch_assemble.argtypes = [vp, i32p, u64]
         L.psm_batch_assemble_glibc.argtypes = [vp, u32p]
         L.psm_glibc_jump.argtypes = [u32p, u64]
+        L.psm_glibc_fill_device.argtypes = [vp, u32p, u64, u64, i32p, u64]
         L.psm_batch_capacity.argtypes = [vp, u32, u32, u32, u32, u32, u32, u32p]
         L.psm_batch_get_training.argtypes = [vp, u32, u32p, dp]
         L.psm_batch_train.argtypes = [vp, u32, u32, u32p, u64p, u32p, u32]
@@ -217,6 +218,15 @@ class Context:
         w = np.ascontiguousarray(window31, np.uint32)
         assert w.size == 31
         self._ck(self.L.psm_batch_assemble_glibc(self.h, _p(w, u32p)))
+
+    def glibc_fill_device(self, window31, count, skip=0, n_out=None):
+        """outputs [skip, skip + n_out) of the next `count` rand() draws, generated on the device"""
+        w = np.ascontiguousarray(window31, np.uint32)
+        assert w.size == 31
+        n_out = count - skip if n_out is None else n_out
+        out = np.empty(n_out, np.int32)
+        self._ck(self.L.psm_glibc_fill_device(self.h, _p(w, u32p), count, skip, _p(out, i32p), n_out))
+        return out
 
     def batch_capacity(self, nParts, fp, ratio, nTrees, mtry, p0):
         c = u32()

@@ -647,6 +647,19 @@ int psm_glibc_jump(uint32_t* window31, uint64_t n) {
 	return PSM_OK;
 }
 
+int psm_glibc_fill_device(psm_ctx* ctx, const uint32_t* window31, uint64_t count, uint64_t skip, int32_t* out, uint64_t nOut) {
+	if (!ctx || !window31 || count == 0 || skip + nOut > count || (nOut && !out)) return fail(ctx, PSM_E_ARG, "glibc_fill_device: bad arguments");
+	CU(cudaSetDevice(ctx->device));
+	ENSURE(ctx->dDraws, (size_t)count * 4);
+	ENSURE(ctx->dRandScratch, (61 + 64 * 31) * 4);
+	if (launch_glibc_rand_fill(window31, count, ctx->dRandScratch.as<uint32_t>(), ctx->dDraws.as<int32_t>(), ctx->stream))
+		return fail(ctx, PSM_E_LIMIT, "glibc_fill_device: rand replay launch failed (count above 248 * 2^24?)");
+	CU(cudaGetLastError());
+	if (nOut) CU(cudaMemcpyAsync(out, ctx->dDraws.as<int32_t>() + skip, (size_t)nOut * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return PSM_OK;
+}
+
 int psm_batch_get_training(psm_ctx* ctx, uint32_t p, uint32_t* sizes, double* out) {
 	if (!ctx || !ctx->assembled || p < ctx->p0 || p >= ctx->p1) return fail(ctx, PSM_E_ARG, "batch_get_training: partition not assembled");
 	const PartDesc& d = ctx->hParts[p - ctx->p0];

@@ -8,6 +8,8 @@
 #include "kernels.cuh"
 
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 namespace psm {
@@ -65,20 +67,31 @@ void glibc_window_jump(uint32_t* w31, uint64_t n) {
 	memcpy(w31, nw, sizeof(nw));
 }
 
-__global__ void __launch_bounds__(128) glibc_rand_fill_kernel(const uint32_t* __restrict__ w61, const uint32_t* __restrict__ jump /*[nj][31]*/,
-                                                               int nj, unsigned long long count, int32_t* __restrict__ out) {
+// Jump tables, radix 256: T[d][v] = x^(GR_CHUNK * v * 256^d) mod charpoly, d < GR_LEVELS.  They depend on nothing but GR_CHUNK,
+// so they are built once per device (host, ~1.5 ms) and every thread reaches its chunk with at most GR_LEVELS - 1 polynomial
+// products -- none below 256 chunks, one up to 16 M draws.  (r02 before: x^(GR_CHUNK * 2^j) powers recomputed by the host for every
+// launch and one product per set bit of the chunk index, ~10 per warp at a fold's 800 k shuffle draws: 138 us per launch on the
+// two dozen CTAs such a launch has, 1.4 ms per BASELINE configs[1] CV and on the critical path of every fold's set-up.)
+constexpr int GR_LEVELS = 3;
+constexpr unsigned long long GR_MAX_DRAWS = (unsigned long long)GR_CHUNK << 24;
+
+__global__ void __launch_bounds__(128) glibc_rand_fill_kernel(const uint32_t* __restrict__ w61, const uint32_t* __restrict__ tab /*[GR_LEVELS][256][31]*/,
+                                                               unsigned long long count, int32_t* __restrict__ out) {
 	const unsigned long long chunk = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned long long first = chunk * GR_CHUNK;
 	if (first >= count) return;
 	uint32_t q[GR_DEG], t[GR_DEG], pj[GR_DEG];
-	for (int k = 0; k < GR_DEG; k++) q[k] = 0;
-	q[0] = 1;                                              // x^0
-	for (int j = 0; j < nj; j++) {
-		if ((chunk >> j) & 1ull) {
-			for (int k = 0; k < GR_DEG; k++) pj[k] = jump[j * GR_DEG + k];
-			gr_polymul(q, pj, t);
-			for (int k = 0; k < GR_DEG; k++) q[k] = t[k];
-		}
+	{
+		const uint32_t* t0 = tab + (size_t)(chunk & 255ull) * GR_DEG;
+		for (int k = 0; k < GR_DEG; k++) q[k] = t0[k];
+	}
+	for (int d = 1; d < GR_LEVELS; d++) {                  // (a warp's 32 chunks share the higher digits: uniform branches)
+		const uint32_t v = (uint32_t)(chunk >> (8 * d)) & 255u;
+		if (v == 0) continue;
+		const uint32_t* td = tab + ((size_t)d * 256 + v) * GR_DEG;
+		for (int k = 0; k < GR_DEG; k++) pj[k] = td[k];
+		gr_polymul(q, pj, t);
+		for (int k = 0; k < GR_DEG; k++) q[k] = t[k];
 	}
 	uint32_t w[GR_DEG];                                    // window at the chunk start: r[first-31 .. first-1] relative to the stream
 #pragma unroll
@@ -107,26 +120,47 @@ __global__ void __launch_bounds__(128) glibc_rand_fill_kernel(const uint32_t* __
 	}
 }
 
+// the jump tables of a device: built on first use, shared by every context (fold lane) of the device, never freed
+static const uint32_t* glibc_jump_tables(int device) {
+	static std::mutex mu;
+	static std::map<int, uint32_t*> tabs;
+	std::lock_guard<std::mutex> lk(mu);
+	auto it = tabs.find(device);
+	if (it != tabs.end()) return it->second;
+	std::vector<uint32_t> h((size_t)GR_LEVELS * 256 * GR_DEG, 0u);
+	uint32_t step[GR_DEG], tmp[GR_DEG];
+	uint64_t e = GR_CHUNK;
+	for (int d = 0; d < GR_LEVELS; d++, e *= 256) {
+		gr_xpow(e, step);                                          // x^(GR_CHUNK * 256^d)
+		uint32_t* T = &h[(size_t)d * 256 * GR_DEG];
+		T[0] = 1;                                                  // v = 0: the polynomial 1
+		for (int v = 1; v < 256; v++) {
+			gr_polymul(T + (size_t)(v - 1) * GR_DEG, step, tmp);
+			memcpy(T + (size_t)v * GR_DEG, tmp, sizeof(tmp));
+		}
+	}
+	uint32_t* dev = nullptr;
+	if (cudaMalloc(&dev, h.size() * 4) != cudaSuccess) return nullptr;
+	if (cudaMemcpy(dev, h.data(), h.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(dev); return nullptr; }
+	tabs[device] = dev;
+	return dev;
+}
+
 // host side of the launch: fills `out` (device) with the next `count` rand() outputs of the stream whose chronological
-// window is w31; scratch = device buffer of at least (61 + 64*31) uint32
+// window is w31; scratch = device buffer of at least 61 uint32
 int launch_glibc_rand_fill(const uint32_t* w31, unsigned long long count, uint32_t* scratchDev, int32_t* out, cudaStream_t s) {
 	if (count == 0) return 0;
+	if (count > GR_MAX_DRAWS) return -1;
+	int device = 0;
+	if (cudaGetDevice(&device) != cudaSuccess) return -1;
+	const uint32_t* tab = glibc_jump_tables(device);
+	if (!tab) return -1;
 	const unsigned long long chunks = (count + GR_CHUNK - 1) / GR_CHUNK;
-	int nj = 0;
-	while ((1ull << nj) < chunks) nj++;
-	if (nj == 0) nj = 1;
-	std::vector<uint32_t> h(61 + (size_t)nj * GR_DEG);
-	gr_extend(w31, h.data());
-	uint32_t p[GR_DEG], tmp[GR_DEG];
-	gr_xpow(GR_CHUNK, p);
-	for (int j = 0; j < nj; j++) {
-		memcpy(&h[61 + (size_t)j * GR_DEG], p, sizeof(p));
-		gr_polymul(p, p, tmp);
-		memcpy(p, tmp, sizeof(p));
-	}
-	if (cudaMemcpyAsync(scratchDev, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+	uint32_t h[61];
+	gr_extend(w31, h);
+	if (cudaMemcpyAsync(scratchDev, h, sizeof(h), cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
 	if (cudaStreamSynchronize(s) != cudaSuccess) return -1;    // `h` is a local
-	glibc_rand_fill_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(scratchDev, scratchDev + 61, nj, count, out);
+	glibc_rand_fill_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(scratchDev, tab, count, out);
 	return 0;
 }
 

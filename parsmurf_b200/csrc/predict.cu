@@ -187,6 +187,21 @@ struct __align__(8) Node8 {
 	uint32_t meta;   // internal: left child (bits 0..19) | feature << 20 (top bit clear) ; leaf: 0xFFFFFFFF
 };
 constexpr int LEAF_TAB = 121;
+// The table of leaf fractions lives in global memory (one 16-byte L1-resident load per row and tree).  As a __shared__ array its
+// 1.9 KB of static shared memory were what kept BASELINE configs[1] at four CTAs per SM instead of five (ncu r02:
+// launch__occupancy_limit_shared_mem 4 with 44.9 KB of dynamic shared memory per CTA; the walk is latency-bound -- short
+// scoreboard 3.9 and fixed-latency waits 3.2 cycles per issue at 8 warps per scheduler).
+#ifndef PSM_PREDICT_LTAB_GLOBAL
+#define PSM_PREDICT_LTAB_GLOBAL 1
+#endif
+__device__ double2 g_leaf_tab[LEAF_TAB];
+__global__ void leaf_tab_init_kernel() {
+	const int tid = threadIdx.x;
+	if (tid >= LEAF_TAB) return;
+	const int n = tid / 11, p2 = tid % 11;
+	const bool ok = n >= 1 && p2 <= n;
+	g_leaf_tab[tid] = make_double2(ok ? __ddiv_rn((double)p2, (double)n) : 0.0, ok ? __ddiv_rn((double)(n - p2), (double)n) : 0.0);
+}
 
 // the one-in-10^7 visit where float(value) == float(threshold): decide with the exact fp64 values.  Kept out of line on
 // purpose -- inlined, the compiler if-converts it and its ~12 predicated instructions are issued on EVERY node visit
@@ -221,6 +236,10 @@ __global__ void __launch_bounds__(256) pack_forest_kernel(const Node16* __restri
 	out[i] = o;
 }
 
+#ifndef PSM_CPT
+#define PSM_CPT 256
+#endif
+constexpr int CPT = PSM_CPT;          // rows per CTA of the compact kernel
 #ifndef PSM_NBUF
 #define PSM_NBUF 2
 #endif
@@ -231,29 +250,33 @@ constexpr uint32_t NBUF = PSM_NBUF;   // pipeline depth: the TMA runs NBUF-1 sta
 // fold score buffer right here, in ascending partition order with the arithmetic of accumulate_kernel (sampler.cpp:121-132) --
 // no [partition][row] scratch plane is written and read back (2 x 22 GB per BASELINE configs[2] fold).
 template <uint32_t TPS, bool DIRECT>
-__global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __restrict__ x, uint32_t m, const uint32_t* __restrict__ testIdx,
+__global__ void __launch_bounds__(CPT) predict_compact_kernel(const double* __restrict__ x, uint32_t m, const uint32_t* __restrict__ testIdx,
                                                               uint32_t Nte, const Node16* __restrict__ nodes, const Node8* __restrict__ nodes8,
                                                               uint32_t NC, const TreeState* __restrict__ ts, uint32_t nPartsBatch, uint32_t T,
                                                               uint32_t pch, uint32_t maxNodes, double* __restrict__ scratch, double divider,
                                                               double* __restrict__ class12) {
 	extern __shared__ __align__(128) unsigned char smraw[];
-	float* tile = reinterpret_cast<float*>(smraw);                                     // [m][PT]
-	Node8* tbuf = reinterpret_cast<Node8*>(smraw + (size_t)m * PT * sizeof(float));    // [NBUF][TPS][maxNodes]
+	float* tile = reinterpret_cast<float*>(smraw);                                     // [m][CPT]
+	Node8* tbuf = reinterpret_cast<Node8*>(smraw + (size_t)m * CPT * sizeof(float));    // [NBUF][TPS][maxNodes]
 	uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf + (size_t)NBUF * TPS * maxNodes);   // [NBUF]
+#if !PSM_PREDICT_LTAB_GLOBAL
 	__shared__ double ltab[2][LEAF_TAB];
+#endif
 	const uint32_t ld = m + 1;
-	const uint32_t r0 = blockIdx.x * PT;
+	const uint32_t r0 = blockIdx.x * CPT;
 	const int tid = threadIdx.x;
 	const uint32_t p0 = blockIdx.y * pch;
 	const uint32_t p1 = min(p0 + pch, nPartsBatch);
 	const uint32_t g0 = p0 * T, nT = (p1 - p0) * T;
 	const uint32_t nStages = (nT + TPS - 1) / TPS;
+#if !PSM_PREDICT_LTAB_GLOBAL
 	if (tid < LEAF_TAB) {
 		const int n = tid / 11, p2 = tid % 11;
 		const bool ok = n >= 1 && p2 <= n;
 		ltab[0][tid] = ok ? __ddiv_rn((double)p2, (double)n) : 0.0;
 		ltab[1][tid] = ok ? __ddiv_rn((double)(n - p2), (double)n) : 0.0;
 	}
+#endif
 	if (tid == 0) {
 		for (uint32_t q = 0; q < NBUF; q++) mbar_init(&bars[q], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -289,11 +312,11 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 	}
 	{
 		const int lane = tid & 31, w = tid >> 5;
-		for (int rr = w; rr < PT; rr += PT / 32) {
+		for (int rr = w; rr < CPT; rr += CPT / 32) {
 			uint32_t r = r0 + rr;
 			if (r < Nte) {
 				const double* src = x + (size_t)testIdx[r] * ld;
-				for (uint32_t c = lane; c < m; c += 32) tile[(size_t)c * PT + rr] = __double2float_rn(src[c]);
+				for (uint32_t c = lane; c < m; c += 32) tile[(size_t)c * CPT + rr] = __double2float_rn(src[c]);
 			}
 		}
 	}
@@ -301,7 +324,7 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 	const uint32_t row = r0 + tid;
 	const bool valid = row < Nte;
 	const double Td = (double)T;
-	const uint32_t tileLane = smem_u32(tile) + (uint32_t)tid * 4u;   // shared address of tile[0][tid]; PT*4 = 1024 bytes per feature
+	const uint32_t tileLane = smem_u32(tile) + (uint32_t)tid * 4u;   // shared address of tile[0][tid]; CPT*4 bytes per feature
 	const uint32_t tbuf32 = smem_u32(tbuf);
 	const uint32_t treeBytes = maxNodes * (uint32_t)sizeof(Node8);
 	double s0 = 0.0, s1 = 0.0;
@@ -340,7 +363,7 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 				    "@pl bra PSM_WALK_DONE;\n"
 				    "PSM_WALK:\n\t"
 				    "shr.u32 f, ny, 20;\n\t"
-				    "mad.lo.u32 fa, f, 1024, %3;\n\t"
+				    "mad.lo.u32 fa, f, %5, %3;\n\t"
 				    "ld.shared.f32 v, [fa];\n\t"
 				    "and.b32 c, ny, 0xFFFFF;\n\t"
 				    "mad.lo.u32 a, c, 8, %4;\n\t"
@@ -357,7 +380,7 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 				    "selp.u32 %2, 1, 0, pu;\n\t"
 				    "}"
 				    : "=r"(lx), "=r"(na), "=r"(und)
-				    : "r"(tileLane), "r"(nbase)
+				    : "r"(tileLane), "r"(nbase), "n"(CPT * 4)
 				    : "memory");
 				double f0, f1;
 				if (und | (lx >= (uint32_t)LEAF_TAB)) {                       // rare: exact redo and/or an uncoded leaf
@@ -367,7 +390,14 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 					const uint4 raw = __ldg(reinterpret_cast<const uint4*>(gtree + idx));
 					f0 = __hiloint2double((int)raw.y, (int)raw.x);
 					f1 = __hiloint2double((int)(raw.w & 0x7FFFFFFFu), (int)raw.z);
-				} else { f0 = ltab[0][lx]; f1 = ltab[1][lx]; }
+				} else {
+#if PSM_PREDICT_LTAB_GLOBAL
+					const double2 lf = __ldg(&g_leaf_tab[lx]);
+					f0 = lf.x; f1 = lf.y;
+#else
+					f0 = ltab[0][lx]; f1 = ltab[1][lx];
+#endif
+				}
 				s0 = __dadd_rn(s0, f0);                                      // ForestProbability.cpp:136-141
 				s1 = __dadd_rn(s1, f1);
 				if (++tInPart == T) {
@@ -383,6 +413,9 @@ __global__ void __launch_bounds__(PT) predict_compact_kernel(const double* __res
 				}
 			}
 		}
+		// (r02, measured and not kept: no CTA barrier per tree -- every warp arrives on a "buffer free" mbarrier when it leaves a tree
+		// and the producer waits on it before reusing the buffer, so the warps drift up to a tree apart: predict 13.0 ms per
+		// BASELINE configs[1] CV against 12.4 with the barrier, 14.3 with three buffers)
 		__syncthreads();
 	}
 	if (DIRECT && valid) { class12[row] = c1; class12[(size_t)Nte + row] = c2; }
@@ -419,9 +452,9 @@ int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_
 		// rows 14.6 (1) / 16.6 (2) / 20.3 (4) / 26.2 (8) -- larger stages cost resident CTAs, and occupancy is what this kernel needs.
 		uint32_t tps = 1;
 		if (const char* e = getenv("PSM_PREDICT_TPS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) tps = (uint32_t)v; }
-		const size_t smemC = (size_t)m * PT * sizeof(float) + (size_t)NBUF * tps * mn * sizeof(Node8) + 128;
+		const size_t smemC = (size_t)m * CPT * sizeof(float) + (size_t)NBUF * tps * mn * sizeof(Node8) + 128;
 		if (nodes8 && maxNodes > 0 && m <= 2047 && NC < (1u << 20) && smemC <= 100 * 1024 && !getenv("PSM_PREDICT_WIDE")) {
-			const uint32_t rowTiles = (Nte + PT - 1) / PT;
+			const uint32_t rowTiles = (Nte + CPT - 1) / CPT;
 			uint32_t ctasPerSm = (uint32_t)((227 * 1024) / (smemC + 1024));
 			if (ctasPerSm < 1) ctasPerSm = 1;
 			if (ctasPerSm > 8) ctasPerSm = 8;
@@ -434,14 +467,17 @@ int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_
 			const dim3 grid(rowTiles, chunks);
 			const Node8* n8 = reinterpret_cast<const Node8*>(nodes8);
 			const bool direct = chunks == 1 && class12 != nullptr && !getenv("PSM_PREDICT_SCRATCH");
+#if PSM_PREDICT_LTAB_GLOBAL
+			leaf_tab_init_kernel<<<1, 128, 0, s>>>();     // idempotent (every launch writes the same values), so fold lanes need no lock
+#endif
 #define PSM_LAUNCH_COMPACT(K)                                                                                                              \
 	do {                                                                                                                                   \
 		if (direct) {                                                                                                                      \
 			if (allow_max_dyn_smem(predict_compact_kernel<K, true>) != cudaSuccess) return -1;                                             \
-			predict_compact_kernel<K, true><<<grid, PT, smemC, s>>>(x, m, testIdx, Nte, nodes, n8, NC, ts, nPartsBatch, T, pch, mn, scratch, divider, class12);  \
+			predict_compact_kernel<K, true><<<grid, CPT, smemC, s>>>(x, m, testIdx, Nte, nodes, n8, NC, ts, nPartsBatch, T, pch, mn, scratch, divider, class12);  \
 		} else {                                                                                                                           \
 			if (allow_max_dyn_smem(predict_compact_kernel<K, false>) != cudaSuccess) return -1;                                            \
-			predict_compact_kernel<K, false><<<grid, PT, smemC, s>>>(x, m, testIdx, Nte, nodes, n8, NC, ts, nPartsBatch, T, pch, mn, scratch, divider, class12); \
+			predict_compact_kernel<K, false><<<grid, CPT, smemC, s>>>(x, m, testIdx, Nte, nodes, n8, NC, ts, nPartsBatch, T, pch, mn, scratch, divider, class12); \
 		}                                                                                                                                  \
 	} while (0)
 			if (tps == 8) PSM_LAUNCH_COMPACT(8);

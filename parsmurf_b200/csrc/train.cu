@@ -395,6 +395,9 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 #ifndef PSM_SS_IPL_MULTI
 #define PSM_SS_IPL_MULTI 8
 #endif
+#ifndef PSM_SS_PREFETCH
+#define PSM_SS_PREFETCH 1       // chunk loop: request the next chunk's entries before the current chunk is evaluated
+#endif
 #ifndef SS_BLOCK_DEFAULT
 #define SS_BLOCK_DEFAULT 64     // threads per CTA of the merged launch (PSM_SS_BLOCK=32|64|128 overrides)
 #endif
@@ -577,7 +580,7 @@ __device__ __forceinline__ void split_search_body(const TrainArgs& A, const uint
 	uint32_t b = 0;
 	do {
 		const uint32_t v0 = b + gl * IPL;
-		if (MULTI) ss_load<E, IPL>(base, v0 + G * IPL, lo, hi, nx);   // prefetch the next chunk
+		if (MULTI && PSM_SS_PREFETCH) ss_load<E, IPL>(base, v0 + G * IPL, lo, hi, nx);   // prefetch the next chunk
 		else {
 #pragma unroll
 			for (int j = 0; j < IPL; j++) nx[j] = (E)0;
@@ -601,7 +604,11 @@ __device__ __forceinline__ void split_search_body(const TrainArgs& A, const uint
 		const pk_t excl = absBase + inc - run;
 		// the entry that follows this lane's last one: first entry of the next lane, or of the next chunk for the last lane
 		E enext = __shfl_down_sync(FULL, e[0], 1, G);
-		if (MULTI) { const E c0 = __shfl_sync(FULL, nx[0], 0, G); if (gl == G - 1) enext = c0; }
+		if (MULTI && PSM_SS_PREFETCH) { const E c0 = __shfl_sync(FULL, nx[0], 0, G); if (gl == G - 1) enext = c0; }
+		else if (MULTI) {
+			// no prefetch: the last lane fetches the first entry of the next chunk itself (index b + G*IPL, valid iff < hi)
+			if (gl == G - 1) { const uint32_t vn = b + G * IPL; enext = vn < hi ? __ldg(base + vn) : (E)0; }
+		}
 		else if (gl == G - 1) enext = (E)0;
 		// chunks that touch a segment end check the position range; the others run without (MULTI only: a single chunk always does)
 		const bool edge = !MULTI || (b == 0 && off != 0) || (b + G * IPL >= hi);
@@ -669,8 +676,10 @@ __device__ __forceinline__ void split_search_body(const TrainArgs& A, const uint
 		}
 		if (MULTI) {
 			absBase += __shfl_sync(FULL, inc, G - 1, G);
+			if (PSM_SS_PREFETCH) {
 #pragma unroll
-			for (int j = 0; j < IPL; j++) e[j] = nx[j];
+				for (int j = 0; j < IPL; j++) e[j] = nx[j];
+			} else if (b + G * IPL < hi) ss_load<E, IPL>(base, v0 + G * IPL, lo, hi, e);
 		}
 		b += G * IPL;
 	} while (MULTI && b < hi);

@@ -20,14 +20,14 @@ $S > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none
 	--log-file "$OUT/${TAG}_launches_cfg2_1gpu.csv" $S > "$OUT/ncu_launches.log" 2>&1
 
 # DRAM bytes of every split-search launch of one CV (roofline.traffic)
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:split_search_kernel --csv \
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:split_search --csv \
 	--log-file "$OUT/${TAG}_dram_split_search_all_levels.csv" $S > "$OUT/ncu_dram.log" 2>&1
 
 # full-section captures: a window of launches from the first fold for the per-level kernels, one launch for the per-fold ones
-for K in split_search_kernel partition_lists_kernel predict_compact_kernel feature_sort_radix_kernel build_lists_multi_kernel tree_level_kernel split_select_kernel; do
+# (KERNELS="a b" restricts the list: a capture costs one profiled CV each)
+for K in ${KERNELS:-split_search_merged_kernel partition_lists_kernel predict_compact_kernel feature_sort_radix_kernel build_lists_multi_kernel tree_level_kernel split_select_kernel}; do
 	case $K in
-		split_search_kernel) SKIP=0; CNT=24 ;;
-		partition_lists_kernel|tree_level_kernel|split_select_kernel) SKIP=0; CNT=12 ;;
+		split_search_merged_kernel|partition_lists_kernel|tree_level_kernel|split_select_kernel) SKIP=0; CNT=12 ;;
 		*) SKIP=0; CNT=1 ;;
 	esac
 	ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip $SKIP --launch-count $CNT \

@@ -99,7 +99,7 @@ def main():
         md += ["## Launch list (ncu gpu__time_duration, serialised and cold-cache: compare SHARES with the live event timing)\n",
                "| kernel | launches | ms | share | live ms (bench, events) |", "|---|---|---|---|---|"]
         live = bench["roofline"]["kernel_ms_per_step"] if bench else {}
-        m2 = {"split_search_kernel": "split_search", "partition_lists_kernel": "partition_lists", "feature_sort_split_kernel": "feature_sort", "predict_compact_kernel": "predict",
+        m2 = {"split_search_kernel": "split_search", "split_search_merged_kernel": "split_search", "build_lists_multi_kernel": "build_lists", "partition_lists_kernel": "partition_lists", "feature_sort_split_kernel": "feature_sort", "predict_compact_kernel": "predict",
               "build_lists_kernel": "build_lists", "level_finalize_kernel": "level_finalize", "tree_level_kernel": "level_finalize", "split_select_kernel": "split_select",
               "feature_sort_radix_kernel": "feature_sort", "bootstrap_kernel": "bootstrap", "assemble_kernel": "assemble"}
         for k in sorted(L, key=lambda k_: -L[k_]["ms"]):

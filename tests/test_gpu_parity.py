@@ -123,6 +123,30 @@ def test_device_rand_replay_equals_host_draws(ctx, oracle):
         assert np.array_equal(got.view(np.uint64), want[p].view(np.uint64))
 
 
+def test_device_rand_replay_far_into_the_stream(ctx):
+    """psm_glibc_fill_device == the host generator at every digit of the radix-256 jump tables: the first chunk, chunk
+    indices with a second digit (>= 256 chunks of 248 draws) and with a third one (>= 65536 chunks = 16.25 M draws)"""
+    import parsmurf_b200._capi as capi
+    from parsmurf_b200 import host_api as H
+    w0 = capi.glibc_initial_window(1)
+    head = H.rand_fill(1, 70000)
+    got = ctx.glibc_fill_device(w0, 70000)
+    assert np.array_equal(got, head)                                  # chunks 0..282: digits 0 and 1
+    count = 248 * 65536 * 2 + 1000                                     # third digit 0, 1 and 2
+    for skip in (248 * 65536 - 500, 248 * 65536 * 2 - 300, count - 1000):
+        got = ctx.glibc_fill_device(w0, count, skip, 1000)
+        wj = capi.glibc_jump(w0, skip)                                # host: O(log n) jump, then the plain recurrence
+        r = list(wj.astype(np.uint64))
+        want = []
+        for _ in range(1000):
+            v = (int(r[-3]) + int(r[-31])) & 0xFFFFFFFF
+            r.append(v); want.append(v >> 1)
+        assert np.array_equal(got, np.array(want, np.int32)), skip
+    # a stream entered in the middle (the window of a later position) continues identically
+    w1 = capi.glibc_jump(w0, 12345)
+    assert np.array_equal(ctx.glibc_fill_device(w1, 3000), head[12345:15345])
+
+
 def test_device_folds_equal_the_host_test_train_divider(ctx, oracle):
     """psm_fold_begin_device: the four index arrays of every fold, built from the per-class fold lists on the device, with the
     training negatives shuffled by the device replay of std::random_shuffle on glibc rand() (csrc/shuffle.cu) == the host
