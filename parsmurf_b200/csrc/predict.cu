@@ -182,11 +182,15 @@ __global__ void __launch_bounds__(PT) predict_tma_kernel(const double* __restric
 // n <= 10 samples (min_node_size), so its pair of fractions is one of the 66 values p/n, n <= 10: the leaf stores the code
 // n*11+p and the kernel looks the two doubles up in a shared-memory table built with the same IEEE division; the rare other
 // leaf (a larger node without a valid split) stores code 0xFFFFFFFF and reads its fractions from the 16-byte node array.
+// A leaf is a fixed point of the walk step: its "threshold" is a NaN (every ordered compare is false, so the step neither
+// goes left nor records an equality) whose payload carries the fraction code, and its child field is its own index -- a walk
+// that has arrived can be stepped again without moving, which is what lets two walks share one loop (walk_two).
 struct __align__(8) Node8 {
-	float thr;       // internal: float(threshold); leaf: fraction code (as bits)
-	uint32_t meta;   // internal: left child (bits 0..19) | feature << 20 (top bit clear) ; leaf: 0xFFFFFFFF
+	float thr;       // internal: float(threshold); leaf: LEAF_NAN | fraction code
+	uint32_t meta;   // internal: RIGHT child = left + 1 (bits 0..19) | feature << 20 (top bit clear); leaf: 0x80000000 | own index
 };
 constexpr int LEAF_TAB = 121;
+constexpr uint32_t LEAF_NAN = 0x7FC00000u, LEAF_UNCODED = 0x3FFFFFu;   // quiet NaN; payload = code n*11+p, or "read the 16-byte node"
 // The table of leaf fractions lives in global memory (one 16-byte L1-resident load per row and tree).  As a __shared__ array its
 // 1.9 KB of static shared memory were what kept BASELINE configs[1] at four CTAs per SM instead of five (ncu r02:
 // launch__occupancy_limit_shared_mem 4 with 44.9 KB of dynamic shared memory per CTA; the walk is latency-bound -- short
@@ -220,17 +224,17 @@ __global__ void __launch_bounds__(256) pack_forest_kernel(const Node16* __restri
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= (size_t)nTrees * NC) return;
 	const uint32_t tree = (uint32_t)(i / NC), node = (uint32_t)(i % NC);
-	Node8 o; o.thr = 0.0f; o.meta = 0xFFFFFFFFu;
+	Node8 o; o.thr = __uint_as_float(LEAF_NAN | LEAF_UNCODED); o.meta = 0x80000000u | node;
 	if (node < ts[tree].nNodes) {
 		const Node16 nd = nodes[i];
-		if (!node_is_leaf(nd)) { o.thr = __double2float_rn(nd.a); o.meta = (uint32_t)(nd.b >> 32) | ((uint32_t)(nd.b & 0x7FFu) << 20); }
+		if (!node_is_leaf(nd)) { o.thr = __double2float_rn(nd.a); o.meta = ((uint32_t)(nd.b >> 32) + 1u) | ((uint32_t)(nd.b & 0x7FFu) << 20); }
 		else {
 			const double f0 = nd.a, f1 = __longlong_as_double((long long)(nd.b & 0x7FFFFFFFFFFFFFFFull));
-			uint32_t code = 0xFFFFFFFFu;
-			for (int n = 1; n <= 10 && code == 0xFFFFFFFFu; n++)
+			uint32_t code = LEAF_UNCODED;
+			for (int n = 1; n <= 10 && code == LEAF_UNCODED; n++)
 				for (int p2 = 0; p2 <= n; p2++)
 					if (__ddiv_rn((double)p2, (double)n) == f0 && __ddiv_rn((double)(n - p2), (double)n) == f1) { code = (uint32_t)(n * 11 + p2); break; }
-			o.thr = __uint_as_float(code);
+			o.thr = __uint_as_float(LEAF_NAN | code);
 		}
 	}
 	out[i] = o;
@@ -245,12 +249,114 @@ constexpr int CPT = PSM_CPT;          // rows per CTA of the compact kernel
 #endif
 constexpr uint32_t NBUF = PSM_NBUF;   // pipeline depth: the TMA runs NBUF-1 stages ahead of the traversal (deeper pipelines cost occupancy and measured slower)
 
+// Hand-written traversal, 11 instructions per node visit (nvcc's version of the same loop: 17; the kernel is issue- and
+// latency-bound, ncu r01 / r02).  Node8: .x = float(threshold), .y = right child (bits 0..19) | feature << 20; leaves: .x = NaN
+// with the fraction code, .y = sign bit | own index.  Go left iff value < threshold (Tree.cpp:163: left iff value <= split_value;
+// the float compare only differs from the double one when float(value) == float(threshold), tracked in `und`).
+// (all working registers are PTX-local and the outputs are written once at the end: an output operand may share its register
+// with an input, so it must not be written while an input is still needed)
+__device__ __forceinline__ void walk_one(uint32_t tileLane, uint32_t nbase, uint32_t& lx, uint32_t& na, uint32_t& und) {
+	asm volatile(
+	    "{\n\t"
+	    ".reg .pred pl, pg, pu;\n\t"
+	    ".reg .b32 nx, ny, a, f, fa, c;\n\t"
+	    ".reg .f32 v, t;\n\t"
+	    "setp.ne.u32 pu, 0, 0;\n\t"
+	    "mov.u32 a, %4;\n\t"
+	    "ld.shared.v2.u32 {nx, ny}, [a];\n\t"
+	    "setp.lt.s32 pl, ny, 0;\n\t"
+	    "@pl bra PSM_WALK_DONE;\n"
+	    "PSM_WALK:\n\t"
+	    "shr.u32 f, ny, 20;\n\t"
+	    "mad.lo.u32 fa, f, %5, %3;\n\t"
+	    "ld.shared.f32 v, [fa];\n\t"
+	    "and.b32 c, ny, 0xFFFFF;\n\t"
+	    "mad.lo.u32 a, c, 8, %4;\n\t"
+	    "mov.b32 t, nx;\n\t"
+	    "setp.lt.f32 pg, v, t;\n\t"
+	    "setp.eq.or.f32 pu, v, t, pu;\n\t"
+	    "@pg sub.u32 a, a, 8;\n\t"
+	    "ld.shared.v2.u32 {nx, ny}, [a];\n\t"
+	    "setp.ge.s32 pl, ny, 0;\n\t"
+	    "@pl bra PSM_WALK;\n"
+	    "PSM_WALK_DONE:\n\t"
+	    "mov.u32 %0, nx;\n\t"
+	    "mov.u32 %1, a;\n\t"
+	    "selp.u32 %2, 1, 0, pu;\n\t"
+	    "}"
+	    : "=r"(lx), "=r"(na), "=r"(und)
+	    : "r"(tileLane), "r"(nbase), "n"(CPT * 4)
+	    : "memory");
+}
+// Two trees at once for the same row: the walk is a chain of dependent shared-memory loads (ncu r02: short-scoreboard and
+// fixed-latency stalls are 7 of the 12 stall cycles per issued instruction at 10 warps per scheduler), so a second,
+// independent chain in the same warp doubles the loads in flight at the same instruction count -- the warp already runs
+// to the deepest of its 32 walks, now to the deepest of 64.  A walk that has reached its leaf keeps being stepped: the leaf
+// is a fixed point (Node8), only the two loads are switched off by the walk's predicate (plA / plB), so a finished walk costs
+// no shared-memory wavefronts and nothing has to be selected or restored.
+__device__ __forceinline__ void walk_two(uint32_t tileLane, uint32_t nbaseA, uint32_t nbaseB, uint32_t& lxA, uint32_t& naA, uint32_t& undA,
+                                         uint32_t& lxB, uint32_t& naB, uint32_t& undB) {
+	asm volatile(
+	    "{\n\t"
+	    ".reg .pred plA, pgA, puA, plB, pgB, puB, pany;\n\t"
+	    ".reg .b32 nxA, nyA, aA, fA, faA, cA, nxB, nyB, aB, fB, faB, cB;\n\t"
+	    ".reg .f32 vA, tA, vB, tB;\n\t"
+	    "setp.ne.u32 puA, 0, 0;\n\t"
+	    "setp.ne.u32 puB, 0, 0;\n\t"
+	    "mov.f32 vA, 0f00000000;\n\t"
+	    "mov.f32 vB, 0f00000000;\n\t"
+	    "mov.u32 aA, %7;\n\t"
+	    "mov.u32 aB, %8;\n\t"
+	    "ld.shared.v2.u32 {nxA, nyA}, [aA];\n\t"
+	    "ld.shared.v2.u32 {nxB, nyB}, [aB];\n\t"
+	    "setp.ge.s32 plA, nyA, 0;\n\t"
+	    "setp.ge.s32 plB, nyB, 0;\n\t"
+	    "or.pred pany, plA, plB;\n\t"
+	    "@!pany bra PSM_WALK2_DONE;\n"
+	    "PSM_WALK2:\n\t"
+	    "shr.u32 fA, nyA, 20;\n\t"
+	    "shr.u32 fB, nyB, 20;\n\t"
+	    "mad.lo.u32 faA, fA, %9, %6;\n\t"
+	    "mad.lo.u32 faB, fB, %9, %6;\n\t"
+	    "@plA ld.shared.f32 vA, [faA];\n\t"
+	    "@plB ld.shared.f32 vB, [faB];\n\t"
+	    "and.b32 cA, nyA, 0xFFFFF;\n\t"
+	    "and.b32 cB, nyB, 0xFFFFF;\n\t"
+	    "mad.lo.u32 aA, cA, 8, %7;\n\t"
+	    "mad.lo.u32 aB, cB, 8, %8;\n\t"
+	    "mov.b32 tA, nxA;\n\t"
+	    "mov.b32 tB, nxB;\n\t"
+	    "setp.lt.f32 pgA, vA, tA;\n\t"
+	    "setp.lt.f32 pgB, vB, tB;\n\t"
+	    "setp.eq.or.f32 puA, vA, tA, puA;\n\t"
+	    "setp.eq.or.f32 puB, vB, tB, puB;\n\t"
+	    "@pgA sub.u32 aA, aA, 8;\n\t"
+	    "@pgB sub.u32 aB, aB, 8;\n\t"
+	    "@plA ld.shared.v2.u32 {nxA, nyA}, [aA];\n\t"
+	    "@plB ld.shared.v2.u32 {nxB, nyB}, [aB];\n\t"
+	    "setp.ge.s32 plA, nyA, 0;\n\t"
+	    "setp.ge.s32 plB, nyB, 0;\n\t"
+	    "or.pred pany, plA, plB;\n\t"
+	    "@pany bra PSM_WALK2;\n"
+	    "PSM_WALK2_DONE:\n\t"
+	    "mov.u32 %0, nxA;\n\t"
+	    "mov.u32 %1, aA;\n\t"
+	    "selp.u32 %2, 1, 0, puA;\n\t"
+	    "mov.u32 %3, nxB;\n\t"
+	    "mov.u32 %4, aB;\n\t"
+	    "selp.u32 %5, 1, 0, puB;\n\t"
+	    "}"
+	    : "=r"(lxA), "=r"(naA), "=r"(undA), "=r"(lxB), "=r"(naB), "=r"(undB)
+	    : "r"(tileLane), "r"(nbaseA), "r"(nbaseB), "n"(CPT * 4)
+	    : "memory");
+}
+
 // TPS = trees per pipeline stage (PSM_PREDICT_TPS=1|2|4|8 overrides the default of 1, see launch_predict).
 // DIRECT (one partition chunk: the CTA walks every forest of the batch for its rows): the partition means are added into the
 // fold score buffer right here, in ascending partition order with the arithmetic of accumulate_kernel (sampler.cpp:121-132) --
 // no [partition][row] scratch plane is written and read back (2 x 22 GB per BASELINE configs[2] fold).
 template <uint32_t TPS, bool DIRECT>
-__global__ void __launch_bounds__(CPT) predict_compact_kernel(const double* __restrict__ x, uint32_t m, const uint32_t* __restrict__ testIdx,
+__global__ void __launch_bounds__(CPT, TPS == 2 ? 5 : 6) predict_compact_kernel(const double* __restrict__ x, uint32_t m, const uint32_t* __restrict__ testIdx,
                                                               uint32_t Nte, const Node16* __restrict__ nodes, const Node8* __restrict__ nodes8,
                                                               uint32_t NC, const TreeState* __restrict__ ts, uint32_t nPartsBatch, uint32_t T,
                                                               uint32_t pch, uint32_t maxNodes, double* __restrict__ scratch, double divider,
@@ -342,50 +448,13 @@ __global__ void __launch_bounds__(CPT) predict_compact_kernel(const double* __re
 		if (valid) {
 			const uint32_t nq = min(TPS, nT - st * TPS);
 			uint32_t nbase = tbuf32 + b * TPS * treeBytes;
-#pragma unroll 1
-			for (uint32_t q = 0; q < nq; q++, nbase += treeBytes) {
-				// Hand-written traversal, 11 instructions per node visit (nvcc's version of the same loop: 17; the kernel is
-				// issue-bound, ncu r01).  Node8: .x = float(threshold) | leaf code, .y = left child (bits 0..19) | feature << 20,
-				// sign bit set on leaves.  Go right iff !(value < threshold) (Tree.cpp:163: left iff value <= split_value; the
-				// float compare only differs from the double one when float(value) == float(threshold), tracked in `und`).
-				// (all working registers are PTX-local and the outputs are written once at the end: an output operand may share
-				// its register with an input, so it must not be written while an input is still needed)
-				uint32_t lx, na, und;
-				asm volatile(
-				    "{\n\t"
-				    ".reg .pred pl, pg, pu;\n\t"
-				    ".reg .b32 nx, ny, a, f, fa, c;\n\t"
-				    ".reg .f32 v, t;\n\t"
-				    "setp.ne.u32 pu, 0, 0;\n\t"
-				    "mov.u32 a, %4;\n\t"
-				    "ld.shared.v2.u32 {nx, ny}, [a];\n\t"
-				    "setp.lt.s32 pl, ny, 0;\n\t"
-				    "@pl bra PSM_WALK_DONE;\n"
-				    "PSM_WALK:\n\t"
-				    "shr.u32 f, ny, 20;\n\t"
-				    "mad.lo.u32 fa, f, %5, %3;\n\t"
-				    "ld.shared.f32 v, [fa];\n\t"
-				    "and.b32 c, ny, 0xFFFFF;\n\t"
-				    "mad.lo.u32 a, c, 8, %4;\n\t"
-				    "mov.b32 t, nx;\n\t"
-				    "setp.geu.f32 pg, v, t;\n\t"
-				    "setp.eq.or.f32 pu, v, t, pu;\n\t"
-				    "@pg add.u32 a, a, 8;\n\t"
-				    "ld.shared.v2.u32 {nx, ny}, [a];\n\t"
-				    "setp.ge.s32 pl, ny, 0;\n\t"
-				    "@pl bra PSM_WALK;\n"
-				    "PSM_WALK_DONE:\n\t"
-				    "mov.u32 %0, nx;\n\t"
-				    "mov.u32 %1, a;\n\t"
-				    "selp.u32 %2, 1, 0, pu;\n\t"
-				    "}"
-				    : "=r"(lx), "=r"(na), "=r"(und)
-				    : "r"(tileLane), "r"(nbase), "n"(CPT * 4)
-				    : "memory");
+			// leaf payload of one finished walk -> the partition sums, in tree order (ForestProbability.cpp:136-149)
+			auto finish = [&](uint32_t lx, uint32_t na, uint32_t und, uint32_t nb, uint32_t q) {
 				double f0, f1;
+				lx &= LEAF_UNCODED;                                          // the payload of the leaf's NaN
 				if (und | (lx >= (uint32_t)LEAF_TAB)) {                       // rare: exact redo and/or an uncoded leaf
 					const Node16* gtree = nodes + (size_t)(g0 + st * TPS + q) * NC;
-					uint32_t idx = (na - nbase) >> 3;
+					uint32_t idx = (na - nb) >> 3;
 					if (und) idx = predict_exact_leaf(x + (size_t)testIdx[row] * ld, gtree);   // about one row-tree in 10^6
 					const uint4 raw = __ldg(reinterpret_cast<const uint4*>(gtree + idx));
 					f0 = __hiloint2double((int)raw.y, (int)raw.x);
@@ -410,6 +479,20 @@ __global__ void __launch_bounds__(CPT) predict_compact_kernel(const double* __re
 						outp += (size_t)2 * Nte;
 					}
 					s0 = 0.0; s1 = 0.0; tInPart = 0;
+				}
+			};
+			if (TPS == 2 && nq == 2) {
+				// two trees per stage: the two walks are interleaved in one loop (walk_two), tree order kept in the sums
+				uint32_t lxA, naA, undA, lxB, naB, undB;
+				walk_two(tileLane, nbase, nbase + treeBytes, lxA, naA, undA, lxB, naB, undB);
+				finish(lxA, naA, undA, nbase, 0);
+				finish(lxB, naB, undB, nbase + treeBytes, 1);
+			} else {
+#pragma unroll 1
+				for (uint32_t q = 0; q < nq; q++, nbase += treeBytes) {
+					uint32_t lx, na, und;
+					walk_one(tileLane, nbase, lx, na, und);
+					finish(lx, na, und, nbase, q);
 				}
 			}
 		}
@@ -448,9 +531,15 @@ int launch_predict(const double* x, uint32_t m, const uint32_t* testIdx, uint32_
 	{
 		// compact path: fp32 tile + 8-byte nodes (feature < 2047, child id < 2^20)
 		const uint32_t mn = (maxNodes + 1u) & ~1u;
-		// trees per stage: 1.  Measured on B200 (predict ms per CV): configs[1] 13.3 (1) / 16.6 (2); configs[2] at a tenth of the
-		// rows 14.6 (1) / 16.6 (2) / 20.3 (4) / 26.2 (8) -- larger stages cost resident CTAs, and occupancy is what this kernel needs.
+		// trees per stage: two, walked side by side (walk_two), when four tree buffers still leave the five CTAs per SM its 48
+		// registers allow -- small trees, e.g. BASELINE configs[2]; otherwise one.  Measured on B200 (predict ms per CV, r02): configs[2]
+		// at a tenth of the rows 14.9 (1) / 14.1 (2); configs[1], whose ~9 KB trees drop the kernel from five CTAs per SM to three
+		// with four buffers, 12.3 (1) / 13.5 (2).  (r01, two trees walked one after the other: 13.3 / 16.6 and 14.6 / 16.6.)
 		uint32_t tps = 1;
+		{
+			const size_t smem2 = (size_t)m * CPT * sizeof(float) + (size_t)NBUF * 2 * mn * sizeof(Node8) + 128;
+			if ((227 * 1024) / (smem2 + 1024) >= 5) tps = 2;
+		}
 		if (const char* e = getenv("PSM_PREDICT_TPS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) tps = (uint32_t)v; }
 		const size_t smemC = (size_t)m * CPT * sizeof(float) + (size_t)NBUF * tps * mn * sizeof(Node8) + 128;
 		if (nodes8 && maxNodes > 0 && m <= 2047 && NC < (1u << 20) && smemC <= 100 * 1024 && !getenv("PSM_PREDICT_WIDE")) {

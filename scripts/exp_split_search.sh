@@ -24,4 +24,7 @@ EOF
 }
 : > "$OUT/summary.txt"
 V=$PWD/parsmurf_b200
-run base
+run tps1 PSM_PREDICT_TPS=1
+run tps2 PSM_PREDICT_TPS=2
+BARGS="--workload cfg3s" run tps1_cfg3s PSM_PREDICT_TPS=1
+BARGS="--workload cfg3s" run tps2_cfg3s PSM_PREDICT_TPS=2

@@ -637,9 +637,18 @@ def test_predict_paths_agree_bitwise(oracle, monkeypatch):
     args = (x, case["y"], case["f"], case["nF"], case["nParts"], case["fp"], case["ratio"], case["k"], case["T"], case["mtry"], 7)
     rc, o1, o2 = oracle.o_cv(*args)
     a = H.cv_run(*args, tie_mode=0)
+    assert np.array_equal(a["class1"].view(np.uint64), o1.view(np.uint64)) and np.array_equal(a["class2"].view(np.uint64), o2.view(np.uint64))
+    # one tree per stage (walk_one), two walked side by side (walk_two; with T odd a pair straddles two partitions), and the
+    # sequential multi-tree stages
+    for tps, T in (("1", case["T"]), ("2", case["T"]), ("2", 3), ("4", case["T"])):
+        monkeypatch.setenv("PSM_PREDICT_TPS", tps)
+        args_t = args[:8] + (T,) + args[9:]
+        want1, want2 = (o1, o2) if T == case["T"] else oracle.o_cv(*args_t)[1:]
+        c = H.cv_run(*args_t, tie_mode=0)
+        assert np.array_equal(c["class1"].view(np.uint64), want1.view(np.uint64)) and np.array_equal(c["class2"].view(np.uint64), want2.view(np.uint64)), (tps, T)
+    monkeypatch.delenv("PSM_PREDICT_TPS")
     monkeypatch.setenv("PSM_PREDICT_WIDE", "1")
     b = H.cv_run(*args, tie_mode=0)
-    assert np.array_equal(a["class1"].view(np.uint64), o1.view(np.uint64)) and np.array_equal(a["class2"].view(np.uint64), o2.view(np.uint64))
     assert np.array_equal(b["class1"].view(np.uint64), o1.view(np.uint64)) and np.array_equal(b["class2"].view(np.uint64), o2.view(np.uint64))
 
 
