@@ -395,9 +395,6 @@ __global__ void __launch_bounds__(32) init_trees_kernel(TrainArgs A) {
 #ifndef PSM_SS_IPL_MULTI
 #define PSM_SS_IPL_MULTI 8
 #endif
-#ifndef PSM_SS_PREFETCH
-#define PSM_SS_PREFETCH 1       // chunk loop: request the next chunk's entries before the current chunk is evaluated
-#endif
 #ifndef SS_BLOCK_DEFAULT
 #define SS_BLOCK_DEFAULT 64     // threads per CTA of the merged launch (PSM_SS_BLOCK=32|64|128 overrides)
 #endif
@@ -512,10 +509,11 @@ template <int G> __device__ __forceinline__ uint32_t grp_min(uint32_t v) {
 }
 
 // G = lanes per (node, candidate) work item, MULTI = the segment may span several chunks of G*IPL entries.
-// level_finalize sorts the open nodes of a level into four size classes (kernels.cuh: size_class) and every class is
-// launched over its own compact item list with the instantiation that fits it:
+// tree_level_kernel sorts the open nodes of a level into six size classes (kernels.cuh: size_class); every class has its own
+// compact item list and the instantiation that fits it, and ONE launch covers them all, longest class first
+// (split_search_merged_kernel below):
 //   class 0 (<= 32 grid entries): G = 8, four work items per warp      class 1 (<= 64): G = 16, two per warp
-//   class 2 (<= 128): G = 32, one chunk, straight-line code             class 3: G = 32, chunk loop with prefetch
+//   class 2 (<= 128): G = 32, one chunk, straight-line code             classes 3-5: G = 32, chunk loop with prefetch
 // At the mid and deep levels most nodes hold a few dozen rows and the kernel is instruction-issue bound (ncu r01: 557 warp
 // instructions per (node, candidate) for an 89-entry segment, 65% issue-active), so the per-warp fixed cost -- work-item
 // set-up, the scan, the exact block, the arg-max -- is what the small classes share between two or four items.
@@ -580,7 +578,7 @@ __device__ __forceinline__ void split_search_body(const TrainArgs& A, const uint
 	uint32_t b = 0;
 	do {
 		const uint32_t v0 = b + gl * IPL;
-		if (MULTI && PSM_SS_PREFETCH) ss_load<E, IPL>(base, v0 + G * IPL, lo, hi, nx);   // prefetch the next chunk
+		if (MULTI) ss_load<E, IPL>(base, v0 + G * IPL, lo, hi, nx);   // prefetch the next chunk
 		else {
 #pragma unroll
 			for (int j = 0; j < IPL; j++) nx[j] = (E)0;
@@ -604,11 +602,7 @@ __device__ __forceinline__ void split_search_body(const TrainArgs& A, const uint
 		const pk_t excl = absBase + inc - run;
 		// the entry that follows this lane's last one: first entry of the next lane, or of the next chunk for the last lane
 		E enext = __shfl_down_sync(FULL, e[0], 1, G);
-		if (MULTI && PSM_SS_PREFETCH) { const E c0 = __shfl_sync(FULL, nx[0], 0, G); if (gl == G - 1) enext = c0; }
-		else if (MULTI) {
-			// no prefetch: the last lane fetches the first entry of the next chunk itself (index b + G*IPL, valid iff < hi)
-			if (gl == G - 1) { const uint32_t vn = b + G * IPL; enext = vn < hi ? __ldg(base + vn) : (E)0; }
-		}
+		if (MULTI) { const E c0 = __shfl_sync(FULL, nx[0], 0, G); if (gl == G - 1) enext = c0; }
 		else if (gl == G - 1) enext = (E)0;
 		// chunks that touch a segment end check the position range; the others run without (MULTI only: a single chunk always does)
 		const bool edge = !MULTI || (b == 0 && off != 0) || (b + G * IPL >= hi);
@@ -676,10 +670,8 @@ __device__ __forceinline__ void split_search_body(const TrainArgs& A, const uint
 		}
 		if (MULTI) {
 			absBase += __shfl_sync(FULL, inc, G - 1, G);
-			if (PSM_SS_PREFETCH) {
 #pragma unroll
-				for (int j = 0; j < IPL; j++) e[j] = nx[j];
-			} else if (b + G * IPL < hi) ss_load<E, IPL>(base, v0 + G * IPL, lo, hi, e);
+			for (int j = 0; j < IPL; j++) e[j] = nx[j];
 		}
 		b += G * IPL;
 	} while (MULTI && b < hi);
@@ -727,7 +719,11 @@ struct SsPlan {
 };
 // Registers: the chunk loop wants 72 (SS_MINB_MULTI), but with every class in one launch the resident warps are what hides the
 // latency of the short segments: measured on B200 at BASELINE configs[1] (split search ms per CV, 64-thread CTAs):
-// 72 registers 8.97, 64: 8.33, 56: 7.96, 48 (a few dozen bytes of spills outside the chunk loop): 7.87; one launch per class: 11.95.
+// 72 registers 8.97, 64: 8.33, 56: 7.96, 48 (15 spill stores + 15 reloads per chunk): 7.87, 40: 7.76; one launch per class (six
+// classes): 11.95; CTAs of 32 / 128 threads at 72 registers: 9.23 / 9.16; class cuts at 254 / 1022 entries instead of 510 / 2046:
+// the same; 128-entry chunks at 48 / 40 registers: 8.27 / 7.92; no prefetch of the next chunk at 48 / 40 registers: 7.91 / 7.79.
+// Below ~56 registers everything lands within 2%: ncu (profiles/r02_summary.md) shows the merged kernel at 62-71% issue-active
+// with 27-35 resident warps per SM -- what is left is the instruction count (~290 warp instructions per 256-entry chunk).
 #ifndef SS_MINB_MERGED32
 #define SS_MINB_MERGED32 10     // 4-byte entries: 48 registers
 #endif

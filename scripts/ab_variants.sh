@@ -1,7 +1,9 @@
 #!/bin/bash
-# A/B measurement of the split-search launch forms on one B200 (run through gpurun from the repo root):
-#   gpurun --timeout 900 -- 'bash scripts/exp_split_search.sh'
-# Every line of gpurun_out/exp_ss/summary.txt: variant, ms per CV, split-search ms per CV (own timed region), roofline.frac.
+# A/B measurement of kernel variants on one B200 (run through gpurun from the repo root; the r02 kernel comments quote its output):
+#   scripts/build_variant.sh m9 "-DSS_MINB_MERGED32=9"; gpurun --timeout 900 -- 'AB_VARIANTS="m9" bash scripts/ab_variants.sh [tests]'
+# Every line of gpurun_out/exp_ss/summary.txt: variant, ms per CV, e2e, split-search ms per CV (own timed region), roofline.frac,
+# per-kernel ms of the list partition, prediction, curves and fold set-up.  Environment switches (PSM_SS_BLOCK, PSM_SS_SEPARATE,
+# PSM_PREDICT_TPS, PSM_CURVES_TWO_SORTS, ...) can be measured the same way: run NAME VAR=value.
 set -u
 OUT=gpurun_out/exp_ss
 mkdir -p "$OUT"
@@ -24,7 +26,6 @@ EOF
 }
 : > "$OUT/summary.txt"
 V=$PWD/parsmurf_b200
-run tps1 PSM_PREDICT_TPS=1
-run tps2 PSM_PREDICT_TPS=2
-BARGS="--workload cfg3s" run tps1_cfg3s PSM_PREDICT_TPS=1
-BARGS="--workload cfg3s" run tps2_cfg3s PSM_PREDICT_TPS=2
+run base
+# variants: scripts/build_variant.sh NAME "-DFOO=1" first, then list the names (AB_VARIANTS="a b c")
+for v in ${AB_VARIANTS:-}; do run $v PSM_BUILD_DIR=$V/_build_$v; done
