@@ -320,7 +320,7 @@ def measure_cv(rig, w, x_pinned, x_dev, y, f, steps, warmup, roof_steps, with_br
     peak, peak_src = peaks()
     ss_ms, ss_launches = km["split_search"], max(kl_roof, 1)
     achieved = split_bytes / (ss_ms / 1000.0) / 1e9 if ss_ms > 0 else 0.0
-    roofline = {"kernel": "split_search_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"kernel": "split_search_merged_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": split_bytes / ss_launches,
                 "avg_launch_ms": ss_ms / ss_launches, "launches": kl_roof, "kernel_ms_per_step_in_region": ss_ms / roof_steps,
                 "timed_region": "%d steps with the folds one after the other (fold lanes = 1), %.2f ms per step; events around every split-search launch" % (roof_steps, ms_roof / roof_steps)}
