@@ -690,7 +690,7 @@ void hyperSMURF::smurfIt() {                                                // s
 	if (wmode == MODE_TRAIN && commonParams->forestDirname.empty()) throw Error(PSM_E_ARG, "mode \"train\" needs data.forestDir");
 	uint32_t startingFold = 0, endingFold = nFolds;
 	if (!inInternalCV && commonParams->minFold != (uint32_t)-1) startingFold = commonParams->minFold;
-	if (!inInternalCV && commonParams->maxFold != (uint32_t)-1) endingFold = commonParams->maxFold;
+	if (!inInternalCV && commonParams->maxFold != (uint32_t)-1) endingFold = std::min(commonParams->maxFold, nFolds);   // clamped like initStandard (an "endingFold" beyond nFolds would index past the fold lists)
 	if (woptimiz != OPT_NO) { tempcl1.assign(nn, 0.0); tempcl2.assign(nn, 0.0); }
 	if (!inInternalCV) { foldAuroc.assign(nFolds, 0.0); foldAuprc.assign(nFolds, 0.0); }
 	// scores live on the device for the whole CV (class1Prob/class2Prob of src/parSMURF.cpp:90-93); they are added into the
